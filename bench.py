@@ -1,0 +1,396 @@
+#!/usr/bin/env python
+"""bench.py — particle-steps/s of physim's `astro ! verlet` step on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W                  (N > 1: launched under torchrun)
+    python bench.py --impl reference --gpus N --steps K --warmup W (CPU oracle = the reference arm)
+
+Workload (config.workload = "c3"): BASELINE.json configs[2] — cube n=1,000,000 seed=1 spin=500 + 4
+stars (m=1e5) ! astro theta=1.3 (e default 1.0) ! verlet, dt = 1e-6 (pipeline default), synthetic
+bodies from physim_b200.generators (the reference's distributions, our seeds).
+
+  value      device-resident steps (state in HBM), CUDA events on the launching stream, max over ranks
+  e2e        the same step through the C ABI with HOST Entity buffers (pb200_verlet_step_fused):
+             pack -> H2D -> tree/force/verlet kernels -> D2H -> unpack, wall clock, every step
+  roofline   the kernel with the largest share of the device step, timed live with CUDA event
+             pairs around each of its launches; algorithmic bytes from DESIGN.md's table
+  cpu_baseline  the CPU oracle (fp64 restatement of the reference, 1 thread like the reference's
+             simulation thread) on a bounded number of steps of the same workload
+  direct_sum tiled all-pairs kernel on 2^24 bodies (BASELINE configs[3]) sampled over a target
+             slice: interactions/s and fraction of the FP32 peak (19 flop per interaction)
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (generator args, element, theta, e, dt)
+    "c3": dict(n=1_000_000, element="astro", theta=1.3, e=1.0, dt=1e-6,
+               desc="cube n=1000000 seed=1 spin=500 + 4 stars ! astro theta=1.3 ! verlet"),
+    "c1": dict(n=100_000, element="astro2", theta=1.5, e=0.5, dt=1e-5,
+               desc="cube n=100000 seed=1 spin=1000 + 2 stars ! astro2 theta=1.5 e=0.5 ! verlet"),
+    "c3o": dict(n=1_000_000, element="astro2", theta=1.5, e=0.5, dt=1e-5,
+                desc="cube n=1000000 seed=1 spin=500 + 4 stars ! astro2 theta=1.5 e=0.5 ! verlet"),
+}
+
+# Algorithmic HBM bytes per body per launch for each kernel (DESIGN.md "kernels" table).
+ALG_BYTES_PER_BODY = {
+    "extent_kernel": 32, "encode_kernel": 32 + 12, "sort_tile_hist": 8, "sort_scatter": 12 + 12,
+    "gather_kernel": 4 + 32 + 32, "unit_kernel": 8 + 32 + 2 + 4, "scan_tile_sums": 4, "scan_apply": 8,
+    "fill_kernel": 8 + 32 + 4 + 2 + 4 + 1.5 * (1 + 5 * 4 + 32) + 32, "com_kernel": 1.5 * (32 + 32 + 12),
+    "walk_kernel": 32 + 4 + 1 + 16, "verlet_kernel": 32 + 32 + 16 + 32 + 32 + 32,
+    "to_float4_kernel": 32 + 16,
+}
+FLOP_PER_INTERACTION = 19
+
+
+def make_state(w):
+    from physim_b200 import generators as gen
+    if w["n"] >= 1_000_000:
+        return gen.headline_pipeline(w["n"], seed=1, spin=500.0)
+    return gen.readme_pipeline(w["n"], seed=1, spin=1000.0)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured", d
+        except Exception:
+            pass
+    return 6650.0, "fallback", {}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for k, nm in enumerate(names):
+                    if r[5 + k].lower().startswith("active"):
+                        reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_info():
+    model = "unknown"
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                model = line.split(":", 1)[1].strip()
+                break
+    except Exception:
+        pass
+    return model, os.cpu_count()
+
+
+def run_reference(args, w):
+    """The reference arm: the CPU oracle (fp64 restatement of the Rust reference; rustc is not
+    available so the reference itself cannot be built) on the host cores.  One thread: the
+    reference's whole step runs on its single simulation thread (pipeline.rs:134)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import binding as ob
+    ob.build()
+    state = make_state(w)
+    n = len(state)
+    cur = state
+    for _ in range(args.warmup):
+        cur, _ = ob.run_pipeline(w["element"], cur, w["theta"], w["e"], w["dt"], 1)
+    t0 = time.perf_counter()
+    cur, secs = ob.run_pipeline(w["element"], cur, w["theta"], w["e"], w["dt"], args.steps)
+    dt = time.perf_counter() - t0
+    value = n * args.steps / dt
+    model, cores = cpu_info()
+    line = {
+        "impl": "reference", "metric": "particle-steps/s", "value": value, "unit": "particle-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "description": w["desc"], "n_bodies": n,
+                   "element": w["element"], "theta": w["theta"], "e": w["e"], "dt": w["dt"]},
+        "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": 1, "kind": "port",
+                         "sample": f"{args.steps} full steps of the {n}-body workload after {args.warmup} warm-up",
+                         "phases_s_per_step": {"build": secs[0] / args.steps, "walk_force": secs[1] / args.steps,
+                                               "integrate_copies": secs[2] / args.steps},
+                         "cpu": model, "host_cores": cores},
+        "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def cuda_tensor_view(ptr, nbytes):
+    """torch view (float64) of raw device memory, for torch.distributed collectives."""
+    import torch
+
+    class Raw:
+        __cuda_array_interface__ = {"shape": (nbytes // 8,), "typestr": "<f8", "data": (ptr, False),
+                                    "version": 2}
+    return torch.as_tensor(Raw(), device="cuda")
+
+
+def run_ours(args, w):
+    import torch
+    from physim_b200 import api
+    import physim_b200._build as b
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if rank == 0:
+        b.build()
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.barrier()
+    if api.device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device: physim_b200 has no CPU fallback")
+    api.lib().pb200_set_device(local_rank)
+    torch.cuda.set_device(local_rank)
+
+    state = make_state(w)
+    n = len(state)
+    hbm_peak, peak_kind, peaks = measured_peaks()
+
+    # ---------------- device-resident steps (value) ----------------
+    sim = api.Sim(w["element"], theta=w["theta"], e=w["e"], dt=w["dt"], rank=rank, world=world)
+    stream = torch.cuda.Stream(device=local_rank)
+    sim.set_stream(stream.cuda_stream)
+    sim.upload(state)
+    gathered = None
+    if world > 1:
+        ptr, total, off, sl = sim.gather_buffer()
+        gathered = cuda_tensor_view(ptr, total)
+        mine = gathered[off // 8:(off + sl) // 8]
+
+    def steps(k):
+        if world == 1:
+            sim.run(k)  # k steps enqueued back to back; one host sync at the end
+        else:
+            for _ in range(k):
+                sim.step_local()
+                with torch.cuda.stream(stream):
+                    dist.all_gather_into_tensor(gathered, mine)
+
+    steps(max(args.warmup, 3))
+    launches0 = sim.stats()["kernel_launches"]
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+        torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    steps(args.steps)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    if dist:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    st = sim.stats()
+    launches = st["kernel_launches"] - launches0 - 1  # the stats call itself counts interactions
+    value = n * args.steps / (ms * 1e-3)
+
+    # ---------------- per-kernel device times (roofline) ----------------
+    sim.profile(True)
+    prof_steps = 5
+    steps(prof_steps)
+    torch.cuda.synchronize()
+    report = sim.profile_report()
+    sim.profile(False)
+    tot_ms = sum(k["ms"] for k in report) or 1.0
+    top = max(report, key=lambda k: k["ms"])
+    per_launch_ms = top["ms"] / top["launches"]
+    alg_bytes = ALG_BYTES_PER_BODY.get(top["kernel"], 0) * n
+    achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9 if alg_bytes else None
+    roofline = {"kernel": top["kernel"], "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
+                "unit": "GB/s", "frac": (achieved / hbm_peak) if achieved else None, "traffic": None,
+                "peak_source": peak_kind, "avg_launch_ms": per_launch_ms,
+                "share_of_step": top["ms"] / tot_ms,
+                "alg_bytes_per_launch": alg_bytes,
+                "kernels": [{"kernel": k["kernel"], "launches_per_step": k["launches"] / prof_steps,
+                             "ms_per_step": k["ms"] / prof_steps,
+                             "gbs": (ALG_BYTES_PER_BODY.get(k["kernel"], 0) * n / (k["ms"] / k["launches"] * 1e-3) / 1e9)
+                             if k["ms"] > 0 else None}
+                            for k in sorted(report, key=lambda k: -k["ms"])]}
+
+    line = {
+        "metric": "particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": args.workload, "description": w["desc"], "n_bodies": n,
+                   "element": w["element"], "theta": w["theta"], "e": w["e"], "dt": w["dt"],
+                   "n_cells": st["n_cells"], "interactions_per_step": st["interactions"],
+                   "parallelism": "replicated tree build, targets + verlet sharded by body index, "
+                                  "NCCL all-gather of fp64 {x,y,z,m}" if world > 1 else "single GPU",
+                   "l2": "no flush: per-step working set (~0.4 GB) exceeds the 126 MB L2; steps run "
+                         "back to back as in the simulation loop",
+                   "precision": "keys/tree/acceptance/integrator fp64, force law fp32"},
+        "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks,
+    }
+
+    if rank == 0 and world == 1 and not args.skip_extras:
+        line["e2e"] = measure_e2e(api, state, w, args)
+        line["direct_sum"] = measure_direct(api, args, hbm_peak)
+        line["cpu_baseline"] = measure_cpu(state, w)
+    elif rank == 0:
+        line["e2e"] = {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0,
+                       "d2h_bytes_per_step": 0,
+                       "note": "multi-rank run: state stays in HBM; the host-boundary number is the N=1 line's"}
+    if rank == 0:
+        print(json.dumps(line))
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def measure_e2e(api, state, w, args):
+    """The call a physim user's pipeline makes, with host buffers: fused verlet step via the C ABI."""
+    n = len(state)
+    el = api.TransformElement(w["element"], theta=w["theta"], e=w["e"])
+    v = api.Verlet()
+    cur = state
+    for _ in range(max(args.warmup, 3)):
+        cur = v.integrate_fused(cur, el, w["dt"])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cur = v.integrate_fused(cur, el, w["dt"])
+    dt = time.perf_counter() - t0
+    vs = v.stats()
+    # transform-only boundary (today's drop-in: astro*_transform through `*_get_api`)
+    acc = el.transform(cur)
+    t1 = time.perf_counter()
+    for _ in range(5):
+        acc = el.transform(cur, acc)
+    dt_tr = (time.perf_counter() - t1) / 5
+    return {"value": n * args.steps / dt, "unit": "particle-steps/s", "ms_per_step": dt / args.steps * 1e3,
+            "h2d_bytes_per_step": n * 33, "d2h_bytes_per_step": n * 64,
+            "api": "pb200_verlet_step_fused(host Entity[n] -> host Entity[n])",
+            "device_ms": {"h2d": vs["ms_h2d"], "force": vs["ms_force"], "integrate": vs["ms_integrate"],
+                          "d2h": vs["ms_d2h"]},
+            "transform_only": {"api": f"{w['element']}_get_api()->transform", "ms_per_call": dt_tr * 1e3,
+                               "h2d_bytes": n * 33, "d2h_bytes": n * 16}}
+
+
+def measure_direct(api, args, hbm_peak):
+    """BASELINE configs[3]: 2^24 bodies, astro2 theta=0 (== all pairs) e=0.5; a 1/64 target slice."""
+    from physim_b200 import generators as gen
+    n = 1 << 24
+    state = gen.cube(n, seed=1)
+    parts = 64
+    sim = api.Sim("astro2", theta=0.0, e=0.5, dt=1e-6, rank=0, world=parts)
+    sim.upload(state)
+    sim.run_timed(1)
+    steps = 3
+    ms = sim.run_timed(steps)
+    n_t = n // parts
+    inter = n_t * n * steps
+    rate = inter / (ms * 1e-3)
+    fp32_probe = api.probe_fp32_tflops()
+    import torch
+    props = torch.cuda.get_device_properties(0)
+    sms = props.multi_processor_count
+    nominal = sms * 128 * 2 * 1.965e9 / 1e12
+    tf = rate * FLOP_PER_INTERACTION / 1e12
+    return {"workload": "cube n=16777216 ! astro2 theta=0 e=0.5 (all pairs)",
+            "sample": f"targets [0, {n_t}) x all {n} sources, {steps} evaluations",
+            "interactions_per_s": rate, "ms_per_evaluation": ms / steps,
+            "full_step_s_extrapolated": n * n / rate,
+            "roofline": {"bound": "fp32", "achieved": tf, "unit": "TFLOP/s", "flop_per_interaction": 19,
+                         "peak": nominal, "peak_source": f"{sms} SMs x 128 lanes x 2 x 1.965 GHz (max boost)",
+                         "frac": tf / nominal, "ffma_probe_tflops": fp32_probe,
+                         "frac_of_probe": tf / fp32_probe if fp32_probe > 0 else None}}
+
+
+def measure_cpu(state, w):
+    from oracle import binding as ob
+    ob.build()
+    n = len(state)
+    steps = max(2, min(10, int(12e6 // max(n, 1))))  # about 10-20 s of CPU work
+    t0 = time.perf_counter()
+    _, secs = ob.run_pipeline(w["element"], state, w["theta"], w["e"], w["dt"], steps)
+    dt = time.perf_counter() - t0
+    model, cores = cpu_info()
+    return {"value": n * steps / dt, "unit": "particle-steps/s", "cores": 1, "kind": "port",
+            "sample": f"{steps} full steps of the same {n}-body workload",
+            "phases_s_per_step": {"build": secs[0] / steps, "walk_force": secs[1] / steps,
+                                  "integrate_copies": secs[2] / steps},
+            "cpu": model, "host_cores": cores,
+            "note": "1 thread: the reference runs the whole step on one simulation thread (pipeline.rs:134)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--skip-extras", action="store_true", help="skip e2e / direct-sum / cpu legs")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, w)
+    else:
+        run_ours(args, w)
+
+
+if __name__ == "__main__":
+    main()

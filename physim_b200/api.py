@@ -1,0 +1,388 @@
+"""Host-side mirror of physim's element interface over libphysim_b200.so (ctypes; no torch).
+
+`TransformElement` drives the library exactly as physim's `TransformElementHandler` does
+(physim-core/src/plugin/transform.rs:58-104): dlopen, `{name}_get_api`, `init(json, len)` with a
+non-NUL-terminated JSON object, `transform(obj, state, n, acc, n)`, `destroy(obj)`.
+`Verlet` mirrors `IntegratorElement::integrate` (physim-core/src/plugin/integrator.rs:5-13) over the
+`pb200_verlet_*` entry points the Rust shim forwards to.  `Sim` is the device-resident loop.
+
+The CUDA library is the only implementation: importing this module builds nothing and computes
+nothing; calling into it without a GPU raises (or aborts inside the plugin ABI, as physim's own
+trampolines do).
+"""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+
+from .entity import ACCELERATION, ENTITY
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libphysim_b200.so")
+
+KINDS = {"astro": 0, "astro2": 1, "simple_astro": 2}
+
+ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_char_p)  # RustStringAllocFn: char* (*)(const char*)
+ACC_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
+
+
+class CMessage(C.Structure):
+    _fields_ = [("priority", C.c_int), ("topic", C.c_char_p), ("message", C.c_char_p),
+                ("sender_id", C.c_size_t), ("origin", C.c_int)]
+
+
+class TransformElementAPI(C.Structure):
+    """c_plugin/physim.h:58-65 — field order is ABI."""
+    _fields_ = [
+        ("init", C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)),
+        ("transform", C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t)),
+        ("destroy", C.CFUNCTYPE(None, C.c_void_p)),
+        ("get_property_descriptions", C.CFUNCTYPE(C.c_void_p, C.c_void_p, ALLOC_FN)),
+        ("recv_message", C.CFUNCTYPE(None, C.c_void_p, C.POINTER(CMessage))),
+        ("post_configuration_messages", C.CFUNCTYPE(None, C.c_void_p)),
+    ]
+
+
+class ElementMetaFFI(C.Structure):
+    """c_plugin/physim.h:70-79."""
+    _fields_ = [("kind", C.c_int)] + [(k, C.c_void_p) for k in
+                                      ("name", "plugin", "version", "license", "author", "blurb", "repo")]
+
+
+class Pb200Stats(C.Structure):
+    _fields_ = [("n_bodies", C.c_uint64), ("n_cells", C.c_uint64), ("interactions", C.c_uint64),
+                ("kernel_launches", C.c_uint64), ("extent", C.c_double), ("ms_h2d", C.c_float),
+                ("ms_build", C.c_float), ("ms_force", C.c_float), ("ms_integrate", C.c_float),
+                ("ms_d2h", C.c_float)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class Pb200Error(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Loads libphysim_b200.so (built by physim_b200._build / __graft_entry__.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise Pb200Error(f"{LIB_PATH} is missing: run `python -m physim_b200._build` "
+                         "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    vp, sz, dbl, i32 = C.c_void_p, C.c_size_t, C.c_double, C.c_int
+    L.get_plugin_abi_info.restype = C.c_char_p
+    L.register_plugin.restype = C.c_char_p
+    L.set_callback_target.argtypes = [vp]
+    for el in KINDS:
+        getattr(L, f"{el}_get_api").restype = C.POINTER(TransformElementAPI)
+        getattr(L, f"{el}_register").restype = ElementMetaFFI
+        getattr(L, f"{el}_register").argtypes = [ALLOC_FN]
+    L.pb200_device_count.restype = i32
+    L.pb200_set_device.argtypes = [i32]
+    L.pb200_last_error.restype = C.c_char_p
+    L.pb200_transform_create.restype = vp
+    L.pb200_transform_create.argtypes = [i32, dbl, dbl]
+    L.pb200_transform_create_json.restype = vp
+    L.pb200_transform_create_json.argtypes = [i32, vp, sz]
+    L.pb200_transform_destroy.argtypes = [vp]
+    L.pb200_transform_apply.argtypes = [vp, vp, sz, vp, sz]
+    L.pb200_transform_stats.argtypes = [vp, C.POINTER(Pb200Stats)]
+    L.pb200_transform_theta.restype = dbl
+    L.pb200_transform_theta.argtypes = [vp]
+    L.pb200_transform_easing.restype = dbl
+    L.pb200_transform_easing.argtypes = [vp]
+    L.pb200_transform_debug_tree.argtypes = [vp] * 12
+    L.pb200_verlet_create.restype = vp
+    L.pb200_verlet_destroy.argtypes = [vp]
+    L.pb200_verlet_step.argtypes = [vp, vp, vp, sz, ACC_FN, vp, dbl]
+    L.pb200_verlet_step_fused.argtypes = [vp, vp, vp, vp, sz, dbl]
+    L.pb200_verlet_stats.argtypes = [vp, C.POINTER(Pb200Stats)]
+    L.pb200_sim_create.restype = vp
+    L.pb200_sim_create.argtypes = [i32, dbl, dbl, dbl, i32, i32]
+    L.pb200_sim_destroy.argtypes = [vp]
+    L.pb200_sim_upload.argtypes = [vp, vp, sz]
+    L.pb200_sim_run.argtypes = [vp, sz]
+    L.pb200_sim_step_local.argtypes = [vp]
+    L.pb200_sim_run_timed.argtypes = [vp, sz, C.POINTER(C.c_float)]
+    L.pb200_sim_profile.argtypes = [vp, i32]
+    L.pb200_sim_profile_report.argtypes = [vp, C.c_char_p, sz]
+    L.pb200_sim_gather_buffer.argtypes = [vp, C.POINTER(vp), C.POINTER(sz), C.POINTER(sz), C.POINTER(sz)]
+    L.pb200_sim_download.argtypes = [vp, vp, sz]
+    L.pb200_sim_last_accelerations.argtypes = [vp, vp, sz]
+    L.pb200_sim_stats.argtypes = [vp, C.POINTER(Pb200Stats)]
+    L.pb200_sim_set_stream.argtypes = [vp, vp]
+    L.pb200_sim_stream.restype = vp
+    L.pb200_sim_stream.argtypes = [vp]
+    L.pb200_probe_fp32_tflops.restype = dbl
+    _lib = L
+    return L
+
+
+def last_error():
+    return lib().pb200_last_error().decode(errors="replace")
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _state(state):
+    state = np.ascontiguousarray(state)
+    if state.dtype.itemsize != ENTITY.itemsize:
+        raise TypeError("state must be an array of 80-byte physim Entity records")
+    return state
+
+
+# strings handed to the "host allocator" during a call; freed when the call returns
+_host_strings = []
+
+
+@ALLOC_FN
+def host_alloc_string(s):
+    """Stand-in for physim's host_alloc_string (physim-core/src/plugin/mod.rs): copies into host-owned
+    storage and returns the pointer."""
+    buf = C.create_string_buffer(s)
+    _host_strings.append(buf)
+    return C.addressof(buf)
+
+
+def element_meta(name):
+    """`{name}_register(alloc)` as discover.rs:363-371 calls it."""
+    m = getattr(lib(), f"{name}_register")(host_alloc_string)
+    out = {"kind": m.kind}
+    for k in ("name", "plugin", "version", "license", "author", "blurb", "repo"):
+        out[k] = C.string_at(getattr(m, k)).decode()
+    _host_strings.clear()
+    return out
+
+
+class TransformElement:
+    """A transform element loaded through the plugin C ABI (the drop-in boundary)."""
+
+    def __init__(self, name, **properties):
+        if name not in KINDS:
+            raise KeyError(name)
+        self.name = name
+        self._api = getattr(lib(), f"{name}_get_api")().contents
+        blob = json.dumps(properties).encode()            # serde_json::to_string(&properties)
+        self._blob = np.frombuffer(blob, dtype=np.uint8)  # not NUL-terminated, like into_raw_parts
+        self._obj = self._api.init(_ptr(self._blob), len(blob))
+        if not self._obj:
+            raise Pb200Error("Failed to load transform element: " + last_error())
+
+    @property
+    def theta(self):
+        return lib().pb200_transform_theta(self._obj)
+
+    @property
+    def easing(self):
+        return lib().pb200_transform_easing(self._obj)
+
+    def transform(self, state, accelerations=None):
+        """accelerations[i] += a_i (transformers.rs:32-69,123-160,220-244). Returns the array."""
+        state = _state(state)
+        n = len(state)
+        if accelerations is None:
+            accelerations = np.zeros(n, dtype=ACCELERATION)
+        assert accelerations.dtype.itemsize == 24 and len(accelerations) == n
+        self._api.transform(self._obj, _ptr(state), n, _ptr(accelerations), n)
+        return accelerations
+
+    def get_property_descriptions(self):
+        p = self._api.get_property_descriptions(self._obj, host_alloc_string)
+        if not p:
+            raise Pb200Error("Unable to load descriptions of properties")
+        out = json.loads(C.string_at(p).decode())
+        _host_strings.clear()
+        return out
+
+    def recv_message(self, topic="t", message="m", sender_id=0, priority=2):
+        msg = CMessage(priority, topic.encode(), message.encode(), sender_id, 0)
+        self._api.recv_message(self._obj, C.byref(msg))
+
+    def post_configuration_messages(self):
+        self._api.post_configuration_messages(self._obj)
+
+    def stats(self):
+        st = Pb200Stats()
+        if lib().pb200_transform_stats(self._obj, C.byref(st)) != 0:
+            raise Pb200Error(last_error())
+        return st.as_dict()
+
+    def debug_tree(self):
+        """Arrays of the tree built by the last transform() (parity tests)."""
+        st = self.stats()
+        n, c = st["n_bodies"], st["n_cells"]
+        out = {
+            "key": np.zeros(n, np.uint64), "perm": np.zeros(n, np.uint32),
+            "cell_start": np.zeros(n + 1, np.uint32), "level": np.zeros(c, np.uint8),
+            "head": np.zeros(c, np.uint32), "count": np.zeros(c, np.uint32),
+            "skip": np.zeros(c, np.uint32), "parent": np.zeros(c, np.uint32),
+            "centre_ext": np.zeros((c, 4), np.float64), "com_mass": np.zeros((c, 4), np.float64),
+            "counts": np.zeros(n, np.uint32),
+        }
+        rc = lib().pb200_transform_debug_tree(self._obj, *[_ptr(out[k]) for k in (
+            "key", "perm", "cell_start", "level", "head", "count", "skip", "parent", "centre_ext",
+            "com_mass", "counts")])
+        if rc != 0:
+            raise Pb200Error(last_error())
+        out["extent"] = st["extent"]
+        return out
+
+    def destroy(self):
+        if getattr(self, "_obj", None):
+            self._api.destroy(self._obj)
+            self._obj = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+class Verlet:
+    """`verlet` integrator (integrators/src/verlet.rs) over pb200_verlet_*."""
+
+    def __init__(self):
+        self._v = lib().pb200_verlet_create()
+
+    def integrate(self, entities, acc_fn, dt):
+        """IntegratorElement::integrate: acc_fn(state, accelerations) adds into accelerations."""
+        entities = _state(entities)
+        n = len(entities)
+        new_state = np.zeros(n, dtype=ENTITY)
+
+        def tramp(_ctx, sp, nn, ap):
+            if nn == 0:
+                return
+            s = np.ctypeslib.as_array(C.cast(sp, C.POINTER(C.c_uint8)), shape=(nn * 80,)).view(ENTITY)
+            a = np.ctypeslib.as_array(C.cast(ap, C.POINTER(C.c_double)), shape=(nn * 3,)).view(ACCELERATION)
+            acc_fn(s, a)
+
+        cb = ACC_FN(tramp)
+        if lib().pb200_verlet_step(self._v, _ptr(entities), _ptr(new_state), n, cb, None, float(dt)) != 0:
+            raise Pb200Error(last_error())
+        return new_state
+
+    def integrate_fused(self, entities, transform, dt):
+        """Same step with the accelerations of `transform` (a TransformElement) kept on the device."""
+        entities = _state(entities)
+        n = len(entities)
+        new_state = np.zeros(n, dtype=ENTITY)
+        rc = lib().pb200_verlet_step_fused(self._v, transform._obj, _ptr(entities), _ptr(new_state), n,
+                                           float(dt))
+        if rc != 0:
+            raise Pb200Error(last_error())
+        return new_state
+
+    def stats(self):
+        st = Pb200Stats()
+        lib().pb200_verlet_stats(self._v, C.byref(st))
+        return st.as_dict()
+
+    def __del__(self):
+        try:
+            if getattr(self, "_v", None):
+                lib().pb200_verlet_destroy(self._v)
+                self._v = None
+        except Exception:
+            pass
+
+
+class Sim:
+    """Device-resident `transform ! verlet` loop (pipeline.rs:143-182 without the host copies)."""
+
+    def __init__(self, name, theta=float("nan"), e=float("nan"), dt=1e-6, rank=0, world=1, device=None):
+        if device is not None:
+            lib().pb200_set_device(int(device))
+        self.rank, self.world = rank, world
+        self._s = lib().pb200_sim_create(KINDS[name], float(theta), float(e), float(dt), rank, world)
+        if not self._s:
+            raise Pb200Error(last_error())
+        self.n = 0
+
+    def upload(self, state):
+        state = _state(state)
+        self.n = len(state)
+        if lib().pb200_sim_upload(self._s, _ptr(state), self.n) != 0:
+            raise Pb200Error(last_error())
+
+    def run(self, steps):
+        if lib().pb200_sim_run(self._s, int(steps)) != 0:
+            raise Pb200Error(last_error())
+
+    def run_timed(self, steps):
+        """Runs `steps` steps; returns their device time in ms (CUDA events on the sim's stream)."""
+        ms = C.c_float()
+        if lib().pb200_sim_run_timed(self._s, int(steps), C.byref(ms)) != 0:
+            raise Pb200Error(last_error())
+        return ms.value
+
+    def profile(self, enable=True):
+        lib().pb200_sim_profile(self._s, 1 if enable else 0)
+
+    def profile_report(self):
+        buf = C.create_string_buffer(1 << 16)
+        if lib().pb200_sim_profile_report(self._s, buf, len(buf)) != 0:
+            raise Pb200Error("profile report failed")
+        return json.loads(buf.value.decode())
+
+    def step_local(self):
+        if lib().pb200_sim_step_local(self._s) != 0:
+            raise Pb200Error(last_error())
+
+    def gather_buffer(self):
+        """(device pointer, total bytes, slice offset, slice bytes) of the fp64 {x,y,z,m} buffer."""
+        p, tot, off, sl = C.c_void_p(), C.c_size_t(), C.c_size_t(), C.c_size_t()
+        lib().pb200_sim_gather_buffer(self._s, C.byref(p), C.byref(tot), C.byref(off), C.byref(sl))
+        return p.value, tot.value, off.value, sl.value
+
+    def download(self, state):
+        state = _state(state)
+        if lib().pb200_sim_download(self._s, _ptr(state), len(state)) != 0:
+            raise Pb200Error(last_error())
+        return state
+
+    def last_accelerations(self):
+        acc = np.zeros(self.n, dtype=ACCELERATION)
+        if lib().pb200_sim_last_accelerations(self._s, _ptr(acc), self.n) != 0:
+            raise Pb200Error(last_error())
+        return acc
+
+    def stats(self):
+        st = Pb200Stats()
+        if lib().pb200_sim_stats(self._s, C.byref(st)) != 0:
+            raise Pb200Error(last_error())
+        return st.as_dict()
+
+    def set_stream(self, cuda_stream_ptr):
+        if lib().pb200_sim_set_stream(self._s, C.c_void_p(cuda_stream_ptr)) != 0:
+            raise Pb200Error(last_error())
+
+    @property
+    def stream(self):
+        return lib().pb200_sim_stream(self._s)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_s", None):
+                lib().pb200_sim_destroy(self._s)
+                self._s = None
+        except Exception:
+            pass
+
+
+def device_count():
+    return lib().pb200_device_count()
+
+
+def probe_fp32_tflops():
+    return lib().pb200_probe_fp32_tflops()

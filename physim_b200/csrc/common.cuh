@@ -1,0 +1,241 @@
+// common.cuh — shared declarations for the physim_b200 CUDA engine (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../include/physim_b200.h"
+
+static_assert(sizeof(Entity) == 80, "physim Entity is 80 bytes (physim-core/src/lib.rs:16-30)");
+static_assert(sizeof(Acceleration) == 24, "physim Acceleration is 24 bytes (lib.rs:32-37)");
+static_assert(offsetof(Entity, mass) == 56 && offsetof(Entity, id) == 64 && offsetof(Entity, fixed) == 72,
+              "Entity field offsets");
+
+namespace pb200 {
+
+void set_error(const char* fmt, ...);
+extern thread_local char g_error[512];
+
+#define PB_CUDA(expr)                                                                         \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      ::pb200::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return _e;                                                                              \
+    }                                                                                         \
+  } while (0)
+
+// propagate an error whose message was already recorded by the callee
+#define PB_PASS(expr)                  \
+  do {                                 \
+    cudaError_t _e = (expr);           \
+    if (_e != cudaSuccess) return _e;  \
+  } while (0)
+
+// Grow-only device / pinned-host buffers.
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      set_error("cudaMalloc(%zu) -> %s", want, cudaGetErrorString(e));
+      return e;
+    }
+    cap = want;
+    return cudaSuccess;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() const {
+    return static_cast<T*>(p);
+  }
+};
+
+struct PinnedBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMallocHost(&p, want);
+    if (e != cudaSuccess) {
+      set_error("cudaMallocHost(%zu) -> %s", want, cudaGetErrorString(e));
+      return e;
+    }
+    cap = want;
+    return cudaSuccess;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() const {
+    return static_cast<T*>(p);
+  }
+};
+
+// ---- device workspace of one gravity evaluation ------------------------------------------------
+// Layout in HBM (N bodies, C cells ≈ 1.5 N):
+//   pos64   double4[N]  {x,y,z,m}, original order            32 B/body   (input of every kernel)
+//   fixed   u8[N]                                              1 B/body
+//   src4    float4[N]   {x,y,z,m} fp32 (direct sum sources)   16 B/body
+//   key[2]  u64[N], idx[2] u32[N]  (radix sort ping-pong)      24 B/body
+//   spos64  double4[N]  sorted {x,y,z,m}                       32 B/body
+//   ab      uchar2[N], cell_start u32[N+1]                      6 B/body
+//   cells:  level u8, head/count/skip/parent/arrived u32, centre_ext double4, com double4
+//                                                              85 B/cell
+//   acc     float4[N]   {ax,ay,az, bits(interactions)}, original order   16 B/body
+struct GravityWorkspace {
+  // inputs (owned elsewhere when running device-resident)
+  const double4* pos64 = nullptr;
+  const uint8_t* fixed = nullptr;
+  size_t n = 0;
+  // owned
+  DevBuf src4, key0, key1, idx0, idx1, spos64, ab, cell_start, scan_tmp, tile_counts, digit_base,
+      extent_bits, tgt_list, tgt_flags;
+  DevBuf c_level, c_head, c_count, c_skip, c_parent, c_arrived, c_centre_ext, c_com;
+  DevBuf acc, acc_part, counters;
+  size_t n_cells = 0;   // cells of the last checked evaluation
+  size_t cell_cap = 0;  // capacity of the cell arrays
+  // where the sorted keys / permutation ended up after the last sort
+  const uint64_t* sorted_key = nullptr;
+  const uint32_t* perm = nullptr;
+  void release_all();
+};
+
+struct GravityParams {
+  int kind;       // Pb200Kind
+  double theta;   // reference semantics: accept iff half_width / |p - centre| < theta
+  double easing;  // added to r^2
+};
+
+// Launch bookkeeping.  `launches` always counts; with `profiling` on, every launch is bracketed by a
+// CUDA event pair on the launching stream and collect() aggregates device time per kernel name
+// (what bench.py reports as the live per-kernel durations behind `roofline`).
+struct KernelTime {
+  const char* name;
+  uint64_t launches;
+  double ms;
+};
+struct LaunchStats {
+  uint64_t launches = 0;
+  bool profiling = false;
+  struct Pending {
+    const char* name;
+    cudaEvent_t e0, e1;
+  };
+  std::vector<Pending> pending;
+  std::vector<cudaEvent_t> pool;
+  std::vector<KernelTime> totals;
+  cudaEvent_t get_event() {
+    if (!pool.empty()) {
+      cudaEvent_t e = pool.back();
+      pool.pop_back();
+      return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+  }
+  void begin(const char* name, cudaStream_t st) {
+    ++launches;
+    if (!profiling) return;
+    Pending p{name, get_event(), get_event()};
+    cudaEventRecord(p.e0, st);
+    pending.push_back(p);
+  }
+  void end(cudaStream_t st) {
+    if (profiling && !pending.empty()) cudaEventRecord(pending.back().e1, st);
+  }
+  // requires the stream to be idle (caller synchronises)
+  void collect() {
+    for (const Pending& p : pending) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, p.e0, p.e1) != cudaSuccess) {
+        cudaGetLastError();
+        ms = 0.f;
+      }
+      bool found = false;
+      for (KernelTime& k : totals)
+        if (k.name == p.name || !std::strcmp(k.name, p.name)) {
+          k.launches += 1;
+          k.ms += ms;
+          found = true;
+          break;
+        }
+      if (!found) totals.push_back(KernelTime{p.name, 1, ms});
+      pool.push_back(p.e0);
+      pool.push_back(p.e1);
+    }
+    pending.clear();
+  }
+  void reset_profile() {
+    collect();
+    totals.clear();
+  }
+  ~LaunchStats() {
+    for (const Pending& p : pending) {
+      cudaEventDestroy(p.e0);
+      cudaEventDestroy(p.e1);
+    }
+    for (cudaEvent_t e : pool) cudaEventDestroy(e);
+  }
+};
+
+// PB_LAUNCH(ls, stream, "name", kernel<<<grid, block, smem, stream>>>(args...));
+#define PB_LAUNCH(ls, st, name, ...) \
+  do {                               \
+    (ls).begin(name, st);            \
+    __VA_ARGS__;                     \
+    (ls).end(st);                    \
+  } while (0)
+
+// Computes acc[i] (original order) for targets with original index in [t0, t1) from all n bodies.
+// Fixed targets and targets outside the range are left at zero.  *n_cells_out receives the cell count.
+// host_check: read the cell total back (one stream sync) and re-run once if the cell table was too
+// small; without it the caller must poll gravity_cell_total() before trusting the result.
+cudaError_t gravity_evaluate(GravityWorkspace& ws, const GravityParams& prm, size_t t0, size_t t1,
+                             cudaStream_t stream, LaunchStats& ls, bool host_check = true);
+// Cell total of the last tree build (synchronises); compare with ws.cell_cap for overflow.
+cudaError_t gravity_cell_total(GravityWorkspace& ws, cudaStream_t stream, uint32_t* total);
+// Sum of per-target interaction counters of the last evaluation (synchronises the stream).
+cudaError_t gravity_count_interactions(GravityWorkspace& ws, cudaStream_t stream, LaunchStats& ls,
+                                       uint64_t* out);
+
+// ---- packing / unpacking at the host boundary ---------------------------------------------------
+// AoS Entity (device copy not needed): host packs into {x,y,z,m} + fixed flags (see host_pack.cpp).
+
+// ---- verlet --------------------------------------------------------------------------------------
+// In-place update of cur (double4 {x,y,z,m}), prev (double3-as-double4 without mass use), vel.
+// first != 0: x1 = x0 + v0 dt + ½ a dt², v1 = v0 + a dt, prev = x0      (verlet.rs:24-50)
+// else      : x' = 2x − prev + a dt², v' = (x' − x)/dt, prev = x         (verlet.rs:52-82)
+// acc32 (float4, index i - acc_offset... see verlet.cu) or acc64 (3 doubles per body) is used.
+cudaError_t verlet_update(double4* cur, double4* prev, double4* vel, const float4* acc32,
+                          const double* acc64, size_t n, double dt, int first, cudaStream_t stream,
+                          LaunchStats& ls);
+
+// fp32 FFMA probe
+cudaError_t probe_fp32(double* tflops);
+
+}  // namespace pb200

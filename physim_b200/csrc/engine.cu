@@ -1,0 +1,914 @@
+// engine.cu — host side of libphysim_b200.so: the handles behind include/physim_b200.h section 3.
+//
+//   TransformObj  ~ AstroElement / AstroOctreeElement / SimpleAstroElement (astro/src/transformers.rs)
+//   Verlet     ~ integrators/src/verlet.rs
+//   Sim        ~ the simulation thread's loop (physim-core/src/pipeline.rs:143-182) kept in HBM
+//
+// Nothing here touches the GPU until the first force evaluation: physim instantiates and drops
+// every transform during plugin discovery (physim-core/src/plugin/discover.rs:376-387).
+#include <cmath>
+#include <cstdarg>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "host_pool.hpp"
+
+namespace pb200 {
+
+thread_local char g_error[512] = {0};
+static thread_local int g_device = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof g_error, fmt, ap);
+  va_end(ap);
+  if (std::getenv("PB200_VERBOSE")) std::fprintf(stderr, "[physim_b200] %s\n", g_error);
+}
+
+namespace {
+
+constexpr size_t kParallelGrain = 1 << 14;
+
+struct GpuContext {
+  bool ready = false;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaError_t init(int dev) {
+    if (ready) return cudaSetDevice(device);
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) {
+      set_error("no CUDA device available (%s); physim_b200 has no CPU fallback",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+      return e == cudaSuccess ? cudaErrorNoDevice : e;
+    }
+    device = dev;
+    PB_CUDA(cudaSetDevice(device));
+    PB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    for (auto& x : ev) PB_CUDA(cudaEventCreate(&x));
+    ready = true;
+    return cudaSuccess;
+  }
+  void destroy() {
+    if (!ready) return;
+    cudaSetDevice(device);
+    for (auto& x : ev)
+      if (x) cudaEventDestroy(x);
+    if (stream && own_stream) cudaStreamDestroy(stream);
+    ready = false;
+  }
+};
+
+float elapsed(cudaEvent_t a, cudaEvent_t b) {
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, a, b) != cudaSuccess) {
+    cudaGetLastError();
+    return 0.f;
+  }
+  return ms;
+}
+
+struct TransformObj {
+  GravityParams prm;
+  std::mutex mu;
+  GpuContext gpu;
+  int device;
+  GravityWorkspace ws;
+  DevBuf d_pos, d_fixed;
+  PinnedBuf h_pos, h_fixed, h_acc;
+  LaunchStats ls;
+  Pb200Stats stats;
+  size_t last_n = 0;
+  bool have_tree = false;
+
+  ~TransformObj() {
+    if (gpu.ready) {
+      cudaSetDevice(gpu.device);
+      ws.release_all();
+      d_pos.release();
+      d_fixed.release();
+      h_pos.release();
+      h_fixed.release();
+      h_acc.release();
+      gpu.destroy();
+    }
+  }
+};
+
+// pack Entity AoS -> pinned {x,y,z,m} (+ fixed bytes)
+void pack_positions(const Entity* state, size_t n, double4* pos, uint8_t* fixed) {
+  HostPool::instance().parallel_for(n, kParallelGrain, [&](size_t b, size_t e) {
+    for (size_t i = b; i < e; ++i) {
+      const Entity& s = state[i];
+      pos[i] = make_double4(s.x, s.y, s.z, s.mass);
+      if (fixed) fixed[i] = s.fixed ? 1 : 0;
+    }
+  });
+}
+
+cudaError_t transform_forces(TransformObj& t, const Entity* state, size_t n) {
+  PB_PASS(t.gpu.init(t.device));
+  cudaStream_t st = t.gpu.stream;
+  PB_PASS(t.h_pos.ensure(n * sizeof(double4)));
+  PB_PASS(t.h_fixed.ensure(n));
+  PB_PASS(t.h_acc.ensure(n * sizeof(float4)));
+  PB_PASS(t.d_pos.ensure(n * sizeof(double4)));
+  PB_PASS(t.d_fixed.ensure(n));
+  pack_positions(state, n, t.h_pos.as<double4>(), t.h_fixed.as<uint8_t>());
+  PB_CUDA(cudaEventRecord(t.gpu.ev[0], st));
+  PB_CUDA(cudaMemcpyAsync(t.d_pos.p, t.h_pos.p, n * sizeof(double4), cudaMemcpyHostToDevice, st));
+  PB_CUDA(cudaMemcpyAsync(t.d_fixed.p, t.h_fixed.p, n, cudaMemcpyHostToDevice, st));
+  PB_CUDA(cudaEventRecord(t.gpu.ev[1], st));
+  t.ws.pos64 = t.d_pos.as<double4>();
+  t.ws.fixed = t.d_fixed.as<uint8_t>();
+  t.ws.n = n;
+  PB_PASS(gravity_evaluate(t.ws, t.prm, 0, n, st, t.ls, true));
+  PB_CUDA(cudaEventRecord(t.gpu.ev[2], st));
+  PB_CUDA(cudaMemcpyAsync(t.h_acc.p, t.ws.acc.p, n * sizeof(float4), cudaMemcpyDeviceToHost, st));
+  PB_CUDA(cudaEventRecord(t.gpu.ev[3], st));
+  PB_CUDA(cudaStreamSynchronize(st));
+  t.last_n = n;
+  t.have_tree = t.ws.n_cells > 0;
+  t.stats.n_bodies = n;
+  t.stats.n_cells = t.ws.n_cells;
+  t.stats.kernel_launches = t.ls.launches;
+  t.stats.ms_h2d = elapsed(t.gpu.ev[0], t.gpu.ev[1]);
+  t.stats.ms_build = 0.f;
+  t.stats.ms_force = elapsed(t.gpu.ev[1], t.gpu.ev[2]);
+  t.stats.ms_integrate = 0.f;
+  t.stats.ms_d2h = elapsed(t.gpu.ev[2], t.gpu.ev[3]);
+  return cudaSuccess;
+}
+
+struct VerletObj {
+  std::mutex mu;
+  GpuContext gpu;
+  int device;
+  size_t n_prev = 0;  // length of the stored previous state (verlet.rs:102: len != n => first step)
+  DevBuf cur, prev, vel, acc64, fixed;
+  PinnedBuf h_pos, h_vel, h_fixed, h_acc;
+  LaunchStats ls;
+  Pb200Stats stats;
+  ~VerletObj() {
+    if (gpu.ready) {
+      cudaSetDevice(gpu.device);
+      cur.release(); prev.release(); vel.release(); acc64.release(); fixed.release();
+      h_pos.release(); h_vel.release(); h_fixed.release(); h_acc.release();
+      gpu.destroy();
+    }
+  }
+};
+
+void pack_velocities(const Entity* state, size_t n, double4* vel) {
+  HostPool::instance().parallel_for(n, kParallelGrain, [&](size_t b, size_t e) {
+    for (size_t i = b; i < e; ++i) vel[i] = make_double4(state[i].vx, state[i].vy, state[i].vz, 0.0);
+  });
+}
+
+// new_state[i] = entities[i] with position and velocity replaced (verlet.rs:41-48 / :72-79)
+void unpack_state(const Entity* entities, Entity* out, size_t n, const double4* pos, const double4* vel) {
+  HostPool::instance().parallel_for(n, kParallelGrain, [&](size_t b, size_t e) {
+    for (size_t i = b; i < e; ++i) {
+      Entity o = entities[i];
+      o.x = pos[i].x; o.y = pos[i].y; o.z = pos[i].z;
+      o.vx = vel[i].x; o.vy = vel[i].y; o.vz = vel[i].z;
+      out[i] = o;
+    }
+  });
+}
+
+cudaError_t verlet_buffers(VerletObj& v, size_t n) {
+  PB_PASS(v.gpu.init(v.device));
+  PB_PASS(v.cur.ensure(n * sizeof(double4)));
+  PB_PASS(v.prev.ensure(n * sizeof(double4)));
+  PB_PASS(v.vel.ensure(n * sizeof(double4)));
+  PB_PASS(v.fixed.ensure(n));
+  PB_PASS(v.h_pos.ensure(n * sizeof(double4)));
+  PB_PASS(v.h_vel.ensure(n * sizeof(double4)));
+  PB_PASS(v.h_fixed.ensure(n));
+  return cudaSuccess;
+}
+
+// shared tail of both verlet entry points: D2H of the updated state, unpack, bookkeeping
+cudaError_t verlet_finish(VerletObj& v, cudaStream_t st, const Entity* entities, Entity* new_state, size_t n) {
+  PB_CUDA(cudaMemcpyAsync(v.h_pos.p, v.cur.p, n * sizeof(double4), cudaMemcpyDeviceToHost, st));
+  PB_CUDA(cudaMemcpyAsync(v.h_vel.p, v.vel.p, n * sizeof(double4), cudaMemcpyDeviceToHost, st));
+  PB_CUDA(cudaEventRecord(v.gpu.ev[4], st));
+  PB_CUDA(cudaStreamSynchronize(st));
+  unpack_state(entities, new_state, n, v.h_pos.as<double4>(), v.h_vel.as<double4>());
+  v.n_prev = n;
+  v.stats.n_bodies = n;
+  v.stats.kernel_launches = v.ls.launches;
+  return cudaSuccess;
+}
+
+cudaError_t verlet_step_generic(VerletObj& v, const Entity* entities, Entity* new_state, size_t n,
+                                Pb200AccFn acc_fn, void* ctx, double dt) {
+  std::vector<Acceleration> acc(n, Acceleration{0.0, 0.0, 0.0});  // verlet.rs:93
+  acc_fn(ctx, entities, n, acc.data());                           // verlet.rs:94
+  if (n == 0) {
+    v.n_prev = 0;
+    return cudaSuccess;
+  }
+  PB_PASS(verlet_buffers(v, n));
+  PB_PASS(v.acc64.ensure(n * sizeof(Acceleration)));
+  PB_PASS(v.h_acc.ensure(n * sizeof(Acceleration)));
+  cudaStream_t st = v.gpu.stream;
+  const bool first = v.n_prev != n;
+  pack_positions(entities, n, v.h_pos.as<double4>(), nullptr);
+  if (first) pack_velocities(entities, n, v.h_vel.as<double4>());
+  std::memcpy(v.h_acc.p, acc.data(), n * sizeof(Acceleration));
+  PB_CUDA(cudaEventRecord(v.gpu.ev[0], st));
+  PB_CUDA(cudaMemcpyAsync(v.cur.p, v.h_pos.p, n * sizeof(double4), cudaMemcpyHostToDevice, st));
+  if (first) PB_CUDA(cudaMemcpyAsync(v.vel.p, v.h_vel.p, n * sizeof(double4), cudaMemcpyHostToDevice, st));
+  PB_CUDA(cudaMemcpyAsync(v.acc64.p, v.h_acc.p, n * sizeof(Acceleration), cudaMemcpyHostToDevice, st));
+  PB_CUDA(cudaEventRecord(v.gpu.ev[1], st));
+  PB_PASS(verlet_update(v.cur.as<double4>(), v.prev.as<double4>(), v.vel.as<double4>(), nullptr,
+                        v.acc64.as<double>(), n, dt, first ? 1 : 0, st, v.ls));
+  PB_CUDA(cudaEventRecord(v.gpu.ev[3], st));
+  PB_PASS(verlet_finish(v, st, entities, new_state, n));
+  v.stats.ms_h2d = elapsed(v.gpu.ev[0], v.gpu.ev[1]);
+  v.stats.ms_force = 0.f;
+  v.stats.ms_integrate = elapsed(v.gpu.ev[1], v.gpu.ev[3]);
+  v.stats.ms_d2h = elapsed(v.gpu.ev[3], v.gpu.ev[4]);
+  return cudaSuccess;
+}
+
+cudaError_t verlet_step_fused(VerletObj& v, TransformObj& t, const Entity* entities, Entity* new_state, size_t n,
+                              double dt) {
+  if (n == 0) {
+    v.n_prev = 0;
+    return cudaSuccess;
+  }
+  v.device = t.device;
+  PB_PASS(verlet_buffers(v, n));
+  PB_PASS(t.gpu.init(t.device));
+  cudaStream_t st = v.gpu.stream;
+  const bool first = v.n_prev != n;
+  pack_positions(entities, n, v.h_pos.as<double4>(), v.h_fixed.as<uint8_t>());
+  if (first) pack_velocities(entities, n, v.h_vel.as<double4>());
+  PB_CUDA(cudaEventRecord(v.gpu.ev[0], st));
+  PB_CUDA(cudaMemcpyAsync(v.cur.p, v.h_pos.p, n * sizeof(double4), cudaMemcpyHostToDevice, st));
+  PB_CUDA(cudaMemcpyAsync(v.fixed.p, v.h_fixed.p, n, cudaMemcpyHostToDevice, st));
+  if (first) PB_CUDA(cudaMemcpyAsync(v.vel.p, v.h_vel.p, n * sizeof(double4), cudaMemcpyHostToDevice, st));
+  PB_CUDA(cudaEventRecord(v.gpu.ev[1], st));
+  t.ws.pos64 = v.cur.as<double4>();
+  t.ws.fixed = v.fixed.as<uint8_t>();
+  t.ws.n = n;
+  PB_PASS(gravity_evaluate(t.ws, t.prm, 0, n, st, t.ls, true));
+  PB_CUDA(cudaEventRecord(v.gpu.ev[2], st));
+  PB_PASS(verlet_update(v.cur.as<double4>(), v.prev.as<double4>(), v.vel.as<double4>(),
+                        t.ws.acc.as<float4>(), nullptr, n, dt, first ? 1 : 0, st, v.ls));
+  PB_CUDA(cudaEventRecord(v.gpu.ev[3], st));
+  PB_PASS(verlet_finish(v, st, entities, new_state, n));
+  t.last_n = n;
+  t.stats.n_bodies = n;
+  t.stats.n_cells = t.ws.n_cells;
+  t.stats.kernel_launches = t.ls.launches;
+  v.stats.n_cells = t.ws.n_cells;
+  v.stats.kernel_launches = v.ls.launches + t.ls.launches;
+  v.stats.ms_h2d = elapsed(v.gpu.ev[0], v.gpu.ev[1]);
+  v.stats.ms_force = elapsed(v.gpu.ev[1], v.gpu.ev[2]);
+  v.stats.ms_integrate = elapsed(v.gpu.ev[2], v.gpu.ev[3]);
+  v.stats.ms_d2h = elapsed(v.gpu.ev[3], v.gpu.ev[4]);
+  return cudaSuccess;
+}
+
+struct SimObj {
+  GravityParams prm;
+  double dt;
+  int rank, world, device;
+  std::mutex mu;
+  GpuContext gpu;
+  GravityWorkspace ws;
+  DevBuf cur, prev, vel, fixed;  // cur doubles as the all-gather buffer ({x,y,z,m} of all n bodies)
+  PinnedBuf h_pos, h_vel, h_fixed, h_acc;
+  size_t n = 0, t0 = 0, t1 = 0;
+  bool first = true, checked = false;
+  LaunchStats ls;
+  Pb200Stats stats;
+  ~SimObj() {
+    if (gpu.ready) {
+      cudaSetDevice(gpu.device);
+      ws.release_all();
+      cur.release(); prev.release(); vel.release(); fixed.release();
+      h_pos.release(); h_vel.release(); h_fixed.release(); h_acc.release();
+      gpu.destroy();
+    }
+  }
+};
+
+cudaError_t sim_upload(SimObj& s, const Entity* state, size_t n) {
+  PB_PASS(s.gpu.init(s.device));
+  cudaStream_t st = s.gpu.stream;
+  s.n = n;
+  s.t0 = n * size_t(s.rank) / size_t(s.world);
+  s.t1 = n * size_t(s.rank + 1) / size_t(s.world);
+  s.first = true;
+  s.checked = false;
+  if (n == 0) return cudaSuccess;
+  PB_PASS(s.cur.ensure(n * sizeof(double4)));
+  PB_PASS(s.prev.ensure(n * sizeof(double4)));
+  PB_PASS(s.vel.ensure(n * sizeof(double4)));
+  PB_PASS(s.fixed.ensure(n));
+  PB_PASS(s.h_pos.ensure(n * sizeof(double4)));
+  PB_PASS(s.h_vel.ensure(n * sizeof(double4)));
+  PB_PASS(s.h_fixed.ensure(n));
+  pack_positions(state, n, s.h_pos.as<double4>(), s.h_fixed.as<uint8_t>());
+  pack_velocities(state, n, s.h_vel.as<double4>());
+  PB_CUDA(cudaMemcpyAsync(s.cur.p, s.h_pos.p, n * sizeof(double4), cudaMemcpyHostToDevice, st));
+  PB_CUDA(cudaMemcpyAsync(s.vel.p, s.h_vel.p, n * sizeof(double4), cudaMemcpyHostToDevice, st));
+  PB_CUDA(cudaMemcpyAsync(s.fixed.p, s.h_fixed.p, n, cudaMemcpyHostToDevice, st));
+  PB_CUDA(cudaStreamSynchronize(st));
+  s.ws.pos64 = s.cur.as<double4>();
+  s.ws.fixed = s.fixed.as<uint8_t>();
+  s.ws.n = n;
+  s.ws.n_cells = 0;
+  return cudaSuccess;
+}
+
+// one step: forces for targets [t0,t1) from all n positions, then verlet on the owned slice
+cudaError_t sim_step(SimObj& s) {
+  if (s.n == 0) return cudaSuccess;
+  cudaStream_t st = s.gpu.stream;
+  const bool check = !s.checked;  // size the cell table once, then stay asynchronous
+  PB_PASS(gravity_evaluate(s.ws, s.prm, s.t0, s.t1, st, s.ls, check));
+  s.checked = true;
+  const size_t nl = s.t1 - s.t0;
+  PB_PASS(verlet_update(s.cur.as<double4>() + s.t0, s.prev.as<double4>() + s.t0,
+                        s.vel.as<double4>() + s.t0, s.ws.acc.as<float4>() + s.t0, nullptr, nl, s.dt,
+                        s.first ? 1 : 0, st, s.ls));
+  s.first = false;
+  return cudaSuccess;
+}
+
+cudaError_t sim_verify_tree(SimObj& s) {
+  const bool direct = s.prm.kind == PB200_SIMPLE_ASTRO || !(s.prm.theta > 0.0);
+  if (direct || s.n == 0) return cudaSuccess;
+  uint32_t total = 0;
+  PB_PASS(gravity_cell_total(s.ws, s.gpu.stream, &total));
+  if (total > s.ws.cell_cap) {
+    s.checked = false;  // next step re-sizes the table
+    set_error("cell table overflow during an unchecked step (%u cells > capacity %zu): state invalid",
+              total, s.ws.cell_cap);
+    return cudaErrorUnknown;
+  }
+  return cudaSuccess;
+}
+
+// ---- tiny flat-JSON reader for the plugin's init(): {"theta": 1.5, "e": 0.5, ...} --------------
+struct JsonProps {
+  bool ok = true;
+  bool has_theta = false, has_e = false;
+  double theta = 0.0, e = 0.0;
+};
+
+struct JsonCursor {
+  const char* p;
+  const char* end;
+  void ws() {
+    while (p < end && (*p == ' ' || *p == '\t' || *p == '\n' || *p == '\r')) ++p;
+  }
+  bool eat(char c) {
+    ws();
+    if (p < end && *p == c) {
+      ++p;
+      return true;
+    }
+    return false;
+  }
+  bool string(std::string* out) {
+    ws();
+    if (p >= end || *p != '"') return false;
+    ++p;
+    while (p < end && *p != '"') {
+      if (*p == '\\') {
+        ++p;
+        if (p >= end) return false;
+        if (*p == 'u') {
+          if (end - p < 5) return false;
+          p += 4;
+          if (out) out->push_back('?');
+        } else if (out) {
+          out->push_back(*p);
+        }
+        ++p;
+      } else {
+        if (out) out->push_back(*p);
+        ++p;
+      }
+    }
+    if (p >= end) return false;
+    ++p;
+    return true;
+  }
+  // skips any JSON value; *num/*is_num report a number (serde's as_f64 accepts ints and floats)
+  bool value(double* num, bool* is_num, int depth = 0) {
+    ws();
+    *is_num = false;
+    if (p >= end || depth > 32) return false;
+    const char c = *p;
+    if (c == '"') return string(nullptr);
+    if (c == '{' || c == '[') {
+      const char close = (c == '{') ? '}' : ']';
+      ++p;
+      ws();
+      if (eat(close)) return true;
+      for (;;) {
+        if (c == '{') {
+          if (!string(nullptr) || !eat(':')) return false;
+        }
+        double d;
+        bool b;
+        if (!value(&d, &b, depth + 1)) return false;
+        if (eat(',')) continue;
+        return eat(close);
+      }
+    }
+    if (end - p >= 4 && !std::strncmp(p, "true", 4)) { p += 4; return true; }
+    if (end - p >= 5 && !std::strncmp(p, "false", 5)) { p += 5; return true; }
+    if (end - p >= 4 && !std::strncmp(p, "null", 4)) { p += 4; return true; }
+    if (c == '-' || (c >= '0' && c <= '9')) {
+      char buf[64];
+      size_t k = 0;
+      while (p < end && k + 1 < sizeof buf &&
+             ((*p >= '0' && *p <= '9') || *p == '-' || *p == '+' || *p == '.' || *p == 'e' || *p == 'E'))
+        buf[k++] = *p++;
+      buf[k] = 0;
+      char* stop = nullptr;
+      *num = std::strtod(buf, &stop);
+      if (stop == buf || *stop != 0) return false;
+      *is_num = true;
+      return true;
+    }
+    return false;
+  }
+};
+
+JsonProps parse_props(const uint8_t* json, size_t len) {
+  JsonProps out;
+  JsonCursor c{reinterpret_cast<const char*>(json), reinterpret_cast<const char*>(json) + len};
+  if (!json) { out.ok = false; return out; }
+  if (!c.eat('{')) { out.ok = false; return out; }
+  if (c.eat('}')) { c.ws(); out.ok = (c.p == c.end); return out; }
+  for (;;) {
+    std::string key;
+    double d = 0.0;
+    bool is_num = false;
+    if (!c.string(&key) || !c.eat(':') || !c.value(&d, &is_num)) { out.ok = false; return out; }
+    if (is_num && key == "theta") { out.has_theta = true; out.theta = d; }
+    if (is_num && key == "e") { out.has_e = true; out.e = d; }
+    if (c.eat(',')) continue;
+    if (!c.eat('}')) { out.ok = false; return out; }
+    break;
+  }
+  c.ws();
+  out.ok = (c.p == c.end);
+  return out;
+}
+
+template <class T>
+cudaError_t copy_out(T* host, const void* dev, size_t count, cudaStream_t st) {
+  if (!host || !count) return cudaSuccess;
+  PB_CUDA(cudaMemcpyAsync(host, dev, count * sizeof(T), cudaMemcpyDeviceToHost, st));
+  return cudaSuccess;
+}
+
+}  // namespace
+}  // namespace pb200
+
+using namespace pb200;
+
+extern "C" {
+
+int pb200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int pb200_set_device(int device) {
+  g_device = device;
+  return 0;
+}
+
+const char* pb200_last_error(void) { return g_error; }
+
+void* pb200_transform_create(int kind, double theta, double e) {
+  if (kind < PB200_ASTRO || kind > PB200_SIMPLE_ASTRO) {
+    set_error("unknown element kind %d", kind);
+    return nullptr;
+  }
+  auto* t = new TransformObj();
+  t->prm.kind = kind;
+  t->prm.theta = std::isnan(theta) ? 1.0 : theta;        // transformers.rs:72-75
+  t->prm.easing = std::isnan(e) ? 1.0 : std::fabs(e);    // transformers.rs:77-81 (.abs())
+  t->device = g_device;
+  std::memset(&t->stats, 0, sizeof t->stats);
+  return t;
+}
+
+void* pb200_transform_create_json(int kind, const uint8_t* json, size_t len) {
+  const JsonProps p = parse_props(json, len);
+  if (!p.ok) {
+    set_error("malformed property JSON");
+    return nullptr;
+  }
+  return pb200_transform_create(kind, p.has_theta ? p.theta : NAN, p.has_e ? p.e : NAN);
+}
+
+void pb200_transform_destroy(void* obj) { delete static_cast<TransformObj*>(obj); }
+
+double pb200_transform_theta(void* obj) { return static_cast<TransformObj*>(obj)->prm.theta; }
+double pb200_transform_easing(void* obj) { return static_cast<TransformObj*>(obj)->prm.easing; }
+
+int pb200_transform_apply(void* obj, const Entity* state, size_t n, Acceleration* acc, size_t n_acc) {
+  if (!obj) {
+    set_error("null transform");
+    return -1;
+  }
+  auto& t = *static_cast<TransformObj*>(obj);
+  std::lock_guard<std::mutex> lk(t.mu);
+  if (n_acc < n) n = n_acc;
+  if (n == 0) return 0;
+  if (!state || !acc) {
+    set_error("null state/acceleration pointer");
+    return -1;
+  }
+  if (transform_forces(t, state, n) != cudaSuccess) {
+    std::fprintf(stderr, "[physim_b200] transform failed: %s\n", g_error);
+    return -1;
+  }
+  const float4* a = t.h_acc.as<float4>();
+  // accelerations[i] += f / m_a for every non-fixed body (transformers.rs:139-141,154-158)
+  HostPool::instance().parallel_for(n, kParallelGrain, [&](size_t b, size_t e) {
+    for (size_t i = b; i < e; ++i) {
+      if (state[i].fixed) continue;
+      acc[i].x += double(a[i].x);
+      acc[i].y += double(a[i].y);
+      acc[i].z += double(a[i].z);
+    }
+  });
+  return 0;
+}
+
+int pb200_transform_stats(void* obj, Pb200Stats* out) {
+  if (!obj || !out) return -1;
+  auto& t = *static_cast<TransformObj*>(obj);
+  std::lock_guard<std::mutex> lk(t.mu);
+  if (t.gpu.ready && t.last_n) {
+    cudaSetDevice(t.gpu.device);
+    uint64_t inter = 0;
+    if (gravity_count_interactions(t.ws, t.gpu.stream, t.ls, &inter) != cudaSuccess) return -1;
+    t.stats.interactions = inter;
+    if (t.ws.extent_bits.p && t.have_tree) {
+      unsigned long long bits = 0;
+      cudaMemcpy(&bits, t.ws.extent_bits.p, 8, cudaMemcpyDeviceToHost);
+      std::memcpy(&t.stats.extent, &bits, 8);
+    }
+    t.stats.kernel_launches = t.ls.launches;
+  }
+  *out = t.stats;
+  return 0;
+}
+
+int pb200_transform_debug_tree(void* obj, uint64_t* key, uint32_t* perm, uint32_t* cell_start,
+                               uint8_t* level, uint32_t* head, uint32_t* count, uint32_t* skip,
+                               uint32_t* parent, double* centre_ext, double* com_mass,
+                               uint32_t* counts) {
+  if (!obj) return -1;
+  auto& t = *static_cast<TransformObj*>(obj);
+  std::lock_guard<std::mutex> lk(t.mu);
+  if (!t.gpu.ready || !t.last_n) {
+    set_error("no evaluation to inspect");
+    return -1;
+  }
+  cudaSetDevice(t.gpu.device);
+  cudaStream_t st = t.gpu.stream;
+  const size_t n = t.last_n, c = t.ws.n_cells;
+  auto run = [&]() -> cudaError_t {
+    if (t.have_tree) {
+      PB_PASS(copy_out(key, t.ws.sorted_key, n, st));
+      PB_PASS(copy_out(perm, t.ws.perm, n, st));
+      PB_PASS(copy_out(cell_start, t.ws.cell_start.p, n + 1, st));
+      PB_PASS(copy_out(level, t.ws.c_level.p, c, st));
+      PB_PASS(copy_out(head, t.ws.c_head.p, c, st));
+      PB_PASS(copy_out(count, t.ws.c_count.p, c, st));
+      PB_PASS(copy_out(skip, t.ws.c_skip.p, c, st));
+      PB_PASS(copy_out(parent, t.ws.c_parent.p, c, st));
+      PB_PASS(copy_out(centre_ext, t.ws.c_centre_ext.p, c * 4, st));
+      PB_PASS(copy_out(com_mass, t.ws.c_com.p, c * 4, st));
+    }
+    PB_CUDA(cudaStreamSynchronize(st));
+    if (counts) {
+      std::vector<float4> a(n);
+      PB_CUDA(cudaMemcpy(a.data(), t.ws.acc.p, n * sizeof(float4), cudaMemcpyDeviceToHost));
+      for (size_t i = 0; i < n; ++i) std::memcpy(&counts[i], &a[i].w, 4);
+    }
+    return cudaSuccess;
+  };
+  return run() == cudaSuccess ? 0 : -1;
+}
+
+// ---- verlet -----------------------------------------------------------------------------------
+
+void* pb200_verlet_create(void) {
+  auto* v = new VerletObj();
+  v->device = g_device;
+  std::memset(&v->stats, 0, sizeof v->stats);
+  return v;
+}
+void pb200_verlet_destroy(void* v) { delete static_cast<VerletObj*>(v); }
+
+int pb200_verlet_step(void* vp, const Entity* entities, Entity* new_state, size_t n, Pb200AccFn acc_fn,
+                      void* ctx, double dt) {
+  if (!vp || !acc_fn || (n && (!entities || !new_state))) {
+    set_error("null argument");
+    return -1;
+  }
+  auto& v = *static_cast<VerletObj*>(vp);
+  std::lock_guard<std::mutex> lk(v.mu);
+  if (verlet_step_generic(v, entities, new_state, n, acc_fn, ctx, dt) != cudaSuccess) {
+    std::fprintf(stderr, "[physim_b200] verlet step failed: %s\n", g_error);
+    return -1;
+  }
+  return 0;
+}
+
+int pb200_verlet_step_fused(void* vp, void* transform, const Entity* entities, Entity* new_state, size_t n,
+                            double dt) {
+  if (!vp || !transform || (n && (!entities || !new_state))) {
+    set_error("null argument");
+    return -1;
+  }
+  auto& v = *static_cast<VerletObj*>(vp);
+  auto& t = *static_cast<TransformObj*>(transform);
+  std::lock_guard<std::mutex> lk(v.mu);
+  std::lock_guard<std::mutex> lk2(t.mu);
+  if (verlet_step_fused(v, t, entities, new_state, n, dt) != cudaSuccess) {
+    std::fprintf(stderr, "[physim_b200] fused verlet step failed: %s\n", g_error);
+    return -1;
+  }
+  return 0;
+}
+
+int pb200_verlet_stats(void* vp, Pb200Stats* out) {
+  if (!vp || !out) return -1;
+  auto& v = *static_cast<VerletObj*>(vp);
+  std::lock_guard<std::mutex> lk(v.mu);
+  *out = v.stats;
+  return 0;
+}
+
+// ---- device-resident simulation ----------------------------------------------------------------
+
+void* pb200_sim_create(int kind, double theta, double e, double dt, int rank, int world) {
+  if (kind < PB200_ASTRO || kind > PB200_SIMPLE_ASTRO || world < 1 || rank < 0 || rank >= world) {
+    set_error("bad arguments to pb200_sim_create");
+    return nullptr;
+  }
+  auto* s = new SimObj();
+  s->prm.kind = kind;
+  s->prm.theta = std::isnan(theta) ? 1.0 : theta;
+  s->prm.easing = std::isnan(e) ? 1.0 : std::fabs(e);
+  s->dt = dt;
+  s->rank = rank;
+  s->world = world;
+  s->device = g_device;
+  std::memset(&s->stats, 0, sizeof s->stats);
+  return s;
+}
+
+void pb200_sim_destroy(void* sim) { delete static_cast<SimObj*>(sim); }
+
+int pb200_sim_upload(void* sim, const Entity* state, size_t n) {
+  if (!sim || (n && !state)) return -1;
+  auto& s = *static_cast<SimObj*>(sim);
+  std::lock_guard<std::mutex> lk(s.mu);
+  if (sim_upload(s, state, n) != cudaSuccess) {
+    std::fprintf(stderr, "[physim_b200] sim upload failed: %s\n", g_error);
+    return -1;
+  }
+  return 0;
+}
+
+int pb200_sim_run(void* sim, size_t steps) {
+  if (!sim) return -1;
+  auto& s = *static_cast<SimObj*>(sim);
+  std::lock_guard<std::mutex> lk(s.mu);
+  if (!s.gpu.ready) {
+    set_error("pb200_sim_upload first");
+    return -1;
+  }
+  cudaSetDevice(s.gpu.device);
+  for (size_t i = 0; i < steps; ++i)
+    if (sim_step(s) != cudaSuccess) {
+      std::fprintf(stderr, "[physim_b200] sim step failed: %s\n", g_error);
+      return -1;
+    }
+  if (sim_verify_tree(s) != cudaSuccess) {
+    std::fprintf(stderr, "[physim_b200] %s\n", g_error);
+    return -1;
+  }
+  return 0;
+}
+
+int pb200_sim_run_timed(void* sim, size_t steps, float* ms) {
+  if (!sim || !ms) return -1;
+  auto& s = *static_cast<SimObj*>(sim);
+  {
+    std::lock_guard<std::mutex> lk(s.mu);
+    if (!s.gpu.ready) {
+      set_error("pb200_sim_upload first");
+      return -1;
+    }
+    cudaSetDevice(s.gpu.device);
+    if (cudaStreamSynchronize(s.gpu.stream) != cudaSuccess ||
+        cudaEventRecord(s.gpu.ev[0], s.gpu.stream) != cudaSuccess)
+      return -1;
+  }
+  const int rc = pb200_sim_run(sim, steps);
+  std::lock_guard<std::mutex> lk(s.mu);
+  if (rc != 0) return rc;
+  if (cudaEventRecord(s.gpu.ev[1], s.gpu.stream) != cudaSuccess ||
+      cudaEventSynchronize(s.gpu.ev[1]) != cudaSuccess)
+    return -1;
+  *ms = elapsed(s.gpu.ev[0], s.gpu.ev[1]);
+  return 0;
+}
+
+int pb200_sim_profile(void* sim, int enable) {
+  if (!sim) return -1;
+  auto& s = *static_cast<SimObj*>(sim);
+  std::lock_guard<std::mutex> lk(s.mu);
+  if (s.gpu.ready) {
+    cudaSetDevice(s.gpu.device);
+    cudaStreamSynchronize(s.gpu.stream);
+  }
+  s.ls.reset_profile();
+  s.ls.profiling = enable != 0;
+  return 0;
+}
+
+int pb200_sim_profile_report(void* sim, char* buf, size_t cap) {
+  if (!sim || !buf || cap < 3) return -1;
+  auto& s = *static_cast<SimObj*>(sim);
+  std::lock_guard<std::mutex> lk(s.mu);
+  if (s.gpu.ready) {
+    cudaSetDevice(s.gpu.device);
+    cudaStreamSynchronize(s.gpu.stream);
+  }
+  s.ls.collect();
+  std::string out = "[";
+  for (size_t i = 0; i < s.ls.totals.size(); ++i) {
+    char row[256];
+    const KernelTime& k = s.ls.totals[i];
+    std::snprintf(row, sizeof row, "%s{\"kernel\":\"%s\",\"launches\":%llu,\"ms\":%.6f}", i ? "," : "",
+                  k.name, static_cast<unsigned long long>(k.launches), k.ms);
+    out += row;
+  }
+  out += "]";
+  if (out.size() + 1 > cap) return -1;
+  std::memcpy(buf, out.c_str(), out.size() + 1);
+  return 0;
+}
+
+int pb200_sim_step_local(void* sim) {
+  if (!sim) return -1;
+  auto& s = *static_cast<SimObj*>(sim);
+  std::lock_guard<std::mutex> lk(s.mu);
+  if (!s.gpu.ready) {
+    set_error("pb200_sim_upload first");
+    return -1;
+  }
+  cudaSetDevice(s.gpu.device);
+  if (sim_step(s) != cudaSuccess) {
+    std::fprintf(stderr, "[physim_b200] sim step failed: %s\n", g_error);
+    return -1;
+  }
+  return 0;
+}
+
+int pb200_sim_gather_buffer(void* sim, void** dev_ptr, size_t* total_bytes, size_t* slice_offset,
+                            size_t* slice_bytes) {
+  if (!sim) return -1;
+  auto& s = *static_cast<SimObj*>(sim);
+  std::lock_guard<std::mutex> lk(s.mu);
+  if (dev_ptr) *dev_ptr = s.cur.p;
+  if (total_bytes) *total_bytes = s.n * sizeof(double4);
+  if (slice_offset) *slice_offset = s.t0 * sizeof(double4);
+  if (slice_bytes) *slice_bytes = (s.t1 - s.t0) * sizeof(double4);
+  return 0;
+}
+
+int pb200_sim_download(void* sim, Entity* state, size_t n) {
+  if (!sim || (n && !state)) return -1;
+  auto& s = *static_cast<SimObj*>(sim);
+  std::lock_guard<std::mutex> lk(s.mu);
+  if (n != s.n) {
+    set_error("pb200_sim_download: n = %zu but the simulation holds %zu bodies", n, s.n);
+    return -1;
+  }
+  if (n == 0) return 0;
+  cudaSetDevice(s.gpu.device);
+  cudaStream_t st = s.gpu.stream;
+  auto run = [&]() -> cudaError_t {
+    PB_PASS(sim_verify_tree(s));
+    PB_CUDA(cudaMemcpyAsync(s.h_pos.p, s.cur.p, n * sizeof(double4), cudaMemcpyDeviceToHost, st));
+    PB_CUDA(cudaMemcpyAsync(s.h_vel.p, s.vel.p, n * sizeof(double4), cudaMemcpyDeviceToHost, st));
+    PB_CUDA(cudaStreamSynchronize(st));
+    return cudaSuccess;
+  };
+  if (run() != cudaSuccess) {
+    std::fprintf(stderr, "[physim_b200] sim download failed: %s\n", g_error);
+    return -1;
+  }
+  const double4* p = s.h_pos.as<double4>();
+  const double4* v = s.h_vel.as<double4>();
+  const size_t b0 = s.world == 1 ? 0 : s.t0, b1 = s.world == 1 ? n : s.t1;
+  HostPool::instance().parallel_for(b1 - b0, kParallelGrain, [&](size_t b, size_t e) {
+    for (size_t i = b0 + b; i < b0 + e; ++i) {
+      state[i].x = p[i].x; state[i].y = p[i].y; state[i].z = p[i].z;
+      state[i].vx = v[i].x; state[i].vy = v[i].y; state[i].vz = v[i].z;
+    }
+  });
+  return 0;
+}
+
+int pb200_sim_last_accelerations(void* sim, Acceleration* acc, size_t n) {
+  if (!sim || (n && !acc)) return -1;
+  auto& s = *static_cast<SimObj*>(sim);
+  std::lock_guard<std::mutex> lk(s.mu);
+  if (n != s.n || !s.ws.acc.p) {
+    set_error("pb200_sim_last_accelerations: nothing evaluated or size mismatch");
+    return -1;
+  }
+  cudaSetDevice(s.gpu.device);
+  std::vector<float4> a(n);
+  if (cudaStreamSynchronize(s.gpu.stream) != cudaSuccess ||
+      cudaMemcpy(a.data(), s.ws.acc.p, n * sizeof(float4), cudaMemcpyDeviceToHost) != cudaSuccess) {
+    set_error("copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return -1;
+  }
+  for (size_t i = 0; i < n; ++i) acc[i] = Acceleration{double(a[i].x), double(a[i].y), double(a[i].z)};
+  return 0;
+}
+
+int pb200_sim_stats(void* sim, Pb200Stats* out) {
+  if (!sim || !out) return -1;
+  auto& s = *static_cast<SimObj*>(sim);
+  std::lock_guard<std::mutex> lk(s.mu);
+  if (s.gpu.ready && s.n && s.ws.acc.p) {
+    cudaSetDevice(s.gpu.device);
+    uint64_t inter = 0;
+    if (gravity_count_interactions(s.ws, s.gpu.stream, s.ls, &inter) != cudaSuccess) return -1;
+    s.stats.interactions = inter;
+    uint32_t total = 0;
+    const bool direct = s.prm.kind == PB200_SIMPLE_ASTRO || !(s.prm.theta > 0.0);
+    if (!direct) {
+      gravity_cell_total(s.ws, s.gpu.stream, &total);
+      unsigned long long bits = 0;
+      cudaMemcpy(&bits, s.ws.extent_bits.p, 8, cudaMemcpyDeviceToHost);
+      std::memcpy(&s.stats.extent, &bits, 8);
+    }
+    s.stats.n_cells = total;
+  }
+  s.stats.n_bodies = s.n;
+  s.stats.kernel_launches = s.ls.launches;
+  *out = s.stats;
+  return 0;
+}
+
+int pb200_sim_set_stream(void* sim, void* stream) {
+  if (!sim) return -1;
+  auto& s = *static_cast<SimObj*>(sim);
+  std::lock_guard<std::mutex> lk(s.mu);
+  if (s.gpu.init(s.device) != cudaSuccess) return -1;
+  cudaStreamSynchronize(s.gpu.stream);
+  if (s.gpu.own_stream && s.gpu.stream) cudaStreamDestroy(s.gpu.stream);
+  s.gpu.stream = static_cast<cudaStream_t>(stream);
+  s.gpu.own_stream = false;
+  return 0;
+}
+
+void* pb200_sim_stream(void* sim) {
+  if (!sim) return nullptr;
+  return static_cast<SimObj*>(sim)->gpu.stream;
+}
+
+double pb200_probe_fp32_tflops(void) {
+  double t = 0.0;
+  if (cudaSetDevice(g_device) != cudaSuccess || probe_fp32(&t) != cudaSuccess) return -1.0;
+  return t;
+}
+
+}  // extern "C"

@@ -1,0 +1,1013 @@
+// gravity.cu — force evaluation kernels of physim's astro / astro2 / simple_astro on sm_100a.
+//
+// Reference behaviour being reproduced (jhb123/physim v0.4.4):
+//   astro/src/transformers.rs:32-69,123-160,220-244   orchestration, skip rules, acc += f/m
+//   astro/src/octree.rs:59-215, quadtree.rs:59-194     tree topology, acceptance, octant rule
+//   astro/src/lib.rs:84-113                            force law  m_b (p_b - p_a) / (|r| (r^2 + e))
+// The pointer tree of the reference is replaced by: compare-and-halve keys (fp64, the reference's own
+// octant arithmetic) -> LSD radix sort -> DFS pre-order cell table -> bottom-up centres of mass ->
+// warp-cooperative walk with per-lane acceptance.  oracle/physim_oracle.cpp ("oracle 2") builds the
+// same table on the CPU; tests compare the two bit for bit.
+#include "common.cuh"
+
+namespace pb200 {
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr uint32_t NO_PARENT = 0xffffffffu;
+constexpr int MERGE_RUN_CAP = 1024;  // longer chains of <1e-9 neighbours are left unmerged
+
+template <int DIM>
+struct TreeDim {
+  static constexpr int LM = (DIM == 3) ? 21 : 31;  // key levels: 63 / 62 bits
+};
+
+template <int DIM>
+__device__ __forceinline__ int shared_levels(uint64_t a, uint64_t b) {
+  const uint64_t x = a ^ b;
+  if (x == 0) return TreeDim<DIM>::LM;
+  const int top = 63 - __clzll(static_cast<long long>(x));
+  return TreeDim<DIM>::LM - 1 - top / DIM;
+}
+
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
+  return v;
+}
+
+// Block-wide exclusive scan of one unsigned per thread (blockDim.x == 256). Returns the exclusive
+// prefix; *total (optional, smem-broadcast) receives the block sum.
+__device__ __forceinline__ unsigned block_exclusive_scan_256(unsigned v, unsigned* total) {
+  __shared__ unsigned warp_sums[8];
+  __shared__ unsigned block_total;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned t = __shfl_up_sync(FULL, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) warp_sums[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned w = lane < 8 ? warp_sums[lane] : 0u;
+    unsigned wi = w;
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      const unsigned t = __shfl_up_sync(FULL, wi, o);
+      if (lane >= o) wi += t;
+    }
+    if (lane < 8) warp_sums[lane] = wi - w;  // exclusive per warp
+    if (lane == 7) block_total = wi;
+  }
+  __syncthreads();
+  const unsigned r = warp_sums[warp] + incl - v;
+  if (total) *total = block_total;
+  __syncthreads();  // smem reusable by a following call
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1  extent = max_i max(|x|,|y|,|z|)                        (transformers.rs:35-40 / :126-131)
+// HBM: 32 B read per body.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) extent_kernel(const double4* __restrict__ pos, size_t n,
+                                                     unsigned long long* __restrict__ out_bits) {
+  double m = 0.0;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n;
+       i += size_t(gridDim.x) * blockDim.x) {
+    const double4 p = pos[i];
+    m = fmax(m, fabs(p.x));  // fmax drops NaN operands, like Rust's f64::max
+    m = fmax(m, fabs(p.y));
+    m = fmax(m, fabs(p.z));
+  }
+  m = warp_max(m);
+  __shared__ double s[8];
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = threadIdx.x < 8 ? s[threadIdx.x] : 0.0;
+    v = warp_max(v);
+    // non-negative doubles order like their bit patterns
+    if (threadIdx.x == 0) atomicMax(out_bits, static_cast<unsigned long long>(__double_as_longlong(v)));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2  keys: one digit (x | y<<1 | z<<2) per level from the reference's strict compare and
+//     centre ± extent/2 halving, in fp64, so every visited centre is the reference's double.
+// HBM: 32 B read, 12 B written per body.
+// ---------------------------------------------------------------------------------------------
+template <int DIM>
+__global__ void __launch_bounds__(256) encode_kernel(const double4* __restrict__ pos, size_t n,
+                                                     const unsigned long long* __restrict__ extent_bits,
+                                                     uint64_t* __restrict__ key,
+                                                     uint32_t* __restrict__ idx) {
+  const size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const double4 p = pos[i];
+  double ext = __longlong_as_double(static_cast<long long>(*extent_bits));
+  double cx = 0.0, cy = 0.0, cz = 0.0;
+  uint64_t k = 0;
+#pragma unroll
+  for (int l = 0; l < TreeDim<DIM>::LM; ++l) {
+    const double half = ext * 0.5;  // == ext / 2.0 in IEEE arithmetic
+    const bool bx = p.x > cx, by = p.y > cy;
+    unsigned digit = unsigned(bx) | (unsigned(by) << 1);
+    cx = bx ? cx + half : cx - half;
+    cy = by ? cy + half : cy - half;
+    if (DIM == 3) {
+      const bool bz = p.z > cz;
+      digit |= unsigned(bz) << 2;
+      cz = bz ? cz + half : cz - half;
+    }
+    k = (k << DIM) | digit;
+    ext = half;
+  }
+  key[i] = k;
+  idx[i] = static_cast<uint32_t>(i);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3  LSD radix sort, 8-bit digits, stable, (u64 key, u32 value) pairs.
+//     per pass: tile histogram -> per-digit scan along tiles -> ranked scatter.
+// HBM per pass per body: 8 B (hist) + 12 B + 12 B (scatter).
+// ---------------------------------------------------------------------------------------------
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_ITEMS = 16;
+constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
+
+__global__ void __launch_bounds__(SORT_THREADS) sort_tile_hist(const uint64_t* __restrict__ kin,
+                                                               size_t n, int shift,
+                                                               unsigned* __restrict__ tile_counts,
+                                                               unsigned num_tiles) {
+  __shared__ unsigned h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  const size_t base = size_t(blockIdx.x) * SORT_TILE;
+  const int lane = threadIdx.x & 31;
+#pragma unroll 4
+  for (int i = 0; i < SORT_ITEMS; ++i) {
+    const size_t g = base + size_t(i) * SORT_THREADS + threadIdx.x;
+    const bool ok = g < n;
+    const unsigned d = ok ? unsigned((kin[g] >> shift) & 255u) : 256u;
+    const unsigned peers = __match_any_sync(FULL, d);
+    if (ok && (peers & ((1u << lane) - 1u)) == 0u) atomicAdd(&h[d], unsigned(__popc(peers)));
+  }
+  __syncthreads();
+  tile_counts[size_t(threadIdx.x) * num_tiles + blockIdx.x] = h[threadIdx.x];
+}
+
+// one block per digit: exclusive scan of that digit's counts along the tiles; total -> digit_total
+__global__ void __launch_bounds__(256) sort_row_scan(unsigned* __restrict__ tile_counts,
+                                                     unsigned num_tiles,
+                                                     unsigned* __restrict__ digit_total) {
+  unsigned* row = tile_counts + size_t(blockIdx.x) * num_tiles;
+  const unsigned chunk = (num_tiles + 255u) / 256u;
+  const unsigned b = threadIdx.x * chunk;
+  const unsigned e = min(b + chunk, num_tiles);
+  unsigned sum = 0;
+  for (unsigned j = b; j < e; ++j) sum += row[j];
+  unsigned total;
+  unsigned run = block_exclusive_scan_256(sum, &total);
+  for (unsigned j = b; j < e; ++j) {
+    const unsigned c = row[j];
+    row[j] = run;
+    run += c;
+  }
+  if (threadIdx.x == 0) digit_total[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(SORT_THREADS) sort_scatter(
+    const uint64_t* __restrict__ kin, const uint32_t* __restrict__ vin, uint64_t* __restrict__ kout,
+    uint32_t* __restrict__ vout, size_t n, int shift, const unsigned* __restrict__ tile_prefix,
+    const unsigned* __restrict__ digit_total, unsigned num_tiles) {
+  __shared__ unsigned whist[8][256];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int j = tid; j < 8 * 256; j += SORT_THREADS) (&whist[0][0])[j] = 0;
+  // start of each digit's output segment
+  const unsigned dbase = block_exclusive_scan_256(digit_total[tid], nullptr);  // syncs
+  const size_t base = size_t(blockIdx.x) * SORT_TILE + size_t(warp) * 32 * SORT_ITEMS;
+
+  uint64_t k[SORT_ITEMS];
+  uint32_t v[SORT_ITEMS];
+  unsigned rank[SORT_ITEMS];
+#pragma unroll
+  for (int i = 0; i < SORT_ITEMS; ++i) {
+    const size_t g = base + size_t(i) * 32 + lane;
+    const bool ok = g < n;
+    k[i] = ok ? kin[g] : ~0ull;
+    v[i] = ok ? vin[g] : 0u;
+  }
+  // stable rank inside the warp's contiguous segment: items in (i, lane) order == memory order
+#pragma unroll
+  for (int i = 0; i < SORT_ITEMS; ++i) {
+    const bool ok = (base + size_t(i) * 32 + lane) < n;
+    const unsigned d = ok ? unsigned((k[i] >> shift) & 255u) : 256u;
+    const unsigned peers = __match_any_sync(FULL, d);
+    const unsigned before = ok ? whist[warp][d] : 0u;
+    __syncwarp();
+    const unsigned r = __popc(peers & ((1u << lane) - 1u));
+    if (ok && r == 0u) whist[warp][d] = before + unsigned(__popc(peers));
+    __syncwarp();
+    rank[i] = before + r;
+  }
+  __syncthreads();
+  {  // thread = digit: turn per-warp counts into global offsets
+    unsigned run = dbase + tile_prefix[size_t(tid) * num_tiles + blockIdx.x];
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const unsigned c = whist[w][tid];
+      whist[w][tid] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < SORT_ITEMS; ++i) {
+    const bool ok = (base + size_t(i) * 32 + lane) < n;
+    if (ok) {
+      const unsigned d = unsigned((k[i] >> shift) & 255u);
+      const unsigned dst = whist[warp][d] + rank[i];
+      kout[dst] = k[i];
+      vout[dst] = v[i];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic exclusive scan of u32[n] -> out[n+1] (out[n] = total); 3 launches
+// ---------------------------------------------------------------------------------------------
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = 256 * SCAN_ITEMS;
+
+__global__ void __launch_bounds__(256) scan_tile_sums(const uint32_t* __restrict__ in, size_t n,
+                                                      uint32_t* __restrict__ sums) {
+  const size_t base = size_t(blockIdx.x) * SCAN_TILE + size_t(threadIdx.x) * SCAN_ITEMS;
+  unsigned s = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i)
+    if (base + i < n) s += in[base + i];
+  unsigned total;
+  block_exclusive_scan_256(s, &total);
+  if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+
+// single block: exclusive scan of sums[m] in place
+__global__ void __launch_bounds__(256) scan_sums(uint32_t* __restrict__ sums, unsigned m) {
+  const unsigned chunk = (m + 255u) / 256u;
+  const unsigned b = threadIdx.x * chunk, e = min(b + chunk, m);
+  unsigned s = 0;
+  for (unsigned j = b; j < e; ++j) s += sums[j];
+  unsigned run = block_exclusive_scan_256(s, nullptr);
+  for (unsigned j = b; j < e; ++j) {
+    const unsigned c = sums[j];
+    sums[j] = run;
+    run += c;
+  }
+}
+
+__global__ void __launch_bounds__(256) scan_apply(const uint32_t* __restrict__ in, size_t n,
+                                                  const uint32_t* __restrict__ sums,
+                                                  uint32_t* __restrict__ out) {
+  const size_t base = size_t(blockIdx.x) * SCAN_TILE + size_t(threadIdx.x) * SCAN_ITEMS;
+  unsigned v[SCAN_ITEMS];
+  unsigned s = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) {
+    v[i] = (base + i < n) ? in[base + i] : 0u;
+    s += v[i];
+  }
+  unsigned run = block_exclusive_scan_256(s, nullptr) + sums[blockIdx.x];
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) {
+    if (base + i < n) out[base + i] = run;
+    run += v[i];
+    if (base + i + 1 == n) out[n] = run;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4  gather sorted {x,y,z,m}.  HBM: 4 + 32 read, 32 written per body.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gather_kernel(const double4* __restrict__ pos,
+                                                     const uint32_t* __restrict__ perm, size_t n,
+                                                     double4* __restrict__ spos) {
+  const size_t s = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  if (s < n) spos[s] = pos[perm[s]];
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5  merged-leaf runs and the number of cells each sorted body heads.
+//     a = levels shared with the previous unit, b = with the next; a unit heads the cells at
+//     levels a+1 .. max(a,b)+1 (the last one is its leaf).  See oracle 2 for the rule's derivation.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool close_1e9(const double4& u, const double4& v) {
+  return fabs(u.x - v.x) < 1e-9 && fabs(u.y - v.y) < 1e-9 && fabs(u.z - v.z) < 1e-9;
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(256) unit_kernel(const uint64_t* __restrict__ key,
+                                                   const double4* __restrict__ sp, size_t n,
+                                                   uchar2* __restrict__ ab,
+                                                   uint32_t* __restrict__ cnt) {
+  constexpr int LM = TreeDim<DIM>::LM;
+  const size_t s = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  if (s >= n) return;
+  const double4 me = sp[s];
+  const uint64_t kme = key[s];
+  const bool cp = s > 0 && close_1e9(sp[s - 1], me);
+  const bool cn = s + 1 < n && close_1e9(me, sp[s + 1]);
+  int a = s > 0 ? shared_levels<DIM>(key[s - 1], kme) : -1;
+  int b = s + 1 < n ? shared_levels<DIM>(kme, key[s + 1]) : -1;
+  bool head = true;
+  if (cp || cn) {
+    size_t r0 = s, r1 = s;
+    int inner = LM + 1;
+    bool capped = false;
+    int steps = 0;
+    while (r0 > 0 && close_1e9(sp[r0 - 1], sp[r0])) {
+      inner = min(inner, shared_levels<DIM>(key[r0 - 1], key[r0]));
+      --r0;
+      if (++steps > MERGE_RUN_CAP) { capped = true; break; }
+    }
+    steps = 0;
+    while (!capped && r1 + 1 < n && close_1e9(sp[r1], sp[r1 + 1])) {
+      inner = min(inner, shared_levels<DIM>(key[r1], key[r1 + 1]));
+      ++r1;
+      if (++steps > MERGE_RUN_CAP) { capped = true; break; }
+    }
+    if (!capped && (r1 - r0 + 1) <= size_t(MERGE_RUN_CAP)) {
+      const int ra = r0 > 0 ? shared_levels<DIM>(key[r0 - 1], key[r0]) : -1;
+      const int rb = r1 + 1 < n ? shared_levels<DIM>(key[r1], key[r1 + 1]) : -1;
+      if (inner >= min(max(ra, rb) + 1, LM)) {
+        head = (s == r0);
+        a = ra;
+        b = rb;
+      }
+    }
+  }
+  ab[s] = make_uchar2(static_cast<unsigned char>(a + 1), static_cast<unsigned char>(b + 1));
+  cnt[s] = head ? unsigned(max(0, b - a) + 1) : 0u;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K6  cell table in DFS pre-order (children in ascending digit order).
+//     cell(head s, level l) = cell_start[s] + (l - (a_s + 1)).
+// ---------------------------------------------------------------------------------------------
+struct CellArrays {
+  uint8_t* level;
+  uint32_t* head;
+  uint32_t* count;
+  uint32_t* skip;
+  uint32_t* parent;
+  uint32_t* arrived;
+  double4* centre_ext;  // {cx, cy, cz, half-width}
+  double4* com;         // {X, Y, Z, M}
+  uint32_t capacity;
+};
+
+template <int DIM>
+__global__ void __launch_bounds__(128) fill_kernel(const uint64_t* __restrict__ key,
+                                                   const double4* __restrict__ sp,
+                                                   const uint32_t* __restrict__ perm,
+                                                   const uchar2* __restrict__ ab,
+                                                   const uint32_t* __restrict__ cell_start, size_t n,
+                                                   const unsigned long long* __restrict__ extent_bits,
+                                                   CellArrays cells) {
+  constexpr int LM = TreeDim<DIM>::LM;
+  const size_t s = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  if (s >= n) return;
+  if (cell_start[n] > cells.capacity) return;  // host grows the table and re-runs
+  const uint32_t c0 = cell_start[s];
+  if (cell_start[s + 1] == c0) return;  // not a unit head
+  const uchar2 abv = ab[s];
+  const int a = int(abv.x) - 1, b = int(abv.y) - 1;
+  const int top = a + 1, leaf_level = max(a, b) + 1;
+  size_t e_unit = s + 1;
+  while (e_unit < n && cell_start[e_unit + 1] == cell_start[e_unit]) ++e_unit;
+  const uint64_t kme = key[s];
+  const double4 me = sp[s];
+
+  // geometric centre of the level-`top` cell: replay the head's digits from the root
+  double ext = __longlong_as_double(static_cast<long long>(*extent_bits));
+  double cx = 0.0, cy = 0.0, cz = 0.0;
+  auto descend = [&](int l) {  // from level l to level l+1
+    unsigned digit;
+    if (l < LM) {
+      digit = unsigned((kme >> (DIM * (LM - 1 - l))) & ((1u << DIM) - 1u));
+    } else {  // pseudo level below the key: compare the head body itself
+      digit = unsigned(me.x > cx) | (unsigned(me.y > cy) << 1);
+      if (DIM == 3) digit |= unsigned(me.z > cz) << 2;
+    }
+    const double half = ext * 0.5;
+    cx = (digit & 1u) ? cx + half : cx - half;
+    cy = (digit & 2u) ? cy + half : cy - half;
+    if (DIM == 3) cz = (digit & 4u) ? cz + half : cz - half;
+    ext = half;
+  };
+  for (int l = 0; l < top; ++l) descend(l);
+
+  // parent of the top cell
+  uint32_t parent_of_top = NO_PARENT;
+  if (top > 0) {
+    const int pl = top - 1;  // parent level, <= LM
+    const int shift = DIM * (LM - pl);
+    // first sorted body h sharing pl levels with s: gallop backwards, then bisect
+    auto same = [&](size_t j) {
+      return shift >= 64 ? true : ((key[j] >> shift) == (kme >> shift));
+    };
+    size_t lo = s, step = 1;  // invariant: same(lo)
+    size_t bad = size_t(-1);  // highest known index with !same (or -1)
+    while (true) {
+      if (lo == 0) break;
+      const size_t probe = lo >= step ? lo - step : 0;
+      if (same(probe)) {
+        lo = probe;
+        step <<= 1;
+      } else {
+        bad = probe;
+        break;
+      }
+    }
+    if (bad != size_t(-1)) {
+      size_t l2 = bad, h2 = lo;  // !same(l2), same(h2)
+      while (h2 - l2 > 1) {
+        const size_t mid = l2 + (h2 - l2) / 2;
+        if (same(mid)) h2 = mid; else l2 = mid;
+      }
+      lo = h2;
+    }
+    const size_t h = lo;
+    const int ah = int(ab[h].x) - 1;
+    parent_of_top = cell_start[h] + uint32_t(pl - (ah + 1));
+  }
+
+  for (int lev = top; lev <= leaf_level; ++lev) {
+    const uint32_t c = c0 + uint32_t(lev - top);
+    size_t e;
+    if (lev == leaf_level) {
+      e = e_unit;
+    } else {
+      // end of the run of bodies sharing `lev` levels with s: gallop forward from the unit end
+      const int shift = DIM * (LM - lev);  // lev <= LM here
+      auto same = [&](size_t j) {
+        return shift >= 64 ? true : ((key[j] >> shift) == (kme >> shift));
+      };
+      size_t lo = e_unit - 1, step = 1;  // same(lo)
+      size_t bad = n;                    // lowest known index with !same (or n)
+      while (true) {
+        const size_t probe = lo + step;
+        if (probe >= n) break;
+        if (same(probe)) {
+          lo = probe;
+          step <<= 1;
+        } else {
+          bad = probe;
+          break;
+        }
+      }
+      if (bad == n && lo + 1 < n) {  // ran off the end while galloping: bisect (lo, n)
+        size_t l2 = lo, h2 = n;      // same(l2), "!same"(h2 = n sentinel)
+        while (h2 - l2 > 1) {
+          const size_t mid = l2 + (h2 - l2) / 2;
+          if (same(mid)) l2 = mid; else h2 = mid;
+        }
+        e = h2;
+      } else if (bad == n) {
+        e = n;
+      } else {
+        size_t l2 = lo, h2 = bad;
+        while (h2 - l2 > 1) {
+          const size_t mid = l2 + (h2 - l2) / 2;
+          if (same(mid)) l2 = mid; else h2 = mid;
+        }
+        e = h2;
+      }
+    }
+    cells.level[c] = static_cast<uint8_t>(lev);
+    cells.head[c] = static_cast<uint32_t>(s);
+    cells.count[c] = static_cast<uint32_t>(e - s);
+    cells.skip[c] = cell_start[e];
+    cells.parent[c] = (lev == top) ? parent_of_top : c - 1;
+    cells.arrived[c] = 0u;
+    cells.centre_ext[c] = make_double4(cx, cy, cz, ext);
+    if (lev == leaf_level) {
+      // merged leaf: masses add, the member inserted last (largest original index) keeps its place
+      double m = 0.0;
+      size_t newest = s;
+      uint32_t newest_idx = perm[s];
+      for (size_t j = s; j < e_unit; ++j) {
+        m += sp[j].w;
+        const uint32_t pj = perm[j];
+        if (pj > newest_idx) { newest_idx = pj; newest = j; }
+      }
+      const double4 q = sp[newest];
+      cells.com[c] = make_double4(q.x, q.y, q.z, m);
+    } else {
+      descend(lev);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K7  bottom-up masses and centres of mass.  One thread per leaf climbs; the child that completes
+//     a cell (arrived bodies == cell bodies) sums the children in pre-order and continues upward.
+//     (reference: incremental pairwise update, octree.rs:83-88 / lib.rs:40-50 — same value up to
+//     fp64 rounding; zero-mass cells, where the reference panics, fall back to the geometric centre)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double4 ld_cg_double4(const double4* p) {
+  const double2 lo = __ldcg(reinterpret_cast<const double2*>(p));
+  const double2 hi = __ldcg(reinterpret_cast<const double2*>(p) + 1);
+  return make_double4(lo.x, lo.y, hi.x, hi.y);
+}
+
+__global__ void __launch_bounds__(128) com_kernel(const uint32_t* __restrict__ cell_start, size_t n,
+                                                  CellArrays cells) {
+  const size_t s = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  if (s >= n) return;
+  if (cell_start[n] > cells.capacity) return;
+  if (cell_start[s + 1] == cell_start[s]) return;
+  uint32_t c = cell_start[s + 1] - 1;  // this unit's leaf
+  while (true) {
+    const uint32_t p = cells.parent[c];
+    if (p == NO_PARENT) break;
+    const uint32_t mine = cells.count[c];
+    __threadfence();  // publish com[c] before announcing it
+    const uint32_t old = atomicAdd(&cells.arrived[p], mine);
+    if (old + mine != cells.count[p]) break;
+    __threadfence();
+    double m = 0.0, sx = 0.0, sy = 0.0, sz = 0.0;
+    const uint32_t end = cells.skip[p];
+    for (uint32_t ch = p + 1; ch < end; ch = cells.skip[ch]) {
+      const double4 q = ld_cg_double4(&cells.com[ch]);
+      m += q.w;
+      sx += q.w * q.x;
+      sy += q.w * q.y;
+      sz += q.w * q.z;
+    }
+    double4 out;
+    if (m != 0.0) {
+      out = make_double4(sx / m, sy / m, sz / m, m);
+    } else {
+      const double4 g = cells.centre_ext[p];
+      out = make_double4(g.x, g.y, g.z, 0.0);
+    }
+    cells.com[p] = out;
+    c = p;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// target lists for sharded evaluation: sorted positions whose original index is in [t0, t1)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tgt_flag_kernel(const uint32_t* __restrict__ perm, size_t n,
+                                                       uint32_t t0, uint32_t t1,
+                                                       uint32_t* __restrict__ flags) {
+  const size_t s = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  if (s < n) {
+    const uint32_t i = perm[s];
+    flags[s] = (i >= t0 && i < t1) ? 1u : 0u;
+  }
+}
+__global__ void __launch_bounds__(256) tgt_scatter_kernel(const uint32_t* __restrict__ flags,
+                                                          const uint32_t* __restrict__ offs, size_t n,
+                                                          uint32_t* __restrict__ list) {
+  const size_t s = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  if (s < n && flags[s]) list[offs[s]] = static_cast<uint32_t>(s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K8  Barnes-Hut walk.  One warp = 32 Morton-consecutive targets.  Control flow is warp-uniform
+//     (the warp visits cell c = min over lanes of the next cell each lane needs), decisions are
+//     per lane, so every target gets exactly the reference's interaction list
+//     (octree.rs:130-158: accept iff half_width / |p − centre| < theta, leaves always).
+//     Acceptance and p_b − p_a are evaluated in fp64 (a heavy body inside an accepted cell sits
+//     ~1e-7 from that cell's centre of mass); the force law runs in fp32.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float rsqrt_approx(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ bool accept_cell(double px, double py, double pz, const double4& ce,
+                                            double theta, double theta2) {
+  if (!(theta > 0.0)) return false;  // half_width / r >= 0 is never < theta <= 0
+  const double ax = px - ce.x, ay = py - ce.y, az = pz - ce.z;
+  const double d2 = ax * ax + ay * ay + az * az;
+  const double lhs = ce.w * ce.w, rhs = theta2 * d2;
+  if (fabs(lhs - rhs) > 1e-12 * fmax(lhs, rhs)) return lhs < rhs;
+  // borderline: the reference's own expression, operation for operation (no contraction)
+  const double e2 = __dadd_rn(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)), __dmul_rn(az, az));
+  const double r = __dsqrt_rn(e2);
+  return __ddiv_rn(ce.w, r) < theta;
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(256) walk_kernel(const double4* __restrict__ sp,
+                                                   const uint32_t* __restrict__ perm,
+                                                   const uint8_t* __restrict__ fixed,
+                                                   const uint32_t* __restrict__ tgt_list,
+                                                   size_t n_targets, const uint32_t* __restrict__ cell_start,
+                                                   size_t n, CellArrays cells, double theta, float easing,
+                                                   float tiny, float4* __restrict__ acc) {
+  const uint32_t total = cell_start[n];
+  if (total > cells.capacity) return;
+  const size_t t = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  bool active = t < n_targets;
+  uint32_t s = 0, orig = 0;
+  double px = 0.0, py = 0.0, pz = 0.0;
+  if (active) {
+    s = tgt_list ? tgt_list[t] : static_cast<uint32_t>(t);
+    orig = perm[s];
+    const double4 p = sp[s];
+    px = p.x; py = p.y; pz = p.z;
+    if (fixed[orig]) active = false;  // transformers.rs:139-141
+  }
+  const double theta2 = theta * theta;
+  float fx = 0.f, fy = 0.f, fz = 0.f;
+  uint32_t inter = 0;
+  uint32_t next = active ? 0u : total;
+  while (true) {
+    const uint32_t c = __reduce_min_sync(FULL, next);
+    if (c >= total) break;
+    const double4 ce = cells.centre_ext[c];
+    const double4 cm = cells.com[c];
+    const uint32_t sk = cells.skip[c];
+    if (next == c) {
+      const bool leaf = (sk == c + 1u);
+      if (leaf || accept_cell(px, py, pz, ce, theta, theta2)) {
+        const float dx = static_cast<float>(cm.x - px);
+        const float dy = static_cast<float>(cm.y - py);
+        const float dz = static_cast<float>(cm.z - pz);
+        float r2 = fmaf(dx, dx, tiny);  // tiny keeps r = 0 (self / coincident: skipped by the
+        r2 = fmaf(dy, dy, r2);          // reference, transformers.rs:145-147) finite: w·0 = 0
+        r2 = fmaf(dz, dz, r2);
+        const float sft = r2 + easing;
+        const float w = rsqrt_approx(r2 * sft * sft);  // 1 / (|r| (r² + e))
+        const float mw = static_cast<float>(cm.w) * w;
+        fx = fmaf(mw, dx, fx);
+        fy = fmaf(mw, dy, fy);
+        fz = fmaf(mw, dz, fz);
+        ++inter;
+        next = sk;
+      } else {
+        next = c + 1u;
+      }
+    }
+  }
+  if (t < n_targets) {
+    // a_i = f/m_a: a massless target is 0/0 = NaN in the reference (transformers.rs:154-158)
+    if (active && sp[s].w == 0.0) fx = fy = fz = __int_as_float(0x7fc00000);
+    acc[orig] = make_float4(fx, fy, fz, __uint_as_float(inter));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K9  tiled direct sum (simple_astro, and astro/astro2 with theta <= 0 where no cell is ever
+//     accepted).  FP32 FMA-pipe bound: 13 FP32 instructions + 1 MUFU.RSQ per interaction
+//     (19 flop).  Sources are staged through shared memory and broadcast to the warp; each thread
+//     keeps T targets in registers.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) to_float4_kernel(const double4* __restrict__ pos, size_t n,
+                                                        float4* __restrict__ out) {
+  const size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  if (i < n) {
+    const double4 p = pos[i];
+    out[i] = make_float4(float(p.x), float(p.y), float(p.z), float(p.w));
+  }
+}
+
+constexpr int DIRECT_THREADS = 256;
+constexpr int DIRECT_TILE = 1024;  // sources per shared-memory tile (16 KB)
+
+template <int T>
+__global__ void __launch_bounds__(DIRECT_THREADS) direct_kernel(
+    const float4* __restrict__ src, size_t n_src, size_t src_per_split, size_t t0, size_t n_targets,
+    float easing, float tiny, float4* __restrict__ part /* [splits][n_targets] */) {
+  __shared__ float4 tile[DIRECT_TILE];
+  const size_t tbase = size_t(blockIdx.x) * (DIRECT_THREADS * T);
+  float px[T], py[T], pz[T], ax[T], ay[T], az[T];
+#pragma unroll
+  for (int k = 0; k < T; ++k) {
+    const size_t lt = tbase + size_t(k) * DIRECT_THREADS + threadIdx.x;
+    const float4 p = lt < n_targets ? src[t0 + lt] : make_float4(0.f, 0.f, 0.f, 0.f);
+    px[k] = p.x; py[k] = p.y; pz[k] = p.z;
+    ax[k] = ay[k] = az[k] = 0.f;
+  }
+  const size_t sb = size_t(blockIdx.y) * src_per_split;
+  const size_t se = min(sb + src_per_split, n_src);
+  for (size_t j0 = sb; j0 < se; j0 += DIRECT_TILE) {
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < DIRECT_TILE / DIRECT_THREADS; ++q) {
+      const size_t j = j0 + size_t(q) * DIRECT_THREADS + threadIdx.x;
+      tile[q * DIRECT_THREADS + threadIdx.x] = j < se ? src[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int j = 0; j < DIRECT_TILE; ++j) {
+      const float4 sj = tile[j];
+#pragma unroll
+      for (int k = 0; k < T; ++k) {
+        const float dx = sj.x - px[k];
+        const float dy = sj.y - py[k];
+        const float dz = sj.z - pz[k];
+        float r2 = fmaf(dx, dx, tiny);
+        r2 = fmaf(dy, dy, r2);
+        r2 = fmaf(dz, dz, r2);
+        const float sft = r2 + easing;
+        const float u = (r2 * sft) * sft;
+        const float mw = sj.w * rsqrt_approx(u);
+        ax[k] = fmaf(mw, dx, ax[k]);
+        ay[k] = fmaf(mw, dy, ay[k]);
+        az[k] = fmaf(mw, dz, az[k]);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < T; ++k) {
+    const size_t lt = tbase + size_t(k) * DIRECT_THREADS + threadIdx.x;
+    if (lt < n_targets)
+      part[size_t(blockIdx.y) * n_targets + lt] = make_float4(ax[k], ay[k], az[k], 0.f);
+  }
+}
+
+// sums the source splits in a fixed order and applies the per-target rules
+__global__ void __launch_bounds__(256) direct_finish_kernel(const float4* __restrict__ part, int splits,
+                                                            size_t t0, size_t n_targets,
+                                                            const double4* __restrict__ pos,
+                                                            const uint8_t* __restrict__ fixed,
+                                                            uint32_t n_src, float4* __restrict__ acc) {
+  const size_t lt = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  if (lt >= n_targets) return;
+  float x = 0.f, y = 0.f, z = 0.f;
+  for (int sidx = 0; sidx < splits; ++sidx) {
+    const float4 p = part[size_t(sidx) * n_targets + lt];
+    x += p.x; y += p.y; z += p.z;
+  }
+  const size_t i = t0 + lt;
+  uint32_t inter = n_src;
+  if (fixed[i]) {
+    x = y = z = 0.f;
+    inter = 0;
+  } else if (pos[i].w == 0.0) {
+    x = y = z = __int_as_float(0x7fc00000);
+  }
+  acc[i] = make_float4(x, y, z, __uint_as_float(inter));
+}
+
+__global__ void __launch_bounds__(256) count_kernel(const float4* __restrict__ acc, size_t n,
+                                                    unsigned long long* __restrict__ out) {
+  unsigned long long s = 0;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n;
+       i += size_t(gridDim.x) * blockDim.x)
+    s += __float_as_uint(acc[i].w);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+  if ((threadIdx.x & 31) == 0 && s) atomicAdd(out, s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// FP32 FFMA issue-rate probe (roofline denominator check)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ffma_probe_kernel(float* out, int iters) {
+  float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f;
+  float a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+  const float m = 0.999f, c = 1e-3f;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
+      a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+inline unsigned blocks_for(size_t n, int per_block) {
+  return static_cast<unsigned>((n + per_block - 1) / per_block);
+}
+
+// u32 exclusive scan: in[n] -> out[n+1]
+cudaError_t exclusive_scan(const uint32_t* in, uint32_t* out, size_t n, DevBuf& tmp, cudaStream_t st,
+                           LaunchStats& ls) {
+  const unsigned tiles = blocks_for(n, SCAN_TILE);
+  PB_PASS(tmp.ensure(size_t(tiles) * 4));
+  PB_LAUNCH(ls, st, "scan_tile_sums", scan_tile_sums<<<tiles, 256, 0, st>>>(in, n, tmp.as<uint32_t>()));
+  PB_LAUNCH(ls, st, "scan_sums", scan_sums<<<1, 256, 0, st>>>(tmp.as<uint32_t>(), tiles));
+  PB_LAUNCH(ls, st, "scan_apply", scan_apply<<<tiles, 256, 0, st>>>(in, n, tmp.as<uint32_t>(), out));
+  return cudaGetLastError();
+}
+
+cudaError_t radix_sort(GravityWorkspace& ws, size_t n, int key_bits, cudaStream_t st, LaunchStats& ls) {
+  const unsigned tiles = blocks_for(n, SORT_TILE);
+  PB_PASS(ws.tile_counts.ensure(size_t(tiles) * 256 * 4));
+  PB_PASS(ws.digit_base.ensure(256 * 4));
+  uint64_t* k[2] = {ws.key0.as<uint64_t>(), ws.key1.as<uint64_t>()};
+  uint32_t* v[2] = {ws.idx0.as<uint32_t>(), ws.idx1.as<uint32_t>()};
+  int cur = 0;
+  for (int shift = 0; shift < key_bits; shift += 8) {
+    PB_LAUNCH(ls, st, "sort_tile_hist", sort_tile_hist<<<tiles, SORT_THREADS, 0, st>>>(k[cur], n, shift, ws.tile_counts.as<unsigned>(), tiles));
+    PB_LAUNCH(ls, st, "sort_row_scan", sort_row_scan<<<256, 256, 0, st>>>(ws.tile_counts.as<unsigned>(), tiles, ws.digit_base.as<unsigned>()));
+    PB_LAUNCH(ls, st, "sort_scatter", sort_scatter<<<tiles, SORT_THREADS, 0, st>>>(k[cur], v[cur], k[cur ^ 1], v[cur ^ 1], n, shift,
+                                                 ws.tile_counts.as<unsigned>(),
+                                                 ws.digit_base.as<unsigned>(), tiles));
+    cur ^= 1;
+  }
+  ws.sorted_key = k[cur];
+  ws.perm = v[cur];
+  return cudaGetLastError();
+}
+
+template <int DIM>
+cudaError_t tree_evaluate(GravityWorkspace& ws, const GravityParams& prm, size_t t0, size_t t1,
+                          float easing, float tiny, cudaStream_t st, LaunchStats& ls) {
+  const size_t n = ws.n;
+  PB_PASS(ws.extent_bits.ensure(8));
+  PB_PASS(ws.key0.ensure(n * 8));
+  PB_PASS(ws.key1.ensure(n * 8));
+  PB_PASS(ws.idx0.ensure(n * 4));
+  PB_PASS(ws.idx1.ensure(n * 4));
+  PB_PASS(ws.spos64.ensure(n * sizeof(double4)));
+  PB_PASS(ws.ab.ensure(n * 2));
+  PB_PASS(ws.cell_start.ensure((n + 1) * 4));
+  PB_PASS(ws.tgt_flags.ensure(n * 4));  // also the per-body cell counts before the scan
+
+  PB_CUDA(cudaMemsetAsync(ws.extent_bits.p, 0, 8, st));
+  const unsigned nb = blocks_for(n, 256);
+  PB_LAUNCH(ls, st, "extent_kernel", extent_kernel<<<min(nb, 148u * 8u), 256, 0, st>>>(ws.pos64, n, ws.extent_bits.as<unsigned long long>()));
+  PB_LAUNCH(ls, st, "encode_kernel", encode_kernel<DIM><<<nb, 256, 0, st>>>(ws.pos64, n, ws.extent_bits.as<unsigned long long>(),
+                                         ws.key0.as<uint64_t>(), ws.idx0.as<uint32_t>()));
+  PB_PASS(radix_sort(ws, n, DIM * TreeDim<DIM>::LM, st, ls));
+  PB_LAUNCH(ls, st, "gather_kernel", gather_kernel<<<nb, 256, 0, st>>>(ws.pos64, ws.perm, n, ws.spos64.as<double4>()));
+  PB_LAUNCH(ls, st, "unit_kernel", unit_kernel<DIM><<<nb, 256, 0, st>>>(ws.sorted_key, ws.spos64.as<double4>(), n, ws.ab.as<uchar2>(),
+                                       ws.tgt_flags.as<uint32_t>()));
+  PB_PASS(exclusive_scan(ws.tgt_flags.as<uint32_t>(), ws.cell_start.as<uint32_t>(), n, ws.scan_tmp, st, ls));
+
+  // cell table capacity: grows when a previous evaluation reported more cells
+  size_t cap = ws.n_cells ? ws.n_cells + ws.n_cells / 4 + 1024 : n * 5 / 2 + 1024;
+  if (cap < ws.cell_cap) cap = ws.cell_cap;  // never shrink
+  if (cap > 0xfffffff0ull) cap = 0xfffffff0ull;
+  ws.cell_cap = cap;
+  PB_PASS(ws.c_level.ensure(cap));
+  PB_PASS(ws.c_head.ensure(cap * 4));
+  PB_PASS(ws.c_count.ensure(cap * 4));
+  PB_PASS(ws.c_skip.ensure(cap * 4));
+  PB_PASS(ws.c_parent.ensure(cap * 4));
+  PB_PASS(ws.c_arrived.ensure(cap * 4));
+  PB_PASS(ws.c_centre_ext.ensure(cap * sizeof(double4)));
+  PB_PASS(ws.c_com.ensure(cap * sizeof(double4)));
+  CellArrays cells{ws.c_level.as<uint8_t>(),   ws.c_head.as<uint32_t>(),  ws.c_count.as<uint32_t>(),
+                   ws.c_skip.as<uint32_t>(),   ws.c_parent.as<uint32_t>(), ws.c_arrived.as<uint32_t>(),
+                   ws.c_centre_ext.as<double4>(), ws.c_com.as<double4>(), static_cast<uint32_t>(cap)};
+  const unsigned nb128 = blocks_for(n, 128);
+  PB_LAUNCH(ls, st, "fill_kernel", fill_kernel<DIM><<<nb128, 128, 0, st>>>(ws.sorted_key, ws.spos64.as<double4>(), ws.perm,
+                                          ws.ab.as<uchar2>(), ws.cell_start.as<uint32_t>(), n,
+                                          ws.extent_bits.as<unsigned long long>(), cells));
+  PB_LAUNCH(ls, st, "com_kernel", com_kernel<<<nb128, 128, 0, st>>>(ws.cell_start.as<uint32_t>(), n, cells));
+
+  const uint32_t* list = nullptr;
+  const size_t n_targets = t1 - t0;
+  if (n_targets != n) {
+    PB_PASS(ws.tgt_list.ensure((n + 1) * 4 + n_targets * 4));
+    uint32_t* offs = ws.tgt_list.as<uint32_t>();
+    uint32_t* lst = offs + (n + 1);
+    PB_LAUNCH(ls, st, "tgt_flag_kernel", tgt_flag_kernel<<<nb, 256, 0, st>>>(ws.perm, n, uint32_t(t0), uint32_t(t1), ws.tgt_flags.as<uint32_t>()));
+    PB_PASS(exclusive_scan(ws.tgt_flags.as<uint32_t>(), offs, n, ws.scan_tmp, st, ls));
+    PB_LAUNCH(ls, st, "tgt_scatter_kernel", tgt_scatter_kernel<<<nb, 256, 0, st>>>(ws.tgt_flags.as<uint32_t>(), offs, n, lst));
+    list = lst;
+  }
+  if (n_targets) {
+    PB_LAUNCH(ls, st, "walk_kernel", walk_kernel<DIM><<<blocks_for(n_targets, 256), 256, 0, st>>>(
+        ws.spos64.as<double4>(), ws.perm, ws.fixed, list, n_targets, ws.cell_start.as<uint32_t>(), n,
+        cells, prm.theta, easing, tiny, ws.acc.as<float4>()));
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t direct_evaluate(GravityWorkspace& ws, size_t t0, size_t t1, float easing, float tiny,
+                            cudaStream_t st, LaunchStats& ls) {
+  const size_t n = ws.n, n_targets = t1 - t0;
+  PB_PASS(ws.src4.ensure(n * sizeof(float4)));
+  PB_LAUNCH(ls, st, "to_float4_kernel", to_float4_kernel<<<blocks_for(n, 256), 256, 0, st>>>(ws.pos64, n, ws.src4.as<float4>()));
+  if (!n_targets) return cudaGetLastError();
+  // 4 targets per thread when that still fills the chip, else 1; split the sources across
+  // blockIdx.y until there are >= 2 CTAs per SM (partials summed in a fixed order afterwards)
+  const int T = (n_targets >= size_t(148) * 2 * DIRECT_THREADS * 4) ? 4 : 1;
+  const unsigned tb = blocks_for(n_targets, DIRECT_THREADS * T);
+  unsigned splits = 1;
+  const unsigned max_splits = blocks_for(n, DIRECT_TILE);
+  while (tb * splits < 148u * 2u && splits * 2 <= max_splits && splits < 64) splits *= 2;
+  size_t per = (n + splits - 1) / splits;
+  per = (per + DIRECT_TILE - 1) / DIRECT_TILE * DIRECT_TILE;
+  splits = blocks_for(n, int(per));
+  PB_PASS(ws.acc_part.ensure(size_t(splits) * n_targets * sizeof(float4)));
+  const dim3 grid(tb, splits);
+  if (T == 4)
+    PB_LAUNCH(ls, st, "direct_kernel", direct_kernel<4><<<grid, DIRECT_THREADS, 0, st>>>(ws.src4.as<float4>(), n, per, t0, n_targets, easing,
+                                                      tiny, ws.acc_part.as<float4>()));
+  else
+    PB_LAUNCH(ls, st, "direct_kernel", direct_kernel<1><<<grid, DIRECT_THREADS, 0, st>>>(ws.src4.as<float4>(), n, per, t0, n_targets, easing,
+                                                      tiny, ws.acc_part.as<float4>()));
+  PB_LAUNCH(ls, st, "direct_finish_kernel", direct_finish_kernel<<<blocks_for(n_targets, 256), 256, 0, st>>>(
+      ws.acc_part.as<float4>(), int(splits), t0, n_targets, ws.pos64, ws.fixed, uint32_t(n),
+      ws.acc.as<float4>()));
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+void GravityWorkspace::release_all() {
+  DevBuf* all[] = {&src4, &key0, &key1, &idx0, &idx1, &spos64, &ab, &cell_start, &scan_tmp,
+                   &tile_counts, &digit_base, &extent_bits, &tgt_list, &tgt_flags, &c_level, &c_head,
+                   &c_count, &c_skip, &c_parent, &c_arrived, &c_centre_ext, &c_com, &acc, &acc_part,
+                   &counters};
+  for (DevBuf* b : all) b->release();
+}
+
+cudaError_t gravity_evaluate(GravityWorkspace& ws, const GravityParams& prm, size_t t0, size_t t1,
+                             cudaStream_t st, LaunchStats& ls, bool host_check) {
+  const size_t n = ws.n;
+  if (n == 0) return cudaSuccess;
+  if (n >= 0xfffffff0ull) {
+    set_error("n = %zu exceeds the 32-bit body index range", n);
+    return cudaErrorInvalidValue;
+  }
+  if (t1 > n) t1 = n;
+  if (t0 > t1) t0 = t1;
+  PB_PASS(ws.acc.ensure(n * sizeof(float4)));
+  if (t1 - t0 != n) PB_CUDA(cudaMemsetAsync(ws.acc.p, 0, n * sizeof(float4), st));
+  const float easing = static_cast<float>(prm.easing);
+  // r² gets `tiny` added so that r = 0 pairs give w·0 = 0 instead of inf·0; chosen so that
+  // tiny·(tiny+e)² stays a normal fp32 number
+  const float tiny = (prm.easing >= 3e-5) ? 1e-24f : 1e-11f;
+  const bool direct = prm.kind == PB200_SIMPLE_ASTRO || !(prm.theta > 0.0);
+  if (direct) {
+    ws.n_cells = 0;
+    return direct_evaluate(ws, t0, t1, easing, tiny, st, ls);
+  }
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    cudaError_t e = prm.kind == PB200_ASTRO ? tree_evaluate<2>(ws, prm, t0, t1, easing, tiny, st, ls)
+                                            : tree_evaluate<3>(ws, prm, t0, t1, easing, tiny, st, ls);
+    if (e != cudaSuccess) return e;
+    if (!host_check) return cudaSuccess;  // caller polls gravity_cell_total() later
+    // the only host read of the build: the cell total (also detects table overflow)
+    uint32_t total = 0;
+    PB_PASS(gravity_cell_total(ws, st, &total));
+    if (total <= ws.cell_cap) return cudaSuccess;
+    // overflow: every tree kernel bailed out; capacity now follows n_cells, run again
+  }
+  set_error("cell table overflow persisted after regrowing");
+  return cudaErrorUnknown;
+}
+
+cudaError_t gravity_cell_total(GravityWorkspace& ws, cudaStream_t st, uint32_t* total) {
+  *total = 0;
+  if (ws.n == 0 || !ws.cell_start.p) return cudaSuccess;
+  PB_CUDA(cudaMemcpyAsync(total, ws.cell_start.as<uint32_t>() + ws.n, 4, cudaMemcpyDeviceToHost, st));
+  PB_CUDA(cudaStreamSynchronize(st));
+  ws.n_cells = *total;
+  return cudaSuccess;
+}
+
+cudaError_t gravity_count_interactions(GravityWorkspace& ws, cudaStream_t st, LaunchStats& ls,
+                                       uint64_t* out) {
+  *out = 0;
+  if (ws.n == 0) return cudaSuccess;
+  PB_PASS(ws.counters.ensure(8));
+  PB_CUDA(cudaMemsetAsync(ws.counters.p, 0, 8, st));
+  PB_LAUNCH(ls, st, "count_kernel", count_kernel<<<148 * 4, 256, 0, st>>>(ws.acc.as<float4>(), ws.n, ws.counters.as<unsigned long long>()));
+  unsigned long long h = 0;
+  PB_CUDA(cudaMemcpyAsync(&h, ws.counters.p, 8, cudaMemcpyDeviceToHost, st));
+  PB_CUDA(cudaStreamSynchronize(st));
+  *out = h;
+  return cudaSuccess;
+}
+
+cudaError_t probe_fp32(double* tflops) {
+  float* d = nullptr;
+  const int blocks = 148 * 8, iters = 4096;
+  PB_CUDA(cudaMalloc(&d, size_t(blocks) * 256 * 4));
+  cudaEvent_t e0, e1;
+  PB_CUDA(cudaEventCreate(&e0));
+  PB_CUDA(cudaEventCreate(&e1));
+  ffma_probe_kernel<<<blocks, 256>>>(d, 64);  // warm-up
+  PB_CUDA(cudaEventRecord(e0));
+  ffma_probe_kernel<<<blocks, 256>>>(d, iters);
+  PB_CUDA(cudaEventRecord(e1));
+  PB_CUDA(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  PB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  const double flops = double(blocks) * 256.0 * iters * 16.0 * 8.0 * 2.0;
+  *tflops = flops / (ms * 1e-3) / 1e12;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  return cudaSuccess;
+}
+
+}  // namespace pb200

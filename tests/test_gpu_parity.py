@@ -1,0 +1,205 @@
+"""GPU parity: the CUDA path, called through the plugin C ABI (`*_get_api` vtables), against the
+CPU oracle on identical seeded inputs.
+
+Bars (BASELINE.json north_star):
+  * keys, sort permutation, cell table (level, head, count, skip, parent, geometric centres and
+    half-widths): bit-exact vs oracle 2, which tests/test_oracle_table.py ties to the reference's
+    pointer tree;
+  * per-target interaction counts: exact vs oracle 1 (the walk takes the reference's decisions);
+  * accelerations (fp32 on device vs fp64 reference): relative error median <= 1e-5, p99 <= 1e-3.
+"""
+import numpy as np
+import pytest
+
+from oracle import binding as ob
+from physim_b200 import api
+from physim_b200 import generators as gen
+from physim_b200.entity import accelerations, entities
+from tests.util import assert_acc_parity, rel_err, vec
+
+pytestmark = pytest.mark.gpu
+
+DIM = {"astro": 2, "astro2": 3}
+
+
+def with_merges(seed):
+    rng = np.random.default_rng(seed)
+    e = gen.cube(500, seed=seed)
+    dup = e[:40].copy()
+    near = e[40:80].copy()
+    near["x"] += 3e-10
+    far = e[80:120].copy()
+    far["y"] += 2e-5
+    out = np.concatenate([e, dup, near, far])
+    rng.shuffle(out)
+    return out
+
+
+def bucket_twins(seed):
+    s = gen.cube(400, seed=seed)
+    twin = s[:20].copy()
+    twin["x"] += 2e-8
+    return np.concatenate([s, twin])
+
+
+TREE_CASES = {
+    "cube20k": lambda: gen.readme_pipeline(20_000, seed=3),
+    "merges": lambda: with_merges(7),
+    "bucket": lambda: bucket_twins(9),
+    "single": lambda: gen.star(x=0.3, y=-0.2, z=0.1, mass=2.0),
+    "pair": lambda: np.concatenate([gen.star(x=1.0, mass=1.0), gen.star(x=-1.0, mass=3.0)]),
+    "coincident10": lambda: np.concatenate([gen.star(mass=1.0)] * 10),
+    "solar": lambda: gen.solar(),
+    "ragged4097": lambda: gen.cube(4097, seed=21),
+}
+
+
+@pytest.mark.parametrize("name", ["astro2", "astro"])
+@pytest.mark.parametrize("case", sorted(TREE_CASES))
+def test_tree_is_bit_exact(name, case):
+    s = TREE_CASES[case]()
+    if name == "astro" and case == "solar":
+        s = s.copy()
+        s["x"] += 1e-3 * np.arange(len(s))  # moons share (x, y) structure; keep the quadtree finite
+    el = api.TransformElement(name, theta=1.0, e=0.5)
+    el.transform(s)
+    t = el.debug_tree()
+    o = ob.CellTable(DIM[name], s)
+    assert t["extent"] == o.extent
+    assert np.array_equal(t["key"], o.key)
+    assert np.array_equal(t["perm"], o.perm)
+    assert np.array_equal(t["cell_start"], o.cell_start)
+    assert len(t["level"]) == o.n_cells
+    for k in ("level", "head", "count", "skip", "parent"):
+        assert np.array_equal(t[k], getattr(o, k)), k
+    assert np.array_equal(t["centre_ext"], o.centre_ext)          # identical doubles
+    leaf = o.skip == np.arange(o.n_cells) + 1
+    assert np.array_equal(t["com_mass"][leaf], o.com_mass[leaf])  # leaves: the body itself
+    np.testing.assert_allclose(t["com_mass"][:, 3], o.com_mass[:, 3], rtol=1e-13)
+    np.testing.assert_allclose(t["com_mass"][:, :3], o.com_mass[:, :3], rtol=0, atol=1e-12 * max(o.extent, 1e-300))
+
+
+@pytest.mark.parametrize("name", ["astro2", "astro"])
+@pytest.mark.parametrize("theta", [0.5, 0.7, 1.0, 1.3, 1.5])
+def test_barnes_hut_matches_reference(name, theta):
+    s = gen.readme_pipeline(20_000, seed=5)
+    s["fixed"][17] = True
+    el = api.TransformElement(name, theta=theta, e=0.5)
+    acc = el.transform(s)
+    ref, cnt = ob.transform(name, s, theta, 0.5, counts=True)
+    t = el.debug_tree()
+    assert np.array_equal(t["counts"], cnt)               # the reference's interaction lists
+    assert el.stats()["interactions"] == int(cnt.sum())
+    assert acc["x"][17] == 0.0 and acc["y"][17] == 0.0    # fixed body untouched
+    free = ~s["fixed"]
+    assert_acc_parity(acc, ref, free)
+
+
+def test_readme_config_c1():
+    """BASELINE config 1: cube n=100000 seed=1 spin=1000 + 2 stars ! astro2 theta=1.5 e=0.5."""
+    s = gen.readme_pipeline(100_000, seed=1, spin=1000.0)
+    el = api.TransformElement("astro2", theta=1.5, e=0.5)
+    acc = el.transform(s)
+    ref, cnt = ob.transform("astro2", s, 1.5, 0.5, counts=True)
+    assert np.array_equal(el.debug_tree()["counts"], cnt)
+    r = assert_acc_parity(acc, ref)
+    assert r.max() < 1e-2
+
+
+@pytest.mark.parametrize("case", ["solar", "cube4096", "clumpy"])
+def test_direct_sum_matches_reference(case):
+    if case == "solar":
+        s, e = gen.solar(), 0.1                     # BASELINE config 2 (example_pipelines/solar.toml)
+    elif case == "cube4096":
+        s, e = gen.readme_pipeline(4094, seed=2), 0.5
+    else:
+        s, e = gen.cube(3000, seed=8, size=50.0), 0.0
+    el = api.TransformElement("simple_astro", e=e)
+    acc = el.transform(s)
+    ref = ob.transform("simple_astro", s, e=e)
+    free = ~s["fixed"]
+    assert_acc_parity(acc, ref, free)
+    assert not vec(acc)[s["fixed"]].any()
+    assert el.stats()["interactions"] == int(free.sum()) * len(s)
+
+
+@pytest.mark.parametrize("name", ["astro2", "astro"])
+def test_nonpositive_theta_is_direct_sum(name):
+    s = gen.readme_pipeline(3000, seed=12)
+    ref = ob.transform(name, s, 0.0, 0.5)
+    for theta in (0.0, -0.1):
+        acc = api.TransformElement(name, theta=theta, e=0.5).transform(s)
+        assert_acc_parity(acc, ref)
+
+
+def test_direct_sum_sampled_at_c1_size():
+    """N = 100 002 all-pairs on the GPU, checked on a 256-target sample of the O(N²) oracle."""
+    s = gen.readme_pipeline(100_000, seed=1)
+    acc = api.TransformElement("simple_astro", e=0.5).transform(s)
+    pick = np.random.default_rng(0).choice(len(s), 256, replace=False)
+    pick.sort()
+    ref = accelerations(len(s))
+    for i in pick:
+        ob.direct_range(s, 0.5, int(i), int(i) + 1, acc=ref)
+    assert_acc_parity(acc[pick], ref[pick])
+
+
+def test_accumulates_and_respects_fixed_and_massless():
+    s = gen.cube(2000, seed=4)
+    s["fixed"][::7] = True
+    s["mass"][5] = 0.0                 # massless free target: f/m = 0/0 = NaN in the reference
+    base = accelerations(len(s))
+    base["x"], base["y"], base["z"] = 1.0, -2.0, 3.0
+    for name, kw in (("astro2", dict(theta=0.7, e=0.5)), ("simple_astro", dict(e=0.5)), ("astro", dict(theta=1.0))):
+        acc = api.TransformElement(name, **kw).transform(s, base.copy())
+        ref = ob.transform(name, s, kw.get("theta", 1.0), kw.get("e", 1.0), acc=base.copy())
+        fx = s["fixed"]
+        assert np.array_equal(vec(acc)[fx], vec(base)[fx])          # untouched
+        assert np.isnan(acc["x"][5]) and np.isnan(ref["x"][5])
+        ok = ~fx
+        ok[5] = False
+        shifted = accelerations(len(s))
+        sref = accelerations(len(s))
+        for k in "xyz":
+            shifted[k] = acc[k] - base[k]
+            sref[k] = ref[k] - base[k]
+        assert_acc_parity(shifted, sref, ok, median=1e-4, p99=1e-2)  # looser: cancellation with base
+
+
+def test_transform_twice_same_object_and_changing_n():
+    el = api.TransformElement("astro2", theta=1.0, e=0.5)
+    for n in (5000, 1200, 9000):
+        s = gen.cube(n, seed=n)
+        a1 = el.transform(s)
+        a2 = el.transform(s)
+        assert np.array_equal(vec(a1), vec(a2))                    # deterministic
+        assert_acc_parity(a1, ob.transform("astro2", s, 1.0, 0.5))
+
+
+def test_momentum_conservation_direct_sum():
+    """Newton's third law as a size-independent property: sum_i m_i a_i ~ 0 for all-free bodies."""
+    s = gen.cube(20_000, seed=6)
+    acc = api.TransformElement("simple_astro", e=0.5).transform(s)
+    p = (s["mass"][:, None] * vec(acc)).sum(axis=0)
+    scale = (s["mass"][:, None] * np.abs(vec(acc))).sum()
+    assert np.abs(p).max() / scale < 1e-5
+
+
+def test_headline_size_properties():
+    """BASELINE config 3 size (1 000 004 bodies, astro theta=1.3): properties that need no oracle
+    run at this size, plus the oracle itself (a few seconds)."""
+    s = gen.headline_pipeline(1_000_000, seed=1)
+    el = api.TransformElement("astro", theta=1.3)
+    acc = el.transform(s)
+    t = el.debug_tree()
+    n = len(s)
+    assert (np.diff(t["key"].astype(np.uint64).view(np.int64)) >= 0).all()      # sorted
+    assert np.array_equal(np.sort(t["perm"]), np.arange(n, dtype=np.uint32))    # a permutation
+    leaf = t["skip"] == np.arange(len(t["skip"])) + 1
+    assert t["count"][leaf].sum() == n and t["count"][0] == n
+    np.testing.assert_allclose(t["com_mass"][0, 3], s["mass"].sum(), rtol=1e-12)
+    com = (s["mass"][:, None] * np.stack([s["x"], s["y"], s["z"]], 1)).sum(0) / s["mass"].sum()
+    np.testing.assert_allclose(t["com_mass"][0, :3], com, atol=1e-12)
+    ref, cnt = ob.transform("astro", s, 1.3, 1.0, counts=True)
+    assert np.array_equal(t["counts"], cnt)
+    assert_acc_parity(acc, ref)

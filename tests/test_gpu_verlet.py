@@ -1,0 +1,146 @@
+"""GPU parity for the verlet step and the composed `transform ! verlet` loop."""
+import numpy as np
+import pytest
+
+from oracle import binding as ob
+from physim_b200 import api
+from physim_b200 import generators as gen
+from tests.util import assert_acc_parity, vec
+
+pytestmark = pytest.mark.gpu
+
+POS = ("x", "y", "z", "vx", "vy", "vz")
+
+
+def test_generic_step_is_bit_exact():
+    """Same accelerations in -> identical doubles out (first step, regular steps, N change)."""
+    s = gen.cube(5000, seed=4, spin=3.0)
+    s["fixed"][3] = True
+    a = np.random.default_rng(1).normal(size=(5000, 3)) * 10.0
+
+    def fn(state, acc):
+        acc["x"] += a[: len(state), 0]; acc["y"] += a[: len(state), 1]; acc["z"] += a[: len(state), 2]
+
+    g, o = api.Verlet(), ob.Verlet()
+    sg, so = s, s
+    for step in range(4):
+        sg, so = g.integrate(sg, fn, 0.125), o.integrate(so, fn, 0.125)
+        assert sg.tobytes() == so.tobytes(), f"step {step}"
+    sg, so = g.integrate(sg[:777], fn, 0.125), o.integrate(so[:777], fn, 0.125)  # N changed: first-step rule
+    assert sg.tobytes() == so.tobytes()
+
+
+def test_shm_analytic_kat():
+    """example_pipelines/shm.toml: x(t) = cos(sqrt(5) t), dt = 0.01, 3140 steps."""
+    k, dt, iters = 5.0, 0.01, 3140
+
+    def fn(state, acc):
+        for c in "xyz":
+            acc[c] += -k * state[c] / state["mass"]
+
+    st = gen.star(x=1.0, mass=1.0, radius=0.2)
+    v = api.Verlet()
+    xs = []
+    for _ in range(iters):
+        st = v.integrate(st, fn, dt)
+        xs.append(st["x"][0])
+    t = dt * np.arange(1, iters + 1)
+    assert np.abs(np.array(xs) - np.cos(np.sqrt(k) * t)).max() < 2e-3
+
+
+@pytest.mark.parametrize("name,theta,e", [("astro2", 1.5, 0.5), ("astro", 1.3, 1.0), ("simple_astro", 1.0, 0.5)])
+def test_fused_step_matches_reference_pipeline(name, theta, e):
+    s = gen.readme_pipeline(20_000, seed=2, spin=1000.0)
+    dt, steps = 1e-5, 5
+    ref, _ = ob.run_pipeline(name, s, theta, e, dt, steps)
+    el, v = api.TransformElement(name, theta=theta, e=e), api.Verlet()
+    cur = s
+    for _ in range(steps):
+        cur = v.integrate_fused(cur, el, dt)
+    for f in ("radius", "mass", "id", "fixed"):
+        assert np.array_equal(cur[f], s[f])
+    dx = np.abs(np.stack([cur[k] - ref[k] for k in "xyz"], 1)).max()
+    disp = np.abs(np.stack([ref[k] - s[k] for k in "xyz"], 1)).max()
+    assert dx <= 1e-6 * disp
+    vref = np.stack([ref[k] for k in ("vx", "vy", "vz")], 1)
+    dv = np.abs(np.stack([cur[k] for k in ("vx", "vy", "vz")], 1) - vref).max()
+    assert dv <= 1e-6 * np.abs(vref).max()
+
+
+def test_generic_step_with_plugin_transform_as_callback():
+    """The drop-in composition physim runs: verlet.integrate(acc_fn = our transform via the C ABI)."""
+    s = gen.solar()
+    el = api.TransformElement("simple_astro", e=0.1)
+    g, o = api.Verlet(), ob.Verlet()
+    sg = so = s
+    for _ in range(20):
+        sg = g.integrate(sg, lambda st, ac: el.transform(st, ac), 0.01)
+        so = o.integrate(so, lambda st, ac: ob.transform("simple_astro", st, e=0.1, acc=ac), 0.01)
+    for k in POS:
+        np.testing.assert_allclose(sg[k], so[k], rtol=1e-5, atol=1e-9)
+
+
+@pytest.mark.parametrize("name,theta,e", [("astro2", 1.5, 0.5), ("simple_astro", 1.0, 0.5)])
+def test_device_resident_sim_matches_reference_pipeline(name, theta, e):
+    s = gen.readme_pipeline(10_000, seed=9, spin=1000.0)
+    dt, steps = 1e-5, 10
+    ref, _ = ob.run_pipeline(name, s, theta, e, dt, steps)
+    sim = api.Sim(name, theta=theta, e=e, dt=dt)
+    sim.upload(s)
+    sim.run(steps)
+    out = sim.download(s.copy())
+    disp = np.abs(np.stack([ref[k] - s[k] for k in "xyz"], 1)).max()
+    assert np.abs(np.stack([out[k] - ref[k] for k in "xyz"], 1)).max() <= 1e-6 * disp
+    # sharded evaluation (world = 2) over one device: each rank's slice equals the full run's slice
+    outs = []
+    for rank in range(2):
+        sh = api.Sim(name, theta=theta, e=e, dt=dt, rank=rank, world=2)
+        sh.upload(s)
+        sh.step_local()
+        outs.append(sh.download(s.copy()))
+    one = api.Sim(name, theta=theta, e=e, dt=dt)
+    one.upload(s)
+    one.run(1)
+    full = one.download(s.copy())
+    h = len(s) // 2
+    for k in POS:
+        assert np.array_equal(outs[0][k][:h], full[k][:h])
+        assert np.array_equal(outs[1][k][h:], full[k][h:])
+
+
+def potential(s, e):
+    """Conserved potential of the reference's force law: U = -mi mj (pi/2 - atan(r/sqrt(e)))/sqrt(e)."""
+    p = np.stack([s["x"], s["y"], s["z"]], 1)
+    m = s["mass"]
+    r = np.linalg.norm(p[:, None, :] - p[None, :, :], axis=2)
+    iu = np.triu_indices(len(s), 1)
+    se = np.sqrt(e)
+    return -(m[iu[0]] * m[iu[1]] * (np.pi / 2 - np.arctan(r[iu] / se)) / se).sum()
+
+
+def energy(s, e):
+    k = 0.5 * (s["mass"] * (s["vx"] ** 2 + s["vy"] ** 2 + s["vz"] ** 2)).sum()
+    return k + potential(s, e)
+
+
+def test_energy_and_momentum_drift_solar():
+    """BASELINE config 2 (solar.toml: simple_astro e=0.1, verlet, dt=0.01), 1000 steps, sun free so
+    that momentum is conserved: GPU drift within 2x of the oracle's and small in absolute terms."""
+    s = gen.solar()
+    s["fixed"][:] = False
+    e, dt, steps = 0.1, 0.01, 1000
+    e0 = energy(s, e)
+    ref, _ = ob.run_pipeline("simple_astro", s, 1.0, e, dt, steps)
+    sim = api.Sim("simple_astro", e=e, dt=dt)
+    sim.upload(s)
+    sim.run(steps)
+    out = sim.download(s.copy())
+    d_ref = abs(energy(ref, e) - e0) / abs(e0)
+    d_gpu = abs(energy(out, e) - e0) / abs(e0)
+    assert d_gpu <= max(2.0 * d_ref, 1e-6) and d_gpu < 1e-3
+
+    def mom(x):
+        return (x["mass"][:, None] * np.stack([x["vx"], x["vy"], x["vz"]], 1)).sum(0)
+
+    scale = (s["mass"] * np.sqrt(s["vx"] ** 2 + s["vy"] ** 2 + s["vz"] ** 2)).sum()
+    assert np.abs(mom(out) - mom(s)).max() / scale < 1e-6 + 10 * np.abs(mom(ref) - mom(s)).max() / scale
