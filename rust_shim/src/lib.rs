@@ -1,0 +1,93 @@
+//! `verlet` integrator element backed by libphysim_b200.so.
+//!
+//! physim loads integrators through an `extern "Rust"` constructor returning
+//! `Box<dyn IntegratorElement>` (physim-core/src/plugin/mod.rs:92-103), so a C library cannot be an
+//! integrator plugin by itself; this crate is the thin FFI layer (bindings as cbindgen would emit
+//! them from include/physim_b200.h).  Behaviour mirrors integrators/src/verlet.rs:86-107.
+//!
+//! NOT compiled in the physim_b200 repository (no rustc in its build image).
+use std::{collections::HashMap, ffi::c_void};
+
+use physim_attribute::integrator_element;
+use physim_core::{
+    Acceleration, Entity,
+    messages::MessageClient,
+    plugin::{Element, ElementCreator, integrator::IntegratorElement},
+    register_plugin,
+};
+use serde_json::Value;
+
+register_plugin!("verlet");
+
+type AccFn = unsafe extern "C" fn(ctx: *mut c_void, state: *const Entity, n: usize, acc: *mut Acceleration);
+
+unsafe extern "C" {
+    fn pb200_verlet_create() -> *mut c_void;
+    fn pb200_verlet_destroy(v: *mut c_void);
+    fn pb200_verlet_step(
+        v: *mut c_void,
+        entities: *const Entity,
+        new_state: *mut Entity,
+        n: usize,
+        acc_fn: AccFn,
+        ctx: *mut c_void,
+        dt: f64,
+    ) -> i32;
+}
+
+#[integrator_element(
+    name = "verlet",
+    blurb = "Evaluate evolution with time using Verlet integration (B200)"
+)]
+struct Verlet {
+    handle: *mut c_void,
+}
+
+unsafe impl Send for Verlet {}
+unsafe impl Sync for Verlet {}
+
+/// Turns the `&dyn Fn(&[Entity], &mut [Acceleration])` closure (pipeline.rs:137-141) into ctx + fn ptr.
+unsafe extern "C" fn trampoline(ctx: *mut c_void, state: *const Entity, n: usize, acc: *mut Acceleration) {
+    let f = unsafe { &*(ctx as *const &dyn Fn(&[Entity], &mut [Acceleration])) };
+    let (s, a) = unsafe { (std::slice::from_raw_parts(state, n), std::slice::from_raw_parts_mut(acc, n)) };
+    f(s, a)
+}
+
+impl IntegratorElement for Verlet {
+    fn integrate(
+        &self,
+        entities: &[Entity],
+        new_state: &mut [Entity],
+        acc_fn: &dyn Fn(&[Entity], &mut [Acceleration]),
+        dt: f64,
+    ) {
+        let ctx = &acc_fn as *const &dyn Fn(&[Entity], &mut [Acceleration]) as *mut c_void;
+        let rc = unsafe {
+            pb200_verlet_step(self.handle, entities.as_ptr(), new_state.as_mut_ptr(), entities.len(), trampoline, ctx, dt)
+        };
+        if rc != 0 {
+            eprintln!("physim_b200 verlet step failed");
+            std::process::exit(1) // integrators/src/verlet.rs:98-100 exits on an unusable state too
+        }
+    }
+}
+
+impl Drop for Verlet {
+    fn drop(&mut self) {
+        unsafe { pb200_verlet_destroy(self.handle) }
+    }
+}
+
+impl MessageClient for Verlet {}
+
+impl ElementCreator for Verlet {
+    fn create_element(_: HashMap<String, Value>) -> Box<Self> {
+        Box::new(Self { handle: unsafe { pb200_verlet_create() } })
+    }
+}
+
+impl Element for Verlet {
+    fn get_property_descriptions(&self) -> Result<HashMap<String, String>, Box<dyn std::error::Error>> {
+        Ok(HashMap::from([]))
+    }
+}
