@@ -45,7 +45,7 @@ WORKLOADS = {
 
 # Algorithmic HBM bytes per body per launch for each kernel (DESIGN.md "kernels" table).
 ALG_BYTES_PER_BODY = {
-    "extent_kernel": 32, "encode_kernel": 32 + 12, "sort_tile_hist": 8, "sort_scatter": 12 + 12,
+    "extent_kernel": 32, "encode_kernel": 32 + 12, "sort_hist_all": 8, "sort_onesweep_pass": 12 + 12,
     "gather_kernel": 4 + 32 + 32, "unit_kernel": 8 + 32 + 2 + 4, "scan_tile_sums": 4, "scan_apply": 8,
     "fill_kernel": 8 + 32 + 4 + 2 + 4 + 1.5 * (1 + 5 * 4 + 32) + 32, "com_kernel": 1.5 * (32 + 32 + 12),
     "walk_kernel": 32 + 4 + 1 + 16, "verlet_kernel": 32 + 32 + 16 + 32 + 32 + 32,

@@ -185,6 +185,11 @@ int pb200_transform_debug_tree(void *obj, uint64_t *key, uint32_t *perm, uint32_
                                uint32_t *parent, double *centre_ext, double *com_mass,
                                uint32_t *counts);
 
+/* Test hook: pretend the previous evaluation saw a tree that needs only key bits >= sort_lo and
+ * n_cells_hint cells, so that the next one exercises the validate-and-retry paths (truncated sort
+ * too short, cell table too small). */
+int pb200_transform_debug_hint(void *obj, int sort_lo, size_t n_cells_hint);
+
 /* --- verlet (integrators/src/verlet.rs:86-107) -------------------------------------------
  * The Rust shim's IntegratorElement::integrate forwards here.  acc_fn has the meaning of the
  * `&dyn Fn(&[Entity], &mut [Acceleration])` closure built at pipeline.rs:137-141. */

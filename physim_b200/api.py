@@ -99,6 +99,7 @@ def lib():
     L.pb200_transform_easing.restype = dbl
     L.pb200_transform_easing.argtypes = [vp]
     L.pb200_transform_debug_tree.argtypes = [vp] * 12
+    L.pb200_transform_debug_hint.argtypes = [vp, i32, sz]
     L.pb200_verlet_create.restype = vp
     L.pb200_verlet_destroy.argtypes = [vp]
     L.pb200_verlet_step.argtypes = [vp, vp, vp, sz, ACC_FN, vp, dbl]
@@ -235,6 +236,9 @@ class TransformElement:
             raise Pb200Error(last_error())
         out["extent"] = st["extent"]
         return out
+
+    def debug_hint(self, sort_lo, n_cells_hint):
+        lib().pb200_transform_debug_hint(self._obj, int(sort_lo), int(n_cells_hint))
 
     def destroy(self):
         if getattr(self, "_obj", None):

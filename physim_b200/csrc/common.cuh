@@ -118,6 +118,10 @@ struct GravityWorkspace {
   DevBuf acc, acc_part, counters;
   size_t n_cells = 0;   // cells of the last checked evaluation
   size_t cell_cap = 0;  // capacity of the cell arrays
+  int tree_dim = 0;     // 2 / 3 after a tree build, 0 otherwise
+  int sort_lo = 0;      // lowest key bit the next sort will include (0 = all bits)
+  int last_lo = 0;      // ... that the last sort included
+  unsigned* sort_err_flag = nullptr;
   // where the sorted keys / permutation ended up after the last sort
   const uint64_t* sorted_key = nullptr;
   const uint32_t* perm = nullptr;
@@ -217,7 +221,18 @@ struct LaunchStats {
 // small; without it the caller must poll gravity_cell_total() before trusting the result.
 cudaError_t gravity_evaluate(GravityWorkspace& ws, const GravityParams& prm, size_t t0, size_t t1,
                              cudaStream_t stream, LaunchStats& ls, bool host_check = true);
-// Cell total of the last tree build (synchronises); compare with ws.cell_cap for overflow.
+// Host-side verdict on the last tree build (one small D2H + stream sync).  Also feeds the next
+// evaluation: cell-table capacity follows the observed total, the sort drops the key bits below
+// the observed tree depth (+2 levels) and is re-validated every time.
+struct TreeCheck {
+  uint32_t total = 0;       // cells
+  int deepest_shared = -1;  // deepest level shared by two sorted neighbours with different keys
+  bool overflow = false;    // total > capacity: the tree kernels bailed out
+  bool sort_short = false;  // truncated sort left ties that the dropped bits would have ordered
+  bool sort_error = false;  // look-back spin limit hit (never expected)
+  bool ok() const { return !overflow && !sort_short && !sort_error; }
+};
+cudaError_t gravity_check(GravityWorkspace& ws, cudaStream_t stream, TreeCheck* out);
 cudaError_t gravity_cell_total(GravityWorkspace& ws, cudaStream_t stream, uint32_t* total);
 // Sum of per-target interaction counters of the last evaluation (synchronises the stream).
 cudaError_t gravity_count_interactions(GravityWorkspace& ws, cudaStream_t stream, LaunchStats& ls,

@@ -288,6 +288,8 @@ struct SimObj {
   GpuContext gpu;
   GravityWorkspace ws;
   DevBuf cur, prev, vel, fixed;  // cur doubles as the all-gather buffer ({x,y,z,m} of all n bodies)
+  DevBuf ck_cur, ck_prev, ck_vel;  // checkpoint of the last verified state
+  uint64_t replays = 0;
   PinnedBuf h_pos, h_vel, h_fixed, h_acc;
   size_t n = 0, t0 = 0, t1 = 0;
   bool first = true, checked = false;
@@ -298,6 +300,7 @@ struct SimObj {
       cudaSetDevice(gpu.device);
       ws.release_all();
       cur.release(); prev.release(); vel.release(); fixed.release();
+      ck_cur.release(); ck_prev.release(); ck_vel.release();
       h_pos.release(); h_vel.release(); h_fixed.release(); h_acc.release();
       gpu.destroy();
     }
@@ -334,10 +337,10 @@ cudaError_t sim_upload(SimObj& s, const Entity* state, size_t n) {
 }
 
 // one step: forces for targets [t0,t1) from all n positions, then verlet on the owned slice
-cudaError_t sim_step(SimObj& s) {
+cudaError_t sim_step(SimObj& s, bool force_check) {
   if (s.n == 0) return cudaSuccess;
   cudaStream_t st = s.gpu.stream;
-  const bool check = !s.checked;  // size the cell table once, then stay asynchronous
+  const bool check = force_check || !s.checked;  // size the cell table once, then stay asynchronous
   PB_PASS(gravity_evaluate(s.ws, s.prm, s.t0, s.t1, st, s.ls, check));
   s.checked = true;
   const size_t nl = s.t1 - s.t0;
@@ -348,16 +351,47 @@ cudaError_t sim_step(SimObj& s) {
   return cudaSuccess;
 }
 
-cudaError_t sim_verify_tree(SimObj& s) {
-  const bool direct = s.prm.kind == PB200_SIMPLE_ASTRO || !(s.prm.theta > 0.0);
-  if (direct || s.n == 0) return cudaSuccess;
-  uint32_t total = 0;
-  PB_PASS(gravity_cell_total(s.ws, s.gpu.stream, &total));
-  if (total > s.ws.cell_cap) {
-    s.checked = false;  // next step re-sizes the table
-    set_error("cell table overflow during an unchecked step (%u cells > capacity %zu): state invalid",
-              total, s.ws.cell_cap);
-    return cudaErrorUnknown;
+bool sim_is_direct(const SimObj& s) {
+  return s.prm.kind == PB200_SIMPLE_ASTRO || !(s.prm.theta > 0.0);
+}
+
+// `steps` steps back to back.  Tree builds run unchecked (no host sync) in chunks of up to 32 steps;
+// each chunk starts from a device-side checkpoint and is verified at its end (cell-table capacity,
+// truncated-sort validity).  A chunk that fails verification is restored and replayed with a
+// host check after every build, so the result never depends on an unverified tree.
+cudaError_t sim_run_steps(SimObj& s, size_t steps) {
+  if (s.n == 0) return cudaSuccess;
+  cudaStream_t st = s.gpu.stream;
+  if (sim_is_direct(s)) {
+    for (size_t i = 0; i < steps; ++i) PB_PASS(sim_step(s, false));
+    return cudaSuccess;
+  }
+  const size_t bytes = s.n * sizeof(double4);
+  while (steps) {
+    const size_t chunk = steps < 32 ? steps : 32;
+    PB_PASS(s.ck_cur.ensure(bytes));
+    PB_PASS(s.ck_prev.ensure(bytes));
+    PB_PASS(s.ck_vel.ensure(bytes));
+    PB_CUDA(cudaMemcpyAsync(s.ck_cur.p, s.cur.p, bytes, cudaMemcpyDeviceToDevice, st));
+    PB_CUDA(cudaMemcpyAsync(s.ck_prev.p, s.prev.p, bytes, cudaMemcpyDeviceToDevice, st));
+    PB_CUDA(cudaMemcpyAsync(s.ck_vel.p, s.vel.p, bytes, cudaMemcpyDeviceToDevice, st));
+    const bool first_at_ck = s.first;
+    for (size_t i = 0; i < chunk; ++i) PB_PASS(sim_step(s, false));
+    TreeCheck chk;
+    PB_PASS(gravity_check(s.ws, st, &chk));
+    if (!chk.ok()) {
+      if (chk.sort_error) {
+        set_error("radix sort look-back did not complete");
+        return cudaErrorUnknown;
+      }
+      PB_CUDA(cudaMemcpyAsync(s.cur.p, s.ck_cur.p, bytes, cudaMemcpyDeviceToDevice, st));
+      PB_CUDA(cudaMemcpyAsync(s.prev.p, s.ck_prev.p, bytes, cudaMemcpyDeviceToDevice, st));
+      PB_CUDA(cudaMemcpyAsync(s.vel.p, s.ck_vel.p, bytes, cudaMemcpyDeviceToDevice, st));
+      s.first = first_at_ck;
+      s.replays += 1;
+      for (size_t i = 0; i < chunk; ++i) PB_PASS(sim_step(s, true));
+    }
+    steps -= chunk;
   }
   return cudaSuccess;
 }
@@ -619,6 +653,16 @@ int pb200_transform_debug_tree(void* obj, uint64_t* key, uint32_t* perm, uint32_
   return run() == cudaSuccess ? 0 : -1;
 }
 
+int pb200_transform_debug_hint(void* obj, int sort_lo, size_t n_cells_hint) {
+  if (!obj) return -1;
+  auto& t = *static_cast<TransformObj*>(obj);
+  std::lock_guard<std::mutex> lk(t.mu);
+  t.ws.sort_lo = sort_lo;
+  t.ws.tree_dim = t.prm.kind == PB200_ASTRO ? 2 : 3;
+  t.ws.n_cells = n_cells_hint;
+  return 0;
+}
+
 // ---- verlet -----------------------------------------------------------------------------------
 
 void* pb200_verlet_create(void) {
@@ -710,13 +754,8 @@ int pb200_sim_run(void* sim, size_t steps) {
     return -1;
   }
   cudaSetDevice(s.gpu.device);
-  for (size_t i = 0; i < steps; ++i)
-    if (sim_step(s) != cudaSuccess) {
-      std::fprintf(stderr, "[physim_b200] sim step failed: %s\n", g_error);
-      return -1;
-    }
-  if (sim_verify_tree(s) != cudaSuccess) {
-    std::fprintf(stderr, "[physim_b200] %s\n", g_error);
+  if (sim_run_steps(s, steps) != cudaSuccess || cudaStreamSynchronize(s.gpu.stream) != cudaSuccess) {
+    std::fprintf(stderr, "[physim_b200] sim run failed: %s\n", g_error);
     return -1;
   }
   return 0;
@@ -791,7 +830,7 @@ int pb200_sim_step_local(void* sim) {
     return -1;
   }
   cudaSetDevice(s.gpu.device);
-  if (sim_step(s) != cudaSuccess) {
+  if (sim_step(s, true) != cudaSuccess) {  // multi-rank steps are host-checked every time
     std::fprintf(stderr, "[physim_b200] sim step failed: %s\n", g_error);
     return -1;
   }
@@ -822,7 +861,6 @@ int pb200_sim_download(void* sim, Entity* state, size_t n) {
   cudaSetDevice(s.gpu.device);
   cudaStream_t st = s.gpu.stream;
   auto run = [&]() -> cudaError_t {
-    PB_PASS(sim_verify_tree(s));
     PB_CUDA(cudaMemcpyAsync(s.h_pos.p, s.cur.p, n * sizeof(double4), cudaMemcpyDeviceToHost, st));
     PB_CUDA(cudaMemcpyAsync(s.h_vel.p, s.vel.p, n * sizeof(double4), cudaMemcpyDeviceToHost, st));
     PB_CUDA(cudaStreamSynchronize(st));

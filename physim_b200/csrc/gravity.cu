@@ -8,6 +8,8 @@
 // octant arithmetic) -> LSD radix sort -> DFS pre-order cell table -> bottom-up centres of mass ->
 // warp-cooperative walk with per-lane acceptance.  oracle/physim_oracle.cpp ("oracle 2") builds the
 // same table on the CPU; tests compare the two bit for bit.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace pb200 {
@@ -131,65 +133,62 @@ __global__ void __launch_bounds__(256) encode_kernel(const double4* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------
-// K3  LSD radix sort, 8-bit digits, stable, (u64 key, u32 value) pairs.
-//     per pass: tile histogram -> per-digit scan along tiles -> ranked scatter.
-// HBM per pass per body: 8 B (hist) + 12 B + 12 B (scatter).
+// K3  LSD radix sort, <= 8-bit digits, stable, (u64 key, u32 value) pairs, "onesweep" form:
+//     one histogram kernel for every pass up front, then ONE kernel per pass that ranks a tile,
+//     obtains its global offsets by decoupled look-back over the preceding tiles, and scatters.
+//     Only the key bits [lo, key_bits) are sorted (lo > 0 when the previous evaluation showed
+//     that the tree is shallower than the key; validated after the build, see gravity_evaluate).
+// HBM per body: 8 B (histograms) + passes x (12 B + 12 B).
 // ---------------------------------------------------------------------------------------------
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_ITEMS = 16;
 constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
+constexpr int SORT_MAX_PASSES = 8;
+constexpr unsigned LB_INCL = 0x80000000u, LB_PART = 0x40000000u, LB_MASK = 0x3fffffffu;
+constexpr unsigned LB_SPIN_LIMIT = 1u << 26;
 
-__global__ void __launch_bounds__(SORT_THREADS) sort_tile_hist(const uint64_t* __restrict__ kin,
-                                                               size_t n, int shift,
-                                                               unsigned* __restrict__ tile_counts,
-                                                               unsigned num_tiles) {
-  __shared__ unsigned h[256];
-  h[threadIdx.x] = 0;
+struct SortPlan {
+  int npass;
+  int shift[SORT_MAX_PASSES];
+  unsigned mask[SORT_MAX_PASSES];
+};
+
+__global__ void __launch_bounds__(256) sort_hist_all(const uint64_t* __restrict__ keys, size_t n,
+                                                     SortPlan plan, unsigned* __restrict__ ghist) {
+  __shared__ unsigned h[SORT_MAX_PASSES * 256];
+  for (int j = threadIdx.x; j < SORT_MAX_PASSES * 256; j += 256) h[j] = 0;
   __syncthreads();
-  const size_t base = size_t(blockIdx.x) * SORT_TILE;
   const int lane = threadIdx.x & 31;
-#pragma unroll 4
-  for (int i = 0; i < SORT_ITEMS; ++i) {
-    const size_t g = base + size_t(i) * SORT_THREADS + threadIdx.x;
+  const size_t stride = size_t(gridDim.x) * 256;
+  // whole warps iterate together (match_any needs every lane)
+  for (size_t base = size_t(blockIdx.x) * 256 + (threadIdx.x & ~31); base < n; base += stride) {
+    const size_t g = base + lane;
     const bool ok = g < n;
-    const unsigned d = ok ? unsigned((kin[g] >> shift) & 255u) : 256u;
-    const unsigned peers = __match_any_sync(FULL, d);
-    if (ok && (peers & ((1u << lane) - 1u)) == 0u) atomicAdd(&h[d], unsigned(__popc(peers)));
+    const uint64_t k = ok ? keys[g] : 0ull;
+    for (int p = 0; p < plan.npass; ++p) {
+      const unsigned d = ok ? unsigned((k >> plan.shift[p]) & plan.mask[p]) : 256u;
+      const unsigned peers = __match_any_sync(FULL, d);
+      if (ok && (peers & ((1u << lane) - 1u)) == 0u) atomicAdd(&h[p * 256 + d], unsigned(__popc(peers)));
+    }
   }
   __syncthreads();
-  tile_counts[size_t(threadIdx.x) * num_tiles + blockIdx.x] = h[threadIdx.x];
+  for (int j = threadIdx.x; j < plan.npass * 256; j += 256)
+    if (h[j]) atomicAdd(&ghist[j], h[j]);
 }
 
-// one block per digit: exclusive scan of that digit's counts along the tiles; total -> digit_total
-__global__ void __launch_bounds__(256) sort_row_scan(unsigned* __restrict__ tile_counts,
-                                                     unsigned num_tiles,
-                                                     unsigned* __restrict__ digit_total) {
-  unsigned* row = tile_counts + size_t(blockIdx.x) * num_tiles;
-  const unsigned chunk = (num_tiles + 255u) / 256u;
-  const unsigned b = threadIdx.x * chunk;
-  const unsigned e = min(b + chunk, num_tiles);
-  unsigned sum = 0;
-  for (unsigned j = b; j < e; ++j) sum += row[j];
-  unsigned total;
-  unsigned run = block_exclusive_scan_256(sum, &total);
-  for (unsigned j = b; j < e; ++j) {
-    const unsigned c = row[j];
-    row[j] = run;
-    run += c;
-  }
-  if (threadIdx.x == 0) digit_total[blockIdx.x] = total;
-}
-
-__global__ void __launch_bounds__(SORT_THREADS) sort_scatter(
+__global__ void __launch_bounds__(SORT_THREADS, 2) sort_onesweep_pass(
     const uint64_t* __restrict__ kin, const uint32_t* __restrict__ vin, uint64_t* __restrict__ kout,
-    uint32_t* __restrict__ vout, size_t n, int shift, const unsigned* __restrict__ tile_prefix,
-    const unsigned* __restrict__ digit_total, unsigned num_tiles) {
+    uint32_t* __restrict__ vout, size_t n, int shift, unsigned mask,
+    const unsigned* __restrict__ ghist /*[256] of this pass*/, unsigned* status /*[tiles][256]*/,
+    unsigned* tile_counter, unsigned* err_flag) {
   __shared__ unsigned whist[8][256];
+  __shared__ unsigned tile_s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) tile_s = atomicAdd(tile_counter, 1u);  // tiles are numbered in start order
   for (int j = tid; j < 8 * 256; j += SORT_THREADS) (&whist[0][0])[j] = 0;
-  // start of each digit's output segment
-  const unsigned dbase = block_exclusive_scan_256(digit_total[tid], nullptr);  // syncs
-  const size_t base = size_t(blockIdx.x) * SORT_TILE + size_t(warp) * 32 * SORT_ITEMS;
+  const unsigned dbase = block_exclusive_scan_256(ghist[tid], nullptr);  // start of each digit; syncs
+  const unsigned tile = tile_s;
+  const size_t base = size_t(tile) * SORT_TILE + size_t(warp) * 32 * SORT_ITEMS;
 
   uint64_t k[SORT_ITEMS];
   uint32_t v[SORT_ITEMS];
@@ -205,7 +204,7 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_scatter(
 #pragma unroll
   for (int i = 0; i < SORT_ITEMS; ++i) {
     const bool ok = (base + size_t(i) * 32 + lane) < n;
-    const unsigned d = ok ? unsigned((k[i] >> shift) & 255u) : 256u;
+    const unsigned d = ok ? unsigned((k[i] >> shift) & mask) : 256u;
     const unsigned peers = __match_any_sync(FULL, d);
     const unsigned before = ok ? whist[warp][d] : 0u;
     __syncwarp();
@@ -215,21 +214,48 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_scatter(
     rank[i] = before + r;
   }
   __syncthreads();
-  {  // thread = digit: turn per-warp counts into global offsets
-    unsigned run = dbase + tile_prefix[size_t(tid) * num_tiles + blockIdx.x];
+  {  // thread = digit
+    unsigned cnt = 0;
 #pragma unroll
     for (int w = 0; w < 8; ++w) {
       const unsigned c = whist[w][tid];
-      whist[w][tid] = run;
-      run += c;
+      whist[w][tid] = cnt;  // exclusive offset of warp w inside the tile
+      cnt += c;
     }
+    // decoupled look-back: one 32-bit word per (tile, digit) carries flag + count
+    volatile unsigned* st = status + size_t(tile) * 256 + tid;
+    unsigned prefix = 0;
+    if (tile == 0) {
+      *st = cnt | LB_INCL;
+    } else {
+      *st = cnt | LB_PART;
+      unsigned t = tile - 1;
+      unsigned spins = 0;
+      for (;;) {
+        const unsigned val = *reinterpret_cast<volatile unsigned*>(status + size_t(t) * 256 + tid);
+        if ((val & (LB_INCL | LB_PART)) == 0u) {
+          if (++spins > LB_SPIN_LIMIT) {  // never expected; avoids an unbounded hang
+            atomicExch(err_flag, 1u);
+            break;
+          }
+          continue;
+        }
+        prefix += val & LB_MASK;
+        if (val & LB_INCL) break;
+        --t;  // tile 0 always publishes INCL, so t never underflows
+      }
+      *st = ((prefix + cnt) & LB_MASK) | LB_INCL;
+    }
+    const unsigned gbase = dbase + prefix;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) whist[w][tid] += gbase;
   }
   __syncthreads();
 #pragma unroll
   for (int i = 0; i < SORT_ITEMS; ++i) {
     const bool ok = (base + size_t(i) * 32 + lane) < n;
     if (ok) {
-      const unsigned d = unsigned((k[i] >> shift) & 255u);
+      const unsigned d = unsigned((k[i] >> shift) & mask);
       const unsigned dst = whist[warp][d] + rank[i];
       kout[dst] = k[i];
       vout[dst] = v[i];
@@ -312,45 +338,53 @@ template <int DIM>
 __global__ void __launch_bounds__(256) unit_kernel(const uint64_t* __restrict__ key,
                                                    const double4* __restrict__ sp, size_t n,
                                                    uchar2* __restrict__ ab,
-                                                   uint32_t* __restrict__ cnt) {
+                                                   uint32_t* __restrict__ cnt,
+                                                   unsigned* __restrict__ max_shared_plus1) {
   constexpr int LM = TreeDim<DIM>::LM;
   const size_t s = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
-  if (s >= n) return;
-  const double4 me = sp[s];
-  const uint64_t kme = key[s];
-  const bool cp = s > 0 && close_1e9(sp[s - 1], me);
-  const bool cn = s + 1 < n && close_1e9(me, sp[s + 1]);
-  int a = s > 0 ? shared_levels<DIM>(key[s - 1], kme) : -1;
-  int b = s + 1 < n ? shared_levels<DIM>(kme, key[s + 1]) : -1;
-  bool head = true;
-  if (cp || cn) {
-    size_t r0 = s, r1 = s;
-    int inner = LM + 1;
-    bool capped = false;
-    int steps = 0;
-    while (r0 > 0 && close_1e9(sp[r0 - 1], sp[r0])) {
-      inner = min(inner, shared_levels<DIM>(key[r0 - 1], key[r0]));
-      --r0;
-      if (++steps > MERGE_RUN_CAP) { capped = true; break; }
-    }
-    steps = 0;
-    while (!capped && r1 + 1 < n && close_1e9(sp[r1], sp[r1 + 1])) {
-      inner = min(inner, shared_levels<DIM>(key[r1], key[r1 + 1]));
-      ++r1;
-      if (++steps > MERGE_RUN_CAP) { capped = true; break; }
-    }
-    if (!capped && (r1 - r0 + 1) <= size_t(MERGE_RUN_CAP)) {
-      const int ra = r0 > 0 ? shared_levels<DIM>(key[r0 - 1], key[r0]) : -1;
-      const int rb = r1 + 1 < n ? shared_levels<DIM>(key[r1], key[r1 + 1]) : -1;
-      if (inner >= min(max(ra, rb) + 1, LM)) {
-        head = (s == r0);
-        a = ra;
-        b = rb;
+  unsigned deepest = 0;  // 1 + deepest level shared by two neighbours with DIFFERENT keys
+  if (s < n) {
+    const double4 me = sp[s];
+    const uint64_t kme = key[s];
+    const bool cp = s > 0 && close_1e9(sp[s - 1], me);
+    const bool cn = s + 1 < n && close_1e9(me, sp[s + 1]);
+    int a = s > 0 ? shared_levels<DIM>(key[s - 1], kme) : -1;
+    int b = s + 1 < n ? shared_levels<DIM>(kme, key[s + 1]) : -1;
+    if (s > 0 && key[s - 1] != kme) deepest = unsigned(a + 1);
+    bool head = true;
+    if (cp || cn) {
+      size_t r0 = s, r1 = s;
+      int inner = LM + 1;
+      bool capped = false;
+      int steps = 0;
+      while (r0 > 0 && close_1e9(sp[r0 - 1], sp[r0])) {
+        inner = min(inner, shared_levels<DIM>(key[r0 - 1], key[r0]));
+        --r0;
+        if (++steps > MERGE_RUN_CAP) { capped = true; break; }
+      }
+      steps = 0;
+      while (!capped && r1 + 1 < n && close_1e9(sp[r1], sp[r1 + 1])) {
+        inner = min(inner, shared_levels<DIM>(key[r1], key[r1 + 1]));
+        ++r1;
+        if (++steps > MERGE_RUN_CAP) { capped = true; break; }
+      }
+      if (!capped && (r1 - r0 + 1) <= size_t(MERGE_RUN_CAP)) {
+        const int ra = r0 > 0 ? shared_levels<DIM>(key[r0 - 1], key[r0]) : -1;
+        const int rb = r1 + 1 < n ? shared_levels<DIM>(key[r1], key[r1 + 1]) : -1;
+        if (inner >= min(max(ra, rb) + 1, LM)) {
+          head = (s == r0);
+          a = ra;
+          b = rb;
+        }
       }
     }
+    ab[s] = make_uchar2(static_cast<unsigned char>(a + 1), static_cast<unsigned char>(b + 1));
+    cnt[s] = head ? unsigned(max(0, b - a) + 1) : 0u;
   }
-  ab[s] = make_uchar2(static_cast<unsigned char>(a + 1), static_cast<unsigned char>(b + 1));
-  cnt[s] = head ? unsigned(max(0, b - a) + 1) : 0u;
+  // sizes the next sort and validates this one (a truncated sort is exact iff no two neighbours
+  // with different keys agree on every sorted bit)
+  deepest = __reduce_max_sync(FULL, deepest);
+  if ((threadIdx.x & 31) == 0 && deepest > 0u) atomicMax(max_shared_plus1, deepest);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -803,23 +837,46 @@ cudaError_t exclusive_scan(const uint32_t* in, uint32_t* out, size_t n, DevBuf& 
   return cudaGetLastError();
 }
 
-cudaError_t radix_sort(GravityWorkspace& ws, size_t n, int key_bits, cudaStream_t st, LaunchStats& ls) {
+// sorts key bits [lo, key_bits); returns with ws.sorted_key / ws.perm pointing at the result
+cudaError_t radix_sort(GravityWorkspace& ws, size_t n, int key_bits, int lo, cudaStream_t st,
+                       LaunchStats& ls) {
   const unsigned tiles = blocks_for(n, SORT_TILE);
-  PB_PASS(ws.tile_counts.ensure(size_t(tiles) * 256 * 4));
-  PB_PASS(ws.digit_base.ensure(256 * 4));
+  SortPlan plan;
+  const int total = key_bits - lo;
+  plan.npass = (total + 7) / 8;
+  {
+    int at = lo;
+    for (int p = 0; p < plan.npass; ++p) {
+      const int width = total / plan.npass + (p < total % plan.npass ? 1 : 0);
+      plan.shift[p] = at;
+      plan.mask[p] = (1u << width) - 1u;
+      at += width;
+    }
+  }
+  // [ghist: 8 x 256][tile counters: 8][error flag][status: npass x tiles x 256]
+  const size_t head_words = SORT_MAX_PASSES * 256 + SORT_MAX_PASSES + 8;
+  const size_t words = head_words + size_t(plan.npass) * tiles * 256;
+  PB_PASS(ws.tile_counts.ensure(words * 4));
+  unsigned* ghist = ws.tile_counts.as<unsigned>();
+  unsigned* counters = ghist + SORT_MAX_PASSES * 256;
+  unsigned* err_flag = counters + SORT_MAX_PASSES;
+  unsigned* status = ghist + head_words;
+  PB_CUDA(cudaMemsetAsync(ghist, 0, words * 4, st));
   uint64_t* k[2] = {ws.key0.as<uint64_t>(), ws.key1.as<uint64_t>()};
   uint32_t* v[2] = {ws.idx0.as<uint32_t>(), ws.idx1.as<uint32_t>()};
+  PB_LAUNCH(ls, st, "sort_hist_all",
+            sort_hist_all<<<min(blocks_for(n, 256), 148u * 8u), 256, 0, st>>>(k[0], n, plan, ghist));
   int cur = 0;
-  for (int shift = 0; shift < key_bits; shift += 8) {
-    PB_LAUNCH(ls, st, "sort_tile_hist", sort_tile_hist<<<tiles, SORT_THREADS, 0, st>>>(k[cur], n, shift, ws.tile_counts.as<unsigned>(), tiles));
-    PB_LAUNCH(ls, st, "sort_row_scan", sort_row_scan<<<256, 256, 0, st>>>(ws.tile_counts.as<unsigned>(), tiles, ws.digit_base.as<unsigned>()));
-    PB_LAUNCH(ls, st, "sort_scatter", sort_scatter<<<tiles, SORT_THREADS, 0, st>>>(k[cur], v[cur], k[cur ^ 1], v[cur ^ 1], n, shift,
-                                                 ws.tile_counts.as<unsigned>(),
-                                                 ws.digit_base.as<unsigned>(), tiles));
+  for (int p = 0; p < plan.npass; ++p) {
+    PB_LAUNCH(ls, st, "sort_onesweep_pass",
+              sort_onesweep_pass<<<tiles, SORT_THREADS, 0, st>>>(
+                  k[cur], v[cur], k[cur ^ 1], v[cur ^ 1], n, plan.shift[p], plan.mask[p], ghist + p * 256,
+                  status + size_t(p) * tiles * 256, counters + p, err_flag));
     cur ^= 1;
   }
   ws.sorted_key = k[cur];
   ws.perm = v[cur];
+  ws.sort_err_flag = err_flag;
   return cudaGetLastError();
 }
 
@@ -827,7 +884,7 @@ template <int DIM>
 cudaError_t tree_evaluate(GravityWorkspace& ws, const GravityParams& prm, size_t t0, size_t t1,
                           float easing, float tiny, cudaStream_t st, LaunchStats& ls) {
   const size_t n = ws.n;
-  PB_PASS(ws.extent_bits.ensure(8));
+  PB_PASS(ws.extent_bits.ensure(16));
   PB_PASS(ws.key0.ensure(n * 8));
   PB_PASS(ws.key1.ensure(n * 8));
   PB_PASS(ws.idx0.ensure(n * 4));
@@ -837,15 +894,22 @@ cudaError_t tree_evaluate(GravityWorkspace& ws, const GravityParams& prm, size_t
   PB_PASS(ws.cell_start.ensure((n + 1) * 4));
   PB_PASS(ws.tgt_flags.ensure(n * 4));  // also the per-body cell counts before the scan
 
-  PB_CUDA(cudaMemsetAsync(ws.extent_bits.p, 0, 8, st));
+  // extent_bits: [0] extent (u64 bits)  [1] low word: 1 + deepest level shared by distinct keys
+  PB_CUDA(cudaMemsetAsync(ws.extent_bits.p, 0, 16, st));
+  unsigned* max_shared_plus1 = reinterpret_cast<unsigned*>(ws.extent_bits.as<unsigned long long>() + 1);
+  const int key_bits = DIM * TreeDim<DIM>::LM;
+  if (ws.tree_dim != DIM) ws.sort_lo = 0;  // depth estimate belongs to the other tree kind
+  ws.tree_dim = DIM;
+  const int lo = (ws.sort_lo > 0 && ws.sort_lo < key_bits) ? ws.sort_lo : 0;
+  ws.last_lo = lo;
   const unsigned nb = blocks_for(n, 256);
   PB_LAUNCH(ls, st, "extent_kernel", extent_kernel<<<min(nb, 148u * 8u), 256, 0, st>>>(ws.pos64, n, ws.extent_bits.as<unsigned long long>()));
   PB_LAUNCH(ls, st, "encode_kernel", encode_kernel<DIM><<<nb, 256, 0, st>>>(ws.pos64, n, ws.extent_bits.as<unsigned long long>(),
                                          ws.key0.as<uint64_t>(), ws.idx0.as<uint32_t>()));
-  PB_PASS(radix_sort(ws, n, DIM * TreeDim<DIM>::LM, st, ls));
+  PB_PASS(radix_sort(ws, n, key_bits, lo, st, ls));
   PB_LAUNCH(ls, st, "gather_kernel", gather_kernel<<<nb, 256, 0, st>>>(ws.pos64, ws.perm, n, ws.spos64.as<double4>()));
   PB_LAUNCH(ls, st, "unit_kernel", unit_kernel<DIM><<<nb, 256, 0, st>>>(ws.sorted_key, ws.spos64.as<double4>(), n, ws.ab.as<uchar2>(),
-                                       ws.tgt_flags.as<uint32_t>()));
+                                       ws.tgt_flags.as<uint32_t>(), max_shared_plus1));
   PB_PASS(exclusive_scan(ws.tgt_flags.as<uint32_t>(), ws.cell_start.as<uint32_t>(), n, ws.scan_tmp, st, ls));
 
   // cell table capacity: grows when a previous evaluation reported more cells
@@ -948,29 +1012,62 @@ cudaError_t gravity_evaluate(GravityWorkspace& ws, const GravityParams& prm, siz
   const bool direct = prm.kind == PB200_SIMPLE_ASTRO || !(prm.theta > 0.0);
   if (direct) {
     ws.n_cells = 0;
+    ws.tree_dim = 0;
     return direct_evaluate(ws, t0, t1, easing, tiny, st, ls);
   }
-  for (int attempt = 0; attempt < 2; ++attempt) {
+  for (int attempt = 0; attempt < 3; ++attempt) {
     cudaError_t e = prm.kind == PB200_ASTRO ? tree_evaluate<2>(ws, prm, t0, t1, easing, tiny, st, ls)
                                             : tree_evaluate<3>(ws, prm, t0, t1, easing, tiny, st, ls);
     if (e != cudaSuccess) return e;
-    if (!host_check) return cudaSuccess;  // caller polls gravity_cell_total() later
-    // the only host read of the build: the cell total (also detects table overflow)
-    uint32_t total = 0;
-    PB_PASS(gravity_cell_total(ws, st, &total));
-    if (total <= ws.cell_cap) return cudaSuccess;
-    // overflow: every tree kernel bailed out; capacity now follows n_cells, run again
+    if (!host_check) return cudaSuccess;  // caller runs gravity_check() later
+    // the only host read of the build: cell total, tree depth, sort status (one small sync)
+    TreeCheck chk;
+    PB_PASS(gravity_check(ws, st, &chk));
+    if (chk.ok()) return cudaSuccess;
+    if (chk.sort_error) break;
+    // overflow / truncated sort too short: gravity_check() already adjusted capacity / sort_lo
   }
-  set_error("cell table overflow persisted after regrowing");
+  set_error("tree build did not converge (cell table overflow or sort failure)");
   return cudaErrorUnknown;
 }
 
-cudaError_t gravity_cell_total(GravityWorkspace& ws, cudaStream_t st, uint32_t* total) {
-  *total = 0;
-  if (ws.n == 0 || !ws.cell_start.p) return cudaSuccess;
-  PB_CUDA(cudaMemcpyAsync(total, ws.cell_start.as<uint32_t>() + ws.n, 4, cudaMemcpyDeviceToHost, st));
+cudaError_t gravity_check(GravityWorkspace& ws, cudaStream_t st, TreeCheck* out) {
+  *out = TreeCheck();
+  if (ws.n == 0 || !ws.cell_start.p || ws.tree_dim == 0) return cudaSuccess;
+  struct {
+    uint32_t total;
+    uint32_t deepest_plus1;
+    uint32_t sort_err;
+  } h = {0, 0, 0};
+  PB_CUDA(cudaMemcpyAsync(&h.total, ws.cell_start.as<uint32_t>() + ws.n, 4, cudaMemcpyDeviceToHost, st));
+  PB_CUDA(cudaMemcpyAsync(&h.deepest_plus1, ws.extent_bits.as<unsigned long long>() + 1, 4,
+                          cudaMemcpyDeviceToHost, st));
+  PB_CUDA(cudaMemcpyAsync(&h.sort_err, ws.sort_err_flag, 4, cudaMemcpyDeviceToHost, st));
   PB_CUDA(cudaStreamSynchronize(st));
-  ws.n_cells = *total;
+  const int dim = ws.tree_dim;
+  const int key_bits = dim * (dim == 3 ? 21 : 31);
+  out->total = h.total;
+  out->deepest_shared = int(h.deepest_plus1) - 1;
+  out->overflow = h.total > ws.cell_cap;
+  out->sort_error = h.sort_err != 0;
+  // a sort of key bits [lo, key_bits) is exact iff no two neighbours with different keys agree on
+  // all of those bits, i.e. share fewer than floor((key_bits - lo) / dim) levels
+  out->sort_short = ws.last_lo > 0 && out->deepest_shared >= (key_bits - ws.last_lo) / dim;
+  ws.n_cells = h.total;
+  if (out->sort_short) {
+    ws.sort_lo = 0;
+  } else if (!out->sort_error) {
+    // next time sort two levels deeper than anything seen now
+    const int want_levels = out->deepest_shared + 3;
+    ws.sort_lo = std::max(0, key_bits - dim * want_levels);
+  }
+  return cudaSuccess;
+}
+
+cudaError_t gravity_cell_total(GravityWorkspace& ws, cudaStream_t st, uint32_t* total) {
+  TreeCheck chk;
+  PB_PASS(gravity_check(ws, st, &chk));
+  *total = chk.total;
   return cudaSuccess;
 }
 

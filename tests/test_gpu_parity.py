@@ -176,6 +176,29 @@ def test_transform_twice_same_object_and_changing_n():
         assert_acc_parity(a1, ob.transform("astro2", s, 1.0, 0.5))
 
 
+@pytest.mark.parametrize("name", ["astro2", "astro"])
+def test_validate_and_retry_paths(name):
+    """The sort drops key bits below the tree depth seen last time and the cell table is sized from
+    the last total; both guesses are validated after every build and the build re-runs when they
+    were wrong.  Force both wrong guesses and require the bit-exact tree anyway."""
+    s = bucket_twins(9) if name == "astro2" else with_merges(7)
+    o = ob.CellTable(DIM[name], s)
+    for sort_lo, cells in ((DIM[name] * (31 if name == "astro" else 21) - 2 * DIM[name], 0), (0, 1), (40, 1)):
+        el = api.TransformElement(name, theta=1.0, e=0.5)
+        el.debug_hint(sort_lo, cells)
+        acc = el.transform(s)
+        t = el.debug_tree()
+        for k in ("key", "perm", "cell_start", "level", "head", "count", "skip", "parent"):
+            assert np.array_equal(t[k], getattr(o, k)), (k, sort_lo, cells)
+        assert_acc_parity(acc, ob.transform(name, s, 1.0, 0.5))
+    # shallow data first, deep data second on the same object (the depth estimate is stale)
+    el = api.TransformElement(name, theta=1.0, e=0.5)
+    el.transform(gen.cube(3000, seed=1))
+    el.transform(s)
+    t = el.debug_tree()
+    assert np.array_equal(t["perm"], o.perm) and np.array_equal(t["skip"], o.skip)
+
+
 def test_momentum_conservation_direct_sum():
     """Newton's third law as a size-independent property: sum_i m_i a_i ~ 0 for all-free bodies."""
     s = gen.cube(20_000, seed=6)
