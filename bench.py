@@ -47,7 +47,7 @@ WORKLOADS = {
 ALG_BYTES_PER_BODY = {
     "extent_kernel": 32, "encode_kernel": 32 + 12, "sort_hist_all": 8, "sort_onesweep_pass": 12 + 12,
     "gather_kernel": 4 + 32 + 32, "unit_kernel": 8 + 32 + 2 + 4, "scan_tile_sums": 4, "scan_apply": 8,
-    "fill_kernel": 8 + 32 + 4 + 2 + 4 + 1.5 * (1 + 5 * 4 + 32) + 32, "com_kernel": 1.5 * (32 + 32 + 12),
+    "chain_kernel": 8 + 32 + 2 + 4 + 1.5 * (1 + 4 + 4 + 32) + 32, "skip_kernel": 1.5 * (5 + 8) + 24, "parent_kernel": 1.5 * 8, "com_kernel": 1.5 * (32 + 32 + 12),
     "walk_kernel": 32 + 4 + 1 + 16, "verlet_kernel": 32 + 32 + 16 + 32 + 32 + 32,
     "to_float4_kernel": 32 + 16,
 }
@@ -306,13 +306,18 @@ def measure_e2e(api, state, w, args):
     n = len(state)
     el = api.TransformElement(w["element"], theta=w["theta"], e=w["e"])
     v = api.Verlet()
-    cur = state
+    # state / new_state are two persistent host arrays, as in pipeline.rs:100-173
+    bufs = [state.copy(), state.copy()]
+    k = 0
     for _ in range(max(args.warmup, 3)):
-        cur = v.integrate_fused(cur, el, w["dt"])
+        v.integrate_fused(bufs[k], el, w["dt"], out=bufs[k ^ 1])
+        k ^= 1
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cur = v.integrate_fused(cur, el, w["dt"])
+        v.integrate_fused(bufs[k], el, w["dt"], out=bufs[k ^ 1])
+        k ^= 1
     dt = time.perf_counter() - t0
+    cur = bufs[k]
     vs = v.stats()
     # transform-only boundary (today's drop-in: astro*_transform through `*_get_api`)
     acc = el.transform(cur)
@@ -321,10 +326,11 @@ def measure_e2e(api, state, w, args):
         acc = el.transform(cur, acc)
     dt_tr = (time.perf_counter() - t1) / 5
     return {"value": n * args.steps / dt, "unit": "particle-steps/s", "ms_per_step": dt / args.steps * 1e3,
-            "h2d_bytes_per_step": n * 33, "d2h_bytes_per_step": n * 64,
+            "h2d_bytes_per_step": n * 33, "d2h_bytes_per_step": n * 48,
             "api": "pb200_verlet_step_fused(host Entity[n] -> host Entity[n])",
             "device_ms": {"h2d": vs["ms_h2d"], "force": vs["ms_force"], "integrate": vs["ms_integrate"],
                           "d2h": vs["ms_d2h"]},
+            "host_ms": {"pack": vs["ms_host_pack"], "unpack": vs["ms_host_unpack"], "call": vs["ms_wall"]},
             "transform_only": {"api": f"{w['element']}_get_api()->transform", "ms_per_call": dt_tr * 1e3,
                                "h2d_bytes": n * 33, "d2h_bytes": n * 16}}
 

@@ -153,6 +153,7 @@ typedef struct Pb200Stats {
   uint64_t kernel_launches;/* kernels launched by this library since the handle was created */
   double extent;           /* root half-width used */
   float ms_h2d, ms_build, ms_force, ms_integrate, ms_d2h; /* CUDA-event times of the last call */
+  float ms_host_pack, ms_host_unpack, ms_wall;             /* host wall-clock parts of the last call */
 } Pb200Stats;
 
 /* Number of CUDA devices visible; <= 0 means the GPU entry points will fail. No context is made. */

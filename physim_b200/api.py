@@ -54,7 +54,8 @@ class Pb200Stats(C.Structure):
     _fields_ = [("n_bodies", C.c_uint64), ("n_cells", C.c_uint64), ("interactions", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("extent", C.c_double), ("ms_h2d", C.c_float),
                 ("ms_build", C.c_float), ("ms_force", C.c_float), ("ms_integrate", C.c_float),
-                ("ms_d2h", C.c_float)]
+                ("ms_d2h", C.c_float), ("ms_host_pack", C.c_float), ("ms_host_unpack", C.c_float),
+                ("ms_wall", C.c_float)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -276,11 +277,13 @@ class Verlet:
             raise Pb200Error(last_error())
         return new_state
 
-    def integrate_fused(self, entities, transform, dt):
-        """Same step with the accelerations of `transform` (a TransformElement) kept on the device."""
+    def integrate_fused(self, entities, transform, dt, out=None):
+        """Same step with the accelerations of `transform` (a TransformElement) kept on the device.
+        `out` is the caller's `new_state` buffer (physim reuses one Vec across steps)."""
         entities = _state(entities)
         n = len(entities)
-        new_state = np.zeros(n, dtype=ENTITY)
+        new_state = np.zeros(n, dtype=ENTITY) if out is None else out
+        assert new_state.dtype.itemsize == 80 and len(new_state) == n
         rc = lib().pb200_verlet_step_fused(self._v, transform._obj, _ptr(entities), _ptr(new_state), n,
                                            float(dt))
         if rc != 0:

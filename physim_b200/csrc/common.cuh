@@ -248,7 +248,7 @@ cudaError_t gravity_count_interactions(GravityWorkspace& ws, cudaStream_t stream
 // acc32 (float4, index i - acc_offset... see verlet.cu) or acc64 (3 doubles per body) is used.
 cudaError_t verlet_update(double4* cur, double4* prev, double4* vel, const float4* acc32,
                           const double* acc64, size_t n, double dt, int first, cudaStream_t stream,
-                          LaunchStats& ls);
+                          LaunchStats& ls, double* out6 = nullptr);
 
 // fp32 FFMA probe
 cudaError_t probe_fp32(double* tflops);

@@ -6,9 +6,12 @@
 //
 // Nothing here touches the GPU until the first force evaluation: physim instantiates and drops
 // every transform during plugin discovery (physim-core/src/plugin/discover.rs:376-387).
+#include <emmintrin.h>
+
 #include <cmath>
 #include <cstdarg>
 #include <cstring>
+#include <ctime>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -31,7 +34,15 @@ void set_error(const char* fmt, ...) {
 
 namespace {
 
-constexpr size_t kParallelGrain = 1 << 14;
+constexpr size_t kParallelGrain = 1 << 12;
+
+double now_ms() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
+thread_local double g_pack_ms = 0.0, g_unpack_ms = 0.0;
 
 struct GpuContext {
   bool ready = false;
@@ -39,6 +50,7 @@ struct GpuContext {
   cudaStream_t stream = nullptr;
   bool own_stream = true;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t chunk_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaError_t init(int dev) {
     if (ready) return cudaSetDevice(device);
     int count = 0;
@@ -52,6 +64,7 @@ struct GpuContext {
     PB_CUDA(cudaSetDevice(device));
     PB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     for (auto& x : ev) PB_CUDA(cudaEventCreate(&x));
+    for (auto& x : chunk_ev) PB_CUDA(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
     ready = true;
     return cudaSuccess;
   }
@@ -59,6 +72,8 @@ struct GpuContext {
     if (!ready) return;
     cudaSetDevice(device);
     for (auto& x : ev)
+      if (x) cudaEventDestroy(x);
+    for (auto& x : chunk_ev)
       if (x) cudaEventDestroy(x);
     if (stream && own_stream) cudaStreamDestroy(stream);
     ready = false;
@@ -101,18 +116,63 @@ struct TransformObj {
   }
 };
 
-// pack Entity AoS -> pinned {x,y,z,m} (+ fixed bytes)
+// pack Entity AoS -> pinned {x,y,z,m} (+ fixed bytes).  The staging buffer is written with
+// non-temporal stores: it is read next by the DMA engine, not by a core.
 void pack_positions(const Entity* state, size_t n, double4* pos, uint8_t* fixed) {
   HostPool::instance().parallel_for(n, kParallelGrain, [&](size_t b, size_t e) {
     for (size_t i = b; i < e; ++i) {
       const Entity& s = state[i];
-      pos[i] = make_double4(s.x, s.y, s.z, s.mass);
+      double* d = reinterpret_cast<double*>(pos + i);  // 32-byte aligned (pinned base, 32 B records)
+      _mm_stream_pd(d, _mm_set_pd(s.y, s.x));
+      _mm_stream_pd(d + 2, _mm_set_pd(s.mass, s.z));
       if (fixed) fixed[i] = s.fixed ? 1 : 0;
     }
+    _mm_sfence();
   });
 }
 
-cudaError_t transform_forces(TransformObj& t, const Entity* state, size_t n) {
+void pack_velocities(const Entity* state, size_t n, double4* vel) {
+  HostPool::instance().parallel_for(n, kParallelGrain, [&](size_t b, size_t e) {
+    for (size_t i = b; i < e; ++i) {
+      double* d = reinterpret_cast<double*>(vel + i);
+      _mm_stream_pd(d, _mm_set_pd(state[i].vy, state[i].vx));
+      _mm_stream_pd(d + 2, _mm_set_pd(0.0, state[i].vz));
+    }
+    _mm_sfence();
+  });
+}
+
+// Chunking of the host<->device pipeline: packing chunk c+1 overlaps the H2D copy of chunk c, and
+// unpacking chunk c overlaps the D2H copy of chunk c+1.
+constexpr int kMaxChunks = 8;
+inline int chunk_count(size_t n) { return n >= (size_t(1) << 18) ? kMaxChunks : 1; }
+inline size_t chunk_begin(size_t n, int chunks, int c) { return n * size_t(c) / size_t(chunks); }
+
+// pack + enqueue the upload of positions (+ fixed flags, + velocities when d_vel != nullptr)
+cudaError_t upload_packed(const Entity* state, size_t n, double4* h_pos, uint8_t* h_fixed, double4* h_vel,
+                          double4* d_pos, uint8_t* d_fixed, double4* d_vel, cudaStream_t st) {
+  const int chunks = chunk_count(n);
+  for (int c = 0; c < chunks; ++c) {
+    const size_t b = chunk_begin(n, chunks, c), e = chunk_begin(n, chunks, c + 1), m = e - b;
+    if (!m) continue;
+    const double t_pack = now_ms();
+    pack_positions(state + b, m, h_pos + b, h_fixed ? h_fixed + b : nullptr);
+    g_pack_ms += now_ms() - t_pack;
+    PB_CUDA(cudaMemcpyAsync(d_pos + b, h_pos + b, m * sizeof(double4), cudaMemcpyHostToDevice, st));
+    if (h_fixed) PB_CUDA(cudaMemcpyAsync(d_fixed + b, h_fixed + b, m, cudaMemcpyHostToDevice, st));
+    if (d_vel) {
+      const double t_pv = now_ms();
+      pack_velocities(state + b, m, h_vel + b);
+      g_pack_ms += now_ms() - t_pv;
+      PB_CUDA(cudaMemcpyAsync(d_vel + b, h_vel + b, m * sizeof(double4), cudaMemcpyHostToDevice, st));
+    }
+  }
+  return cudaSuccess;
+}
+
+cudaError_t transform_forces(TransformObj& t, const Entity* state, size_t n, Acceleration* acc) {
+  const double t_wall = now_ms();
+  g_pack_ms = g_unpack_ms = 0.0;
   PB_PASS(t.gpu.init(t.device));
   cudaStream_t st = t.gpu.stream;
   PB_PASS(t.h_pos.ensure(n * sizeof(double4)));
@@ -120,18 +180,40 @@ cudaError_t transform_forces(TransformObj& t, const Entity* state, size_t n) {
   PB_PASS(t.h_acc.ensure(n * sizeof(float4)));
   PB_PASS(t.d_pos.ensure(n * sizeof(double4)));
   PB_PASS(t.d_fixed.ensure(n));
-  pack_positions(state, n, t.h_pos.as<double4>(), t.h_fixed.as<uint8_t>());
   PB_CUDA(cudaEventRecord(t.gpu.ev[0], st));
-  PB_CUDA(cudaMemcpyAsync(t.d_pos.p, t.h_pos.p, n * sizeof(double4), cudaMemcpyHostToDevice, st));
-  PB_CUDA(cudaMemcpyAsync(t.d_fixed.p, t.h_fixed.p, n, cudaMemcpyHostToDevice, st));
+  PB_PASS(upload_packed(state, n, t.h_pos.as<double4>(), t.h_fixed.as<uint8_t>(), nullptr,
+                        t.d_pos.as<double4>(), t.d_fixed.as<uint8_t>(), nullptr, st));
   PB_CUDA(cudaEventRecord(t.gpu.ev[1], st));
   t.ws.pos64 = t.d_pos.as<double4>();
   t.ws.fixed = t.d_fixed.as<uint8_t>();
   t.ws.n = n;
   PB_PASS(gravity_evaluate(t.ws, t.prm, 0, n, st, t.ls, true));
   PB_CUDA(cudaEventRecord(t.gpu.ev[2], st));
-  PB_CUDA(cudaMemcpyAsync(t.h_acc.p, t.ws.acc.p, n * sizeof(float4), cudaMemcpyDeviceToHost, st));
+  const int chunks = chunk_count(n);
+  float4* h = t.h_acc.as<float4>();
+  for (int c = 0; c < chunks; ++c) {
+    const size_t b = chunk_begin(n, chunks, c), e = chunk_begin(n, chunks, c + 1);
+    if (e > b)
+      PB_CUDA(cudaMemcpyAsync(h + b, t.ws.acc.as<float4>() + b, (e - b) * sizeof(float4), cudaMemcpyDeviceToHost, st));
+    PB_CUDA(cudaEventRecord(t.gpu.chunk_ev[c], st));
+  }
   PB_CUDA(cudaEventRecord(t.gpu.ev[3], st));
+  // accelerations[i] += f / m_a for every non-fixed body (transformers.rs:139-141,154-158),
+  // chunk by chunk behind the copies
+  for (int c = 0; c < chunks; ++c) {
+    const size_t cb = chunk_begin(n, chunks, c), ce = chunk_begin(n, chunks, c + 1);
+    PB_CUDA(cudaEventSynchronize(t.gpu.chunk_ev[c]));
+    const double t_un = now_ms();
+    HostPool::instance().parallel_for(ce - cb, kParallelGrain, [&](size_t b, size_t e) {
+      for (size_t i = cb + b; i < cb + e; ++i) {
+        if (state[i].fixed) continue;
+        acc[i].x += double(h[i].x);
+        acc[i].y += double(h[i].y);
+        acc[i].z += double(h[i].z);
+      }
+    });
+    g_unpack_ms += now_ms() - t_un;
+  }
   PB_CUDA(cudaStreamSynchronize(st));
   t.last_n = n;
   t.have_tree = t.ws.n_cells > 0;
@@ -143,6 +225,9 @@ cudaError_t transform_forces(TransformObj& t, const Entity* state, size_t n) {
   t.stats.ms_force = elapsed(t.gpu.ev[1], t.gpu.ev[2]);
   t.stats.ms_integrate = 0.f;
   t.stats.ms_d2h = elapsed(t.gpu.ev[2], t.gpu.ev[3]);
+  t.stats.ms_host_pack = float(g_pack_ms);
+  t.stats.ms_host_unpack = float(g_unpack_ms);
+  t.stats.ms_wall = float(now_ms() - t_wall);
   return cudaSuccess;
 }
 
@@ -151,34 +236,46 @@ struct VerletObj {
   GpuContext gpu;
   int device;
   size_t n_prev = 0;  // length of the stored previous state (verlet.rs:102: len != n => first step)
-  DevBuf cur, prev, vel, acc64, fixed;
-  PinnedBuf h_pos, h_vel, h_fixed, h_acc;
+  DevBuf cur, prev, vel, acc64, fixed, out6;
+  PinnedBuf h_pos, h_vel, h_fixed, h_acc, h_out;
   LaunchStats ls;
   Pb200Stats stats;
   ~VerletObj() {
     if (gpu.ready) {
       cudaSetDevice(gpu.device);
-      cur.release(); prev.release(); vel.release(); acc64.release(); fixed.release();
-      h_pos.release(); h_vel.release(); h_fixed.release(); h_acc.release();
+      cur.release(); prev.release(); vel.release(); acc64.release(); fixed.release(); out6.release();
+      h_pos.release(); h_vel.release(); h_fixed.release(); h_acc.release(); h_out.release();
       gpu.destroy();
     }
   }
 };
 
-void pack_velocities(const Entity* state, size_t n, double4* vel) {
+// new_state[i] = entities[i] with position and velocity replaced (verlet.rs:41-48 / :72-79).
+// out6 holds {x,y,z,vx,vy,vz} per body.  new_state is written with non-temporal 16-byte stores when
+// aligned (it is 80 MB the caller reads later; no read-for-ownership traffic).
+void unpack_state(const Entity* entities, Entity* out, size_t n, const double* out6) {
+  const bool aligned = (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
   HostPool::instance().parallel_for(n, kParallelGrain, [&](size_t b, size_t e) {
-    for (size_t i = b; i < e; ++i) vel[i] = make_double4(state[i].vx, state[i].vy, state[i].vz, 0.0);
-  });
-}
-
-// new_state[i] = entities[i] with position and velocity replaced (verlet.rs:41-48 / :72-79)
-void unpack_state(const Entity* entities, Entity* out, size_t n, const double4* pos, const double4* vel) {
-  HostPool::instance().parallel_for(n, kParallelGrain, [&](size_t b, size_t e) {
-    for (size_t i = b; i < e; ++i) {
-      Entity o = entities[i];
-      o.x = pos[i].x; o.y = pos[i].y; o.z = pos[i].z;
-      o.vx = vel[i].x; o.vy = vel[i].y; o.vz = vel[i].z;
-      out[i] = o;
+    if (aligned) {
+      for (size_t i = b; i < e; ++i) {
+        const double* o = out6 + 6 * i;
+        const double* src = reinterpret_cast<const double*>(entities + i);
+        double* dst = reinterpret_cast<double*>(out + i);
+        _mm_stream_pd(dst, _mm_loadu_pd(o));
+        _mm_stream_pd(dst + 2, _mm_loadu_pd(o + 2));
+        _mm_stream_pd(dst + 4, _mm_loadu_pd(o + 4));
+        _mm_stream_pd(dst + 6, _mm_loadu_pd(src + 6));  // radius, mass
+        _mm_stream_pd(dst + 8, _mm_loadu_pd(src + 8));  // id, fixed (+ padding)
+      }
+      _mm_sfence();
+    } else {
+      for (size_t i = b; i < e; ++i) {
+        const double* o = out6 + 6 * i;
+        Entity t = entities[i];
+        t.x = o[0]; t.y = o[1]; t.z = o[2];
+        t.vx = o[3]; t.vy = o[4]; t.vz = o[5];
+        out[i] = t;
+      }
     }
   });
 }
@@ -192,16 +289,31 @@ cudaError_t verlet_buffers(VerletObj& v, size_t n) {
   PB_PASS(v.h_pos.ensure(n * sizeof(double4)));
   PB_PASS(v.h_vel.ensure(n * sizeof(double4)));
   PB_PASS(v.h_fixed.ensure(n));
+  PB_PASS(v.out6.ensure(n * 48));
+  PB_PASS(v.h_out.ensure(n * 48));
   return cudaSuccess;
 }
 
-// shared tail of both verlet entry points: D2H of the updated state, unpack, bookkeeping
+// shared tail of both verlet entry points: chunked D2H of the packed result, unpack behind the copies
 cudaError_t verlet_finish(VerletObj& v, cudaStream_t st, const Entity* entities, Entity* new_state, size_t n) {
-  PB_CUDA(cudaMemcpyAsync(v.h_pos.p, v.cur.p, n * sizeof(double4), cudaMemcpyDeviceToHost, st));
-  PB_CUDA(cudaMemcpyAsync(v.h_vel.p, v.vel.p, n * sizeof(double4), cudaMemcpyDeviceToHost, st));
+  const int chunks = chunk_count(n);
+  double* h = v.h_out.as<double>();
+  const double* d = v.out6.as<double>();
+  for (int c = 0; c < chunks; ++c) {
+    const size_t b = chunk_begin(n, chunks, c), e = chunk_begin(n, chunks, c + 1);
+    if (e > b)
+      PB_CUDA(cudaMemcpyAsync(h + 6 * b, d + 6 * b, (e - b) * 48, cudaMemcpyDeviceToHost, st));
+    PB_CUDA(cudaEventRecord(v.gpu.chunk_ev[c], st));
+  }
   PB_CUDA(cudaEventRecord(v.gpu.ev[4], st));
+  for (int c = 0; c < chunks; ++c) {
+    const size_t b = chunk_begin(n, chunks, c), e = chunk_begin(n, chunks, c + 1);
+    PB_CUDA(cudaEventSynchronize(v.gpu.chunk_ev[c]));
+    const double t_un = now_ms();
+    if (e > b) unpack_state(entities + b, new_state + b, e - b, h + 6 * b);
+    g_unpack_ms += now_ms() - t_un;
+  }
   PB_CUDA(cudaStreamSynchronize(st));
-  unpack_state(entities, new_state, n, v.h_pos.as<double4>(), v.h_vel.as<double4>());
   v.n_prev = n;
   v.stats.n_bodies = n;
   v.stats.kernel_launches = v.ls.launches;
@@ -221,16 +333,16 @@ cudaError_t verlet_step_generic(VerletObj& v, const Entity* entities, Entity* ne
   PB_PASS(v.h_acc.ensure(n * sizeof(Acceleration)));
   cudaStream_t st = v.gpu.stream;
   const bool first = v.n_prev != n;
-  pack_positions(entities, n, v.h_pos.as<double4>(), nullptr);
-  if (first) pack_velocities(entities, n, v.h_vel.as<double4>());
-  std::memcpy(v.h_acc.p, acc.data(), n * sizeof(Acceleration));
   PB_CUDA(cudaEventRecord(v.gpu.ev[0], st));
-  PB_CUDA(cudaMemcpyAsync(v.cur.p, v.h_pos.p, n * sizeof(double4), cudaMemcpyHostToDevice, st));
-  if (first) PB_CUDA(cudaMemcpyAsync(v.vel.p, v.h_vel.p, n * sizeof(double4), cudaMemcpyHostToDevice, st));
+  PB_PASS(upload_packed(entities, n, v.h_pos.as<double4>(), nullptr, v.h_vel.as<double4>(),
+                        v.cur.as<double4>(), nullptr, first ? v.vel.as<double4>() : nullptr, st));
+  HostPool::instance().parallel_for(n, kParallelGrain, [&](size_t b, size_t e) {
+    std::memcpy(v.h_acc.as<Acceleration>() + b, acc.data() + b, (e - b) * sizeof(Acceleration));
+  });
   PB_CUDA(cudaMemcpyAsync(v.acc64.p, v.h_acc.p, n * sizeof(Acceleration), cudaMemcpyHostToDevice, st));
   PB_CUDA(cudaEventRecord(v.gpu.ev[1], st));
   PB_PASS(verlet_update(v.cur.as<double4>(), v.prev.as<double4>(), v.vel.as<double4>(), nullptr,
-                        v.acc64.as<double>(), n, dt, first ? 1 : 0, st, v.ls));
+                        v.acc64.as<double>(), n, dt, first ? 1 : 0, st, v.ls, v.out6.as<double>()));
   PB_CUDA(cudaEventRecord(v.gpu.ev[3], st));
   PB_PASS(verlet_finish(v, st, entities, new_state, n));
   v.stats.ms_h2d = elapsed(v.gpu.ev[0], v.gpu.ev[1]);
@@ -246,17 +358,16 @@ cudaError_t verlet_step_fused(VerletObj& v, TransformObj& t, const Entity* entit
     v.n_prev = 0;
     return cudaSuccess;
   }
+  const double t_wall = now_ms();
+  g_pack_ms = g_unpack_ms = 0.0;
   v.device = t.device;
   PB_PASS(verlet_buffers(v, n));
   PB_PASS(t.gpu.init(t.device));
   cudaStream_t st = v.gpu.stream;
   const bool first = v.n_prev != n;
-  pack_positions(entities, n, v.h_pos.as<double4>(), v.h_fixed.as<uint8_t>());
-  if (first) pack_velocities(entities, n, v.h_vel.as<double4>());
   PB_CUDA(cudaEventRecord(v.gpu.ev[0], st));
-  PB_CUDA(cudaMemcpyAsync(v.cur.p, v.h_pos.p, n * sizeof(double4), cudaMemcpyHostToDevice, st));
-  PB_CUDA(cudaMemcpyAsync(v.fixed.p, v.h_fixed.p, n, cudaMemcpyHostToDevice, st));
-  if (first) PB_CUDA(cudaMemcpyAsync(v.vel.p, v.h_vel.p, n * sizeof(double4), cudaMemcpyHostToDevice, st));
+  PB_PASS(upload_packed(entities, n, v.h_pos.as<double4>(), v.h_fixed.as<uint8_t>(), v.h_vel.as<double4>(),
+                        v.cur.as<double4>(), v.fixed.as<uint8_t>(), first ? v.vel.as<double4>() : nullptr, st));
   PB_CUDA(cudaEventRecord(v.gpu.ev[1], st));
   t.ws.pos64 = v.cur.as<double4>();
   t.ws.fixed = v.fixed.as<uint8_t>();
@@ -264,7 +375,7 @@ cudaError_t verlet_step_fused(VerletObj& v, TransformObj& t, const Entity* entit
   PB_PASS(gravity_evaluate(t.ws, t.prm, 0, n, st, t.ls, true));
   PB_CUDA(cudaEventRecord(v.gpu.ev[2], st));
   PB_PASS(verlet_update(v.cur.as<double4>(), v.prev.as<double4>(), v.vel.as<double4>(),
-                        t.ws.acc.as<float4>(), nullptr, n, dt, first ? 1 : 0, st, v.ls));
+                        t.ws.acc.as<float4>(), nullptr, n, dt, first ? 1 : 0, st, v.ls, v.out6.as<double>()));
   PB_CUDA(cudaEventRecord(v.gpu.ev[3], st));
   PB_PASS(verlet_finish(v, st, entities, new_state, n));
   t.last_n = n;
@@ -277,6 +388,9 @@ cudaError_t verlet_step_fused(VerletObj& v, TransformObj& t, const Entity* entit
   v.stats.ms_force = elapsed(v.gpu.ev[1], v.gpu.ev[2]);
   v.stats.ms_integrate = elapsed(v.gpu.ev[2], v.gpu.ev[3]);
   v.stats.ms_d2h = elapsed(v.gpu.ev[3], v.gpu.ev[4]);
+  v.stats.ms_host_pack = float(g_pack_ms);
+  v.stats.ms_host_unpack = float(g_unpack_ms);
+  v.stats.ms_wall = float(now_ms() - t_wall);
   return cudaSuccess;
 }
 
@@ -323,11 +437,8 @@ cudaError_t sim_upload(SimObj& s, const Entity* state, size_t n) {
   PB_PASS(s.h_pos.ensure(n * sizeof(double4)));
   PB_PASS(s.h_vel.ensure(n * sizeof(double4)));
   PB_PASS(s.h_fixed.ensure(n));
-  pack_positions(state, n, s.h_pos.as<double4>(), s.h_fixed.as<uint8_t>());
-  pack_velocities(state, n, s.h_vel.as<double4>());
-  PB_CUDA(cudaMemcpyAsync(s.cur.p, s.h_pos.p, n * sizeof(double4), cudaMemcpyHostToDevice, st));
-  PB_CUDA(cudaMemcpyAsync(s.vel.p, s.h_vel.p, n * sizeof(double4), cudaMemcpyHostToDevice, st));
-  PB_CUDA(cudaMemcpyAsync(s.fixed.p, s.h_fixed.p, n, cudaMemcpyHostToDevice, st));
+  PB_PASS(upload_packed(state, n, s.h_pos.as<double4>(), s.h_fixed.as<uint8_t>(), s.h_vel.as<double4>(),
+                        s.cur.as<double4>(), s.fixed.as<uint8_t>(), s.vel.as<double4>(), st));
   PB_CUDA(cudaStreamSynchronize(st));
   s.ws.pos64 = s.cur.as<double4>();
   s.ws.fixed = s.fixed.as<uint8_t>();
@@ -578,20 +689,10 @@ int pb200_transform_apply(void* obj, const Entity* state, size_t n, Acceleration
     set_error("null state/acceleration pointer");
     return -1;
   }
-  if (transform_forces(t, state, n) != cudaSuccess) {
+  if (transform_forces(t, state, n, acc) != cudaSuccess) {
     std::fprintf(stderr, "[physim_b200] transform failed: %s\n", g_error);
     return -1;
   }
-  const float4* a = t.h_acc.as<float4>();
-  // accelerations[i] += f / m_a for every non-fixed body (transformers.rs:139-141,154-158)
-  HostPool::instance().parallel_for(n, kParallelGrain, [&](size_t b, size_t e) {
-    for (size_t i = b; i < e; ++i) {
-      if (state[i].fixed) continue;
-      acc[i].x += double(a[i].x);
-      acc[i].y += double(a[i].y);
-      acc[i].z += double(a[i].z);
-    }
-  });
   return 0;
 }
 

@@ -33,6 +33,19 @@ __device__ __forceinline__ int shared_levels(uint64_t a, uint64_t b) {
   return TreeDim<DIM>::LM - 1 - top / DIM;
 }
 
+// Lanes holding the same 8-bit digit (and ok): eight ballots instead of MATCH.ANY, which costs
+// ~1 us per call with ~30 distinct values in the warp on sm_100.
+__device__ __forceinline__ unsigned peers_of(unsigned d, bool ok) {
+  unsigned peers = __ballot_sync(FULL, ok);
+#pragma unroll
+  for (int bit = 0; bit < 8; ++bit) {
+    const bool one = (d >> bit) & 1u;
+    const unsigned m = __ballot_sync(FULL, one);
+    peers &= one ? m : ~m;
+  }
+  return peers;
+}
+
 __device__ __forceinline__ double warp_max(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
@@ -102,34 +115,77 @@ __global__ void __launch_bounds__(256) extent_kernel(const double4* __restrict__
 //     centre ± extent/2 halving, in fp64, so every visited centre is the reference's double.
 // HBM: 32 B read, 12 B written per body.
 // ---------------------------------------------------------------------------------------------
+// Sort passes over key bits [lo, lo + total): pass p covers `width(p)` bits starting at `shift(p)`,
+// the first `rem` passes being one bit wider (plain arithmetic: no per-pass tables in the kernels).
+struct SortPlan {
+  int npass, lo, base, rem;
+  __host__ __device__ int width(int p) const { return base + (p < rem ? 1 : 0); }
+  __host__ __device__ int shift(int p) const { return lo + p * base + (p < rem ? p : rem); }
+  __host__ __device__ unsigned mask(int p) const { return (1u << width(p)) - 1u; }
+};
+
+// pos > centre, then centre +/- half: one DSETP + one DADD per axis and level (the sign of `half`
+// is set with an integer op on the high word instead of computing both candidates)
+__device__ __forceinline__ double with_sign(double half, bool negative) {
+  const int hi = __double2hiint(half) ^ (negative ? int(0x80000000u) : 0);
+  return __hiloint2double(hi, __double2loint(half));
+}
+
+// Also accumulates the digit histograms of every sort pass (the keys are in registers anyway),
+// warp-aggregated into shared memory, flushed once per block: gridDim.x is kept small.
 template <int DIM>
 __global__ void __launch_bounds__(256) encode_kernel(const double4* __restrict__ pos, size_t n,
                                                      const unsigned long long* __restrict__ extent_bits,
                                                      uint64_t* __restrict__ key,
-                                                     uint32_t* __restrict__ idx) {
-  const size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
-  if (i >= n) return;
-  const double4 p = pos[i];
-  double ext = __longlong_as_double(static_cast<long long>(*extent_bits));
-  double cx = 0.0, cy = 0.0, cz = 0.0;
-  uint64_t k = 0;
+                                                     uint32_t* __restrict__ idx, SortPlan plan,
+                                                     unsigned* __restrict__ ghist) {
+  __shared__ unsigned h[8 * 256];
+  for (int j = threadIdx.x; j < 8 * 256; j += 256) h[j] = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const double ext0 = __longlong_as_double(static_cast<long long>(*extent_bits));
+  const size_t stride = size_t(gridDim.x) * 256;
+  // whole warps iterate together (the histogram step is warp-collective)
+  for (size_t base = size_t(blockIdx.x) * 256 + (threadIdx.x & ~31); base < n; base += stride) {
+    const size_t i = base + lane;
+    const bool ok = i < n;
+    uint64_t k = 0;
+    if (ok) {
+      const double4 p = pos[i];
+      double half = ext0;
+      double cx = 0.0, cy = 0.0, cz = 0.0;
 #pragma unroll
-  for (int l = 0; l < TreeDim<DIM>::LM; ++l) {
-    const double half = ext * 0.5;  // == ext / 2.0 in IEEE arithmetic
-    const bool bx = p.x > cx, by = p.y > cy;
-    unsigned digit = unsigned(bx) | (unsigned(by) << 1);
-    cx = bx ? cx + half : cx - half;
-    cy = by ? cy + half : cy - half;
-    if (DIM == 3) {
-      const bool bz = p.z > cz;
-      digit |= unsigned(bz) << 2;
-      cz = bz ? cz + half : cz - half;
+      for (int l = 0; l < TreeDim<DIM>::LM; ++l) {
+        half *= 0.5;  // == extent / 2.0 in IEEE arithmetic
+        const bool bx = p.x > cx, by = p.y > cy;
+        unsigned digit = unsigned(bx) | (unsigned(by) << 1);
+        cx += with_sign(half, !bx);  // x + (-h) == x - h exactly
+        cy += with_sign(half, !by);
+        if (DIM == 3) {
+          const bool bz = p.z > cz;
+          digit |= unsigned(bz) << 2;
+          cz += with_sign(half, !bz);
+        }
+        k = (k << DIM) | digit;
+      }
+      key[i] = k;
+      idx[i] = static_cast<uint32_t>(i);
     }
-    k = (k << DIM) | digit;
-    ext = half;
+    const unsigned okmask = __ballot_sync(FULL, ok);
+    for (int p = 0; p < plan.npass; ++p) {
+      const unsigned d = unsigned(k >> plan.shift(p)) & plan.mask(p);
+      // the high digits are the same for the whole warp: one add; otherwise per-lane adds
+      const unsigned d0 = __shfl_sync(FULL, d, 0);
+      if (__all_sync(FULL, !ok || d == d0)) {
+        if (lane == 0) atomicAdd(&h[p * 256 + d0], unsigned(__popc(okmask)));
+      } else if (ok) {
+        atomicAdd(&h[p * 256 + d], 1u);
+      }
+    }
   }
-  key[i] = k;
-  idx[i] = static_cast<uint32_t>(i);
+  __syncthreads();
+  for (int j = threadIdx.x; j < plan.npass * 256; j += 256)
+    if (h[j]) atomicAdd(&ghist[j], h[j]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -145,36 +201,8 @@ constexpr int SORT_ITEMS = 16;
 constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
 constexpr int SORT_MAX_PASSES = 8;
 constexpr unsigned LB_INCL = 0x80000000u, LB_PART = 0x40000000u, LB_MASK = 0x3fffffffu;
-constexpr unsigned LB_SPIN_LIMIT = 1u << 26;
-
-struct SortPlan {
-  int npass;
-  int shift[SORT_MAX_PASSES];
-  unsigned mask[SORT_MAX_PASSES];
-};
-
-__global__ void __launch_bounds__(256) sort_hist_all(const uint64_t* __restrict__ keys, size_t n,
-                                                     SortPlan plan, unsigned* __restrict__ ghist) {
-  __shared__ unsigned h[SORT_MAX_PASSES * 256];
-  for (int j = threadIdx.x; j < SORT_MAX_PASSES * 256; j += 256) h[j] = 0;
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const size_t stride = size_t(gridDim.x) * 256;
-  // whole warps iterate together (match_any needs every lane)
-  for (size_t base = size_t(blockIdx.x) * 256 + (threadIdx.x & ~31); base < n; base += stride) {
-    const size_t g = base + lane;
-    const bool ok = g < n;
-    const uint64_t k = ok ? keys[g] : 0ull;
-    for (int p = 0; p < plan.npass; ++p) {
-      const unsigned d = ok ? unsigned((k >> plan.shift[p]) & plan.mask[p]) : 256u;
-      const unsigned peers = __match_any_sync(FULL, d);
-      if (ok && (peers & ((1u << lane) - 1u)) == 0u) atomicAdd(&h[p * 256 + d], unsigned(__popc(peers)));
-    }
-  }
-  __syncthreads();
-  for (int j = threadIdx.x; j < plan.npass * 256; j += 256)
-    if (h[j]) atomicAdd(&ghist[j], h[j]);
-}
+constexpr unsigned LB_SPIN_LIMIT = 1u << 24;
+constexpr int LB_BATCH = 16;
 
 __global__ void __launch_bounds__(SORT_THREADS, 2) sort_onesweep_pass(
     const uint64_t* __restrict__ kin, const uint32_t* __restrict__ vin, uint64_t* __restrict__ kout,
@@ -204,8 +232,8 @@ __global__ void __launch_bounds__(SORT_THREADS, 2) sort_onesweep_pass(
 #pragma unroll
   for (int i = 0; i < SORT_ITEMS; ++i) {
     const bool ok = (base + size_t(i) * 32 + lane) < n;
-    const unsigned d = ok ? unsigned((k[i] >> shift) & mask) : 256u;
-    const unsigned peers = __match_any_sync(FULL, d);
+    const unsigned d = unsigned((k[i] >> shift) & mask);
+    const unsigned peers = peers_of(d, ok);
     const unsigned before = ok ? whist[warp][d] : 0u;
     __syncwarp();
     const unsigned r = __popc(peers & ((1u << lane) - 1u));
@@ -229,20 +257,35 @@ __global__ void __launch_bounds__(SORT_THREADS, 2) sort_onesweep_pass(
       *st = cnt | LB_INCL;
     } else {
       *st = cnt | LB_PART;
-      unsigned t = tile - 1;
+      // walk back over the predecessors, LB_BATCH status words in flight at a time (the tiles of
+      // one wave publish their partial counts at about the same moment, so the walk is long)
+      unsigned t = tile;  // tiles t-1, t-2, ... remain to be examined
       unsigned spins = 0;
-      for (;;) {
-        const unsigned val = *reinterpret_cast<volatile unsigned*>(status + size_t(t) * 256 + tid);
-        if ((val & (LB_INCL | LB_PART)) == 0u) {
-          if (++spins > LB_SPIN_LIMIT) {  // never expected; avoids an unbounded hang
-            atomicExch(err_flag, 1u);
-            break;
+      bool done = false;
+      while (!done) {
+        unsigned vals[LB_BATCH];
+#pragma unroll
+        for (int j = 0; j < LB_BATCH; ++j)
+          vals[j] = (t > unsigned(j))
+                        ? *reinterpret_cast<volatile unsigned*>(status + size_t(t - 1 - j) * 256 + tid)
+                        : unsigned(LB_INCL);  // before tile 0: inclusive prefix 0
+        unsigned used = 0;
+#pragma unroll
+        for (int j = 0; j < LB_BATCH; ++j) {
+          if (!done && used == unsigned(j)) {
+            const unsigned val = vals[j];
+            if ((val & (LB_INCL | LB_PART)) != 0u) {
+              prefix += val & LB_MASK;
+              ++used;
+              if (val & LB_INCL) done = true;
+            }
           }
-          continue;
         }
-        prefix += val & LB_MASK;
-        if (val & LB_INCL) break;
-        --t;  // tile 0 always publishes INCL, so t never underflows
+        t -= used;
+        if (used == 0u && ++spins > LB_SPIN_LIMIT) {  // never expected; avoids an unbounded hang
+          atomicExch(err_flag, 1u);
+          break;
+        }
       }
       *st = ((prefix + cnt) & LB_MASK) | LB_INCL;
     }
@@ -378,7 +421,8 @@ __global__ void __launch_bounds__(256) unit_kernel(const uint64_t* __restrict__ 
         }
       }
     }
-    ab[s] = make_uchar2(static_cast<unsigned char>(a + 1), static_cast<unsigned char>(b + 1));
+    ab[s] = head ? make_uchar2(static_cast<unsigned char>(a + 1), static_cast<unsigned char>(b + 1))
+                 : make_uchar2(255, 255);  // NOT_HEAD: merged into the unit before it
     cnt[s] = head ? unsigned(max(0, b - a) + 1) : 0u;
   }
   // sizes the next sort and validates this one (a truncated sort is exact iff no two neighbours
@@ -390,6 +434,10 @@ __global__ void __launch_bounds__(256) unit_kernel(const uint64_t* __restrict__ 
 // ---------------------------------------------------------------------------------------------
 // K6  cell table in DFS pre-order (children in ascending digit order).
 //     cell(head s, level l) = cell_start[s] + (l - (a_s + 1)).
+//     Run ends and parents come from short linear scans over the per-body shared-level bytes
+//     (`ab`, L1-resident) with a galloping search on the keys as the fallback for large cells.
+//     Cells with <= SMALL_CELL bodies also get their mass / centre of mass here, by summing their
+//     bodies in order; only the larger cells are left to the bottom-up pass (K7).
 // ---------------------------------------------------------------------------------------------
 struct CellArrays {
   uint8_t* level;
@@ -403,32 +451,58 @@ struct CellArrays {
   uint32_t capacity;
 };
 
+constexpr uint32_t SMALL_CELL = 16;
+constexpr unsigned char NOT_HEAD = 255;  // ab[j].x of a body merged into the unit before it
+
+// {x, y, z, m} of the leaf made of sorted bodies [s, e): masses add, the member inserted last
+// (largest original index) keeps its place (octree.rs:69-80)
+__device__ __forceinline__ double4 unit_leaf(const double4* __restrict__ sp,
+                                             const uint32_t* __restrict__ perm, size_t s, size_t e) {
+  double4 q = sp[s];
+  if (e > s + 1) {
+    double m = 0.0;
+    size_t newest = s;
+    uint32_t newest_idx = perm[s];
+    for (size_t j = s; j < e; ++j) {
+      m += sp[j].w;
+      const uint32_t pj = perm[j];
+      if (pj > newest_idx) { newest_idx = pj; newest = j; }
+    }
+    q = sp[newest];
+    q.w = m;
+  }
+  return q;
+}
+
+// K6a  one thread per unit head: the chain of cells it heads (levels a+1 .. leaf level) gets its
+//      level, head, geometric centre / half-width (replaying the head's key digits), in-chain
+//      parent links, and the leaf its body data.
 template <int DIM>
-__global__ void __launch_bounds__(128) fill_kernel(const uint64_t* __restrict__ key,
-                                                   const double4* __restrict__ sp,
-                                                   const uint32_t* __restrict__ perm,
-                                                   const uchar2* __restrict__ ab,
-                                                   const uint32_t* __restrict__ cell_start, size_t n,
-                                                   const unsigned long long* __restrict__ extent_bits,
-                                                   CellArrays cells) {
+__global__ void __launch_bounds__(256) chain_kernel(const uint64_t* __restrict__ key,
+                                                    const double4* __restrict__ sp,
+                                                    const uint32_t* __restrict__ perm,
+                                                    const uchar2* __restrict__ ab,
+                                                    const uint32_t* __restrict__ cell_start, size_t n,
+                                                    const unsigned long long* __restrict__ extent_bits,
+                                                    CellArrays cells) {
   constexpr int LM = TreeDim<DIM>::LM;
   const size_t s = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
   if (s >= n) return;
-  if (cell_start[n] > cells.capacity) return;  // host grows the table and re-runs
-  const uint32_t c0 = cell_start[s];
-  if (cell_start[s + 1] == c0) return;  // not a unit head
+  const uint32_t total = cell_start[n];
+  if (total > cells.capacity) return;  // host grows the table and re-runs
   const uchar2 abv = ab[s];
+  if (abv.x == NOT_HEAD) return;
+  const uint32_t c0 = cell_start[s];
   const int a = int(abv.x) - 1, b = int(abv.y) - 1;
   const int top = a + 1, leaf_level = max(a, b) + 1;
   size_t e_unit = s + 1;
-  while (e_unit < n && cell_start[e_unit + 1] == cell_start[e_unit]) ++e_unit;
+  while (e_unit < n && ab[e_unit].x == NOT_HEAD) ++e_unit;
   const uint64_t kme = key[s];
   const double4 me = sp[s];
 
-  // geometric centre of the level-`top` cell: replay the head's digits from the root
-  double ext = __longlong_as_double(static_cast<long long>(*extent_bits));
+  double half = __longlong_as_double(static_cast<long long>(*extent_bits));
   double cx = 0.0, cy = 0.0, cz = 0.0;
-  auto descend = [&](int l) {  // from level l to level l+1
+  auto descend = [&](int l) {  // from level l to level l+1 along the head body's path
     unsigned digit;
     if (l < LM) {
       digit = unsigned((kme >> (DIM * (LM - 1 - l))) & ((1u << DIM) - 1u));
@@ -436,121 +510,139 @@ __global__ void __launch_bounds__(128) fill_kernel(const uint64_t* __restrict__ 
       digit = unsigned(me.x > cx) | (unsigned(me.y > cy) << 1);
       if (DIM == 3) digit |= unsigned(me.z > cz) << 2;
     }
-    const double half = ext * 0.5;
-    cx = (digit & 1u) ? cx + half : cx - half;
-    cy = (digit & 2u) ? cy + half : cy - half;
-    if (DIM == 3) cz = (digit & 4u) ? cz + half : cz - half;
-    ext = half;
+    half *= 0.5;
+    cx += with_sign(half, !(digit & 1u));
+    cy += with_sign(half, !(digit & 2u));
+    if (DIM == 3) cz += with_sign(half, !(digit & 4u));
   };
   for (int l = 0; l < top; ++l) descend(l);
 
-  // parent of the top cell
-  uint32_t parent_of_top = NO_PARENT;
-  if (top > 0) {
-    const int pl = top - 1;  // parent level, <= LM
-    const int shift = DIM * (LM - pl);
-    // first sorted body h sharing pl levels with s: gallop backwards, then bisect
-    auto same = [&](size_t j) {
-      return shift >= 64 ? true : ((key[j] >> shift) == (kme >> shift));
-    };
-    size_t lo = s, step = 1;  // invariant: same(lo)
-    size_t bad = size_t(-1);  // highest known index with !same (or -1)
-    while (true) {
-      if (lo == 0) break;
-      const size_t probe = lo >= step ? lo - step : 0;
-      if (same(probe)) {
-        lo = probe;
-        step <<= 1;
-      } else {
-        bad = probe;
-        break;
-      }
-    }
-    if (bad != size_t(-1)) {
-      size_t l2 = bad, h2 = lo;  // !same(l2), same(h2)
-      while (h2 - l2 > 1) {
-        const size_t mid = l2 + (h2 - l2) / 2;
-        if (same(mid)) h2 = mid; else l2 = mid;
-      }
-      lo = h2;
-    }
-    const size_t h = lo;
-    const int ah = int(ab[h].x) - 1;
-    parent_of_top = cell_start[h] + uint32_t(pl - (ah + 1));
-  }
-
   for (int lev = top; lev <= leaf_level; ++lev) {
     const uint32_t c = c0 + uint32_t(lev - top);
-    size_t e;
-    if (lev == leaf_level) {
-      e = e_unit;
-    } else {
-      // end of the run of bodies sharing `lev` levels with s: gallop forward from the unit end
-      const int shift = DIM * (LM - lev);  // lev <= LM here
-      auto same = [&](size_t j) {
-        return shift >= 64 ? true : ((key[j] >> shift) == (kme >> shift));
-      };
-      size_t lo = e_unit - 1, step = 1;  // same(lo)
-      size_t bad = n;                    // lowest known index with !same (or n)
-      while (true) {
-        const size_t probe = lo + step;
-        if (probe >= n) break;
-        if (same(probe)) {
-          lo = probe;
-          step <<= 1;
-        } else {
-          bad = probe;
-          break;
-        }
-      }
-      if (bad == n && lo + 1 < n) {  // ran off the end while galloping: bisect (lo, n)
-        size_t l2 = lo, h2 = n;      // same(l2), "!same"(h2 = n sentinel)
-        while (h2 - l2 > 1) {
-          const size_t mid = l2 + (h2 - l2) / 2;
-          if (same(mid)) l2 = mid; else h2 = mid;
-        }
-        e = h2;
-      } else if (bad == n) {
-        e = n;
-      } else {
-        size_t l2 = lo, h2 = bad;
-        while (h2 - l2 > 1) {
-          const size_t mid = l2 + (h2 - l2) / 2;
-          if (same(mid)) l2 = mid; else h2 = mid;
-        }
-        e = h2;
-      }
-    }
     cells.level[c] = static_cast<uint8_t>(lev);
     cells.head[c] = static_cast<uint32_t>(s);
-    cells.count[c] = static_cast<uint32_t>(e - s);
-    cells.skip[c] = cell_start[e];
-    cells.parent[c] = (lev == top) ? parent_of_top : c - 1;
     cells.arrived[c] = 0u;
-    cells.centre_ext[c] = make_double4(cx, cy, cz, ext);
+    cells.centre_ext[c] = make_double4(cx, cy, cz, half);
     if (lev == leaf_level) {
-      // merged leaf: masses add, the member inserted last (largest original index) keeps its place
-      double m = 0.0;
-      size_t newest = s;
-      uint32_t newest_idx = perm[s];
-      for (size_t j = s; j < e_unit; ++j) {
-        m += sp[j].w;
-        const uint32_t pj = perm[j];
-        if (pj > newest_idx) { newest_idx = pj; newest = j; }
-      }
-      const double4 q = sp[newest];
-      cells.com[c] = make_double4(q.x, q.y, q.z, m);
+      cells.count[c] = static_cast<uint32_t>(e_unit - s);
+      cells.skip[c] = cell_start[e_unit];
+      cells.com[c] = unit_leaf(sp, perm, s, e_unit);
     } else {
       descend(lev);
     }
   }
 }
 
+// K6b  one thread per cell.  In DFS pre-order the first later cell that is not deeper is the next
+//      non-descendant, so the skip link comes from a forward scan over the level bytes (8 cells
+//      per 64-bit load); subtrees of more than TOPO_SCAN cells fall back to a galloping search on
+//      the sorted keys.  The body count follows from the heads, and cells with <= SMALL_CELL bodies
+//      get their mass / centre of mass by summing their units in order.
+constexpr uint32_t TOPO_SCAN = 512;
+
+// index (0..7) of the first byte >= `from` of the little-endian word w that is <= lev, or 8
+__device__ __forceinline__ int first_byte_le(unsigned long long w, int lev, int from) {
+  const unsigned long long ones = 0x0101010101010101ull, highs = 0x8080808080808080ull;
+  // per byte: (b | 0x80) - (lev + 1) keeps its high bit iff b > lev (levels are < 64)
+  const unsigned long long t = (w | highs) - ones * static_cast<unsigned long long>(lev + 1);
+  unsigned long long m = ~t & highs;
+  if (from > 0) m &= ~0ull << (8 * from);
+  return m ? (__ffsll(static_cast<long long>(m)) - 1) >> 3 : 8;
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(256) skip_kernel(const uint64_t* __restrict__ key,
+                                                   const double4* __restrict__ sp,
+                                                   const uint32_t* __restrict__ perm,
+                                                   const uchar2* __restrict__ ab,
+                                                   const uint32_t* __restrict__ cell_start, size_t n,
+                                                   CellArrays cells) {
+  constexpr int LM = TreeDim<DIM>::LM;
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t total = cell_start[n];
+  if (total > cells.capacity || c >= total) return;
+  if (c == 0u) cells.parent[0] = NO_PARENT;
+  const int lev = cells.level[c];
+  const size_t s = cells.head[c];
+
+  uint32_t skip = total;
+  size_t e = n;  // first sorted body past this cell's run
+  {
+    const unsigned long long* words = reinterpret_cast<const unsigned long long*>(cells.level);
+    const uint32_t lim = min(total, c + 1u + TOPO_SCAN);
+    uint32_t i = c + 1u;  // next cell to examine
+    uint32_t hit = lim;
+    while (i < lim) {
+      const uint32_t wi = i >> 3;
+      const int k = first_byte_le(words[wi], lev, int(i & 7u));
+      if (k < 8) {
+        hit = min(lim, (wi << 3) + uint32_t(k));
+        break;
+      }
+      i = (wi + 1u) << 3;
+    }
+    if (hit < lim) {
+      skip = hit;
+      e = cells.head[hit];
+    } else if (lim < total) {
+      // big subtree: cells c+1 .. lim-1 are descendants, so head[lim-1] lies inside the run; gallop
+      // on the keys from there (lev <= LM: a cell with descendants is not at the pseudo level)
+      const int shift = DIM * (LM - lev);
+      const uint64_t pre = shift >= 64 ? 0ull : (key[s] >> shift);
+      auto shares = [&](size_t j) { return shift >= 64 ? true : ((key[j] >> shift) == pre); };
+      size_t lo = cells.head[lim - 1u], step = 1, bad = n;
+      while (true) {
+        const size_t probe = lo + step;
+        if (probe >= n) break;
+        if (shares(probe)) { lo = probe; step <<= 1; } else { bad = probe; break; }
+      }
+      size_t l2 = lo, h2 = bad;
+      while (h2 - l2 > 1) {
+        const size_t mid = l2 + (h2 - l2) / 2;
+        if (shares(mid)) l2 = mid; else h2 = mid;
+      }
+      e = h2;
+      skip = cell_start[e];
+    }
+  }
+  if (skip == c + 1u) return;  // leaf: count, skip and body data were written by K6a
+  const uint32_t cnt = static_cast<uint32_t>(e - s);
+  cells.count[c] = cnt;
+  cells.skip[c] = skip;
+  if (cnt <= SMALL_CELL) {
+    double sm = 0.0, sx = 0.0, sy = 0.0, sz = 0.0;
+    for (size_t j = s; j < e;) {  // units in order
+      size_t je = j + 1;
+      while (je < e && ab[je].x == NOT_HEAD) ++je;
+      const double4 q = unit_leaf(sp, perm, j, je);
+      sm += q.w; sx += q.w * q.x; sy += q.w * q.y; sz += q.w * q.z;
+      j = je;
+    }
+    // a massless cell (the reference panics there): geometric centre instead of 0/0
+    const double4 g = cells.centre_ext[c];
+    cells.com[c] = sm != 0.0 ? make_double4(sx / sm, sy / sm, sz / sm, sm)
+                             : make_double4(g.x, g.y, g.z, 0.0);
+  }
+}
+
+// K6c  one thread per internal cell: its children are p+1, skip[p+1], ... (at most 2^DIM of them,
+//      whatever the size of the cell), each gets its parent link.
+__global__ void __launch_bounds__(256) parent_kernel(const uint32_t* __restrict__ cell_start, size_t n,
+                                                     CellArrays cells) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t total = cell_start[n];
+  if (total > cells.capacity || p >= total) return;
+  const uint32_t end = cells.skip[p];
+  for (uint32_t ch = p + 1u; ch < end; ch = cells.skip[ch]) cells.parent[ch] = p;
+}
+
 // ---------------------------------------------------------------------------------------------
-// K7  bottom-up masses and centres of mass.  One thread per leaf climbs; the child that completes
-//     a cell (arrived bodies == cell bodies) sums the children in pre-order and continues upward.
-//     (reference: incremental pairwise update, octree.rs:83-88 / lib.rs:40-50 — same value up to
-//     fp64 rounding; zero-mass cells, where the reference panics, fall back to the geometric centre)
+// K7  bottom-up masses and centres of mass of the cells with more than SMALL_CELL bodies.
+//     One thread per unit: the shallowest cell of its chain that K6 already finished climbs; the
+//     child whose arrival completes a cell (arrived bodies == cell bodies) sums the children in
+//     pre-order and continues upward.  (reference: incremental pairwise update, octree.rs:83-88 /
+//     lib.rs:40-50 — same value up to fp64 rounding; zero-mass cells fall back to the geometric
+//     centre.)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ double4 ld_cg_double4(const double4* p) {
   const double2 lo = __ldcg(reinterpret_cast<const double2*>(p));
@@ -558,13 +650,25 @@ __device__ __forceinline__ double4 ld_cg_double4(const double4* p) {
   return make_double4(lo.x, lo.y, hi.x, hi.y);
 }
 
-__global__ void __launch_bounds__(128) com_kernel(const uint32_t* __restrict__ cell_start, size_t n,
+__device__ __forceinline__ bool done_in_fill(const CellArrays& cells, uint32_t c) {
+  return cells.count[c] <= SMALL_CELL || cells.skip[c] == c + 1u;
+}
+
+__global__ void __launch_bounds__(128) com_kernel(const uchar2* __restrict__ ab,
+                                                  const uint32_t* __restrict__ cell_start, size_t n,
                                                   CellArrays cells) {
   const size_t s = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
   if (s >= n) return;
   if (cell_start[n] > cells.capacity) return;
-  if (cell_start[s + 1] == cell_start[s]) return;
-  uint32_t c = cell_start[s + 1] - 1;  // this unit's leaf
+  if (ab[s].x == NOT_HEAD) return;
+  // chain of cells headed by s: c0 (shallowest) .. c_last (leaf); body counts shrink with depth
+  const uint32_t c0 = cell_start[s], c_last = cell_start[s + 1] - 1;
+  uint32_t c = c0;
+  while (c < c_last && !done_in_fill(cells, c)) ++c;  // shallowest finished cell of the chain
+  if (c == c0) {
+    const uint32_t p = cells.parent[c0];
+    if (p == NO_PARENT || done_in_fill(cells, p)) return;  // an ancestor's sum already covers it
+  }
   while (true) {
     const uint32_t p = cells.parent[c];
     if (p == NO_PARENT) break;
@@ -837,46 +941,50 @@ cudaError_t exclusive_scan(const uint32_t* in, uint32_t* out, size_t n, DevBuf& 
   return cudaGetLastError();
 }
 
-// sorts key bits [lo, key_bits); returns with ws.sorted_key / ws.perm pointing at the result
-cudaError_t radix_sort(GravityWorkspace& ws, size_t n, int key_bits, int lo, cudaStream_t st,
-                       LaunchStats& ls) {
-  const unsigned tiles = blocks_for(n, SORT_TILE);
+struct SortBuffers {
   SortPlan plan;
+  unsigned tiles;
+  unsigned *ghist, *counters, *err_flag, *status;
+};
+
+// plans the passes over key bits [lo, key_bits) and clears histograms / look-back state
+cudaError_t sort_prepare(GravityWorkspace& ws, size_t n, int key_bits, int lo, cudaStream_t st,
+                         SortBuffers* sb) {
+  sb->tiles = blocks_for(n, SORT_TILE);
+  SortPlan& plan = sb->plan;
   const int total = key_bits - lo;
   plan.npass = (total + 7) / 8;
-  {
-    int at = lo;
-    for (int p = 0; p < plan.npass; ++p) {
-      const int width = total / plan.npass + (p < total % plan.npass ? 1 : 0);
-      plan.shift[p] = at;
-      plan.mask[p] = (1u << width) - 1u;
-      at += width;
-    }
-  }
-  // [ghist: 8 x 256][tile counters: 8][error flag][status: npass x tiles x 256]
+  plan.lo = lo;
+  plan.base = total / plan.npass;
+  plan.rem = total % plan.npass;
+  // [ghist: 8 x 256][tile counters: 8][error flag + pad: 8][status: npass x tiles x 256]
   const size_t head_words = SORT_MAX_PASSES * 256 + SORT_MAX_PASSES + 8;
-  const size_t words = head_words + size_t(plan.npass) * tiles * 256;
+  const size_t words = head_words + size_t(plan.npass) * sb->tiles * 256;
   PB_PASS(ws.tile_counts.ensure(words * 4));
-  unsigned* ghist = ws.tile_counts.as<unsigned>();
-  unsigned* counters = ghist + SORT_MAX_PASSES * 256;
-  unsigned* err_flag = counters + SORT_MAX_PASSES;
-  unsigned* status = ghist + head_words;
-  PB_CUDA(cudaMemsetAsync(ghist, 0, words * 4, st));
+  sb->ghist = ws.tile_counts.as<unsigned>();
+  sb->counters = sb->ghist + SORT_MAX_PASSES * 256;
+  sb->err_flag = sb->counters + SORT_MAX_PASSES;
+  sb->status = sb->ghist + head_words;
+  PB_CUDA(cudaMemsetAsync(sb->ghist, 0, words * 4, st));
+  ws.sort_err_flag = sb->err_flag;
+  return cudaSuccess;
+}
+
+// the passes; returns with ws.sorted_key / ws.perm pointing at the result
+cudaError_t sort_passes(GravityWorkspace& ws, size_t n, const SortBuffers& sb, cudaStream_t st,
+                        LaunchStats& ls) {
   uint64_t* k[2] = {ws.key0.as<uint64_t>(), ws.key1.as<uint64_t>()};
   uint32_t* v[2] = {ws.idx0.as<uint32_t>(), ws.idx1.as<uint32_t>()};
-  PB_LAUNCH(ls, st, "sort_hist_all",
-            sort_hist_all<<<min(blocks_for(n, 256), 148u * 8u), 256, 0, st>>>(k[0], n, plan, ghist));
   int cur = 0;
-  for (int p = 0; p < plan.npass; ++p) {
+  for (int p = 0; p < sb.plan.npass; ++p) {
     PB_LAUNCH(ls, st, "sort_onesweep_pass",
-              sort_onesweep_pass<<<tiles, SORT_THREADS, 0, st>>>(
-                  k[cur], v[cur], k[cur ^ 1], v[cur ^ 1], n, plan.shift[p], plan.mask[p], ghist + p * 256,
-                  status + size_t(p) * tiles * 256, counters + p, err_flag));
+              sort_onesweep_pass<<<sb.tiles, SORT_THREADS, 0, st>>>(
+                  k[cur], v[cur], k[cur ^ 1], v[cur ^ 1], n, sb.plan.shift(p), sb.plan.mask(p),
+                  sb.ghist + p * 256, sb.status + size_t(p) * sb.tiles * 256, sb.counters + p, sb.err_flag));
     cur ^= 1;
   }
   ws.sorted_key = k[cur];
   ws.perm = v[cur];
-  ws.sort_err_flag = err_flag;
   return cudaGetLastError();
 }
 
@@ -904,9 +1012,13 @@ cudaError_t tree_evaluate(GravityWorkspace& ws, const GravityParams& prm, size_t
   ws.last_lo = lo;
   const unsigned nb = blocks_for(n, 256);
   PB_LAUNCH(ls, st, "extent_kernel", extent_kernel<<<min(nb, 148u * 8u), 256, 0, st>>>(ws.pos64, n, ws.extent_bits.as<unsigned long long>()));
-  PB_LAUNCH(ls, st, "encode_kernel", encode_kernel<DIM><<<nb, 256, 0, st>>>(ws.pos64, n, ws.extent_bits.as<unsigned long long>(),
-                                         ws.key0.as<uint64_t>(), ws.idx0.as<uint32_t>()));
-  PB_PASS(radix_sort(ws, n, key_bits, lo, st, ls));
+  SortBuffers sb;
+  PB_PASS(sort_prepare(ws, n, key_bits, lo, st, &sb));
+  PB_LAUNCH(ls, st, "encode_kernel",
+            encode_kernel<DIM><<<min(nb, 148u * 4u), 256, 0, st>>>(
+                ws.pos64, n, ws.extent_bits.as<unsigned long long>(), ws.key0.as<uint64_t>(),
+                ws.idx0.as<uint32_t>(), sb.plan, sb.ghist));
+  PB_PASS(sort_passes(ws, n, sb, st, ls));
   PB_LAUNCH(ls, st, "gather_kernel", gather_kernel<<<nb, 256, 0, st>>>(ws.pos64, ws.perm, n, ws.spos64.as<double4>()));
   PB_LAUNCH(ls, st, "unit_kernel", unit_kernel<DIM><<<nb, 256, 0, st>>>(ws.sorted_key, ws.spos64.as<double4>(), n, ws.ab.as<uchar2>(),
                                        ws.tgt_flags.as<uint32_t>(), max_shared_plus1));
@@ -917,7 +1029,7 @@ cudaError_t tree_evaluate(GravityWorkspace& ws, const GravityParams& prm, size_t
   if (cap < ws.cell_cap) cap = ws.cell_cap;  // never shrink
   if (cap > 0xfffffff0ull) cap = 0xfffffff0ull;
   ws.cell_cap = cap;
-  PB_PASS(ws.c_level.ensure(cap));
+  PB_PASS(ws.c_level.ensure(cap + 16));
   PB_PASS(ws.c_head.ensure(cap * 4));
   PB_PASS(ws.c_count.ensure(cap * 4));
   PB_PASS(ws.c_skip.ensure(cap * 4));
@@ -929,10 +1041,17 @@ cudaError_t tree_evaluate(GravityWorkspace& ws, const GravityParams& prm, size_t
                    ws.c_skip.as<uint32_t>(),   ws.c_parent.as<uint32_t>(), ws.c_arrived.as<uint32_t>(),
                    ws.c_centre_ext.as<double4>(), ws.c_com.as<double4>(), static_cast<uint32_t>(cap)};
   const unsigned nb128 = blocks_for(n, 128);
-  PB_LAUNCH(ls, st, "fill_kernel", fill_kernel<DIM><<<nb128, 128, 0, st>>>(ws.sorted_key, ws.spos64.as<double4>(), ws.perm,
-                                          ws.ab.as<uchar2>(), ws.cell_start.as<uint32_t>(), n,
-                                          ws.extent_bits.as<unsigned long long>(), cells));
-  PB_LAUNCH(ls, st, "com_kernel", com_kernel<<<nb128, 128, 0, st>>>(ws.cell_start.as<uint32_t>(), n, cells));
+  PB_LAUNCH(ls, st, "chain_kernel",
+            chain_kernel<DIM><<<nb, 256, 0, st>>>(ws.sorted_key, ws.spos64.as<double4>(), ws.perm,
+                                                  ws.ab.as<uchar2>(), ws.cell_start.as<uint32_t>(), n,
+                                                  ws.extent_bits.as<unsigned long long>(), cells));
+  PB_LAUNCH(ls, st, "skip_kernel",
+            skip_kernel<DIM><<<blocks_for(cap, 256), 256, 0, st>>>(
+                ws.sorted_key, ws.spos64.as<double4>(), ws.perm, ws.ab.as<uchar2>(),
+                ws.cell_start.as<uint32_t>(), n, cells));
+  PB_LAUNCH(ls, st, "parent_kernel",
+            parent_kernel<<<blocks_for(cap, 256), 256, 0, st>>>(ws.cell_start.as<uint32_t>(), n, cells));
+  PB_LAUNCH(ls, st, "com_kernel", com_kernel<<<nb128, 128, 0, st>>>(ws.ab.as<uchar2>(), ws.cell_start.as<uint32_t>(), n, cells));
 
   const uint32_t* list = nullptr;
   const size_t n_targets = t1 - t0;

@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(256) verlet_kernel(double4* __restrict__ cur, 
                                                      double4* __restrict__ vel,
                                                      const float4* __restrict__ acc32,
                                                      const double* __restrict__ acc64, size_t n,
-                                                     double dt, double dt2) {
+                                                     double dt, double dt2, double2* __restrict__ out6) {
   const size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
   if (i >= n) return;
   const double4 x = cur[i];
@@ -64,26 +64,31 @@ __global__ void __launch_bounds__(256) verlet_kernel(double4* __restrict__ cur, 
   prev[i] = x;
   cur[i] = nx;
   vel[i] = nv;
+  if (out6) {  // packed {x,y,z,vx,vy,vz} for the D2H copy at the host boundary (48 B/body)
+    out6[3 * i] = make_double2(nx.x, nx.y);
+    out6[3 * i + 1] = make_double2(nx.z, nv.x);
+    out6[3 * i + 2] = make_double2(nv.y, nv.z);
+  }
 }
 
 }  // namespace
 
 cudaError_t verlet_update(double4* cur, double4* prev, double4* vel, const float4* acc32,
                           const double* acc64, size_t n, double dt, int first, cudaStream_t st,
-                          LaunchStats& ls) {
+                          LaunchStats& ls, double* out6) {
   if (n == 0) return cudaSuccess;
   const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
   const double dt2 = dt * dt;  // dt.powi(2)
   if (acc64) {
     if (first)
-      PB_LAUNCH(ls, st, "verlet_kernel", verlet_kernel<true, true><<<blocks, 256, 0, st>>>(cur, prev, vel, acc32, acc64, n, dt, dt2));
+      PB_LAUNCH(ls, st, "verlet_kernel", verlet_kernel<true, true><<<blocks, 256, 0, st>>>(cur, prev, vel, acc32, acc64, n, dt, dt2, reinterpret_cast<double2*>(out6)));
     else
-      PB_LAUNCH(ls, st, "verlet_kernel", verlet_kernel<false, true><<<blocks, 256, 0, st>>>(cur, prev, vel, acc32, acc64, n, dt, dt2));
+      PB_LAUNCH(ls, st, "verlet_kernel", verlet_kernel<false, true><<<blocks, 256, 0, st>>>(cur, prev, vel, acc32, acc64, n, dt, dt2, reinterpret_cast<double2*>(out6)));
   } else {
     if (first)
-      PB_LAUNCH(ls, st, "verlet_kernel", verlet_kernel<true, false><<<blocks, 256, 0, st>>>(cur, prev, vel, acc32, acc64, n, dt, dt2));
+      PB_LAUNCH(ls, st, "verlet_kernel", verlet_kernel<true, false><<<blocks, 256, 0, st>>>(cur, prev, vel, acc32, acc64, n, dt, dt2, reinterpret_cast<double2*>(out6)));
     else
-      PB_LAUNCH(ls, st, "verlet_kernel", verlet_kernel<false, false><<<blocks, 256, 0, st>>>(cur, prev, vel, acc32, acc64, n, dt, dt2));
+      PB_LAUNCH(ls, st, "verlet_kernel", verlet_kernel<false, false><<<blocks, 256, 0, st>>>(cur, prev, vel, acc32, acc64, n, dt, dt2, reinterpret_cast<double2*>(out6)));
   }
   return cudaGetLastError();
 }
