@@ -73,47 +73,46 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons DURING the timed region, sampled in-process through NVML
+    (same counters as the nvidia-smi line of B200_PROFILING.md, without its start-up latency)."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown",
+               0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown"}
 
-    def __init__(self, gpu_index=0):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+    def __init__(self, gpu_index=0, period=0.005):
+        self.gpu, self.period = gpu_index, period
+        self.sm, self.mask, self.max_mhz, self.err = [], 0, None, None
+        self._stop = threading.Event()
+        self.thread = None
+
+    def _run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not self._stop.is_set():
+                self.sm.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                self.mask |= int(get_reasons(h))
+                time.sleep(self.period)
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = set()
-        for r in self.rows:
-            if len(r) >= 9:
-                for k, nm in enumerate(names):
-                    if r[5 + k].lower().startswith("active"):
-                        reasons.add(nm)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        self._stop.set()
+        if self.thread:
+            self.thread.join(timeout=2)
+        reasons = [n for bit, n in self.REASONS.items() if self.mask & bit]
+        out = {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.max_mhz,
+               "samples": len(self.sm), "reasons": reasons}
+        if self.err:
+            out["error"] = self.err
+        return out
 
 
 def cpu_info():
@@ -340,12 +339,15 @@ def measure_direct(api, args, hbm_peak):
     from physim_b200 import generators as gen
     n = 1 << 24
     state = gen.cube(n, seed=1)
-    parts = 64
+    parts = 28  # 599,186 targets = 2 full waves of the 4-targets-per-thread CTAs (296 CTAs per wave)
     sim = api.Sim("astro2", theta=0.0, e=0.5, dt=1e-6, rank=0, world=parts)
     sim.upload(state)
     sim.run_timed(1)
-    steps = 3
+    steps = 2
+    sampler = ClockSampler(0, period=0.02)
+    sampler.start()
     ms = sim.run_timed(steps)
+    clocks = sampler.stop()
     n_t = n // parts
     inter = n_t * n * steps
     rate = inter / (ms * 1e-3)
@@ -358,7 +360,7 @@ def measure_direct(api, args, hbm_peak):
     return {"workload": "cube n=16777216 ! astro2 theta=0 e=0.5 (all pairs)",
             "sample": f"targets [0, {n_t}) x all {n} sources, {steps} evaluations",
             "interactions_per_s": rate, "ms_per_evaluation": ms / steps,
-            "full_step_s_extrapolated": n * n / rate,
+            "full_step_s_extrapolated": n * n / rate, "clocks": clocks,
             "roofline": {"bound": "fp32", "achieved": tf, "unit": "TFLOP/s", "flop_per_interaction": 19,
                          "peak": nominal, "peak_source": f"{sms} SMs x 128 lanes x 2 x 1.965 GHz (max boost)",
                          "frac": tf / nominal, "ffma_probe_tflops": fp32_probe,
@@ -385,7 +387,7 @@ def measure_cpu(state, w):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))

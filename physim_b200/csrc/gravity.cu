@@ -9,6 +9,7 @@
 // warp-cooperative walk with per-lane acceptance.  oracle/physim_oracle.cpp ("oracle 2") builds the
 // same table on the CPU; tests compare the two bit for bit.
 #include <algorithm>
+#include <cmath>
 
 #include "common.cuh"
 
@@ -874,6 +875,115 @@ __global__ void __launch_bounds__(DIRECT_THREADS) direct_kernel(
   }
 }
 
+// ---- packed variant: Blackwell's FFMA2 / FADD2 / FMUL2 (fma/add/sub/mul .f32x2) process two fp32
+// values per issue slot.  Two SOURCES are paired per instruction (the target's coordinates are a
+// loop-invariant broadcast pair), so one interaction costs 6.5 FP32 issue slots + 1 MUFU instead of
+// 13 + 1 and the kernel is bound by the FP32 pipe instead of by instruction issue.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+template <int T>
+__global__ void __launch_bounds__(DIRECT_THREADS) direct_kernel_x2(
+    const float4* __restrict__ src, size_t n_src, size_t src_per_split, size_t t0, size_t n_targets,
+    float easing, float tiny, float4* __restrict__ part /* [splits][n_targets] */) {
+  // SoA tile: consecutive sources are adjacent, so an aligned 16-byte read yields two source pairs
+  __shared__ __align__(16) float tx[DIRECT_TILE];
+  __shared__ __align__(16) float ty[DIRECT_TILE];
+  __shared__ __align__(16) float tz[DIRECT_TILE];
+  __shared__ __align__(16) float tm[DIRECT_TILE];
+  const size_t tbase = size_t(blockIdx.x) * (DIRECT_THREADS * T);
+  f32x2 px[T], py[T], pz[T], ax[T], ay[T], az[T];
+#pragma unroll
+  for (int k = 0; k < T; ++k) {
+    const size_t lt = tbase + size_t(k) * DIRECT_THREADS + threadIdx.x;
+    const float4 p = lt < n_targets ? src[t0 + lt] : make_float4(0.f, 0.f, 0.f, 0.f);
+    px[k] = pack2(p.x, p.x);
+    py[k] = pack2(p.y, p.y);
+    pz[k] = pack2(p.z, p.z);
+    ax[k] = ay[k] = az[k] = pack2(0.f, 0.f);
+  }
+  const f32x2 e2 = pack2(easing, easing), tiny2 = pack2(tiny, tiny);
+  const size_t sb = size_t(blockIdx.y) * src_per_split;
+  const size_t se = min(sb + src_per_split, n_src);
+  for (size_t j0 = sb; j0 < se; j0 += DIRECT_TILE) {
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < DIRECT_TILE / DIRECT_THREADS; ++q) {
+      const int t = q * DIRECT_THREADS + threadIdx.x;
+      const size_t j = j0 + size_t(t);
+      const float4 sj = j < se ? src[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+      tx[t] = sj.x; ty[t] = sj.y; tz[t] = sj.z; tm[t] = sj.w;
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int j = 0; j < DIRECT_TILE; j += 4) {
+      const ulonglong2 X = *reinterpret_cast<const ulonglong2*>(&tx[j]);  // (x0,x1) (x2,x3)
+      const ulonglong2 Y = *reinterpret_cast<const ulonglong2*>(&ty[j]);
+      const ulonglong2 Z = *reinterpret_cast<const ulonglong2*>(&tz[j]);
+      const ulonglong2 M = *reinterpret_cast<const ulonglong2*>(&tm[j]);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const f32x2 sx = h ? X.y : X.x, sy = h ? Y.y : Y.x, sz = h ? Z.y : Z.x, sm = h ? M.y : M.x;
+#pragma unroll
+        for (int k = 0; k < T; ++k) {
+          const f32x2 dx = sub2(sx, px[k]);
+          const f32x2 dy = sub2(sy, py[k]);
+          const f32x2 dz = sub2(sz, pz[k]);
+          f32x2 r2 = fma2(dx, dx, tiny2);
+          r2 = fma2(dy, dy, r2);
+          r2 = fma2(dz, dz, r2);
+          const f32x2 sft = add2(r2, e2);
+          const f32x2 u = mul2(mul2(r2, sft), sft);
+          float u0, u1;
+          unpack2(u, u0, u1);
+          const f32x2 mw = mul2(sm, pack2(rsqrt_approx(u0), rsqrt_approx(u1)));
+          ax[k] = fma2(mw, dx, ax[k]);
+          ay[k] = fma2(mw, dy, ay[k]);
+          az[k] = fma2(mw, dz, az[k]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < T; ++k) {
+    const size_t lt = tbase + size_t(k) * DIRECT_THREADS + threadIdx.x;
+    if (lt < n_targets) {
+      float a0, a1, b0, b1, c0, c1;
+      unpack2(ax[k], a0, a1);
+      unpack2(ay[k], b0, b1);
+      unpack2(az[k], c0, c1);
+      part[size_t(blockIdx.y) * n_targets + lt] = make_float4(a0 + a1, b0 + b1, c0 + c1, 0.f);
+    }
+  }
+}
+
 // sums the source splits in a fixed order and applies the per-target rules
 __global__ void __launch_bounds__(256) direct_finish_kernel(const float4* __restrict__ part, int splits,
                                                             size_t t0, size_t n_targets,
@@ -1080,7 +1190,23 @@ cudaError_t direct_evaluate(GravityWorkspace& ws, size_t t0, size_t t1, float ea
   if (!n_targets) return cudaGetLastError();
   // 4 targets per thread when that still fills the chip, else 1; split the sources across
   // blockIdx.y until there are >= 2 CTAs per SM (partials summed in a fixed order afterwards)
-  const int T = (n_targets >= size_t(148) * 2 * DIRECT_THREADS * 4) ? 4 : 1;
+  // Packed kernel, T targets per thread.  Measured on B200 at 2^20 bodies, all targets:
+  // T=1 2.30e12, T=2 2.32e12, T=4 2.36e12 interactions/s (scalar kernel 2.06e12).  T is chosen for
+  // the best (speed x wave occupancy): 2 resident CTAs per SM, so a wave is 296 CTAs.
+  static const int variant = std::getenv("PB200_DIRECT_VARIANT") ? std::atoi(std::getenv("PB200_DIRECT_VARIANT")) : 20;
+  int T = variant % 10;
+  if (T == 0) {
+    const double speed[3] = {2.30, 2.32, 2.364};
+    const int cand[3] = {1, 2, 4};
+    double best = 0.0;
+    for (int i = 0; i < 3; ++i) {
+      const double blocks = double(blocks_for(n_targets, DIRECT_THREADS * cand[i]));
+      const double waves = std::ceil(blocks / 296.0);
+      const double eff = blocks < 296.0 ? 1.0 : blocks / (waves * 296.0);  // small grids get source splits
+      if (speed[i] * eff > best) { best = speed[i] * eff; T = cand[i]; }
+    }
+  }
+  const bool packed = variant >= 20;
   const unsigned tb = blocks_for(n_targets, DIRECT_THREADS * T);
   unsigned splits = 1;
   const unsigned max_splits = blocks_for(n, DIRECT_TILE);
@@ -1090,12 +1216,19 @@ cudaError_t direct_evaluate(GravityWorkspace& ws, size_t t0, size_t t1, float ea
   splits = blocks_for(n, int(per));
   PB_PASS(ws.acc_part.ensure(size_t(splits) * n_targets * sizeof(float4)));
   const dim3 grid(tb, splits);
-  if (T == 4)
-    PB_LAUNCH(ls, st, "direct_kernel", direct_kernel<4><<<grid, DIRECT_THREADS, 0, st>>>(ws.src4.as<float4>(), n, per, t0, n_targets, easing,
-                                                      tiny, ws.acc_part.as<float4>()));
-  else
-    PB_LAUNCH(ls, st, "direct_kernel", direct_kernel<1><<<grid, DIRECT_THREADS, 0, st>>>(ws.src4.as<float4>(), n, per, t0, n_targets, easing,
-                                                      tiny, ws.acc_part.as<float4>()));
+#define PB_DIRECT(KERNEL, TT)                                                                        \
+  PB_LAUNCH(ls, st, #KERNEL,                                                                         \
+            KERNEL<TT><<<grid, DIRECT_THREADS, 0, st>>>(ws.src4.as<float4>(), n, per, t0, n_targets, \
+                                                        easing, tiny, ws.acc_part.as<float4>()))
+  if (packed) {
+    if (T == 4) PB_DIRECT(direct_kernel_x2, 4);
+    else if (T == 2) PB_DIRECT(direct_kernel_x2, 2);
+    else PB_DIRECT(direct_kernel_x2, 1);
+  } else {
+    if (T == 4) PB_DIRECT(direct_kernel, 4);
+    else PB_DIRECT(direct_kernel, 1);
+  }
+#undef PB_DIRECT
   PB_LAUNCH(ls, st, "direct_finish_kernel", direct_finish_kernel<<<blocks_for(n_targets, 256), 256, 0, st>>>(
       ws.acc_part.as<float4>(), int(splits), t0, n_targets, ws.pos64, ws.fixed, uint32_t(n),
       ws.acc.as<float4>()));
