@@ -206,9 +206,9 @@ def run_ours(args, w):
     sim.upload(state)
     gathered = None
     if world > 1:
+        from physim_b200.sharding import exchange
         ptr, total, off, sl = sim.gather_buffer()
         gathered = cuda_tensor_view(ptr, total)
-        mine = gathered[off // 8:(off + sl) // 8]
 
     def steps(k):
         if world == 1:
@@ -217,7 +217,7 @@ def run_ours(args, w):
             for _ in range(k):
                 sim.step_local()
                 with torch.cuda.stream(stream):
-                    dist.all_gather_into_tensor(gathered, mine)
+                    exchange(gathered, n, rank, world)
 
     steps(max(args.warmup, 3))
     launches0 = sim.stats()["kernel_launches"]
