@@ -39,6 +39,8 @@ WORKLOADS = {
                desc="cube n=1000000 seed=1 spin=500 + 4 stars ! astro theta=1.3 ! verlet"),
     "c1": dict(n=100_000, element="astro2", theta=1.5, e=0.5, dt=1e-5,
                desc="cube n=100000 seed=1 spin=1000 + 2 stars ! astro2 theta=1.5 e=0.5 ! verlet"),
+    "c5s": dict(n=4_194_304, element="astro2", theta=0.7, e=0.5, dt=1e-6,
+                desc="cube n=4194304 seed=1 ! astro2 theta=0.7 e=0.5 ! verlet (configs[4] at 1/16 size)"),
     "c3o": dict(n=1_000_000, element="astro2", theta=1.5, e=0.5, dt=1e-5,
                 desc="cube n=1000000 seed=1 spin=500 + 4 stars ! astro2 theta=1.5 e=0.5 ! verlet"),
 }
@@ -56,7 +58,9 @@ FLOP_PER_INTERACTION = 19
 
 def make_state(w):
     from physim_b200 import generators as gen
-    if w["n"] >= 1_000_000:
+    if w["n"] > 1_000_000:
+        return gen.cube(w["n"], seed=1)
+    if w["n"] == 1_000_000:
         return gen.headline_pipeline(w["n"], seed=1, spin=500.0)
     return gen.readme_pipeline(w["n"], seed=1, spin=1000.0)
 

@@ -8,6 +8,8 @@
 // octant arithmetic) -> LSD radix sort -> DFS pre-order cell table -> bottom-up centres of mass ->
 // warp-cooperative walk with per-lane acceptance.  oracle/physim_oracle.cpp ("oracle 2") builds the
 // same table on the CPU; tests compare the two bit for bit.
+#include <cuda/atomic>
+
 #include <algorithm>
 #include <cmath>
 
@@ -424,6 +426,7 @@ __global__ void __launch_bounds__(256) unit_kernel(const uint64_t* __restrict__ 
     }
     ab[s] = head ? make_uchar2(static_cast<unsigned char>(a + 1), static_cast<unsigned char>(b + 1))
                  : make_uchar2(255, 255);  // NOT_HEAD: merged into the unit before it
+    if (!head) max_shared_plus1[1] = 1u;  // "some leaf is a merged unit" (rare): slow summation paths
     cnt[s] = head ? unsigned(max(0, b - a) + 1) : 0u;
   }
   // sizes the next sort and validates this one (a truncated sort is exact iff no two neighbours
@@ -557,6 +560,7 @@ __global__ void __launch_bounds__(256) skip_kernel(const uint64_t* __restrict__ 
                                                    const uint32_t* __restrict__ perm,
                                                    const uchar2* __restrict__ ab,
                                                    const uint32_t* __restrict__ cell_start, size_t n,
+                                                   const unsigned* __restrict__ any_merged,
                                                    CellArrays cells) {
   constexpr int LM = TreeDim<DIM>::LM;
   const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -612,12 +616,19 @@ __global__ void __launch_bounds__(256) skip_kernel(const uint64_t* __restrict__ 
   cells.skip[c] = skip;
   if (cnt <= SMALL_CELL) {
     double sm = 0.0, sx = 0.0, sy = 0.0, sz = 0.0;
-    for (size_t j = s; j < e;) {  // units in order
-      size_t je = j + 1;
-      while (je < e && ab[je].x == NOT_HEAD) ++je;
-      const double4 q = unit_leaf(sp, perm, j, je);
-      sm += q.w; sx += q.w * q.x; sy += q.w * q.y; sz += q.w * q.z;
-      j = je;
+    if (*any_merged == 0u) {  // every unit is one body: plain sums over the run
+      for (size_t j = s; j < e; ++j) {
+        const double4 q = sp[j];
+        sm += q.w; sx += q.w * q.x; sy += q.w * q.y; sz += q.w * q.z;
+      }
+    } else {
+      for (size_t j = s; j < e;) {  // units in order
+        size_t je = j + 1;
+        while (je < e && ab[je].x == NOT_HEAD) ++je;
+        const double4 q = unit_leaf(sp, perm, j, je);
+        sm += q.w; sx += q.w * q.x; sy += q.w * q.y; sz += q.w * q.z;
+        j = je;
+      }
     }
     // a massless cell (the reference panics there): geometric centre instead of 0/0
     const double4 g = cells.centre_ext[c];
@@ -674,10 +685,12 @@ __global__ void __launch_bounds__(128) com_kernel(const uchar2* __restrict__ ab,
     const uint32_t p = cells.parent[c];
     if (p == NO_PARENT) break;
     const uint32_t mine = cells.count[c];
-    __threadfence();  // publish com[c] before announcing it
-    const uint32_t old = atomicAdd(&cells.arrived[p], mine);
+    // release: com[c] is visible (at L2) before the arrival is.  The children are then read with
+    // ld.cg straight from L2, so no acquire fence (which would invalidate this SM's whole L1, as
+    // __threadfence() does) is needed.
+    cuda::atomic_ref<uint32_t, cuda::thread_scope_device> arrived(cells.arrived[p]);
+    const uint32_t old = arrived.fetch_add(mine, cuda::std::memory_order_release);
     if (old + mine != cells.count[p]) break;
-    __threadfence();
     double m = 0.0, sx = 0.0, sy = 0.0, sz = 0.0;
     const uint32_t end = cells.skip[p];
     for (uint32_t ch = p + 1; ch < end; ch = cells.skip[ch]) {
@@ -732,6 +745,20 @@ __device__ __forceinline__ float rsqrt_approx(float x) {
   return y;
 }
 
+// Unconditional, un-sinkable loads: the compiler otherwise moves each of the three per-cell loads
+// behind the branch that first uses it, and every visit pays three serial memory latencies.
+__device__ __forceinline__ double4 ld_now_double4(const double4* p) {
+  double4 v;
+  asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2+16];" : "=d"(v.z), "=d"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_now_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
 __device__ __forceinline__ bool accept_cell(double px, double py, double pz, const double4& ce,
                                             double theta, double theta2) {
   if (!(theta > 0.0)) return false;  // half_width / r >= 0 is never < theta <= 0
@@ -773,9 +800,9 @@ __global__ void __launch_bounds__(256) walk_kernel(const double4* __restrict__ s
   while (true) {
     const uint32_t c = __reduce_min_sync(FULL, next);
     if (c >= total) break;
-    const double4 ce = cells.centre_ext[c];
-    const double4 cm = cells.com[c];
-    const uint32_t sk = cells.skip[c];
+    const double4 ce = ld_now_double4(cells.centre_ext + c);
+    const double4 cm = ld_now_double4(cells.com + c);
+    const uint32_t sk = ld_now_u32(cells.skip + c);
     if (next == c) {
       const bool leaf = (sk == c + 1u);
       if (leaf || accept_cell(px, py, pz, ce, theta, theta2)) {
@@ -1158,7 +1185,7 @@ cudaError_t tree_evaluate(GravityWorkspace& ws, const GravityParams& prm, size_t
   PB_LAUNCH(ls, st, "skip_kernel",
             skip_kernel<DIM><<<blocks_for(cap, 256), 256, 0, st>>>(
                 ws.sorted_key, ws.spos64.as<double4>(), ws.perm, ws.ab.as<uchar2>(),
-                ws.cell_start.as<uint32_t>(), n, cells));
+                ws.cell_start.as<uint32_t>(), n, max_shared_plus1 + 1, cells));
   PB_LAUNCH(ls, st, "parent_kernel",
             parent_kernel<<<blocks_for(cap, 256), 256, 0, st>>>(ws.cell_start.as<uint32_t>(), n, cells));
   PB_LAUNCH(ls, st, "com_kernel", com_kernel<<<nb128, 128, 0, st>>>(ws.ab.as<uchar2>(), ws.cell_start.as<uint32_t>(), n, cells));
