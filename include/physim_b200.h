@@ -237,6 +237,9 @@ int pb200_sim_download(void *sim, Entity *state, size_t n);
 /* Accelerations of the last force evaluation, original order, for the owned targets. */
 int pb200_sim_last_accelerations(void *sim, Acceleration *acc, size_t n);
 int pb200_sim_stats(void *sim, Pb200Stats *out);
+/* Override the owned target range [t0, t1) chosen by rank/world at upload (sampled timing of a
+ * target slice of a large all-pairs problem). */
+int pb200_sim_set_targets(void *sim, size_t t0, size_t t1);
 /* Launch on a caller-owned CUDA stream (cudaStream_t; e.g. the stream a collective library uses)
  * instead of the handle's own.  NULL selects the legacy default stream. */
 int pb200_sim_set_stream(void *sim, void *stream);

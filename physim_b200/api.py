@@ -120,6 +120,7 @@ def lib():
     L.pb200_sim_last_accelerations.argtypes = [vp, vp, sz]
     L.pb200_sim_stats.argtypes = [vp, C.POINTER(Pb200Stats)]
     L.pb200_sim_set_stream.argtypes = [vp, vp]
+    L.pb200_sim_set_targets.argtypes = [vp, sz, sz]
     L.pb200_sim_stream.restype = vp
     L.pb200_sim_stream.argtypes = [vp]
     L.pb200_probe_fp32_tflops.restype = dbl
@@ -369,6 +370,10 @@ class Sim:
         if lib().pb200_sim_stats(self._s, C.byref(st)) != 0:
             raise Pb200Error(last_error())
         return st.as_dict()
+
+    def set_targets(self, t0, t1):
+        if lib().pb200_sim_set_targets(self._s, int(t0), int(t1)) != 0:
+            raise Pb200Error(last_error())
 
     def set_stream(self, cuda_stream_ptr):
         if lib().pb200_sim_set_stream(self._s, C.c_void_p(cuda_stream_ptr)) != 0:

@@ -1027,6 +1027,19 @@ int pb200_sim_stats(void* sim, Pb200Stats* out) {
   return 0;
 }
 
+int pb200_sim_set_targets(void* sim, size_t t0, size_t t1) {
+  if (!sim) return -1;
+  auto& s = *static_cast<SimObj*>(sim);
+  std::lock_guard<std::mutex> lk(s.mu);
+  if (t0 > t1 || t1 > s.n) {
+    set_error("pb200_sim_set_targets: bad range");
+    return -1;
+  }
+  s.t0 = t0;
+  s.t1 = t1;
+  return 0;
+}
+
 int pb200_sim_set_stream(void* sim, void* stream) {
   if (!sim) return -1;
   auto& s = *static_cast<SimObj*>(sim);

@@ -936,15 +936,15 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
   return d;
 }
 
-template <int T>
+template <int T, int TILE = DIRECT_TILE, int UNR = 2>
 __global__ void __launch_bounds__(DIRECT_THREADS) direct_kernel_x2(
     const float4* __restrict__ src, size_t n_src, size_t src_per_split, size_t t0, size_t n_targets,
     float easing, float tiny, float4* __restrict__ part /* [splits][n_targets] */) {
   // SoA tile: consecutive sources are adjacent, so an aligned 16-byte read yields two source pairs
-  __shared__ __align__(16) float tx[DIRECT_TILE];
-  __shared__ __align__(16) float ty[DIRECT_TILE];
-  __shared__ __align__(16) float tz[DIRECT_TILE];
-  __shared__ __align__(16) float tm[DIRECT_TILE];
+  __shared__ __align__(16) float tx[TILE];
+  __shared__ __align__(16) float ty[TILE];
+  __shared__ __align__(16) float tz[TILE];
+  __shared__ __align__(16) float tm[TILE];
   const size_t tbase = size_t(blockIdx.x) * (DIRECT_THREADS * T);
   f32x2 px[T], py[T], pz[T], ax[T], ay[T], az[T];
 #pragma unroll
@@ -959,18 +959,18 @@ __global__ void __launch_bounds__(DIRECT_THREADS) direct_kernel_x2(
   const f32x2 e2 = pack2(easing, easing), tiny2 = pack2(tiny, tiny);
   const size_t sb = size_t(blockIdx.y) * src_per_split;
   const size_t se = min(sb + src_per_split, n_src);
-  for (size_t j0 = sb; j0 < se; j0 += DIRECT_TILE) {
+  for (size_t j0 = sb; j0 < se; j0 += TILE) {
     __syncthreads();
 #pragma unroll
-    for (int q = 0; q < DIRECT_TILE / DIRECT_THREADS; ++q) {
+    for (int q = 0; q < TILE / DIRECT_THREADS; ++q) {
       const int t = q * DIRECT_THREADS + threadIdx.x;
       const size_t j = j0 + size_t(t);
       const float4 sj = j < se ? src[j] : make_float4(0.f, 0.f, 0.f, 0.f);
       tx[t] = sj.x; ty[t] = sj.y; tz[t] = sj.z; tm[t] = sj.w;
     }
     __syncthreads();
-#pragma unroll 2
-    for (int j = 0; j < DIRECT_TILE; j += 4) {
+#pragma unroll UNR
+    for (int j = 0; j < TILE; j += 4) {
       const ulonglong2 X = *reinterpret_cast<const ulonglong2*>(&tx[j]);  // (x0,x1) (x2,x3)
       const ulonglong2 Y = *reinterpret_cast<const ulonglong2*>(&ty[j]);
       const ulonglong2 Z = *reinterpret_cast<const ulonglong2*>(&tz[j]);
@@ -1247,7 +1247,14 @@ cudaError_t direct_evaluate(GravityWorkspace& ws, size_t t0, size_t t1, float ea
   PB_LAUNCH(ls, st, #KERNEL,                                                                         \
             KERNEL<TT><<<grid, DIRECT_THREADS, 0, st>>>(ws.src4.as<float4>(), n, per, t0, n_targets, \
                                                         easing, tiny, ws.acc_part.as<float4>()))
-  if (packed) {
+  static const int tune = std::getenv("PB200_DIRECT_TUNE") ? std::atoi(std::getenv("PB200_DIRECT_TUNE")) : 0;
+  if (packed && T == 4 && tune == 1) {
+    PB_LAUNCH(ls, st, "direct_kernel_x2", (direct_kernel_x2<4, 2048, 2><<<grid, DIRECT_THREADS, 0, st>>>(ws.src4.as<float4>(), n, per, t0, n_targets, easing, tiny, ws.acc_part.as<float4>())));
+  } else if (packed && T == 4 && tune == 2) {
+    PB_LAUNCH(ls, st, "direct_kernel_x2", (direct_kernel_x2<4, 1024, 4><<<grid, DIRECT_THREADS, 0, st>>>(ws.src4.as<float4>(), n, per, t0, n_targets, easing, tiny, ws.acc_part.as<float4>())));
+  } else if (packed && T == 4 && tune == 3) {
+    PB_LAUNCH(ls, st, "direct_kernel_x2", (direct_kernel_x2<4, 2048, 1><<<grid, DIRECT_THREADS, 0, st>>>(ws.src4.as<float4>(), n, per, t0, n_targets, easing, tiny, ws.acc_part.as<float4>())));
+  } else if (packed) {
     if (T == 4) PB_DIRECT(direct_kernel_x2, 4);
     else if (T == 2) PB_DIRECT(direct_kernel_x2, 2);
     else PB_DIRECT(direct_kernel_x2, 1);
