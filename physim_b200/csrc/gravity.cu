@@ -200,14 +200,14 @@ __global__ void __launch_bounds__(256) encode_kernel(const double4* __restrict__
 // HBM per body: 8 B (histograms) + passes x (12 B + 12 B).
 // ---------------------------------------------------------------------------------------------
 constexpr int SORT_THREADS = 256;
-constexpr int SORT_ITEMS = 16;
-constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
+
 constexpr int SORT_MAX_PASSES = 8;
 constexpr unsigned LB_INCL = 0x80000000u, LB_PART = 0x40000000u, LB_MASK = 0x3fffffffu;
 constexpr unsigned LB_SPIN_LIMIT = 1u << 24;
 constexpr int LB_BATCH = 16;
 
-__global__ void __launch_bounds__(SORT_THREADS, 2) sort_onesweep_pass(
+template <int SORT_ITEMS>
+__global__ void __launch_bounds__(SORT_THREADS, SORT_ITEMS >= 16 ? 2 : 4) sort_onesweep_pass(
     const uint64_t* __restrict__ kin, const uint32_t* __restrict__ vin, uint64_t* __restrict__ kout,
     uint32_t* __restrict__ vout, size_t n, int shift, unsigned mask,
     const unsigned* __restrict__ ghist /*[256] of this pass*/, unsigned* status /*[tiles][256]*/,
@@ -219,6 +219,7 @@ __global__ void __launch_bounds__(SORT_THREADS, 2) sort_onesweep_pass(
   for (int j = tid; j < 8 * 256; j += SORT_THREADS) (&whist[0][0])[j] = 0;
   const unsigned dbase = block_exclusive_scan_256(ghist[tid], nullptr);  // start of each digit; syncs
   const unsigned tile = tile_s;
+  constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
   const size_t base = size_t(tile) * SORT_TILE + size_t(warp) * 32 * SORT_ITEMS;
 
   uint64_t k[SORT_ITEMS];
@@ -1081,13 +1082,17 @@ cudaError_t exclusive_scan(const uint32_t* in, uint32_t* out, size_t n, DevBuf& 
 struct SortBuffers {
   SortPlan plan;
   unsigned tiles;
+  int items;
   unsigned *ghist, *counters, *err_flag, *status;
 };
 
 // plans the passes over key bits [lo, key_bits) and clears histograms / look-back state
 cudaError_t sort_prepare(GravityWorkspace& ws, size_t n, int key_bits, int lo, cudaStream_t st,
                          SortBuffers* sb) {
-  sb->tiles = blocks_for(n, SORT_TILE);
+  // keys per thread: 8 wins at 1e5 bodies (more CTAs in flight), 16 from 1e6 up (measured on B200)
+  static const int items_env = std::getenv("PB200_SORT_ITEMS") ? std::atoi(std::getenv("PB200_SORT_ITEMS")) : 0;
+  sb->items = items_env ? items_env : (n <= (size_t(1) << 19) ? 8 : 16);
+  sb->tiles = blocks_for(n, SORT_THREADS * sb->items);
   SortPlan& plan = sb->plan;
   const int total = key_bits - lo;
   plan.npass = (total + 7) / 8;
@@ -1114,10 +1119,16 @@ cudaError_t sort_passes(GravityWorkspace& ws, size_t n, const SortBuffers& sb, c
   uint32_t* v[2] = {ws.idx0.as<uint32_t>(), ws.idx1.as<uint32_t>()};
   int cur = 0;
   for (int p = 0; p < sb.plan.npass; ++p) {
-    PB_LAUNCH(ls, st, "sort_onesweep_pass",
-              sort_onesweep_pass<<<sb.tiles, SORT_THREADS, 0, st>>>(
-                  k[cur], v[cur], k[cur ^ 1], v[cur ^ 1], n, sb.plan.shift(p), sb.plan.mask(p),
-                  sb.ghist + p * 256, sb.status + size_t(p) * sb.tiles * 256, sb.counters + p, sb.err_flag));
+    if (sb.items == 8)
+      PB_LAUNCH(ls, st, "sort_onesweep_pass",
+                sort_onesweep_pass<8><<<sb.tiles, SORT_THREADS, 0, st>>>(
+                    k[cur], v[cur], k[cur ^ 1], v[cur ^ 1], n, sb.plan.shift(p), sb.plan.mask(p),
+                    sb.ghist + p * 256, sb.status + size_t(p) * sb.tiles * 256, sb.counters + p, sb.err_flag));
+    else
+      PB_LAUNCH(ls, st, "sort_onesweep_pass",
+                sort_onesweep_pass<16><<<sb.tiles, SORT_THREADS, 0, st>>>(
+                    k[cur], v[cur], k[cur ^ 1], v[cur ^ 1], n, sb.plan.shift(p), sb.plan.mask(p),
+                    sb.ghist + p * 256, sb.status + size_t(p) * sb.tiles * 256, sb.counters + p, sb.err_flag));
     cur ^= 1;
   }
   ws.sorted_key = k[cur];
