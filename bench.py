@@ -218,10 +218,10 @@ def run_ours(args, w):
         if world == 1:
             sim.run(k)  # k steps enqueued back to back; one host sync at the end
         else:
-            for _ in range(k):
-                sim.step_local()
+            def xchg():
                 with torch.cuda.stream(stream):
                     exchange(gathered, n, rank, world)
+            sim.run_sharded(k, xchg)
 
     steps(max(args.warmup, 3))
     launches0 = sim.stats()["kernel_launches"]

@@ -8,6 +8,7 @@
 // every transform during plugin discovery (physim-core/src/plugin/discover.rs:376-387).
 #include <emmintrin.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstring>
@@ -405,7 +406,7 @@ struct SimObj {
   DevBuf ck_cur, ck_prev, ck_vel;  // checkpoint of the last verified state
   uint64_t replays = 0;
   PinnedBuf h_pos, h_vel, h_fixed, h_acc;
-  size_t n = 0, t0 = 0, t1 = 0;
+  size_t n = 0, t0 = 0, t1 = 0, slice = 0;
   bool first = true, checked = false;
   LaunchStats ls;
   Pb200Stats stats;
@@ -425,12 +426,15 @@ cudaError_t sim_upload(SimObj& s, const Entity* state, size_t n) {
   PB_PASS(s.gpu.init(s.device));
   cudaStream_t st = s.gpu.stream;
   s.n = n;
-  s.t0 = n * size_t(s.rank) / size_t(s.world);
-  s.t1 = n * size_t(s.rank + 1) / size_t(s.world);
+  // equal slices of S = ceil(n / world) bodies (the last rank's is shorter); the gather buffer holds
+  // world * S records so that one in-place all-gather with equal counts serves every n
+  s.slice = (n + size_t(s.world) - 1) / size_t(s.world);
+  s.t0 = std::min(n, s.slice * size_t(s.rank));
+  s.t1 = std::min(n, s.slice * size_t(s.rank + 1));
   s.first = true;
   s.checked = false;
   if (n == 0) return cudaSuccess;
-  PB_PASS(s.cur.ensure(n * sizeof(double4)));
+  PB_PASS(s.cur.ensure(s.slice * size_t(s.world) * sizeof(double4)));
   PB_PASS(s.prev.ensure(n * sizeof(double4)));
   PB_PASS(s.vel.ensure(n * sizeof(double4)));
   PB_PASS(s.fixed.ensure(n));
@@ -470,14 +474,19 @@ bool sim_is_direct(const SimObj& s) {
 // each chunk starts from a device-side checkpoint and is verified at its end (cell-table capacity,
 // truncated-sort validity).  A chunk that fails verification is restored and replayed with a
 // host check after every build, so the result never depends on an unverified tree.
-cudaError_t sim_run_steps(SimObj& s, size_t steps) {
+typedef void (*ExchangeFn)(void*);
+
+cudaError_t sim_run_steps(SimObj& s, size_t steps, ExchangeFn exchange = nullptr, void* xctx = nullptr) {
   if (s.n == 0) return cudaSuccess;
   cudaStream_t st = s.gpu.stream;
   if (sim_is_direct(s)) {
-    for (size_t i = 0; i < steps; ++i) PB_PASS(sim_step(s, false));
+    for (size_t i = 0; i < steps; ++i) {
+      PB_PASS(sim_step(s, false));
+      if (exchange) exchange(xctx);
+    }
     return cudaSuccess;
   }
-  const size_t bytes = s.n * sizeof(double4);
+  const size_t bytes = s.n * sizeof(double4);  // every rank holds all n positions
   while (steps) {
     const size_t chunk = steps < 32 ? steps : 32;
     PB_PASS(s.ck_cur.ensure(bytes));
@@ -487,7 +496,10 @@ cudaError_t sim_run_steps(SimObj& s, size_t steps) {
     PB_CUDA(cudaMemcpyAsync(s.ck_prev.p, s.prev.p, bytes, cudaMemcpyDeviceToDevice, st));
     PB_CUDA(cudaMemcpyAsync(s.ck_vel.p, s.vel.p, bytes, cudaMemcpyDeviceToDevice, st));
     const bool first_at_ck = s.first;
-    for (size_t i = 0; i < chunk; ++i) PB_PASS(sim_step(s, false));
+    for (size_t i = 0; i < chunk; ++i) {
+      PB_PASS(sim_step(s, false));
+      if (exchange) exchange(xctx);
+    }
     TreeCheck chk;
     PB_PASS(gravity_check(s.ws, st, &chk));
     if (!chk.ok()) {
@@ -500,7 +512,10 @@ cudaError_t sim_run_steps(SimObj& s, size_t steps) {
       PB_CUDA(cudaMemcpyAsync(s.vel.p, s.ck_vel.p, bytes, cudaMemcpyDeviceToDevice, st));
       s.first = first_at_ck;
       s.replays += 1;
-      for (size_t i = 0; i < chunk; ++i) PB_PASS(sim_step(s, true));
+      for (size_t i = 0; i < chunk; ++i) {
+        PB_PASS(sim_step(s, true));
+        if (exchange) exchange(xctx);
+      }
     }
     steps -= chunk;
   }
@@ -862,6 +877,22 @@ int pb200_sim_run(void* sim, size_t steps) {
   return 0;
 }
 
+int pb200_sim_run_sharded(void* sim, size_t steps, void (*exchange)(void*), void* ctx) {
+  if (!sim || !exchange) return -1;
+  auto& s = *static_cast<SimObj*>(sim);
+  std::lock_guard<std::mutex> lk(s.mu);
+  if (!s.gpu.ready) {
+    set_error("pb200_sim_upload first");
+    return -1;
+  }
+  cudaSetDevice(s.gpu.device);
+  if (sim_run_steps(s, steps, exchange, ctx) != cudaSuccess) {
+    std::fprintf(stderr, "[physim_b200] sharded sim run failed: %s\n", g_error);
+    return -1;
+  }
+  return 0;
+}
+
 int pb200_sim_run_timed(void* sim, size_t steps, float* ms) {
   if (!sim || !ms) return -1;
   auto& s = *static_cast<SimObj*>(sim);
@@ -944,9 +975,9 @@ int pb200_sim_gather_buffer(void* sim, void** dev_ptr, size_t* total_bytes, size
   auto& s = *static_cast<SimObj*>(sim);
   std::lock_guard<std::mutex> lk(s.mu);
   if (dev_ptr) *dev_ptr = s.cur.p;
-  if (total_bytes) *total_bytes = s.n * sizeof(double4);
-  if (slice_offset) *slice_offset = s.t0 * sizeof(double4);
-  if (slice_bytes) *slice_bytes = (s.t1 - s.t0) * sizeof(double4);
+  if (total_bytes) *total_bytes = s.slice * size_t(s.world) * sizeof(double4);
+  if (slice_offset) *slice_offset = s.slice * size_t(s.rank) * sizeof(double4);
+  if (slice_bytes) *slice_bytes = s.slice * sizeof(double4);
   return 0;
 }
 

@@ -7,35 +7,36 @@ the kernels read.  These helpers mirror `sim_upload` in csrc/engine.cu and wrap 
 """
 
 
+def slice_size(n, world):
+    """S = ceil(n / world): every rank's slice of the gather buffer holds S bodies."""
+    return (n + world - 1) // world
+
+
 def owned_range(n, rank, world):
-    """[t0, t1) of the bodies rank `rank` owns; identical to engine.cu (n*rank/world)."""
-    return n * rank // world, n * (rank + 1) // world
+    """[t0, t1) of the bodies rank `rank` owns; identical to sim_upload in csrc/engine.cu:
+    equal slices of S bodies, the last one shorter (possibly empty)."""
+    s = slice_size(n, world)
+    return min(n, s * rank), min(n, s * (rank + 1))
+
+
+def gather_elems(n, world, width=4):
+    """Elements of the gather buffer: world * S records (>= n: the tail is padding)."""
+    return slice_size(n, world) * world * width
 
 
 def slice_elems(n, rank, world, width=4):
-    """(offset, count) in elements of the rank's slice of an n x width buffer."""
-    t0, t1 = owned_range(n, rank, world)
-    return t0 * width, (t1 - t0) * width
+    """(offset, count) in elements of the rank's slice of the gather buffer."""
+    s = slice_size(n, world)
+    return s * rank * width, s * width
 
 
 def exchange(gathered, n, rank, world, width=4):
-    """All-gather of the owned slices, in place on `gathered` (a flat torch tensor of n*width
-    elements whose owned slice holds this rank's new positions).  Uneven slices (n % world != 0)
-    use all_gather with per-rank views."""
+    """One all-gather of the equal-sized slices, in place on `gathered` (a flat torch tensor of
+    gather_elems(n, world) elements whose owned slice holds this rank's new positions)."""
     import torch.distributed as dist
 
     if world == 1:
         return
-    if n % world == 0:
-        off, cnt = slice_elems(n, rank, world, width)
-        dist.all_gather_into_tensor(gathered, gathered[off:off + cnt].clone() if gathered.device.type == "cpu"
-                                    else gathered[off:off + cnt])
-    else:
-        views = []
-        for r in range(world):
-            o, c = slice_elems(n, r, world, width)
-            views.append(gathered[o:o + c])
-        off, cnt = slice_elems(n, rank, world, width)
-        # ranks own different counts: broadcast each slice from its owner
-        for r in range(world):
-            dist.broadcast(views[r], src=r)
+    off, cnt = slice_elems(n, rank, world, width)
+    mine = gathered[off:off + cnt]
+    dist.all_gather_into_tensor(gathered, mine.clone() if gathered.device.type == "cpu" else mine)

@@ -12,7 +12,7 @@ import torch.multiprocessing as mp
 
 from oracle import binding as ob
 from physim_b200 import generators as gen
-from physim_b200.sharding import exchange, owned_range, slice_elems
+from physim_b200.sharding import exchange, gather_elems, owned_range, slice_elems, slice_size
 
 
 def free_port():
@@ -28,8 +28,11 @@ def test_owned_ranges_tile_the_bodies():
             assert edges[0][0] == 0 and edges[-1][1] == n
             assert all(edges[i][1] == edges[i + 1][0] for i in range(world - 1))
             sizes = [b - a for a, b in edges]
-            assert max(sizes) - min(sizes) <= 1
-            assert slice_elems(n, world - 1, world) == (edges[-1][0] * 4, sizes[-1] * 4)
+            s = slice_size(n, world)
+            assert all(sz == s for sz in sizes[:-1] if sz) and max(sizes, default=0) <= s
+            # the gather buffer has world equal slots; only the tail past n is padding
+            assert gather_elems(n, world) == world * s * 4 >= n * 4
+            assert slice_elems(n, 1 % world, world) == (s * (1 % world) * 4, s * 4)
 
 
 def _worker(rank, world, port, n_bodies, steps, out):
@@ -40,8 +43,8 @@ def _worker(rank, world, port, n_bodies, steps, out):
     n = len(state)
     t0, t1 = owned_range(n, rank, world)
     dt, e = 0.01, 0.1
-    gathered = torch.zeros(n * 4, dtype=torch.float64)   # {x, y, z, m} of every body
-    g = gathered.view(n, 4).numpy()
+    gathered = torch.zeros(gather_elems(n, world), dtype=torch.float64)   # {x, y, z, m} + padding
+    g = gathered.view(-1, 4).numpy()[:n]
     g[:, 0], g[:, 1], g[:, 2], g[:, 3] = state["x"], state["y"], state["z"], state["mass"]
     prev = np.zeros((n, 3))
     vel = np.stack([state["vx"], state["vy"], state["vz"]], 1)
