@@ -262,8 +262,16 @@ def run_ours(args, w):
     per_launch_ms = top["ms"] / top["launches"]
     alg_bytes = ALG_BYTES_PER_BODY.get(top["kernel"], 0) * n
     achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9 if alg_bytes else None
+    traffic = None  # dram read + write bytes per launch, from the committed ncu --set full capture
+    try:
+        if args.workload == "c3":
+            nc = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_c3_kernels.json")))[top["kernel"]]
+            traffic = (nc["dram_read_mb_per_launch"] + nc["dram_write_mb_per_launch"]) * 1e6
+    except Exception:
+        pass
     roofline = {"kernel": top["kernel"], "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
-                "unit": "GB/s", "frac": (achieved / hbm_peak) if achieved else None, "traffic": None,
+                "unit": "GB/s", "frac": (achieved / hbm_peak) if achieved else None, "traffic": traffic,
+                "traffic_source": "profiles/r01_ncu_c3_kernels.json (ncu --set full, cold L2)" if traffic else None,
                 "peak_source": peak_kind, "avg_launch_ms": per_launch_ms,
                 "share_of_step": top["ms"] / tot_ms,
                 "alg_bytes_per_launch": alg_bytes,
