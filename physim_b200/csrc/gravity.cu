@@ -835,7 +835,7 @@ __global__ void __launch_bounds__(256) walk_kernel(const double4* __restrict__ s
 
 // ---------------------------------------------------------------------------------------------
 // K9  tiled direct sum (simple_astro, and astro/astro2 with theta <= 0 where no cell is ever
-//     accepted).  FP32 FMA-pipe bound: 13 FP32 instructions + 1 MUFU.RSQ per interaction
+//     accepted).  FP32 FMA-pipe bound: 13 FP32 lane-operations + 1 MUFU.RSQ per interaction
 //     (19 flop).  Sources are staged through shared memory and broadcast to the warp; each thread
 //     keeps T targets in registers.
 // ---------------------------------------------------------------------------------------------
@@ -851,62 +851,11 @@ __global__ void __launch_bounds__(256) to_float4_kernel(const double4* __restric
 constexpr int DIRECT_THREADS = 256;
 constexpr int DIRECT_TILE = 1024;  // sources per shared-memory tile (16 KB)
 
-template <int T>
-__global__ void __launch_bounds__(DIRECT_THREADS) direct_kernel(
-    const float4* __restrict__ src, size_t n_src, size_t src_per_split, size_t t0, size_t n_targets,
-    float easing, float tiny, float4* __restrict__ part /* [splits][n_targets] */) {
-  __shared__ float4 tile[DIRECT_TILE];
-  const size_t tbase = size_t(blockIdx.x) * (DIRECT_THREADS * T);
-  float px[T], py[T], pz[T], ax[T], ay[T], az[T];
-#pragma unroll
-  for (int k = 0; k < T; ++k) {
-    const size_t lt = tbase + size_t(k) * DIRECT_THREADS + threadIdx.x;
-    const float4 p = lt < n_targets ? src[t0 + lt] : make_float4(0.f, 0.f, 0.f, 0.f);
-    px[k] = p.x; py[k] = p.y; pz[k] = p.z;
-    ax[k] = ay[k] = az[k] = 0.f;
-  }
-  const size_t sb = size_t(blockIdx.y) * src_per_split;
-  const size_t se = min(sb + src_per_split, n_src);
-  for (size_t j0 = sb; j0 < se; j0 += DIRECT_TILE) {
-    __syncthreads();
-#pragma unroll
-    for (int q = 0; q < DIRECT_TILE / DIRECT_THREADS; ++q) {
-      const size_t j = j0 + size_t(q) * DIRECT_THREADS + threadIdx.x;
-      tile[q * DIRECT_THREADS + threadIdx.x] = j < se ? src[j] : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    __syncthreads();
-#pragma unroll 8
-    for (int j = 0; j < DIRECT_TILE; ++j) {
-      const float4 sj = tile[j];
-#pragma unroll
-      for (int k = 0; k < T; ++k) {
-        const float dx = sj.x - px[k];
-        const float dy = sj.y - py[k];
-        const float dz = sj.z - pz[k];
-        float r2 = fmaf(dx, dx, tiny);
-        r2 = fmaf(dy, dy, r2);
-        r2 = fmaf(dz, dz, r2);
-        const float sft = r2 + easing;
-        const float u = (r2 * sft) * sft;
-        const float mw = sj.w * rsqrt_approx(u);
-        ax[k] = fmaf(mw, dx, ax[k]);
-        ay[k] = fmaf(mw, dy, ay[k]);
-        az[k] = fmaf(mw, dz, az[k]);
-      }
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < T; ++k) {
-    const size_t lt = tbase + size_t(k) * DIRECT_THREADS + threadIdx.x;
-    if (lt < n_targets)
-      part[size_t(blockIdx.y) * n_targets + lt] = make_float4(ax[k], ay[k], az[k], 0.f);
-  }
-}
-
-// ---- packed variant: Blackwell's FFMA2 / FADD2 / FMUL2 (fma/add/sub/mul .f32x2) process two fp32
-// values per issue slot.  Two SOURCES are paired per instruction (the target's coordinates are a
-// loop-invariant broadcast pair), so one interaction costs 6.5 FP32 issue slots + 1 MUFU instead of
-// 13 + 1 and the kernel is bound by the FP32 pipe instead of by instruction issue.
+// Blackwell's FFMA2 / FADD2 / FMUL2 (fma/add/sub/mul .f32x2) process two fp32 values per issue
+// slot.  Two SOURCES are paired per instruction (the target's coordinates are a loop-invariant
+// broadcast pair), so one interaction costs 6.5 FP32 issue slots + 1 MUFU instead of 13 + 1 and the
+// kernel is bound by the FP32 pipe instead of by instruction issue (measured: 2.36e12 vs 2.06e12
+// interactions/s for the scalar-FP32 form of the same loop).
 typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 pack2(float lo, float hi) {
   f32x2 r;
@@ -937,15 +886,15 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
   return d;
 }
 
-template <int T, int TILE = DIRECT_TILE, int UNR = 2>
+template <int T>
 __global__ void __launch_bounds__(DIRECT_THREADS) direct_kernel_x2(
     const float4* __restrict__ src, size_t n_src, size_t src_per_split, size_t t0, size_t n_targets,
     float easing, float tiny, float4* __restrict__ part /* [splits][n_targets] */) {
   // SoA tile: consecutive sources are adjacent, so an aligned 16-byte read yields two source pairs
-  __shared__ __align__(16) float tx[TILE];
-  __shared__ __align__(16) float ty[TILE];
-  __shared__ __align__(16) float tz[TILE];
-  __shared__ __align__(16) float tm[TILE];
+  __shared__ __align__(16) float tx[DIRECT_TILE];
+  __shared__ __align__(16) float ty[DIRECT_TILE];
+  __shared__ __align__(16) float tz[DIRECT_TILE];
+  __shared__ __align__(16) float tm[DIRECT_TILE];
   const size_t tbase = size_t(blockIdx.x) * (DIRECT_THREADS * T);
   f32x2 px[T], py[T], pz[T], ax[T], ay[T], az[T];
 #pragma unroll
@@ -960,18 +909,18 @@ __global__ void __launch_bounds__(DIRECT_THREADS) direct_kernel_x2(
   const f32x2 e2 = pack2(easing, easing), tiny2 = pack2(tiny, tiny);
   const size_t sb = size_t(blockIdx.y) * src_per_split;
   const size_t se = min(sb + src_per_split, n_src);
-  for (size_t j0 = sb; j0 < se; j0 += TILE) {
+  for (size_t j0 = sb; j0 < se; j0 += DIRECT_TILE) {
     __syncthreads();
 #pragma unroll
-    for (int q = 0; q < TILE / DIRECT_THREADS; ++q) {
+    for (int q = 0; q < DIRECT_TILE / DIRECT_THREADS; ++q) {
       const int t = q * DIRECT_THREADS + threadIdx.x;
       const size_t j = j0 + size_t(t);
       const float4 sj = j < se ? src[j] : make_float4(0.f, 0.f, 0.f, 0.f);
       tx[t] = sj.x; ty[t] = sj.y; tz[t] = sj.z; tm[t] = sj.w;
     }
     __syncthreads();
-#pragma unroll UNR
-    for (int j = 0; j < TILE; j += 4) {
+#pragma unroll 2
+    for (int j = 0; j < DIRECT_TILE; j += 4) {
       const ulonglong2 X = *reinterpret_cast<const ulonglong2*>(&tx[j]);  // (x0,x1) (x2,x3)
       const ulonglong2 Y = *reinterpret_cast<const ulonglong2*>(&ty[j]);
       const ulonglong2 Z = *reinterpret_cast<const ulonglong2*>(&tz[j]);
@@ -1228,12 +1177,11 @@ cudaError_t direct_evaluate(GravityWorkspace& ws, size_t t0, size_t t1, float ea
   if (!n_targets) return cudaGetLastError();
   // 4 targets per thread when that still fills the chip, else 1; split the sources across
   // blockIdx.y until there are >= 2 CTAs per SM (partials summed in a fixed order afterwards)
-  // Packed kernel, T targets per thread.  Measured on B200 at 2^20 bodies, all targets:
-  // T=1 2.30e12, T=2 2.32e12, T=4 2.36e12 interactions/s (scalar kernel 2.06e12).  T is chosen for
-  // the best (speed x wave occupancy): 2 resident CTAs per SM, so a wave is 296 CTAs.
-  static const int variant = std::getenv("PB200_DIRECT_VARIANT") ? std::atoi(std::getenv("PB200_DIRECT_VARIANT")) : 20;
-  int T = variant % 10;
-  if (T == 0) {
+  // T targets per thread.  Measured on B200 at 2^20 bodies, all targets: T=1 2.30e12, T=2 2.32e12,
+  // T=4 2.36e12 interactions/s.  T is chosen for the best (speed x wave occupancy): 2 resident CTAs
+  // per SM, so a wave is 296 CTAs.
+  int T = 1;
+  {
     const double speed[3] = {2.30, 2.32, 2.364};
     const int cand[3] = {1, 2, 4};
     double best = 0.0;
@@ -1244,7 +1192,6 @@ cudaError_t direct_evaluate(GravityWorkspace& ws, size_t t0, size_t t1, float ea
       if (speed[i] * eff > best) { best = speed[i] * eff; T = cand[i]; }
     }
   }
-  const bool packed = variant >= 20;
   const unsigned tb = blocks_for(n_targets, DIRECT_THREADS * T);
   unsigned splits = 1;
   const unsigned max_splits = blocks_for(n, DIRECT_TILE);
@@ -1254,25 +1201,14 @@ cudaError_t direct_evaluate(GravityWorkspace& ws, size_t t0, size_t t1, float ea
   splits = blocks_for(n, int(per));
   PB_PASS(ws.acc_part.ensure(size_t(splits) * n_targets * sizeof(float4)));
   const dim3 grid(tb, splits);
-#define PB_DIRECT(KERNEL, TT)                                                                        \
-  PB_LAUNCH(ls, st, #KERNEL,                                                                         \
-            KERNEL<TT><<<grid, DIRECT_THREADS, 0, st>>>(ws.src4.as<float4>(), n, per, t0, n_targets, \
-                                                        easing, tiny, ws.acc_part.as<float4>()))
-  static const int tune = std::getenv("PB200_DIRECT_TUNE") ? std::atoi(std::getenv("PB200_DIRECT_TUNE")) : 0;
-  if (packed && T == 4 && tune == 1) {
-    PB_LAUNCH(ls, st, "direct_kernel_x2", (direct_kernel_x2<4, 2048, 2><<<grid, DIRECT_THREADS, 0, st>>>(ws.src4.as<float4>(), n, per, t0, n_targets, easing, tiny, ws.acc_part.as<float4>())));
-  } else if (packed && T == 4 && tune == 2) {
-    PB_LAUNCH(ls, st, "direct_kernel_x2", (direct_kernel_x2<4, 1024, 4><<<grid, DIRECT_THREADS, 0, st>>>(ws.src4.as<float4>(), n, per, t0, n_targets, easing, tiny, ws.acc_part.as<float4>())));
-  } else if (packed && T == 4 && tune == 3) {
-    PB_LAUNCH(ls, st, "direct_kernel_x2", (direct_kernel_x2<4, 2048, 1><<<grid, DIRECT_THREADS, 0, st>>>(ws.src4.as<float4>(), n, per, t0, n_targets, easing, tiny, ws.acc_part.as<float4>())));
-  } else if (packed) {
-    if (T == 4) PB_DIRECT(direct_kernel_x2, 4);
-    else if (T == 2) PB_DIRECT(direct_kernel_x2, 2);
-    else PB_DIRECT(direct_kernel_x2, 1);
-  } else {
-    if (T == 4) PB_DIRECT(direct_kernel, 4);
-    else PB_DIRECT(direct_kernel, 1);
-  }
+#define PB_DIRECT(TT)                                                                                  \
+  PB_LAUNCH(ls, st, "direct_kernel_x2",                                                                \
+            direct_kernel_x2<TT><<<grid, DIRECT_THREADS, 0, st>>>(ws.src4.as<float4>(), n, per, t0,    \
+                                                                  n_targets, easing, tiny,             \
+                                                                  ws.acc_part.as<float4>()))
+  if (T == 4) PB_DIRECT(4);
+  else if (T == 2) PB_DIRECT(2);
+  else PB_DIRECT(1);
 #undef PB_DIRECT
   PB_LAUNCH(ls, st, "direct_finish_kernel", direct_finish_kernel<<<blocks_for(n_targets, 256), 256, 0, st>>>(
       ws.acc_part.as<float4>(), int(splits), t0, n_targets, ws.pos64, ws.fixed, uint32_t(n),

@@ -199,6 +199,38 @@ def test_validate_and_retry_paths(name):
     assert np.array_equal(t["perm"], o.perm) and np.array_equal(t["skip"], o.skip)
 
 
+def plummer_like(n, seed):
+    """Centrally concentrated 3-D cluster (deep, unbalanced tree), off-centre and large-scale."""
+    rng = np.random.default_rng(seed)
+    r = 1.0 / np.sqrt(rng.random(n) ** (-2.0 / 3.0) - 1.0 + 1e-12)
+    r = np.minimum(r, 50.0)
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1)[:, None]
+    e = entities(n)
+    p = d * r[:, None] * 20.0 + np.array([300.0, -150.0, 40.0])
+    e["x"], e["y"], e["z"] = p.T
+    e["mass"] = (rng.random(n) + 0.5) / n
+    return e
+
+
+@pytest.mark.parametrize("name", ["astro2", "astro"])
+@pytest.mark.parametrize("theta", [0.5, 1.0])
+def test_clustered_offcentre_distribution(name, theta):
+    """Deep unbalanced tree, coordinates ~300 with structure down to ~1e-2: bit-exact tree, exact
+    interaction lists, accelerations in tolerance."""
+    s = plummer_like(30_000, 13)
+    el = api.TransformElement(name, theta=theta, e=0.05)
+    acc = el.transform(s)
+    t = el.debug_tree()
+    o = ob.CellTable(DIM[name], s)
+    for k in ("key", "perm", "cell_start", "level", "head", "count", "skip", "parent"):
+        assert np.array_equal(t[k], getattr(o, k)), k
+    assert np.array_equal(t["centre_ext"], o.centre_ext)
+    ref, cnt = ob.transform(name, s, theta, 0.05, counts=True)
+    assert np.array_equal(t["counts"], cnt)
+    assert_acc_parity(acc, ref)
+
+
 def test_momentum_conservation_direct_sum():
     """Newton's third law as a size-independent property: sum_i m_i a_i ~ 0 for all-free bodies."""
     s = gen.cube(20_000, seed=6)

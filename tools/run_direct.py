@@ -25,6 +25,6 @@ ms = sim.run_timed(reps)
 stop = True; th.join()
 mhz = sorted(c[0] for c in clocks if isinstance(c[0], int))
 pw = [c[1] for c in clocks if isinstance(c[0], int)]
-print("variant", os.environ.get("PB200_DIRECT_VARIANT"), "n", n, "ms/eval %.2f" % (ms / reps),
+print("n", n, "ms/eval %.2f" % (ms / reps),
       "interactions/s %.4g" % (n * n * reps / (ms * 1e-3)), "sm_mhz median", mhz[len(mhz) // 2] if mhz else None,
       "power max", max(pw) if pw else None, "samples", len(mhz))
