@@ -213,14 +213,21 @@ __global__ void __launch_bounds__(SORT_THREADS, SORT_ITEMS >= 16 ? 2 : 4) sort_o
     const unsigned* __restrict__ ghist /*[256] of this pass*/, unsigned* status /*[tiles][256]*/,
     unsigned* tile_counter, unsigned* err_flag) {
   __shared__ unsigned whist[8][256];
+  __shared__ unsigned tstart[256];  // first tile-local slot of each digit
+  __shared__ unsigned gadj[256];    // global slot of a digit's first element minus its tile-local slot
   __shared__ unsigned tile_s;
+  extern __shared__ __align__(16) unsigned char sort_smem[];
+  constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
+  uint64_t* ks = reinterpret_cast<uint64_t*>(sort_smem);            // tile keys, digit-sorted
+  uint32_t* vs = reinterpret_cast<uint32_t*>(ks + SORT_TILE);       // tile values, digit-sorted
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) tile_s = atomicAdd(tile_counter, 1u);  // tiles are numbered in start order
   for (int j = tid; j < 8 * 256; j += SORT_THREADS) (&whist[0][0])[j] = 0;
   const unsigned dbase = block_exclusive_scan_256(ghist[tid], nullptr);  // start of each digit; syncs
   const unsigned tile = tile_s;
-  constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
-  const size_t base = size_t(tile) * SORT_TILE + size_t(warp) * 32 * SORT_ITEMS;
+  const size_t tile_base = size_t(tile) * SORT_TILE;
+  const size_t base = tile_base + size_t(warp) * 32 * SORT_ITEMS;
+  const unsigned nvalid = static_cast<unsigned>(min(size_t(SORT_TILE), n - tile_base));
 
   uint64_t k[SORT_ITEMS];
   uint32_t v[SORT_ITEMS];
@@ -246,21 +253,35 @@ __global__ void __launch_bounds__(SORT_THREADS, SORT_ITEMS >= 16 ? 2 : 4) sort_o
     rank[i] = before + r;
   }
   __syncthreads();
-  {  // thread = digit
-    unsigned cnt = 0;
+  // thread = digit: tile count, per-warp exclusive offsets, and the partial count published at once
+  unsigned cnt = 0;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) {
-      const unsigned c = whist[w][tid];
-      whist[w][tid] = cnt;  // exclusive offset of warp w inside the tile
-      cnt += c;
+  for (int w = 0; w < 8; ++w) {
+    const unsigned c = whist[w][tid];
+    whist[w][tid] = cnt;  // exclusive offset of warp w inside the tile's run of this digit
+    cnt += c;
+  }
+  // decoupled look-back: one 32-bit word per (tile, digit) carries flag + count
+  volatile unsigned* st = status + size_t(tile) * 256 + tid;
+  *st = cnt | (tile == 0 ? LB_INCL : LB_PART);
+  const unsigned my_start = block_exclusive_scan_256(cnt, nullptr);  // syncs
+  tstart[tid] = my_start;
+  __syncthreads();
+  // reorder the tile in shared memory (digit-sorted, stable), so that the global writes below are
+  // coalesced: each digit's run is contiguous both here and at its destination
+#pragma unroll
+  for (int i = 0; i < SORT_ITEMS; ++i) {
+    const bool ok = (base + size_t(i) * 32 + lane) < n;
+    if (ok) {
+      const unsigned d = unsigned((k[i] >> shift) & mask);
+      const unsigned slot = tstart[d] + whist[warp][d] + rank[i];
+      ks[slot] = k[i];
+      vs[slot] = v[i];
     }
-    // decoupled look-back: one 32-bit word per (tile, digit) carries flag + count
-    volatile unsigned* st = status + size_t(tile) * 256 + tid;
+  }
+  {
     unsigned prefix = 0;
-    if (tile == 0) {
-      *st = cnt | LB_INCL;
-    } else {
-      *st = cnt | LB_PART;
+    if (tile != 0) {
       // walk back over the predecessors, LB_BATCH status words in flight at a time (the tiles of
       // one wave publish their partial counts at about the same moment, so the walk is long)
       unsigned t = tile;  // tiles t-1, t-2, ... remain to be examined
@@ -293,20 +314,15 @@ __global__ void __launch_bounds__(SORT_THREADS, SORT_ITEMS >= 16 ? 2 : 4) sort_o
       }
       *st = ((prefix + cnt) & LB_MASK) | LB_INCL;
     }
-    const unsigned gbase = dbase + prefix;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) whist[w][tid] += gbase;
+    gadj[tid] = dbase + prefix - my_start;
   }
   __syncthreads();
-#pragma unroll
-  for (int i = 0; i < SORT_ITEMS; ++i) {
-    const bool ok = (base + size_t(i) * 32 + lane) < n;
-    if (ok) {
-      const unsigned d = unsigned((k[i] >> shift) & mask);
-      const unsigned dst = whist[warp][d] + rank[i];
-      kout[dst] = k[i];
-      vout[dst] = v[i];
-    }
+  for (unsigned slot = tid; slot < nvalid; slot += SORT_THREADS) {
+    const uint64_t key = ks[slot];
+    const unsigned d = unsigned((key >> shift) & mask);
+    const unsigned dst = gadj[d] + slot;
+    kout[dst] = key;
+    vout[dst] = vs[slot];
   }
 }
 
@@ -1066,16 +1082,22 @@ cudaError_t sort_passes(GravityWorkspace& ws, size_t n, const SortBuffers& sb, c
                         LaunchStats& ls) {
   uint64_t* k[2] = {ws.key0.as<uint64_t>(), ws.key1.as<uint64_t>()};
   uint32_t* v[2] = {ws.idx0.as<uint32_t>(), ws.idx1.as<uint32_t>()};
+  // 48 KB of dynamic + 10 KB of static shared memory for the 16-keys-per-thread tile: opt in
+  // (per device, so per call: the handle may live on any device)
+  if (sb.items == 16)
+    PB_CUDA(cudaFuncSetAttribute(sort_onesweep_pass<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 SORT_THREADS * 16 * 12));
   int cur = 0;
   for (int p = 0; p < sb.plan.npass; ++p) {
+    const size_t smem = size_t(SORT_THREADS) * sb.items * 12;  // digit-sorted tile: u64 keys + u32 values
     if (sb.items == 8)
       PB_LAUNCH(ls, st, "sort_onesweep_pass",
-                sort_onesweep_pass<8><<<sb.tiles, SORT_THREADS, 0, st>>>(
+                sort_onesweep_pass<8><<<sb.tiles, SORT_THREADS, smem, st>>>(
                     k[cur], v[cur], k[cur ^ 1], v[cur ^ 1], n, sb.plan.shift(p), sb.plan.mask(p),
                     sb.ghist + p * 256, sb.status + size_t(p) * sb.tiles * 256, sb.counters + p, sb.err_flag));
     else
       PB_LAUNCH(ls, st, "sort_onesweep_pass",
-                sort_onesweep_pass<16><<<sb.tiles, SORT_THREADS, 0, st>>>(
+                sort_onesweep_pass<16><<<sb.tiles, SORT_THREADS, smem, st>>>(
                     k[cur], v[cur], k[cur ^ 1], v[cur ^ 1], n, sb.plan.shift(p), sb.plan.mask(p),
                     sb.ghist + p * 256, sb.status + size_t(p) * sb.tiles * 256, sb.counters + p, sb.err_flag));
     cur ^= 1;
