@@ -649,7 +649,8 @@ __global__ void __launch_bounds__(256) skip_kernel(const uint64_t* __restrict__ 
     }
     // a massless cell (the reference panics there): geometric centre instead of 0/0
     const double4 g = cells.centre_ext[c];
-    cells.com[c] = sm != 0.0 ? make_double4(sx / sm, sy / sm, sz / sm, sm)
+    const double inv = 1.0 / sm;  // one division: the reference's own (…) * inv_total_mass form (lib.rs:43-49)
+    cells.com[c] = sm != 0.0 ? make_double4(sx * inv, sy * inv, sz * inv, sm)
                              : make_double4(g.x, g.y, g.z, 0.0);
   }
 }
@@ -719,7 +720,8 @@ __global__ void __launch_bounds__(128) com_kernel(const uchar2* __restrict__ ab,
     }
     double4 out;
     if (m != 0.0) {
-      out = make_double4(sx / m, sy / m, sz / m, m);
+      const double inv = 1.0 / m;  // (…) * inv_total_mass, lib.rs:43-49
+      out = make_double4(sx * inv, sy * inv, sz * inv, m);
     } else {
       const double4 g = cells.centre_ext[p];
       out = make_double4(g.x, g.y, g.z, 0.0);
@@ -749,10 +751,15 @@ __global__ void __launch_bounds__(256) tgt_scatter_kernel(const uint32_t* __rest
 }
 
 // ---------------------------------------------------------------------------------------------
-// K8  Barnes-Hut walk.  One warp = 32 Morton-consecutive targets.  Control flow is warp-uniform
-//     (the warp visits cell c = min over lanes of the next cell each lane needs), decisions are
-//     per lane, so every target gets exactly the reference's interaction list
-//     (octree.rs:130-158: accept iff half_width / |p − centre| < theta, leaves always).
+// K8  Barnes-Hut walk.  One thread per target, targets in Morton order, stack-free: each lane
+//     follows its own pre-order path through the cell table (c -> c+1 when it opens a cell,
+//     c -> skip[c] when it accepts one), so every target gets exactly the reference's interaction
+//     list (octree.rs:130-158: accept iff half_width / |p − centre| < theta, leaves always).
+//     The 32 lanes of a warp are spatial neighbours and touch mostly the same cell records, which
+//     the L1 serves; a warp-cooperative variant (one cell per iteration for the whole warp, chosen
+//     with __reduce_min_sync, lanes that do not need it idle) was measured 1.5x SLOWER at
+//     theta = 0.7 (2.60 vs 1.71 ms at 4.2 M bodies): it executes the union of the lanes' paths
+//     (210 cells per warp) instead of the longest one (~110).
 //     Acceptance and p_b − p_a are evaluated in fp64 (a heavy body inside an accepted cell sits
 //     ~1e-7 from that cell's centre of mass); the force law runs in fp32.
 // ---------------------------------------------------------------------------------------------
@@ -813,14 +820,15 @@ __global__ void __launch_bounds__(256) walk_kernel(const double4* __restrict__ s
   const double theta2 = theta * theta;
   float fx = 0.f, fy = 0.f, fz = 0.f;
   uint32_t inter = 0;
-  uint32_t next = active ? 0u : total;
-  while (true) {
-    const uint32_t c = __reduce_min_sync(FULL, next);
-    if (c >= total) break;
+  // every lane follows its own pre-order path (c -> c+1 or skip[c]); lanes of a warp are spatial
+  // neighbours, so they mostly touch the same cache lines, and no lane waits for cells that only
+  // other lanes need
+  uint32_t c = active ? 0u : total;
+  while (c < total) {
     const double4 ce = ld_now_double4(cells.centre_ext + c);
     const double4 cm = ld_now_double4(cells.com + c);
     const uint32_t sk = ld_now_u32(cells.skip + c);
-    if (next == c) {
+    {
       const bool leaf = (sk == c + 1u);
       if (leaf || accept_cell(px, py, pz, ce, theta, theta2)) {
         const float dx = static_cast<float>(cm.x - px);
@@ -836,9 +844,9 @@ __global__ void __launch_bounds__(256) walk_kernel(const double4* __restrict__ s
         fy = fmaf(mw, dy, fy);
         fz = fmaf(mw, dz, fz);
         ++inter;
-        next = sk;
+        c = sk;
       } else {
-        next = c + 1u;
+        c = c + 1u;
       }
     }
   }
@@ -1054,9 +1062,10 @@ struct SortBuffers {
 // plans the passes over key bits [lo, key_bits) and clears histograms / look-back state
 cudaError_t sort_prepare(GravityWorkspace& ws, size_t n, int key_bits, int lo, cudaStream_t st,
                          SortBuffers* sb) {
-  // keys per thread: 8 wins at 1e5 bodies (more CTAs in flight), 16 from 1e6 up (measured on B200)
+  // keys per thread, measured on B200: 8 wins at 1e5 bodies and from 4e6 up (more CTAs in flight),
+  // 16 at 1e6 (one wave of 245 CTAs)
   static const int items_env = std::getenv("PB200_SORT_ITEMS") ? std::atoi(std::getenv("PB200_SORT_ITEMS")) : 0;
-  sb->items = items_env ? items_env : (n <= (size_t(1) << 19) ? 8 : 16);
+  sb->items = items_env ? items_env : ((n <= (size_t(1) << 19) || n >= (size_t(1) << 21)) ? 8 : 16);
   sb->tiles = blocks_for(n, SORT_THREADS * sb->items);
   SortPlan& plan = sb->plan;
   const int total = key_bits - lo;
