@@ -327,54 +327,88 @@ __global__ void __launch_bounds__(SORT_THREADS, SORT_ITEMS >= 16 ? 2 : 4) sort_o
 }
 
 // ---------------------------------------------------------------------------------------------
-// generic exclusive scan of u32[n] -> out[n+1] (out[n] = total); 3 launches
+// exclusive scan of u32[n] -> out[n+1] (out[n] = total): one kernel, decoupled look-back done by a
+// warp (32 predecessor tiles per round; status word = flag << 32 | value)
 // ---------------------------------------------------------------------------------------------
-constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_ITEMS = 16;
 constexpr int SCAN_TILE = 256 * SCAN_ITEMS;
+constexpr unsigned long long SCAN_PART = 1ull << 32, SCAN_INCL = 2ull << 32;
 
-__global__ void __launch_bounds__(256) scan_tile_sums(const uint32_t* __restrict__ in, size_t n,
-                                                      uint32_t* __restrict__ sums) {
-  const size_t base = size_t(blockIdx.x) * SCAN_TILE + size_t(threadIdx.x) * SCAN_ITEMS;
-  unsigned s = 0;
-#pragma unroll
-  for (int i = 0; i < SCAN_ITEMS; ++i)
-    if (base + i < n) s += in[base + i];
-  unsigned total;
-  block_exclusive_scan_256(s, &total);
-  if (threadIdx.x == 0) sums[blockIdx.x] = total;
-}
-
-// single block: exclusive scan of sums[m] in place
-__global__ void __launch_bounds__(256) scan_sums(uint32_t* __restrict__ sums, unsigned m) {
-  const unsigned chunk = (m + 255u) / 256u;
-  const unsigned b = threadIdx.x * chunk, e = min(b + chunk, m);
-  unsigned s = 0;
-  for (unsigned j = b; j < e; ++j) s += sums[j];
-  unsigned run = block_exclusive_scan_256(s, nullptr);
-  for (unsigned j = b; j < e; ++j) {
-    const unsigned c = sums[j];
-    sums[j] = run;
-    run += c;
-  }
-}
-
-__global__ void __launch_bounds__(256) scan_apply(const uint32_t* __restrict__ in, size_t n,
-                                                  const uint32_t* __restrict__ sums,
-                                                  uint32_t* __restrict__ out) {
-  const size_t base = size_t(blockIdx.x) * SCAN_TILE + size_t(threadIdx.x) * SCAN_ITEMS;
+__global__ void __launch_bounds__(256) scan_lookback_kernel(const uint32_t* __restrict__ in, size_t n,
+                                                            uint32_t* __restrict__ out,
+                                                            unsigned long long* status,
+                                                            unsigned* tile_counter) {
+  __shared__ unsigned tile_s, tile_prefix_s;
+  if (threadIdx.x == 0) tile_s = atomicAdd(tile_counter, 1u);
+  __syncthreads();
+  const unsigned tile = tile_s;
+  const size_t base = size_t(tile) * SCAN_TILE + size_t(threadIdx.x) * SCAN_ITEMS;
   unsigned v[SCAN_ITEMS];
-  unsigned s = 0;
+  unsigned sum = 0;
+  if (base + SCAN_ITEMS <= n) {
 #pragma unroll
-  for (int i = 0; i < SCAN_ITEMS; ++i) {
-    v[i] = (base + i < n) ? in[base + i] : 0u;
-    s += v[i];
+    for (int q = 0; q < SCAN_ITEMS / 4; ++q) {
+      const uint4 w = reinterpret_cast<const uint4*>(in + base)[q];
+      v[4 * q] = w.x; v[4 * q + 1] = w.y; v[4 * q + 2] = w.z; v[4 * q + 3] = w.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) v[i] = (base + i < n) ? in[base + i] : 0u;
   }
-  unsigned run = block_exclusive_scan_256(s, nullptr) + sums[blockIdx.x];
 #pragma unroll
-  for (int i = 0; i < SCAN_ITEMS; ++i) {
-    if (base + i < n) out[base + i] = run;
-    run += v[i];
-    if (base + i + 1 == n) out[n] = run;
+  for (int i = 0; i < SCAN_ITEMS; ++i) sum += v[i];
+  unsigned total;
+  const unsigned mine = block_exclusive_scan_256(sum, &total);
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    volatile unsigned long long* st = status + tile;
+    unsigned prefix = 0;
+    if (tile == 0) {
+      if (lane == 0) *st = SCAN_INCL | total;
+    } else {
+      if (lane == 0) *st = SCAN_PART | total;
+      unsigned t = tile;  // tiles t-1, t-2, ... remain
+      while (true) {
+        const bool valid = t > unsigned(lane);
+        unsigned long long w = SCAN_INCL;  // before tile 0: inclusive 0
+        if (valid) {
+          do {
+            w = *reinterpret_cast<volatile unsigned long long*>(status + (t - 1 - lane));
+          } while ((w >> 32) == 0ull);
+        }
+        const unsigned incl = __ballot_sync(FULL, (w >> 32) == 2ull);
+        const int first = incl ? __ffs(incl) - 1 : 31;  // nearest predecessor with an inclusive value
+        unsigned val = lane <= first ? unsigned(w) : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(FULL, val, o);
+        prefix += val;
+        if (incl) break;
+        t -= 32;
+      }
+      if (lane == 0) *st = SCAN_INCL | (unsigned long long)(prefix + total);
+    }
+    if (lane == 0) tile_prefix_s = prefix;
+  }
+  __syncthreads();
+  unsigned run = tile_prefix_s + mine;
+  if (base + SCAN_ITEMS <= n) {
+#pragma unroll
+    for (int q = 0; q < SCAN_ITEMS / 4; ++q) {
+      uint4 w;
+      w.x = run; run += v[4 * q];
+      w.y = run; run += v[4 * q + 1];
+      w.z = run; run += v[4 * q + 2];
+      w.w = run; run += v[4 * q + 3];
+      reinterpret_cast<uint4*>(out + base)[q] = w;
+    }
+    if (base + SCAN_ITEMS == n) out[n] = run;
+  } else {
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+      if (base + i < n) out[base + i] = run;
+      run += v[i];
+      if (base + i + 1 == n) out[n] = run;
+    }
   }
 }
 
@@ -1045,10 +1079,11 @@ inline unsigned blocks_for(size_t n, int per_block) {
 cudaError_t exclusive_scan(const uint32_t* in, uint32_t* out, size_t n, DevBuf& tmp, cudaStream_t st,
                            LaunchStats& ls) {
   const unsigned tiles = blocks_for(n, SCAN_TILE);
-  PB_PASS(tmp.ensure(size_t(tiles) * 4));
-  PB_LAUNCH(ls, st, "scan_tile_sums", scan_tile_sums<<<tiles, 256, 0, st>>>(in, n, tmp.as<uint32_t>()));
-  PB_LAUNCH(ls, st, "scan_sums", scan_sums<<<1, 256, 0, st>>>(tmp.as<uint32_t>(), tiles));
-  PB_LAUNCH(ls, st, "scan_apply", scan_apply<<<tiles, 256, 0, st>>>(in, n, tmp.as<uint32_t>(), out));
+  PB_PASS(tmp.ensure(size_t(tiles) * 8 + 16));  // [tile status words][tile counter]
+  PB_CUDA(cudaMemsetAsync(tmp.p, 0, size_t(tiles) * 8 + 16, st));
+  PB_LAUNCH(ls, st, "scan_lookback_kernel",
+            scan_lookback_kernel<<<tiles, 256, 0, st>>>(in, n, out, tmp.as<unsigned long long>(),
+                                                        reinterpret_cast<unsigned*>(tmp.as<unsigned long long>() + tiles)));
   return cudaGetLastError();
 }
 
@@ -1321,8 +1356,8 @@ cudaError_t gravity_check(GravityWorkspace& ws, cudaStream_t st, TreeCheck* out)
   if (out->sort_short) {
     ws.sort_lo = 0;
   } else if (!out->sort_error) {
-    // next time sort two levels deeper than anything seen now
-    const int want_levels = out->deepest_shared + 3;
+    // next time sort one level deeper than anything seen now (a deeper pair re-runs the build)
+    const int want_levels = out->deepest_shared + 2;
     ws.sort_lo = std::max(0, key_bits - dim * want_levels);
   }
   return cudaSuccess;
