@@ -84,7 +84,8 @@ class ClockSampler:
 
     def __init__(self, gpu_index=0, period=0.005):
         self.gpu, self.period = gpu_index, period
-        self.sm, self.mask, self.max_mhz, self.err = [], 0, None, None
+        self.samples, self.max_mhz, self.err = [], None, None
+        self.window = None  # (t0, t1) of the timed region, perf_counter clock
         self._stop = threading.Event()
         self.thread = None
 
@@ -97,8 +98,9 @@ class ClockSampler:
             get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
                 pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
             while not self._stop.is_set():
-                self.sm.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
-                self.mask |= int(get_reasons(h))
+                mhz = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                bits = int(get_reasons(h))
+                self.samples.append((time.perf_counter(), mhz, bits))
                 time.sleep(self.period)
         except Exception as e:  # noqa: BLE001
             self.err = repr(e)
@@ -111,9 +113,18 @@ class ClockSampler:
         self._stop.set()
         if self.thread:
             self.thread.join(timeout=2)
-        reasons = [n for bit, n in self.REASONS.items() if self.mask & bit]
-        out = {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.max_mhz,
-               "samples": len(self.sm), "reasons": reasons}
+        rows = self.samples
+        if self.window:  # samples inside the timed region (one NVML round trip is ~10-20 ms)
+            inside = [r for r in rows if self.window[0] <= r[0] <= self.window[1]]
+            # a region shorter than the sampling period: the samples bracketing it
+            rows = inside or sorted(rows, key=lambda r: min(abs(r[0] - self.window[0]), abs(r[0] - self.window[1])))[:2]
+        sm = [r[1] for r in rows]
+        mask = 0
+        for r in rows:
+            mask |= r[2]
+        reasons = [n for bit, n in self.REASONS.items() if mask & bit]
+        out = {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_mhz,
+               "samples": len(sm), "samples_total": len(self.samples), "reasons": reasons}
         if self.err:
             out["error"] = self.err
         return out
@@ -223,20 +234,22 @@ def run_ours(args, w):
                     exchange(gathered, n, rank, world)
             sim.run_sharded(k, xchg)
 
-    steps(max(args.warmup, 3))
-    launches0 = sim.stats()["kernel_launches"]
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    steps(max(args.warmup, 3))
+    launches0 = sim.stats()["kernel_launches"]
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
         torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_region0 = time.perf_counter()
     e0.record(stream)
     steps(args.steps)
     e1.record(stream)
     torch.cuda.synchronize()
+    sampler.window = (t_region0, time.perf_counter())
     if dist:
         dist.barrier()
         torch.cuda.synchronize()
