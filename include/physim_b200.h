@@ -207,6 +207,22 @@ int pb200_verlet_step_fused(void *v, void *transform, const Entity *entities, En
                             size_t n, double dt);
 int pb200_verlet_stats(void *v, Pb200Stats *out);
 
+/* --- euler and rk4 (integrators/src/euler.rs:17-50, rk4.rs:23-183) ------
+ * Same handle type and calling convention as verlet; a Rust shim's `euler` / `rk4` elements forward
+ * to these.  euler applies x + v dt + a dt²/2, v + a dt every step; rk4 evaluates acc_fn four times
+ * (on temporaries, as the reference does) and honours `fixed` (position kept, velocity zeroed). */
+typedef enum Pb200Integrator {
+  PB200_VERLET = 0,
+  PB200_EULER = 1,
+  PB200_RK4 = 2,
+} Pb200Integrator;
+void *pb200_integrator_create(int kind);
+void pb200_integrator_destroy(void *g);
+int pb200_integrator_step(void *g, const Entity *entities, Entity *new_state, size_t n,
+                          Pb200AccFn acc_fn, void *ctx, double dt);
+int pb200_integrator_step_fused(void *g, void *transform, const Entity *entities, Entity *new_state,
+                                size_t n, double dt);
+
 /* --- device-resident simulation (bench `value`, multi-GPU sharding) ----------------------
  * State lives in HBM across steps: fp64 {x,y,z,m}, previous positions, velocities.
  * rank/world: this process owns bodies [rank*S, min(n, (rank+1)*S)), S = ceil(n/world), as force targets and
@@ -242,6 +258,8 @@ int pb200_sim_download(void *sim, Entity *state, size_t n);
 /* Accelerations of the last force evaluation, original order, for the owned targets. */
 int pb200_sim_last_accelerations(void *sim, Acceleration *acc, size_t n);
 int pb200_sim_stats(void *sim, Pb200Stats *out);
+/* Integrator of the device-resident loop (default verlet; rk4 only with world == 1). */
+int pb200_sim_set_integrator(void *sim, int kind);
 /* Override the owned target range [t0, t1) chosen by rank/world at upload (sampled timing of a
  * target slice of a large all-pairs problem). */
 int pb200_sim_set_targets(void *sim, size_t t0, size_t t1);

@@ -53,6 +53,13 @@ def lib():
                                          C.c_void_p, C.c_double]
         L.oracle_run_pipeline.argtypes = [C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_size_t,
                                           C.c_double, C.c_size_t, C.c_void_p]
+        L.oracle_integrator_new.restype = C.c_void_p
+        L.oracle_integrator_new.argtypes = [C.c_int]
+        L.oracle_integrator_free.argtypes = [C.c_void_p]
+        L.oracle_integrator_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, ACC_FN,
+                                             C.c_void_p, C.c_double]
+        L.oracle_run_pipeline_with.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p,
+                                               C.c_size_t, C.c_double, C.c_size_t]
         L.oracle_encode_key.restype = C.c_uint64
         L.oracle_encode_key.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double]
         L.oracle_table_build.restype = C.c_void_p
@@ -168,6 +175,47 @@ class Verlet:
         if getattr(self, "_h", None):
             lib().oracle_verlet_free(self._h)
             self._h = None
+
+
+INTEGRATOR = {"verlet": 0, "euler": 1, "rk4": 2}
+
+
+class Integrator:
+    """verlet / euler / rk4 (integrators/src/{verlet,euler,rk4}.rs)."""
+
+    def __init__(self, name):
+        self._h = lib().oracle_integrator_new(INTEGRATOR[name])
+
+    def integrate(self, ents, acc_fn, dt, out=None):
+        ents = _ents(ents)
+        n = len(ents)
+        out = ents.copy() if out is None else out  # rk4 assigns fields of the caller's new_state
+
+        def tramp(_ctx, sp, nn, ap):
+            if nn == 0:
+                return
+            s = np.ctypeslib.as_array(C.cast(sp, C.POINTER(C.c_uint8)), shape=(nn * 80,)).view(ENTITY)
+            a = np.ctypeslib.as_array(C.cast(ap, C.POINTER(C.c_double)), shape=(nn * 3,)).view(ACCELERATION)
+            acc_fn(s, a)
+
+        cb = ACC_FN(tramp)
+        lib().oracle_integrator_step(self._h, _ptr(ents), _ptr(out), n, cb, None, float(dt))
+        return out
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().oracle_integrator_free(self._h)
+            self._h = None
+
+
+def run_pipeline_with(integrator, kind, state, theta, e, dt, iterations):
+    """The simulation loop with a choice of integrator; returns the final state."""
+    state = _ents(state).copy()
+    rc = lib().oracle_run_pipeline_with(INTEGRATOR[integrator], KIND[kind], float(theta), abs(float(e)),
+                                        _ptr(state), len(state), float(dt), int(iterations))
+    if rc != 0:
+        raise OraclePanic(lib().oracle_last_error().decode())
+    return state
 
 
 def run_pipeline(kind, state, theta, e, dt, iterations):

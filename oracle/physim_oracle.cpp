@@ -379,6 +379,101 @@ struct Verlet {
   }
 };
 
+// ---- euler (integrators/src/euler.rs:17-50) and rk4 (integrators/src/rk4.rs:23-183) --------------
+// the integrators either side of verlet.  euler is verlet's first-step formula
+// every step; rk4 evaluates the accelerations four times on temporaries and honours `fixed`.
+
+struct Euler {
+  void step(const Entity* ent, Entity* out, size_t n, AccFn fn, void* ctx, double dt) {
+    std::vector<Acceleration> acc(n, Acceleration{0.0, 0.0, 0.0});  // euler.rs:25
+    fn(ctx, ent, n, acc.data());
+    const double dt2 = dt * dt;
+    for (size_t i = 0; i < n; ++i) {
+      const Entity& e = ent[i];
+      const Acceleration& a = acc[i];
+      Entity o = e;
+      o.x = e.x + e.vx * dt + 0.5 * a.x * dt2;  // euler.rs:30-32
+      o.y = e.y + e.vy * dt + 0.5 * a.y * dt2;
+      o.z = e.z + e.vz * dt + 0.5 * a.z * dt2;
+      o.vx = e.vx + a.x * dt;                   // euler.rs:35-37
+      o.vy = e.vy + a.y * dt;
+      o.vz = e.vz + a.z * dt;
+      out[i] = o;
+    }
+  }
+};
+
+struct Rk4 {
+  // k = (dt * e.v, dt * a) with the other fields of e               (rk4.rs:36-50 and repeats)
+  static void slope(const std::vector<Entity>& at, const std::vector<Acceleration>& f, double dt,
+                    std::vector<Entity>& k) {
+    k = at;
+    for (size_t i = 0; i < at.size(); ++i) {
+      k[i].x = dt * at[i].vx; k[i].y = dt * at[i].vy; k[i].z = dt * at[i].vz;
+      k[i].vx = dt * f[i].x;  k[i].vy = dt * f[i].y;  k[i].vz = dt * f[i].z;
+    }
+  }
+  // temp = e + w * k (w = 0.5, 0.5, 1.0; the last one is written `e.x + k.x`)   (rk4.rs:53-66 ...)
+  static void advance(const Entity* e, const std::vector<Entity>& k, double w, bool plain,
+                      std::vector<Entity>& t) {
+    t.assign(e, e + k.size());
+    for (size_t i = 0; i < k.size(); ++i) {
+      if (plain) {
+        t[i].x = e[i].x + k[i].x;   t[i].y = e[i].y + k[i].y;   t[i].z = e[i].z + k[i].z;
+        t[i].vx = e[i].vx + k[i].vx; t[i].vy = e[i].vy + k[i].vy; t[i].vz = e[i].vz + k[i].vz;
+      } else {
+        t[i].x = e[i].x + w * k[i].x;   t[i].y = e[i].y + w * k[i].y;   t[i].z = e[i].z + w * k[i].z;
+        t[i].vx = e[i].vx + w * k[i].vx; t[i].vy = e[i].vy + w * k[i].vy; t[i].vz = e[i].vz + w * k[i].vz;
+      }
+    }
+  }
+  void step(const Entity* ent, Entity* out, size_t n, AccFn fn, void* ctx, double dt) {
+    std::vector<Entity> cur(ent, ent + n), k1, k2, k3, k4, tmp;
+    std::vector<Acceleration> f(n);
+    auto eval = [&](const std::vector<Entity>& at, std::vector<Entity>& k) {
+      std::fill(f.begin(), f.end(), Acceleration{0.0, 0.0, 0.0});
+      fn(ctx, at.data(), n, f.data());
+      slope(at, f, dt, k);
+    };
+    eval(cur, k1);
+    advance(ent, k1, 0.5, false, tmp);
+    eval(tmp, k2);
+    advance(ent, k2, 0.5, false, tmp);
+    eval(tmp, k3);
+    advance(ent, k3, 1.0, true, tmp);
+    eval(tmp, k4);
+    for (size_t i = 0; i < n; ++i) {  // rk4.rs:150-176
+      const Entity& e = ent[i];
+      Entity& ns = out[i];
+      if (!e.fixed) {
+        ns.x = e.x + (k1[i].x + 2.0 * k2[i].x + 2.0 * k3[i].x + k4[i].x) / 6.0;
+        ns.y = e.y + (k1[i].y + 2.0 * k2[i].y + 2.0 * k3[i].y + k4[i].y) / 6.0;
+        ns.z = e.z + (k1[i].z + 2.0 * k2[i].z + 2.0 * k3[i].z + k4[i].z) / 6.0;
+        ns.vx = e.vx + (k1[i].vx + 2.0 * k2[i].vx + 2.0 * k3[i].vx + k4[i].vx) / 6.0;
+        ns.vy = e.vy + (k1[i].vy + 2.0 * k2[i].vy + 2.0 * k3[i].vy + k4[i].vy) / 6.0;
+        ns.vz = e.vz + (k1[i].vz + 2.0 * k2[i].vz + 2.0 * k3[i].vz + k4[i].vz) / 6.0;
+      } else {
+        ns.x = e.x; ns.y = e.y; ns.z = e.z;
+        ns.vx = 0.0; ns.vy = 0.0; ns.vz = 0.0;
+      }
+      ns.mass = e.mass; ns.radius = e.radius; ns.id = e.id; ns.fixed = e.fixed;
+    }
+  }
+};
+
+// kind: 0 verlet, 1 euler, 2 rk4
+struct Integrator {
+  int kind;
+  Verlet verlet;
+  Euler euler;
+  Rk4 rk4;
+  void step(const Entity* ent, Entity* out, size_t n, AccFn fn, void* ctx, double dt) {
+    if (kind == 0) verlet.step(ent, out, n, fn, ctx, dt);
+    else if (kind == 1) euler.step(ent, out, n, fn, ctx, dt);
+    else rk4.step(ent, out, n, fn, ctx, dt);
+  }
+};
+
 // ---- oracle 2: level-array tree ------------------------------------------------------------
 // Keys: one digit per level, digit = octant id of the reference (x | y<<1 | z<<2), obtained by
 // repeating the reference's compare (strict >) and halve (centre ± extent/2) in fp64 so the
@@ -782,6 +877,33 @@ int oracle_run_pipeline(int kind, double theta, double easing, Entity* state, si
       seconds[1] += ctx.phases[1];
       seconds[2] += total - ctx.phases[0] - ctx.phases[1];
     }
+  });
+}
+
+void* oracle_integrator_new(int kind) {
+  auto* g = new Integrator;
+  g->kind = kind;
+  return g;
+}
+void oracle_integrator_free(void* g) { delete static_cast<Integrator*>(g); }
+void oracle_integrator_step(void* g, const Entity* ent, Entity* out, size_t n, AccFn fn, void* ctx,
+                            double dt) {
+  static_cast<Integrator*>(g)->step(ent, out, n, fn, ctx, dt);
+}
+
+// oracle_run_pipeline with a choice of integrator (0 verlet, 1 euler, 2 rk4)
+int oracle_run_pipeline_with(int integrator, int kind, double theta, double easing, Entity* state,
+                             size_t n, double dt, size_t iterations) {
+  return guarded([&] {
+    TransformCtx ctx{kind, theta, easing, {0.0, 0.0}};
+    Integrator integ;
+    integ.kind = integrator;
+    std::vector<Entity> cur(state, state + n), nxt(state, state + n);
+    for (size_t it = 0; it < iterations; ++it) {
+      integ.step(cur.data(), nxt.data(), n, transform_cb, &ctx, dt);
+      cur = nxt;
+    }
+    std::memcpy(state, cur.data(), n * sizeof(Entity));
   });
 }
 

@@ -107,6 +107,12 @@ def lib():
     L.pb200_verlet_step.argtypes = [vp, vp, vp, sz, ACC_FN, vp, dbl]
     L.pb200_verlet_step_fused.argtypes = [vp, vp, vp, vp, sz, dbl]
     L.pb200_verlet_stats.argtypes = [vp, C.POINTER(Pb200Stats)]
+    L.pb200_integrator_create.restype = vp
+    L.pb200_integrator_create.argtypes = [i32]
+    L.pb200_integrator_destroy.argtypes = [vp]
+    L.pb200_integrator_step.argtypes = [vp, vp, vp, sz, ACC_FN, vp, dbl]
+    L.pb200_integrator_step_fused.argtypes = [vp, vp, vp, vp, sz, dbl]
+    L.pb200_sim_set_integrator.argtypes = [vp, i32]
     L.pb200_sim_create.restype = vp
     L.pb200_sim_create.argtypes = [i32, dbl, dbl, dbl, i32, i32]
     L.pb200_sim_destroy.argtypes = [vp]
@@ -256,11 +262,18 @@ class TransformElement:
             pass
 
 
-class Verlet:
-    """`verlet` integrator (integrators/src/verlet.rs) over pb200_verlet_*."""
+INTEGRATORS = {"verlet": 0, "euler": 1, "rk4": 2}
 
-    def __init__(self):
-        self._v = lib().pb200_verlet_create()
+
+class Verlet:
+    """`verlet` integrator (integrators/src/verlet.rs) over pb200_verlet_*; with `name` = "euler" or
+    "rk4" the sibling integrators (integrators/src/euler.rs, rk4.rs) over pb200_integrator_*."""
+
+    def __init__(self, name="verlet"):
+        self.name = name
+        self._v = lib().pb200_integrator_create(INTEGRATORS[name])
+        if not self._v:
+            raise Pb200Error(last_error())
 
     def integrate(self, entities, acc_fn, dt):
         """IntegratorElement::integrate: acc_fn(state, accelerations) adds into accelerations."""
@@ -276,7 +289,7 @@ class Verlet:
             acc_fn(s, a)
 
         cb = ACC_FN(tramp)
-        if lib().pb200_verlet_step(self._v, _ptr(entities), _ptr(new_state), n, cb, None, float(dt)) != 0:
+        if lib().pb200_integrator_step(self._v, _ptr(entities), _ptr(new_state), n, cb, None, float(dt)) != 0:
             raise Pb200Error(last_error())
         return new_state
 
@@ -379,6 +392,10 @@ class Sim:
         if lib().pb200_sim_stats(self._s, C.byref(st)) != 0:
             raise Pb200Error(last_error())
         return st.as_dict()
+
+    def set_integrator(self, name):
+        if lib().pb200_sim_set_integrator(self._s, INTEGRATORS[name]) != 0:
+            raise Pb200Error(last_error())
 
     def set_targets(self, t0, t1):
         if lib().pb200_sim_set_targets(self._s, int(t0), int(t1)) != 0:

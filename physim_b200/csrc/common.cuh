@@ -115,7 +115,7 @@ struct GravityWorkspace {
   DevBuf src4, key0, key1, idx0, idx1, spos64, ab, cell_start, scan_tmp, tile_counts, digit_base,
       extent_bits, tgt_list, tgt_flags;
   DevBuf c_level, c_head, c_count, c_skip, c_parent, c_arrived, c_centre_ext, c_com;
-  DevBuf acc, acc_part, counters;
+  DevBuf acc, acc_part, counters, sticky;
   size_t n_cells = 0;   // cells of the last checked evaluation
   size_t cell_cap = 0;  // capacity of the cell arrays
   int tree_dim = 0;     // 2 / 3 after a tree build, 0 otherwise
@@ -224,6 +224,7 @@ cudaError_t gravity_evaluate(GravityWorkspace& ws, const GravityParams& prm, siz
 // Host-side verdict on the last tree build (one small D2H + stream sync).  Also feeds the next
 // evaluation: cell-table capacity follows the observed total, the sort drops the key bits below
 // the observed tree depth (+2 levels) and is re-validated every time.
+// (worst case over every build since the previous check: builds may run unverified in between)
 struct TreeCheck {
   uint32_t total = 0;       // cells
   int deepest_shared = -1;  // deepest level shared by two sorted neighbours with different keys
@@ -249,6 +250,13 @@ cudaError_t gravity_count_interactions(GravityWorkspace& ws, cudaStream_t stream
 cudaError_t verlet_update(double4* cur, double4* prev, double4* vel, const float4* acc32,
                           const double* acc64, size_t n, double dt, int first, cudaStream_t stream,
                           LaunchStats& ls, double* out6 = nullptr);
+
+// One rk4 stage (1..4): folds k_stage into the running sums, writes the next evaluation point
+// (stages 1-3; also packed into out6 when given) or the new state (stage 4: out_pos/out_vel/out6).
+cudaError_t rk4_stage(int stage, const double4* e_pos, const double4* e_vel, const uint8_t* fixed,
+                      double4* t_pos, double4* t_vel, double4* s_pos, double4* s_vel, const float4* acc32,
+                      const double* acc64, size_t n, double dt, double4* out_pos, double4* out_vel,
+                      double* out6, cudaStream_t stream, LaunchStats& ls);
 
 // fp32 FFMA probe
 cudaError_t probe_fp32(double* tflops);

@@ -236,15 +236,19 @@ struct VerletObj {
   std::mutex mu;
   GpuContext gpu;
   int device;
+  int kind = PB200_VERLET;  // Pb200Integrator
   size_t n_prev = 0;  // length of the stored previous state (verlet.rs:102: len != n => first step)
   DevBuf cur, prev, vel, acc64, fixed, out6;
+  DevBuf t_pos, t_vel, s_pos, s_vel;  // rk4: evaluation point and running sums
   PinnedBuf h_pos, h_vel, h_fixed, h_acc, h_out;
+  std::vector<Entity> h_temp;         // rk4, generic form: the evaluation point as host entities
   LaunchStats ls;
   Pb200Stats stats;
   ~VerletObj() {
     if (gpu.ready) {
       cudaSetDevice(gpu.device);
       cur.release(); prev.release(); vel.release(); acc64.release(); fixed.release(); out6.release();
+      t_pos.release(); t_vel.release(); s_pos.release(); s_vel.release();
       h_pos.release(); h_vel.release(); h_fixed.release(); h_acc.release(); h_out.release();
       gpu.destroy();
     }
@@ -321,8 +325,48 @@ cudaError_t verlet_finish(VerletObj& v, cudaStream_t st, const Entity* entities,
   return cudaSuccess;
 }
 
+cudaError_t rk4_buffers(VerletObj& v, size_t n) {
+  PB_PASS(v.t_pos.ensure(n * sizeof(double4)));
+  PB_PASS(v.t_vel.ensure(n * sizeof(double4)));
+  PB_PASS(v.s_pos.ensure(n * sizeof(double4)));
+  PB_PASS(v.s_vel.ensure(n * sizeof(double4)));
+  return cudaSuccess;
+}
+
+// rk4 with a host acceleration callback (integrators/src/rk4.rs:23-183): four evaluations, the
+// evaluation points 2-4 are materialised as host entities for the callback
+cudaError_t rk4_step_generic(VerletObj& v, const Entity* entities, Entity* new_state, size_t n,
+                             Pb200AccFn acc_fn, void* ctx, double dt) {
+  if (n == 0) return cudaSuccess;
+  PB_PASS(verlet_buffers(v, n));
+  PB_PASS(rk4_buffers(v, n));
+  PB_PASS(v.acc64.ensure(n * sizeof(Acceleration)));
+  PB_PASS(v.h_acc.ensure(n * sizeof(Acceleration)));
+  cudaStream_t st = v.gpu.stream;
+  std::vector<Acceleration> acc(n);
+  v.h_temp.resize(n);
+  PB_PASS(upload_packed(entities, n, v.h_pos.as<double4>(), v.h_fixed.as<uint8_t>(), v.h_vel.as<double4>(),
+                        v.cur.as<double4>(), v.fixed.as<uint8_t>(), v.vel.as<double4>(), st));
+  const Entity* at = entities;
+  for (int stage = 1; stage <= 4; ++stage) {
+    std::fill(acc.begin(), acc.end(), Acceleration{0.0, 0.0, 0.0});
+    acc_fn(ctx, at, n, acc.data());
+    std::memcpy(v.h_acc.p, acc.data(), n * sizeof(Acceleration));
+    PB_CUDA(cudaMemcpyAsync(v.acc64.p, v.h_acc.p, n * sizeof(Acceleration), cudaMemcpyHostToDevice, st));
+    PB_PASS(rk4_stage(stage, v.cur.as<double4>(), v.vel.as<double4>(), v.fixed.as<uint8_t>(),
+                      v.t_pos.as<double4>(), v.t_vel.as<double4>(), v.s_pos.as<double4>(),
+                      v.s_vel.as<double4>(), nullptr, v.acc64.as<double>(), n, dt, v.cur.as<double4>(),
+                      v.vel.as<double4>(), v.out6.as<double>(), st, v.ls));
+    // stages 1-3: out6 = next evaluation point -> host entities; stage 4: out6 = new state
+    PB_PASS(verlet_finish(v, st, entities, stage < 4 ? v.h_temp.data() : new_state, n));
+    at = v.h_temp.data();
+  }
+  return cudaSuccess;
+}
+
 cudaError_t verlet_step_generic(VerletObj& v, const Entity* entities, Entity* new_state, size_t n,
                                 Pb200AccFn acc_fn, void* ctx, double dt) {
+  if (v.kind == PB200_RK4) return rk4_step_generic(v, entities, new_state, n, acc_fn, ctx, dt);
   std::vector<Acceleration> acc(n, Acceleration{0.0, 0.0, 0.0});  // verlet.rs:93
   acc_fn(ctx, entities, n, acc.data());                           // verlet.rs:94
   if (n == 0) {
@@ -333,7 +377,8 @@ cudaError_t verlet_step_generic(VerletObj& v, const Entity* entities, Entity* ne
   PB_PASS(v.acc64.ensure(n * sizeof(Acceleration)));
   PB_PASS(v.h_acc.ensure(n * sizeof(Acceleration)));
   cudaStream_t st = v.gpu.stream;
-  const bool first = v.n_prev != n;
+  // euler (euler.rs:30-37) is verlet's first-step formula on every step
+  const bool first = v.kind == PB200_EULER || v.n_prev != n;
   PB_CUDA(cudaEventRecord(v.gpu.ev[0], st));
   PB_PASS(upload_packed(entities, n, v.h_pos.as<double4>(), nullptr, v.h_vel.as<double4>(),
                         v.cur.as<double4>(), nullptr, first ? v.vel.as<double4>() : nullptr, st));
@@ -353,19 +398,50 @@ cudaError_t verlet_step_generic(VerletObj& v, const Entity* entities, Entity* ne
   return cudaSuccess;
 }
 
+// rk4 with the accelerations of `t` evaluated on the device at every stage
+cudaError_t rk4_step_fused(VerletObj& v, TransformObj& t, const Entity* entities, Entity* new_state, size_t n,
+                           double dt) {
+  v.device = t.device;
+  PB_PASS(verlet_buffers(v, n));
+  PB_PASS(rk4_buffers(v, n));
+  PB_PASS(t.gpu.init(t.device));
+  cudaStream_t st = v.gpu.stream;
+  PB_PASS(upload_packed(entities, n, v.h_pos.as<double4>(), v.h_fixed.as<uint8_t>(), v.h_vel.as<double4>(),
+                        v.cur.as<double4>(), v.fixed.as<uint8_t>(), v.vel.as<double4>(), st));
+  t.ws.fixed = v.fixed.as<uint8_t>();
+  t.ws.n = n;
+  for (int stage = 1; stage <= 4; ++stage) {
+    t.ws.pos64 = stage == 1 ? v.cur.as<double4>() : v.t_pos.as<double4>();
+    PB_PASS(gravity_evaluate(t.ws, t.prm, 0, n, st, t.ls, true));
+    PB_PASS(rk4_stage(stage, v.cur.as<double4>(), v.vel.as<double4>(), v.fixed.as<uint8_t>(),
+                      v.t_pos.as<double4>(), v.t_vel.as<double4>(), v.s_pos.as<double4>(),
+                      v.s_vel.as<double4>(), t.ws.acc.as<float4>(), nullptr, n, dt, v.cur.as<double4>(),
+                      v.vel.as<double4>(), stage == 4 ? v.out6.as<double>() : nullptr, st, v.ls));
+  }
+  PB_PASS(verlet_finish(v, st, entities, new_state, n));
+  t.last_n = n;
+  t.stats.n_bodies = n;
+  t.stats.n_cells = t.ws.n_cells;
+  t.stats.kernel_launches = t.ls.launches;
+  v.stats.n_cells = t.ws.n_cells;
+  v.stats.kernel_launches = v.ls.launches + t.ls.launches;
+  return cudaSuccess;
+}
+
 cudaError_t verlet_step_fused(VerletObj& v, TransformObj& t, const Entity* entities, Entity* new_state, size_t n,
                               double dt) {
   if (n == 0) {
     v.n_prev = 0;
     return cudaSuccess;
   }
+  if (v.kind == PB200_RK4) return rk4_step_fused(v, t, entities, new_state, n, dt);
   const double t_wall = now_ms();
   g_pack_ms = g_unpack_ms = 0.0;
   v.device = t.device;
   PB_PASS(verlet_buffers(v, n));
   PB_PASS(t.gpu.init(t.device));
   cudaStream_t st = v.gpu.stream;
-  const bool first = v.n_prev != n;
+  const bool first = v.kind == PB200_EULER || v.n_prev != n;
   PB_CUDA(cudaEventRecord(v.gpu.ev[0], st));
   PB_PASS(upload_packed(entities, n, v.h_pos.as<double4>(), v.h_fixed.as<uint8_t>(), v.h_vel.as<double4>(),
                         v.cur.as<double4>(), v.fixed.as<uint8_t>(), first ? v.vel.as<double4>() : nullptr, st));
@@ -407,6 +483,8 @@ struct SimObj {
   uint64_t replays = 0;
   PinnedBuf h_pos, h_vel, h_fixed, h_acc;
   size_t n = 0, t0 = 0, t1 = 0, slice = 0;
+  int integrator = PB200_VERLET;
+  DevBuf t_pos, t_vel, s_pos, s_vel;  // rk4
   bool first = true, checked = false;
   LaunchStats ls;
   Pb200Stats stats;
@@ -416,6 +494,7 @@ struct SimObj {
       ws.release_all();
       cur.release(); prev.release(); vel.release(); fixed.release();
       ck_cur.release(); ck_prev.release(); ck_vel.release();
+      t_pos.release(); t_vel.release(); s_pos.release(); s_vel.release();
       h_pos.release(); h_vel.release(); h_fixed.release(); h_acc.release();
       gpu.destroy();
     }
@@ -456,12 +535,32 @@ cudaError_t sim_step(SimObj& s, bool force_check) {
   if (s.n == 0) return cudaSuccess;
   cudaStream_t st = s.gpu.stream;
   const bool check = force_check || !s.checked;  // size the cell table once, then stay asynchronous
+  if (s.integrator == PB200_RK4) {
+    // four force evaluations per step on the device-side evaluation points (world == 1)
+    const size_t bytes = s.n * sizeof(double4);
+    PB_PASS(s.t_pos.ensure(bytes));
+    PB_PASS(s.t_vel.ensure(bytes));
+    PB_PASS(s.s_pos.ensure(bytes));
+    PB_PASS(s.s_vel.ensure(bytes));
+    for (int stage = 1; stage <= 4; ++stage) {
+      s.ws.pos64 = stage == 1 ? s.cur.as<double4>() : s.t_pos.as<double4>();
+      PB_PASS(gravity_evaluate(s.ws, s.prm, 0, s.n, st, s.ls, check));
+      PB_PASS(rk4_stage(stage, s.cur.as<double4>(), s.vel.as<double4>(), s.fixed.as<uint8_t>(),
+                        s.t_pos.as<double4>(), s.t_vel.as<double4>(), s.s_pos.as<double4>(),
+                        s.s_vel.as<double4>(), s.ws.acc.as<float4>(), nullptr, s.n, s.dt,
+                        s.cur.as<double4>(), s.vel.as<double4>(), nullptr, st, s.ls));
+    }
+    s.ws.pos64 = s.cur.as<double4>();
+    s.checked = true;
+    s.first = false;
+    return cudaSuccess;
+  }
   PB_PASS(gravity_evaluate(s.ws, s.prm, s.t0, s.t1, st, s.ls, check));
   s.checked = true;
   const size_t nl = s.t1 - s.t0;
   PB_PASS(verlet_update(s.cur.as<double4>() + s.t0, s.prev.as<double4>() + s.t0,
                         s.vel.as<double4>() + s.t0, s.ws.acc.as<float4>() + s.t0, nullptr, nl, s.dt,
-                        s.first ? 1 : 0, st, s.ls));
+                        (s.first || s.integrator == PB200_EULER) ? 1 : 0, st, s.ls));
   s.first = false;
   return cudaSuccess;
 }
@@ -781,11 +880,26 @@ int pb200_transform_debug_hint(void* obj, int sort_lo, size_t n_cells_hint) {
 
 // ---- verlet -----------------------------------------------------------------------------------
 
-void* pb200_verlet_create(void) {
+void* pb200_integrator_create(int kind) {
+  if (kind < PB200_VERLET || kind > PB200_RK4) {
+    set_error("unknown integrator kind %d", kind);
+    return nullptr;
+  }
   auto* v = new VerletObj();
+  v->kind = kind;
   v->device = g_device;
   std::memset(&v->stats, 0, sizeof v->stats);
   return v;
+}
+void* pb200_verlet_create(void) { return pb200_integrator_create(PB200_VERLET); }
+void pb200_integrator_destroy(void* v) { delete static_cast<VerletObj*>(v); }
+int pb200_integrator_step(void* g, const Entity* entities, Entity* new_state, size_t n, Pb200AccFn acc_fn,
+                          void* ctx, double dt) {
+  return pb200_verlet_step(g, entities, new_state, n, acc_fn, ctx, dt);
+}
+int pb200_integrator_step_fused(void* g, void* transform, const Entity* entities, Entity* new_state, size_t n,
+                                double dt) {
+  return pb200_verlet_step_fused(g, transform, entities, new_state, n, dt);
 }
 void pb200_verlet_destroy(void* v) { delete static_cast<VerletObj*>(v); }
 
@@ -1055,6 +1169,19 @@ int pb200_sim_stats(void* sim, Pb200Stats* out) {
   s.stats.n_bodies = s.n;
   s.stats.kernel_launches = s.ls.launches;
   *out = s.stats;
+  return 0;
+}
+
+int pb200_sim_set_integrator(void* sim, int kind) {
+  if (!sim) return -1;
+  auto& s = *static_cast<SimObj*>(sim);
+  std::lock_guard<std::mutex> lk(s.mu);
+  if (kind < PB200_VERLET || kind > PB200_RK4 || (kind == PB200_RK4 && s.world != 1)) {
+    set_error("pb200_sim_set_integrator: bad kind (rk4 needs world == 1: every stage would need an exchange)");
+    return -1;
+  }
+  s.integrator = kind;
+  s.first = true;
   return 0;
 }
 

@@ -611,11 +611,17 @@ __global__ void __launch_bounds__(256) skip_kernel(const uint64_t* __restrict__ 
                                                    const uint32_t* __restrict__ perm,
                                                    const uchar2* __restrict__ ab,
                                                    const uint32_t* __restrict__ cell_start, size_t n,
-                                                   const unsigned* __restrict__ any_merged,
-                                                   CellArrays cells) {
+                                                   const unsigned* __restrict__ tree_meta,
+                                                   unsigned* __restrict__ sticky, CellArrays cells) {
   constexpr int LM = TreeDim<DIM>::LM;
   const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t total = cell_start[n];
+  if (c == 0u) {
+    // worst case over every build since the last host check (builds run unverified in between):
+    // [0] cells needed, [1] 1 + deepest level shared by distinct neighbouring keys
+    atomicMax(&sticky[0], total);
+    atomicMax(&sticky[1], tree_meta[0]);
+  }
   if (total > cells.capacity || c >= total) return;
   if (c == 0u) cells.parent[0] = NO_PARENT;
   const int lev = cells.level[c];
@@ -667,7 +673,7 @@ __global__ void __launch_bounds__(256) skip_kernel(const uint64_t* __restrict__ 
   cells.skip[c] = skip;
   if (cnt <= SMALL_CELL) {
     double sm = 0.0, sx = 0.0, sy = 0.0, sz = 0.0;
-    if (*any_merged == 0u) {  // every unit is one body: plain sums over the run
+    if (tree_meta[1] == 0u) {  // no merged unit anywhere: plain sums over the run
       for (size_t j = s; j < e; ++j) {
         const double4 q = sp[j];
         sm += q.w; sx += q.w * q.x; sy += q.w * q.y; sz += q.w * q.z;
@@ -1117,6 +1123,7 @@ cudaError_t sort_prepare(GravityWorkspace& ws, size_t n, int key_bits, int lo, c
   sb->err_flag = sb->counters + SORT_MAX_PASSES;
   sb->status = sb->ghist + head_words;
   PB_CUDA(cudaMemsetAsync(sb->ghist, 0, words * 4, st));
+  if (ws.sticky.p) sb->err_flag = ws.sticky.as<unsigned>() + 2;  // survives until the next host check
   ws.sort_err_flag = sb->err_flag;
   return cudaSuccess;
 }
@@ -1156,6 +1163,10 @@ cudaError_t tree_evaluate(GravityWorkspace& ws, const GravityParams& prm, size_t
                           float easing, float tiny, cudaStream_t st, LaunchStats& ls) {
   const size_t n = ws.n;
   PB_PASS(ws.extent_bits.ensure(16));
+  if (!ws.sticky.p) {
+    PB_PASS(ws.sticky.ensure(16));
+    PB_CUDA(cudaMemsetAsync(ws.sticky.p, 0, 16, st));
+  }
   PB_PASS(ws.key0.ensure(n * 8));
   PB_PASS(ws.key1.ensure(n * 8));
   PB_PASS(ws.idx0.ensure(n * 4));
@@ -1211,7 +1222,7 @@ cudaError_t tree_evaluate(GravityWorkspace& ws, const GravityParams& prm, size_t
   PB_LAUNCH(ls, st, "skip_kernel",
             skip_kernel<DIM><<<blocks_for(cap, 256), 256, 0, st>>>(
                 ws.sorted_key, ws.spos64.as<double4>(), ws.perm, ws.ab.as<uchar2>(),
-                ws.cell_start.as<uint32_t>(), n, max_shared_plus1 + 1, cells));
+                ws.cell_start.as<uint32_t>(), n, max_shared_plus1, ws.sticky.as<unsigned>(), cells));
   PB_LAUNCH(ls, st, "parent_kernel",
             parent_kernel<<<blocks_for(cap, 256), 256, 0, st>>>(ws.cell_start.as<uint32_t>(), n, cells));
   PB_LAUNCH(ls, st, "com_kernel", com_kernel<<<nb128, 128, 0, st>>>(ws.ab.as<uchar2>(), ws.cell_start.as<uint32_t>(), n, cells));
@@ -1287,7 +1298,7 @@ cudaError_t direct_evaluate(GravityWorkspace& ws, size_t t0, size_t t1, float ea
 void GravityWorkspace::release_all() {
   DevBuf* all[] = {&src4, &key0, &key1, &idx0, &idx1, &spos64, &ab, &cell_start, &scan_tmp,
                    &tile_counts, &digit_base, &extent_bits, &tgt_list, &tgt_flags, &c_level, &c_head,
-                   &c_count, &c_skip, &c_parent, &c_arrived, &c_centre_ext, &c_com, &acc, &acc_part,
+                   &c_count, &c_skip, &c_parent, &c_arrived, &c_centre_ext, &c_com, &acc, &acc_part, &sticky,
                    &counters};
   for (DevBuf* b : all) b->release();
 }
@@ -1332,27 +1343,21 @@ cudaError_t gravity_evaluate(GravityWorkspace& ws, const GravityParams& prm, siz
 
 cudaError_t gravity_check(GravityWorkspace& ws, cudaStream_t st, TreeCheck* out) {
   *out = TreeCheck();
-  if (ws.n == 0 || !ws.cell_start.p || ws.tree_dim == 0) return cudaSuccess;
-  struct {
-    uint32_t total;
-    uint32_t deepest_plus1;
-    uint32_t sort_err;
-  } h = {0, 0, 0};
-  PB_CUDA(cudaMemcpyAsync(&h.total, ws.cell_start.as<uint32_t>() + ws.n, 4, cudaMemcpyDeviceToHost, st));
-  PB_CUDA(cudaMemcpyAsync(&h.deepest_plus1, ws.extent_bits.as<unsigned long long>() + 1, 4,
-                          cudaMemcpyDeviceToHost, st));
-  PB_CUDA(cudaMemcpyAsync(&h.sort_err, ws.sort_err_flag, 4, cudaMemcpyDeviceToHost, st));
+  if (ws.n == 0 || !ws.cell_start.p || !ws.sticky.p || ws.tree_dim == 0) return cudaSuccess;
+  uint32_t h[4] = {0, 0, 0, 0};  // {max cells, 1 + max deepest shared level, sort error, -} since the last check
+  PB_CUDA(cudaMemcpyAsync(h, ws.sticky.p, 16, cudaMemcpyDeviceToHost, st));
+  PB_CUDA(cudaMemsetAsync(ws.sticky.p, 0, 16, st));
   PB_CUDA(cudaStreamSynchronize(st));
   const int dim = ws.tree_dim;
   const int key_bits = dim * (dim == 3 ? 21 : 31);
-  out->total = h.total;
-  out->deepest_shared = int(h.deepest_plus1) - 1;
-  out->overflow = h.total > ws.cell_cap;
-  out->sort_error = h.sort_err != 0;
+  out->total = h[0];
+  out->deepest_shared = int(h[1]) - 1;
+  out->overflow = h[0] > ws.cell_cap;
+  out->sort_error = h[2] != 0;
   // a sort of key bits [lo, key_bits) is exact iff no two neighbours with different keys agree on
   // all of those bits, i.e. share fewer than floor((key_bits - lo) / dim) levels
   out->sort_short = ws.last_lo > 0 && out->deepest_shared >= (key_bits - ws.last_lo) / dim;
-  ws.n_cells = h.total;
+  ws.n_cells = h[0];
   if (out->sort_short) {
     ws.sort_lo = 0;
   } else if (!out->sort_error) {

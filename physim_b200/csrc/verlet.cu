@@ -71,7 +71,110 @@ __global__ void __launch_bounds__(256) verlet_kernel(double4* __restrict__ cur, 
   }
 }
 
+// ---- rk4 (integrators/src/rk4.rs:23-183) -----------------------------------------------------
+// One kernel per stage.  k = (dt * v_at, dt * a) is folded into the running sums
+// S = ((k1 + 2 k2) + 2 k3) + k4 in the reference's left-to-right order, and the next evaluation
+// point e + w k (w = 0.5, 0.5, then plain e + k) is written for the next force evaluation.  The
+// last stage writes the new state e + S / 6 instead (fixed bodies: position kept, velocity zero).
+template <int STAGE, bool ACC64>
+__global__ void __launch_bounds__(256) rk4_stage_kernel(const double4* __restrict__ e_pos,
+                                                        const double4* __restrict__ e_vel,
+                                                        const uint8_t* __restrict__ fixed,
+                                                        double4* __restrict__ t_pos, double4* __restrict__ t_vel,
+                                                        double4* __restrict__ s_pos, double4* __restrict__ s_vel,
+                                                        const float4* __restrict__ acc32,
+                                                        const double* __restrict__ acc64, size_t n, double dt,
+                                                        double4* __restrict__ out_pos, double4* __restrict__ out_vel,
+                                                        double2* __restrict__ out6) {
+  const size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const double4 ep = e_pos[i], ev = e_vel[i];
+  const double4 at = STAGE == 1 ? ev : t_vel[i];  // velocity the accelerations were evaluated at
+  const D3 a = load_acc<ACC64>(acc32, acc64, i);
+  const double kx = __dmul_rn(dt, at.x), ky = __dmul_rn(dt, at.y), kz = __dmul_rn(dt, at.z);
+  const double kvx = __dmul_rn(dt, a.x), kvy = __dmul_rn(dt, a.y), kvz = __dmul_rn(dt, a.z);
+  double4 sp, sv;
+  if (STAGE == 1) {
+    sp = make_double4(kx, ky, kz, 0.0);
+    sv = make_double4(kvx, kvy, kvz, 0.0);
+  } else {
+    sp = s_pos[i];
+    sv = s_vel[i];
+    const double w = STAGE == 4 ? 1.0 : 2.0;  // 2.0 * k2, 2.0 * k3, k4
+    if (STAGE == 4) {
+      sp.x = __dadd_rn(sp.x, kx); sp.y = __dadd_rn(sp.y, ky); sp.z = __dadd_rn(sp.z, kz);
+      sv.x = __dadd_rn(sv.x, kvx); sv.y = __dadd_rn(sv.y, kvy); sv.z = __dadd_rn(sv.z, kvz);
+    } else {
+      sp.x = __dadd_rn(sp.x, __dmul_rn(w, kx)); sp.y = __dadd_rn(sp.y, __dmul_rn(w, ky));
+      sp.z = __dadd_rn(sp.z, __dmul_rn(w, kz));
+      sv.x = __dadd_rn(sv.x, __dmul_rn(w, kvx)); sv.y = __dadd_rn(sv.y, __dmul_rn(w, kvy));
+      sv.z = __dadd_rn(sv.z, __dmul_rn(w, kvz));
+    }
+  }
+  if (STAGE < 4) {
+    s_pos[i] = sp;
+    s_vel[i] = sv;
+    double4 tp, tv;
+    if (STAGE == 3) {  // e + k3
+      tp = make_double4(__dadd_rn(ep.x, kx), __dadd_rn(ep.y, ky), __dadd_rn(ep.z, kz), ep.w);
+      tv = make_double4(__dadd_rn(ev.x, kvx), __dadd_rn(ev.y, kvy), __dadd_rn(ev.z, kvz), 0.0);
+    } else {  // e + 0.5 * k
+      tp = make_double4(__dadd_rn(ep.x, __dmul_rn(0.5, kx)), __dadd_rn(ep.y, __dmul_rn(0.5, ky)),
+                        __dadd_rn(ep.z, __dmul_rn(0.5, kz)), ep.w);
+      tv = make_double4(__dadd_rn(ev.x, __dmul_rn(0.5, kvx)), __dadd_rn(ev.y, __dmul_rn(0.5, kvy)),
+                        __dadd_rn(ev.z, __dmul_rn(0.5, kvz)), 0.0);
+    }
+    t_pos[i] = tp;
+    t_vel[i] = tv;
+    if (out6) {  // the generic (host-callback) form needs the evaluation point on the host
+      out6[3 * i] = make_double2(tp.x, tp.y);
+      out6[3 * i + 1] = make_double2(tp.z, tv.x);
+      out6[3 * i + 2] = make_double2(tv.y, tv.z);
+    }
+  } else {
+    double4 np, nv;
+    if (!fixed[i]) {  // rk4.rs:155-162
+      np = make_double4(__dadd_rn(ep.x, __ddiv_rn(sp.x, 6.0)), __dadd_rn(ep.y, __ddiv_rn(sp.y, 6.0)),
+                        __dadd_rn(ep.z, __ddiv_rn(sp.z, 6.0)), ep.w);
+      nv = make_double4(__dadd_rn(ev.x, __ddiv_rn(sv.x, 6.0)), __dadd_rn(ev.y, __ddiv_rn(sv.y, 6.0)),
+                        __dadd_rn(ev.z, __ddiv_rn(sv.z, 6.0)), 0.0);
+    } else {          // rk4.rs:163-170
+      np = ep;
+      nv = make_double4(0.0, 0.0, 0.0, 0.0);
+    }
+    out_pos[i] = np;
+    out_vel[i] = nv;
+    if (out6) {
+      out6[3 * i] = make_double2(np.x, np.y);
+      out6[3 * i + 1] = make_double2(np.z, nv.x);
+      out6[3 * i + 2] = make_double2(nv.y, nv.z);
+    }
+  }
+}
+
 }  // namespace
+
+cudaError_t rk4_stage(int stage, const double4* e_pos, const double4* e_vel, const uint8_t* fixed,
+                      double4* t_pos, double4* t_vel, double4* s_pos, double4* s_vel, const float4* acc32,
+                      const double* acc64, size_t n, double dt, double4* out_pos, double4* out_vel,
+                      double* out6, cudaStream_t st, LaunchStats& ls) {
+  if (n == 0) return cudaSuccess;
+  const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
+  double2* o6 = reinterpret_cast<double2*>(out6);
+#define PB_RK4(S, A)                                                                                      \
+  PB_LAUNCH(ls, st, "rk4_stage_kernel",                                                                   \
+            (rk4_stage_kernel<S, A><<<blocks, 256, 0, st>>>(e_pos, e_vel, fixed, t_pos, t_vel, s_pos, s_vel, \
+                                                            acc32, acc64, n, dt, out_pos, out_vel, o6)))
+  if (acc64) {
+    if (stage == 1) PB_RK4(1, true); else if (stage == 2) PB_RK4(2, true);
+    else if (stage == 3) PB_RK4(3, true); else PB_RK4(4, true);
+  } else {
+    if (stage == 1) PB_RK4(1, false); else if (stage == 2) PB_RK4(2, false);
+    else if (stage == 3) PB_RK4(3, false); else PB_RK4(4, false);
+  }
+#undef PB_RK4
+  return cudaGetLastError();
+}
 
 cudaError_t verlet_update(double4* cur, double4* prev, double4* vel, const float4* acc32,
                           const double* acc64, size_t n, double dt, int first, cudaStream_t st,

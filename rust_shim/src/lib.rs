@@ -1,4 +1,4 @@
-//! `verlet` integrator element backed by libphysim_b200.so.
+//! `verlet`, `euler` and `rk4` integrator elements backed by libphysim_b200.so.
 //!
 //! physim loads integrators through an `extern "Rust"` constructor returning
 //! `Box<dyn IntegratorElement>` (physim-core/src/plugin/mod.rs:92-103), so a C library cannot be an
@@ -17,14 +17,15 @@ use physim_core::{
 };
 use serde_json::Value;
 
-register_plugin!("verlet");
+register_plugin!("verlet", "euler", "rk4");
 
 type AccFn = unsafe extern "C" fn(ctx: *mut c_void, state: *const Entity, n: usize, acc: *mut Acceleration);
 
 unsafe extern "C" {
-    fn pb200_verlet_create() -> *mut c_void;
-    fn pb200_verlet_destroy(v: *mut c_void);
-    fn pb200_verlet_step(
+    // include/physim_b200.h: Pb200Integrator { PB200_VERLET = 0, PB200_EULER = 1, PB200_RK4 = 2 }
+    fn pb200_integrator_create(kind: i32) -> *mut c_void;
+    fn pb200_integrator_destroy(v: *mut c_void);
+    fn pb200_integrator_step(
         v: *mut c_void,
         entities: *const Entity,
         new_state: *mut Entity,
@@ -63,7 +64,7 @@ impl IntegratorElement for Verlet {
     ) {
         let ctx = &acc_fn as *const &dyn Fn(&[Entity], &mut [Acceleration]) as *mut c_void;
         let rc = unsafe {
-            pb200_verlet_step(self.handle, entities.as_ptr(), new_state.as_mut_ptr(), entities.len(), trampoline, ctx, dt)
+            pb200_integrator_step(self.handle, entities.as_ptr(), new_state.as_mut_ptr(), entities.len(), trampoline, ctx, dt)
         };
         if rc != 0 {
             eprintln!("physim_b200 verlet step failed");
@@ -74,7 +75,7 @@ impl IntegratorElement for Verlet {
 
 impl Drop for Verlet {
     fn drop(&mut self) {
-        unsafe { pb200_verlet_destroy(self.handle) }
+        unsafe { pb200_integrator_destroy(self.handle) }
     }
 }
 
@@ -82,7 +83,7 @@ impl MessageClient for Verlet {}
 
 impl ElementCreator for Verlet {
     fn create_element(_: HashMap<String, Value>) -> Box<Self> {
-        Box::new(Self { handle: unsafe { pb200_verlet_create() } })
+        Box::new(Self { handle: unsafe { pb200_integrator_create(0) } })
     }
 }
 
@@ -91,3 +92,51 @@ impl Element for Verlet {
         Ok(HashMap::from([]))
     }
 }
+
+// `euler` (integrators/src/euler.rs) and `rk4` (integrators/src/rk4.rs): same forwarding, other kind.
+macro_rules! forwarded_integrator {
+    ($ty:ident, $name:literal, $blurb:literal, $kind:literal) => {
+        #[integrator_element(name = $name, blurb = $blurb)]
+        struct $ty {
+            handle: *mut c_void,
+        }
+        unsafe impl Send for $ty {}
+        unsafe impl Sync for $ty {}
+        impl IntegratorElement for $ty {
+            fn integrate(
+                &self,
+                entities: &[Entity],
+                new_state: &mut [Entity],
+                acc_fn: &dyn Fn(&[Entity], &mut [Acceleration]),
+                dt: f64,
+            ) {
+                let ctx = &acc_fn as *const &dyn Fn(&[Entity], &mut [Acceleration]) as *mut c_void;
+                let rc = unsafe {
+                    pb200_integrator_step(self.handle, entities.as_ptr(), new_state.as_mut_ptr(), entities.len(), trampoline, ctx, dt)
+                };
+                if rc != 0 {
+                    eprintln!("physim_b200 {} step failed", $name);
+                    std::process::exit(1)
+                }
+            }
+        }
+        impl Drop for $ty {
+            fn drop(&mut self) {
+                unsafe { pb200_integrator_destroy(self.handle) }
+            }
+        }
+        impl MessageClient for $ty {}
+        impl ElementCreator for $ty {
+            fn create_element(_: HashMap<String, Value>) -> Box<Self> {
+                Box::new(Self { handle: unsafe { pb200_integrator_create($kind) } })
+            }
+        }
+        impl Element for $ty {
+            fn get_property_descriptions(&self) -> Result<HashMap<String, String>, Box<dyn std::error::Error>> {
+                Ok(HashMap::from([]))
+            }
+        }
+    };
+}
+forwarded_integrator!(Euler, "euler", "Evaluate evolution with time using Euler integration (B200)", 1);
+forwarded_integrator!(Rk4, "rk4", "Evaluate evolution with time using Rk4 integration (B200)", 2);
