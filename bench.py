@@ -314,6 +314,7 @@ def run_ours(args, w):
         line["e2e"] = measure_e2e(api, state, w, args)
         line["direct_sum"] = measure_direct(api, args, hbm_peak)
         line["cpu_baseline"] = measure_cpu(state, w)
+        line["integrators"] = measure_integrators(api, state, w)
     if world > 1 and not args.skip_extras:
         ds = measure_direct_multi(api, rank, world, local_rank, dist, torch, stream)
         if rank == 0:
@@ -450,6 +451,27 @@ def measure_direct_multi(api, rank, world, local_rank, dist, torch, stream):
             "roofline": {"bound": "fp32", "achieved": tf, "unit": "TFLOP/s", "flop_per_interaction": 19,
                          "peak": nominal, "peak_source": f"{world} x {props.multi_processor_count} SMs x 128 x 2 x 1.965 GHz",
                          "frac": tf / nominal}}
+
+
+def measure_integrators(api, state, w):
+    """the same workload under `euler` and `rk4` (four force evaluations per step),
+    device-resident, next to the CPU oracle's loop (1 thread, bounded number of steps)."""
+    from oracle import binding as ob
+    out = {}
+    n = len(state)
+    for name, gpu_steps, cpu_steps in (("euler", 40, 3), ("rk4", 20, 2)):
+        sim = api.Sim(w["element"], theta=w["theta"], e=w["e"], dt=w["dt"])
+        sim.set_integrator(name)
+        sim.upload(state)
+        sim.run_timed(3)
+        ms = sim.run_timed(gpu_steps)
+        t0 = time.perf_counter()
+        ob.run_pipeline_with(name, w["element"], state, w["theta"], w["e"], w["dt"], cpu_steps)
+        cpu = time.perf_counter() - t0
+        out[name] = {"value": n * gpu_steps / (ms * 1e-3), "unit": "particle-steps/s", "ms_per_step": ms / gpu_steps,
+                     "cpu_baseline": {"value": n * cpu_steps / cpu, "cores": 1, "kind": "port",
+                                      "sample": f"{cpu_steps} full steps"}}
+    return out
 
 
 def measure_cpu(state, w):
