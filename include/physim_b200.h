@@ -154,6 +154,8 @@ typedef struct Pb200Stats {
   double extent;           /* root half-width used */
   float ms_h2d, ms_build, ms_force, ms_integrate, ms_d2h; /* CUDA-event times of the last call */
   float ms_host_pack, ms_host_unpack, ms_wall;             /* host wall-clock parts of the last call */
+  uint32_t replays;        /* chunks of unverified steps that failed verification and were replayed */
+  uint32_t sort_bits;      /* key bits the next sort will cover (tree depth seen + margin) */
 } Pb200Stats;
 
 /* Number of CUDA devices visible; <= 0 means the GPU entry points will fail. No context is made. */

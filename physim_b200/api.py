@@ -56,7 +56,7 @@ class Pb200Stats(C.Structure):
                 ("kernel_launches", C.c_uint64), ("extent", C.c_double), ("ms_h2d", C.c_float),
                 ("ms_build", C.c_float), ("ms_force", C.c_float), ("ms_integrate", C.c_float),
                 ("ms_d2h", C.c_float), ("ms_host_pack", C.c_float), ("ms_host_unpack", C.c_float),
-                ("ms_wall", C.c_float)]
+                ("ms_wall", C.c_float), ("replays", C.c_uint32), ("sort_bits", C.c_uint32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

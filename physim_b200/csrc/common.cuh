@@ -121,6 +121,10 @@ struct GravityWorkspace {
   int tree_dim = 0;     // 2 / 3 after a tree build, 0 otherwise
   int sort_lo = 0;      // lowest key bit the next sort will include (0 = all bits)
   int last_lo = 0;      // ... that the last sort included
+  int sort_extra_levels = 0;  // safety margin, grown whenever a truncated sort proved too short
+  int unchecked_builds = 0;   // tree builds since the last gravity_check()
+  uint32_t last_total = 0;    // verdict of the last gravity_check(), returned again when nothing was built since
+  int last_deepest = -1;
   unsigned* sort_err_flag = nullptr;
   // where the sorted keys / permutation ended up after the last sort
   const uint64_t* sorted_key = nullptr;

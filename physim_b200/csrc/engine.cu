@@ -1168,6 +1168,8 @@ int pb200_sim_stats(void* sim, Pb200Stats* out) {
   }
   s.stats.n_bodies = s.n;
   s.stats.kernel_launches = s.ls.launches;
+  s.stats.replays = static_cast<uint32_t>(s.replays);
+  s.stats.sort_bits = s.ws.tree_dim ? uint32_t(s.ws.tree_dim * (s.ws.tree_dim == 3 ? 21 : 31) - s.ws.sort_lo) : 0u;
   *out = s.stats;
   return 0;
 }

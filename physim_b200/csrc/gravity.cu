@@ -436,7 +436,8 @@ __global__ void __launch_bounds__(256) unit_kernel(const uint64_t* __restrict__ 
                                                    const double4* __restrict__ sp, size_t n,
                                                    uchar2* __restrict__ ab,
                                                    uint32_t* __restrict__ cnt,
-                                                   unsigned* __restrict__ max_shared_plus1) {
+                                                   unsigned* __restrict__ max_shared_plus1,
+                                                   int levels_sorted) {
   constexpr int LM = TreeDim<DIM>::LM;
   const size_t s = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
   unsigned deepest = 0;  // 1 + deepest level shared by two neighbours with DIFFERENT keys
@@ -447,7 +448,12 @@ __global__ void __launch_bounds__(256) unit_kernel(const uint64_t* __restrict__ 
     const bool cn = s + 1 < n && close_1e9(me, sp[s + 1]);
     int a = s > 0 ? shared_levels<DIM>(key[s - 1], kme) : -1;
     int b = s + 1 < n ? shared_levels<DIM>(kme, key[s + 1]) : -1;
-    if (s > 0 && key[s - 1] != kme) deepest = unsigned(a + 1);
+    if (s > 0 && key[s - 1] != kme) {
+      deepest = unsigned(a + 1);
+      // two different keys that agree on every sorted bit: their order is not the full sort's, the
+      // arrays below would describe a broken tree -> every later kernel of this build bails out
+      if (a >= levels_sorted) max_shared_plus1[2] = 1u;
+    }
     bool head = true;
     if (cp || cn) {
       size_t r0 = s, r1 = s;
@@ -504,6 +510,8 @@ struct CellArrays {
   double4* centre_ext;  // {cx, cy, cz, half-width}
   double4* com;         // {X, Y, Z, M}
   uint32_t capacity;
+  uint32_t small;
+  const unsigned* bad;   // != 0: the keys are not fully ordered (truncated sort too short): skip the build        // cells with <= this many bodies are summed directly in K6b
 };
 
 constexpr uint32_t SMALL_CELL = 16;
@@ -544,7 +552,7 @@ __global__ void __launch_bounds__(256) chain_kernel(const uint64_t* __restrict__
   const size_t s = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
   if (s >= n) return;
   const uint32_t total = cell_start[n];
-  if (total > cells.capacity) return;  // host grows the table and re-runs
+  if (total > cells.capacity || *cells.bad) return;  // host grows the table / sorts all bits and re-runs
   const uchar2 abv = ab[s];
   if (abv.x == NOT_HEAD) return;
   const uint32_t c0 = cell_start[s];
@@ -622,7 +630,7 @@ __global__ void __launch_bounds__(256) skip_kernel(const uint64_t* __restrict__ 
     atomicMax(&sticky[0], total);
     atomicMax(&sticky[1], tree_meta[0]);
   }
-  if (total > cells.capacity || c >= total) return;
+  if (total > cells.capacity || *cells.bad || c >= total) return;
   if (c == 0u) cells.parent[0] = NO_PARENT;
   const int lev = cells.level[c];
   const size_t s = cells.head[c];
@@ -671,7 +679,7 @@ __global__ void __launch_bounds__(256) skip_kernel(const uint64_t* __restrict__ 
   const uint32_t cnt = static_cast<uint32_t>(e - s);
   cells.count[c] = cnt;
   cells.skip[c] = skip;
-  if (cnt <= SMALL_CELL) {
+  if (cnt <= cells.small) {
     double sm = 0.0, sx = 0.0, sy = 0.0, sz = 0.0;
     if (tree_meta[1] == 0u) {  // no merged unit anywhere: plain sums over the run
       for (size_t j = s; j < e; ++j) {
@@ -701,7 +709,7 @@ __global__ void __launch_bounds__(256) parent_kernel(const uint32_t* __restrict_
                                                      CellArrays cells) {
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t total = cell_start[n];
-  if (total > cells.capacity || p >= total) return;
+  if (total > cells.capacity || *cells.bad || p >= total) return;
   const uint32_t end = cells.skip[p];
   for (uint32_t ch = p + 1u; ch < end; ch = cells.skip[ch]) cells.parent[ch] = p;
 }
@@ -721,7 +729,7 @@ __device__ __forceinline__ double4 ld_cg_double4(const double4* p) {
 }
 
 __device__ __forceinline__ bool done_in_fill(const CellArrays& cells, uint32_t c) {
-  return cells.count[c] <= SMALL_CELL || cells.skip[c] == c + 1u;
+  return cells.count[c] <= cells.small || cells.skip[c] == c + 1u;
 }
 
 __global__ void __launch_bounds__(128) com_kernel(const uchar2* __restrict__ ab,
@@ -729,7 +737,7 @@ __global__ void __launch_bounds__(128) com_kernel(const uchar2* __restrict__ ab,
                                                   CellArrays cells) {
   const size_t s = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
   if (s >= n) return;
-  if (cell_start[n] > cells.capacity) return;
+  if (cell_start[n] > cells.capacity || *cells.bad) return;
   if (ab[s].x == NOT_HEAD) return;
   // chain of cells headed by s: c0 (shallowest) .. c_last (leaf); body counts shrink with depth
   const uint32_t c0 = cell_start[s], c_last = cell_start[s + 1] - 1;
@@ -845,7 +853,7 @@ __global__ void __launch_bounds__(256) walk_kernel(const double4* __restrict__ s
                                                    size_t n, CellArrays cells, double theta, float easing,
                                                    float tiny, float4* __restrict__ acc) {
   const uint32_t total = cell_start[n];
-  if (total > cells.capacity) return;
+  if (total > cells.capacity || *cells.bad) return;
   const size_t t = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
   bool active = t < n_targets;
   uint32_t s = 0, orig = 0;
@@ -1162,7 +1170,7 @@ template <int DIM>
 cudaError_t tree_evaluate(GravityWorkspace& ws, const GravityParams& prm, size_t t0, size_t t1,
                           float easing, float tiny, cudaStream_t st, LaunchStats& ls) {
   const size_t n = ws.n;
-  PB_PASS(ws.extent_bits.ensure(16));
+  PB_PASS(ws.extent_bits.ensure(32));
   if (!ws.sticky.p) {
     PB_PASS(ws.sticky.ensure(16));
     PB_CUDA(cudaMemsetAsync(ws.sticky.p, 0, 16, st));
@@ -1176,14 +1184,16 @@ cudaError_t tree_evaluate(GravityWorkspace& ws, const GravityParams& prm, size_t
   PB_PASS(ws.cell_start.ensure((n + 1) * 4));
   PB_PASS(ws.tgt_flags.ensure(n * 4));  // also the per-body cell counts before the scan
 
-  // extent_bits: [0] extent (u64 bits)  [1] low word: 1 + deepest level shared by distinct keys
-  PB_CUDA(cudaMemsetAsync(ws.extent_bits.p, 0, 16, st));
+  // extent_bits words: [0,1] extent (u64 bits)  [2] 1 + deepest level shared by distinct keys
+  // [3] some leaf is a merged unit  [4] keys not fully ordered (truncated sort too short)
+  PB_CUDA(cudaMemsetAsync(ws.extent_bits.p, 0, 32, st));
   unsigned* max_shared_plus1 = reinterpret_cast<unsigned*>(ws.extent_bits.as<unsigned long long>() + 1);
   const int key_bits = DIM * TreeDim<DIM>::LM;
   if (ws.tree_dim != DIM) ws.sort_lo = 0;  // depth estimate belongs to the other tree kind
   ws.tree_dim = DIM;
   const int lo = (ws.sort_lo > 0 && ws.sort_lo < key_bits) ? ws.sort_lo : 0;
   ws.last_lo = lo;
+  ws.unchecked_builds += 1;
   const unsigned nb = blocks_for(n, 256);
   PB_LAUNCH(ls, st, "extent_kernel", extent_kernel<<<min(nb, 148u * 8u), 256, 0, st>>>(ws.pos64, n, ws.extent_bits.as<unsigned long long>()));
   SortBuffers sb;
@@ -1195,7 +1205,8 @@ cudaError_t tree_evaluate(GravityWorkspace& ws, const GravityParams& prm, size_t
   PB_PASS(sort_passes(ws, n, sb, st, ls));
   PB_LAUNCH(ls, st, "gather_kernel", gather_kernel<<<nb, 256, 0, st>>>(ws.pos64, ws.perm, n, ws.spos64.as<double4>()));
   PB_LAUNCH(ls, st, "unit_kernel", unit_kernel<DIM><<<nb, 256, 0, st>>>(ws.sorted_key, ws.spos64.as<double4>(), n, ws.ab.as<uchar2>(),
-                                       ws.tgt_flags.as<uint32_t>(), max_shared_plus1));
+                                       ws.tgt_flags.as<uint32_t>(), max_shared_plus1,
+                                       lo > 0 ? (key_bits - lo) / DIM : TreeDim<DIM>::LM + 2));
   PB_PASS(exclusive_scan(ws.tgt_flags.as<uint32_t>(), ws.cell_start.as<uint32_t>(), n, ws.scan_tmp, st, ls));
 
   // cell table capacity: grows when a previous evaluation reported more cells
@@ -1213,7 +1224,8 @@ cudaError_t tree_evaluate(GravityWorkspace& ws, const GravityParams& prm, size_t
   PB_PASS(ws.c_com.ensure(cap * sizeof(double4)));
   CellArrays cells{ws.c_level.as<uint8_t>(),   ws.c_head.as<uint32_t>(),  ws.c_count.as<uint32_t>(),
                    ws.c_skip.as<uint32_t>(),   ws.c_parent.as<uint32_t>(), ws.c_arrived.as<uint32_t>(),
-                   ws.c_centre_ext.as<double4>(), ws.c_com.as<double4>(), static_cast<uint32_t>(cap)};
+                   ws.c_centre_ext.as<double4>(), ws.c_com.as<double4>(), static_cast<uint32_t>(cap), SMALL_CELL,
+                   max_shared_plus1 + 2};
   const unsigned nb128 = blocks_for(n, 128);
   PB_LAUNCH(ls, st, "chain_kernel",
             chain_kernel<DIM><<<nb, 256, 0, st>>>(ws.sorted_key, ws.spos64.as<double4>(), ws.perm,
@@ -1344,6 +1356,12 @@ cudaError_t gravity_evaluate(GravityWorkspace& ws, const GravityParams& prm, siz
 cudaError_t gravity_check(GravityWorkspace& ws, cudaStream_t st, TreeCheck* out) {
   *out = TreeCheck();
   if (ws.n == 0 || !ws.cell_start.p || !ws.sticky.p || ws.tree_dim == 0) return cudaSuccess;
+  if (ws.unchecked_builds == 0) {  // nothing built since the last check: same verdict, no side effects
+    out->total = ws.last_total;
+    out->deepest_shared = ws.last_deepest;
+    return cudaSuccess;
+  }
+  ws.unchecked_builds = 0;
   uint32_t h[4] = {0, 0, 0, 0};  // {max cells, 1 + max deepest shared level, sort error, -} since the last check
   PB_CUDA(cudaMemcpyAsync(h, ws.sticky.p, 16, cudaMemcpyDeviceToHost, st));
   PB_CUDA(cudaMemsetAsync(ws.sticky.p, 0, 16, st));
@@ -1358,11 +1376,15 @@ cudaError_t gravity_check(GravityWorkspace& ws, cudaStream_t st, TreeCheck* out)
   // all of those bits, i.e. share fewer than floor((key_bits - lo) / dim) levels
   out->sort_short = ws.last_lo > 0 && out->deepest_shared >= (key_bits - ws.last_lo) / dim;
   ws.n_cells = h[0];
+  ws.last_total = h[0];
+  ws.last_deepest = out->deepest_shared;
   if (out->sort_short) {
     ws.sort_lo = 0;
+    if (ws.sort_extra_levels < 8) ++ws.sort_extra_levels;
   } else if (!out->sort_error) {
-    // next time sort one level deeper than anything seen now (a deeper pair re-runs the build)
-    const int want_levels = out->deepest_shared + 2;
+    // next time sort two levels deeper than anything seen now (plus one more for every time that
+    // turned out too shallow); a deeper pair re-runs the build
+    const int want_levels = out->deepest_shared + 3 + ws.sort_extra_levels;
     ws.sort_lo = std::max(0, key_bits - dim * want_levels);
   }
   return cudaSuccess;

@@ -108,6 +108,28 @@ def test_device_resident_sim_matches_reference_pipeline(name, theta, e):
         assert np.array_equal(outs[1][k][h:], full[k][h:])
 
 
+@pytest.mark.parametrize("name,theta", [("astro", 1.3), ("astro2", 0.7)])
+def test_unverified_chunks_equal_checked_steps(name, theta):
+    """pb200_sim_run enqueues 32-step chunks whose tree builds are verified only at the chunk's end
+    (cell-table size, truncated-sort depth) and replays a chunk that fails.  Whatever happens, the
+    result must be bit-identical to taking the same steps with a host check after every build."""
+    s = gen.readme_pipeline(30_000, seed=8, spin=1000.0)
+    steps, dt = 100, 2e-5          # long enough for the closest pairs (tree depth) to change
+    a = api.Sim(name, theta=theta, e=0.5, dt=dt)
+    a.upload(s)
+    a.run(steps)
+    out_a = a.download(s.copy())
+    b = api.Sim(name, theta=theta, e=0.5, dt=dt)
+    b.upload(s)
+    for _ in range(steps):
+        b.step_local()             # host-checked every step
+    out_b = b.download(s.copy())
+    for k in POS:
+        assert np.array_equal(out_a[k], out_b[k]), k
+    st = a.stats()
+    assert st["sort_bits"] <= 63 and st["replays"] <= 2
+
+
 def potential(s, e):
     """Conserved potential of the reference's force law: U = -mi mj (pi/2 - atan(r/sqrt(e)))/sqrt(e)."""
     p = np.stack([s["x"], s["y"], s["z"]], 1)
