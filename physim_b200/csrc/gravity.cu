@@ -747,15 +747,17 @@ __global__ void __launch_bounds__(128) com_kernel(const uchar2* __restrict__ ab,
     const uint32_t p = cells.parent[c0];
     if (p == NO_PARENT || done_in_fill(cells, p)) return;  // an ancestor's sum already covers it
   }
+  bool wrote = false;  // com[c] was written by this thread in this kernel (else by K6a/K6b, already visible)
   while (true) {
     const uint32_t p = cells.parent[c];
     if (p == NO_PARENT) break;
     const uint32_t mine = cells.count[c];
-    // release: com[c] is visible (at L2) before the arrival is.  The children are then read with
-    // ld.cg straight from L2, so no acquire fence (which would invalidate this SM's whole L1, as
-    // __threadfence() does) is needed.
+    // release only when there is something of ours to publish: com[c] must be visible (at L2) before
+    // the arrival is.  The children are then read with ld.cg straight from L2, so no acquire fence
+    // (which would invalidate this SM's whole L1, as __threadfence() does) is needed.
     cuda::atomic_ref<uint32_t, cuda::thread_scope_device> arrived(cells.arrived[p]);
-    const uint32_t old = arrived.fetch_add(mine, cuda::std::memory_order_release);
+    const uint32_t old = wrote ? arrived.fetch_add(mine, cuda::std::memory_order_release)
+                               : arrived.fetch_add(mine, cuda::std::memory_order_relaxed);
     if (old + mine != cells.count[p]) break;
     double m = 0.0, sx = 0.0, sy = 0.0, sz = 0.0;
     const uint32_t end = cells.skip[p];
@@ -775,6 +777,7 @@ __global__ void __launch_bounds__(128) com_kernel(const uchar2* __restrict__ ab,
       out = make_double4(g.x, g.y, g.z, 0.0);
     }
     cells.com[p] = out;
+    wrote = true;
     c = p;
   }
 }
@@ -911,13 +914,19 @@ __global__ void __launch_bounds__(256) walk_kernel(const double4* __restrict__ s
 //     (19 flop).  Sources are staged through shared memory and broadcast to the warp; each thread
 //     keeps T targets in registers.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) to_float4_kernel(const double4* __restrict__ pos, size_t n,
-                                                        float4* __restrict__ out) {
+// fp32 SoA copy of the sources, [x | y | z | m] with n_pad floats each (n_pad = n rounded up to a
+// whole tile, padded with massless bodies at the origin), so that a tile is four contiguous 4 KB
+// runs: the unit of the bulk (TMA) copies below
+__global__ void __launch_bounds__(256) to_soa_kernel(const double4* __restrict__ pos, size_t n, size_t n_pad,
+                                                     float* __restrict__ soa) {
   const size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
-  if (i < n) {
-    const double4 p = pos[i];
-    out[i] = make_float4(float(p.x), float(p.y), float(p.z), float(p.w));
-  }
+  if (i >= n_pad) return;
+  double4 p = make_double4(0.0, 0.0, 0.0, 0.0);
+  if (i < n) p = pos[i];
+  soa[i] = float(p.x);
+  soa[n_pad + i] = float(p.y);
+  soa[2 * n_pad + i] = float(p.z);
+  soa[3 * n_pad + i] = float(p.w);
 }
 
 constexpr int DIRECT_THREADS = 256;
@@ -958,39 +967,93 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
   return d;
 }
 
+// ---- bulk asynchronous copies (TMA, cp.async.bulk) completing on an mbarrier ------------------
+__device__ __forceinline__ uint32_t smem_addr(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_addr(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_addr(bar)),
+      "r"(parity)
+      : "memory");
+}
+
 template <int T>
 __global__ void __launch_bounds__(DIRECT_THREADS) direct_kernel_x2(
-    const float4* __restrict__ src, size_t n_src, size_t src_per_split, size_t t0, size_t n_targets,
+    const float* __restrict__ soa, size_t n_pad, size_t src_per_split, size_t t0, size_t n_targets,
     float easing, float tiny, float4* __restrict__ part /* [splits][n_targets] */) {
-  // SoA tile: consecutive sources are adjacent, so an aligned 16-byte read yields two source pairs
-  __shared__ __align__(16) float tx[DIRECT_TILE];
-  __shared__ __align__(16) float ty[DIRECT_TILE];
-  __shared__ __align__(16) float tz[DIRECT_TILE];
-  __shared__ __align__(16) float tm[DIRECT_TILE];
+  // Double-buffered SoA source tiles, filled by one elected thread with four 4 KB bulk copies per
+  // tile (TMA) that complete on an mbarrier while the previous tile is being consumed.  Consecutive
+  // sources are adjacent, so an aligned 16-byte shared read yields two source pairs.
+  __shared__ __align__(128) float tile[2][4][DIRECT_TILE];
+  __shared__ __align__(8) uint64_t full[2];
+  constexpr unsigned kTileBytes = 4u * DIRECT_TILE * sizeof(float);
+  const float* gx = soa;
+  const float* gy = soa + n_pad;
+  const float* gz = soa + 2 * n_pad;
+  const float* gm = soa + 3 * n_pad;
+  if (threadIdx.x == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const size_t sb = size_t(blockIdx.y) * src_per_split;
+  const size_t se = min(sb + src_per_split, n_pad);
+  const unsigned n_tiles = static_cast<unsigned>((se - sb) / DIRECT_TILE);  // whole tiles by construction
+  auto issue = [&](unsigned t) {  // tile t of this split -> buffer t & 1
+    const size_t j0 = sb + size_t(t) * DIRECT_TILE;
+    uint64_t* bar = &full[t & 1u];
+    mbar_expect_tx(bar, kTileBytes);
+    bulk_load(tile[t & 1u][0], gx + j0, DIRECT_TILE * sizeof(float), bar);
+    bulk_load(tile[t & 1u][1], gy + j0, DIRECT_TILE * sizeof(float), bar);
+    bulk_load(tile[t & 1u][2], gz + j0, DIRECT_TILE * sizeof(float), bar);
+    bulk_load(tile[t & 1u][3], gm + j0, DIRECT_TILE * sizeof(float), bar);
+  };
+  if (threadIdx.x == 0 && n_tiles > 0) issue(0);
+
   const size_t tbase = size_t(blockIdx.x) * (DIRECT_THREADS * T);
   f32x2 px[T], py[T], pz[T], ax[T], ay[T], az[T];
 #pragma unroll
   for (int k = 0; k < T; ++k) {
     const size_t lt = tbase + size_t(k) * DIRECT_THREADS + threadIdx.x;
-    const float4 p = lt < n_targets ? src[t0 + lt] : make_float4(0.f, 0.f, 0.f, 0.f);
-    px[k] = pack2(p.x, p.x);
-    py[k] = pack2(p.y, p.y);
-    pz[k] = pack2(p.z, p.z);
+    const size_t g = lt < n_targets ? t0 + lt : 0;
+    const float x = gx[g], y = gy[g], z = gz[g];
+    px[k] = pack2(x, x);
+    py[k] = pack2(y, y);
+    pz[k] = pack2(z, z);
     ax[k] = ay[k] = az[k] = pack2(0.f, 0.f);
   }
   const f32x2 e2 = pack2(easing, easing), tiny2 = pack2(tiny, tiny);
-  const size_t sb = size_t(blockIdx.y) * src_per_split;
-  const size_t se = min(sb + src_per_split, n_src);
-  for (size_t j0 = sb; j0 < se; j0 += DIRECT_TILE) {
-    __syncthreads();
-#pragma unroll
-    for (int q = 0; q < DIRECT_TILE / DIRECT_THREADS; ++q) {
-      const int t = q * DIRECT_THREADS + threadIdx.x;
-      const size_t j = j0 + size_t(t);
-      const float4 sj = j < se ? src[j] : make_float4(0.f, 0.f, 0.f, 0.f);
-      tx[t] = sj.x; ty[t] = sj.y; tz[t] = sj.z; tm[t] = sj.w;
-    }
-    __syncthreads();
+  for (unsigned t = 0; t < n_tiles; ++t) {
+    // buffer (t+1)&1 was consumed in iteration t-1; the barrier at the end of that iteration makes
+    // it safe to refill now, while tile t is computed on
+    if (threadIdx.x == 0 && t + 1 < n_tiles) issue(t + 1);
+    mbar_wait(&full[t & 1u], (t >> 1) & 1u);
+    const float* tx = tile[t & 1u][0];
+    const float* ty = tile[t & 1u][1];
+    const float* tz = tile[t & 1u][2];
+    const float* tm = tile[t & 1u][3];
 #pragma unroll 2
     for (int j = 0; j < DIRECT_TILE; j += 4) {
       const ulonglong2 X = *reinterpret_cast<const ulonglong2*>(&tx[j]);  // (x0,x1) (x2,x3)
@@ -1019,6 +1082,7 @@ __global__ void __launch_bounds__(DIRECT_THREADS) direct_kernel_x2(
         }
       }
     }
+    __syncthreads();  // everyone is done with buffer t&1 before it is refilled
   }
 #pragma unroll
   for (int k = 0; k < T; ++k) {
@@ -1261,8 +1325,10 @@ cudaError_t tree_evaluate(GravityWorkspace& ws, const GravityParams& prm, size_t
 cudaError_t direct_evaluate(GravityWorkspace& ws, size_t t0, size_t t1, float easing, float tiny,
                             cudaStream_t st, LaunchStats& ls) {
   const size_t n = ws.n, n_targets = t1 - t0;
-  PB_PASS(ws.src4.ensure(n * sizeof(float4)));
-  PB_LAUNCH(ls, st, "to_float4_kernel", to_float4_kernel<<<blocks_for(n, 256), 256, 0, st>>>(ws.pos64, n, ws.src4.as<float4>()));
+  const size_t n_pad = (n + DIRECT_TILE - 1) / DIRECT_TILE * DIRECT_TILE;
+  PB_PASS(ws.src4.ensure(4 * n_pad * sizeof(float)));
+  PB_LAUNCH(ls, st, "to_soa_kernel",
+            to_soa_kernel<<<blocks_for(n_pad, 256), 256, 0, st>>>(ws.pos64, n, n_pad, ws.src4.as<float>()));
   if (!n_targets) return cudaGetLastError();
   // 4 targets per thread when that still fills the chip, else 1; split the sources across
   // blockIdx.y until there are >= 2 CTAs per SM (partials summed in a fixed order afterwards)
@@ -1292,7 +1358,7 @@ cudaError_t direct_evaluate(GravityWorkspace& ws, size_t t0, size_t t1, float ea
   const dim3 grid(tb, splits);
 #define PB_DIRECT(TT)                                                                                  \
   PB_LAUNCH(ls, st, "direct_kernel_x2",                                                                \
-            direct_kernel_x2<TT><<<grid, DIRECT_THREADS, 0, st>>>(ws.src4.as<float4>(), n, per, t0,    \
+            direct_kernel_x2<TT><<<grid, DIRECT_THREADS, 0, st>>>(ws.src4.as<float>(), n_pad, per, t0, \
                                                                   n_targets, easing, tiny,             \
                                                                   ws.acc_part.as<float4>()))
   if (T == 4) PB_DIRECT(4);

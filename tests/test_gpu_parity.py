@@ -258,3 +258,36 @@ def test_headline_size_properties():
     ref, cnt = ob.transform("astro", s, 1.3, 1.0, counts=True)
     assert np.array_equal(t["counts"], cnt)
     assert_acc_parity(acc, ref)
+
+
+@pytest.mark.parametrize("name", ["astro2", "astro", "simple_astro"])
+def test_tiny_and_degenerate_states(name):
+    """n = 1, 2, 3; all bodies fixed; one massive + massless mix — the shapes discovery-time and toy
+    pipelines produce (example_pipelines/shm.toml has a single star)."""
+    kw = dict(theta=1.0, e=0.5) if name != "simple_astro" else dict(e=0.5)
+    el = api.TransformElement(name, **kw)
+    one = gen.star(x=0.3, y=0.1, z=0.2, mass=2.0)
+    acc = el.transform(one)
+    assert acc["x"][0] == 0.0 and acc["y"][0] == 0.0 and acc["z"][0] == 0.0   # nothing to attract it
+    pair = np.concatenate([gen.star(x=1.0, y=0.5, mass=1.0), gen.star(x=-1.0, y=-0.25, z=0.1, mass=3.0)])
+    ref = ob.transform(name, pair, kw.get("theta", 1.0), 0.5)
+    assert_acc_parity(el.transform(pair), ref)
+    three = np.concatenate([pair, gen.star(x=0.2, y=-0.9, z=0.5, mass=0.5, fixed=True)])
+    ref = ob.transform(name, three, kw.get("theta", 1.0), 0.5)
+    acc = el.transform(three)
+    assert_acc_parity(acc[:2], ref[:2])
+    assert acc["x"][2] == 0.0                                                  # fixed: untouched
+    frozen = three.copy()
+    frozen["fixed"][:] = True
+    assert not vec(el.transform(frozen)).any()
+    # the fused step and the resident loop on the same tiny states
+    v = api.Verlet()
+    out = v.integrate_fused(pair, el, 0.01)
+    want = ob.Verlet().integrate(pair, lambda st, ac: ob.transform(name, st, kw.get("theta", 1.0), 0.5, acc=ac), 0.01)
+    for k in ("x", "y", "z", "vx", "vy", "vz"):
+        np.testing.assert_allclose(out[k], want[k], rtol=1e-6, atol=1e-12)
+    sim = api.Sim(name, dt=0.01, **kw)
+    sim.upload(one)
+    sim.run(3)
+    got = sim.download(one.copy())
+    assert got["x"][0] == one["x"][0] and got["vx"][0] == 0.0
