@@ -51,7 +51,7 @@ ALG_BYTES_PER_BODY = {
     "gather_kernel": 4 + 32 + 32, "unit_kernel": 8 + 32 + 2 + 4, "scan_lookback_kernel": 8,
     "chain_kernel": 8 + 32 + 2 + 4 + 1.5 * (1 + 4 + 4 + 32) + 32, "skip_kernel": 1.5 * (5 + 8) + 24, "parent_kernel": 1.5 * 8, "com_kernel": 1.5 * (32 + 32 + 12),
     "walk_kernel": 32 + 4 + 1 + 16, "verlet_kernel": 32 + 32 + 16 + 32 + 32 + 32,
-    "to_soa_kernel": 32 + 16,
+    "to_soa_kernel": 32 + 16, "sort_local_kernel": 12 + 12 + 32 + 32,
 }
 FLOP_PER_INTERACTION = 19
 

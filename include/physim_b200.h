@@ -156,6 +156,8 @@ typedef struct Pb200Stats {
   float ms_host_pack, ms_host_unpack, ms_wall;             /* host wall-clock parts of the last call */
   uint32_t replays;        /* chunks of unverified steps that failed verification and were replayed */
   uint32_t sort_bits;      /* key bits the next sort will cover (tree depth seen + margin) */
+  uint32_t sort_mode;      /* form of the last sort: 0 global LSD passes, 1 / 2 one global pass + bucket-local passes in shared memory */
+  uint32_t max_bucket;     /* bodies in the fullest bin of the keys' top 8 bits at the last check */
 } Pb200Stats;
 
 /* Number of CUDA devices visible; <= 0 means the GPU entry points will fail. No context is made. */
@@ -192,6 +194,9 @@ int pb200_transform_debug_tree(void *obj, uint64_t *key, uint32_t *perm, uint32_
  * n_cells_hint cells, so that the next one exercises the validate-and-retry paths (truncated sort
  * too short, cell table too small). */
 int pb200_transform_debug_hint(void *obj, int sort_lo, size_t n_cells_hint);
+/* Test hook: form of the next sort (Pb200Stats.sort_mode); a bucket-local form that meets an
+ * oversized bucket must be detected and the build re-run with the global passes. */
+int pb200_transform_debug_sort_mode(void *obj, int mode);
 
 /* --- verlet (integrators/src/verlet.rs:86-107) -------------------------------------------
  * The Rust shim's IntegratorElement::integrate forwards here.  acc_fn has the meaning of the

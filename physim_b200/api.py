@@ -56,7 +56,8 @@ class Pb200Stats(C.Structure):
                 ("kernel_launches", C.c_uint64), ("extent", C.c_double), ("ms_h2d", C.c_float),
                 ("ms_build", C.c_float), ("ms_force", C.c_float), ("ms_integrate", C.c_float),
                 ("ms_d2h", C.c_float), ("ms_host_pack", C.c_float), ("ms_host_unpack", C.c_float),
-                ("ms_wall", C.c_float), ("replays", C.c_uint32), ("sort_bits", C.c_uint32)]
+                ("ms_wall", C.c_float), ("replays", C.c_uint32), ("sort_bits", C.c_uint32),
+                ("sort_mode", C.c_uint32), ("max_bucket", C.c_uint32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -102,6 +103,7 @@ def lib():
     L.pb200_transform_easing.argtypes = [vp]
     L.pb200_transform_debug_tree.argtypes = [vp] * 12
     L.pb200_transform_debug_hint.argtypes = [vp, i32, sz]
+    L.pb200_transform_debug_sort_mode.argtypes = [vp, i32]
     L.pb200_verlet_create.restype = vp
     L.pb200_verlet_destroy.argtypes = [vp]
     L.pb200_verlet_step.argtypes = [vp, vp, vp, sz, ACC_FN, vp, dbl]
@@ -249,6 +251,9 @@ class TransformElement:
 
     def debug_hint(self, sort_lo, n_cells_hint):
         lib().pb200_transform_debug_hint(self._obj, int(sort_lo), int(n_cells_hint))
+
+    def debug_sort_mode(self, mode):
+        lib().pb200_transform_debug_sort_mode(self._obj, int(mode))
 
     def destroy(self):
         if getattr(self, "_obj", None):

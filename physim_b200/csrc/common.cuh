@@ -122,6 +122,9 @@ struct GravityWorkspace {
   int sort_lo = 0;      // lowest key bit the next sort will include (0 = all bits)
   int last_lo = 0;      // ... that the last sort included
   int sort_extra_levels = 0;  // safety margin, grown whenever a truncated sort proved too short
+  int sort_mode = 0;    // next sort: 0 global LSD passes, 1 / 2 bucket-local (chosen by gravity_check)
+  int last_mode = 0;    // ... that the last sort used
+  uint32_t last_max_bucket = 0;  // fullest top-8-bit bin seen at the last check
   int unchecked_builds = 0;   // tree builds since the last gravity_check()
   uint32_t last_total = 0;    // verdict of the last gravity_check(), returned again when nothing was built since
   int last_deepest = -1;
@@ -235,7 +238,9 @@ struct TreeCheck {
   bool overflow = false;    // total > capacity: the tree kernels bailed out
   bool sort_short = false;  // truncated sort left ties that the dropped bits would have ordered
   bool sort_error = false;  // look-back spin limit hit (never expected)
-  bool ok() const { return !overflow && !sort_short && !sort_error; }
+  uint32_t max_bucket = 0;  // bodies in the fullest bin of the keys' top 8 bits
+  bool bucket_overflow = false;  // a bucket-local sort met a bucket larger than its shared-memory tile
+  bool ok() const { return !overflow && !sort_short && !sort_error && !bucket_overflow; }
 };
 cudaError_t gravity_check(GravityWorkspace& ws, cudaStream_t stream, TreeCheck* out);
 cudaError_t gravity_cell_total(GravityWorkspace& ws, cudaStream_t stream, uint32_t* total);

@@ -826,6 +826,8 @@ int pb200_transform_stats(void* obj, Pb200Stats* out) {
     }
     t.stats.kernel_launches = t.ls.launches;
   }
+  t.stats.sort_mode = uint32_t(t.ws.last_mode);
+  t.stats.max_bucket = t.ws.last_max_bucket;
   *out = t.stats;
   return 0;
 }
@@ -875,6 +877,15 @@ int pb200_transform_debug_hint(void* obj, int sort_lo, size_t n_cells_hint) {
   t.ws.sort_lo = sort_lo;
   t.ws.tree_dim = t.prm.kind == PB200_ASTRO ? 2 : 3;
   t.ws.n_cells = n_cells_hint;
+  return 0;
+}
+
+int pb200_transform_debug_sort_mode(void* obj, int mode) {
+  if (!obj || mode < 0 || mode > 2) return -1;
+  auto& t = *static_cast<TransformObj*>(obj);
+  std::lock_guard<std::mutex> lk(t.mu);
+  t.ws.sort_mode = mode;
+  t.ws.tree_dim = t.prm.kind == PB200_ASTRO ? 2 : 3;
   return 0;
 }
 
@@ -1169,6 +1180,8 @@ int pb200_sim_stats(void* sim, Pb200Stats* out) {
   s.stats.n_bodies = s.n;
   s.stats.kernel_launches = s.ls.launches;
   s.stats.replays = static_cast<uint32_t>(s.replays);
+  s.stats.sort_mode = uint32_t(s.ws.last_mode);
+  s.stats.max_bucket = s.ws.last_max_bucket;
   s.stats.sort_bits = s.ws.tree_dim ? uint32_t(s.ws.tree_dim * (s.ws.tree_dim == 3 ? 21 : 31) - s.ws.sort_lo) : 0u;
   *out = s.stats;
   return 0;

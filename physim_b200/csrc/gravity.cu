@@ -134,6 +134,8 @@ __device__ __forceinline__ double with_sign(double half, bool negative) {
   return __hiloint2double(hi, __double2loint(half));
 }
 
+constexpr int SORT_HIST_SLOTS = 9;  // 8 sort passes at most + the top-8-bit statistics histogram
+
 // Also accumulates the digit histograms of every sort pass (the keys are in registers anyway),
 // warp-aggregated into shared memory, flushed once per block: gridDim.x is kept small.
 template <int DIM>
@@ -141,9 +143,11 @@ __global__ void __launch_bounds__(256) encode_kernel(const double4* __restrict__
                                                      const unsigned long long* __restrict__ extent_bits,
                                                      uint64_t* __restrict__ key,
                                                      uint32_t* __restrict__ idx, SortPlan plan,
-                                                     unsigned* __restrict__ ghist) {
-  __shared__ unsigned h[8 * 256];
-  for (int j = threadIdx.x; j < 8 * 256; j += 256) h[j] = 0;
+                                                     int stat_shift, unsigned* __restrict__ ghist) {
+  // slots 0..npass-1: the digits of the sort passes; slot 8 (stat_shift >= 0): the key's top 8 bits,
+  // whose largest bin decides whether the next sort may use the bucket-local form (sort_local_kernel)
+  __shared__ unsigned h[SORT_HIST_SLOTS * 256];
+  for (int j = threadIdx.x; j < SORT_HIST_SLOTS * 256; j += 256) h[j] = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const double ext0 = __longlong_as_double(static_cast<long long>(*extent_bits));
@@ -175,8 +179,11 @@ __global__ void __launch_bounds__(256) encode_kernel(const double4* __restrict__
       idx[i] = static_cast<uint32_t>(i);
     }
     const unsigned okmask = __ballot_sync(FULL, ok);
-    for (int p = 0; p < plan.npass; ++p) {
-      const unsigned d = unsigned(k >> plan.shift(p)) & plan.mask(p);
+    const int nh = plan.npass + (stat_shift >= 0 ? 1 : 0);
+    for (int q = 0; q < nh; ++q) {
+      const bool stat = q == plan.npass;
+      const int p = stat ? SORT_HIST_SLOTS - 1 : q;
+      const unsigned d = stat ? (unsigned(k >> stat_shift) & 255u) : (unsigned(k >> plan.shift(p)) & plan.mask(p));
       // the high digits are the same for the whole warp: one add; otherwise per-lane adds
       const unsigned d0 = __shfl_sync(FULL, d, 0);
       if (__all_sync(FULL, !ok || d == d0)) {
@@ -187,7 +194,7 @@ __global__ void __launch_bounds__(256) encode_kernel(const double4* __restrict__
     }
   }
   __syncthreads();
-  for (int j = threadIdx.x; j < plan.npass * 256; j += 256)
+  for (int j = threadIdx.x; j < SORT_HIST_SLOTS * 256; j += 256)
     if (h[j]) atomicAdd(&ghist[j], h[j]);
 }
 
@@ -211,7 +218,8 @@ __global__ void __launch_bounds__(SORT_THREADS, SORT_ITEMS >= 16 ? 2 : 4) sort_o
     const uint64_t* __restrict__ kin, const uint32_t* __restrict__ vin, uint64_t* __restrict__ kout,
     uint32_t* __restrict__ vout, size_t n, int shift, unsigned mask,
     const unsigned* __restrict__ ghist /*[256] of this pass*/, unsigned* status /*[tiles][256]*/,
-    unsigned* tile_counter, unsigned* err_flag) {
+    unsigned* tile_counter, unsigned* err_flag, const unsigned* __restrict__ stat_hist /*[256] or null*/,
+    unsigned* stat_max) {
   __shared__ unsigned whist[8][256];
   __shared__ unsigned tstart[256];  // first tile-local slot of each digit
   __shared__ unsigned gadj[256];    // global slot of a digit's first element minus its tile-local slot
@@ -225,6 +233,8 @@ __global__ void __launch_bounds__(SORT_THREADS, SORT_ITEMS >= 16 ? 2 : 4) sort_o
   for (int j = tid; j < 8 * 256; j += SORT_THREADS) (&whist[0][0])[j] = 0;
   const unsigned dbase = block_exclusive_scan_256(ghist[tid], nullptr);  // start of each digit; syncs
   const unsigned tile = tile_s;
+  // largest bin of the top-8-bit histogram, worst case since the last host check (gravity_check)
+  if (stat_hist != nullptr && tile == 0u) atomicMax(stat_max, stat_hist[tid]);
   const size_t tile_base = size_t(tile) * SORT_TILE;
   const size_t base = tile_base + size_t(warp) * 32 * SORT_ITEMS;
   const unsigned nvalid = static_cast<unsigned>(min(size_t(SORT_TILE), n - tile_base));
@@ -323,6 +333,154 @@ __global__ void __launch_bounds__(SORT_THREADS, SORT_ITEMS >= 16 ? 2 : 4) sort_o
     const unsigned dst = gadj[d] + slot;
     kout[dst] = key;
     vout[dst] = vs[slot];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3b  bucket-local sort.  When no bin of the keys' top 8 bits holds more than a shared-memory
+//      tile, ONE onesweep pass on that digit (stable, from index order) leaves 256 contiguous
+//      buckets; CTA b then sorts bucket b by the remaining bits [plan.lo, plan.lo + total) with
+//      LSD passes that never leave shared memory, and writes keys, permutation and the gathered
+//      {x,y,z,m} records once.  Same stable order as the all-global LSD sort, 2 trips through HBM
+//      instead of npass.  An oversized bucket is left alone and flagged (`bad`); the host then
+//      re-runs the build with the global passes (gravity_check).
+// HBM per body: 12 R + 12 W (+ 32 R + 32 W for the fused gather).
+// ---------------------------------------------------------------------------------------------
+template <int NT>
+__device__ __forceinline__ unsigned block_exclusive_scan_nt(unsigned v, unsigned* wsum /*smem[32]*/) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned t = __shfl_up_sync(FULL, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) wsum[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    const unsigned w = lane < NT / 32 ? wsum[lane] : 0u;
+    unsigned wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned t = __shfl_up_sync(FULL, wi, o);
+      if (lane >= o) wi += t;
+    }
+    wsum[lane] = wi - w;  // exclusive per warp
+  }
+  __syncthreads();
+  const unsigned r = wsum[warp] + incl - v;
+  __syncthreads();  // wsum reusable
+  return r;
+}
+
+template <int NT, int ITEMS>
+constexpr size_t sort_local_smem() {
+  return size_t(NT) * ITEMS * 12 + size_t(NT / 32) * 256 * 4 + 256 * 4 + 32 * 4 + 16;
+}
+
+template <int NT, int ITEMS>
+__global__ void __launch_bounds__(NT, (NT * ITEMS * 12 <= 64 * 1024) ? 2 : 1) sort_local_kernel(
+    uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, const unsigned* __restrict__ ghist /*[256]*/,
+    SortPlan plan, const double4* __restrict__ pos, double4* __restrict__ spos, unsigned* __restrict__ bad) {
+  static_assert(NT >= 256 && NT % 32 == 0, "thread = digit in the scans");
+  constexpr int WARPS = NT / 32, CAP = NT * ITEMS;
+  extern __shared__ __align__(16) unsigned char sort_smem[];
+  uint64_t* ks = reinterpret_cast<uint64_t*>(sort_smem);
+  uint32_t* vs = reinterpret_cast<uint32_t*>(ks + CAP);
+  unsigned* whist = vs + CAP;               // [WARPS][256]
+  unsigned* tstart = whist + WARPS * 256;   // [256]
+  unsigned* wsum = tstart + 256;            // [32]
+  unsigned* seg = wsum + 32;                // start, count of this bucket
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  {
+    const unsigned c = tid < 256 ? ghist[tid] : 0u;
+    const unsigned ex = block_exclusive_scan_nt<NT>(c, wsum);
+    if (tid == int(blockIdx.x)) { seg[0] = ex; seg[1] = c; }
+    __syncthreads();
+  }
+  const unsigned start = seg[0], cnt = seg[1];
+  if (cnt == 0u) return;
+  if (cnt > unsigned(CAP)) {
+    if (tid == 0) *bad = 1u;
+    return;
+  }
+  uint64_t k[ITEMS];
+  uint32_t v[ITEMS];
+  const unsigned wbase = unsigned(warp) * 32u * ITEMS;
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    const unsigned p = wbase + unsigned(i) * 32u + lane;
+    const bool ok = p < cnt;
+    k[i] = ok ? keys[size_t(start) + p] : ~0ull;
+    v[i] = ok ? vals[size_t(start) + p] : 0u;
+  }
+  if (plan.npass == 0) {
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+      const unsigned p = wbase + unsigned(i) * 32u + lane;
+      if (p < cnt) { ks[p] = k[i]; vs[p] = v[i]; }
+    }
+    __syncthreads();
+  }
+  for (int pass = 0; pass < plan.npass; ++pass) {
+    const int shift = plan.shift(pass);
+    const unsigned mask = plan.mask(pass);
+    for (int j = tid; j < WARPS * 256; j += NT) whist[j] = 0u;
+    __syncthreads();
+    unsigned rank[ITEMS];
+    unsigned* wh = whist + warp * 256;
+    // stable rank inside the warp's contiguous segment: items in (i, lane) order == array order
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+      const bool ok = (wbase + unsigned(i) * 32u + lane) < cnt;
+      const unsigned d = unsigned((k[i] >> shift) & mask);
+      const unsigned peers = peers_of(d, ok);
+      const unsigned before = ok ? wh[d] : 0u;
+      __syncwarp();
+      const unsigned r = __popc(peers & ((1u << lane) - 1u));
+      if (ok && r == 0u) wh[d] = before + unsigned(__popc(peers));
+      __syncwarp();
+      rank[i] = before + r;
+    }
+    __syncthreads();
+    // thread = digit: bucket-wide count, per-warp exclusive offsets
+    unsigned c = 0;
+    if (tid < 256) {
+#pragma unroll
+      for (int w = 0; w < WARPS; ++w) {
+        const unsigned t = whist[w * 256 + tid];
+        whist[w * 256 + tid] = c;
+        c += t;
+      }
+    }
+    const unsigned ex = block_exclusive_scan_nt<NT>(c, wsum);  // syncs
+    if (tid < 256) tstart[tid] = ex;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+      const bool ok = (wbase + unsigned(i) * 32u + lane) < cnt;
+      if (ok) {
+        const unsigned d = unsigned((k[i] >> shift) & mask);
+        const unsigned slot = tstart[d] + wh[d] + rank[i];
+        ks[slot] = k[i];
+        vs[slot] = v[i];
+      }
+    }
+    __syncthreads();
+    if (pass + 1 < plan.npass) {
+#pragma unroll
+      for (int i = 0; i < ITEMS; ++i) {
+        const unsigned p = wbase + unsigned(i) * 32u + lane;
+        if (p < cnt) { k[i] = ks[p]; v[i] = vs[p]; }
+      }
+      // the next pass writes ks/vs only after two more block barriers
+    }
+  }
+  for (unsigned slot = tid; slot < cnt; slot += NT) {
+    const uint32_t id = vs[slot];
+    keys[size_t(start) + slot] = ks[slot];
+    vals[size_t(start) + slot] = id;
+    spos[size_t(start) + slot] = pos[id];
   }
 }
 
@@ -1166,32 +1324,52 @@ cudaError_t exclusive_scan(const uint32_t* in, uint32_t* out, size_t n, DevBuf& 
 }
 
 struct SortBuffers {
-  SortPlan plan;
+  SortPlan plan;   // global passes (bucket-local mode: the single pass on the top 8 bits)
+  SortPlan local;  // bucket-local mode: the shared-memory passes over the remaining bits
+  int mode;        // 0: global LSD passes, 1: bucket-local (4608-key buckets), 2: bucket-local (8192)
+  int stat_shift;  // >= 0: encode_kernel also builds the top-8-bit histogram (slot 8)
   unsigned tiles;
   int items;
   unsigned *ghist, *counters, *err_flag, *status;
 };
 
+constexpr unsigned LOCAL_CAP_SMALL = 512 * 9, LOCAL_CAP_LARGE = 512 * 16;
+
+inline SortPlan even_plan(int lo, int total) {
+  SortPlan plan;
+  plan.npass = (total + 7) / 8;
+  plan.lo = lo;
+  plan.base = plan.npass ? total / plan.npass : 0;
+  plan.rem = plan.npass ? total % plan.npass : 0;
+  return plan;
+}
+
 // plans the passes over key bits [lo, key_bits) and clears histograms / look-back state
-cudaError_t sort_prepare(GravityWorkspace& ws, size_t n, int key_bits, int lo, cudaStream_t st,
+cudaError_t sort_prepare(GravityWorkspace& ws, size_t n, int key_bits, int lo, int mode, cudaStream_t st,
                          SortBuffers* sb) {
   // keys per thread, measured on B200: 8 wins at 1e5 bodies and from 4e6 up (more CTAs in flight),
   // 16 at 1e6 (one wave of 245 CTAs)
   static const int items_env = std::getenv("PB200_SORT_ITEMS") ? std::atoi(std::getenv("PB200_SORT_ITEMS")) : 0;
   sb->items = items_env ? items_env : ((n <= (size_t(1) << 19) || n >= (size_t(1) << 21)) ? 8 : 16);
   sb->tiles = blocks_for(n, SORT_THREADS * sb->items);
-  SortPlan& plan = sb->plan;
-  const int total = key_bits - lo;
-  plan.npass = (total + 7) / 8;
-  plan.lo = lo;
-  plan.base = total / plan.npass;
-  plan.rem = total % plan.npass;
-  // [ghist: 8 x 256][tile counters: 8][error flag + pad: 8][status: npass x tiles x 256]
-  const size_t head_words = SORT_MAX_PASSES * 256 + SORT_MAX_PASSES + 8;
+  if (key_bits - lo < 8) mode = 0;
+  sb->mode = mode;
+  if (mode == 0) {
+    sb->plan = even_plan(lo, key_bits - lo);
+    sb->local = even_plan(lo, 0);
+    sb->stat_shift = key_bits - 8;
+  } else {
+    sb->plan = even_plan(key_bits - 8, 8);
+    sb->local = even_plan(lo, key_bits - 8 - lo);
+    sb->stat_shift = -1;  // pass 0 is that histogram
+  }
+  const SortPlan& plan = sb->plan;
+  // [ghist: 9 x 256][tile counters: 8][error flag + pad: 8][status: npass x tiles x 256]
+  const size_t head_words = SORT_HIST_SLOTS * 256 + SORT_MAX_PASSES + 8;
   const size_t words = head_words + size_t(plan.npass) * sb->tiles * 256;
   PB_PASS(ws.tile_counts.ensure(words * 4));
   sb->ghist = ws.tile_counts.as<unsigned>();
-  sb->counters = sb->ghist + SORT_MAX_PASSES * 256;
+  sb->counters = sb->ghist + SORT_HIST_SLOTS * 256;
   sb->err_flag = sb->counters + SORT_MAX_PASSES;
   sb->status = sb->ghist + head_words;
   PB_CUDA(cudaMemsetAsync(sb->ghist, 0, words * 4, st));
@@ -1200,8 +1378,10 @@ cudaError_t sort_prepare(GravityWorkspace& ws, size_t n, int key_bits, int lo, c
   return cudaSuccess;
 }
 
-// the passes; returns with ws.sorted_key / ws.perm pointing at the result
-cudaError_t sort_passes(GravityWorkspace& ws, size_t n, const SortBuffers& sb, cudaStream_t st,
+// the passes; returns with ws.sorted_key / ws.perm pointing at the result.  In the bucket-local
+// modes the sorted {x,y,z,m} records (ws.spos64) are written as well; `bad` is the build's
+// "keys not ordered" flag.
+cudaError_t sort_passes(GravityWorkspace& ws, size_t n, const SortBuffers& sb, unsigned* bad, cudaStream_t st,
                         LaunchStats& ls) {
   uint64_t* k[2] = {ws.key0.as<uint64_t>(), ws.key1.as<uint64_t>()};
   uint32_t* v[2] = {ws.idx0.as<uint32_t>(), ws.idx1.as<uint32_t>()};
@@ -1210,20 +1390,47 @@ cudaError_t sort_passes(GravityWorkspace& ws, size_t n, const SortBuffers& sb, c
   if (sb.items == 16)
     PB_CUDA(cudaFuncSetAttribute(sort_onesweep_pass<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  SORT_THREADS * 16 * 12));
+  unsigned* stat_max = ws.sticky.as<unsigned>() + 3;
   int cur = 0;
   for (int p = 0; p < sb.plan.npass; ++p) {
     const size_t smem = size_t(SORT_THREADS) * sb.items * 12;  // digit-sorted tile: u64 keys + u32 values
+    // pass 0 also publishes the largest top-8-bit bin (its own histogram in the bucket-local modes)
+    const unsigned* stat_hist = p != 0 ? nullptr : (sb.mode ? sb.ghist : sb.ghist + (SORT_HIST_SLOTS - 1) * 256);
     if (sb.items == 8)
       PB_LAUNCH(ls, st, "sort_onesweep_pass",
                 sort_onesweep_pass<8><<<sb.tiles, SORT_THREADS, smem, st>>>(
                     k[cur], v[cur], k[cur ^ 1], v[cur ^ 1], n, sb.plan.shift(p), sb.plan.mask(p),
-                    sb.ghist + p * 256, sb.status + size_t(p) * sb.tiles * 256, sb.counters + p, sb.err_flag));
+                    sb.ghist + p * 256, sb.status + size_t(p) * sb.tiles * 256, sb.counters + p, sb.err_flag,
+                    stat_hist, stat_max));
     else
       PB_LAUNCH(ls, st, "sort_onesweep_pass",
                 sort_onesweep_pass<16><<<sb.tiles, SORT_THREADS, smem, st>>>(
                     k[cur], v[cur], k[cur ^ 1], v[cur ^ 1], n, sb.plan.shift(p), sb.plan.mask(p),
-                    sb.ghist + p * 256, sb.status + size_t(p) * sb.tiles * 256, sb.counters + p, sb.err_flag));
+                    sb.ghist + p * 256, sb.status + size_t(p) * sb.tiles * 256, sb.counters + p, sb.err_flag,
+                    stat_hist, stat_max));
     cur ^= 1;
+  }
+  if (sb.mode == 1) {
+    static const int variant = std::getenv("PB200_LOCAL_VARIANT") ? std::atoi(std::getenv("PB200_LOCAL_VARIANT")) : 0;
+    if (variant == 0) {
+      constexpr size_t smem = sort_local_smem<512, 9>();
+      PB_CUDA(cudaFuncSetAttribute(sort_local_kernel<512, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+      PB_LAUNCH(ls, st, "sort_local_kernel",
+                sort_local_kernel<512, 9><<<256, 512, smem, st>>>(k[cur], v[cur], sb.ghist, sb.local, ws.pos64,
+                                                                  ws.spos64.as<double4>(), bad));
+    } else {
+      constexpr size_t smem = sort_local_smem<256, 18>();
+      PB_CUDA(cudaFuncSetAttribute(sort_local_kernel<256, 18>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+      PB_LAUNCH(ls, st, "sort_local_kernel",
+                sort_local_kernel<256, 18><<<256, 256, smem, st>>>(k[cur], v[cur], sb.ghist, sb.local, ws.pos64,
+                                                                   ws.spos64.as<double4>(), bad));
+    }
+  } else if (sb.mode == 2) {
+    constexpr size_t smem = sort_local_smem<512, 16>();
+    PB_CUDA(cudaFuncSetAttribute(sort_local_kernel<512, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    PB_LAUNCH(ls, st, "sort_local_kernel",
+              sort_local_kernel<512, 16><<<256, 512, smem, st>>>(k[cur], v[cur], sb.ghist, sb.local, ws.pos64,
+                                                                 ws.spos64.as<double4>(), bad));
   }
   ws.sorted_key = k[cur];
   ws.perm = v[cur];
@@ -1253,7 +1460,7 @@ cudaError_t tree_evaluate(GravityWorkspace& ws, const GravityParams& prm, size_t
   PB_CUDA(cudaMemsetAsync(ws.extent_bits.p, 0, 32, st));
   unsigned* max_shared_plus1 = reinterpret_cast<unsigned*>(ws.extent_bits.as<unsigned long long>() + 1);
   const int key_bits = DIM * TreeDim<DIM>::LM;
-  if (ws.tree_dim != DIM) ws.sort_lo = 0;  // depth estimate belongs to the other tree kind
+  if (ws.tree_dim != DIM) ws.sort_lo = 0, ws.sort_mode = 0;  // depth / bucket estimates belong to the other tree kind
   ws.tree_dim = DIM;
   const int lo = (ws.sort_lo > 0 && ws.sort_lo < key_bits) ? ws.sort_lo : 0;
   ws.last_lo = lo;
@@ -1261,13 +1468,15 @@ cudaError_t tree_evaluate(GravityWorkspace& ws, const GravityParams& prm, size_t
   const unsigned nb = blocks_for(n, 256);
   PB_LAUNCH(ls, st, "extent_kernel", extent_kernel<<<min(nb, 148u * 8u), 256, 0, st>>>(ws.pos64, n, ws.extent_bits.as<unsigned long long>()));
   SortBuffers sb;
-  PB_PASS(sort_prepare(ws, n, key_bits, lo, st, &sb));
+  PB_PASS(sort_prepare(ws, n, key_bits, lo, ws.sort_mode, st, &sb));
+  ws.last_mode = sb.mode;
   PB_LAUNCH(ls, st, "encode_kernel",
             encode_kernel<DIM><<<min(nb, 148u * 4u), 256, 0, st>>>(
                 ws.pos64, n, ws.extent_bits.as<unsigned long long>(), ws.key0.as<uint64_t>(),
-                ws.idx0.as<uint32_t>(), sb.plan, sb.ghist));
-  PB_PASS(sort_passes(ws, n, sb, st, ls));
-  PB_LAUNCH(ls, st, "gather_kernel", gather_kernel<<<nb, 256, 0, st>>>(ws.pos64, ws.perm, n, ws.spos64.as<double4>()));
+                ws.idx0.as<uint32_t>(), sb.plan, sb.stat_shift, sb.ghist));
+  PB_PASS(sort_passes(ws, n, sb, max_shared_plus1 + 2, st, ls));
+  if (sb.mode == 0)
+    PB_LAUNCH(ls, st, "gather_kernel", gather_kernel<<<nb, 256, 0, st>>>(ws.pos64, ws.perm, n, ws.spos64.as<double4>()));
   PB_LAUNCH(ls, st, "unit_kernel", unit_kernel<DIM><<<nb, 256, 0, st>>>(ws.sorted_key, ws.spos64.as<double4>(), n, ws.ab.as<uchar2>(),
                                        ws.tgt_flags.as<uint32_t>(), max_shared_plus1,
                                        lo > 0 ? (key_bits - lo) / DIM : TreeDim<DIM>::LM + 2));
@@ -1428,7 +1637,7 @@ cudaError_t gravity_check(GravityWorkspace& ws, cudaStream_t st, TreeCheck* out)
     return cudaSuccess;
   }
   ws.unchecked_builds = 0;
-  uint32_t h[4] = {0, 0, 0, 0};  // {max cells, 1 + max deepest shared level, sort error, -} since the last check
+  uint32_t h[4] = {0, 0, 0, 0};  // {max cells, 1 + max deepest shared level, sort error, largest top-8-bit bucket} since the last check
   PB_CUDA(cudaMemcpyAsync(h, ws.sticky.p, 16, cudaMemcpyDeviceToHost, st));
   PB_CUDA(cudaMemsetAsync(ws.sticky.p, 0, 16, st));
   PB_CUDA(cudaStreamSynchronize(st));
@@ -1441,6 +1650,16 @@ cudaError_t gravity_check(GravityWorkspace& ws, cudaStream_t st, TreeCheck* out)
   // a sort of key bits [lo, key_bits) is exact iff no two neighbours with different keys agree on
   // all of those bits, i.e. share fewer than floor((key_bits - lo) / dim) levels
   out->sort_short = ws.last_lo > 0 && out->deepest_shared >= (key_bits - ws.last_lo) / dim;
+  // the bucket-local sort leaves a bucket larger than its shared-memory tile unsorted (and the build
+  // skipped): fall back to the mode the observed largest bucket allows and let the caller re-run
+  out->max_bucket = h[3];
+  ws.last_max_bucket = h[3];
+  out->bucket_overflow = (ws.last_mode == 1 && h[3] > LOCAL_CAP_SMALL) || (ws.last_mode == 2 && h[3] > LOCAL_CAP_LARGE);
+  static const char* mode_env = std::getenv("PB200_SORT_MODE");  // "lsd": global passes only (A/B runs)
+  if (mode_env && !std::strcmp(mode_env, "lsd")) ws.sort_mode = 0;
+  else if (h[3] + h[3] / 32 <= LOCAL_CAP_SMALL) ws.sort_mode = 1;
+  else if (h[3] + h[3] / 32 <= LOCAL_CAP_LARGE) ws.sort_mode = 2;
+  else ws.sort_mode = 0;
   ws.n_cells = h[0];
   ws.last_total = h[0];
   ws.last_deepest = out->deepest_shared;

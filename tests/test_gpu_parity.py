@@ -199,6 +199,53 @@ def test_validate_and_retry_paths(name):
     assert np.array_equal(t["perm"], o.perm) and np.array_equal(t["skip"], o.skip)
 
 
+TREE_KEYS = ("key", "perm", "cell_start", "level", "head", "count", "skip", "parent")
+
+
+@pytest.mark.parametrize("name", ["astro2", "astro"])
+def test_bucket_local_sort_matches_global_sort(name):
+    """From the second evaluation on, a body set whose top-8-bit key bins fit a shared-memory tile is
+    sorted by one global pass + bucket-local passes (Pb200Stats.sort_mode 1 / 2).  Same stable
+    permutation, hence the same bit-exact tree, as the all-global LSD sort and the oracle."""
+    s = np.concatenate([gen.cube(60_000, seed=3), with_merges(5)])
+    o = ob.CellTable(DIM[name], s)
+    ref = ob.transform(name, s, 1.0, 0.5)
+    el = api.TransformElement(name, theta=1.0, e=0.5)
+    el.transform(s)
+    assert el.stats()["sort_mode"] == 0                      # nothing known about the buckets yet
+    for forced in (None, 2, 1):
+        if forced is not None:
+            el.debug_sort_mode(forced)
+        acc = el.transform(s)
+        st = el.stats()
+        assert st["sort_mode"] == (forced or 1), st
+        assert 0 < st["max_bucket"] <= 4608
+        t = el.debug_tree()
+        for k in TREE_KEYS:
+            assert np.array_equal(t[k], getattr(o, k)), (k, forced)
+        assert np.array_equal(t["centre_ext"], o.centre_ext)
+        assert_acc_parity(acc, ref)
+
+
+@pytest.mark.parametrize("name", ["astro2", "astro"])
+def test_bucket_local_sort_overflow_falls_back(name):
+    """A clustered set puts more bodies into one top-8-bit bin than a tile holds: the bucket-local
+    kernel flags it, the build is skipped on the device, and the host re-runs with global passes."""
+    s = plummer_like(30_000, 17)
+    o = ob.CellTable(DIM[name], s)
+    el = api.TransformElement(name, theta=1.0, e=0.05)
+    for forced in (1, 2):
+        el.debug_sort_mode(forced)
+        acc = el.transform(s)
+        st = el.stats()
+        t = el.debug_tree()
+        for k in TREE_KEYS:
+            assert np.array_equal(t[k], getattr(o, k)), (k, forced)
+        assert_acc_parity(acc, ob.transform(name, s, 1.0, 0.05))
+        if st["max_bucket"] > (4608 if forced == 1 else 8192):
+            assert st["sort_mode"] != forced, st             # it did fall back
+
+
 def plummer_like(n, seed):
     """Centrally concentrated 3-D cluster (deep, unbalanced tree), off-centre and large-scale."""
     rng = np.random.default_rng(seed)
@@ -258,6 +305,14 @@ def test_headline_size_properties():
     ref, cnt = ob.transform("astro", s, 1.3, 1.0, counts=True)
     assert np.array_equal(t["counts"], cnt)
     assert_acc_parity(acc, ref)
+    # second evaluation: truncated key + bucket-local sort; same tree bit for bit
+    acc2 = el.transform(s)
+    assert el.stats()["sort_mode"] == 1, el.stats()
+    t2 = el.debug_tree()
+    for k in TREE_KEYS + ("counts",):
+        assert np.array_equal(t[k], t2[k]), k
+    assert np.array_equal(t["com_mass"], t2["com_mass"])
+    assert np.array_equal(vec(acc), vec(acc2))
 
 
 @pytest.mark.parametrize("name", ["astro2", "astro", "simple_astro"])
