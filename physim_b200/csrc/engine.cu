@@ -881,7 +881,7 @@ int pb200_transform_debug_hint(void* obj, int sort_lo, size_t n_cells_hint) {
 }
 
 int pb200_transform_debug_sort_mode(void* obj, int mode) {
-  if (!obj || mode < 0 || mode > 2) return -1;
+  if (!obj || mode < 0 || mode > 3) return -1;
   auto& t = *static_cast<TransformObj*>(obj);
   std::lock_guard<std::mutex> lk(t.mu);
   t.ws.sort_mode = mode;

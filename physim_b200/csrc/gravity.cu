@@ -22,6 +22,7 @@ namespace {
 constexpr unsigned FULL = 0xffffffffu;
 constexpr uint32_t NO_PARENT = 0xffffffffu;
 constexpr int MERGE_RUN_CAP = 1024;  // longer chains of <1e-9 neighbours are left unmerged
+constexpr unsigned char NSV_NONE = 255;  // entry of a body that heads no cell (merged into the unit before it)
 
 template <int DIM>
 struct TreeDim {
@@ -337,14 +338,20 @@ __global__ void __launch_bounds__(SORT_THREADS, SORT_ITEMS >= 16 ? 2 : 4) sort_o
 }
 
 // ---------------------------------------------------------------------------------------------
-// K3b  bucket-local sort.  When no bin of the keys' top 8 bits holds more than a shared-memory
-//      tile, ONE onesweep pass on that digit (stable, from index order) leaves 256 contiguous
-//      buckets; CTA b then sorts bucket b by the remaining bits [plan.lo, plan.lo + total) with
-//      LSD passes that never leave shared memory, and writes keys, permutation and the gathered
-//      {x,y,z,m} records once.  Same stable order as the all-global LSD sort, 2 trips through HBM
-//      instead of npass.  An oversized bucket is left alone and flagged (`bad`); the host then
-//      re-runs the build with the global passes (gravity_check).
-// HBM per body: 12 R + 12 W (+ 32 R + 32 W for the fused gather).
+// K3b  bucket sort (replaces K2 + K3 + K4 when no bin of the keys' top 8 bits holds more bodies than
+//      a shared-memory tile; the host knows from the previous evaluation, gravity_check()).
+//      The stable LSD sort from index order is the same permutation as ANY sort by the pair
+//      (key bits >= lo, original index), so neither step below needs to be stable:
+//      encode_bucket_kernel  computes the keys (as K2) and appends (key, index) to one of 256
+//                            fixed-capacity buckets chosen by the key's top 8 bits (per-CTA counts in
+//                            shared memory, one global atomic per CTA and bucket);
+//      sort_local_kernel     CTA b sorts bucket b in shared memory: counting sort on the next <= 12
+//                            key bits, then every element ranks itself inside its (tiny) bin by
+//                            (key >> lo, index); keys, permutation and the gathered {x,y,z,m} records
+//                            go straight to their final places.
+//      A bucket above capacity or a bin above LOCAL_BIN_LIMIT leaves the build flagged `bad`; the
+//      host re-runs it with the global passes.
+// HBM per body: 32 R + 12 W, then 12 R + 12 W + 32 R + 32 W.
 // ---------------------------------------------------------------------------------------------
 template <int NT>
 __device__ __forceinline__ unsigned block_exclusive_scan_nt(unsigned v, unsigned* wsum /*smem[32]*/) {
@@ -373,114 +380,194 @@ __device__ __forceinline__ unsigned block_exclusive_scan_nt(unsigned v, unsigned
   return r;
 }
 
-template <int NT, int ITEMS>
-constexpr size_t sort_local_smem() {
-  return size_t(NT) * ITEMS * 12 + size_t(NT / 32) * 256 * 4 + 256 * 4 + 32 * 4 + 16;
+constexpr int ENC_ITEMS = 4;           // bodies per thread in encode_bucket_kernel
+constexpr int LOCAL_BIN_BITS = 12;     // counting-sort bins inside a bucket
+constexpr unsigned LOCAL_BIN_LIMIT = 64;  // larger bins would make the in-bin ranking quadratic
+constexpr unsigned LOCAL_SKEWED = 0x7fffffffu;  // published as "largest bucket" when a bin is too full
+
+template <int DIM>
+__global__ void __launch_bounds__(256) encode_bucket_kernel(const double4* __restrict__ pos, size_t n,
+                                                            const unsigned long long* __restrict__ extent_bits,
+                                                            uint64_t* __restrict__ bkey, uint32_t* __restrict__ bidx,
+                                                            unsigned cap, unsigned* __restrict__ cursor /*[256]*/) {
+  constexpr int LM = TreeDim<DIM>::LM;
+  constexpr int TOP_SHIFT = DIM * LM - 8;
+  __shared__ unsigned cnt[256];
+  __shared__ unsigned gbase[256];
+  const int tid = threadIdx.x;
+  cnt[tid] = 0u;
+  __syncthreads();
+  const double ext0 = __longlong_as_double(static_cast<long long>(*extent_bits));
+  const size_t tile = size_t(blockIdx.x) * (256 * ENC_ITEMS);
+  double px[ENC_ITEMS], py[ENC_ITEMS], pz[ENC_ITEMS], cx[ENC_ITEMS], cy[ENC_ITEMS], cz[ENC_ITEMS];
+  uint64_t k[ENC_ITEMS];
+#pragma unroll
+  for (int e = 0; e < ENC_ITEMS; ++e) {
+    const size_t i = tile + size_t(e) * 256 + tid;
+    const double4 p = i < n ? pos[i] : make_double4(0.0, 0.0, 0.0, 0.0);
+    px[e] = p.x; py[e] = p.y; pz[e] = p.z;
+    cx[e] = cy[e] = cz[e] = 0.0;
+    k[e] = 0;
+  }
+  double half = ext0;
+#pragma unroll 1
+  for (int l = 0; l < LM; ++l) {
+    half *= 0.5;  // == extent / 2.0 in IEEE arithmetic
+#pragma unroll
+    for (int e = 0; e < ENC_ITEMS; ++e) {  // independent chains: the compare/add latency overlaps
+      const bool bx = px[e] > cx[e], by = py[e] > cy[e];
+      unsigned digit = unsigned(bx) | (unsigned(by) << 1);
+      cx[e] += with_sign(half, !bx);
+      cy[e] += with_sign(half, !by);
+      if (DIM == 3) {
+        const bool bz = pz[e] > cz[e];
+        digit |= unsigned(bz) << 2;
+        cz[e] += with_sign(half, !bz);
+      }
+      k[e] = (k[e] << DIM) | digit;
+    }
+  }
+  unsigned r[ENC_ITEMS];
+#pragma unroll
+  for (int e = 0; e < ENC_ITEMS; ++e) {
+    const size_t i = tile + size_t(e) * 256 + tid;
+    r[e] = i < n ? atomicAdd(&cnt[unsigned(k[e] >> TOP_SHIFT)], 1u) : 0u;
+  }
+  __syncthreads();
+  {
+    const unsigned c = cnt[tid];
+    if (c) gbase[tid] = atomicAdd(&cursor[tid], c);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int e = 0; e < ENC_ITEMS; ++e) {
+    const size_t i = tile + size_t(e) * 256 + tid;
+    if (i < n) {
+      const unsigned d = unsigned(k[e] >> TOP_SHIFT);
+      const unsigned slot = gbase[d] + r[e];
+      if (slot < cap) {  // else: bucket over capacity, sort_local_kernel flags the build
+        bkey[size_t(d) * cap + slot] = k[e];
+        bidx[size_t(d) * cap + slot] = static_cast<uint32_t>(i);
+      }
+    }
+  }
 }
 
-template <int NT, int ITEMS>
-__global__ void __launch_bounds__(NT, (NT * ITEMS * 12 <= 64 * 1024) ? 2 : 1) sort_local_kernel(
-    uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, const unsigned* __restrict__ ghist /*[256]*/,
-    SortPlan plan, const double4* __restrict__ pos, double4* __restrict__ spos, unsigned* __restrict__ bad) {
-  static_assert(NT >= 256 && NT % 32 == 0, "thread = digit in the scans");
-  constexpr int WARPS = NT / 32, CAP = NT * ITEMS;
+inline size_t sort_local_smem(unsigned cap) {
+  return size_t(cap) * 12 + (size_t(1) << LOCAL_BIN_BITS) * 4 + 32 * 4 + 16;
+}
+
+// The first RITEMS * NT elements of the bucket stay in registers between the counting and the
+// scattering loop; anything beyond is read again (L2 hits).
+template <int NT, int RITEMS>
+__global__ void __launch_bounds__(NT, 1024 / NT) sort_local_kernel(
+    const uint64_t* __restrict__ bkey, const uint32_t* __restrict__ bidx, const unsigned* __restrict__ cursor,
+    unsigned cap, int lo, int key_bits, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
+    const double4* __restrict__ pos, double4* __restrict__ spos, unsigned* __restrict__ bad,
+    unsigned* __restrict__ stat_max) {
+  static_assert(NT >= 256 && NT % 32 == 0 && (1 << LOCAL_BIN_BITS) % NT == 0, "scan layout");
+  constexpr int NBINS = 1 << LOCAL_BIN_BITS, BPT = NBINS / NT;  // bins per thread in the scan
   extern __shared__ __align__(16) unsigned char sort_smem[];
   uint64_t* ks = reinterpret_cast<uint64_t*>(sort_smem);
-  uint32_t* vs = reinterpret_cast<uint32_t*>(ks + CAP);
-  unsigned* whist = vs + CAP;               // [WARPS][256]
-  unsigned* tstart = whist + WARPS * 256;   // [256]
-  unsigned* wsum = tstart + 256;            // [32]
-  unsigned* seg = wsum + 32;                // start, count of this bucket
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t* vs = reinterpret_cast<uint32_t*>(ks + cap);
+  unsigned* bins = vs + cap;     // [NBINS]: counts -> running ends
+  unsigned* wsum = bins + NBINS; // [32]
+  unsigned* seg = wsum + 32;     // start, count of this bucket, largest bin
+  const int tid = threadIdx.x;
   {
-    const unsigned c = tid < 256 ? ghist[tid] : 0u;
+    const unsigned c = tid < 256 ? cursor[tid] : 0u;
     const unsigned ex = block_exclusive_scan_nt<NT>(c, wsum);
     if (tid == int(blockIdx.x)) { seg[0] = ex; seg[1] = c; }
+    if (tid == 0) seg[2] = 0u;
     __syncthreads();
   }
   const unsigned start = seg[0], cnt = seg[1];
   if (cnt == 0u) return;
-  if (cnt > unsigned(CAP)) {
+  if (tid == 0) atomicMax(stat_max, cnt);  // worst case since the last host check (gravity_check)
+  if (cnt > cap) {
     if (tid == 0) *bad = 1u;
     return;
   }
-  uint64_t k[ITEMS];
-  uint32_t v[ITEMS];
-  const unsigned wbase = unsigned(warp) * 32u * ITEMS;
+  // bins: the (up to) LOCAL_BIN_BITS key bits right below the bucket digit, never below `lo`
+  const int below = key_bits - 8 - lo;  // sorted bits left after the bucket digit (>= 0)
+  const int nb = below < LOCAL_BIN_BITS ? below : LOCAL_BIN_BITS;
+  const int bshift = key_bits - 8 - nb;
+  const unsigned bmask = (1u << nb) - 1u;
+  for (int j = tid; j < NBINS; j += NT) bins[j] = 0u;
+  const uint64_t* gk = bkey + size_t(blockIdx.x) * cap;
+  const uint32_t* gv = bidx + size_t(blockIdx.x) * cap;
+  uint64_t k[RITEMS];
+  uint32_t v[RITEMS];
 #pragma unroll
-  for (int i = 0; i < ITEMS; ++i) {
-    const unsigned p = wbase + unsigned(i) * 32u + lane;
+  for (int i = 0; i < RITEMS; ++i) {
+    const unsigned p = unsigned(i) * NT + tid;
     const bool ok = p < cnt;
-    k[i] = ok ? keys[size_t(start) + p] : ~0ull;
-    v[i] = ok ? vals[size_t(start) + p] : 0u;
+    k[i] = ok ? gk[p] : 0ull;
+    v[i] = ok ? gv[p] : 0u;
   }
-  if (plan.npass == 0) {
+  __syncthreads();
 #pragma unroll
-    for (int i = 0; i < ITEMS; ++i) {
-      const unsigned p = wbase + unsigned(i) * 32u + lane;
-      if (p < cnt) { ks[p] = k[i]; vs[p] = v[i]; }
+  for (int i = 0; i < RITEMS; ++i)
+    if (unsigned(i) * NT + tid < cnt) atomicAdd(&bins[unsigned(k[i] >> bshift) & bmask], 1u);
+  for (unsigned p = unsigned(RITEMS) * NT + tid; p < cnt; p += NT)
+    atomicAdd(&bins[unsigned(gk[p] >> bshift) & bmask], 1u);
+  __syncthreads();
+  {  // exclusive scan of the bin counts (BPT consecutive bins per thread) + the largest bin
+    unsigned c[BPT], sum = 0, mx = 0;
+#pragma unroll
+    for (int q = 0; q < BPT; ++q) {
+      c[q] = bins[tid * BPT + q];
+      sum += c[q];
+      mx = max(mx, c[q]);
+    }
+    mx = __reduce_max_sync(FULL, mx);
+    if ((tid & 31) == 0 && mx > LOCAL_BIN_LIMIT) atomicMax(&seg[2], mx);
+    unsigned run = block_exclusive_scan_nt<NT>(sum, wsum);  // syncs
+#pragma unroll
+    for (int q = 0; q < BPT; ++q) {
+      bins[tid * BPT + q] = run;
+      run += c[q];
     }
     __syncthreads();
   }
-  for (int pass = 0; pass < plan.npass; ++pass) {
-    const int shift = plan.shift(pass);
-    const unsigned mask = plan.mask(pass);
-    for (int j = tid; j < WARPS * 256; j += NT) whist[j] = 0u;
-    __syncthreads();
-    unsigned rank[ITEMS];
-    unsigned* wh = whist + warp * 256;
-    // stable rank inside the warp's contiguous segment: items in (i, lane) order == array order
-#pragma unroll
-    for (int i = 0; i < ITEMS; ++i) {
-      const bool ok = (wbase + unsigned(i) * 32u + lane) < cnt;
-      const unsigned d = unsigned((k[i] >> shift) & mask);
-      const unsigned peers = peers_of(d, ok);
-      const unsigned before = ok ? wh[d] : 0u;
-      __syncwarp();
-      const unsigned r = __popc(peers & ((1u << lane) - 1u));
-      if (ok && r == 0u) wh[d] = before + unsigned(__popc(peers));
-      __syncwarp();
-      rank[i] = before + r;
+  if (seg[2] > LOCAL_BIN_LIMIT) {  // too many bodies agree on the bin bits: leave it to the global sort
+    if (tid == 0) {
+      *bad = 1u;
+      atomicMax(stat_max, LOCAL_SKEWED);
     }
-    __syncthreads();
-    // thread = digit: bucket-wide count, per-warp exclusive offsets
-    unsigned c = 0;
-    if (tid < 256) {
+    return;
+  }
 #pragma unroll
-      for (int w = 0; w < WARPS; ++w) {
-        const unsigned t = whist[w * 256 + tid];
-        whist[w * 256 + tid] = c;
-        c += t;
-      }
-    }
-    const unsigned ex = block_exclusive_scan_nt<NT>(c, wsum);  // syncs
-    if (tid < 256) tstart[tid] = ex;
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < ITEMS; ++i) {
-      const bool ok = (wbase + unsigned(i) * 32u + lane) < cnt;
-      if (ok) {
-        const unsigned d = unsigned((k[i] >> shift) & mask);
-        const unsigned slot = tstart[d] + wh[d] + rank[i];
-        ks[slot] = k[i];
-        vs[slot] = v[i];
-      }
-    }
-    __syncthreads();
-    if (pass + 1 < plan.npass) {
-#pragma unroll
-      for (int i = 0; i < ITEMS; ++i) {
-        const unsigned p = wbase + unsigned(i) * 32u + lane;
-        if (p < cnt) { k[i] = ks[p]; v[i] = vs[p]; }
-      }
-      // the next pass writes ks/vs only after two more block barriers
+  for (int i = 0; i < RITEMS; ++i) {
+    if (unsigned(i) * NT + tid < cnt) {
+      const unsigned slot = atomicAdd(&bins[unsigned(k[i] >> bshift) & bmask], 1u);
+      ks[slot] = k[i];
+      vs[slot] = v[i];
     }
   }
-  for (unsigned slot = tid; slot < cnt; slot += NT) {
-    const uint32_t id = vs[slot];
-    keys[size_t(start) + slot] = ks[slot];
-    vals[size_t(start) + slot] = id;
-    spos[size_t(start) + slot] = pos[id];
+  for (unsigned p = unsigned(RITEMS) * NT + tid; p < cnt; p += NT) {
+    const uint64_t key = gk[p];
+    const unsigned slot = atomicAdd(&bins[unsigned(key >> bshift) & bmask], 1u);
+    ks[slot] = key;
+    vs[slot] = gv[p];
+  }
+  __syncthreads();
+  // bins[b] is now the end of bin b (and the start of bin b+1)
+  for (unsigned p = tid; p < cnt; p += NT) {
+    const uint64_t key = ks[p];
+    const uint32_t id = vs[p];
+    const unsigned bin = unsigned(key >> bshift) & bmask;
+    const unsigned s = bin ? bins[bin - 1u] : 0u, e = bins[bin];
+    const uint64_t kme = key >> lo;
+    unsigned rank = 0;
+    for (unsigned q = s; q < e; ++q) {
+      const uint64_t kq = ks[q] >> lo;
+      rank += (kq < kme || (kq == kme && vs[q] < id)) ? 1u : 0u;
+    }
+    const size_t dst = size_t(start) + s + rank;
+    keys[dst] = key;
+    vals[dst] = id;
+    spos[dst] = pos[id];
   }
 }
 
@@ -595,10 +682,12 @@ __global__ void __launch_bounds__(256) unit_kernel(const uint64_t* __restrict__ 
                                                    uchar2* __restrict__ ab,
                                                    uint32_t* __restrict__ cnt,
                                                    unsigned* __restrict__ max_shared_plus1,
-                                                   int levels_sorted) {
+                                                   int levels_sorted, uint8_t* __restrict__ nsv1,
+                                                   size_t n_pad, uint8_t* __restrict__ nsv2) {
   constexpr int LM = TreeDim<DIM>::LM;
   const size_t s = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
   unsigned deepest = 0;  // 1 + deepest level shared by two neighbours with DIFFERENT keys
+  unsigned char a1 = NSV_NONE;  // 1 + levels shared with the previous unit (heads only)
   if (s < n) {
     const double4 me = sp[s];
     const uint64_t kme = key[s];
@@ -643,6 +732,27 @@ __global__ void __launch_bounds__(256) unit_kernel(const uint64_t* __restrict__ 
                  : make_uchar2(255, 255);  // NOT_HEAD: merged into the unit before it
     if (!head) max_shared_plus1[1] = 1u;  // "some leaf is a merged unit" (rare): slow summation paths
     cnt[s] = head ? unsigned(max(0, b - a) + 1) : 0u;
+    if (head) a1 = static_cast<unsigned char>(a + 1);
+  }
+  // range-minimum table of a1 over this block of 256 sorted bodies (nsv_next_le); level k at
+  // nsv1[k * n_pad + s] = min a1[s .. s + 2^k), valid while the range stays inside the block
+  {
+    __shared__ unsigned char tab[2][256 + 128];
+    const int t = threadIdx.x;
+    tab[0][t] = a1;
+    if (t < 128) tab[0][256 + t] = tab[1][256 + t] = NSV_NONE;
+    nsv1[s] = a1;
+    __syncthreads();
+    int cur = 0;
+#pragma unroll
+    for (int k = 1; k <= 8; ++k) {
+      const unsigned char m = min(tab[cur][t], tab[cur][t + (1 << (k - 1))]);
+      tab[cur ^ 1][t] = m;
+      nsv1[size_t(k) * n_pad + s] = m;
+      cur ^= 1;
+      __syncthreads();
+    }
+    if (t == 0) nsv2[blockIdx.x] = tab[cur][0];
   }
   // sizes the next sort and validates this one (a truncated sort is exact iff no two neighbours
   // with different keys agree on every sorted bit)
@@ -695,29 +805,111 @@ __device__ __forceinline__ double4 unit_leaf(const double4* __restrict__ sp,
   return q;
 }
 
-// K6a  one thread per unit head: the chain of cells it heads (levels a+1 .. leaf level) gets its
-//      level, head, geometric centre / half-width (replaying the head's key digits), in-chain
-//      parent links, and the leaf its body data.
+// Range-minimum tables for "first body j >= j0 that starts a cell at level <= l", i.e. the end of a
+// cell's run of bodies (in DFS pre-order the first later cell that is not deeper is the next
+// non-descendant, and cell_start[] of the body that heads it is its index):
+//   nsv1[k][j]  min a1[j .. j+2^k) inside blocks of 256 bodies (unit_kernel), k = 0..8
+//   nsv2[k][b]  the same over the block minima inside super-blocks of 256 blocks, k = 0..8
+//   nsv3[q]     super-block minima (scanned linearly: n / 65536 entries)
+// A query is a fixed sequence of <= 9 dependent byte loads per level of the hierarchy, the same for
+// every lane of a warp: no data-dependent scan lengths.
+struct NsvTables {
+  const uint8_t* t1;
+  size_t n_pad;   // stride of a level of t1
+  const uint8_t* t2;
+  size_t b_pad;   // stride of a level of t2
+  const uint8_t* t3;
+  size_t n, nblocks, nsuper;
+};
+
+__global__ void __launch_bounds__(256) nsv_level2_kernel(uint8_t* __restrict__ t2, size_t b_pad, size_t nblocks,
+                                                         uint8_t* __restrict__ t3) {
+  __shared__ unsigned char tab[2][256 + 128];
+  const int t = threadIdx.x;
+  const size_t b = size_t(blockIdx.x) * 256 + t;
+  tab[0][t] = b < nblocks ? t2[b] : NSV_NONE;
+  if (t < 128) tab[0][256 + t] = tab[1][256 + t] = NSV_NONE;
+  __syncthreads();
+  int cur = 0;
+#pragma unroll
+  for (int k = 1; k <= 8; ++k) {
+    const unsigned char m = min(tab[cur][t], tab[cur][t + (1 << (k - 1))]);
+    tab[cur ^ 1][t] = m;
+    if (b < b_pad) t2[size_t(k) * b_pad + b] = m;
+    cur ^= 1;
+    __syncthreads();
+  }
+  if (t == 0) t3[blockIdx.x] = tab[cur][0];
+}
+
+// first index in [j, end) (end - j <= 256, same 256-aligned block) whose entry is <= l, else end
+__device__ __forceinline__ size_t nsv_descend(const uint8_t* __restrict__ tab, size_t stride, size_t j, size_t end,
+                                              unsigned l) {
+#pragma unroll
+  for (int k = 8; k >= 0; --k) {
+    const size_t step = size_t(1) << k;
+    if (j + step <= end && tab[size_t(k) * stride + j] > l) j += step;
+  }
+  return j;
+}
+
+__device__ __forceinline__ size_t nsv_next_le(const NsvTables& tv, size_t j0, unsigned l) {
+  if (j0 >= tv.n) return tv.n;
+  const size_t blk_end = min(tv.n, (j0 | 255) + 1);
+  const size_t j = nsv_descend(tv.t1, tv.n_pad, j0, blk_end, l);
+  if (j < blk_end) return j;
+  if (blk_end == tv.n) return tv.n;  // (the last block may be partial: blk_end >> 8 would name it again)
+  size_t b = blk_end >> 8;  // first block not yet examined
+  if (b >= tv.nblocks) return tv.n;
+  size_t sb_end = min(tv.nblocks, (b | 255) + 1);
+  b = nsv_descend(tv.t2, tv.b_pad, b, sb_end, l);
+  if (b == sb_end) {  // not in the rest of this super-block: whole super-blocks, then inside the one that has it
+    if (sb_end == tv.nblocks) return tv.n;
+    size_t q = sb_end >> 8;
+    while (q < tv.nsuper && tv.t3[q] > l) ++q;
+    if (q >= tv.nsuper) return tv.n;
+    b = q << 8;
+    sb_end = min(tv.nblocks, b + 256);
+    b = nsv_descend(tv.t2, tv.b_pad, b, sb_end, l);
+    if (b == sb_end) return tv.n;  // (not reached: t3[q] <= l)
+  }
+  const size_t lo = b << 8;  // block b holds the answer
+  return nsv_descend(tv.t1, tv.n_pad, lo, min(tv.n, lo + 256), l);
+}
+
+// K6  one thread per unit head s, for the chain of cells it heads (levels a+1 .. leaf level):
+//     pass 1, top -> leaf: level, head, geometric centre / half-width (replaying the head's key digits);
+//     pass 2, leaf -> top: the end of each cell's run of bodies (nsv_next_le, continuing from the end
+//     of the cell below), hence body count and skip link, and - while the cell holds <= SMALL_CELL
+//     bodies - mass / centre of mass as ONE running sum over the bodies in order, emitted at every
+//     level (each body is read once per chain, and the sums equal a per-cell sum in body order).
+//     Larger cells are left to the bottom-up pass (K7).
 template <int DIM>
-__global__ void __launch_bounds__(256) chain_kernel(const uint64_t* __restrict__ key,
+__global__ void __launch_bounds__(256) cells_kernel(const uint64_t* __restrict__ key,
                                                     const double4* __restrict__ sp,
                                                     const uint32_t* __restrict__ perm,
                                                     const uchar2* __restrict__ ab,
                                                     const uint32_t* __restrict__ cell_start, size_t n,
                                                     const unsigned long long* __restrict__ extent_bits,
-                                                    CellArrays cells) {
+                                                    const unsigned* __restrict__ tree_meta,
+                                                    unsigned* __restrict__ sticky, NsvTables tv, CellArrays cells) {
   constexpr int LM = TreeDim<DIM>::LM;
   const size_t s = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
-  if (s >= n) return;
   const uint32_t total = cell_start[n];
+  if (s == 0) {
+    // worst case over every build since the last host check (builds run unverified in between):
+    // [0] cells needed, [1] 1 + deepest level shared by distinct neighbouring keys
+    atomicMax(&sticky[0], total);
+    atomicMax(&sticky[1], tree_meta[0]);
+  }
+  if (s >= n) return;
   if (total > cells.capacity || *cells.bad) return;  // host grows the table / sorts all bits and re-runs
   const uchar2 abv = ab[s];
   if (abv.x == NOT_HEAD) return;
   const uint32_t c0 = cell_start[s];
+  if (s == 0) cells.parent[0] = NO_PARENT;
   const int a = int(abv.x) - 1, b = int(abv.y) - 1;
   const int top = a + 1, leaf_level = max(a, b) + 1;
-  size_t e_unit = s + 1;
-  while (e_unit < n && ab[e_unit].x == NOT_HEAD) ++e_unit;
   const uint64_t kme = key[s];
   const double4 me = sp[s];
 
@@ -737,127 +929,62 @@ __global__ void __launch_bounds__(256) chain_kernel(const uint64_t* __restrict__
     if (DIM == 3) cz += with_sign(half, !(digit & 4u));
   };
   for (int l = 0; l < top; ++l) descend(l);
-
   for (int lev = top; lev <= leaf_level; ++lev) {
     const uint32_t c = c0 + uint32_t(lev - top);
     cells.level[c] = static_cast<uint8_t>(lev);
     cells.head[c] = static_cast<uint32_t>(s);
     cells.arrived[c] = 0u;
     cells.centre_ext[c] = make_double4(cx, cy, cz, half);
-    if (lev == leaf_level) {
-      cells.count[c] = static_cast<uint32_t>(e_unit - s);
-      cells.skip[c] = cell_start[e_unit];
-      cells.com[c] = unit_leaf(sp, perm, s, e_unit);
-    } else {
-      descend(lev);
-    }
+    if (lev < leaf_level) descend(lev);
   }
-}
 
-// K6b  one thread per cell.  In DFS pre-order the first later cell that is not deeper is the next
-//      non-descendant, so the skip link comes from a forward scan over the level bytes (8 cells
-//      per 64-bit load); subtrees of more than TOPO_SCAN cells fall back to a galloping search on
-//      the sorted keys.  The body count follows from the heads, and cells with <= SMALL_CELL bodies
-//      get their mass / centre of mass by summing their units in order.
-constexpr uint32_t TOPO_SCAN = 512;
-
-// index (0..7) of the first byte >= `from` of the little-endian word w that is <= lev, or 8
-__device__ __forceinline__ int first_byte_le(unsigned long long w, int lev, int from) {
-  const unsigned long long ones = 0x0101010101010101ull, highs = 0x8080808080808080ull;
-  // per byte: (b | 0x80) - (lev + 1) keeps its high bit iff b > lev (levels are < 64)
-  const unsigned long long t = (w | highs) - ones * static_cast<unsigned long long>(lev + 1);
-  unsigned long long m = ~t & highs;
-  if (from > 0) m &= ~0ull << (8 * from);
-  return m ? (__ffsll(static_cast<long long>(m)) - 1) >> 3 : 8;
-}
-
-template <int DIM>
-__global__ void __launch_bounds__(256) skip_kernel(const uint64_t* __restrict__ key,
-                                                   const double4* __restrict__ sp,
-                                                   const uint32_t* __restrict__ perm,
-                                                   const uchar2* __restrict__ ab,
-                                                   const uint32_t* __restrict__ cell_start, size_t n,
-                                                   const unsigned* __restrict__ tree_meta,
-                                                   unsigned* __restrict__ sticky, CellArrays cells) {
-  constexpr int LM = TreeDim<DIM>::LM;
-  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t total = cell_start[n];
-  if (c == 0u) {
-    // worst case over every build since the last host check (builds run unverified in between):
-    // [0] cells needed, [1] 1 + deepest level shared by distinct neighbouring keys
-    atomicMax(&sticky[0], total);
-    atomicMax(&sticky[1], tree_meta[0]);
-  }
-  if (total > cells.capacity || *cells.bad || c >= total) return;
-  if (c == 0u) cells.parent[0] = NO_PARENT;
-  const int lev = cells.level[c];
-  const size_t s = cells.head[c];
-
-  uint32_t skip = total;
-  size_t e = n;  // first sorted body past this cell's run
+  // leaf: the unit itself
+  size_t e = s + 1;
+  while (e < n && ab[e].x == NOT_HEAD) ++e;
+  const double4 leaf = unit_leaf(sp, perm, s, e);
   {
-    const unsigned long long* words = reinterpret_cast<const unsigned long long*>(cells.level);
-    const uint32_t lim = min(total, c + 1u + TOPO_SCAN);
-    uint32_t i = c + 1u;  // next cell to examine
-    uint32_t hit = lim;
-    while (i < lim) {
-      const uint32_t wi = i >> 3;
-      const int k = first_byte_le(words[wi], lev, int(i & 7u));
-      if (k < 8) {
-        hit = min(lim, (wi << 3) + uint32_t(k));
-        break;
-      }
-      i = (wi + 1u) << 3;
-    }
-    if (hit < lim) {
-      skip = hit;
-      e = cells.head[hit];
-    } else if (lim < total) {
-      // big subtree: cells c+1 .. lim-1 are descendants, so head[lim-1] lies inside the run; gallop
-      // on the keys from there (lev <= LM: a cell with descendants is not at the pseudo level)
-      const int shift = DIM * (LM - lev);
-      const uint64_t pre = shift >= 64 ? 0ull : (key[s] >> shift);
-      auto shares = [&](size_t j) { return shift >= 64 ? true : ((key[j] >> shift) == pre); };
-      size_t lo = cells.head[lim - 1u], step = 1, bad = n;
-      while (true) {
-        const size_t probe = lo + step;
-        if (probe >= n) break;
-        if (shares(probe)) { lo = probe; step <<= 1; } else { bad = probe; break; }
-      }
-      size_t l2 = lo, h2 = bad;
-      while (h2 - l2 > 1) {
-        const size_t mid = l2 + (h2 - l2) / 2;
-        if (shares(mid)) l2 = mid; else h2 = mid;
-      }
-      e = h2;
-      skip = cell_start[e];
-    }
+    const uint32_t c = c0 + uint32_t(leaf_level - top);
+    cells.count[c] = static_cast<uint32_t>(e - s);
+    cells.skip[c] = cell_start[e];
+    cells.com[c] = leaf;
   }
-  if (skip == c + 1u) return;  // leaf: count, skip and body data were written by K6a
-  const uint32_t cnt = static_cast<uint32_t>(e - s);
-  cells.count[c] = cnt;
-  cells.skip[c] = skip;
-  if (cnt <= cells.small) {
-    double sm = 0.0, sx = 0.0, sy = 0.0, sz = 0.0;
-    if (tree_meta[1] == 0u) {  // no merged unit anywhere: plain sums over the run
-      for (size_t j = s; j < e; ++j) {
-        const double4 q = sp[j];
-        sm += q.w; sx += q.w * q.x; sy += q.w * q.y; sz += q.w * q.z;
+  double sm = leaf.w, sx = leaf.w * leaf.x, sy = leaf.w * leaf.y, sz = leaf.w * leaf.z;
+  // the per-cell sums start from zero: 0 + m x == m x exactly, so carrying the leaf's products is the same
+  const bool merged_units = tree_meta[1] != 0u;
+  bool summing = true;
+  for (int lev = leaf_level - 1; lev >= top; --lev) {
+    const uint32_t c = c0 + uint32_t(lev - top);
+    const size_t e_prev = e;
+    e = nsv_next_le(tv, e_prev, unsigned(lev));
+    const uint32_t cnt = static_cast<uint32_t>(e - s);
+    cells.count[c] = cnt;
+    cells.skip[c] = cell_start[e];
+    if (summing && cnt <= cells.small) {
+      if (!merged_units) {  // no merged unit anywhere: plain sums over the run
+        for (size_t j = e_prev; j < e; ++j) {
+          const double4 q = sp[j];
+          sm += q.w; sx += q.w * q.x; sy += q.w * q.y; sz += q.w * q.z;
+        }
+      } else {
+        for (size_t j = e_prev; j < e;) {  // units in order
+          size_t je = j + 1;
+          while (je < e && ab[je].x == NOT_HEAD) ++je;
+          const double4 q = unit_leaf(sp, perm, j, je);
+          sm += q.w; sx += q.w * q.x; sy += q.w * q.y; sz += q.w * q.z;
+          j = je;
+        }
+      }
+      // a massless cell (the reference panics there): geometric centre instead of 0/0
+      const double inv = 1.0 / sm;  // one division: the reference's own (…) * inv_total_mass form (lib.rs:43-49)
+      if (sm != 0.0) {
+        cells.com[c] = make_double4(sx * inv, sy * inv, sz * inv, sm);
+      } else {
+        const double4 g = cells.centre_ext[c];
+        cells.com[c] = make_double4(g.x, g.y, g.z, 0.0);
       }
     } else {
-      for (size_t j = s; j < e;) {  // units in order
-        size_t je = j + 1;
-        while (je < e && ab[je].x == NOT_HEAD) ++je;
-        const double4 q = unit_leaf(sp, perm, j, je);
-        sm += q.w; sx += q.w * q.x; sy += q.w * q.y; sz += q.w * q.z;
-        j = je;
-      }
+      summing = false;
     }
-    // a massless cell (the reference panics there): geometric centre instead of 0/0
-    const double4 g = cells.centre_ext[c];
-    const double inv = 1.0 / sm;  // one division: the reference's own (…) * inv_total_mass form (lib.rs:43-49)
-    cells.com[c] = sm != 0.0 ? make_double4(sx * inv, sy * inv, sz * inv, sm)
-                             : make_double4(g.x, g.y, g.z, 0.0);
   }
 }
 
@@ -869,7 +996,12 @@ __global__ void __launch_bounds__(256) parent_kernel(const uint32_t* __restrict_
   const uint32_t total = cell_start[n];
   if (total > cells.capacity || *cells.bad || p >= total) return;
   const uint32_t end = cells.skip[p];
-  for (uint32_t ch = p + 1u; ch < end; ch = cells.skip[ch]) cells.parent[ch] = p;
+  for (uint32_t ch = p + 1u; ch < end;) {
+    cells.parent[ch] = p;
+    const uint32_t next = cells.skip[ch];
+    if (next <= ch) break;  // (never in a well-formed table; keeps a broken one from hanging the GPU)
+    ch = next;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -919,12 +1051,15 @@ __global__ void __launch_bounds__(128) com_kernel(const uchar2* __restrict__ ab,
     if (old + mine != cells.count[p]) break;
     double m = 0.0, sx = 0.0, sy = 0.0, sz = 0.0;
     const uint32_t end = cells.skip[p];
-    for (uint32_t ch = p + 1; ch < end; ch = cells.skip[ch]) {
+    for (uint32_t ch = p + 1; ch < end;) {
       const double4 q = ld_cg_double4(&cells.com[ch]);
       m += q.w;
       sx += q.w * q.x;
       sy += q.w * q.y;
       sz += q.w * q.z;
+      const uint32_t next = cells.skip[ch];
+      if (next <= ch) break;  // (never in a well-formed table)
+      ch = next;
     }
     double4 out;
     if (m != 0.0) {
@@ -1053,7 +1188,7 @@ __global__ void __launch_bounds__(256) walk_kernel(const double4* __restrict__ s
         fy = fmaf(mw, dy, fy);
         fz = fmaf(mw, dz, fz);
         ++inter;
-        c = sk;
+        c = max(sk, c + 1u);  // (sk > c in a well-formed table; a broken one must not hang the walk)
       } else {
         c = c + 1u;
       }
@@ -1324,16 +1459,17 @@ cudaError_t exclusive_scan(const uint32_t* in, uint32_t* out, size_t n, DevBuf& 
 }
 
 struct SortBuffers {
-  SortPlan plan;   // global passes (bucket-local mode: the single pass on the top 8 bits)
-  SortPlan local;  // bucket-local mode: the shared-memory passes over the remaining bits
-  int mode;        // 0: global LSD passes, 1: bucket-local (4608-key buckets), 2: bucket-local (8192)
-  int stat_shift;  // >= 0: encode_kernel also builds the top-8-bit histogram (slot 8)
+  SortPlan plan;   // global LSD passes (none in the bucket modes)
+  int mode;        // 0: global LSD passes, 1 / 2 / 3: bucket sort with 4608 / 8192 / 16384-key buckets
+  int lo, key_bits;
+  unsigned cap;    // bucket capacity in the bucket modes
   unsigned tiles;
   int items;
   unsigned *ghist, *counters, *err_flag, *status;
 };
 
-constexpr unsigned LOCAL_CAP_SMALL = 512 * 9, LOCAL_CAP_LARGE = 512 * 16;
+// bucket capacities of modes 1..3: two CTAs of 512 threads per SM, then one CTA of 1024 threads per SM
+constexpr unsigned LOCAL_CAP[4] = {0u, 4608u, 8192u, 16384u};
 
 inline SortPlan even_plan(int lo, int total) {
   SortPlan plan;
@@ -1344,7 +1480,7 @@ inline SortPlan even_plan(int lo, int total) {
   return plan;
 }
 
-// plans the passes over key bits [lo, key_bits) and clears histograms / look-back state
+// plans the sort of key bits [lo, key_bits) and clears histograms / look-back state
 cudaError_t sort_prepare(GravityWorkspace& ws, size_t n, int key_bits, int lo, int mode, cudaStream_t st,
                          SortBuffers* sb) {
   // keys per thread, measured on B200: 8 wins at 1e5 bodies and from 4e6 up (more CTAs in flight),
@@ -1354,17 +1490,13 @@ cudaError_t sort_prepare(GravityWorkspace& ws, size_t n, int key_bits, int lo, i
   sb->tiles = blocks_for(n, SORT_THREADS * sb->items);
   if (key_bits - lo < 8) mode = 0;
   sb->mode = mode;
-  if (mode == 0) {
-    sb->plan = even_plan(lo, key_bits - lo);
-    sb->local = even_plan(lo, 0);
-    sb->stat_shift = key_bits - 8;
-  } else {
-    sb->plan = even_plan(key_bits - 8, 8);
-    sb->local = even_plan(lo, key_bits - 8 - lo);
-    sb->stat_shift = -1;  // pass 0 is that histogram
-  }
+  sb->lo = lo;
+  sb->key_bits = key_bits;
+  sb->cap = LOCAL_CAP[mode];
+  sb->plan = even_plan(lo, mode == 0 ? key_bits - lo : 0);
   const SortPlan& plan = sb->plan;
-  // [ghist: 9 x 256][tile counters: 8][error flag + pad: 8][status: npass x tiles x 256]
+  // [ghist: 9 x 256 (bucket modes: slot 0 = bucket cursors)][tile counters: 8][error flag + pad: 8]
+  // [status: npass x tiles x 256]
   const size_t head_words = SORT_HIST_SLOTS * 256 + SORT_MAX_PASSES + 8;
   const size_t words = head_words + size_t(plan.npass) * sb->tiles * 256;
   PB_PASS(ws.tile_counts.ensure(words * 4));
@@ -1375,27 +1507,58 @@ cudaError_t sort_prepare(GravityWorkspace& ws, size_t n, int key_bits, int lo, i
   PB_CUDA(cudaMemsetAsync(sb->ghist, 0, words * 4, st));
   if (ws.sticky.p) sb->err_flag = ws.sticky.as<unsigned>() + 2;  // survives until the next host check
   ws.sort_err_flag = sb->err_flag;
+  if (mode != 0) {
+    PB_PASS(ws.bucket_key.ensure(size_t(256) * sb->cap * 8));
+    PB_PASS(ws.bucket_idx.ensure(size_t(256) * sb->cap * 4));
+  }
   return cudaSuccess;
 }
 
-// the passes; returns with ws.sorted_key / ws.perm pointing at the result.  In the bucket-local
-// modes the sorted {x,y,z,m} records (ws.spos64) are written as well; `bad` is the build's
-// "keys not ordered" flag.
-cudaError_t sort_passes(GravityWorkspace& ws, size_t n, const SortBuffers& sb, unsigned* bad, cudaStream_t st,
-                        LaunchStats& ls) {
+// keys -> sorted keys + permutation (ws.sorted_key / ws.perm) + sorted {x,y,z,m} (ws.spos64).
+// `bad` is the build's "keys not ordered" flag.
+template <int DIM>
+cudaError_t encode_and_sort(GravityWorkspace& ws, size_t n, const SortBuffers& sb, unsigned* bad, cudaStream_t st,
+                            LaunchStats& ls) {
   uint64_t* k[2] = {ws.key0.as<uint64_t>(), ws.key1.as<uint64_t>()};
   uint32_t* v[2] = {ws.idx0.as<uint32_t>(), ws.idx1.as<uint32_t>()};
+  unsigned* stat_max = ws.sticky.as<unsigned>() + 3;
+  const unsigned nb = blocks_for(n, 256);
+  if (sb.mode != 0) {
+    PB_LAUNCH(ls, st, "encode_bucket_kernel",
+              encode_bucket_kernel<DIM><<<blocks_for(n, 256 * ENC_ITEMS), 256, 0, st>>>(
+                  ws.pos64, n, ws.extent_bits.as<unsigned long long>(), ws.bucket_key.as<uint64_t>(),
+                  ws.bucket_idx.as<uint32_t>(), sb.cap, sb.ghist));
+    const size_t smem = sort_local_smem(sb.cap);
+    if (sb.mode == 1) {
+      PB_CUDA(cudaFuncSetAttribute(sort_local_kernel<512, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+      PB_LAUNCH(ls, st, "sort_local_kernel",
+                sort_local_kernel<512, 9><<<256, 512, smem, st>>>(
+                    ws.bucket_key.as<uint64_t>(), ws.bucket_idx.as<uint32_t>(), sb.ghist, sb.cap, sb.lo, sb.key_bits,
+                    k[0], v[0], ws.pos64, ws.spos64.as<double4>(), bad, stat_max));
+    } else {
+      PB_CUDA(cudaFuncSetAttribute(sort_local_kernel<1024, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+      PB_LAUNCH(ls, st, "sort_local_kernel",
+                sort_local_kernel<1024, 8><<<256, 1024, smem, st>>>(
+                    ws.bucket_key.as<uint64_t>(), ws.bucket_idx.as<uint32_t>(), sb.ghist, sb.cap, sb.lo, sb.key_bits,
+                    k[0], v[0], ws.pos64, ws.spos64.as<double4>(), bad, stat_max));
+    }
+    ws.sorted_key = k[0];
+    ws.perm = v[0];
+    return cudaGetLastError();
+  }
+  PB_LAUNCH(ls, st, "encode_kernel",
+            encode_kernel<DIM><<<min(nb, 148u * 4u), 256, 0, st>>>(
+                ws.pos64, n, ws.extent_bits.as<unsigned long long>(), k[0], v[0], sb.plan, sb.key_bits - 8, sb.ghist));
   // 48 KB of dynamic + 10 KB of static shared memory for the 16-keys-per-thread tile: opt in
   // (per device, so per call: the handle may live on any device)
   if (sb.items == 16)
     PB_CUDA(cudaFuncSetAttribute(sort_onesweep_pass<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  SORT_THREADS * 16 * 12));
-  unsigned* stat_max = ws.sticky.as<unsigned>() + 3;
   int cur = 0;
   for (int p = 0; p < sb.plan.npass; ++p) {
     const size_t smem = size_t(SORT_THREADS) * sb.items * 12;  // digit-sorted tile: u64 keys + u32 values
-    // pass 0 also publishes the largest top-8-bit bin (its own histogram in the bucket-local modes)
-    const unsigned* stat_hist = p != 0 ? nullptr : (sb.mode ? sb.ghist : sb.ghist + (SORT_HIST_SLOTS - 1) * 256);
+    // pass 0 also publishes the largest bin of the top-8-bit histogram (encode_kernel's slot 8)
+    const unsigned* stat_hist = p != 0 ? nullptr : sb.ghist + (SORT_HIST_SLOTS - 1) * 256;
     if (sb.items == 8)
       PB_LAUNCH(ls, st, "sort_onesweep_pass",
                 sort_onesweep_pass<8><<<sb.tiles, SORT_THREADS, smem, st>>>(
@@ -1410,30 +1573,9 @@ cudaError_t sort_passes(GravityWorkspace& ws, size_t n, const SortBuffers& sb, u
                     stat_hist, stat_max));
     cur ^= 1;
   }
-  if (sb.mode == 1) {
-    static const int variant = std::getenv("PB200_LOCAL_VARIANT") ? std::atoi(std::getenv("PB200_LOCAL_VARIANT")) : 0;
-    if (variant == 0) {
-      constexpr size_t smem = sort_local_smem<512, 9>();
-      PB_CUDA(cudaFuncSetAttribute(sort_local_kernel<512, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-      PB_LAUNCH(ls, st, "sort_local_kernel",
-                sort_local_kernel<512, 9><<<256, 512, smem, st>>>(k[cur], v[cur], sb.ghist, sb.local, ws.pos64,
-                                                                  ws.spos64.as<double4>(), bad));
-    } else {
-      constexpr size_t smem = sort_local_smem<256, 18>();
-      PB_CUDA(cudaFuncSetAttribute(sort_local_kernel<256, 18>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-      PB_LAUNCH(ls, st, "sort_local_kernel",
-                sort_local_kernel<256, 18><<<256, 256, smem, st>>>(k[cur], v[cur], sb.ghist, sb.local, ws.pos64,
-                                                                   ws.spos64.as<double4>(), bad));
-    }
-  } else if (sb.mode == 2) {
-    constexpr size_t smem = sort_local_smem<512, 16>();
-    PB_CUDA(cudaFuncSetAttribute(sort_local_kernel<512, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    PB_LAUNCH(ls, st, "sort_local_kernel",
-              sort_local_kernel<512, 16><<<256, 512, smem, st>>>(k[cur], v[cur], sb.ghist, sb.local, ws.pos64,
-                                                                 ws.spos64.as<double4>(), bad));
-  }
   ws.sorted_key = k[cur];
   ws.perm = v[cur];
+  PB_LAUNCH(ls, st, "gather_kernel", gather_kernel<<<nb, 256, 0, st>>>(ws.pos64, ws.perm, n, ws.spos64.as<double4>()));
   return cudaGetLastError();
 }
 
@@ -1470,16 +1612,17 @@ cudaError_t tree_evaluate(GravityWorkspace& ws, const GravityParams& prm, size_t
   SortBuffers sb;
   PB_PASS(sort_prepare(ws, n, key_bits, lo, ws.sort_mode, st, &sb));
   ws.last_mode = sb.mode;
-  PB_LAUNCH(ls, st, "encode_kernel",
-            encode_kernel<DIM><<<min(nb, 148u * 4u), 256, 0, st>>>(
-                ws.pos64, n, ws.extent_bits.as<unsigned long long>(), ws.key0.as<uint64_t>(),
-                ws.idx0.as<uint32_t>(), sb.plan, sb.stat_shift, sb.ghist));
-  PB_PASS(sort_passes(ws, n, sb, max_shared_plus1 + 2, st, ls));
-  if (sb.mode == 0)
-    PB_LAUNCH(ls, st, "gather_kernel", gather_kernel<<<nb, 256, 0, st>>>(ws.pos64, ws.perm, n, ws.spos64.as<double4>()));
+  PB_PASS(encode_and_sort<DIM>(ws, n, sb, max_shared_plus1 + 2, st, ls));
+  // range-minimum tables over the sorted bodies' shared-level bytes (see NsvTables)
+  const size_t n_pad = size_t(nb) * 256, nblocks = nb, b_pad = (nblocks + 255) / 256 * 256, nsuper = b_pad / 256;
+  PB_PASS(ws.nsv1.ensure(9 * n_pad));
+  PB_PASS(ws.nsv2.ensure(9 * b_pad + nsuper));
+  uint8_t* nsv3 = ws.nsv2.as<uint8_t>() + 9 * b_pad;
   PB_LAUNCH(ls, st, "unit_kernel", unit_kernel<DIM><<<nb, 256, 0, st>>>(ws.sorted_key, ws.spos64.as<double4>(), n, ws.ab.as<uchar2>(),
                                        ws.tgt_flags.as<uint32_t>(), max_shared_plus1,
-                                       lo > 0 ? (key_bits - lo) / DIM : TreeDim<DIM>::LM + 2));
+                                       lo > 0 ? (key_bits - lo) / DIM : TreeDim<DIM>::LM + 2,
+                                       ws.nsv1.as<uint8_t>(), n_pad, ws.nsv2.as<uint8_t>()));
+  PB_LAUNCH(ls, st, "nsv_level2_kernel", nsv_level2_kernel<<<unsigned(nsuper), 256, 0, st>>>(ws.nsv2.as<uint8_t>(), b_pad, nblocks, nsv3));
   PB_PASS(exclusive_scan(ws.tgt_flags.as<uint32_t>(), ws.cell_start.as<uint32_t>(), n, ws.scan_tmp, st, ls));
 
   // cell table capacity: grows when a previous evaluation reported more cells
@@ -1500,14 +1643,12 @@ cudaError_t tree_evaluate(GravityWorkspace& ws, const GravityParams& prm, size_t
                    ws.c_centre_ext.as<double4>(), ws.c_com.as<double4>(), static_cast<uint32_t>(cap), SMALL_CELL,
                    max_shared_plus1 + 2};
   const unsigned nb128 = blocks_for(n, 128);
-  PB_LAUNCH(ls, st, "chain_kernel",
-            chain_kernel<DIM><<<nb, 256, 0, st>>>(ws.sorted_key, ws.spos64.as<double4>(), ws.perm,
+  const NsvTables tv{ws.nsv1.as<uint8_t>(), n_pad, ws.nsv2.as<uint8_t>(), b_pad, nsv3, n, nblocks, nsuper};
+  PB_LAUNCH(ls, st, "cells_kernel",
+            cells_kernel<DIM><<<nb, 256, 0, st>>>(ws.sorted_key, ws.spos64.as<double4>(), ws.perm,
                                                   ws.ab.as<uchar2>(), ws.cell_start.as<uint32_t>(), n,
-                                                  ws.extent_bits.as<unsigned long long>(), cells));
-  PB_LAUNCH(ls, st, "skip_kernel",
-            skip_kernel<DIM><<<blocks_for(cap, 256), 256, 0, st>>>(
-                ws.sorted_key, ws.spos64.as<double4>(), ws.perm, ws.ab.as<uchar2>(),
-                ws.cell_start.as<uint32_t>(), n, max_shared_plus1, ws.sticky.as<unsigned>(), cells));
+                                                  ws.extent_bits.as<unsigned long long>(), max_shared_plus1,
+                                                  ws.sticky.as<unsigned>(), tv, cells));
   PB_LAUNCH(ls, st, "parent_kernel",
             parent_kernel<<<blocks_for(cap, 256), 256, 0, st>>>(ws.cell_start.as<uint32_t>(), n, cells));
   PB_LAUNCH(ls, st, "com_kernel", com_kernel<<<nb128, 128, 0, st>>>(ws.ab.as<uchar2>(), ws.cell_start.as<uint32_t>(), n, cells));
@@ -1583,7 +1724,7 @@ cudaError_t direct_evaluate(GravityWorkspace& ws, size_t t0, size_t t1, float ea
 }  // namespace
 
 void GravityWorkspace::release_all() {
-  DevBuf* all[] = {&src4, &key0, &key1, &idx0, &idx1, &spos64, &ab, &cell_start, &scan_tmp,
+  DevBuf* all[] = {&src4, &key0, &key1, &idx0, &idx1, &bucket_key, &bucket_idx, &nsv1, &nsv2, &spos64, &ab, &cell_start, &scan_tmp,
                    &tile_counts, &digit_base, &extent_bits, &tgt_list, &tgt_flags, &c_level, &c_head,
                    &c_count, &c_skip, &c_parent, &c_arrived, &c_centre_ext, &c_com, &acc, &acc_part, &sticky,
                    &counters};
@@ -1654,11 +1795,14 @@ cudaError_t gravity_check(GravityWorkspace& ws, cudaStream_t st, TreeCheck* out)
   // skipped): fall back to the mode the observed largest bucket allows and let the caller re-run
   out->max_bucket = h[3];
   ws.last_max_bucket = h[3];
-  out->bucket_overflow = (ws.last_mode == 1 && h[3] > LOCAL_CAP_SMALL) || (ws.last_mode == 2 && h[3] > LOCAL_CAP_LARGE);
+  out->bucket_overflow = ws.last_mode != 0 && h[3] > LOCAL_CAP[ws.last_mode];
   static const char* mode_env = std::getenv("PB200_SORT_MODE");  // "lsd": global passes only (A/B runs)
-  if (mode_env && !std::strcmp(mode_env, "lsd")) ws.sort_mode = 0;
-  else if (h[3] + h[3] / 32 <= LOCAL_CAP_SMALL) ws.sort_mode = 1;
-  else if (h[3] + h[3] / 32 <= LOCAL_CAP_LARGE) ws.sort_mode = 2;
+  if (h[3] >= LOCAL_SKEWED) ws.bucket_ban = 64;  // bodies too alike inside a bucket: global passes for a while
+  else if (ws.bucket_ban > 0) --ws.bucket_ban;
+  if ((mode_env && !std::strcmp(mode_env, "lsd")) || ws.bucket_ban > 0) ws.sort_mode = 0;
+  else if (h[3] + h[3] / 32 <= LOCAL_CAP[1]) ws.sort_mode = 1;
+  else if (h[3] + h[3] / 32 <= LOCAL_CAP[2]) ws.sort_mode = 2;
+  else if (h[3] + h[3] / 32 <= LOCAL_CAP[3]) ws.sort_mode = 3;
   else ws.sort_mode = 0;
   ws.n_cells = h[0];
   ws.last_total = h[0];

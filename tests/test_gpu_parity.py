@@ -205,15 +205,16 @@ TREE_KEYS = ("key", "perm", "cell_start", "level", "head", "count", "skip", "par
 @pytest.mark.parametrize("name", ["astro2", "astro"])
 def test_bucket_local_sort_matches_global_sort(name):
     """From the second evaluation on, a body set whose top-8-bit key bins fit a shared-memory tile is
-    sorted by one global pass + bucket-local passes (Pb200Stats.sort_mode 1 / 2).  Same stable
-    permutation, hence the same bit-exact tree, as the all-global LSD sort and the oracle."""
+    sorted by the bucket sort (Pb200Stats.sort_mode 1..3: keys scattered to 256 buckets by the
+    encoder, each bucket sorted in shared memory).  Same permutation, hence the same bit-exact tree,
+    as the stable global LSD sort and the oracle."""
     s = np.concatenate([gen.cube(60_000, seed=3), with_merges(5)])
     o = ob.CellTable(DIM[name], s)
     ref = ob.transform(name, s, 1.0, 0.5)
     el = api.TransformElement(name, theta=1.0, e=0.5)
     el.transform(s)
     assert el.stats()["sort_mode"] == 0                      # nothing known about the buckets yet
-    for forced in (None, 2, 1):
+    for forced in (None, 3, 2, 1):
         if forced is not None:
             el.debug_sort_mode(forced)
         acc = el.transform(s)
