@@ -276,6 +276,26 @@ int pb200_sim_set_stream(void *sim, void *stream);
 /* CUDA stream (cudaStream_t) the handle launches on, for event timing by the caller. */
 void *pb200_sim_stream(void *sim);
 
+/* --- csvsink (utilities/src/csvsink.rs:44-80) ---------------------------
+ * The headless renderer of a CPU run: one line per printed state, "x,y,z," per entity, numbers in
+ * Rust's `{}` format for f64 (shortest round-trip digits, positional notation).  The first state
+ * pushed (the initial one, pipeline.rs:129-131) is always printed, state k >= 1 iff k % print_n == 0.
+ * file NULL or "" selects the reference's default "csvsink.csv"; the file is created / truncated. */
+void *pb200_csvsink_create(const char *file, size_t print_n);
+int pb200_csvsink_push(void *sink, const Entity *state, size_t n);
+void pb200_csvsink_destroy(void *sink);
+/* States received so far; whether the next one will be printed; count a state without printing it
+ * (a producer that knows the state is not due can skip the copy back from the device). */
+size_t pb200_csvsink_count(void *sink);
+int pb200_csvsink_next_is_printed(void *sink);
+int pb200_csvsink_skip(void *sink);
+/* Rust `format!("{}", v)` for an f64 into buf (no NUL); returns the length (<= cap; 400 always fits). */
+size_t pb200_csv_format_f64(double v, char *buf, size_t cap);
+/* Device-resident loop feeding a csvsink the way the pipeline feeds its renderer: the current state
+ * if the sink is fresh, then the state after each of `steps` steps (one D2H of the positions per
+ * printed state). */
+int pb200_sim_run_csvsink(void *sim, size_t steps, void *sink);
+
 /* --- microbenchmarks used by bench.py for the roofline denominators ---------------------- */
 /* FP32 FFMA issue-rate probe: returns achieved TFLOP/s (2 flop per FFMA) on the current device. */
 double pb200_probe_fp32_tflops(void);

@@ -275,3 +275,26 @@ class CellTable:
         if getattr(self, "_h", None):
             lib().oracle_table_free(self._h)
             self._h = None
+
+
+# ---- csvsink (utilities/src/csvsink.rs:44-80), restated in Python -----------------------------
+def rust_display_f64(v):
+    """Rust `{}` for f64: shortest round-trip digits in positional notation; "NaN", "inf", "-inf"."""
+    v = float(v)
+    if v != v:
+        return "NaN"
+    if v in (float("inf"), float("-inf")):
+        return "inf" if v > 0 else "-inf"
+    return np.format_float_positional(v, unique=True, trim="-")
+
+
+def csvsink_lines(states, print_n=1):
+    """The file a csvsink with `print_n` writes for the sequence of states a pipeline sends its
+    renderer: state 0 always (csvsink.rs:60-63), state k >= 1 iff k % print_n == 0 (:65-70); each
+    line is "x,y,z," per entity (:74-79)."""
+    out = []
+    for k, st in enumerate(states):
+        if k == 0 or k % print_n == 0:
+            out.append("".join("%s,%s,%s," % (rust_display_f64(e["x"]), rust_display_f64(e["y"]),
+                                              rust_display_f64(e["z"])) for e in st) + "\n")
+    return "".join(out)

@@ -134,6 +134,17 @@ def lib():
     L.pb200_sim_stream.restype = vp
     L.pb200_sim_stream.argtypes = [vp]
     L.pb200_probe_fp32_tflops.restype = dbl
+    L.pb200_csvsink_create.restype = vp
+    L.pb200_csvsink_create.argtypes = [C.c_char_p, sz]
+    L.pb200_csvsink_push.argtypes = [vp, vp, sz]
+    L.pb200_csvsink_destroy.argtypes = [vp]
+    L.pb200_csvsink_count.restype = sz
+    L.pb200_csvsink_count.argtypes = [vp]
+    L.pb200_csvsink_next_is_printed.argtypes = [vp]
+    L.pb200_csvsink_skip.argtypes = [vp]
+    L.pb200_csv_format_f64.restype = sz
+    L.pb200_csv_format_f64.argtypes = [dbl, C.c_char_p, sz]
+    L.pb200_sim_run_csvsink.argtypes = [vp, sz, vp]
     _lib = L
     return L
 
@@ -380,6 +391,12 @@ class Sim:
         lib().pb200_sim_gather_buffer(self._s, C.byref(p), C.byref(tot), C.byref(off), C.byref(sl))
         return p.value, tot.value, off.value, sl.value
 
+    def run_csvsink(self, steps, sink):
+        """`steps` steps with `sink` (a CsvSink) as the pipeline's renderer: it receives the current
+        state first if it is fresh, then the state after every step (pipeline.rs:129-131,179)."""
+        if lib().pb200_sim_run_csvsink(self._s, int(steps), sink._obj) != 0:
+            raise Pb200Error(last_error())
+
     def download(self, state):
         state = _state(state)
         if lib().pb200_sim_download(self._s, _ptr(state), len(state)) != 0:
@@ -429,3 +446,38 @@ def device_count():
 
 def probe_fp32_tflops():
     return lib().pb200_probe_fp32_tflops()
+
+
+def csv_format_f64(v):
+    """Rust `format!("{}", v)` for an f64, as the csvsink writes it (csvsink.rs:76)."""
+    buf = C.create_string_buffer(512)
+    k = lib().pb200_csv_format_f64(float(v), buf, 512)
+    return buf.raw[:k].decode()
+
+
+class CsvSink:
+    """physim's `csvsink` renderer (utilities/src/csvsink.rs:17-80): properties `file`, `print_n`."""
+
+    def __init__(self, file="csvsink.csv", print_n=1):
+        self._obj = lib().pb200_csvsink_create(os.fsencode(file), int(print_n))
+        if not self._obj:
+            raise Pb200Error(last_error())
+
+    def push(self, state):
+        state = _state(state)
+        if lib().pb200_csvsink_push(self._obj, _ptr(state), len(state)) != 0:
+            raise Pb200Error(last_error())
+
+    def count(self):
+        return lib().pb200_csvsink_count(self._obj)
+
+    def close(self):
+        if getattr(self, "_obj", None):
+            lib().pb200_csvsink_destroy(self._obj)
+            self._obj = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1002,6 +1002,47 @@ int pb200_sim_run(void* sim, size_t steps) {
   return 0;
 }
 
+int pb200_sim_run_csvsink(void* sim, size_t steps, void* sink) {
+  if (!sim || !sink) return -1;
+  auto& s = *static_cast<SimObj*>(sim);
+  std::lock_guard<std::mutex> lk(s.mu);
+  if (!s.gpu.ready) {
+    set_error("pb200_sim_upload first");
+    return -1;
+  }
+  if (s.world != 1) {
+    set_error("pb200_sim_run_csvsink: single-rank simulations only");
+    return -1;
+  }
+  cudaSetDevice(s.gpu.device);
+  cudaStream_t st = s.gpu.stream;
+  std::vector<Entity> host;
+  // what the pipeline sends its renderer (pipeline.rs:129-131,179): a copy of the state
+  auto emit = [&]() -> int {
+    if (!pb200_csvsink_next_is_printed(sink)) return pb200_csvsink_skip(sink);
+    if (host.size() != s.n) host.assign(s.n, Entity{});
+    if (cudaMemcpyAsync(s.h_pos.p, s.cur.p, s.n * sizeof(double4), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess) {
+      set_error("pb200_sim_run_csvsink: copy back failed");
+      return -1;
+    }
+    const double4* p = s.h_pos.as<double4>();
+    for (size_t i = 0; i < s.n; ++i) {
+      host[i].x = p[i].x; host[i].y = p[i].y; host[i].z = p[i].z;
+    }
+    return pb200_csvsink_push(sink, host.data(), s.n);
+  };
+  if (pb200_csvsink_count(sink) == 0 && emit() != 0) return -1;
+  for (size_t i = 0; i < steps; ++i) {
+    if (sim_run_steps(s, 1) != cudaSuccess) {
+      std::fprintf(stderr, "[physim_b200] sim run failed: %s\n", g_error);
+      return -1;
+    }
+    if (emit() != 0) return -1;
+  }
+  return cudaStreamSynchronize(st) == cudaSuccess ? 0 : -1;
+}
+
 int pb200_sim_run_sharded(void* sim, size_t steps, void (*exchange)(void*), void* ctx) {
   if (!sim || !exchange) return -1;
   auto& s = *static_cast<SimObj*>(sim);

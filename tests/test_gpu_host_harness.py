@@ -47,6 +47,18 @@ def test_cpp_host_runs_the_pipeline(host, tmp_path, element, props, theta, e):
         assert np.array_equal(got[f], s[f])
 
 
+def test_cpp_host_csvsink_without_gpu(host, tmp_path):
+    """The csvsink renderer through the C ABI from the C++ host: with 0 iterations it receives only
+    the initial state (pipeline.rs:129-131) and writes the reference's one-line format."""
+    s = gen.solar()
+    inp, out, csv = str(tmp_path / "state.bin"), str(tmp_path / "out.bin"), str(tmp_path / "out.csv")
+    s.tofile(inp)
+    r = subprocess.run([host, api.LIB_PATH, "simple_astro", '{"e":0.1}', inp, "0.01", "0", out, csv, "1"],
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert open(csv).read() == ob.csvsink_lines([s], 1)
+
+
 def test_cpp_host_discovery_without_gpu(host, tmp_path):
     """Discovery, throw-away instances and the bus message need no GPU; with 0 iterations nothing
     touches CUDA (lazy initialisation)."""

@@ -166,3 +166,29 @@ def test_energy_and_momentum_drift_solar():
 
     scale = (s["mass"] * np.sqrt(s["vx"] ** 2 + s["vy"] ** 2 + s["vz"] ** 2)).sum()
     assert np.abs(mom(out) - mom(s)).max() / scale < 1e-6 + 10 * np.abs(mom(ref) - mom(s)).max() / scale
+
+
+def test_device_resident_run_feeds_csvsink(tmp_path):
+    """`cube ! astro2 ! verlet ! csvsink print_n=2`: the device-resident loop as the producer of the
+    renderer's states (pipeline.rs:129-131,179); rows against the oracle's pipeline."""
+    s = gen.readme_pipeline(3000, seed=4, spin=1000.0)
+    dt, steps, print_n = 1e-5, 6, 2
+    sim = api.Sim("astro2", theta=1.5, e=0.5, dt=dt)
+    sim.upload(s)
+    path = tmp_path / "run.csv"
+    sink = api.CsvSink(str(path), print_n)
+    sim.run_csvsink(steps, sink)
+    assert sink.count() == steps + 1
+    sink.close()
+    lines = path.read_text().split("\n")
+    assert lines[-1] == "" and len(lines) - 1 == 1 + steps // print_n
+    printed = [0] + [k for k in range(1, steps + 1) if k % print_n == 0]
+    for line, k in zip(lines, printed):
+        want = s if k == 0 else ob.run_pipeline("astro2", s, 1.5, 0.5, dt, k)[0]
+        row = np.array(line.split(",")[:-1], dtype=np.float64).reshape(-1, 3)
+        ref = np.stack([want["x"], want["y"], want["z"]], 1)
+        if k == 0:
+            assert np.array_equal(row, ref)                      # shortest digits round-trip exactly
+        else:
+            disp = np.abs(ref - np.stack([s["x"], s["y"], s["z"]], 1)).max()
+            assert np.abs(row - ref).max() <= 1e-5 * disp

@@ -11,7 +11,10 @@
 //
 // The integrator is `verlet` through pb200_verlet_step (what rust_shim/ forwards to).
 //
-//   physim_host <lib.so> <element> <json-properties> <state.bin> <dt> <iterations> <out.bin>
+//   renderer       utilities/src/csvsink.rs:44-80 through pb200_csvsink_* (optional): receives the
+//                  initial state, then every new state (pipeline.rs:129-131,179)
+//
+//   physim_host <lib.so> <element> <json-properties> <state.bin> <dt> <iterations> <out.bin> [<out.csv> <print_n>]
 //
 // Build: g++ -O2 -std=c++17 -rdynamic tools/physim_host.cpp -o physim_host -ldl
 #include <dlfcn.h>
@@ -69,8 +72,8 @@ static void acc_fn(void* ctx, const Entity* state, size_t n, Acceleration* acc) 
 }
 
 int main(int argc, char** argv) {
-  if (argc != 8) {
-    std::fprintf(stderr, "usage: %s lib element json state.bin dt iterations out.bin\n", argv[0]);
+  if (argc != 8 && argc != 10) {
+    std::fprintf(stderr, "usage: %s lib element json state.bin dt iterations out.bin [out.csv print_n]\n", argv[0]);
     return 2;
   }
   const std::string element = argv[2], props = argv[3];
@@ -139,10 +142,19 @@ int main(int argc, char** argv) {
   // ---- simulation thread (pipeline.rs:143-182) ---------------------------------------------
   void* verlet = verlet_create();
   AccCtx ctx{&transforms};
+  void* sink = nullptr;
+  auto sink_push = sym<int (*)(void*, const Entity*, size_t)>(lib, "pb200_csvsink_push");
+  if (argc == 10) {
+    sink = sym<void* (*)(const char*, size_t)>(lib, "pb200_csvsink_create")(argv[8], size_t(std::atol(argv[9])));
+    if (!sink) return 5;
+    if (sink_push(sink, state.data(), n) != 0) return 5;  // simulation_sender.send(state.clone())
+  }
   for (long it = 0; it < iterations; ++it) {
     if (verlet_step(verlet, state.data(), new_state.data(), n, acc_fn, &ctx, dt) != 0) return 4;
     state = new_state;  // state = new_state.clone()
+    if (sink && sink_push(sink, new_state.data(), n) != 0) return 5;  // simulation_sender.send(new_state.clone())
   }
+  if (sink) sym<void (*)(void*)>(lib, "pb200_csvsink_destroy")(sink);
   verlet_destroy(verlet);
   for (const Loaded& t : transforms) t.api->destroy(t.obj);
   f = std::fopen(argv[7], "wb");
