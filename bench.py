@@ -55,6 +55,7 @@ ALG_BYTES_PER_BODY = {
     "to_soa_kernel": 32 + 16, "sort_local_kernel": 12 + 12 + 32 + 32, "encode_bucket_kernel": 32 + 12,
 }
 FLOP_PER_INTERACTION = 19
+NCU_KERNELS = "r01b_ncu_c3_kernels.json"  # per-kernel DRAM traffic of the committed ncu --set full capture
 
 
 def make_state(w):
@@ -279,13 +280,13 @@ def run_ours(args, w):
     traffic = None  # dram read + write bytes per launch, from the committed ncu --set full capture
     try:
         if args.workload == "c3":
-            nc = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_c3_kernels.json")))[top["kernel"]]
+            nc = json.load(open(os.path.join(ROOT, "profiles", NCU_KERNELS)))[top["kernel"]]
             traffic = (nc["dram_read_mb_per_launch"] + nc["dram_write_mb_per_launch"]) * 1e6
     except Exception:
         pass
     roofline = {"kernel": top["kernel"], "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
                 "unit": "GB/s", "frac": (achieved / hbm_peak) if achieved else None, "traffic": traffic,
-                "traffic_source": "profiles/r01_ncu_c3_kernels.json (ncu --set full, cold L2)" if traffic else None,
+                "traffic_source": f"profiles/{NCU_KERNELS} (ncu --set full, cold L2)" if traffic else None,
                 "peak_source": peak_kind, "avg_launch_ms": per_launch_ms,
                 "share_of_step": top["ms"] / tot_ms,
                 "alg_bytes_per_launch": alg_bytes,

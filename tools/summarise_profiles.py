@@ -25,7 +25,8 @@ for r in rows:
     a[1] += float(r[vi])
 tot = sum(v[1] for v in agg.values())
 out = [f"# ncu launch list, {tag} (workload c3: 1,000,004 bodies, astro theta=1.3 + verlet)", "",
-       "Command: `ncu --metrics gpu__time_duration.sum --clock-control none -s 85 -c 170 --csv python bench.py --steps 5 --warmup 3 --skip-extras`",
+       "Command: `ncu --metrics gpu__time_duration.sum --clock-control none -s 51 -c 111 --csv python bench.py --steps 5 --warmup 3 --skip-extras`",
+       "(the 3 warm-up steps = 51 launches use the global LSD sort and are skipped; the steps after the first host check use the bucket sort)",
        f"({len(rows)} launches = 10 steps; cold-cache, serialised: compare SHARES with bench.py's live `roofline.kernels`)", "",
        "| kernel | launches | total us | us / launch | share |", "|---|---:|---:|---:|---:|"]
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
@@ -52,7 +53,7 @@ for r in rows[2:]:
         except ValueError:
             pass
 out = [f"# ncu --set full summary, {tag} (c3: 1,000,004 bodies, astro theta=1.3 + verlet)", "",
-       "`ncu --set full --clock-control none --import-source on -s 85 -c 17 python bench.py --steps 5 --warmup 3 --skip-extras`",
+       "`ncu --set full --clock-control none --import-source on -s 51 -c 11 python bench.py --steps 5 --warmup 3 --skip-extras`",
        "(one step; caches flushed between replays, so DRAM traffic is the cold-L2 figure; averages per launch)", "",
        "| kernel | launches | us | DRAM read MB | DRAM write MB | DRAM % peak | SM % peak | issue active % | warps active % | active lanes / instr | regs | grid |",
        "|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|"]
