@@ -112,7 +112,7 @@ struct GravityWorkspace {
   const uint8_t* fixed = nullptr;
   size_t n = 0;
   // owned
-  DevBuf src4, key0, key1, idx0, idx1, bucket_key, bucket_idx, nsv1, nsv2, spos64, ab, cell_start, scan_tmp, tile_counts, digit_base,
+  DevBuf src4, key0, key1, idx0, idx1, bucket_key, bucket_idx, splitters, nsv1, nsv2, spos64, ab, cell_start, scan_tmp, tile_counts, digit_base,
       extent_bits, tgt_list, tgt_flags;
   DevBuf c_level, c_head, c_count, c_skip, c_parent, c_arrived, c_centre_ext, c_com;
   DevBuf acc, acc_part, counters, sticky;
@@ -124,6 +124,7 @@ struct GravityWorkspace {
   int sort_extra_levels = 0;  // safety margin, grown whenever a truncated sort proved too short
   int sort_mode = 0;    // next sort: 0 global LSD passes, 1..3 bucket sort (chosen by gravity_check)
   int last_mode = 0;    // ... that the last sort used
+  int splitter_cur = 0; // which of the two splitter sets the next evaluation reads
   int bucket_ban = 0;   // checks left during which the bucket sort stays off (a bucket's bodies were too alike)
   uint32_t last_max_bucket = 0;  // fullest top-8-bit bin seen at the last check
   int unchecked_builds = 0;   // tree builds since the last gravity_check()

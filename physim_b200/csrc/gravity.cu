@@ -135,7 +135,7 @@ __device__ __forceinline__ double with_sign(double half, bool negative) {
   return __hiloint2double(hi, __double2loint(half));
 }
 
-constexpr int SORT_HIST_SLOTS = 9;  // 8 sort passes at most + the top-8-bit statistics histogram
+constexpr int SORT_HIST_SLOTS = 8;  // 8 sort passes at most (bucket sort: slot 0 holds the bucket cursors)
 
 // Also accumulates the digit histograms of every sort pass (the keys are in registers anyway),
 // warp-aggregated into shared memory, flushed once per block: gridDim.x is kept small.
@@ -144,9 +144,7 @@ __global__ void __launch_bounds__(256) encode_kernel(const double4* __restrict__
                                                      const unsigned long long* __restrict__ extent_bits,
                                                      uint64_t* __restrict__ key,
                                                      uint32_t* __restrict__ idx, SortPlan plan,
-                                                     int stat_shift, unsigned* __restrict__ ghist) {
-  // slots 0..npass-1: the digits of the sort passes; slot 8 (stat_shift >= 0): the key's top 8 bits,
-  // whose largest bin decides whether the next sort may use the bucket-local form (sort_local_kernel)
+                                                     unsigned* __restrict__ ghist) {
   __shared__ unsigned h[SORT_HIST_SLOTS * 256];
   for (int j = threadIdx.x; j < SORT_HIST_SLOTS * 256; j += 256) h[j] = 0;
   __syncthreads();
@@ -180,11 +178,8 @@ __global__ void __launch_bounds__(256) encode_kernel(const double4* __restrict__
       idx[i] = static_cast<uint32_t>(i);
     }
     const unsigned okmask = __ballot_sync(FULL, ok);
-    const int nh = plan.npass + (stat_shift >= 0 ? 1 : 0);
-    for (int q = 0; q < nh; ++q) {
-      const bool stat = q == plan.npass;
-      const int p = stat ? SORT_HIST_SLOTS - 1 : q;
-      const unsigned d = stat ? (unsigned(k >> stat_shift) & 255u) : (unsigned(k >> plan.shift(p)) & plan.mask(p));
+    for (int p = 0; p < plan.npass; ++p) {
+      const unsigned d = unsigned(k >> plan.shift(p)) & plan.mask(p);
       // the high digits are the same for the whole warp: one add; otherwise per-lane adds
       const unsigned d0 = __shfl_sync(FULL, d, 0);
       if (__all_sync(FULL, !ok || d == d0)) {
@@ -219,8 +214,7 @@ __global__ void __launch_bounds__(SORT_THREADS, SORT_ITEMS >= 16 ? 2 : 4) sort_o
     const uint64_t* __restrict__ kin, const uint32_t* __restrict__ vin, uint64_t* __restrict__ kout,
     uint32_t* __restrict__ vout, size_t n, int shift, unsigned mask,
     const unsigned* __restrict__ ghist /*[256] of this pass*/, unsigned* status /*[tiles][256]*/,
-    unsigned* tile_counter, unsigned* err_flag, const unsigned* __restrict__ stat_hist /*[256] or null*/,
-    unsigned* stat_max) {
+    unsigned* tile_counter, unsigned* err_flag) {
   __shared__ unsigned whist[8][256];
   __shared__ unsigned tstart[256];  // first tile-local slot of each digit
   __shared__ unsigned gadj[256];    // global slot of a digit's first element minus its tile-local slot
@@ -234,8 +228,6 @@ __global__ void __launch_bounds__(SORT_THREADS, SORT_ITEMS >= 16 ? 2 : 4) sort_o
   for (int j = tid; j < 8 * 256; j += SORT_THREADS) (&whist[0][0])[j] = 0;
   const unsigned dbase = block_exclusive_scan_256(ghist[tid], nullptr);  // start of each digit; syncs
   const unsigned tile = tile_s;
-  // largest bin of the top-8-bit histogram, worst case since the last host check (gravity_check)
-  if (stat_hist != nullptr && tile == 0u) atomicMax(stat_max, stat_hist[tid]);
   const size_t tile_base = size_t(tile) * SORT_TILE;
   const size_t base = tile_base + size_t(warp) * 32 * SORT_ITEMS;
   const unsigned nvalid = static_cast<unsigned>(min(size_t(SORT_TILE), n - tile_base));
@@ -338,17 +330,20 @@ __global__ void __launch_bounds__(SORT_THREADS, SORT_ITEMS >= 16 ? 2 : 4) sort_o
 }
 
 // ---------------------------------------------------------------------------------------------
-// K3b  bucket sort (replaces K2 + K3 + K4 when no bin of the keys' top 8 bits holds more bodies than
-//      a shared-memory tile; the host knows from the previous evaluation, gravity_check()).
+// K3b  bucket sort (replaces K2 + K3 + K4 from the second evaluation on, for N up to ~3.7 M).
 //      The stable LSD sort from index order is the same permutation as ANY sort by the pair
-//      (key bits >= lo, original index), so neither step below needs to be stable:
+//      (key >> lo, original index), so neither step below needs to be stable:
 //      encode_bucket_kernel  computes the keys (as K2) and appends (key, index) to one of 256
-//                            fixed-capacity buckets chosen by the key's top 8 bits (per-CTA counts in
-//                            shared memory, one global atomic per CTA and bucket);
-//      sort_local_kernel     CTA b sorts bucket b in shared memory: counting sort on the next <= 12
-//                            key bits, then every element ranks itself inside its (tiny) bin by
-//                            (key >> lo, index); keys, permutation and the gathered {x,y,z,m} records
-//                            go straight to their final places.
+//                            fixed-capacity buckets: bucket = number of splitters <= key >> lo, the
+//                            splitters being the 1/256 quantiles of the PREVIOUS evaluation's sorted
+//                            keys (splitter_kernel) - bodies move little per step, so the buckets
+//                            stay balanced whatever the distribution.  Any non-decreasing splitters
+//                            keep the result exact; stale ones only unbalance the buckets.
+//                            (per-CTA counts in shared memory, one global atomic per CTA and bucket)
+//      sort_local_kernel     CTA b sorts bucket b in shared memory: counting sort on <= 12 bits of
+//                            (key >> lo) - bucket base, then every element ranks itself inside its
+//                            (tiny) bin by (key >> lo, index); keys, permutation and the gathered
+//                            {x,y,z,m} records go straight to their final places.
 //      A bucket above capacity or a bin above LOCAL_BIN_LIMIT leaves the build flagged `bad`; the
 //      host re-runs it with the global passes.
 // HBM per body: 32 R + 12 W, then 12 R + 12 W + 32 R + 32 W.
@@ -388,14 +383,17 @@ constexpr unsigned LOCAL_SKEWED = 0x7fffffffu;  // published as "largest bucket"
 template <int DIM>
 __global__ void __launch_bounds__(256) encode_bucket_kernel(const double4* __restrict__ pos, size_t n,
                                                             const unsigned long long* __restrict__ extent_bits,
-                                                            uint64_t* __restrict__ bkey, uint32_t* __restrict__ bidx,
-                                                            unsigned cap, unsigned* __restrict__ cursor /*[256]*/) {
+                                                            const uint64_t* __restrict__ splitters /*[256]*/,
+                                                            int lo, uint64_t* __restrict__ bkey,
+                                                            uint32_t* __restrict__ bidx, unsigned cap,
+                                                            unsigned* __restrict__ cursor /*[256]*/) {
   constexpr int LM = TreeDim<DIM>::LM;
-  constexpr int TOP_SHIFT = DIM * LM - 8;
   __shared__ unsigned cnt[256];
   __shared__ unsigned gbase[256];
+  __shared__ uint64_t spl[256];
   const int tid = threadIdx.x;
   cnt[tid] = 0u;
+  spl[tid] = tid ? (splitters[tid] >> lo) : 0ull;
   __syncthreads();
   const double ext0 = __longlong_as_double(static_cast<long long>(*extent_bits));
   const size_t tile = size_t(blockIdx.x) * (256 * ENC_ITEMS);
@@ -427,11 +425,18 @@ __global__ void __launch_bounds__(256) encode_bucket_kernel(const double4* __res
       k[e] = (k[e] << DIM) | digit;
     }
   }
-  unsigned r[ENC_ITEMS];
+  unsigned r[ENC_ITEMS], d[ENC_ITEMS];
 #pragma unroll
   for (int e = 0; e < ENC_ITEMS; ++e) {
+    // bucket = number of splitters <= key >> lo, minus one (spl[0] = 0): 8-step search, no divergence
+    const uint64_t kk = k[e] >> lo;
+    unsigned b = 0;
+#pragma unroll
+    for (int step = 128; step > 0; step >>= 1)
+      if (spl[b + step] <= kk) b += step;
+    d[e] = b;
     const size_t i = tile + size_t(e) * 256 + tid;
-    r[e] = i < n ? atomicAdd(&cnt[unsigned(k[e] >> TOP_SHIFT)], 1u) : 0u;
+    r[e] = i < n ? atomicAdd(&cnt[b], 1u) : 0u;
   }
   __syncthreads();
   {
@@ -443,11 +448,10 @@ __global__ void __launch_bounds__(256) encode_bucket_kernel(const double4* __res
   for (int e = 0; e < ENC_ITEMS; ++e) {
     const size_t i = tile + size_t(e) * 256 + tid;
     if (i < n) {
-      const unsigned d = unsigned(k[e] >> TOP_SHIFT);
-      const unsigned slot = gbase[d] + r[e];
+      const unsigned slot = gbase[d[e]] + r[e];
       if (slot < cap) {  // else: bucket over capacity, sort_local_kernel flags the build
-        bkey[size_t(d) * cap + slot] = k[e];
-        bidx[size_t(d) * cap + slot] = static_cast<uint32_t>(i);
+        bkey[size_t(d[e]) * cap + slot] = k[e];
+        bidx[size_t(d[e]) * cap + slot] = static_cast<uint32_t>(i);
       }
     }
   }
@@ -462,7 +466,8 @@ inline size_t sort_local_smem(unsigned cap) {
 template <int NT, int RITEMS>
 __global__ void __launch_bounds__(NT, 1024 / NT) sort_local_kernel(
     const uint64_t* __restrict__ bkey, const uint32_t* __restrict__ bidx, const unsigned* __restrict__ cursor,
-    unsigned cap, int lo, int key_bits, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
+    const uint64_t* __restrict__ splitters, unsigned cap, int lo, int key_bits, uint64_t* __restrict__ keys,
+    uint32_t* __restrict__ vals,
     const double4* __restrict__ pos, double4* __restrict__ spos, unsigned* __restrict__ bad,
     unsigned* __restrict__ stat_max) {
   static_assert(NT >= 256 && NT % 32 == 0 && (1 << LOCAL_BIN_BITS) % NT == 0, "scan layout");
@@ -488,11 +493,20 @@ __global__ void __launch_bounds__(NT, 1024 / NT) sort_local_kernel(
     if (tid == 0) *bad = 1u;
     return;
   }
-  // bins: the (up to) LOCAL_BIN_BITS key bits right below the bucket digit, never below `lo`
-  const int below = key_bits - 8 - lo;  // sorted bits left after the bucket digit (>= 0)
-  const int nb = below < LOCAL_BIN_BITS ? below : LOCAL_BIN_BITS;
-  const int bshift = key_bits - 8 - nb;
-  const unsigned bmask = (1u << nb) - 1u;
+  // bins: (key >> lo) - bucket base, scaled so that the bucket's key range at the previous evaluation
+  // covers the bins, clamped at both ends (the first and the last bucket are open-ended, and keys
+  // drift): any non-decreasing map keeps the result exact
+  const uint64_t kbase = splitters[blockIdx.x] >> lo;
+  const uint64_t ktop = ((splitters[blockIdx.x + 1u] - 1ull) >> lo) + 1ull;  // splitters[256] = largest key + 1
+  const uint64_t span = ktop > kbase ? ktop - kbase : 1ull;
+  const int span_bits = 64 - __clzll(static_cast<long long>(span - 1ull) | 1ll);
+  const int bshift = span_bits > LOCAL_BIN_BITS ? span_bits - LOCAL_BIN_BITS : 0;
+  constexpr uint64_t bmax = (1u << LOCAL_BIN_BITS) - 1u;
+  auto bin_of = [&](uint64_t key) {
+    const uint64_t kk = key >> lo;
+    const uint64_t rel = kk > kbase ? (kk - kbase) >> bshift : 0ull;
+    return unsigned(rel < bmax ? rel : bmax);
+  };
   for (int j = tid; j < NBINS; j += NT) bins[j] = 0u;
   const uint64_t* gk = bkey + size_t(blockIdx.x) * cap;
   const uint32_t* gv = bidx + size_t(blockIdx.x) * cap;
@@ -508,9 +522,8 @@ __global__ void __launch_bounds__(NT, 1024 / NT) sort_local_kernel(
   __syncthreads();
 #pragma unroll
   for (int i = 0; i < RITEMS; ++i)
-    if (unsigned(i) * NT + tid < cnt) atomicAdd(&bins[unsigned(k[i] >> bshift) & bmask], 1u);
-  for (unsigned p = unsigned(RITEMS) * NT + tid; p < cnt; p += NT)
-    atomicAdd(&bins[unsigned(gk[p] >> bshift) & bmask], 1u);
+    if (unsigned(i) * NT + tid < cnt) atomicAdd(&bins[bin_of(k[i])], 1u);
+  for (unsigned p = unsigned(RITEMS) * NT + tid; p < cnt; p += NT) atomicAdd(&bins[bin_of(gk[p])], 1u);
   __syncthreads();
   {  // exclusive scan of the bin counts (BPT consecutive bins per thread) + the largest bin
     unsigned c[BPT], sum = 0, mx = 0;
@@ -540,14 +553,14 @@ __global__ void __launch_bounds__(NT, 1024 / NT) sort_local_kernel(
 #pragma unroll
   for (int i = 0; i < RITEMS; ++i) {
     if (unsigned(i) * NT + tid < cnt) {
-      const unsigned slot = atomicAdd(&bins[unsigned(k[i] >> bshift) & bmask], 1u);
+      const unsigned slot = atomicAdd(&bins[bin_of(k[i])], 1u);
       ks[slot] = k[i];
       vs[slot] = v[i];
     }
   }
   for (unsigned p = unsigned(RITEMS) * NT + tid; p < cnt; p += NT) {
     const uint64_t key = gk[p];
-    const unsigned slot = atomicAdd(&bins[unsigned(key >> bshift) & bmask], 1u);
+    const unsigned slot = atomicAdd(&bins[bin_of(key)], 1u);
     ks[slot] = key;
     vs[slot] = gv[p];
   }
@@ -556,7 +569,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) sort_local_kernel(
   for (unsigned p = tid; p < cnt; p += NT) {
     const uint64_t key = ks[p];
     const uint32_t id = vs[p];
-    const unsigned bin = unsigned(key >> bshift) & bmask;
+    const unsigned bin = bin_of(key);
     const unsigned s = bin ? bins[bin - 1u] : 0u, e = bins[bin];
     const uint64_t kme = key >> lo;
     unsigned rank = 0;
@@ -569,6 +582,30 @@ __global__ void __launch_bounds__(NT, 1024 / NT) sort_local_kernel(
     vals[dst] = id;
     spos[dst] = pos[id];
   }
+}
+
+// splitters for the NEXT evaluation's bucket sort: out[0] = smallest key, out[1..255] = the 1/256
+// quantiles of the sorted keys, out[256] = largest key + 1; forced non-decreasing (whatever the
+// state of `sorted`, e.g. after a build that was abandoned)
+constexpr int SPLITTER_STRIDE = 264;  // u64 words per splitter set (257 used)
+
+__global__ void __launch_bounds__(256) splitter_kernel(const uint64_t* __restrict__ sorted, size_t n,
+                                                       uint64_t* __restrict__ out /*[257]*/) {
+  __shared__ uint64_t v[257];
+  const int t = threadIdx.x;
+  v[t] = n ? sorted[(size_t(t) * n) >> 8] : 0ull;
+  if (t == 0) v[256] = n ? sorted[n - 1] + 1ull : 0ull;
+  __syncthreads();
+  if (t == 0) {
+    uint64_t run = 0;
+    for (int j = 0; j <= 256; ++j) {
+      run = v[j] > run ? v[j] : run;
+      v[j] = run;
+    }
+  }
+  __syncthreads();
+  out[t] = v[t];
+  if (t == 0) out[256] = v[256];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1564,7 +1601,7 @@ cudaError_t sort_prepare(GravityWorkspace& ws, size_t n, int key_bits, int lo, i
   sb->cap = LOCAL_CAP[mode];
   sb->plan = even_plan(lo, mode == 0 ? key_bits - lo : 0);
   const SortPlan& plan = sb->plan;
-  // [ghist: 9 x 256 (bucket modes: slot 0 = bucket cursors)][tile counters: 8][error flag + pad: 8]
+  // [ghist: 8 x 256 (bucket modes: slot 0 = bucket cursors)][tile counters: 8][error flag + pad: 8]
   // [status: npass x tiles x 256]
   const size_t head_words = SORT_HIST_SLOTS * 256 + SORT_MAX_PASSES + 8;
   const size_t words = head_words + size_t(plan.npass) * sb->tiles * 256;
@@ -1580,6 +1617,10 @@ cudaError_t sort_prepare(GravityWorkspace& ws, size_t n, int key_bits, int lo, i
     PB_PASS(ws.bucket_key.ensure(size_t(256) * sb->cap * 8));
     PB_PASS(ws.bucket_idx.ensure(size_t(256) * sb->cap * 4));
   }
+  if (!ws.splitters.p) {
+    PB_PASS(ws.splitters.ensure(2 * SPLITTER_STRIDE * 8));
+    PB_CUDA(cudaMemsetAsync(ws.splitters.p, 0, 2 * SPLITTER_STRIDE * 8, st));
+  }
   return cudaSuccess;
 }
 
@@ -1592,32 +1633,37 @@ cudaError_t encode_and_sort(GravityWorkspace& ws, size_t n, const SortBuffers& s
   uint32_t* v[2] = {ws.idx0.as<uint32_t>(), ws.idx1.as<uint32_t>()};
   unsigned* stat_max = ws.sticky.as<unsigned>() + 3;
   const unsigned nb = blocks_for(n, 256);
+  // splitters: read the set the previous evaluation left, write the other one
+  const uint64_t* spl_in = ws.splitters.as<uint64_t>() + SPLITTER_STRIDE * ws.splitter_cur;
+  uint64_t* spl_out = ws.splitters.as<uint64_t>() + SPLITTER_STRIDE * (ws.splitter_cur ^ 1);
+  ws.splitter_cur ^= 1;
   if (sb.mode != 0) {
     PB_LAUNCH(ls, st, "encode_bucket_kernel",
               encode_bucket_kernel<DIM><<<blocks_for(n, 256 * ENC_ITEMS), 256, 0, st>>>(
-                  ws.pos64, n, ws.extent_bits.as<unsigned long long>(), ws.bucket_key.as<uint64_t>(),
+                  ws.pos64, n, ws.extent_bits.as<unsigned long long>(), spl_in, sb.lo, ws.bucket_key.as<uint64_t>(),
                   ws.bucket_idx.as<uint32_t>(), sb.cap, sb.ghist));
     const size_t smem = sort_local_smem(sb.cap);
     if (sb.mode == 1) {
       PB_CUDA(cudaFuncSetAttribute(sort_local_kernel<512, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
       PB_LAUNCH(ls, st, "sort_local_kernel",
                 sort_local_kernel<512, 9><<<256, 512, smem, st>>>(
-                    ws.bucket_key.as<uint64_t>(), ws.bucket_idx.as<uint32_t>(), sb.ghist, sb.cap, sb.lo, sb.key_bits,
-                    k[0], v[0], ws.pos64, ws.spos64.as<double4>(), bad, stat_max));
+                    ws.bucket_key.as<uint64_t>(), ws.bucket_idx.as<uint32_t>(), sb.ghist, spl_in, sb.cap, sb.lo,
+                    sb.key_bits, k[0], v[0], ws.pos64, ws.spos64.as<double4>(), bad, stat_max));
     } else {
       PB_CUDA(cudaFuncSetAttribute(sort_local_kernel<1024, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
       PB_LAUNCH(ls, st, "sort_local_kernel",
                 sort_local_kernel<1024, 8><<<256, 1024, smem, st>>>(
-                    ws.bucket_key.as<uint64_t>(), ws.bucket_idx.as<uint32_t>(), sb.ghist, sb.cap, sb.lo, sb.key_bits,
-                    k[0], v[0], ws.pos64, ws.spos64.as<double4>(), bad, stat_max));
+                    ws.bucket_key.as<uint64_t>(), ws.bucket_idx.as<uint32_t>(), sb.ghist, spl_in, sb.cap, sb.lo,
+                    sb.key_bits, k[0], v[0], ws.pos64, ws.spos64.as<double4>(), bad, stat_max));
     }
     ws.sorted_key = k[0];
     ws.perm = v[0];
+    PB_LAUNCH(ls, st, "splitter_kernel", splitter_kernel<<<1, 256, 0, st>>>(ws.sorted_key, n, spl_out));
     return cudaGetLastError();
   }
   PB_LAUNCH(ls, st, "encode_kernel",
             encode_kernel<DIM><<<min(nb, 148u * 4u), 256, 0, st>>>(
-                ws.pos64, n, ws.extent_bits.as<unsigned long long>(), k[0], v[0], sb.plan, sb.key_bits - 8, sb.ghist));
+                ws.pos64, n, ws.extent_bits.as<unsigned long long>(), k[0], v[0], sb.plan, sb.ghist));
   // 48 KB of dynamic + 10 KB of static shared memory for the 16-keys-per-thread tile: opt in
   // (per device, so per call: the handle may live on any device)
   if (sb.items == 16)
@@ -1626,24 +1672,21 @@ cudaError_t encode_and_sort(GravityWorkspace& ws, size_t n, const SortBuffers& s
   int cur = 0;
   for (int p = 0; p < sb.plan.npass; ++p) {
     const size_t smem = size_t(SORT_THREADS) * sb.items * 12;  // digit-sorted tile: u64 keys + u32 values
-    // pass 0 also publishes the largest bin of the top-8-bit histogram (encode_kernel's slot 8)
-    const unsigned* stat_hist = p != 0 ? nullptr : sb.ghist + (SORT_HIST_SLOTS - 1) * 256;
     if (sb.items == 8)
       PB_LAUNCH(ls, st, "sort_onesweep_pass",
                 sort_onesweep_pass<8><<<sb.tiles, SORT_THREADS, smem, st>>>(
                     k[cur], v[cur], k[cur ^ 1], v[cur ^ 1], n, sb.plan.shift(p), sb.plan.mask(p),
-                    sb.ghist + p * 256, sb.status + size_t(p) * sb.tiles * 256, sb.counters + p, sb.err_flag,
-                    stat_hist, stat_max));
+                    sb.ghist + p * 256, sb.status + size_t(p) * sb.tiles * 256, sb.counters + p, sb.err_flag));
     else
       PB_LAUNCH(ls, st, "sort_onesweep_pass",
                 sort_onesweep_pass<16><<<sb.tiles, SORT_THREADS, smem, st>>>(
                     k[cur], v[cur], k[cur ^ 1], v[cur ^ 1], n, sb.plan.shift(p), sb.plan.mask(p),
-                    sb.ghist + p * 256, sb.status + size_t(p) * sb.tiles * 256, sb.counters + p, sb.err_flag,
-                    stat_hist, stat_max));
+                    sb.ghist + p * 256, sb.status + size_t(p) * sb.tiles * 256, sb.counters + p, sb.err_flag));
     cur ^= 1;
   }
   ws.sorted_key = k[cur];
   ws.perm = v[cur];
+  PB_LAUNCH(ls, st, "splitter_kernel", splitter_kernel<<<1, 256, 0, st>>>(ws.sorted_key, n, spl_out));
   PB_LAUNCH(ls, st, "gather_kernel", gather_kernel<<<nb, 256, 0, st>>>(ws.pos64, ws.perm, n, ws.spos64.as<double4>()));
   return cudaGetLastError();
 }
@@ -1796,7 +1839,7 @@ cudaError_t direct_evaluate(GravityWorkspace& ws, size_t t0, size_t t1, float ea
 }  // namespace
 
 void GravityWorkspace::release_all() {
-  DevBuf* all[] = {&src4, &key0, &key1, &idx0, &idx1, &bucket_key, &bucket_idx, &nsv1, &nsv2, &spos64, &ab, &cell_start, &scan_tmp,
+  DevBuf* all[] = {&src4, &key0, &key1, &idx0, &idx1, &bucket_key, &bucket_idx, &splitters, &nsv1, &nsv2, &spos64, &ab, &cell_start, &scan_tmp,
                    &tile_counts, &digit_base, &extent_bits, &tgt_list, &tgt_flags, &c_level, &c_head,
                    &c_count, &c_skip, &c_parent, &c_arrived, &c_centre_ext, &c_com, &acc, &acc_part, &sticky,
                    &counters};
@@ -1869,13 +1912,23 @@ cudaError_t gravity_check(GravityWorkspace& ws, cudaStream_t st, TreeCheck* out)
   ws.last_max_bucket = h[3];
   out->bucket_overflow = ws.last_mode != 0 && h[3] > LOCAL_CAP[ws.last_mode];
   static const char* mode_env = std::getenv("PB200_SORT_MODE");  // "lsd": global passes only (A/B runs)
-  if (h[3] >= LOCAL_SKEWED) ws.bucket_ban = 64;  // bodies too alike inside a bucket: global passes for a while
+  if (h[3] >= LOCAL_SKEWED || out->bucket_overflow) ws.bucket_ban = 16;  // global passes for a while
   else if (ws.bucket_ban > 0) --ws.bucket_ban;
-  if ((mode_env && !std::strcmp(mode_env, "lsd")) || ws.bucket_ban > 0) ws.sort_mode = 0;
-  else if (h[3] + h[3] / 32 <= LOCAL_CAP[1]) ws.sort_mode = 1;
-  else if (h[3] + h[3] / 32 <= LOCAL_CAP[2]) ws.sort_mode = 2;
-  else if (h[3] + h[3] / 32 <= LOCAL_CAP[3]) ws.sort_mode = 3;
+  // the splitters left by a verified build balance the buckets at ~n/256 bodies: pick the smallest
+  // capacity with ~12 % headroom (bodies drift between evaluations)
+  const size_t want = ws.n / 256 + ws.n / 2048 + 64;
+  if ((mode_env && !std::strcmp(mode_env, "lsd")) || ws.bucket_ban > 0 || out->overflow || out->sort_short || out->sort_error)
+    ws.sort_mode = 0;
+  else if (want <= LOCAL_CAP[1]) ws.sort_mode = 1;
+  else if (want <= LOCAL_CAP[2]) ws.sort_mode = 2;
+  else if (want <= LOCAL_CAP[3]) ws.sort_mode = 3;
   else ws.sort_mode = 0;
+  static const bool debug_check = std::getenv("PB200_DEBUG_CHECK") != nullptr;
+  if (debug_check)
+    std::fprintf(stderr, "[physim_b200] check: cells %u (cap %zu) deepest %d lo %d mode %d max_bucket %u overflow %d short %d "
+                 "sort_error %d bucket_overflow %d ban %d -> next mode %d\n", h[0], ws.cell_cap, out->deepest_shared,
+                 ws.last_lo, ws.last_mode, h[3], int(out->overflow), int(out->sort_short), int(out->sort_error),
+                 int(out->bucket_overflow), ws.bucket_ban, ws.sort_mode);
   ws.n_cells = h[0];
   ws.last_total = h[0];
   ws.last_deepest = out->deepest_shared;

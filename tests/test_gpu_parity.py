@@ -229,12 +229,15 @@ def test_bucket_local_sort_matches_global_sort(name):
 
 
 @pytest.mark.parametrize("name", ["astro2", "astro"])
-def test_bucket_local_sort_overflow_falls_back(name):
-    """A clustered set puts more bodies into one top-8-bit bin than a tile holds: the bucket-local
-    kernel flags it, the build is skipped on the device, and the host re-runs with global passes."""
-    s = plummer_like(30_000, 17)
-    o = ob.CellTable(DIM[name], s)
+def test_bucket_sort_overflow_and_skew_fall_back(name):
+    """The buckets are cut at the previous evaluation's key quantiles.  A different body set on the
+    same object makes them stale: one bucket overflows its tile, the kernel flags the build, the
+    device skips it and the host re-runs with global passes.  Likewise when more bodies than a bin
+    may hold agree on every sorted key bit."""
     el = api.TransformElement(name, theta=1.0, e=0.05)
+    el.transform(gen.cube(30_000, seed=2))                   # splitters of a uniform cube
+    s = plummer_like(30_000, 17)                             # concentrated far off-centre
+    o = ob.CellTable(DIM[name], s)
     for forced in (1, 2):
         el.debug_sort_mode(forced)
         acc = el.transform(s)
@@ -243,8 +246,21 @@ def test_bucket_local_sort_overflow_falls_back(name):
         for k in TREE_KEYS:
             assert np.array_equal(t[k], getattr(o, k)), (k, forced)
         assert_acc_parity(acc, ob.transform(name, s, 1.0, 0.05))
-        if st["max_bucket"] > (4608 if forced == 1 else 8192):
-            assert st["sort_mode"] != forced, st             # it did fall back
+        if forced == 1:
+            assert st["sort_mode"] == 0, st                                 # it did fall back
+        el.transform(gen.cube(30_000, seed=2))
+    # 100 bodies on one spot (one key): a bin of the counting sort would hold them all
+    twins = gen.cube(20_000, seed=8)
+    twins["x"][:100], twins["y"][:100], twins["z"][:100] = 0.3, -0.2, 0.6
+    o = ob.CellTable(DIM[name], twins)
+    el = api.TransformElement(name, theta=1.0, e=0.5)
+    el.transform(twins)
+    acc = el.transform(twins)                                # bucket sort attempted, abandoned
+    t = el.debug_tree()
+    for k in TREE_KEYS:
+        assert np.array_equal(t[k], getattr(o, k)), k
+    assert el.stats()["sort_mode"] == 0
+    assert_acc_parity(acc, ob.transform(name, twins, 1.0, 0.5))
 
 
 def plummer_like(n, seed):
