@@ -12,6 +12,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
+#include <string>
 
 #include "common.cuh"
 
@@ -914,15 +916,216 @@ __device__ __forceinline__ size_t nsv_next_le(const NsvTables& tv, size_t j0, un
   return nsv_descend(tv.t1, tv.n_pad, lo, min(tv.n, lo + 256), l);
 }
 
-// K6  one thread per unit head s, for the chain of cells it heads (levels a+1 .. leaf level):
-//     pass 1, top -> leaf: level, head, geometric centre / half-width (replaying the head's key digits);
-//     pass 2, leaf -> top: the end of each cell's run of bodies (nsv_next_le, continuing from the end
-//     of the cell below), hence body count and skip link, and - while the cell holds <= SMALL_CELL
-//     bodies - mass / centre of mass as ONE running sum over the bodies in order, emitted at every
-//     level (each body is read once per chain, and the sums equal a per-cell sum in body order).
-//     Larger cells are left to the bottom-up pass (K7).
+// first byte at or after `off` of the 16 in w that is <= l (splat = l in every byte), else 16
+__device__ __forceinline__ int first_le_16(const uint4& w, unsigned splat, int off) {
+  const unsigned m[4] = {__vcmpleu4(w.x, splat), __vcmpleu4(w.y, splat), __vcmpleu4(w.z, splat),
+                         __vcmpleu4(w.w, splat)};
+  int pos = 16;
+#pragma unroll
+  for (int q = 3; q >= 0; --q) {
+    unsigned mm = m[q];
+    const int skip = off - 4 * q;
+    if (skip >= 4) mm = 0u;
+    else if (skip > 0) mm &= 0xffffffffu << (8 * skip);
+    if (mm) pos = 4 * q + ((__ffs(mm) - 1) >> 3);
+  }
+  return pos;
+}
+
+// The same query in at most three rounds of INDEPENDENT loads for runs of up to 288 bodies (the table
+// descent is 9 dependent byte loads per level of the hierarchy, and nearly every warp holds one cell
+// that needs it): (1) the level-0 bytes of the 17..32 bodies from j0 on, two 16-byte loads; (2) the
+// level-4 minima (16 bodies each) of the next 16 aligned windows; (3) the level-0 bytes of the first
+// window that holds a hit.  Longer runs continue with the table descent from where the scan stopped.
+__device__ __forceinline__ size_t nsv_next_le_short(const NsvTables& tv, size_t j0, unsigned l) {
+  if (j0 + 32 > tv.n_pad) return nsv_next_le(tv, j0, l);  // (the 32-byte window would leave level 0)
+  const size_t base = j0 & ~size_t(15);
+  const uint4 w0 = *reinterpret_cast<const uint4*>(tv.t1 + base);
+  const uint4 w1 = *reinterpret_cast<const uint4*>(tv.t1 + base + 16);
+  const unsigned splat = l * 0x01010101u;
+  // (bytes of bodies past n are NSV_NONE and never match, so a hit is always < n)
+  int pos = first_le_16(w0, splat, int(j0 - base));
+  if (pos < 16) return base + size_t(pos);
+  pos = first_le_16(w1, splat, 0);
+  if (pos < 16) return base + 16 + size_t(pos);
+  const size_t j1 = base + 32;
+  const uint8_t* __restrict__ t4 = tv.t1 + 4 * tv.n_pad;  // min a1[j .. j+16): aligned windows never leave their block
+  int hit = 16;
+#pragma unroll
+  for (int i = 15; i >= 0; --i) {
+    const size_t idx = j1 + 16 * size_t(i);
+    const unsigned v = idx < tv.n_pad ? unsigned(t4[idx]) : unsigned(NSV_NONE);
+    if (v <= l) hit = i;
+  }
+  if (hit < 16) {
+    const size_t jw = j1 + 16 * size_t(hit);
+    const uint4 w = *reinterpret_cast<const uint4*>(tv.t1 + jw);
+    return jw + size_t(first_le_16(w, splat, 0));
+  }
+  return nsv_next_le(tv, j1 + 256, l);
+}
+
+// K6  one thread per unit head s, for the chain of cells it heads (levels a+1 .. leaf level).
+//     Phase 1 (per lane, its own chain): one replay of the head's key digits from the root to its leaf,
+//     writing level, head, geometric centre / half-width of every cell of the chain on the way, then the
+//     leaf (the unit itself).
+//     Phase 2: the INTERNAL cells of the warp's 32 chains (0 for most lanes, several for a few) are dealt
+//     out evenly to the lanes - a prefix sum over the per-lane counts and a 5-step search by shuffles name
+//     the owner of task t - so every lane runs one range-minimum query (the end of the cell's run of
+//     bodies: first later body that starts a cell at a level <= its own), hence body count and skip link,
+//     and - for cells of <= SMALL_CELL bodies - the mass / centre of mass as a sum over its units in
+//     body order.  Larger cells are left to the bottom-up pass (K7).
+//     (cells_kernel_chain below is the earlier per-lane form: each lane loops over its own chain, the
+//     ends found leaf -> top and one running sum per chain; same results, ~10 of 32 lanes busy.)
 template <int DIM>
 __global__ void __launch_bounds__(256) cells_kernel(const uint64_t* __restrict__ key,
+                                                    const double4* __restrict__ sp,
+                                                    const uint32_t* __restrict__ perm,
+                                                    const uchar2* __restrict__ ab,
+                                                    const uint32_t* __restrict__ cell_start, size_t n,
+                                                    const unsigned long long* __restrict__ extent_bits,
+                                                    const unsigned* __restrict__ tree_meta,
+                                                    unsigned* __restrict__ sticky, NsvTables tv, CellArrays cells) {
+  constexpr int LM = TreeDim<DIM>::LM;
+  const size_t s = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  const unsigned lane = threadIdx.x & 31u;
+  const uint32_t total = cell_start[n];
+  if (s == 0) {
+    // worst case over every build since the last host check (builds run unverified in between):
+    // [0] cells needed, [1] 1 + deepest level shared by distinct neighbouring keys
+    atomicMax(&sticky[0], total);
+    atomicMax(&sticky[1], tree_meta[0]);
+  }
+  if (total > cells.capacity || *cells.bad) return;  // host grows the table / sorts all bits and re-runs (grid-uniform)
+  const uchar2 abv = s < n ? ab[s] : make_uchar2(NOT_HEAD, NOT_HEAD);
+  const bool is_head = abv.x != NOT_HEAD;  // (lanes past n and merged bodies stay for the shuffles)
+  int top = 0, leaf_level = 0;
+  uint32_t c0 = 0;
+  if (is_head) {
+    c0 = cell_start[s];
+    if (s == 0) cells.parent[0] = NO_PARENT;
+    const int a = int(abv.x) - 1, b = int(abv.y) - 1;
+    top = a + 1;
+    leaf_level = max(a, b) + 1;
+    const uint64_t kme = key[s];
+    const double4 me = sp[s];
+    double half = __longlong_as_double(static_cast<long long>(*extent_bits));
+    double cx = 0.0, cy = 0.0, cz = 0.0;
+    for (int l = 0; l <= leaf_level; ++l) {
+      if (l >= top) {
+        const uint32_t c = c0 + uint32_t(l - top);
+        cells.level[c] = static_cast<uint8_t>(l);
+        cells.head[c] = static_cast<uint32_t>(s);
+        cells.arrived[c] = 0u;
+        cells.centre_ext[c] = make_double4(cx, cy, cz, half);
+      }
+      if (l < leaf_level) {  // from level l to level l+1 along the head body's path
+        unsigned digit;
+        if (l < LM) {
+          digit = unsigned((kme >> (DIM * (LM - 1 - l))) & ((1u << DIM) - 1u));
+        } else {  // pseudo level below the key: compare the head body itself
+          digit = unsigned(me.x > cx) | (unsigned(me.y > cy) << 1);
+          if (DIM == 3) digit |= unsigned(me.z > cz) << 2;
+        }
+        half *= 0.5;
+        cx += with_sign(half, !(digit & 1u));
+        cy += with_sign(half, !(digit & 2u));
+        if (DIM == 3) cz += with_sign(half, !(digit & 4u));
+      }
+    }
+    // leaf: the unit itself
+    size_t e = s + 1;
+    while (e < n && ab[e].x == NOT_HEAD) ++e;
+    const uint32_t c = c0 + uint32_t(leaf_level - top);
+    cells.count[c] = static_cast<uint32_t>(e - s);
+    cells.skip[c] = cell_start[e];
+    cells.com[c] = unit_leaf(sp, perm, s, e);
+  }
+
+  // phase 2: task t of the warp = internal cell number (t - excl[o]) of the chain of lane o
+  const int mine = is_head ? leaf_level - top : 0;
+  int incl = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int v = __shfl_up_sync(FULL, incl, d);
+    if (int(lane) >= d) incl += v;
+  }
+  const int n_tasks = __shfl_sync(FULL, incl, 31);
+  const int excl = incl - mine;
+  const bool merged_units = tree_meta[1] != 0u;
+  for (int t0 = 0; t0 < n_tasks; t0 += 32) {
+    const int t = t0 + int(lane);
+    int o = 0;  // number of lanes whose inclusive count is <= t  ==  the lane that owns task t
+#pragma unroll
+    for (int step = 16; step > 0; step >>= 1) {
+      const int probe = __shfl_sync(FULL, incl, o + step - 1);
+      if (probe <= t) o += step;
+    }
+    const int k = t - __shfl_sync(FULL, excl, o);
+    const int lev = __shfl_sync(FULL, top, o) + k;  // internal levels top .. leaf_level-1
+    const uint32_t c = __shfl_sync(FULL, c0, o) + uint32_t(k);
+    if (t >= n_tasks) continue;
+    const size_t so = s - lane + size_t(o);  // the chain's head
+    const size_t e = nsv_next_le_short(tv, so + 1, unsigned(lev));
+    const uint32_t cnt = static_cast<uint32_t>(e - so);
+    cells.count[c] = cnt;
+    cells.skip[c] = cell_start[e];
+    if (cnt > cells.small) continue;
+    // the per-cell sums start from zero: 0 + m x == m x exactly, so starting from the first unit's products is the same
+    double sm, sx, sy, sz;
+    if (!merged_units) {  // no merged unit anywhere: plain sums over the run
+      const double4 q0 = sp[so];
+      sm = q0.w; sx = q0.w * q0.x; sy = q0.w * q0.y; sz = q0.w * q0.z;
+      double4 q = sp[min(so + 1, e - 1)];
+      for (size_t j = so + 1; j < e; ++j) {  // (the next body is fetched before this one is added)
+        const double4 nq = sp[min(j + 1, e - 1)];
+        sm += q.w; sx += q.w * q.x; sy += q.w * q.y; sz += q.w * q.z;
+        q = nq;
+      }
+    } else {
+      size_t j = so + 1;
+      while (j < e && ab[j].x == NOT_HEAD) ++j;
+      const double4 q0 = unit_leaf(sp, perm, so, j);
+      sm = q0.w; sx = q0.w * q0.x; sy = q0.w * q0.y; sz = q0.w * q0.z;
+      while (j < e) {  // units in order
+        size_t je = j + 1;
+        while (je < e && ab[je].x == NOT_HEAD) ++je;
+        const double4 q = unit_leaf(sp, perm, j, je);
+        sm += q.w; sx += q.w * q.x; sy += q.w * q.y; sz += q.w * q.z;
+        j = je;
+      }
+    }
+    // a massless cell (the reference panics there): geometric centre instead of 0/0
+    const double inv = 1.0 / sm;  // one division: the reference's own (…) * inv_total_mass form (lib.rs:43-49)
+    if (sm != 0.0) {
+      cells.com[c] = make_double4(sx * inv, sy * inv, sz * inv, sm);
+    } else {
+      // (written by another lane in phase 1: recompute instead of reading it back)
+      double half = __longlong_as_double(static_cast<long long>(*extent_bits));
+      double gx = 0.0, gy = 0.0, gz = 0.0;
+      const uint64_t ko = key[so];
+      const double4 mo = sp[so];
+      for (int l = 0; l < lev; ++l) {
+        unsigned digit;
+        if (l < LM) {
+          digit = unsigned((ko >> (DIM * (LM - 1 - l))) & ((1u << DIM) - 1u));
+        } else {
+          digit = unsigned(mo.x > gx) | (unsigned(mo.y > gy) << 1);
+          if (DIM == 3) digit |= unsigned(mo.z > gz) << 2;
+        }
+        half *= 0.5;
+        gx += with_sign(half, !(digit & 1u));
+        gy += with_sign(half, !(digit & 2u));
+        if (DIM == 3) gz += with_sign(half, !(digit & 4u));
+      }
+      cells.com[c] = make_double4(gx, gy, gz, 0.0);
+    }
+  }
+}
+
+// K6 (earlier form, kept for A/B runs: PB200_CELLS=chain)
+template <int DIM>
+__global__ void __launch_bounds__(256) cells_kernel_chain(const uint64_t* __restrict__ key,
                                                     const double4* __restrict__ sp,
                                                     const uint32_t* __restrict__ perm,
                                                     const uchar2* __restrict__ ab,
@@ -1750,17 +1953,28 @@ cudaError_t tree_evaluate(GravityWorkspace& ws, const GravityParams& prm, size_t
   PB_PASS(ws.c_arrived.ensure(cap * 4));
   PB_PASS(ws.c_centre_ext.ensure(cap * sizeof(double4)));
   PB_PASS(ws.c_com.ensure(cap * sizeof(double4)));
+  static const uint32_t small_cell =
+      std::getenv("PB200_SMALL_CELL") ? uint32_t(std::atoi(std::getenv("PB200_SMALL_CELL"))) : SMALL_CELL;  // (tuning runs)
   CellArrays cells{ws.c_level.as<uint8_t>(),   ws.c_head.as<uint32_t>(),  ws.c_count.as<uint32_t>(),
                    ws.c_skip.as<uint32_t>(),   ws.c_parent.as<uint32_t>(), ws.c_arrived.as<uint32_t>(),
-                   ws.c_centre_ext.as<double4>(), ws.c_com.as<double4>(), static_cast<uint32_t>(cap), SMALL_CELL,
+                   ws.c_centre_ext.as<double4>(), ws.c_com.as<double4>(), static_cast<uint32_t>(cap), small_cell,
                    max_shared_plus1 + 2};
   const unsigned nb128 = blocks_for(n, 128);
   const NsvTables tv{ws.nsv1.as<uint8_t>(), n_pad, ws.nsv2.as<uint8_t>(), b_pad, nsv3, n, nblocks, nsuper};
-  PB_LAUNCH(ls, st, "cells_kernel",
-            cells_kernel<DIM><<<nb, 256, 0, st>>>(ws.sorted_key, ws.spos64.as<double4>(), ws.perm,
-                                                  ws.ab.as<uchar2>(), ws.cell_start.as<uint32_t>(), n,
-                                                  ws.extent_bits.as<unsigned long long>(), max_shared_plus1,
-                                                  ws.sticky.as<unsigned>(), tv, cells));
+  static const bool cells_chain = std::getenv("PB200_CELLS") && std::string(std::getenv("PB200_CELLS")) == "chain";
+  if (cells_chain) {
+    PB_LAUNCH(ls, st, "cells_kernel_chain",
+              cells_kernel_chain<DIM><<<nb, 256, 0, st>>>(ws.sorted_key, ws.spos64.as<double4>(), ws.perm,
+                                                          ws.ab.as<uchar2>(), ws.cell_start.as<uint32_t>(), n,
+                                                          ws.extent_bits.as<unsigned long long>(), max_shared_plus1,
+                                                          ws.sticky.as<unsigned>(), tv, cells));
+  } else {
+    PB_LAUNCH(ls, st, "cells_kernel",
+              cells_kernel<DIM><<<nb, 256, 0, st>>>(ws.sorted_key, ws.spos64.as<double4>(), ws.perm,
+                                                    ws.ab.as<uchar2>(), ws.cell_start.as<uint32_t>(), n,
+                                                    ws.extent_bits.as<unsigned long long>(), max_shared_plus1,
+                                                    ws.sticky.as<unsigned>(), tv, cells));
+  }
   PB_LAUNCH(ls, st, "parent_kernel",
             parent_kernel<<<blocks_for(cap, 256), 256, 0, st>>>(ws.cell_start.as<uint32_t>(), n, cells));
   PB_LAUNCH(ls, st, "com_kernel", com_kernel<<<nb128, 128, 0, st>>>(ws.ab.as<uchar2>(), ws.cell_start.as<uint32_t>(), n, cells));
