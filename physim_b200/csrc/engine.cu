@@ -17,6 +17,10 @@
 #include <string>
 #include <vector>
 
+#include <atomic>
+#include <functional>
+#include <thread>
+
 #include "common.cuh"
 #include "host_pool.hpp"
 
@@ -51,7 +55,7 @@ struct GpuContext {
   cudaStream_t stream = nullptr;
   bool own_stream = true;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t chunk_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t chunk_ev[16] = {};
   cudaError_t init(int dev) {
     if (ready) return cudaSetDevice(device);
     int count = 0;
@@ -119,54 +123,160 @@ struct TransformObj {
 
 // pack Entity AoS -> pinned {x,y,z,m} (+ fixed bytes).  The staging buffer is written with
 // non-temporal stores: it is read next by the DMA engine, not by a core.
-void pack_positions(const Entity* state, size_t n, double4* pos, uint8_t* fixed) {
-  HostPool::instance().parallel_for(n, kParallelGrain, [&](size_t b, size_t e) {
-    for (size_t i = b; i < e; ++i) {
-      const Entity& s = state[i];
-      double* d = reinterpret_cast<double*>(pos + i);  // 32-byte aligned (pinned base, 32 B records)
-      _mm_stream_pd(d, _mm_set_pd(s.y, s.x));
-      _mm_stream_pd(d + 2, _mm_set_pd(s.mass, s.z));
-      if (fixed) fixed[i] = s.fixed ? 1 : 0;
-    }
-    _mm_sfence();
-  });
+inline void pack_positions_range(const Entity* state, size_t b, size_t e, double4* pos, uint8_t* fixed) {
+  for (size_t i = b; i < e; ++i) {
+    const Entity& s = state[i];
+    double* d = reinterpret_cast<double*>(pos + i);  // 32-byte aligned (pinned base, 32 B records)
+    _mm_stream_pd(d, _mm_set_pd(s.y, s.x));
+    _mm_stream_pd(d + 2, _mm_set_pd(s.mass, s.z));
+    if (fixed) fixed[i] = s.fixed ? 1 : 0;
+  }
 }
 
-void pack_velocities(const Entity* state, size_t n, double4* vel) {
-  HostPool::instance().parallel_for(n, kParallelGrain, [&](size_t b, size_t e) {
-    for (size_t i = b; i < e; ++i) {
-      double* d = reinterpret_cast<double*>(vel + i);
-      _mm_stream_pd(d, _mm_set_pd(state[i].vy, state[i].vx));
-      _mm_stream_pd(d + 2, _mm_set_pd(0.0, state[i].vz));
-    }
-    _mm_sfence();
-  });
+inline void pack_velocities_range(const Entity* state, size_t b, size_t e, double4* vel) {
+  for (size_t i = b; i < e; ++i) {
+    double* d = reinterpret_cast<double*>(vel + i);
+    _mm_stream_pd(d, _mm_set_pd(state[i].vy, state[i].vx));
+    _mm_stream_pd(d + 2, _mm_set_pd(0.0, state[i].vz));
+  }
 }
 
 // Chunking of the host<->device pipeline: packing chunk c+1 overlaps the H2D copy of chunk c, and
-// unpacking chunk c overlaps the D2H copy of chunk c+1.
-constexpr int kMaxChunks = 8;
-inline int chunk_count(size_t n) { return n >= (size_t(1) << 18) ? kMaxChunks : 1; }
+// unpacking chunk c overlaps the D2H copy of chunk c+1.  The pool is woken ONCE per direction: its
+// parts walk the chunks together, each doing its share of every chunk; part 0 (the calling thread, the
+// only one that talks to CUDA) enqueues the copy of a chunk when all shares of it are packed, and
+// publishes the arrival of a chunk for the parts that unpack it.  (One parallel_for per chunk costs
+// ~20 us of wake-up each; measured on the 16-core host, tools/scratch/host_pack_bench.cpp.)
+constexpr int kMaxChunks = 16;
+inline int env_int(const char* name, int dflt) {
+  const char* e = std::getenv(name);
+  return e ? std::atoi(e) : dflt;
+}
+inline int chunk_count(size_t n) {
+  static const int chunks = std::max(1, std::min(kMaxChunks, env_int("PB200_CHUNKS", 16)));  // (tuning runs)
+  return n >= (size_t(1) << 18) ? chunks : 1;
+}
+inline bool per_chunk_regions() {  // PB200_HOST_PIPE=perchunk: one parallel_for per chunk (A/B runs)
+  static const bool v = std::getenv("PB200_HOST_PIPE") && std::string(std::getenv("PB200_HOST_PIPE")) == "perchunk";
+  return v;
+}
 inline size_t chunk_begin(size_t n, int chunks, int c) { return n * size_t(c) / size_t(chunks); }
+inline void share_of(size_t b, size_t e, int part, int parts, size_t* sb, size_t* se) {
+  const size_t m = e - b;
+  *sb = b + m * size_t(part) / size_t(parts);
+  *se = b + m * size_t(part + 1) / size_t(parts);
+}
+inline void spin_until(const std::atomic<int>& a, int at_least) {
+  for (int spins = 0; a.load(std::memory_order_acquire) < at_least; ++spins) {
+    if (spins < 4096) _mm_pause();
+    else std::this_thread::yield();
+  }
+}
 
 // pack + enqueue the upload of positions (+ fixed flags, + velocities when d_vel != nullptr)
 cudaError_t upload_packed(const Entity* state, size_t n, double4* h_pos, uint8_t* h_fixed, double4* h_vel,
                           double4* d_pos, uint8_t* d_fixed, double4* d_vel, cudaStream_t st) {
   const int chunks = chunk_count(n);
-  for (int c = 0; c < chunks; ++c) {
-    const size_t b = chunk_begin(n, chunks, c), e = chunk_begin(n, chunks, c + 1), m = e - b;
-    if (!m) continue;
-    const double t_pack = now_ms();
-    pack_positions(state + b, m, h_pos + b, h_fixed ? h_fixed + b : nullptr);
-    g_pack_ms += now_ms() - t_pack;
-    PB_CUDA(cudaMemcpyAsync(d_pos + b, h_pos + b, m * sizeof(double4), cudaMemcpyHostToDevice, st));
-    if (h_fixed) PB_CUDA(cudaMemcpyAsync(d_fixed + b, h_fixed + b, m, cudaMemcpyHostToDevice, st));
-    if (d_vel) {
-      const double t_pv = now_ms();
-      pack_velocities(state + b, m, h_vel + b);
-      g_pack_ms += now_ms() - t_pv;
-      PB_CUDA(cudaMemcpyAsync(d_vel + b, h_vel + b, m * sizeof(double4), cudaMemcpyHostToDevice, st));
+  std::atomic<int> packed[kMaxChunks];
+  for (auto& a : packed) a.store(0, std::memory_order_relaxed);
+  std::atomic<int> failed{0};  // part 0 hit a CUDA error: the other parts stop packing
+  cudaError_t err = cudaSuccess;
+  const double t_pack = now_ms();
+  HostPool& pool = HostPool::instance();
+  if (per_chunk_regions()) {
+    for (int c = 0; c < chunks; ++c) {
+      const size_t b = chunk_begin(n, chunks, c), e = chunk_begin(n, chunks, c + 1);
+      if (e == b) continue;
+      pool.parallel_for(e - b, kParallelGrain, [&](size_t sb, size_t se) {
+        pack_positions_range(state, b + sb, b + se, h_pos, h_fixed);
+        if (d_vel) pack_velocities_range(state, b + sb, b + se, h_vel);
+        _mm_sfence();
+      });
+      PB_CUDA(cudaMemcpyAsync(d_pos + b, h_pos + b, (e - b) * sizeof(double4), cudaMemcpyHostToDevice, st));
+      if (d_vel) PB_CUDA(cudaMemcpyAsync(d_vel + b, h_vel + b, (e - b) * sizeof(double4), cudaMemcpyHostToDevice, st));
     }
+    g_pack_ms += now_ms() - t_pack;
+    if (h_fixed && n) PB_CUDA(cudaMemcpyAsync(d_fixed, h_fixed, n, cudaMemcpyHostToDevice, st));
+    return cudaSuccess;
+  }
+  pool.parallel_parts(pool.parts_for(n, kParallelGrain), [&](int part, int parts) {
+    for (int c = 0; c < chunks; ++c) {
+      const size_t b = chunk_begin(n, chunks, c), e = chunk_begin(n, chunks, c + 1);
+      if (failed.load(std::memory_order_relaxed)) return;
+      size_t sb, se;
+      share_of(b, e, part, parts, &sb, &se);
+      pack_positions_range(state, sb, se, h_pos, h_fixed);
+      if (d_vel) pack_velocities_range(state, sb, se, h_vel);
+      _mm_sfence();
+      packed[c].fetch_add(1, std::memory_order_release);
+      if (part != 0 || e == b) continue;
+      spin_until(packed[c], parts);
+      err = cudaMemcpyAsync(d_pos + b, h_pos + b, (e - b) * sizeof(double4), cudaMemcpyHostToDevice, st);
+      if (err == cudaSuccess && d_vel)
+        err = cudaMemcpyAsync(d_vel + b, h_vel + b, (e - b) * sizeof(double4), cudaMemcpyHostToDevice, st);
+      if (err != cudaSuccess) {
+        failed.store(1, std::memory_order_relaxed);
+        return;
+      }
+    }
+  });
+  g_pack_ms += now_ms() - t_pack;
+  if (err != cudaSuccess) {
+    set_error("CUDA error: %s (upload_packed)", cudaGetErrorString(err));
+    return err;
+  }
+  if (h_fixed && n) PB_CUDA(cudaMemcpyAsync(d_fixed, h_fixed, n, cudaMemcpyHostToDevice, st));
+  return cudaSuccess;
+}
+
+// D2H of `bytes_per_item`-byte records in chunks, fn(begin, end) applied to each chunk behind its copy
+// by all parts of the pool (see the note on chunking above)
+cudaError_t download_chunked(GpuContext& gpu, cudaStream_t st, void* host, const void* dev, size_t n,
+                             size_t bytes_per_item, cudaEvent_t after_copies,
+                             const std::function<void(size_t, size_t)>& fn) {
+  const int chunks = chunk_count(n);
+  for (int c = 0; c < chunks; ++c) {
+    const size_t b = chunk_begin(n, chunks, c), e = chunk_begin(n, chunks, c + 1);
+    if (e > b)
+      PB_CUDA(cudaMemcpyAsync(static_cast<char*>(host) + b * bytes_per_item,
+                              static_cast<const char*>(dev) + b * bytes_per_item, (e - b) * bytes_per_item,
+                              cudaMemcpyDeviceToHost, st));
+    PB_CUDA(cudaEventRecord(gpu.chunk_ev[c], st));
+  }
+  if (after_copies) PB_CUDA(cudaEventRecord(after_copies, st));
+  std::atomic<int> arrived{0};  // chunks whose copy has completed (-1: CUDA error)
+  cudaError_t err = cudaSuccess;
+  const double t_un = now_ms();
+  HostPool& pool = HostPool::instance();
+  if (per_chunk_regions()) {
+    for (int c = 0; c < chunks; ++c) {
+      const size_t b = chunk_begin(n, chunks, c), e = chunk_begin(n, chunks, c + 1);
+      PB_CUDA(cudaEventSynchronize(gpu.chunk_ev[c]));
+      if (e > b) pool.parallel_for(e - b, kParallelGrain, [&](size_t sb, size_t se) { fn(b + sb, b + se); });
+    }
+    g_unpack_ms += now_ms() - t_un;
+    return cudaSuccess;
+  }
+  pool.parallel_parts(pool.parts_for(n, kParallelGrain), [&](int part, int parts) {
+    for (int c = 0; c < chunks; ++c) {
+      if (part == 0) {
+        err = cudaEventSynchronize(gpu.chunk_ev[c]);
+        arrived.store(err == cudaSuccess ? c + 1 : 1 << 20, std::memory_order_release);
+        if (err != cudaSuccess) return;
+      } else {
+        spin_until(arrived, c + 1);
+        if (arrived.load(std::memory_order_relaxed) >= (1 << 20)) return;
+      }
+      const size_t b = chunk_begin(n, chunks, c), e = chunk_begin(n, chunks, c + 1);
+      size_t sb, se;
+      share_of(b, e, part, parts, &sb, &se);
+      if (se > sb) fn(sb, se);
+    }
+  });
+  g_unpack_ms += now_ms() - t_un;
+  if (err != cudaSuccess) {
+    set_error("CUDA error: %s (download_chunked)", cudaGetErrorString(err));
+    return err;
   }
   return cudaSuccess;
 }
@@ -190,31 +300,18 @@ cudaError_t transform_forces(TransformObj& t, const Entity* state, size_t n, Acc
   t.ws.n = n;
   PB_PASS(gravity_evaluate(t.ws, t.prm, 0, n, st, t.ls, true));
   PB_CUDA(cudaEventRecord(t.gpu.ev[2], st));
-  const int chunks = chunk_count(n);
-  float4* h = t.h_acc.as<float4>();
-  for (int c = 0; c < chunks; ++c) {
-    const size_t b = chunk_begin(n, chunks, c), e = chunk_begin(n, chunks, c + 1);
-    if (e > b)
-      PB_CUDA(cudaMemcpyAsync(h + b, t.ws.acc.as<float4>() + b, (e - b) * sizeof(float4), cudaMemcpyDeviceToHost, st));
-    PB_CUDA(cudaEventRecord(t.gpu.chunk_ev[c], st));
-  }
-  PB_CUDA(cudaEventRecord(t.gpu.ev[3], st));
+  const float4* h = t.h_acc.as<float4>();
   // accelerations[i] += f / m_a for every non-fixed body (transformers.rs:139-141,154-158),
   // chunk by chunk behind the copies
-  for (int c = 0; c < chunks; ++c) {
-    const size_t cb = chunk_begin(n, chunks, c), ce = chunk_begin(n, chunks, c + 1);
-    PB_CUDA(cudaEventSynchronize(t.gpu.chunk_ev[c]));
-    const double t_un = now_ms();
-    HostPool::instance().parallel_for(ce - cb, kParallelGrain, [&](size_t b, size_t e) {
-      for (size_t i = cb + b; i < cb + e; ++i) {
-        if (state[i].fixed) continue;
-        acc[i].x += double(h[i].x);
-        acc[i].y += double(h[i].y);
-        acc[i].z += double(h[i].z);
-      }
-    });
-    g_unpack_ms += now_ms() - t_un;
-  }
+  PB_PASS(download_chunked(t.gpu, st, t.h_acc.p, t.ws.acc.p, n, sizeof(float4), t.gpu.ev[3],
+                           [&](size_t b, size_t e) {
+                             for (size_t i = b; i < e; ++i) {
+                               if (state[i].fixed) continue;
+                               acc[i].x += double(h[i].x);
+                               acc[i].y += double(h[i].y);
+                               acc[i].z += double(h[i].z);
+                             }
+                           }));
   PB_CUDA(cudaStreamSynchronize(st));
   t.last_n = n;
   t.have_tree = t.ws.n_cells > 0;
@@ -258,31 +355,29 @@ struct VerletObj {
 // new_state[i] = entities[i] with position and velocity replaced (verlet.rs:41-48 / :72-79).
 // out6 holds {x,y,z,vx,vy,vz} per body.  new_state is written with non-temporal 16-byte stores when
 // aligned (it is 80 MB the caller reads later; no read-for-ownership traffic).
-void unpack_state(const Entity* entities, Entity* out, size_t n, const double* out6) {
+void unpack_state_range(const Entity* entities, Entity* out, size_t b, size_t e, const double* out6) {
   const bool aligned = (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
-  HostPool::instance().parallel_for(n, kParallelGrain, [&](size_t b, size_t e) {
-    if (aligned) {
-      for (size_t i = b; i < e; ++i) {
-        const double* o = out6 + 6 * i;
-        const double* src = reinterpret_cast<const double*>(entities + i);
-        double* dst = reinterpret_cast<double*>(out + i);
-        _mm_stream_pd(dst, _mm_loadu_pd(o));
-        _mm_stream_pd(dst + 2, _mm_loadu_pd(o + 2));
-        _mm_stream_pd(dst + 4, _mm_loadu_pd(o + 4));
-        _mm_stream_pd(dst + 6, _mm_loadu_pd(src + 6));  // radius, mass
-        _mm_stream_pd(dst + 8, _mm_loadu_pd(src + 8));  // id, fixed (+ padding)
-      }
-      _mm_sfence();
-    } else {
-      for (size_t i = b; i < e; ++i) {
-        const double* o = out6 + 6 * i;
-        Entity t = entities[i];
-        t.x = o[0]; t.y = o[1]; t.z = o[2];
-        t.vx = o[3]; t.vy = o[4]; t.vz = o[5];
-        out[i] = t;
-      }
+  if (aligned) {
+    for (size_t i = b; i < e; ++i) {
+      const double* o = out6 + 6 * i;
+      const double* src = reinterpret_cast<const double*>(entities + i);
+      double* dst = reinterpret_cast<double*>(out + i);
+      _mm_stream_pd(dst, _mm_loadu_pd(o));
+      _mm_stream_pd(dst + 2, _mm_loadu_pd(o + 2));
+      _mm_stream_pd(dst + 4, _mm_loadu_pd(o + 4));
+      _mm_stream_pd(dst + 6, _mm_loadu_pd(src + 6));  // radius, mass
+      _mm_stream_pd(dst + 8, _mm_loadu_pd(src + 8));  // id, fixed (+ padding)
     }
-  });
+    _mm_sfence();
+  } else {
+    for (size_t i = b; i < e; ++i) {
+      const double* o = out6 + 6 * i;
+      Entity t = entities[i];
+      t.x = o[0]; t.y = o[1]; t.z = o[2];
+      t.vx = o[3]; t.vy = o[4]; t.vz = o[5];
+      out[i] = t;
+    }
+  }
 }
 
 cudaError_t verlet_buffers(VerletObj& v, size_t n) {
@@ -301,23 +396,10 @@ cudaError_t verlet_buffers(VerletObj& v, size_t n) {
 
 // shared tail of both verlet entry points: chunked D2H of the packed result, unpack behind the copies
 cudaError_t verlet_finish(VerletObj& v, cudaStream_t st, const Entity* entities, Entity* new_state, size_t n) {
-  const int chunks = chunk_count(n);
-  double* h = v.h_out.as<double>();
-  const double* d = v.out6.as<double>();
-  for (int c = 0; c < chunks; ++c) {
-    const size_t b = chunk_begin(n, chunks, c), e = chunk_begin(n, chunks, c + 1);
-    if (e > b)
-      PB_CUDA(cudaMemcpyAsync(h + 6 * b, d + 6 * b, (e - b) * 48, cudaMemcpyDeviceToHost, st));
-    PB_CUDA(cudaEventRecord(v.gpu.chunk_ev[c], st));
-  }
-  PB_CUDA(cudaEventRecord(v.gpu.ev[4], st));
-  for (int c = 0; c < chunks; ++c) {
-    const size_t b = chunk_begin(n, chunks, c), e = chunk_begin(n, chunks, c + 1);
-    PB_CUDA(cudaEventSynchronize(v.gpu.chunk_ev[c]));
-    const double t_un = now_ms();
-    if (e > b) unpack_state(entities + b, new_state + b, e - b, h + 6 * b);
-    g_unpack_ms += now_ms() - t_un;
-  }
+  const double* h = v.h_out.as<double>();
+  PB_PASS(download_chunked(v.gpu, st, v.h_out.p, v.out6.p, n, 48, v.gpu.ev[4], [&](size_t b, size_t e) {
+    unpack_state_range(entities, new_state, b, e, h);
+  }));
   PB_CUDA(cudaStreamSynchronize(st));
   v.n_prev = n;
   v.stats.n_bodies = n;

@@ -25,27 +25,42 @@ class HostPool {
 
   int threads() const { return n_threads_; }
 
-  // Runs fn(begin, end) over [0, n) split into contiguous chunks, one per worker; blocks.
-  void parallel_for(size_t n, size_t min_per_thread, const std::function<void(size_t, size_t)>& fn) {
-    int use = static_cast<int>(std::min<size_t>(n_threads_, std::max<size_t>(1, n / std::max<size_t>(1, min_per_thread))));
-    if (use <= 1 || workers_.empty()) {
-      fn(0, n);
+  // Runs fn(part, parts) once on each of `parts` <= threads() threads (part 0 on the caller); blocks.
+  // One wake-up of the pool serves a whole multi-chunk pipeline: the parts walk the chunks together and
+  // hand chunk boundaries to each other through atomics instead of one parallel_for per chunk.
+  void parallel_parts(int parts, const std::function<void(int, int)>& fn) {
+    parts = std::max(1, std::min(parts, n_threads_));
+    if (parts <= 1 || workers_.empty()) {
+      fn(0, 1);
       return;
     }
-    std::unique_lock<std::mutex> call_lock(call_mu_);  // one parallel_for at a time
+    std::unique_lock<std::mutex> call_lock(call_mu_);  // one parallel region at a time
     {
       std::lock_guard<std::mutex> lk(mu_);
       fn_ = &fn;
-      total_ = n;
-      parts_ = use;
-      pending_ = use - 1;
+      parts_ = parts;
+      pending_ = parts - 1;
       ++generation_;
     }
     cv_.notify_all();
-    run_part(0);
+    fn(0, parts);
     std::unique_lock<std::mutex> lk(mu_);
     done_cv_.wait(lk, [&] { return pending_ == 0; });
     fn_ = nullptr;
+  }
+
+  // how many parts a loop over n items is worth
+  int parts_for(size_t n, size_t min_per_thread) const {
+    return static_cast<int>(std::min<size_t>(n_threads_, std::max<size_t>(1, n / std::max<size_t>(1, min_per_thread))));
+  }
+
+  // Runs fn(begin, end) over [0, n) split into contiguous ranges, one per part; blocks.
+  void parallel_for(size_t n, size_t min_per_thread, const std::function<void(size_t, size_t)>& fn) {
+    parallel_parts(parts_for(n, min_per_thread), [&](int part, int parts) {
+      const size_t per = (n + size_t(parts) - 1) / size_t(parts);
+      const size_t b = std::min(n, per * size_t(part)), e = std::min(n, b + per);
+      if (b < e) fn(b, e);
+    });
   }
 
  private:
@@ -57,12 +72,6 @@ class HostPool {
     for (auto& t : workers_) t.detach();
   }
 
-  void run_part(int part) {
-    const size_t per = (total_ + parts_ - 1) / parts_;
-    const size_t b = std::min(total_, per * part), e = std::min(total_, b + per);
-    if (b < e) (*fn_)(b, e);
-  }
-
   void worker(int id) {
     uint64_t seen = 0;
     for (;;) {
@@ -72,7 +81,7 @@ class HostPool {
       const bool mine = id < parts_;
       lk.unlock();
       if (mine) {
-        run_part(id);
+        (*fn_)(id, parts_);
         lk.lock();
         if (--pending_ == 0) done_cv_.notify_all();
       }
@@ -83,8 +92,7 @@ class HostPool {
   std::vector<std::thread> workers_;
   std::mutex mu_, call_mu_;
   std::condition_variable cv_, done_cv_;
-  const std::function<void(size_t, size_t)>* fn_ = nullptr;
-  size_t total_ = 0;
+  const std::function<void(int, int)>* fn_ = nullptr;
   int parts_ = 0, pending_ = 0;
   uint64_t generation_ = 0;
 };
