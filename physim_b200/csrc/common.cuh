@@ -111,6 +111,10 @@ struct GravityWorkspace {
   const double4* pos64 = nullptr;
   const uint8_t* fixed = nullptr;
   size_t n = 0;
+  // extent of pos64 (u64 bits of the double) already reduced on the device by whoever wrote pos64 (the
+  // resident verlet step); consumed by the next tree build instead of running extent_kernel
+  const unsigned long long* extent_pre = nullptr;
+  const unsigned long long* extent_cur = nullptr;  // where the running build reads its extent
   // owned
   DevBuf src4, key0, key1, idx0, idx1, bucket_key, bucket_idx, splitters, nsv1, nsv2, spos64, ab, cell_start, scan_tmp, tile_counts, digit_base,
       extent_bits, tgt_list, tgt_flags;
@@ -258,6 +262,16 @@ cudaError_t gravity_count_interactions(GravityWorkspace& ws, cudaStream_t stream
 // first != 0: x1 = x0 + v0 dt + ½ a dt², v1 = v0 + a dt, prev = x0      (verlet.rs:24-50)
 // else      : x' = 2x − prev + a dt², v' = (x' − x)/dt, prev = x         (verlet.rs:52-82)
 // acc32 (float4, index i - acc_offset... see verlet.cu) or acc64 (3 doubles per body) is used.
+// device-resident verlet step (no first-step form): reads x_n (cur), x_{n-1} (prev_inout) and the
+// accelerations, writes x_{n+1} over x_{n-1} (the caller swaps the two buffers) and nothing else -
+// v_{n+1} = (x_{n+1} - x_n) / dt is derived on demand by verlet_velocity().  Also reduces the extent
+// max(|x|,|y|,|z|) of the new positions into *extent_out (atomicMax on the double's bits) and zeroes
+// *extent_zero (the slot the next step will reduce into).
+cudaError_t verlet_update_lean(const double4* cur, double4* prev_inout, const float4* acc32, size_t n, double dt,
+                               unsigned long long* extent_out, unsigned long long* extent_zero, cudaStream_t st,
+                               LaunchStats& ls);
+cudaError_t verlet_velocity(const double4* cur, const double4* prev, double4* vel, size_t n, double dt,
+                            cudaStream_t st, LaunchStats& ls);
 cudaError_t verlet_update(double4* cur, double4* prev, double4* vel, const float4* acc32,
                           const double* acc64, size_t n, double dt, int first, cudaStream_t stream,
                           LaunchStats& ls, double* out6 = nullptr);

@@ -568,13 +568,20 @@ struct SimObj {
   int integrator = PB200_VERLET;
   DevBuf t_pos, t_vel, s_pos, s_vel;  // rk4
   bool first = true, checked = false;
+  // lean verlet steps (world == 1, all bodies integrated): cur / prev swap roles every step, `vel` is
+  // derived on demand (vel_stale), and the step leaves the extent of its new positions in ext[ext_slot]
+  // for the next tree build (ext_ready); ext_dirty: the slots must be zeroed before the next lean step
+  bool vel_stale = false, ext_ready = false, ext_dirty = true;
+  bool pin_cur = false;  // pb200_sim_gather_buffer handed out cur's address
+  int ext_slot = 0;
+  DevBuf ext;
   LaunchStats ls;
   Pb200Stats stats;
   ~SimObj() {
     if (gpu.ready) {
       cudaSetDevice(gpu.device);
       ws.release_all();
-      cur.release(); prev.release(); vel.release(); fixed.release();
+      cur.release(); prev.release(); vel.release(); fixed.release(); ext.release();
       ck_cur.release(); ck_prev.release(); ck_vel.release();
       t_pos.release(); t_vel.release(); s_pos.release(); s_vel.release();
       h_pos.release(); h_vel.release(); h_fixed.release(); h_acc.release();
@@ -594,6 +601,9 @@ cudaError_t sim_upload(SimObj& s, const Entity* state, size_t n) {
   s.t1 = std::min(n, s.slice * size_t(s.rank + 1));
   s.first = true;
   s.checked = false;
+  s.vel_stale = false;
+  s.ext_ready = false;
+  s.ext_dirty = true;
   if (n == 0) return cudaSuccess;
   PB_PASS(s.cur.ensure(s.slice * size_t(s.world) * sizeof(double4)));
   PB_PASS(s.prev.ensure(n * sizeof(double4)));
@@ -612,11 +622,28 @@ cudaError_t sim_upload(SimObj& s, const Entity* state, size_t n) {
   return cudaSuccess;
 }
 
+// velocities of the current state, if the lean steps left them implicit
+cudaError_t sim_materialise_velocities(SimObj& s) {
+  if (!s.vel_stale) return cudaSuccess;
+  PB_PASS(verlet_velocity(s.cur.as<double4>(), s.prev.as<double4>(), s.vel.as<double4>(), s.n, s.dt,
+                          s.gpu.stream, s.ls));
+  s.vel_stale = false;
+  return cudaSuccess;
+}
+
+inline bool sim_lean_enabled() {  // PB200_VERLET_LEAN=0: general verlet kernel every step (A/B runs, tests)
+  const char* e = std::getenv("PB200_VERLET_LEAN");  // (read per step: tests flip it inside one process)
+  return !(e && std::atoi(e) == 0);
+}
+
 // one step: forces for targets [t0,t1) from all n positions, then verlet on the owned slice
 cudaError_t sim_step(SimObj& s, bool force_check) {
   if (s.n == 0) return cudaSuccess;
   cudaStream_t st = s.gpu.stream;
   const bool check = force_check || !s.checked;  // size the cell table once, then stay asynchronous
+  const bool lean = sim_lean_enabled() && s.integrator == PB200_VERLET && !s.first && s.world == 1 &&
+                    !s.pin_cur && s.t0 == 0 && s.t1 == s.n;
+  if (!lean) PB_PASS(sim_materialise_velocities(s));
   if (s.integrator == PB200_RK4) {
     // four force evaluations per step on the device-side evaluation points (world == 1)
     const size_t bytes = s.n * sizeof(double4);
@@ -635,15 +662,41 @@ cudaError_t sim_step(SimObj& s, bool force_check) {
     s.ws.pos64 = s.cur.as<double4>();
     s.checked = true;
     s.first = false;
+    s.ext_ready = false;
+    s.ext_dirty = true;
     return cudaSuccess;
   }
+  s.ws.pos64 = s.cur.as<double4>();
+  s.ws.extent_pre = (lean && s.ext_ready) ? s.ext.as<unsigned long long>() + s.ext_slot : nullptr;
   PB_PASS(gravity_evaluate(s.ws, s.prm, s.t0, s.t1, st, s.ls, check));
+  s.ws.extent_pre = nullptr;  // (the direct sum does not consume it)
   s.checked = true;
+  if (lean) {
+    PB_PASS(s.ext.ensure(16));
+    if (s.ext_dirty) {
+      PB_CUDA(cudaMemsetAsync(s.ext.p, 0, 16, st));
+      s.ext_dirty = false;
+    }
+    // the extent just consumed (if any) sits in ext_slot: reduce the new one into the other slot, and
+    // let the kernel zero the consumed one for the step after
+    const int out = s.ext_slot ^ 1;
+    PB_PASS(verlet_update_lean(s.cur.as<double4>(), s.prev.as<double4>(), s.ws.acc.as<float4>(), s.n, s.dt,
+                               s.ext.as<unsigned long long>() + out, s.ext.as<unsigned long long>() + s.ext_slot,
+                               st, s.ls));
+    std::swap(s.cur, s.prev);  // x_{n+1} was written over x_{n-1}
+    s.ws.pos64 = s.cur.as<double4>();
+    s.ext_slot = out;
+    s.ext_ready = true;
+    s.vel_stale = true;
+    return cudaSuccess;
+  }
   const size_t nl = s.t1 - s.t0;
   PB_PASS(verlet_update(s.cur.as<double4>() + s.t0, s.prev.as<double4>() + s.t0,
                         s.vel.as<double4>() + s.t0, s.ws.acc.as<float4>() + s.t0, nullptr, nl, s.dt,
                         (s.first || s.integrator == PB200_EULER) ? 1 : 0, st, s.ls));
   s.first = false;
+  s.ext_ready = false;
+  s.ext_dirty = true;
   return cudaSuccess;
 }
 
@@ -676,7 +729,7 @@ cudaError_t sim_run_steps(SimObj& s, size_t steps, ExchangeFn exchange = nullptr
     PB_CUDA(cudaMemcpyAsync(s.ck_cur.p, s.cur.p, bytes, cudaMemcpyDeviceToDevice, st));
     PB_CUDA(cudaMemcpyAsync(s.ck_prev.p, s.prev.p, bytes, cudaMemcpyDeviceToDevice, st));
     PB_CUDA(cudaMemcpyAsync(s.ck_vel.p, s.vel.p, bytes, cudaMemcpyDeviceToDevice, st));
-    const bool first_at_ck = s.first;
+    const bool first_at_ck = s.first, vel_stale_at_ck = s.vel_stale;
     for (size_t i = 0; i < chunk; ++i) {
       PB_PASS(sim_step(s, false));
       if (exchange) exchange(xctx);
@@ -692,6 +745,10 @@ cudaError_t sim_run_steps(SimObj& s, size_t steps, ExchangeFn exchange = nullptr
       PB_CUDA(cudaMemcpyAsync(s.prev.p, s.ck_prev.p, bytes, cudaMemcpyDeviceToDevice, st));
       PB_CUDA(cudaMemcpyAsync(s.vel.p, s.ck_vel.p, bytes, cudaMemcpyDeviceToDevice, st));
       s.first = first_at_ck;
+      s.vel_stale = vel_stale_at_ck;
+      s.ext_ready = false;  // (the extent slots belong to the abandoned steps)
+      s.ext_dirty = true;
+      s.ws.pos64 = s.cur.as<double4>();
       s.replays += 1;
       for (size_t i = 0; i < chunk; ++i) {
         PB_PASS(sim_step(s, true));
@@ -1222,6 +1279,7 @@ int pb200_sim_gather_buffer(void* sim, void** dev_ptr, size_t* total_bytes, size
   if (!sim) return -1;
   auto& s = *static_cast<SimObj*>(sim);
   std::lock_guard<std::mutex> lk(s.mu);
+  s.pin_cur = true;  // the caller holds the address: the lean steps' buffer swap is off from now on
   if (dev_ptr) *dev_ptr = s.cur.p;
   if (total_bytes) *total_bytes = s.slice * size_t(s.world) * sizeof(double4);
   if (slice_offset) *slice_offset = s.slice * size_t(s.rank) * sizeof(double4);
@@ -1241,6 +1299,7 @@ int pb200_sim_download(void* sim, Entity* state, size_t n) {
   cudaSetDevice(s.gpu.device);
   cudaStream_t st = s.gpu.stream;
   auto run = [&]() -> cudaError_t {
+    PB_PASS(sim_materialise_velocities(s));
     PB_CUDA(cudaMemcpyAsync(s.h_pos.p, s.cur.p, n * sizeof(double4), cudaMemcpyDeviceToHost, st));
     PB_CUDA(cudaMemcpyAsync(s.h_vel.p, s.vel.p, n * sizeof(double4), cudaMemcpyDeviceToHost, st));
     PB_CUDA(cudaStreamSynchronize(st));

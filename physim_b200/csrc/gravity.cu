@@ -591,8 +591,8 @@ __global__ void __launch_bounds__(NT, 1024 / NT) sort_local_kernel(
 // state of `sorted`, e.g. after a build that was abandoned)
 constexpr int SPLITTER_STRIDE = 264;  // u64 words per splitter set (257 used)
 
-__global__ void __launch_bounds__(256) splitter_kernel(const uint64_t* __restrict__ sorted, size_t n,
-                                                       uint64_t* __restrict__ out /*[257]*/) {
+__device__ __forceinline__ void splitter_block(const uint64_t* __restrict__ sorted, size_t n,
+                                               uint64_t* __restrict__ out /*[257]*/) {
   __shared__ uint64_t v[257];
   const int t = threadIdx.x;
   v[t] = n ? sorted[(size_t(t) * n) >> 8] : 0ull;
@@ -610,6 +610,40 @@ __global__ void __launch_bounds__(256) splitter_kernel(const uint64_t* __restric
   if (t == 0) out[256] = v[256];
 }
 
+// second level of the range-minimum tables (see NsvTables below): block minima -> tables inside
+// super-blocks of 256 blocks, super-block minima
+__device__ __forceinline__ void nsv_level2_block(unsigned sb, uint8_t* __restrict__ t2, size_t b_pad, size_t nblocks,
+                                                 uint8_t* __restrict__ t3) {
+  __shared__ unsigned char tab[2][256 + 128];
+  const int t = threadIdx.x;
+  const size_t b = size_t(sb) * 256 + t;
+  tab[0][t] = b < nblocks ? t2[b] : 255;  // NSV_NONE
+  if (t < 128) tab[0][256 + t] = tab[1][256 + t] = 255;
+  __syncthreads();
+  int cur = 0;
+#pragma unroll
+  for (int k = 1; k <= 8; ++k) {
+    const unsigned char m = min(tab[cur][t], tab[cur][t + (1 << (k - 1))]);
+    tab[cur ^ 1][t] = m;
+    if (b < b_pad) t2[size_t(k) * b_pad + b] = m;
+    cur ^= 1;
+    __syncthreads();
+  }
+  if (t == 0) t3[sb] = tab[cur][0];
+}
+
+// small jobs that ride along with the scan of the cell counts (each would otherwise be a launch of a
+// few CTAs between two kernels of the build): the CTAs whose ticket is past the last scan tile do them
+struct ScanSide {
+  unsigned nsuper;            // CTAs [0, nsuper): nsv_level2_block
+  uint8_t* t2;
+  size_t b_pad, nblocks;
+  uint8_t* t3;
+  const uint64_t* sorted;     // CTA nsuper: splitter_block
+  size_t n;
+  uint64_t* spl_out;
+};
+
 // ---------------------------------------------------------------------------------------------
 // exclusive scan of u32[n] -> out[n+1] (out[n] = total): one kernel, decoupled look-back done by a
 // warp (32 predecessor tiles per round; status word = flag << 32 | value)
@@ -618,14 +652,21 @@ constexpr int SCAN_ITEMS = 16;
 constexpr int SCAN_TILE = 256 * SCAN_ITEMS;
 constexpr unsigned long long SCAN_PART = 1ull << 32, SCAN_INCL = 2ull << 32;
 
+template <bool SIDE>
 __global__ void __launch_bounds__(256) scan_lookback_kernel(const uint32_t* __restrict__ in, size_t n,
                                                             uint32_t* __restrict__ out,
                                                             unsigned long long* status,
-                                                            unsigned* tile_counter) {
+                                                            unsigned* tile_counter, unsigned tiles, ScanSide side) {
   __shared__ unsigned tile_s, tile_prefix_s;
   if (threadIdx.x == 0) tile_s = atomicAdd(tile_counter, 1u);
   __syncthreads();
   const unsigned tile = tile_s;
+  if (SIDE && tile >= tiles) {  // (the last tickets: nothing of the scan waits for these CTAs)
+    const unsigned job = tile - tiles;
+    if (job < side.nsuper) nsv_level2_block(job, side.t2, side.b_pad, side.nblocks, side.t3);
+    else if (job == side.nsuper) splitter_block(side.sorted, side.n, side.spl_out);
+    return;
+  }
   const size_t base = size_t(tile) * SCAN_TILE + size_t(threadIdx.x) * SCAN_ITEMS;
   unsigned v[SCAN_ITEMS];
   unsigned sum = 0;
@@ -860,26 +901,6 @@ struct NsvTables {
   const uint8_t* t3;
   size_t n, nblocks, nsuper;
 };
-
-__global__ void __launch_bounds__(256) nsv_level2_kernel(uint8_t* __restrict__ t2, size_t b_pad, size_t nblocks,
-                                                         uint8_t* __restrict__ t3) {
-  __shared__ unsigned char tab[2][256 + 128];
-  const int t = threadIdx.x;
-  const size_t b = size_t(blockIdx.x) * 256 + t;
-  tab[0][t] = b < nblocks ? t2[b] : NSV_NONE;
-  if (t < 128) tab[0][256 + t] = tab[1][256 + t] = NSV_NONE;
-  __syncthreads();
-  int cur = 0;
-#pragma unroll
-  for (int k = 1; k <= 8; ++k) {
-    const unsigned char m = min(tab[cur][t], tab[cur][t + (1 << (k - 1))]);
-    tab[cur ^ 1][t] = m;
-    if (b < b_pad) t2[size_t(k) * b_pad + b] = m;
-    cur ^= 1;
-    __syncthreads();
-  }
-  if (t == 0) t3[blockIdx.x] = tab[cur][0];
-}
 
 // first index in [j, end) (end - j <= 256, same 256-aligned block) whose entry is <= l, else end
 __device__ __forceinline__ size_t nsv_descend(const uint8_t* __restrict__ tab, size_t stride, size_t j, size_t end,
@@ -1762,8 +1783,21 @@ cudaError_t exclusive_scan(const uint32_t* in, uint32_t* out, size_t n, DevBuf& 
   PB_PASS(tmp.ensure(size_t(tiles) * 8 + 16));  // [tile status words][tile counter]
   PB_CUDA(cudaMemsetAsync(tmp.p, 0, size_t(tiles) * 8 + 16, st));
   PB_LAUNCH(ls, st, "scan_lookback_kernel",
-            scan_lookback_kernel<<<tiles, 256, 0, st>>>(in, n, out, tmp.as<unsigned long long>(),
-                                                        reinterpret_cast<unsigned*>(tmp.as<unsigned long long>() + tiles)));
+            scan_lookback_kernel<false><<<tiles, 256, 0, st>>>(in, n, out, tmp.as<unsigned long long>(),
+                                                               reinterpret_cast<unsigned*>(tmp.as<unsigned long long>() + tiles),
+                                                               tiles, ScanSide{}));
+  return cudaGetLastError();
+}
+
+// the scan of the build's cell counts, with the side jobs; `scratch` ([tiles status words][counter]) is
+// part of the build's zeroed scratch block
+inline size_t scan_scratch_bytes(size_t n) { return size_t(blocks_for(n, SCAN_TILE)) * 8 + 16; }
+cudaError_t exclusive_scan_with_side(const uint32_t* in, uint32_t* out, size_t n, unsigned long long* scratch,
+                                     const ScanSide& side, cudaStream_t st, LaunchStats& ls) {
+  const unsigned tiles = blocks_for(n, SCAN_TILE);
+  PB_LAUNCH(ls, st, "scan_lookback_kernel",
+            scan_lookback_kernel<true><<<tiles + side.nsuper + 1, 256, 0, st>>>(
+                in, n, out, scratch, reinterpret_cast<unsigned*>(scratch + tiles), tiles, side));
   return cudaGetLastError();
 }
 
@@ -1790,8 +1824,9 @@ inline SortPlan even_plan(int lo, int total) {
 }
 
 // plans the sort of key bits [lo, key_bits) and clears histograms / look-back state
+constexpr size_t SORT_HEAD_WORDS = SORT_HIST_SLOTS * 256 + SORT_MAX_PASSES + 8;
 cudaError_t sort_prepare(GravityWorkspace& ws, size_t n, int key_bits, int lo, int mode, cudaStream_t st,
-                         SortBuffers* sb) {
+                         unsigned* head /* SORT_HEAD_WORDS zeroed words */, SortBuffers* sb) {
   // keys per thread, measured on B200: 8 wins at 1e5 bodies and from 4e6 up (more CTAs in flight),
   // 16 at 1e6 (one wave of 245 CTAs)
   static const int items_env = std::getenv("PB200_SORT_ITEMS") ? std::atoi(std::getenv("PB200_SORT_ITEMS")) : 0;
@@ -1804,16 +1839,18 @@ cudaError_t sort_prepare(GravityWorkspace& ws, size_t n, int key_bits, int lo, i
   sb->cap = LOCAL_CAP[mode];
   sb->plan = even_plan(lo, mode == 0 ? key_bits - lo : 0);
   const SortPlan& plan = sb->plan;
-  // [ghist: 8 x 256 (bucket modes: slot 0 = bucket cursors)][tile counters: 8][error flag + pad: 8]
-  // [status: npass x tiles x 256]
-  const size_t head_words = SORT_HIST_SLOTS * 256 + SORT_MAX_PASSES + 8;
-  const size_t words = head_words + size_t(plan.npass) * sb->tiles * 256;
-  PB_PASS(ws.tile_counts.ensure(words * 4));
-  sb->ghist = ws.tile_counts.as<unsigned>();
+  // head (zeroed by the caller): [ghist: 8 x 256 (bucket modes: slot 0 = bucket cursors)][tile counters: 8]
+  // [error flag + pad: 8]; look-back status of the global passes: npass x tiles x 256 words
+  sb->ghist = head;
   sb->counters = sb->ghist + SORT_HIST_SLOTS * 256;
   sb->err_flag = sb->counters + SORT_MAX_PASSES;
-  sb->status = sb->ghist + head_words;
-  PB_CUDA(cudaMemsetAsync(sb->ghist, 0, words * 4, st));
+  sb->status = nullptr;
+  if (plan.npass) {
+    const size_t words = size_t(plan.npass) * sb->tiles * 256;
+    PB_PASS(ws.tile_counts.ensure(words * 4));
+    sb->status = ws.tile_counts.as<unsigned>();
+    PB_CUDA(cudaMemsetAsync(sb->status, 0, words * 4, st));
+  }
   if (ws.sticky.p) sb->err_flag = ws.sticky.as<unsigned>() + 2;  // survives until the next host check
   ws.sort_err_flag = sb->err_flag;
   if (mode != 0) {
@@ -1831,7 +1868,7 @@ cudaError_t sort_prepare(GravityWorkspace& ws, size_t n, int key_bits, int lo, i
 // `bad` is the build's "keys not ordered" flag.
 template <int DIM>
 cudaError_t encode_and_sort(GravityWorkspace& ws, size_t n, const SortBuffers& sb, unsigned* bad, cudaStream_t st,
-                            LaunchStats& ls) {
+                            LaunchStats& ls, uint64_t** splitters_out) {
   uint64_t* k[2] = {ws.key0.as<uint64_t>(), ws.key1.as<uint64_t>()};
   uint32_t* v[2] = {ws.idx0.as<uint32_t>(), ws.idx1.as<uint32_t>()};
   unsigned* stat_max = ws.sticky.as<unsigned>() + 3;
@@ -1840,10 +1877,11 @@ cudaError_t encode_and_sort(GravityWorkspace& ws, size_t n, const SortBuffers& s
   const uint64_t* spl_in = ws.splitters.as<uint64_t>() + SPLITTER_STRIDE * ws.splitter_cur;
   uint64_t* spl_out = ws.splitters.as<uint64_t>() + SPLITTER_STRIDE * (ws.splitter_cur ^ 1);
   ws.splitter_cur ^= 1;
+  *splitters_out = spl_out;  // written by the side job of the scan that follows the sort
   if (sb.mode != 0) {
     PB_LAUNCH(ls, st, "encode_bucket_kernel",
               encode_bucket_kernel<DIM><<<blocks_for(n, 256 * ENC_ITEMS), 256, 0, st>>>(
-                  ws.pos64, n, ws.extent_bits.as<unsigned long long>(), spl_in, sb.lo, ws.bucket_key.as<uint64_t>(),
+                  ws.pos64, n, ws.extent_cur, spl_in, sb.lo, ws.bucket_key.as<uint64_t>(),
                   ws.bucket_idx.as<uint32_t>(), sb.cap, sb.ghist));
     const size_t smem = sort_local_smem(sb.cap);
     if (sb.mode == 1) {
@@ -1861,12 +1899,11 @@ cudaError_t encode_and_sort(GravityWorkspace& ws, size_t n, const SortBuffers& s
     }
     ws.sorted_key = k[0];
     ws.perm = v[0];
-    PB_LAUNCH(ls, st, "splitter_kernel", splitter_kernel<<<1, 256, 0, st>>>(ws.sorted_key, n, spl_out));
     return cudaGetLastError();
   }
   PB_LAUNCH(ls, st, "encode_kernel",
             encode_kernel<DIM><<<min(nb, 148u * 4u), 256, 0, st>>>(
-                ws.pos64, n, ws.extent_bits.as<unsigned long long>(), k[0], v[0], sb.plan, sb.ghist));
+                ws.pos64, n, ws.extent_cur, k[0], v[0], sb.plan, sb.ghist));
   // 48 KB of dynamic + 10 KB of static shared memory for the 16-keys-per-thread tile: opt in
   // (per device, so per call: the handle may live on any device)
   if (sb.items == 16)
@@ -1889,7 +1926,6 @@ cudaError_t encode_and_sort(GravityWorkspace& ws, size_t n, const SortBuffers& s
   }
   ws.sorted_key = k[cur];
   ws.perm = v[cur];
-  PB_LAUNCH(ls, st, "splitter_kernel", splitter_kernel<<<1, 256, 0, st>>>(ws.sorted_key, n, spl_out));
   PB_LAUNCH(ls, st, "gather_kernel", gather_kernel<<<nb, 256, 0, st>>>(ws.pos64, ws.perm, n, ws.spos64.as<double4>()));
   return cudaGetLastError();
 }
@@ -1898,7 +1934,10 @@ template <int DIM>
 cudaError_t tree_evaluate(GravityWorkspace& ws, const GravityParams& prm, size_t t0, size_t t1,
                           float easing, float tiny, cudaStream_t st, LaunchStats& ls) {
   const size_t n = ws.n;
-  PB_PASS(ws.extent_bits.ensure(32));
+  // one zeroed scratch block per build: [extent / flags: 32 B][scan status + counter][sort head]
+  const size_t scan_bytes = (scan_scratch_bytes(n) + 15) / 16 * 16;
+  const size_t scratch_bytes = 32 + scan_bytes + SORT_HEAD_WORDS * 4;
+  PB_PASS(ws.extent_bits.ensure(scratch_bytes));
   if (!ws.sticky.p) {
     PB_PASS(ws.sticky.ensure(16));
     PB_CUDA(cudaMemsetAsync(ws.sticky.p, 0, 16, st));
@@ -1914,7 +1953,9 @@ cudaError_t tree_evaluate(GravityWorkspace& ws, const GravityParams& prm, size_t
 
   // extent_bits words: [0,1] extent (u64 bits)  [2] 1 + deepest level shared by distinct keys
   // [3] some leaf is a merged unit  [4] keys not fully ordered (truncated sort too short)
-  PB_CUDA(cudaMemsetAsync(ws.extent_bits.p, 0, 32, st));
+  PB_CUDA(cudaMemsetAsync(ws.extent_bits.p, 0, scratch_bytes, st));
+  unsigned long long* scan_scratch = ws.extent_bits.as<unsigned long long>() + 4;
+  unsigned* sort_head = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(ws.extent_bits.p) + 32 + scan_bytes);
   unsigned* max_shared_plus1 = reinterpret_cast<unsigned*>(ws.extent_bits.as<unsigned long long>() + 1);
   const int key_bits = DIM * TreeDim<DIM>::LM;
   if (ws.tree_dim != DIM) ws.sort_lo = 0, ws.sort_mode = 0;  // depth / bucket estimates belong to the other tree kind
@@ -1923,11 +1964,19 @@ cudaError_t tree_evaluate(GravityWorkspace& ws, const GravityParams& prm, size_t
   ws.last_lo = lo;
   ws.unchecked_builds += 1;
   const unsigned nb = blocks_for(n, 256);
-  PB_LAUNCH(ls, st, "extent_kernel", extent_kernel<<<min(nb, 148u * 8u), 256, 0, st>>>(ws.pos64, n, ws.extent_bits.as<unsigned long long>()));
+  // the extent of pos64: left on the device by the resident verlet step, else reduced here
+  const unsigned long long* extent = ws.extent_pre;
+  ws.extent_pre = nullptr;  // (good for one build)
+  if (!extent) {
+    PB_LAUNCH(ls, st, "extent_kernel", extent_kernel<<<min(nb, 148u * 8u), 256, 0, st>>>(ws.pos64, n, ws.extent_bits.as<unsigned long long>()));
+    extent = ws.extent_bits.as<unsigned long long>();
+  }
+  ws.extent_cur = extent;
   SortBuffers sb;
-  PB_PASS(sort_prepare(ws, n, key_bits, lo, ws.sort_mode, st, &sb));
+  PB_PASS(sort_prepare(ws, n, key_bits, lo, ws.sort_mode, st, sort_head, &sb));
   ws.last_mode = sb.mode;
-  PB_PASS(encode_and_sort<DIM>(ws, n, sb, max_shared_plus1 + 2, st, ls));
+  uint64_t* spl_out = nullptr;
+  PB_PASS(encode_and_sort<DIM>(ws, n, sb, max_shared_plus1 + 2, st, ls, &spl_out));
   // range-minimum tables over the sorted bodies' shared-level bytes (see NsvTables)
   const size_t n_pad = size_t(nb) * 256, nblocks = nb, b_pad = (nblocks + 255) / 256 * 256, nsuper = b_pad / 256;
   PB_PASS(ws.nsv1.ensure(9 * n_pad));
@@ -1937,8 +1986,8 @@ cudaError_t tree_evaluate(GravityWorkspace& ws, const GravityParams& prm, size_t
                                        ws.tgt_flags.as<uint32_t>(), max_shared_plus1,
                                        lo > 0 ? (key_bits - lo) / DIM : TreeDim<DIM>::LM + 2,
                                        ws.nsv1.as<uint8_t>(), n_pad, ws.nsv2.as<uint8_t>()));
-  PB_LAUNCH(ls, st, "nsv_level2_kernel", nsv_level2_kernel<<<unsigned(nsuper), 256, 0, st>>>(ws.nsv2.as<uint8_t>(), b_pad, nblocks, nsv3));
-  PB_PASS(exclusive_scan(ws.tgt_flags.as<uint32_t>(), ws.cell_start.as<uint32_t>(), n, ws.scan_tmp, st, ls));
+  const ScanSide side{unsigned(nsuper), ws.nsv2.as<uint8_t>(), b_pad, nblocks, nsv3, ws.sorted_key, n, spl_out};
+  PB_PASS(exclusive_scan_with_side(ws.tgt_flags.as<uint32_t>(), ws.cell_start.as<uint32_t>(), n, scan_scratch, side, st, ls));
 
   // cell table capacity: grows when a previous evaluation reported more cells
   size_t cap = ws.n_cells ? ws.n_cells + ws.n_cells / 4 + 1024 : n * 5 / 2 + 1024;
@@ -1966,13 +2015,13 @@ cudaError_t tree_evaluate(GravityWorkspace& ws, const GravityParams& prm, size_t
     PB_LAUNCH(ls, st, "cells_kernel_chain",
               cells_kernel_chain<DIM><<<nb, 256, 0, st>>>(ws.sorted_key, ws.spos64.as<double4>(), ws.perm,
                                                           ws.ab.as<uchar2>(), ws.cell_start.as<uint32_t>(), n,
-                                                          ws.extent_bits.as<unsigned long long>(), max_shared_plus1,
+                                                          ws.extent_cur, max_shared_plus1,
                                                           ws.sticky.as<unsigned>(), tv, cells));
   } else {
     PB_LAUNCH(ls, st, "cells_kernel",
               cells_kernel<DIM><<<nb, 256, 0, st>>>(ws.sorted_key, ws.spos64.as<double4>(), ws.perm,
                                                     ws.ab.as<uchar2>(), ws.cell_start.as<uint32_t>(), n,
-                                                    ws.extent_bits.as<unsigned long long>(), max_shared_plus1,
+                                                    ws.extent_cur, max_shared_plus1,
                                                     ws.sticky.as<unsigned>(), tv, cells));
   }
   PB_LAUNCH(ls, st, "parent_kernel",

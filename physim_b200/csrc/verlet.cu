@@ -71,6 +71,55 @@ __global__ void __launch_bounds__(256) verlet_kernel(double4* __restrict__ cur, 
   }
 }
 
+// Device-resident form of the regular step (verlet.rs:52-82) for the loop that keeps its state in HBM:
+// 32 + 32 + 16 B read, 32 B written per body (the general kernel above: 80 read, 96 written).  x_{n+1}
+// replaces x_{n-1} in place and the caller swaps the buffers; the velocity (x_{n+1} - x_n) / dt is not
+// stored - verlet_velocity_kernel derives it, bit for bit the same, when somebody asks for it.  The
+// kernel also leaves max(|x|,|y|,|z|) of the new positions for the next tree build (transformers.rs:35-40).
+__global__ void __launch_bounds__(256) verlet_lean_kernel(const double4* __restrict__ cur,
+                                                          double4* __restrict__ prev_inout,
+                                                          const float4* __restrict__ acc32, size_t n, double dt2,
+                                                          unsigned long long* __restrict__ extent_out,
+                                                          unsigned long long* __restrict__ extent_zero) {
+  const size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  if (i == 0) *extent_zero = 0ull;
+  double m = 0.0;
+  if (i < n) {
+    const double4 x = cur[i];
+    const double4 p = prev_inout[i];
+    const float4 a = acc32[i];
+    double4 nx;
+    nx.x = next_pos(x.x, p.x, double(a.x), dt2);
+    nx.y = next_pos(x.y, p.y, double(a.y), dt2);
+    nx.z = next_pos(x.z, p.z, double(a.z), dt2);
+    nx.w = x.w;  // mass passes through
+    prev_inout[i] = nx;
+    m = fmax(fmax(fabs(nx.x), fabs(nx.y)), fabs(nx.z));  // fmax drops NaN operands, like Rust's f64::max
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  __shared__ double s[8];
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double v = s[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) v = fmax(v, s[w]);
+    // non-negative doubles order like their bit patterns
+    if (v > 0.0) atomicMax(extent_out, static_cast<unsigned long long>(__double_as_longlong(v)));
+  }
+}
+
+__global__ void __launch_bounds__(256) verlet_velocity_kernel(const double4* __restrict__ cur,
+                                                              const double4* __restrict__ prev,
+                                                              double4* __restrict__ vel, size_t n, double dt) {
+  const size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const double4 x = cur[i], p = prev[i];
+  vel[i] = make_double4(__ddiv_rn(__dsub_rn(x.x, p.x), dt), __ddiv_rn(__dsub_rn(x.y, p.y), dt),
+                        __ddiv_rn(__dsub_rn(x.z, p.z), dt), 0.0);  // (x' - x)/dt     (verlet.rs:68-70)
+}
+
 // ---- rk4 (integrators/src/rk4.rs:23-183) -----------------------------------------------------
 // One kernel per stage.  k = (dt * v_at, dt * a) is folded into the running sums
 // S = ((k1 + 2 k2) + 2 k3) + k4 in the reference's left-to-right order, and the next evaluation
@@ -173,6 +222,25 @@ cudaError_t rk4_stage(int stage, const double4* e_pos, const double4* e_vel, con
     else if (stage == 3) PB_RK4(3, false); else PB_RK4(4, false);
   }
 #undef PB_RK4
+  return cudaGetLastError();
+}
+
+cudaError_t verlet_update_lean(const double4* cur, double4* prev_inout, const float4* acc32, size_t n, double dt,
+                               unsigned long long* extent_out, unsigned long long* extent_zero, cudaStream_t st,
+                               LaunchStats& ls) {
+  if (n == 0) return cudaSuccess;
+  const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
+  const double dt2 = dt * dt;  // dt.powi(2)
+  PB_LAUNCH(ls, st, "verlet_lean_kernel",
+            verlet_lean_kernel<<<blocks, 256, 0, st>>>(cur, prev_inout, acc32, n, dt2, extent_out, extent_zero));
+  return cudaGetLastError();
+}
+
+cudaError_t verlet_velocity(const double4* cur, const double4* prev, double4* vel, size_t n, double dt,
+                            cudaStream_t st, LaunchStats& ls) {
+  if (n == 0) return cudaSuccess;
+  const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
+  PB_LAUNCH(ls, st, "verlet_velocity_kernel", verlet_velocity_kernel<<<blocks, 256, 0, st>>>(cur, prev, vel, n, dt));
   return cudaGetLastError();
 }
 

@@ -130,6 +130,38 @@ def test_unverified_chunks_equal_checked_steps(name, theta):
     assert st["sort_bits"] <= 63 and st["replays"] <= 2
 
 
+@pytest.mark.parametrize("name,theta", [("astro", 1.3), ("astro2", 0.7), ("simple_astro", 1.0)])
+def test_lean_resident_steps_equal_general_kernel(name, theta, monkeypatch):
+    """The device-resident loop's lean verlet step (x_{n+1} written over x_{n-1}, buffers swapped, velocity
+    derived on demand, extent of the new positions handed to the next tree build) must leave the same bits
+    as the general kernel, also when the state is read out mid-run and when the integrator changes."""
+    s = gen.readme_pipeline(20_000, seed=12, spin=1000.0)
+    dt = 2e-5
+
+    def run(lean):
+        monkeypatch.setenv("PB200_VERLET_LEAN", "1" if lean else "0")
+        sim = api.Sim(name, theta=theta, e=0.5, dt=dt)
+        sim.upload(s)
+        outs = []
+        sim.run(1)
+        outs.append(sim.download(s.copy()))      # after the first-step formula
+        sim.run(4)
+        outs.append(sim.download(s.copy()))      # mid-run read-out (velocities materialised)
+        sim.run(35)                              # crosses a 32-step checkpoint
+        outs.append(sim.download(s.copy()))
+        sim.set_integrator("euler")              # needs the velocities of the current state
+        sim.run(2)
+        sim.set_integrator("verlet")             # first-step formula again, then lean steps
+        sim.run(3)
+        outs.append(sim.download(s.copy()))
+        return outs
+
+    a, b = run(True), run(False)
+    for i, (x, y) in enumerate(zip(a, b)):
+        for k in POS:
+            assert np.array_equal(x[k], y[k]), (i, k)
+
+
 def potential(s, e):
     """Conserved potential of the reference's force law: U = -mi mj (pi/2 - atan(r/sqrt(e)))/sqrt(e)."""
     p = np.stack([s["x"], s["y"], s["z"]], 1)
