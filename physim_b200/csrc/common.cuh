@@ -119,6 +119,8 @@ struct GravityWorkspace {
   DevBuf src4, key0, key1, idx0, idx1, bucket_key, bucket_idx, splitters, nsv1, nsv2, spos64, ab, cell_start, scan_tmp, tile_counts, digit_base,
       extent_bits, tgt_list, tgt_flags;
   DevBuf c_level, c_head, c_count, c_skip, c_parent, c_arrived, c_centre_ext, c_com;
+  DevBuf c_kids, c_ready;       // child tables / climb starts of the cells summed bottom-up
+  bool parents_filled = false;  // c_parent holds every cell's parent (else only those the bottom-up sums needed)
   DevBuf acc, acc_part, counters, sticky;
   size_t n_cells = 0;   // cells of the last checked evaluation
   size_t cell_cap = 0;  // capacity of the cell arrays
@@ -250,6 +252,7 @@ struct TreeCheck {
 };
 cudaError_t gravity_check(GravityWorkspace& ws, cudaStream_t stream, TreeCheck* out);
 cudaError_t gravity_cell_total(GravityWorkspace& ws, cudaStream_t stream, uint32_t* total);
+cudaError_t gravity_fill_parents(GravityWorkspace& ws, cudaStream_t stream, LaunchStats& ls);
 // Sum of per-target interaction counters of the last evaluation (synchronises the stream).
 cudaError_t gravity_count_interactions(GravityWorkspace& ws, cudaStream_t stream, LaunchStats& ls,
                                        uint64_t* out);

@@ -987,6 +987,7 @@ int pb200_transform_debug_tree(void* obj, uint64_t* key, uint32_t* perm, uint32_
   const size_t n = t.last_n, c = t.ws.n_cells;
   auto run = [&]() -> cudaError_t {
     if (t.have_tree) {
+      PB_PASS(gravity_fill_parents(t.ws, st, t.ls));
       PB_PASS(copy_out(key, t.ws.sorted_key, n, st));
       PB_PASS(copy_out(perm, t.ws.perm, n, st));
       PB_PASS(copy_out(cell_start, t.ws.cell_start.p, n + 1, st));

@@ -998,8 +998,8 @@ __device__ __forceinline__ size_t nsv_next_le_short(const NsvTables& tv, size_t 
 //     body order.  Larger cells are left to the bottom-up pass (K7).
 //     (cells_kernel_chain below is the earlier per-lane form: each lane loops over its own chain, the
 //     ends found leaf -> top and one running sum per chain; same results, ~10 of 32 lanes busy.)
-template <int DIM>
-__global__ void __launch_bounds__(256) cells_kernel(const uint64_t* __restrict__ key,
+template <int DIM, int MIN_BLOCKS>
+__global__ void __launch_bounds__(256, MIN_BLOCKS) cells_kernel(const uint64_t* __restrict__ key,
                                                     const double4* __restrict__ sp,
                                                     const uint32_t* __restrict__ perm,
                                                     const uchar2* __restrict__ ab,
@@ -1018,19 +1018,26 @@ __global__ void __launch_bounds__(256) cells_kernel(const uint64_t* __restrict__
     atomicMax(&sticky[1], tree_meta[0]);
   }
   if (total > cells.capacity || *cells.bad) return;  // host grows the table / sorts all bits and re-runs (grid-uniform)
-  const uchar2 abv = s < n ? ab[s] : make_uchar2(NOT_HEAD, NOT_HEAD);
+  // everything phase 1 reads is fetched up front, unconditionally: one round of memory latency instead
+  // of four dependent ones (the body after s is the end of the leaf unless it was merged into it)
+  const bool in_range = s < n;
+  const uchar2 abv = in_range ? ab[s] : make_uchar2(NOT_HEAD, NOT_HEAD);
+  const uchar2 abn = s + 1 < n ? ab[s + 1] : make_uchar2(0, 0);
+  const uint32_t cs0 = in_range ? cell_start[s] : 0u, cs1 = in_range ? cell_start[s + 1] : 0u;
+  const uint64_t kme = in_range ? key[s] : 0ull;
+  const double4 me = in_range ? sp[s] : make_double4(0.0, 0.0, 0.0, 0.0);
+  const double ext0 = __longlong_as_double(static_cast<long long>(*extent_bits));
+  const bool merged_units = tree_meta[1] != 0u;
   const bool is_head = abv.x != NOT_HEAD;  // (lanes past n and merged bodies stay for the shuffles)
   int top = 0, leaf_level = 0;
   uint32_t c0 = 0;
   if (is_head) {
-    c0 = cell_start[s];
+    c0 = cs0;
     if (s == 0) cells.parent[0] = NO_PARENT;
     const int a = int(abv.x) - 1, b = int(abv.y) - 1;
     top = a + 1;
     leaf_level = max(a, b) + 1;
-    const uint64_t kme = key[s];
-    const double4 me = sp[s];
-    double half = __longlong_as_double(static_cast<long long>(*extent_bits));
+    double half = ext0;
     double cx = 0.0, cy = 0.0, cz = 0.0;
     for (int l = 0; l <= leaf_level; ++l) {
       if (l >= top) {
@@ -1055,12 +1062,18 @@ __global__ void __launch_bounds__(256) cells_kernel(const uint64_t* __restrict__
       }
     }
     // leaf: the unit itself
-    size_t e = s + 1;
-    while (e < n && ab[e].x == NOT_HEAD) ++e;
     const uint32_t c = c0 + uint32_t(leaf_level - top);
-    cells.count[c] = static_cast<uint32_t>(e - s);
-    cells.skip[c] = cell_start[e];
-    cells.com[c] = unit_leaf(sp, perm, s, e);
+    if (abn.x != NOT_HEAD) {  // (always, unless bodies were merged)
+      cells.count[c] = 1u;
+      cells.skip[c] = cs1;
+      cells.com[c] = me;
+    } else {
+      size_t e = s + 2;
+      while (e < n && ab[e].x == NOT_HEAD) ++e;
+      cells.count[c] = static_cast<uint32_t>(e - s);
+      cells.skip[c] = cell_start[e];
+      cells.com[c] = unit_leaf(sp, perm, s, e);
+    }
   }
 
   // phase 2: task t of the warp = internal cell number (t - excl[o]) of the chain of lane o
@@ -1073,7 +1086,6 @@ __global__ void __launch_bounds__(256) cells_kernel(const uint64_t* __restrict__
   }
   const int n_tasks = __shfl_sync(FULL, incl, 31);
   const int excl = incl - mine;
-  const bool merged_units = tree_meta[1] != 0u;
   for (int t0 = 0; t0 < n_tasks; t0 += 32) {
     const int t = t0 + int(lane);
     int o = 0;  // number of lanes whose inclusive count is <= t  ==  the lane that owns task t
@@ -1122,7 +1134,7 @@ __global__ void __launch_bounds__(256) cells_kernel(const uint64_t* __restrict__
       cells.com[c] = make_double4(sx * inv, sy * inv, sz * inv, sm);
     } else {
       // (written by another lane in phase 1: recompute instead of reading it back)
-      double half = __longlong_as_double(static_cast<long long>(*extent_bits));
+      double half = ext0;
       double gx = 0.0, gy = 0.0, gz = 0.0;
       const uint64_t ko = key[so];
       const double4 mo = sp[so];
@@ -1333,6 +1345,142 @@ __global__ void __launch_bounds__(128) com_kernel(const uchar2* __restrict__ ab,
     cells.com[p] = out;
     wrote = true;
     c = p;
+  }
+}
+
+// K7 (current form)  the same sums in two kernels without the per-unit scan and with one round of
+//     loads per level instead of a chain through the skip links:
+//     kids_kernel, one thread per cell, acts on the cells K6 left open (more than SMALL_CELL bodies, not
+//     a leaf): walks the children once and leaves kid_tab[p] = {number of children, child 1, child 2, ..}
+//     (child 0 is p + 1), the parent link of every child that is open itself, arrived[p] = the bodies of
+//     the children K6 already finished, and ready[p] = "all of them": a climb starts here.
+//     climb_kernel: the thread of a ready cell sums its children in pre-order, then arrives at the parent
+//     (release atomic on the body counter); whoever completes a cell goes on with it.  Per level:
+//     parent link -> atomic (the child table and the counts load meanwhile) -> the children's sums (one
+//     round of ld.cg) -> store.  Same operations in the same order as com_kernel: identical bits.
+constexpr uint32_t KIDS_OVERFLOW = 0xffffffffu;  // more children than 2^DIM (sibling leaves of a pseudo level)
+
+template <int DIM>
+__global__ void __launch_bounds__(256) kids_kernel(const uint32_t* __restrict__ cell_start, size_t n,
+                                                   CellArrays cells, uint32_t* __restrict__ kid_tab,
+                                                   uint32_t* __restrict__ ready_list, unsigned* __restrict__ n_ready) {
+  constexpr uint32_t K = 1u << DIM;
+  __shared__ uint32_t s_list[256];
+  __shared__ uint32_t s_n, s_base;
+  if (threadIdx.x == 0) s_n = 0u;
+  __syncthreads();
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t total = cell_start[n];
+  const bool live = !(total > cells.capacity || *cells.bad) && p < total;
+  if (live) {
+    const uint32_t cnt = cells.count[p], end = cells.skip[p];
+    if (cnt > cells.small && end != p + 1u) {
+      uint32_t nk = 0, pre = 0;
+      for (uint32_t ch = p + 1u; ch < end;) {
+        const uint32_t c_cnt = cells.count[ch], next = cells.skip[ch];
+        if (c_cnt <= cells.small || next == ch + 1u) pre += c_cnt;  // finished by K6
+        else cells.parent[ch] = p;                                  // climbs later
+        if (nk >= 1u && nk < K) kid_tab[size_t(p) * K + nk] = ch;
+        ++nk;
+        if (next <= ch) break;  // (never in a well-formed table; keeps a broken one from hanging the GPU)
+        ch = next;
+      }
+      kid_tab[size_t(p) * K] = nk <= K ? nk : KIDS_OVERFLOW;
+      cells.arrived[p] = pre;
+      if (pre == cnt) s_list[atomicAdd(&s_n, 1u)] = p;  // a climb starts here
+    }
+  }
+  // the block's climb starts go to the global list with one atomic (their order there does not matter:
+  // every sum is taken by one thread, over the children in pre-order)
+  __syncthreads();
+  if (threadIdx.x == 0 && s_n) s_base = atomicAdd(n_ready, s_n);
+  __syncthreads();
+  if (threadIdx.x < s_n) ready_list[s_base + threadIdx.x] = s_list[threadIdx.x];
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(128) climb_kernel(const uint32_t* __restrict__ cell_start, size_t n,
+                                                    CellArrays cells, const uint32_t* __restrict__ kid_tab,
+                                                    const uint32_t* __restrict__ ready_list,
+                                                    const unsigned* __restrict__ n_ready) {
+  constexpr int K = 1 << DIM;
+  const uint32_t total = cell_start[n];
+  if (total > cells.capacity || *cells.bad) return;
+  const uint32_t starts = *n_ready;
+  for (uint32_t it = blockIdx.x * blockDim.x + threadIdx.x; it < starts; it += gridDim.x * blockDim.x) {
+  const uint32_t p0 = ready_list[it];
+  // what the climb needs to know about a cell (immutable during this kernel): fetched for the parent while
+  // the children's sums of the current cell are still on their way, so that a level costs one round of
+  // loads (the children's sums) + store + release atomic
+  struct Meta {
+    uint32_t parent, count;
+    uint32_t kid[K];
+  };
+  auto load_meta = [&](uint32_t c) {
+    Meta mt;
+    mt.parent = cells.parent[c];
+    mt.count = cells.count[c];
+#pragma unroll
+    for (int q = 0; q < K / 4; ++q) {
+      const uint4 w = reinterpret_cast<const uint4*>(kid_tab + size_t(c) * K)[q];
+      mt.kid[4 * q] = w.x; mt.kid[4 * q + 1] = w.y; mt.kid[4 * q + 2] = w.z; mt.kid[4 * q + 3] = w.w;
+    }
+    return mt;
+  };
+  uint32_t c = p0;
+  Meta me = load_meta(c);
+  while (true) {
+    const uint32_t nk = me.kid[0];
+    me.kid[0] = c + 1u;
+    double m = 0.0, sx = 0.0, sy = 0.0, sz = 0.0;
+    double4 q[K];
+    if (nk != KIDS_OVERFLOW) {
+#pragma unroll
+      for (int i = 0; i < K; ++i)
+        if (uint32_t(i) < nk) q[i] = ld_cg_double4(&cells.com[me.kid[i]]);
+    }
+    const double4 g = cells.centre_ext[c];
+    Meta up;  // the parent's, in case this thread completes it
+    if (me.parent != NO_PARENT) up = load_meta(me.parent);
+    if (nk != KIDS_OVERFLOW) {
+#pragma unroll
+      for (int i = 0; i < K; ++i)
+        if (uint32_t(i) < nk) {
+          m += q[i].w;
+          sx += q[i].w * q[i].x;
+          sy += q[i].w * q[i].y;
+          sz += q[i].w * q[i].z;
+        }
+    } else {
+      const uint32_t end = cells.skip[c];
+      for (uint32_t ch = c + 1u; ch < end;) {
+        const double4 qq = ld_cg_double4(&cells.com[ch]);
+        m += qq.w;
+        sx += qq.w * qq.x;
+        sy += qq.w * qq.y;
+        sz += qq.w * qq.z;
+        const uint32_t next = cells.skip[ch];
+        if (next <= ch) break;
+        ch = next;
+      }
+    }
+    double4 out;
+    if (m != 0.0) {
+      const double inv = 1.0 / m;  // (…) * inv_total_mass, lib.rs:43-49
+      out = make_double4(sx * inv, sy * inv, sz * inv, m);
+    } else {  // a massless cell (the reference panics there): geometric centre instead of 0/0
+      out = make_double4(g.x, g.y, g.z, 0.0);
+    }
+    cells.com[c] = out;
+    if (me.parent == NO_PARENT) break;
+    // release: com[c] must be visible (at L2) before the arrival is.  The children are read with ld.cg
+    // straight from L2, so no acquire fence (which would invalidate this SM's whole L1) is needed.
+    cuda::atomic_ref<uint32_t, cuda::thread_scope_device> arrived(cells.arrived[me.parent]);
+    const uint32_t old = arrived.fetch_add(me.count, cuda::std::memory_order_release);
+    if (old + me.count != up.count) break;
+    c = me.parent;
+    me = up;
+  }
   }
 }
 
@@ -1953,6 +2101,7 @@ cudaError_t tree_evaluate(GravityWorkspace& ws, const GravityParams& prm, size_t
 
   // extent_bits words: [0,1] extent (u64 bits)  [2] 1 + deepest level shared by distinct keys
   // [3] some leaf is a merged unit  [4] keys not fully ordered (truncated sort too short)
+  // [6] number of climb starts (kids_kernel -> climb_kernel)
   PB_CUDA(cudaMemsetAsync(ws.extent_bits.p, 0, scratch_bytes, st));
   unsigned long long* scan_scratch = ws.extent_bits.as<unsigned long long>() + 4;
   unsigned* sort_head = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(ws.extent_bits.p) + 32 + scan_bytes);
@@ -2018,15 +2167,38 @@ cudaError_t tree_evaluate(GravityWorkspace& ws, const GravityParams& prm, size_t
                                                           ws.extent_cur, max_shared_plus1,
                                                           ws.sticky.as<unsigned>(), tv, cells));
   } else {
-    PB_LAUNCH(ls, st, "cells_kernel",
-              cells_kernel<DIM><<<nb, 256, 0, st>>>(ws.sorted_key, ws.spos64.as<double4>(), ws.perm,
-                                                    ws.ab.as<uchar2>(), ws.cell_start.as<uint32_t>(), n,
-                                                    ws.extent_cur, max_shared_plus1,
-                                                    ws.sticky.as<unsigned>(), tv, cells));
+    static const bool cells_b5 = std::getenv("PB200_CELLS") && std::string(std::getenv("PB200_CELLS")) == "b5";
+    if (cells_b5)
+      PB_LAUNCH(ls, st, "cells_kernel",
+                (cells_kernel<DIM, 5><<<nb, 256, 0, st>>>(ws.sorted_key, ws.spos64.as<double4>(), ws.perm,
+                                                          ws.ab.as<uchar2>(), ws.cell_start.as<uint32_t>(), n,
+                                                          ws.extent_cur, max_shared_plus1,
+                                                          ws.sticky.as<unsigned>(), tv, cells)));
+    else
+      PB_LAUNCH(ls, st, "cells_kernel",
+                (cells_kernel<DIM, 4><<<nb, 256, 0, st>>>(ws.sorted_key, ws.spos64.as<double4>(), ws.perm,
+                                                          ws.ab.as<uchar2>(), ws.cell_start.as<uint32_t>(), n,
+                                                          ws.extent_cur, max_shared_plus1,
+                                                          ws.sticky.as<unsigned>(), tv, cells)));
   }
-  PB_LAUNCH(ls, st, "parent_kernel",
-            parent_kernel<<<blocks_for(cap, 256), 256, 0, st>>>(ws.cell_start.as<uint32_t>(), n, cells));
-  PB_LAUNCH(ls, st, "com_kernel", com_kernel<<<nb128, 128, 0, st>>>(ws.ab.as<uchar2>(), ws.cell_start.as<uint32_t>(), n, cells));
+  static const bool com_old = std::getenv("PB200_COM") && std::string(std::getenv("PB200_COM")) == "old";
+  ws.parents_filled = false;
+  if (com_old) {
+    PB_LAUNCH(ls, st, "parent_kernel",
+              parent_kernel<<<blocks_for(cap, 256), 256, 0, st>>>(ws.cell_start.as<uint32_t>(), n, cells));
+    ws.parents_filled = true;
+    PB_LAUNCH(ls, st, "com_kernel", com_kernel<<<nb128, 128, 0, st>>>(ws.ab.as<uchar2>(), ws.cell_start.as<uint32_t>(), n, cells));
+  } else {
+    PB_PASS(ws.c_kids.ensure(cap * (size_t(4) << DIM)));
+    PB_PASS(ws.c_ready.ensure((cap / 2 + 256) * 4));  // (a start has >= 2 finished children: < cap / 3 of them)
+    unsigned* n_ready = max_shared_plus1 + 4;         // word 6 of the build's zeroed scratch block
+    PB_LAUNCH(ls, st, "kids_kernel",
+              kids_kernel<DIM><<<blocks_for(cap, 256), 256, 0, st>>>(ws.cell_start.as<uint32_t>(), n, cells,
+                                                                     ws.c_kids.as<uint32_t>(), ws.c_ready.as<uint32_t>(), n_ready));
+    PB_LAUNCH(ls, st, "climb_kernel",
+              climb_kernel<DIM><<<148 * 4, 128, 0, st>>>(ws.cell_start.as<uint32_t>(), n, cells,
+                                                         ws.c_kids.as<uint32_t>(), ws.c_ready.as<uint32_t>(), n_ready));
+  }
 
   const uint32_t* list = nullptr;
   const size_t n_targets = t1 - t0;
@@ -2104,7 +2276,7 @@ cudaError_t direct_evaluate(GravityWorkspace& ws, size_t t0, size_t t1, float ea
 void GravityWorkspace::release_all() {
   DevBuf* all[] = {&src4, &key0, &key1, &idx0, &idx1, &bucket_key, &bucket_idx, &splitters, &nsv1, &nsv2, &spos64, &ab, &cell_start, &scan_tmp,
                    &tile_counts, &digit_base, &extent_bits, &tgt_list, &tgt_flags, &c_level, &c_head,
-                   &c_count, &c_skip, &c_parent, &c_arrived, &c_centre_ext, &c_com, &acc, &acc_part, &sticky,
+                   &c_count, &c_skip, &c_parent, &c_arrived, &c_kids, &c_ready, &c_centre_ext, &c_com, &acc, &acc_part, &sticky,
                    &counters};
   for (DevBuf* b : all) b->release();
 }
@@ -2205,6 +2377,20 @@ cudaError_t gravity_check(GravityWorkspace& ws, cudaStream_t st, TreeCheck* out)
     ws.sort_lo = std::max(0, key_bits - dim * want_levels);
   }
   return cudaSuccess;
+}
+
+// every cell's parent link, for inspection (the bottom-up sums only set the links they climb through)
+cudaError_t gravity_fill_parents(GravityWorkspace& ws, cudaStream_t st, LaunchStats& ls) {
+  if (ws.parents_filled || ws.n == 0 || ws.tree_dim == 0 || !ws.c_parent.p || !ws.cell_cap) return cudaSuccess;
+  unsigned* flags = reinterpret_cast<unsigned*>(ws.extent_bits.as<unsigned long long>() + 1);
+  CellArrays cells{ws.c_level.as<uint8_t>(),   ws.c_head.as<uint32_t>(),  ws.c_count.as<uint32_t>(),
+                   ws.c_skip.as<uint32_t>(),   ws.c_parent.as<uint32_t>(), ws.c_arrived.as<uint32_t>(),
+                   ws.c_centre_ext.as<double4>(), ws.c_com.as<double4>(), static_cast<uint32_t>(ws.cell_cap), SMALL_CELL,
+                   flags + 2};
+  PB_LAUNCH(ls, st, "parent_kernel",
+            parent_kernel<<<blocks_for(ws.cell_cap, 256), 256, 0, st>>>(ws.cell_start.as<uint32_t>(), ws.n, cells));
+  ws.parents_filled = true;
+  return cudaGetLastError();
 }
 
 cudaError_t gravity_cell_total(GravityWorkspace& ws, cudaStream_t st, uint32_t* total) {
