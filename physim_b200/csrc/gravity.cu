@@ -1358,57 +1358,68 @@ __global__ void __launch_bounds__(128) com_kernel(const uchar2* __restrict__ ab,
 //     (release atomic on the body counter); whoever completes a cell goes on with it.  Per level:
 //     parent link -> atomic (the child table and the counts load meanwhile) -> the children's sums (one
 //     round of ld.cg) -> store.  Same operations in the same order as com_kernel: identical bits.
-constexpr uint32_t KIDS_OVERFLOW = 0xffffffffu;  // more children than 2^DIM (sibling leaves of a pseudo level)
+constexpr uint32_t KIDS_OVERFLOW = 0xffffffffu;
+constexpr uint32_t READY_LISTS = 16;
+constexpr uint32_t READY_STRIDE = 32;  // words between the lists' counters: one 128-byte line (one L2 atomic unit) each  // more children than 2^DIM (sibling leaves of a pseudo level)
 
 template <int DIM>
 __global__ void __launch_bounds__(256) kids_kernel(const uint32_t* __restrict__ cell_start, size_t n,
                                                    CellArrays cells, uint32_t* __restrict__ kid_tab,
-                                                   uint32_t* __restrict__ ready_list, unsigned* __restrict__ n_ready) {
+                                                   uint32_t* __restrict__ ready_list, unsigned* __restrict__ n_ready,
+                                                   uint32_t sub_cap) {
   constexpr uint32_t K = 1u << DIM;
-  __shared__ uint32_t s_list[256];
-  __shared__ uint32_t s_n, s_base;
-  if (threadIdx.x == 0) s_n = 0u;
-  __syncthreads();
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t total = cell_start[n];
   const bool live = !(total > cells.capacity || *cells.bad) && p < total;
+  uint32_t cnt = 0, end = 0;
   if (live) {
-    const uint32_t cnt = cells.count[p], end = cells.skip[p];
-    if (cnt > cells.small && end != p + 1u) {
-      uint32_t nk = 0, pre = 0;
-      for (uint32_t ch = p + 1u; ch < end;) {
-        const uint32_t c_cnt = cells.count[ch], next = cells.skip[ch];
-        if (c_cnt <= cells.small || next == ch + 1u) pre += c_cnt;  // finished by K6
-        else cells.parent[ch] = p;                                  // climbs later
-        if (nk >= 1u && nk < K) kid_tab[size_t(p) * K + nk] = ch;
-        ++nk;
-        if (next <= ch) break;  // (never in a well-formed table; keeps a broken one from hanging the GPU)
-        ch = next;
-      }
-      kid_tab[size_t(p) * K] = nk <= K ? nk : KIDS_OVERFLOW;
-      cells.arrived[p] = pre;
-      if (pre == cnt) s_list[atomicAdd(&s_n, 1u)] = p;  // a climb starts here
-    }
+    cnt = cells.count[p];
+    end = cells.skip[p];
   }
-  // the block's climb starts go to the global list with one atomic (their order there does not matter:
-  // every sum is taken by one thread, over the children in pre-order)
-  __syncthreads();
-  if (threadIdx.x == 0 && s_n) s_base = atomicAdd(n_ready, s_n);
-  __syncthreads();
-  if (threadIdx.x < s_n) ready_list[s_base + threadIdx.x] = s_list[threadIdx.x];
+  const bool open = live && cnt > cells.small && end != p + 1u;
+  if (!__any_sync(FULL, open)) return;  // (most warps: nothing but finished cells)
+  bool start = false;
+  if (open) {
+    uint32_t nk = 0, pre = 0;
+    for (uint32_t ch = p + 1u; ch < end;) {
+      const uint32_t c_cnt = cells.count[ch], next = cells.skip[ch];
+      if (c_cnt <= cells.small || next == ch + 1u) pre += c_cnt;  // finished by K6
+      else cells.parent[ch] = p;                                  // climbs later
+      if (nk >= 1u && nk < K) kid_tab[size_t(p) * K + nk] = ch;
+      ++nk;
+      if (next <= ch) break;  // (never in a well-formed table; keeps a broken one from hanging the GPU)
+      ch = next;
+    }
+    kid_tab[size_t(p) * K] = nk <= K ? nk : KIDS_OVERFLOW;
+    cells.arrived[p] = pre;
+    start = pre == cnt;  // a climb starts here
+  }
+  // the warp's climb starts go to one of READY_LISTS global lists with one atomic (one list: ~25000
+  // same-address atomics with a return value cost ~20 us; a block-wide hand-over costs a barrier behind
+  // the slowest walk; the order inside a list does not matter: every sum is taken by one thread, over
+  // the children in pre-order)
+  const unsigned who = __ballot_sync(FULL, start);
+  if (!who) return;
+  const unsigned lane = threadIdx.x & 31u, leader = unsigned(__ffs(who) - 1);
+  const uint32_t l = (p >> 5) % READY_LISTS;
+  uint32_t base = 0;
+  if (lane == leader) base = atomicAdd(n_ready + l * READY_STRIDE, unsigned(__popc(who)));
+  base = __shfl_sync(FULL, base, leader);
+  if (start) ready_list[size_t(l) * sub_cap + base + __popc(who & ((1u << lane) - 1u))] = p;
 }
 
 template <int DIM>
 __global__ void __launch_bounds__(128) climb_kernel(const uint32_t* __restrict__ cell_start, size_t n,
                                                     CellArrays cells, const uint32_t* __restrict__ kid_tab,
                                                     const uint32_t* __restrict__ ready_list,
-                                                    const unsigned* __restrict__ n_ready) {
+                                                    const unsigned* __restrict__ n_ready, uint32_t sub_cap) {
   constexpr int K = 1 << DIM;
   const uint32_t total = cell_start[n];
   if (total > cells.capacity || *cells.bad) return;
-  const uint32_t starts = *n_ready;
-  for (uint32_t it = blockIdx.x * blockDim.x + threadIdx.x; it < starts; it += gridDim.x * blockDim.x) {
-  const uint32_t p0 = ready_list[it];
+  const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t l = gt % READY_LISTS, starts = n_ready[l * READY_STRIDE];
+  for (uint32_t it = gt / READY_LISTS; it < starts; it += gridDim.x * blockDim.x / READY_LISTS) {
+  const uint32_t p0 = ready_list[size_t(l) * sub_cap + it];
   // what the climb needs to know about a cell (immutable during this kernel): fetched for the parent while
   // the children's sums of the current cell are still on their way, so that a level costs one round of
   // loads (the children's sums) + store + release atomic
@@ -2082,9 +2093,10 @@ template <int DIM>
 cudaError_t tree_evaluate(GravityWorkspace& ws, const GravityParams& prm, size_t t0, size_t t1,
                           float easing, float tiny, cudaStream_t st, LaunchStats& ls) {
   const size_t n = ws.n;
-  // one zeroed scratch block per build: [extent / flags: 32 B][scan status + counter][sort head]
+  // one zeroed scratch block per build: [extent / flags: 32 B][scan status + counter][sort head][climb-start counters]
   const size_t scan_bytes = (scan_scratch_bytes(n) + 15) / 16 * 16;
-  const size_t scratch_bytes = 32 + scan_bytes + SORT_HEAD_WORDS * 4;
+  const size_t ready_off = (32 + scan_bytes + SORT_HEAD_WORDS * 4 + 127) / 128 * 128;
+  const size_t scratch_bytes = ready_off + size_t(READY_LISTS) * READY_STRIDE * 4;
   PB_PASS(ws.extent_bits.ensure(scratch_bytes));
   if (!ws.sticky.p) {
     PB_PASS(ws.sticky.ensure(16));
@@ -2101,10 +2113,10 @@ cudaError_t tree_evaluate(GravityWorkspace& ws, const GravityParams& prm, size_t
 
   // extent_bits words: [0,1] extent (u64 bits)  [2] 1 + deepest level shared by distinct keys
   // [3] some leaf is a merged unit  [4] keys not fully ordered (truncated sort too short)
-  // [6] number of climb starts (kids_kernel -> climb_kernel)
   PB_CUDA(cudaMemsetAsync(ws.extent_bits.p, 0, scratch_bytes, st));
   unsigned long long* scan_scratch = ws.extent_bits.as<unsigned long long>() + 4;
   unsigned* sort_head = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(ws.extent_bits.p) + 32 + scan_bytes);
+  unsigned* n_ready = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(ws.extent_bits.p) + ready_off);
   unsigned* max_shared_plus1 = reinterpret_cast<unsigned*>(ws.extent_bits.as<unsigned long long>() + 1);
   const int key_bits = DIM * TreeDim<DIM>::LM;
   if (ws.tree_dim != DIM) ws.sort_lo = 0, ws.sort_mode = 0;  // depth / bucket estimates belong to the other tree kind
@@ -2167,14 +2179,6 @@ cudaError_t tree_evaluate(GravityWorkspace& ws, const GravityParams& prm, size_t
                                                           ws.extent_cur, max_shared_plus1,
                                                           ws.sticky.as<unsigned>(), tv, cells));
   } else {
-    static const bool cells_b5 = std::getenv("PB200_CELLS") && std::string(std::getenv("PB200_CELLS")) == "b5";
-    if (cells_b5)
-      PB_LAUNCH(ls, st, "cells_kernel",
-                (cells_kernel<DIM, 5><<<nb, 256, 0, st>>>(ws.sorted_key, ws.spos64.as<double4>(), ws.perm,
-                                                          ws.ab.as<uchar2>(), ws.cell_start.as<uint32_t>(), n,
-                                                          ws.extent_cur, max_shared_plus1,
-                                                          ws.sticky.as<unsigned>(), tv, cells)));
-    else
       PB_LAUNCH(ls, st, "cells_kernel",
                 (cells_kernel<DIM, 4><<<nb, 256, 0, st>>>(ws.sorted_key, ws.spos64.as<double4>(), ws.perm,
                                                           ws.ab.as<uchar2>(), ws.cell_start.as<uint32_t>(), n,
@@ -2190,14 +2194,16 @@ cudaError_t tree_evaluate(GravityWorkspace& ws, const GravityParams& prm, size_t
     PB_LAUNCH(ls, st, "com_kernel", com_kernel<<<nb128, 128, 0, st>>>(ws.ab.as<uchar2>(), ws.cell_start.as<uint32_t>(), n, cells));
   } else {
     PB_PASS(ws.c_kids.ensure(cap * (size_t(4) << DIM)));
-    PB_PASS(ws.c_ready.ensure((cap / 2 + 256) * 4));  // (a start has >= 2 finished children: < cap / 3 of them)
-    unsigned* n_ready = max_shared_plus1 + 4;         // word 6 of the build's zeroed scratch block
+    // (a warp of 32 cells holds at most 32 starts; list l takes the warps = l mod READY_LISTS)
+    const unsigned kid_blocks = blocks_for(cap, 256);
+    const uint32_t sub_cap = ((kid_blocks + READY_LISTS - 1) / READY_LISTS) * 256u;
+    PB_PASS(ws.c_ready.ensure(size_t(READY_LISTS) * sub_cap * 4));
     PB_LAUNCH(ls, st, "kids_kernel",
-              kids_kernel<DIM><<<blocks_for(cap, 256), 256, 0, st>>>(ws.cell_start.as<uint32_t>(), n, cells,
-                                                                     ws.c_kids.as<uint32_t>(), ws.c_ready.as<uint32_t>(), n_ready));
+              kids_kernel<DIM><<<kid_blocks, 256, 0, st>>>(ws.cell_start.as<uint32_t>(), n, cells,
+                                                           ws.c_kids.as<uint32_t>(), ws.c_ready.as<uint32_t>(), n_ready, sub_cap));
     PB_LAUNCH(ls, st, "climb_kernel",
               climb_kernel<DIM><<<148 * 4, 128, 0, st>>>(ws.cell_start.as<uint32_t>(), n, cells,
-                                                         ws.c_kids.as<uint32_t>(), ws.c_ready.as<uint32_t>(), n_ready));
+                                                         ws.c_kids.as<uint32_t>(), ws.c_ready.as<uint32_t>(), n_ready, sub_cap));
   }
 
   const uint32_t* list = nullptr;
