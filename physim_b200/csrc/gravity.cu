@@ -953,11 +953,31 @@ __device__ __forceinline__ int first_le_16(const uint4& w, unsigned splat, int o
   return pos;
 }
 
-// The same query in at most three rounds of INDEPENDENT loads for runs of up to 288 bodies (the table
-// descent is 9 dependent byte loads per level of the hierarchy, and nearly every warp holds one cell
-// that needs it): (1) the level-0 bytes of the 17..32 bodies from j0 on, two 16-byte loads; (2) the
-// level-4 minima (16 bodies each) of the next 16 aligned windows; (3) the level-0 bytes of the first
-// window that holds a hit.  Longer runs continue with the table descent from where the scan stopped.
+// The same query in rounds of INDEPENDENT loads (the table descent is 9 dependent byte loads per level
+// of the hierarchy, and nearly every warp holds one cell that needs it):
+//   (1) the level-0 bytes of the 17..32 bodies from j0 on, two 16-byte loads;
+//   (2) the level-4 minima (16 bodies each) of the aligned windows up to the second block boundary;
+//   (3) the level-0 bytes of the first window that holds a hit;           -> runs of up to ~290 bodies
+//   (4) the minima of the next 17..32 blocks of 256 bodies, two 16-byte loads, then (2') the 16 windows
+//       of the block that holds the hit and (3) again;                   -> runs of up to ~4000 bodies
+// Longer runs continue with the table descent from where the scan stopped.
+__device__ __forceinline__ size_t nsv_hit_in_windows(const NsvTables& tv, size_t j1, size_t end, unsigned l,
+                                                     unsigned splat) {
+  // first body in [j1, end) (16-aligned, end - j1 <= 31 * 16) whose entry is <= l, else `end`
+  const uint8_t* __restrict__ t4 = tv.t1 + 4 * tv.n_pad;  // min a1[j .. j+16): aligned windows never leave their block
+  int hit = 31;
+#pragma unroll
+  for (int i = 30; i >= 0; --i) {
+    const size_t idx = j1 + 16 * size_t(i);
+    const unsigned v = idx < end ? unsigned(t4[idx]) : unsigned(NSV_NONE);
+    if (v <= l) hit = i;
+  }
+  if (hit == 31) return end;
+  const size_t jw = j1 + 16 * size_t(hit);
+  const uint4 w = *reinterpret_cast<const uint4*>(tv.t1 + jw);
+  return jw + size_t(first_le_16(w, splat, 0));
+}
+
 __device__ __forceinline__ size_t nsv_next_le_short(const NsvTables& tv, size_t j0, unsigned l) {
   if (j0 + 32 > tv.n_pad) return nsv_next_le(tv, j0, l);  // (the 32-byte window would leave level 0)
   const size_t base = j0 & ~size_t(15);
@@ -970,20 +990,26 @@ __device__ __forceinline__ size_t nsv_next_le_short(const NsvTables& tv, size_t 
   pos = first_le_16(w1, splat, 0);
   if (pos < 16) return base + 16 + size_t(pos);
   const size_t j1 = base + 32;
-  const uint8_t* __restrict__ t4 = tv.t1 + 4 * tv.n_pad;  // min a1[j .. j+16): aligned windows never leave their block
-  int hit = 16;
-#pragma unroll
-  for (int i = 15; i >= 0; --i) {
-    const size_t idx = j1 + 16 * size_t(i);
-    const unsigned v = idx < tv.n_pad ? unsigned(t4[idx]) : unsigned(NSV_NONE);
-    if (v <= l) hit = i;
+  const size_t end2 = min(tv.n_pad, ((j1 + 255) | 255) + 1);  // second block boundary after j1: 16..31 windows
+  size_t j = nsv_hit_in_windows(tv, j1, end2, l, splat);
+  if (j < end2) return j;
+  if (end2 >= tv.n) return tv.n;
+  // block minima (level 0 of t2; entries of blocks past nblocks are not initialised: masked by position)
+  const size_t b0 = end2 >> 8, bb = b0 & ~size_t(15);
+  if (bb + 32 > tv.b_pad) return nsv_next_le(tv, end2, l);
+  const uint4 m0 = *reinterpret_cast<const uint4*>(tv.t2 + bb);
+  const uint4 m1 = *reinterpret_cast<const uint4*>(tv.t2 + bb + 16);
+  pos = first_le_16(m0, splat, int(b0 - bb));
+  if (pos == 16) {
+    pos = first_le_16(m1, splat, 0);
+    if (pos < 16) pos += 16; else pos = 32;
   }
-  if (hit < 16) {
-    const size_t jw = j1 + 16 * size_t(hit);
-    const uint4 w = *reinterpret_cast<const uint4*>(tv.t1 + jw);
-    return jw + size_t(first_le_16(w, splat, 0));
-  }
-  return nsv_next_le(tv, j1 + 256, l);
+  const size_t b = bb + size_t(pos);
+  if (b >= tv.nblocks) return tv.n;  // (nothing up to the last block, or a match on an uninitialised entry past it)
+  if (pos == 32) return nsv_next_le(tv, b << 8, l);
+  const size_t lo = b << 8;
+  j = nsv_hit_in_windows(tv, lo, lo + 256, l, splat);
+  return j < lo + 256 ? j : tv.n;  // (always found: the block minimum said so)
 }
 
 // K6  one thread per unit head s, for the chain of cells it heads (levels a+1 .. leaf level).
