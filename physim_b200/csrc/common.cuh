@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <utility>
 #include <vector>
 
 #include "../../include/physim_b200.h"
@@ -221,6 +222,38 @@ struct LaunchStats {
     for (cudaEvent_t e : pool) cudaEventDestroy(e);
   }
 };
+
+// Programmatic dependent launch for the kernels of the step's critical chain: the next kernel's CTAs are
+// scheduled while this one's last CTAs drain (its launch latency and ramp-up hide behind the tail), and
+// wait in pb_pdl_sync() until everything before them in the stream is complete and visible.  A kernel
+// launched this way must call pb_pdl_sync() before it touches global memory.  PB200_PDL=0: plain launches.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pb_pdl_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;");
+}
+#endif
+
+inline bool pb_pdl_enabled() {
+  static const bool v = !(std::getenv("PB200_PDL") && std::atoi(std::getenv("PB200_PDL")) == 0);
+  return v;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t pb_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                 Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pb_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
 
 // PB_LAUNCH(ls, stream, "name", kernel<<<grid, block, smem, stream>>>(args...));
 #define PB_LAUNCH(ls, st, name, ...) \

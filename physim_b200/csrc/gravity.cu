@@ -96,6 +96,7 @@ __device__ __forceinline__ unsigned block_exclusive_scan_256(unsigned v, unsigne
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) extent_kernel(const double4* __restrict__ pos, size_t n,
                                                      unsigned long long* __restrict__ out_bits) {
+  pb_pdl_sync();
   double m = 0.0;
   for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n;
        i += size_t(gridDim.x) * blockDim.x) {
@@ -389,6 +390,7 @@ __global__ void __launch_bounds__(256) encode_bucket_kernel(const double4* __res
                                                             int lo, uint64_t* __restrict__ bkey,
                                                             uint32_t* __restrict__ bidx, unsigned cap,
                                                             unsigned* __restrict__ cursor /*[256]*/) {
+  pb_pdl_sync();
   constexpr int LM = TreeDim<DIM>::LM;
   __shared__ unsigned cnt[256];
   __shared__ unsigned gbase[256];
@@ -472,6 +474,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) sort_local_kernel(
     uint32_t* __restrict__ vals,
     const double4* __restrict__ pos, double4* __restrict__ spos, unsigned* __restrict__ bad,
     unsigned* __restrict__ stat_max) {
+  pb_pdl_sync();
   static_assert(NT >= 256 && NT % 32 == 0 && (1 << LOCAL_BIN_BITS) % NT == 0, "scan layout");
   constexpr int NBINS = 1 << LOCAL_BIN_BITS, BPT = NBINS / NT;  // bins per thread in the scan
   extern __shared__ __align__(16) unsigned char sort_smem[];
@@ -657,6 +660,7 @@ __global__ void __launch_bounds__(256) scan_lookback_kernel(const uint32_t* __re
                                                             uint32_t* __restrict__ out,
                                                             unsigned long long* status,
                                                             unsigned* tile_counter, unsigned tiles, ScanSide side) {
+  pb_pdl_sync();
   __shared__ unsigned tile_s, tile_prefix_s;
   if (threadIdx.x == 0) tile_s = atomicAdd(tile_counter, 1u);
   __syncthreads();
@@ -764,6 +768,7 @@ __global__ void __launch_bounds__(256) unit_kernel(const uint64_t* __restrict__ 
                                                    unsigned* __restrict__ max_shared_plus1,
                                                    int levels_sorted, uint8_t* __restrict__ nsv1,
                                                    size_t n_pad, uint8_t* __restrict__ nsv2) {
+  pb_pdl_sync();
   constexpr int LM = TreeDim<DIM>::LM;
   const size_t s = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
   unsigned deepest = 0;  // 1 + deepest level shared by two neighbours with DIFFERENT keys
@@ -814,25 +819,25 @@ __global__ void __launch_bounds__(256) unit_kernel(const uint64_t* __restrict__ 
     cnt[s] = head ? unsigned(max(0, b - a) + 1) : 0u;
     if (head) a1 = static_cast<unsigned char>(a + 1);
   }
-  // range-minimum table of a1 over this block of 256 sorted bodies (nsv_next_le); level k at
-  // nsv1[k * n_pad + s] = min a1[s .. s + 2^k), valid while the range stays inside the block
+  // minima of a1 for the run-end queries (NsvTables): per body, per aligned window of 16 bodies (shuffles),
+  // per block of 256 (one barrier)
   {
-    __shared__ unsigned char tab[2][256 + 128];
-    const int t = threadIdx.x;
-    tab[0][t] = a1;
-    if (t < 128) tab[0][256 + t] = tab[1][256 + t] = NSV_NONE;
+    const unsigned lane = threadIdx.x & 31u;
     nsv1[s] = a1;
-    __syncthreads();
-    int cur = 0;
+    unsigned m = a1;
 #pragma unroll
-    for (int k = 1; k <= 8; ++k) {
-      const unsigned char m = min(tab[cur][t], tab[cur][t + (1 << (k - 1))]);
-      tab[cur ^ 1][t] = m;
-      nsv1[size_t(k) * n_pad + s] = m;
-      cur ^= 1;
-      __syncthreads();
+    for (int o = 1; o < 16; o <<= 1) m = min(m, __shfl_xor_sync(FULL, m, o));
+    if ((lane & 15u) == 0u) nsv1[n_pad + (s >> 4)] = static_cast<unsigned char>(m);
+    m = min(m, __shfl_xor_sync(FULL, m, 16));
+    __shared__ unsigned char warp_min[8];
+    if (lane == 0u) warp_min[threadIdx.x >> 5] = static_cast<unsigned char>(m);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned bm = warp_min[0];
+#pragma unroll
+      for (int w = 1; w < 8; ++w) bm = min(bm, unsigned(warp_min[w]));
+      nsv2[blockIdx.x] = static_cast<unsigned char>(bm);
     }
-    if (t == 0) nsv2[blockIdx.x] = tab[cur][0];
   }
   // sizes the next sort and validates this one (a truncated sort is exact iff no two neighbours
   // with different keys agree on every sorted bit)
@@ -885,17 +890,25 @@ __device__ __forceinline__ double4 unit_leaf(const double4* __restrict__ sp,
   return q;
 }
 
-// Range-minimum tables for "first body j >= j0 that starts a cell at level <= l", i.e. the end of a
-// cell's run of bodies (in DFS pre-order the first later cell that is not deeper is the next
-// non-descendant, and cell_start[] of the body that heads it is its index):
-//   nsv1[k][j]  min a1[j .. j+2^k) inside blocks of 256 bodies (unit_kernel), k = 0..8
-//   nsv2[k][b]  the same over the block minima inside super-blocks of 256 blocks, k = 0..8
-//   nsv3[q]     super-block minima (scanned linearly: n / 65536 entries)
-// A query is a fixed sequence of <= 9 dependent byte loads per level of the hierarchy, the same for
-// every lane of a warp: no data-dependent scan lengths.
+// Minima for "first body j >= j0 that starts a cell at level <= l", i.e. the end of a cell's run of
+// bodies (in DFS pre-order the first later cell that is not deeper is the next non-descendant, and
+// cell_start[] of the body that heads it is its index):
+//   t1[j]      a1 of body j (255 for a body that heads no cell, and for the padding up to n_pad)
+//   t16[w]     minimum over the aligned window of 16 bodies w             (unit_kernel, shuffles)
+//   t2[0][b]   minimum over the block of 256 bodies b                      (unit_kernel)
+//   t2[k][b]   range minima over 2^k blocks inside super-blocks of 256 blocks, k = 1..8 (nsv_level2_block)
+//   t3[q]      super-block minima (scanned linearly: n / 65536 entries)
+// A query runs in rounds of INDEPENDENT 16-byte loads - nearly every warp of cells_kernel holds a cell
+// whose run is long, and a chain of dependent byte loads there stalls the whole warp:
+//   (1) the bytes of the 17..32 bodies from j0 on + the 16 window minima of j0's block;
+//   (2) the bytes of the window that holds the hit                      -> the run ends inside the block
+//   (3) the minima of the next 17..32 blocks; (4) the window minima of the block that holds the hit;
+//   (5) the bytes of its window                                         -> runs of up to ~4000 bodies
+// Longer runs find their block by descending t2 / t3 (9 dependent byte loads per level), then (4), (5).
 struct NsvTables {
   const uint8_t* t1;
-  size_t n_pad;   // stride of a level of t1
+  const uint8_t* t16;
+  size_t n_pad;   // bodies rounded up to whole blocks
   const uint8_t* t2;
   size_t b_pad;   // stride of a level of t2
   const uint8_t* t3;
@@ -911,30 +924,6 @@ __device__ __forceinline__ size_t nsv_descend(const uint8_t* __restrict__ tab, s
     if (j + step <= end && tab[size_t(k) * stride + j] > l) j += step;
   }
   return j;
-}
-
-__device__ __forceinline__ size_t nsv_next_le(const NsvTables& tv, size_t j0, unsigned l) {
-  if (j0 >= tv.n) return tv.n;
-  const size_t blk_end = min(tv.n, (j0 | 255) + 1);
-  const size_t j = nsv_descend(tv.t1, tv.n_pad, j0, blk_end, l);
-  if (j < blk_end) return j;
-  if (blk_end == tv.n) return tv.n;  // (the last block may be partial: blk_end >> 8 would name it again)
-  size_t b = blk_end >> 8;  // first block not yet examined
-  if (b >= tv.nblocks) return tv.n;
-  size_t sb_end = min(tv.nblocks, (b | 255) + 1);
-  b = nsv_descend(tv.t2, tv.b_pad, b, sb_end, l);
-  if (b == sb_end) {  // not in the rest of this super-block: whole super-blocks, then inside the one that has it
-    if (sb_end == tv.nblocks) return tv.n;
-    size_t q = sb_end >> 8;
-    while (q < tv.nsuper && tv.t3[q] > l) ++q;
-    if (q >= tv.nsuper) return tv.n;
-    b = q << 8;
-    sb_end = min(tv.nblocks, b + 256);
-    b = nsv_descend(tv.t2, tv.b_pad, b, sb_end, l);
-    if (b == sb_end) return tv.n;  // (not reached: t3[q] <= l)
-  }
-  const size_t lo = b << 8;  // block b holds the answer
-  return nsv_descend(tv.t1, tv.n_pad, lo, min(tv.n, lo + 256), l);
 }
 
 // first byte at or after `off` of the 16 in w that is <= l (splat = l in every byte), else 16
@@ -953,63 +942,70 @@ __device__ __forceinline__ int first_le_16(const uint4& w, unsigned splat, int o
   return pos;
 }
 
-// The same query in rounds of INDEPENDENT loads (the table descent is 9 dependent byte loads per level
-// of the hierarchy, and nearly every warp holds one cell that needs it):
-//   (1) the level-0 bytes of the 17..32 bodies from j0 on, two 16-byte loads;
-//   (2) the level-4 minima (16 bodies each) of the aligned windows up to the second block boundary;
-//   (3) the level-0 bytes of the first window that holds a hit;           -> runs of up to ~290 bodies
-//   (4) the minima of the next 17..32 blocks of 256 bodies, two 16-byte loads, then (2') the 16 windows
-//       of the block that holds the hit and (3) again;                   -> runs of up to ~4000 bodies
-// Longer runs continue with the table descent from where the scan stopped.
-__device__ __forceinline__ size_t nsv_hit_in_windows(const NsvTables& tv, size_t j1, size_t end, unsigned l,
-                                                     unsigned splat) {
-  // first body in [j1, end) (16-aligned, end - j1 <= 31 * 16) whose entry is <= l, else `end`
-  const uint8_t* __restrict__ t4 = tv.t1 + 4 * tv.n_pad;  // min a1[j .. j+16): aligned windows never leave their block
-  int hit = 31;
-#pragma unroll
-  for (int i = 30; i >= 0; --i) {
-    const size_t idx = j1 + 16 * size_t(i);
-    const unsigned v = idx < end ? unsigned(t4[idx]) : unsigned(NSV_NONE);
-    if (v <= l) hit = i;
-  }
-  if (hit == 31) return end;
-  const size_t jw = j1 + 16 * size_t(hit);
-  const uint4 w = *reinterpret_cast<const uint4*>(tv.t1 + jw);
-  return jw + size_t(first_le_16(w, splat, 0));
+__device__ __forceinline__ uint4 ld16(const uint8_t* p) { return *reinterpret_cast<const uint4*>(p); }
+
+// the answer inside block b, whose minimum is known to be <= l: window minima, then the window's bytes
+__device__ __forceinline__ size_t nsv_in_block(const NsvTables& tv, size_t b, unsigned splat) {
+  const int w = first_le_16(ld16(tv.t16 + (b << 4)), splat, 0);
+  if (w == 16) return tv.n;  // (not reached)
+  const size_t jw = (b << 8) + (size_t(w) << 4);
+  return jw + size_t(first_le_16(ld16(tv.t1 + jw), splat, 0));
 }
 
-__device__ __forceinline__ size_t nsv_next_le_short(const NsvTables& tv, size_t j0, unsigned l) {
-  if (j0 + 32 > tv.n_pad) return nsv_next_le(tv, j0, l);  // (the 32-byte window would leave level 0)
-  const size_t base = j0 & ~size_t(15);
-  const uint4 w0 = *reinterpret_cast<const uint4*>(tv.t1 + base);
-  const uint4 w1 = *reinterpret_cast<const uint4*>(tv.t1 + base + 16);
+__device__ __forceinline__ size_t nsv_next_le(const NsvTables& tv, size_t j0, unsigned l) {
+  if (j0 >= tv.n) return tv.n;
+  // (bytes of bodies past n are 255 and never match, so a hit is always < n)
   const unsigned splat = l * 0x01010101u;
-  // (bytes of bodies past n are NSV_NONE and never match, so a hit is always < n)
+  const size_t base = j0 & ~size_t(15), blk = j0 >> 8;
+  const bool two = base + 32 <= tv.n_pad;
+  const uint4 w0 = ld16(tv.t1 + base);
+  const uint4 w1 = two ? ld16(tv.t1 + base + 16) : make_uint4(~0u, ~0u, ~0u, ~0u);
+  const uint4 wm = ld16(tv.t16 + (blk << 4));
   int pos = first_le_16(w0, splat, int(j0 - base));
   if (pos < 16) return base + size_t(pos);
   pos = first_le_16(w1, splat, 0);
   if (pos < 16) return base + 16 + size_t(pos);
-  const size_t j1 = base + 32;
-  const size_t end2 = min(tv.n_pad, ((j1 + 255) | 255) + 1);  // second block boundary after j1: 16..31 windows
-  size_t j = nsv_hit_in_windows(tv, j1, end2, l, splat);
-  if (j < end2) return j;
-  if (end2 >= tv.n) return tv.n;
-  // block minima (level 0 of t2; entries of blocks past nblocks are not initialised: masked by position)
-  const size_t b0 = end2 >> 8, bb = b0 & ~size_t(15);
-  if (bb + 32 > tv.b_pad) return nsv_next_le(tv, end2, l);
-  const uint4 m0 = *reinterpret_cast<const uint4*>(tv.t2 + bb);
-  const uint4 m1 = *reinterpret_cast<const uint4*>(tv.t2 + bb + 16);
+  // windows of j0's block past the bytes just examined (none if those reached the block's end)
+  const size_t seen = base + (two ? 32 : 16);
+  if ((seen >> 8) == blk) {
+    pos = first_le_16(wm, splat, int((seen >> 4) - (blk << 4)));
+    if (pos < 16) {
+      const size_t jw = (blk << 8) + (size_t(pos) << 4);
+      return jw + size_t(first_le_16(ld16(tv.t1 + jw), splat, 0));
+    }
+  }
+  // following blocks: their minima, 17..32 at a time (entries of blocks past nblocks are not initialised:
+  // a match there lies after every real block and is discarded by position)
+  const size_t b0 = blk + 1;
+  if (b0 >= tv.nblocks) return tv.n;
+  const size_t bb = b0 & ~size_t(15);
+  const bool two_b = bb + 32 <= tv.b_pad;
+  const uint4 m0 = ld16(tv.t2 + bb);
+  const uint4 m1 = two_b ? ld16(tv.t2 + bb + 16) : make_uint4(~0u, ~0u, ~0u, ~0u);
   pos = first_le_16(m0, splat, int(b0 - bb));
   if (pos == 16) {
     pos = first_le_16(m1, splat, 0);
-    if (pos < 16) pos += 16; else pos = 32;
+    pos = pos < 16 ? pos + 16 : 32;
   }
-  const size_t b = bb + size_t(pos);
-  if (b >= tv.nblocks) return tv.n;  // (nothing up to the last block, or a match on an uninitialised entry past it)
-  if (pos == 32) return nsv_next_le(tv, b << 8, l);
-  const size_t lo = b << 8;
-  j = nsv_hit_in_windows(tv, lo, lo + 256, l, splat);
-  return j < lo + 256 ? j : tv.n;  // (always found: the block minimum said so)
+  size_t b = bb + size_t(pos);
+  if (pos == 32) {  // not within those: descend the block tables from the first block not yet examined
+    b = bb + (two_b ? 32 : 16);
+    if (b >= tv.nblocks) return tv.n;
+    size_t sb_end = min(tv.nblocks, (b | 255) + 1);
+    b = nsv_descend(tv.t2, tv.b_pad, b, sb_end, l);
+    if (b == sb_end) {  // not in the rest of this super-block: whole super-blocks, then inside the one that has it
+      if (sb_end == tv.nblocks) return tv.n;
+      size_t q = sb_end >> 8;
+      while (q < tv.nsuper && tv.t3[q] > l) ++q;
+      if (q >= tv.nsuper) return tv.n;
+      b = q << 8;
+      sb_end = min(tv.nblocks, b + 256);
+      b = nsv_descend(tv.t2, tv.b_pad, b, sb_end, l);
+      if (b == sb_end) return tv.n;  // (not reached: t3[q] <= l)
+    }
+  }
+  if (b >= tv.nblocks) return tv.n;
+  return nsv_in_block(tv, b, splat);
 }
 
 // K6  one thread per unit head s, for the chain of cells it heads (levels a+1 .. leaf level).
@@ -1033,6 +1029,7 @@ __global__ void __launch_bounds__(256, MIN_BLOCKS) cells_kernel(const uint64_t* 
                                                     const unsigned long long* __restrict__ extent_bits,
                                                     const unsigned* __restrict__ tree_meta,
                                                     unsigned* __restrict__ sticky, NsvTables tv, CellArrays cells) {
+  pb_pdl_sync();
   constexpr int LM = TreeDim<DIM>::LM;
   const size_t s = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
   const unsigned lane = threadIdx.x & 31u;
@@ -1125,7 +1122,7 @@ __global__ void __launch_bounds__(256, MIN_BLOCKS) cells_kernel(const uint64_t* 
     const uint32_t c = __shfl_sync(FULL, c0, o) + uint32_t(k);
     if (t >= n_tasks) continue;
     const size_t so = s - lane + size_t(o);  // the chain's head
-    const size_t e = nsv_next_le_short(tv, so + 1, unsigned(lev));
+    const size_t e = nsv_next_le(tv, so + 1, unsigned(lev));
     const uint32_t cnt = static_cast<uint32_t>(e - so);
     cells.count[c] = cnt;
     cells.skip[c] = cell_start[e];
@@ -1393,6 +1390,7 @@ __global__ void __launch_bounds__(256) kids_kernel(const uint32_t* __restrict__ 
                                                    CellArrays cells, uint32_t* __restrict__ kid_tab,
                                                    uint32_t* __restrict__ ready_list, unsigned* __restrict__ n_ready,
                                                    uint32_t sub_cap) {
+  pb_pdl_sync();
   constexpr uint32_t K = 1u << DIM;
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t total = cell_start[n];
@@ -1439,6 +1437,7 @@ __global__ void __launch_bounds__(128) climb_kernel(const uint32_t* __restrict__
                                                     CellArrays cells, const uint32_t* __restrict__ kid_tab,
                                                     const uint32_t* __restrict__ ready_list,
                                                     const unsigned* __restrict__ n_ready, uint32_t sub_cap) {
+  pb_pdl_sync();
   constexpr int K = 1 << DIM;
   const uint32_t total = cell_start[n];
   if (total > cells.capacity || *cells.bad) return;
@@ -1594,6 +1593,7 @@ __global__ void __launch_bounds__(256) walk_kernel(const double4* __restrict__ s
                                                    size_t n_targets, const uint32_t* __restrict__ cell_start,
                                                    size_t n, CellArrays cells, double theta, float easing,
                                                    float tiny, float4* __restrict__ acc) {
+  pb_pdl_sync();
   const uint32_t total = cell_start[n];
   if (total > cells.capacity || *cells.bad) return;
   const size_t t = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
@@ -1981,7 +1981,7 @@ cudaError_t exclusive_scan_with_side(const uint32_t* in, uint32_t* out, size_t n
                                      const ScanSide& side, cudaStream_t st, LaunchStats& ls) {
   const unsigned tiles = blocks_for(n, SCAN_TILE);
   PB_LAUNCH(ls, st, "scan_lookback_kernel",
-            scan_lookback_kernel<true><<<tiles + side.nsuper + 1, 256, 0, st>>>(
+            pb_launch_pdl(scan_lookback_kernel<true>, dim3(tiles + side.nsuper + 1), dim3(256), 0, st, 
                 in, n, out, scratch, reinterpret_cast<unsigned*>(scratch + tiles), tiles, side));
   return cudaGetLastError();
 }
@@ -2065,20 +2065,20 @@ cudaError_t encode_and_sort(GravityWorkspace& ws, size_t n, const SortBuffers& s
   *splitters_out = spl_out;  // written by the side job of the scan that follows the sort
   if (sb.mode != 0) {
     PB_LAUNCH(ls, st, "encode_bucket_kernel",
-              encode_bucket_kernel<DIM><<<blocks_for(n, 256 * ENC_ITEMS), 256, 0, st>>>(
+              pb_launch_pdl(encode_bucket_kernel<DIM>, dim3(blocks_for(n, 256 * ENC_ITEMS)), dim3(256), 0, st, 
                   ws.pos64, n, ws.extent_cur, spl_in, sb.lo, ws.bucket_key.as<uint64_t>(),
                   ws.bucket_idx.as<uint32_t>(), sb.cap, sb.ghist));
     const size_t smem = sort_local_smem(sb.cap);
     if (sb.mode == 1) {
       PB_CUDA(cudaFuncSetAttribute(sort_local_kernel<512, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
       PB_LAUNCH(ls, st, "sort_local_kernel",
-                sort_local_kernel<512, 9><<<256, 512, smem, st>>>(
+                pb_launch_pdl(sort_local_kernel<512, 9>, dim3(256), dim3(512), smem, st, 
                     ws.bucket_key.as<uint64_t>(), ws.bucket_idx.as<uint32_t>(), sb.ghist, spl_in, sb.cap, sb.lo,
                     sb.key_bits, k[0], v[0], ws.pos64, ws.spos64.as<double4>(), bad, stat_max));
     } else {
       PB_CUDA(cudaFuncSetAttribute(sort_local_kernel<1024, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
       PB_LAUNCH(ls, st, "sort_local_kernel",
-                sort_local_kernel<1024, 8><<<256, 1024, smem, st>>>(
+                pb_launch_pdl(sort_local_kernel<1024, 8>, dim3(256), dim3(1024), smem, st, 
                     ws.bucket_key.as<uint64_t>(), ws.bucket_idx.as<uint32_t>(), sb.ghist, spl_in, sb.cap, sb.lo,
                     sb.key_bits, k[0], v[0], ws.pos64, ws.spos64.as<double4>(), bad, stat_max));
     }
@@ -2155,7 +2155,7 @@ cudaError_t tree_evaluate(GravityWorkspace& ws, const GravityParams& prm, size_t
   const unsigned long long* extent = ws.extent_pre;
   ws.extent_pre = nullptr;  // (good for one build)
   if (!extent) {
-    PB_LAUNCH(ls, st, "extent_kernel", extent_kernel<<<min(nb, 148u * 8u), 256, 0, st>>>(ws.pos64, n, ws.extent_bits.as<unsigned long long>()));
+    PB_LAUNCH(ls, st, "extent_kernel", pb_launch_pdl(extent_kernel, dim3(min(nb, 148u * 8u)), dim3(256), 0, st, ws.pos64, n, ws.extent_bits.as<unsigned long long>()));
     extent = ws.extent_bits.as<unsigned long long>();
   }
   ws.extent_cur = extent;
@@ -2166,10 +2166,10 @@ cudaError_t tree_evaluate(GravityWorkspace& ws, const GravityParams& prm, size_t
   PB_PASS(encode_and_sort<DIM>(ws, n, sb, max_shared_plus1 + 2, st, ls, &spl_out));
   // range-minimum tables over the sorted bodies' shared-level bytes (see NsvTables)
   const size_t n_pad = size_t(nb) * 256, nblocks = nb, b_pad = (nblocks + 255) / 256 * 256, nsuper = b_pad / 256;
-  PB_PASS(ws.nsv1.ensure(9 * n_pad));
+  PB_PASS(ws.nsv1.ensure(n_pad + n_pad / 16));  // [a1 bytes][window minima]
   PB_PASS(ws.nsv2.ensure(9 * b_pad + nsuper));
   uint8_t* nsv3 = ws.nsv2.as<uint8_t>() + 9 * b_pad;
-  PB_LAUNCH(ls, st, "unit_kernel", unit_kernel<DIM><<<nb, 256, 0, st>>>(ws.sorted_key, ws.spos64.as<double4>(), n, ws.ab.as<uchar2>(),
+  PB_LAUNCH(ls, st, "unit_kernel", pb_launch_pdl(unit_kernel<DIM>, dim3(nb), dim3(256), 0, st, ws.sorted_key, ws.spos64.as<double4>(), n, ws.ab.as<uchar2>(),
                                        ws.tgt_flags.as<uint32_t>(), max_shared_plus1,
                                        lo > 0 ? (key_bits - lo) / DIM : TreeDim<DIM>::LM + 2,
                                        ws.nsv1.as<uint8_t>(), n_pad, ws.nsv2.as<uint8_t>()));
@@ -2196,7 +2196,7 @@ cudaError_t tree_evaluate(GravityWorkspace& ws, const GravityParams& prm, size_t
                    ws.c_centre_ext.as<double4>(), ws.c_com.as<double4>(), static_cast<uint32_t>(cap), small_cell,
                    max_shared_plus1 + 2};
   const unsigned nb128 = blocks_for(n, 128);
-  const NsvTables tv{ws.nsv1.as<uint8_t>(), n_pad, ws.nsv2.as<uint8_t>(), b_pad, nsv3, n, nblocks, nsuper};
+  const NsvTables tv{ws.nsv1.as<uint8_t>(), ws.nsv1.as<uint8_t>() + n_pad, n_pad, ws.nsv2.as<uint8_t>(), b_pad, nsv3, n, nblocks, nsuper};
   static const bool cells_chain = std::getenv("PB200_CELLS") && std::string(std::getenv("PB200_CELLS")) == "chain";
   if (cells_chain) {
     PB_LAUNCH(ls, st, "cells_kernel_chain",
@@ -2206,7 +2206,7 @@ cudaError_t tree_evaluate(GravityWorkspace& ws, const GravityParams& prm, size_t
                                                           ws.sticky.as<unsigned>(), tv, cells));
   } else {
       PB_LAUNCH(ls, st, "cells_kernel",
-                (cells_kernel<DIM, 4><<<nb, 256, 0, st>>>(ws.sorted_key, ws.spos64.as<double4>(), ws.perm,
+                (pb_launch_pdl(cells_kernel<DIM, 4>, dim3(nb), dim3(256), 0, st, ws.sorted_key, ws.spos64.as<double4>(), ws.perm,
                                                           ws.ab.as<uchar2>(), ws.cell_start.as<uint32_t>(), n,
                                                           ws.extent_cur, max_shared_plus1,
                                                           ws.sticky.as<unsigned>(), tv, cells)));
@@ -2225,10 +2225,10 @@ cudaError_t tree_evaluate(GravityWorkspace& ws, const GravityParams& prm, size_t
     const uint32_t sub_cap = ((kid_blocks + READY_LISTS - 1) / READY_LISTS) * 256u;
     PB_PASS(ws.c_ready.ensure(size_t(READY_LISTS) * sub_cap * 4));
     PB_LAUNCH(ls, st, "kids_kernel",
-              kids_kernel<DIM><<<kid_blocks, 256, 0, st>>>(ws.cell_start.as<uint32_t>(), n, cells,
+              pb_launch_pdl(kids_kernel<DIM>, dim3(kid_blocks), dim3(256), 0, st, ws.cell_start.as<uint32_t>(), n, cells,
                                                            ws.c_kids.as<uint32_t>(), ws.c_ready.as<uint32_t>(), n_ready, sub_cap));
     PB_LAUNCH(ls, st, "climb_kernel",
-              climb_kernel<DIM><<<148 * 4, 128, 0, st>>>(ws.cell_start.as<uint32_t>(), n, cells,
+              pb_launch_pdl(climb_kernel<DIM>, dim3(148 * 4), dim3(128), 0, st, ws.cell_start.as<uint32_t>(), n, cells,
                                                          ws.c_kids.as<uint32_t>(), ws.c_ready.as<uint32_t>(), n_ready, sub_cap));
   }
 
@@ -2244,7 +2244,7 @@ cudaError_t tree_evaluate(GravityWorkspace& ws, const GravityParams& prm, size_t
     list = lst;
   }
   if (n_targets) {
-    PB_LAUNCH(ls, st, "walk_kernel", walk_kernel<DIM><<<blocks_for(n_targets, 256), 256, 0, st>>>(
+    PB_LAUNCH(ls, st, "walk_kernel", pb_launch_pdl(walk_kernel<DIM>, dim3(blocks_for(n_targets, 256)), dim3(256), 0, st, 
         ws.spos64.as<double4>(), ws.perm, ws.fixed, list, n_targets, ws.cell_start.as<uint32_t>(), n,
         cells, prm.theta, easing, tiny, ws.acc.as<float4>()));
   }

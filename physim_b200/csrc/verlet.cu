@@ -81,6 +81,7 @@ __global__ void __launch_bounds__(256) verlet_lean_kernel(const double4* __restr
                                                           const float4* __restrict__ acc32, size_t n, double dt2,
                                                           unsigned long long* __restrict__ extent_out,
                                                           unsigned long long* __restrict__ extent_zero) {
+  pb_pdl_sync();
   const size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
   if (i == 0) *extent_zero = 0ull;
   double m = 0.0;
@@ -232,7 +233,7 @@ cudaError_t verlet_update_lean(const double4* cur, double4* prev_inout, const fl
   const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
   const double dt2 = dt * dt;  // dt.powi(2)
   PB_LAUNCH(ls, st, "verlet_lean_kernel",
-            verlet_lean_kernel<<<blocks, 256, 0, st>>>(cur, prev_inout, acc32, n, dt2, extent_out, extent_zero));
+            pb_launch_pdl(verlet_lean_kernel, dim3(blocks), dim3(256), 0, st, cur, prev_inout, acc32, n, dt2, extent_out, extent_zero));
   return cudaGetLastError();
 }
 
