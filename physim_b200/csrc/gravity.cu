@@ -1062,6 +1062,7 @@ __global__ void __launch_bounds__(256, MIN_BLOCKS) cells_kernel(const uint64_t* 
     leaf_level = max(a, b) + 1;
     double half = ext0;
     double cx = 0.0, cy = 0.0, cz = 0.0;
+    uint64_t digits = kme << (64 - DIM * LM);  // next digit in the top DIM bits
     for (int l = 0; l <= leaf_level; ++l) {
       if (l >= top) {
         const uint32_t c = c0 + uint32_t(l - top);
@@ -1071,10 +1072,9 @@ __global__ void __launch_bounds__(256, MIN_BLOCKS) cells_kernel(const uint64_t* 
         cells.centre_ext[c] = make_double4(cx, cy, cz, half);
       }
       if (l < leaf_level) {  // from level l to level l+1 along the head body's path
-        unsigned digit;
-        if (l < LM) {
-          digit = unsigned((kme >> (DIM * (LM - 1 - l))) & ((1u << DIM) - 1u));
-        } else {  // pseudo level below the key: compare the head body itself
+        unsigned digit = unsigned(digits >> (64 - DIM));
+        digits <<= DIM;
+        if (l >= LM) {  // pseudo level below the key (rare: a real branch): compare the head body itself
           digit = unsigned(me.x > cx) | (unsigned(me.y > cy) << 1);
           if (DIM == 3) digit |= unsigned(me.z > cz) << 2;
         }
