@@ -751,6 +751,37 @@ __global__ void __launch_bounds__(256) gather_kernel(const double4* __restrict__
   if (s < n) spos[s] = pos[perm[s]];
 }
 
+// ---- bulk asynchronous copies (TMA, cp.async.bulk) completing on an mbarrier ------------------
+__device__ __forceinline__ uint32_t smem_addr(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_addr(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_addr(bar)),
+      "r"(parity)
+      : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // K5  merged-leaf runs and the number of cells each sorted body heads.
 //     a = levels shared with the previous unit, b = with the next; a unit heads the cells at
@@ -760,6 +791,13 @@ __device__ __forceinline__ bool close_1e9(const double4& u, const double4& v) {
   return fabs(u.x - v.x) < 1e-9 && fabs(u.y - v.y) < 1e-9 && fabs(u.z - v.z) < 1e-9;
 }
 
+// Persistent CTAs over tiles of 256 sorted bodies.  A tile's positions and keys (with one body of halo
+// on either side) arrive in shared memory by two bulk copies (TMA) that complete on an mbarrier, and the
+// copies of the CTA's next tile are in flight while this one is worked on: one element per thread with
+// plain loads left every CTA waiting out a full DRAM latency before it could do anything (1.4 TB/s).
+constexpr int UNIT_TILE = 256;
+constexpr int UNIT_CTAS_PER_SM = 5;
+
 template <int DIM>
 __global__ void __launch_bounds__(256) unit_kernel(const uint64_t* __restrict__ key,
                                                    const double4* __restrict__ sp, size_t n,
@@ -767,21 +805,51 @@ __global__ void __launch_bounds__(256) unit_kernel(const uint64_t* __restrict__ 
                                                    uint32_t* __restrict__ cnt,
                                                    unsigned* __restrict__ max_shared_plus1,
                                                    int levels_sorted, uint8_t* __restrict__ nsv1,
-                                                   size_t n_pad, uint8_t* __restrict__ nsv2) {
+                                                   size_t n_pad, uint8_t* __restrict__ nsv2, unsigned n_tiles) {
   pb_pdl_sync();
   constexpr int LM = TreeDim<DIM>::LM;
-  const size_t s = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  // t_sp[b][i] = sp[s0 - 1 + i] (i = 0 .. 257), t_key[b][i] = key[s0 - 2 + i] (i = 0 .. 259): the windows
+  // start at 16-byte aligned addresses and are a multiple of 16 bytes long, as bulk copies must be
+  __shared__ __align__(128) double4 t_sp[2][UNIT_TILE + 2];
+  __shared__ __align__(128) uint64_t t_key[2][UNIT_TILE + 4];
+  __shared__ __align__(8) uint64_t full[2];
+  __shared__ unsigned char warp_min[8];
+  if (threadIdx.x == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](unsigned tile, unsigned buf) {  // (one thread)
+    const size_t s0 = size_t(tile) * UNIT_TILE;
+    const size_t p0 = s0 ? s0 - 1 : 0, p1 = min(n, s0 + UNIT_TILE + 1);                       // bodies [p0, p1)
+    const size_t k0 = s0 ? s0 - 2 : 0, k1 = min((n + 1) & ~size_t(1), s0 + UNIT_TILE + 2);    // keys [k0, k1), even count
+    // (key[n] may be read when n is odd: inside the allocation's slack, never used)
+    const unsigned sp_bytes = unsigned(p1 - p0) * 32u, key_bytes = unsigned(k1 - k0) * 8u;
+    mbar_expect_tx(&full[buf], sp_bytes + key_bytes);
+    bulk_load(&t_sp[buf][p0 - (s0 - 1)], sp + p0, sp_bytes, &full[buf]);     // (s0 = 0: slot 1 on)
+    bulk_load(&t_key[buf][k0 - (s0 - 2)], key + k0, key_bytes, &full[buf]);   // (s0 = 0: slot 2 on)
+  };
   unsigned deepest = 0;  // 1 + deepest level shared by two neighbours with DIFFERENT keys
+  if (threadIdx.x == 0 && blockIdx.x < n_tiles) issue(blockIdx.x, 0u);
+  unsigned it = 0;
+  for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+  const unsigned buf = it & 1u;
+  // buffer buf ^ 1 was read in the previous iteration; the barrier at its end makes the refill safe
+  if (threadIdx.x == 0 && tile + gridDim.x < n_tiles) issue(tile + gridDim.x, buf ^ 1u);
+  mbar_wait(&full[buf], (it >> 1) & 1u);
+  const size_t s = size_t(tile) * UNIT_TILE + threadIdx.x;
   unsigned char a1 = NSV_NONE;  // 1 + levels shared with the previous unit (heads only)
   if (s < n) {
-    const double4 me = sp[s];
-    const uint64_t kme = key[s];
-    const bool cp = s > 0 && close_1e9(sp[s - 1], me);
-    const bool cn = s + 1 < n && close_1e9(me, sp[s + 1]);
-    int a = s > 0 ? shared_levels<DIM>(key[s - 1], kme) : -1;
-    int b = s + 1 < n ? shared_levels<DIM>(kme, key[s + 1]) : -1;
-    if (s > 0 && key[s - 1] != kme) {
-      deepest = unsigned(a + 1);
+    const double4 me = t_sp[buf][threadIdx.x + 1];
+    const uint64_t kme = t_key[buf][threadIdx.x + 2];
+    const bool cp = s > 0 && close_1e9(t_sp[buf][threadIdx.x], me);
+    const bool cn = s + 1 < n && close_1e9(me, t_sp[buf][threadIdx.x + 2]);
+    const uint64_t kprev = t_key[buf][threadIdx.x + 1], knext = t_key[buf][threadIdx.x + 3];
+    int a = s > 0 ? shared_levels<DIM>(kprev, kme) : -1;
+    int b = s + 1 < n ? shared_levels<DIM>(kme, knext) : -1;
+    if (s > 0 && kprev != kme) {
+      deepest = max(deepest, unsigned(a + 1));
       // two different keys that agree on every sorted bit: their order is not the full sort's, the
       // arrays below would describe a broken tree -> every later kernel of this build bails out
       if (a >= levels_sorted) max_shared_plus1[2] = 1u;
@@ -829,15 +897,16 @@ __global__ void __launch_bounds__(256) unit_kernel(const uint64_t* __restrict__ 
     for (int o = 1; o < 16; o <<= 1) m = min(m, __shfl_xor_sync(FULL, m, o));
     if ((lane & 15u) == 0u) nsv1[n_pad + (s >> 4)] = static_cast<unsigned char>(m);
     m = min(m, __shfl_xor_sync(FULL, m, 16));
-    __shared__ unsigned char warp_min[8];
     if (lane == 0u) warp_min[threadIdx.x >> 5] = static_cast<unsigned char>(m);
     __syncthreads();
     if (threadIdx.x == 0) {
       unsigned bm = warp_min[0];
 #pragma unroll
       for (int w = 1; w < 8; ++w) bm = min(bm, unsigned(warp_min[w]));
-      nsv2[blockIdx.x] = static_cast<unsigned char>(bm);
+      nsv2[tile] = static_cast<unsigned char>(bm);
     }
+  }
+  __syncthreads();  // everybody is done with this tile's buffer (and with warp_min)
   }
   // sizes the next sort and validates this one (a truncated sort is exact iff no two neighbours
   // with different keys agree on every sorted bit)
@@ -1736,37 +1805,6 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
   return d;
 }
 
-// ---- bulk asynchronous copies (TMA, cp.async.bulk) completing on an mbarrier ------------------
-__device__ __forceinline__ uint32_t smem_addr(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, unsigned bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_addr(dst_smem)),
-               "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar))
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(smem_addr(bar)),
-      "r"(parity)
-      : "memory");
-}
-
 // One tile loop of the direct sum.  FOLDED: the source mass is folded into the softened distance,
 //   m / (|r| (r² + e)) = rsqrt(r² · ((r² + e)/m)²),   (r² + e)/m = fma(r², 1/m, e/m),
 // which saves the multiply by m: 12 instead of 13 packed FP32 operations per source pair.
@@ -2169,10 +2207,10 @@ cudaError_t tree_evaluate(GravityWorkspace& ws, const GravityParams& prm, size_t
   PB_PASS(ws.nsv1.ensure(n_pad + n_pad / 16));  // [a1 bytes][window minima]
   PB_PASS(ws.nsv2.ensure(9 * b_pad + nsuper));
   uint8_t* nsv3 = ws.nsv2.as<uint8_t>() + 9 * b_pad;
-  PB_LAUNCH(ls, st, "unit_kernel", pb_launch_pdl(unit_kernel<DIM>, dim3(nb), dim3(256), 0, st, ws.sorted_key, ws.spos64.as<double4>(), n, ws.ab.as<uchar2>(),
+  PB_LAUNCH(ls, st, "unit_kernel", pb_launch_pdl(unit_kernel<DIM>, dim3(min(nb, 148u * unsigned(UNIT_CTAS_PER_SM))), dim3(256), 0, st, ws.sorted_key, ws.spos64.as<double4>(), n, ws.ab.as<uchar2>(),
                                        ws.tgt_flags.as<uint32_t>(), max_shared_plus1,
                                        lo > 0 ? (key_bits - lo) / DIM : TreeDim<DIM>::LM + 2,
-                                       ws.nsv1.as<uint8_t>(), n_pad, ws.nsv2.as<uint8_t>()));
+                                       ws.nsv1.as<uint8_t>(), n_pad, ws.nsv2.as<uint8_t>(), nb));
   const ScanSide side{unsigned(nsuper), ws.nsv2.as<uint8_t>(), b_pad, nblocks, nsv3, ws.sorted_key, n, spl_out};
   PB_PASS(exclusive_scan_with_side(ws.tgt_flags.as<uint32_t>(), ws.cell_start.as<uint32_t>(), n, scan_scratch, side, st, ls));
 
