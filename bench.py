@@ -56,7 +56,7 @@ ALG_BYTES_PER_BODY = {
     "to_soa_kernel": 32 + 16, "sort_local_kernel": 12 + 12 + 32 + 32, "encode_bucket_kernel": 32 + 12,
 }
 FLOP_PER_INTERACTION = 19
-NCU_KERNELS = "r01b_ncu_c3_kernels.json"  # per-kernel DRAM traffic of the committed ncu --set full capture
+NCU_KERNELS = "r01d_ncu_c3_kernels.json"  # per-kernel DRAM traffic of the committed ncu --set full capture
 
 
 def make_state(w):

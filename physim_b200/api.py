@@ -19,7 +19,7 @@ import numpy as np
 from .entity import ACCELERATION, ENTITY
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libphysim_b200.so")
+LIB_PATH = os.environ.get("PB200_LIB_PATH") or os.path.join(_HERE, "libphysim_b200.so")  # (override: A/B runs of two builds)
 
 KINDS = {"astro": 0, "astro2": 1, "simple_astro": 2}
 

@@ -25,9 +25,9 @@ for r in rows:
     a[1] += float(r[vi])
 tot = sum(v[1] for v in agg.values())
 out = [f"# ncu launch list, {tag} (workload c3: 1,000,004 bodies, astro theta=1.3 + verlet)", "",
-       "Command: `ncu --metrics gpu__time_duration.sum --clock-control none -s 51 -c 111 --csv python bench.py --steps 5 --warmup 3 --skip-extras`",
-       "(the 3 warm-up steps = 51 launches use the global LSD sort and are skipped; the steps after the first host check use the bucket sort)",
-       f"({len(rows)} launches = 10 steps; cold-cache, serialised: compare SHARES with bench.py's live `roofline.kernels`)", "",
+       "Command: `ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 108 --csv python bench.py --steps 5 --warmup 3 --skip-extras`",
+       "(the first 60 launches - the warm-up steps, which use the global LSD sort before the first host check - are skipped)",
+       f"({len(rows)} launches = {len(rows) // 9} steps of 9 kernels; cold-cache, serialised: compare SHARES with bench.py's live `roofline.kernels`)", "",
        "| kernel | launches | total us | us / launch | share |", "|---|---:|---:|---:|---:|"]
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     out.append(f"| {k} | {v[0]} | {v[1] / 1e3:.1f} | {v[1] / 1e3 / v[0]:.1f} | {v[1] / tot * 100:.1f}% |")
