@@ -48,8 +48,8 @@ WORKLOADS = {
 # Algorithmic HBM bytes per body per launch for each kernel (DESIGN.md "kernels" table).
 ALG_BYTES_PER_BODY = {
     "extent_kernel": 32, "encode_kernel": 32 + 12, "sort_hist_all": 8, "sort_onesweep_pass": 12 + 12,
-    "gather_kernel": 4 + 32 + 32, "unit_kernel": 8 + 32 + 2 + 4 + 9, "scan_lookback_kernel": 8,
-    "cells_kernel": 8 + 32 + 2 + 4 + 9 + 1.5 * (1 + 4 + 4 + 32 + 4 + 4 + 32) + 32, "parent_kernel": 1.5 * 8, "com_kernel": 1.5 * (32 + 32 + 12),
+    "gather_kernel": 4 + 32 + 32, "unit_kernel": 8 + 32 + 2 + 4 + 1.1, "scan_lookback_kernel": 8,
+    "cells_kernel": 8 + 32 + 2 + 4 + 1.1 + 1.5 * (1 + 4 + 4 + 32 + 4 + 4 + 32) + 32, "parent_kernel": 1.5 * 8, "com_kernel": 1.5 * (32 + 32 + 12),
     "kids_kernel": 1.5 * (4 + 4 + 1) + 0.09 * (4 * 8 + 16 + 4), "climb_kernel": 1.5 * 1 + 0.09 * (16 + 4 * 32 + 32 + 12),
     "walk_kernel": 32 + 4 + 1 + 16, "verlet_kernel": 32 + 32 + 16 + 32 + 32 + 32,
     "verlet_lean_kernel": 32 + 32 + 16 + 32, "verlet_velocity_kernel": 32 + 32 + 32,
