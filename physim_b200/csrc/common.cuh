@@ -104,8 +104,12 @@ struct PinnedBuf {
 //   key[2]  u64[N], idx[2] u32[N]  (radix sort ping-pong)      24 B/body
 //   spos64  double4[N]  sorted {x,y,z,m}                       32 B/body
 //   ab      uchar2[N], cell_start u32[N+1]                      6 B/body
+//   nsv1    u8[N + N/16], nsv2 u8[9][N/256]  shared-level byte per body, minima per window / block
+//                                                             1.1 B/body
 //   cells:  level u8, head/count/skip/parent/arrived u32, centre_ext double4, com double4
 //                                                              85 B/cell
+//   c_kids  u32[2^DIM][C] child tables of the cells summed bottom-up (sparse: ~5 % of the cells touched),
+//   c_ready u32 lists of climb starts                          16-32 + 4 B/cell
 //   acc     float4[N]   {ax,ay,az, bits(interactions)}, original order   16 B/body
 struct GravityWorkspace {
   // inputs (owned elsewhere when running device-resident)

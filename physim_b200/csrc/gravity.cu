@@ -5,9 +5,12 @@
 //   astro/src/octree.rs:59-215, quadtree.rs:59-194     tree topology, acceptance, octant rule
 //   astro/src/lib.rs:84-113                            force law  m_b (p_b - p_a) / (|r| (r^2 + e))
 // The pointer tree of the reference is replaced by: compare-and-halve keys (fp64, the reference's own
-// octant arithmetic) -> LSD radix sort -> DFS pre-order cell table -> bottom-up centres of mass ->
-// warp-cooperative walk with per-lane acceptance.  oracle/physim_oracle.cpp ("oracle 2") builds the
-// same table on the CPU; tests compare the two bit for bit.
+// octant arithmetic) -> stable sort (buckets cut at the previous step's key quantiles and sorted in shared
+// memory, or global LSD radix passes) -> units and cell counts per sorted body (TMA-staged tiles) -> scan
+// -> DFS pre-order cell table (cells_kernel) -> bottom-up centres of mass (kids_kernel, climb_kernel) ->
+// stack-free walk, one lane per target.  The kernels of that chain are launched as programmatic
+// dependents of one another (pb_launch_pdl / pb_pdl_sync).  oracle/physim_oracle.cpp ("oracle 2") builds
+// the same table on the CPU; tests compare the two bit for bit.
 #include <cuda/atomic>
 
 #include <algorithm>
