@@ -2188,7 +2188,11 @@ cudaError_t tree_evaluate(GravityWorkspace& ws, const GravityParams& prm, size_t
   const int key_bits = DIM * TreeDim<DIM>::LM;
   if (ws.tree_dim != DIM) ws.sort_lo = 0, ws.sort_mode = 0;  // depth / bucket estimates belong to the other tree kind
   ws.tree_dim = DIM;
-  const int lo = (ws.sort_lo > 0 && ws.sort_lo < key_bits) ? ws.sort_lo : 0;
+  // Only the global LSD passes get cheaper with fewer key bits (fewer passes).  The bucket sort ranks the
+  // members of a bin by comparing whole keys, so it sorts ALL bits at no extra cost - and a depth guess
+  // that can no longer be wrong cannot make a chunk of the resident loop replay (one replay per ~150
+  // steps of c3 while only the guessed bits were sorted: tools/steps_diag.py).
+  const int lo = (ws.sort_mode == 0 && ws.sort_lo > 0 && ws.sort_lo < key_bits) ? ws.sort_lo : 0;
   ws.last_lo = lo;
   ws.unchecked_builds += 1;
   const unsigned nb = blocks_for(n, 256);
