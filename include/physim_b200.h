@@ -155,7 +155,7 @@ typedef struct Pb200Stats {
   float ms_h2d, ms_build, ms_force, ms_integrate, ms_d2h; /* CUDA-event times of the last call */
   float ms_host_pack, ms_host_unpack, ms_wall;             /* host wall-clock parts of the last call */
   uint32_t replays;        /* chunks of unverified steps that failed verification and were replayed */
-  uint32_t sort_bits;      /* key bits the next sort will cover (tree depth seen + margin) */
+  uint32_t sort_bits;      /* key bits the last sort covered (global passes: tree depth seen + margin; bucket sort: all) */
   uint32_t sort_mode;      /* form of the last sort: 0 global LSD radix passes, 1 / 2 / 3 bucket sort in shared memory (4608 / 8192 / 16384-body buckets) */
   uint32_t max_bucket;     /* bodies in the fullest bin of the keys' top 8 bits at the last check */
 } Pb200Stats;

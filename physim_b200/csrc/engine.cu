@@ -1365,7 +1365,7 @@ int pb200_sim_stats(void* sim, Pb200Stats* out) {
   s.stats.replays = static_cast<uint32_t>(s.replays);
   s.stats.sort_mode = uint32_t(s.ws.last_mode);
   s.stats.max_bucket = s.ws.last_max_bucket;
-  s.stats.sort_bits = s.ws.tree_dim ? uint32_t(s.ws.tree_dim * (s.ws.tree_dim == 3 ? 21 : 31) - s.ws.sort_lo) : 0u;
+  s.stats.sort_bits = s.ws.tree_dim ? uint32_t(s.ws.tree_dim * (s.ws.tree_dim == 3 ? 21 : 31) - s.ws.last_lo) : 0u;
   *out = s.stats;
   return 0;
 }
