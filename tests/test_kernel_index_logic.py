@@ -1,0 +1,131 @@
+"""Host-side restatements of index arithmetic inside the CUDA kernels, checked exhaustively where the GPU
+tests can only sample it (gravity.cu; every function names the device code it follows):
+
+  * cells_kernel, phase 2: dealing the internal cells of a warp's 32 chains out to the lanes
+    (inclusive prefix sum by shuffles + the five-step owner search);
+  * unit_kernel: the source / destination windows and byte counts of the two bulk (TMA) copies of a tile,
+    which must be 16-byte aligned and a multiple of 16 bytes long, and must cover the tile plus its halo;
+  * kids_kernel / climb_kernel: which thread takes which entry of the 16 lists of climb starts.
+"""
+import numpy as np
+import pytest
+
+
+# ---- cells_kernel phase 2 ---------------------------------------------------------------------------
+def warp_inclusive_scan(mine):
+    """for (d = 1; d < 32; d <<= 1) { v = shfl_up(incl, d); if (lane >= d) incl += v; }"""
+    incl = list(mine)
+    d = 1
+    while d < 32:
+        prev = list(incl)
+        for lane in range(32):
+            if lane >= d:
+                incl[lane] = prev[lane] + prev[lane - d]
+        d <<= 1
+    return incl
+
+
+def owner_of(incl, t):
+    """o = 0; for (step = 16; step > 0; step >>= 1) if (incl[o + step - 1] <= t) o += step;"""
+    o = 0
+    step = 16
+    while step > 0:
+        if incl[o + step - 1] <= t:
+            o += step
+        step >>= 1
+    return o
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_internal_cells_are_dealt_out_exactly_once(seed):
+    rng = np.random.default_rng(seed)
+    for trial in range(300):
+        kind = trial % 4
+        if kind == 0:
+            mine = rng.integers(0, 4, 32)                      # the usual: 0..3 internal cells per chain
+        elif kind == 1:
+            mine = np.zeros(32, int)
+            mine[rng.integers(0, 32)] = rng.integers(1, 70)    # one deep chain, nothing else
+        elif kind == 2:
+            mine = np.where(rng.random(32) < 0.1, rng.integers(1, 40, 32), 0)
+        else:
+            mine = np.zeros(32, int)                           # (lanes past n, merged bodies: no tasks at all)
+            if trial % 8 == 3:
+                mine[31] = 5
+        incl = warp_inclusive_scan(mine)
+        assert incl == list(np.cumsum(mine))
+        n_tasks = incl[31]
+        excl = [incl[i] - mine[i] for i in range(32)]
+        seen = set()
+        for t0 in range(0, n_tasks, 32):
+            for lane in range(32):
+                t = t0 + lane
+                o = owner_of(incl, t)
+                assert 0 <= o <= 31                            # (a shuffle source lane, also for idle lanes)
+                if t >= n_tasks:
+                    continue
+                k = t - excl[o]
+                assert 0 <= k < mine[o], (mine, t, o, k)
+                assert (o, k) not in seen
+                seen.add((o, k))
+        assert len(seen) == n_tasks
+
+
+# ---- unit_kernel bulk copies ------------------------------------------------------------------------
+TILE = 256
+
+
+def tile_copies(n, tile):
+    """issue(tile, buf) of unit_kernel: returns (sp_src, sp_dst_slot, sp_count, key_src, key_dst_slot, key_count)"""
+    s0 = tile * TILE
+    p0 = s0 - 1 if s0 else 0
+    p1 = min(n, s0 + TILE + 1)
+    k0 = s0 - 2 if s0 else 0
+    k1 = min((n + 1) & ~1, s0 + TILE + 2)
+    return p0, p0 - (s0 - 1), p1 - p0, k0, k0 - (s0 - 2), k1 - k0
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 255, 256, 257, 258, 511, 512, 513, 1000, 4097, 65535, 65536, 65537, 1000004])
+def test_unit_tile_windows(n):
+    n_tiles = (n + TILE - 1) // TILE
+    key_alloc = n + n // 8 + 32            # DevBuf::ensure: bytes + bytes / 8 + 256 (in keys)
+    for tile in range(n_tiles):
+        s0 = tile * TILE
+        p0, pslot, pc, k0, kslot, kc = tile_copies(n, tile)
+        # bulk copies: 16-byte aligned source and destination, size a multiple of 16 bytes, never empty
+        assert pc > 0 and kc > 0
+        assert (p0 * 32) % 16 == 0 and (pslot * 32) % 16 == 0 and (pc * 32) % 16 == 0
+        assert (k0 * 8) % 16 == 0 and (kslot * 8) % 16 == 0 and (kc * 8) % 16 == 0
+        # inside the shared-memory arrays t_sp[TILE + 2], t_key[TILE + 4] and inside the allocations
+        assert 0 <= pslot and pslot + pc <= TILE + 2
+        assert 0 <= kslot and kslot + kc <= TILE + 4
+        assert p0 + pc <= n and k0 + kc <= key_alloc
+        # thread i reads t_sp[i], [i + 1], [i + 2] = bodies s - 1, s, s + 1 and t_key[i + 1 .. i + 3]
+        for i in range(min(TILE, n - s0)):
+            s = s0 + i
+            for slot, body, needed in ((i, s - 1, s > 0), (i + 1, s, True), (i + 2, s + 1, s + 1 < n)):
+                if needed:
+                    assert pslot <= slot < pslot + pc and p0 + (slot - pslot) == body
+            for slot, body, needed in ((i + 1, s - 1, s > 0), (i + 2, s, True), (i + 3, s + 1, s + 1 < n)):
+                if needed:
+                    assert kslot <= slot < kslot + kc and k0 + (slot - kslot) == body
+
+
+# ---- lists of climb starts --------------------------------------------------------------------------
+LISTS = 16
+
+
+def test_every_climb_start_is_taken_once():
+    rng = np.random.default_rng(3)
+    threads = 148 * 4 * 128
+    for counts in ([0] * 16, [1] * 16, list(rng.integers(0, 5000, 16)), [threads // 16 + 7] + [0] * 15,
+                   list(rng.integers(0, 3 * threads // 16, 16))):
+        taken = [np.zeros(c, int) for c in counts]
+        for gt in range(threads):
+            l = gt % LISTS
+            it = gt // LISTS
+            while it < counts[l]:
+                taken[l][it] += 1
+                it += threads // LISTS
+        for l in range(LISTS):
+            assert (taken[l] == 1).all()
