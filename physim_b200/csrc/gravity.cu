@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(SORT_THREADS, SORT_ITEMS >= 16 ? 2 : 4) sort_o
 //      encode_bucket_kernel  computes the keys (as K2) and appends (key, index) to one of 256
 //                            fixed-capacity buckets: bucket = number of splitters <= key >> lo, the
 //                            splitters being the 1/256 quantiles of the PREVIOUS evaluation's sorted
-//                            keys (splitter_kernel) - bodies move little per step, so the buckets
+//                            keys (splitter_block) - bodies move little per step, so the buckets
 //                            stay balanced whatever the distribution.  Any non-decreasing splitters
 //                            keep the result exact; stale ones only unbalance the buckets.
 //                            (per-CTA counts in shared memory, one global atomic per CTA and bucket)
@@ -935,8 +935,8 @@ struct CellArrays {
   double4* centre_ext;  // {cx, cy, cz, half-width}
   double4* com;         // {X, Y, Z, M}
   uint32_t capacity;
-  uint32_t small;
-  const unsigned* bad;   // != 0: the keys are not fully ordered (truncated sort too short): skip the build        // cells with <= this many bodies are summed directly in K6b
+  uint32_t small;        // cells with <= this many bodies are summed directly in cells_kernel
+  const unsigned* bad;   // != 0: the keys are not fully ordered (truncated sort too short): skip the build
 };
 
 constexpr uint32_t SMALL_CELL = 16;
@@ -1405,7 +1405,7 @@ __global__ void __launch_bounds__(128) com_kernel(const uchar2* __restrict__ ab,
     const uint32_t p = cells.parent[c0];
     if (p == NO_PARENT || done_in_fill(cells, p)) return;  // an ancestor's sum already covers it
   }
-  bool wrote = false;  // com[c] was written by this thread in this kernel (else by K6a/K6b, already visible)
+  bool wrote = false;  // com[c] was written by this thread in this kernel (else by cells_kernel, already visible)
   while (true) {
     const uint32_t p = cells.parent[c];
     if (p == NO_PARENT) break;
