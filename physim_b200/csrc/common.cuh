@@ -306,10 +306,11 @@ cudaError_t gravity_count_interactions(GravityWorkspace& ws, cudaStream_t stream
 // accelerations, writes x_{n+1} over x_{n-1} (the caller swaps the two buffers) and nothing else -
 // v_{n+1} = (x_{n+1} - x_n) / dt is derived on demand by verlet_velocity().  Also reduces the extent
 // max(|x|,|y|,|z|) of the new positions into *extent_out (atomicMax on the double's bits) and zeroes
-// *extent_zero (the slot the next step will reduce into).
+// *extent_zero (the slot the next step will reduce into) after saving its value - the extent the build of
+// this step used - in *extent_last.
 cudaError_t verlet_update_lean(const double4* cur, double4* prev_inout, const float4* acc32, size_t n, double dt,
-                               unsigned long long* extent_out, unsigned long long* extent_zero, cudaStream_t st,
-                               LaunchStats& ls);
+                               unsigned long long* extent_out, unsigned long long* extent_zero,
+                               unsigned long long* extent_last, cudaStream_t st, LaunchStats& ls);
 cudaError_t verlet_velocity(const double4* cur, const double4* prev, double4* vel, size_t n, double dt,
                             cudaStream_t st, LaunchStats& ls);
 cudaError_t verlet_update(double4* cur, double4* prev, double4* vel, const float4* acc32,

@@ -573,6 +573,7 @@ struct SimObj {
   // for the next tree build (ext_ready); ext_dirty: the slots must be zeroed before the next lean step
   bool vel_stale = false, ext_ready = false, ext_dirty = true;
   bool pin_cur = false;  // pb200_sim_gather_buffer handed out cur's address
+  bool ext_last_valid = false;  // ext[2] holds the extent the last build consumed (it came from a lean step's slot)
   int ext_slot = 0;
   DevBuf ext;
   LaunchStats ls;
@@ -604,6 +605,7 @@ cudaError_t sim_upload(SimObj& s, const Entity* state, size_t n) {
   s.vel_stale = false;
   s.ext_ready = false;
   s.ext_dirty = true;
+  s.ext_last_valid = false;
   if (n == 0) return cudaSuccess;
   PB_PASS(s.cur.ensure(s.slice * size_t(s.world) * sizeof(double4)));
   PB_PASS(s.prev.ensure(n * sizeof(double4)));
@@ -664,6 +666,7 @@ cudaError_t sim_step(SimObj& s, bool force_check) {
     s.first = false;
     s.ext_ready = false;
     s.ext_dirty = true;
+    s.ext_last_valid = false;
     return cudaSuccess;
   }
   s.ws.pos64 = s.cur.as<double4>();
@@ -672,7 +675,7 @@ cudaError_t sim_step(SimObj& s, bool force_check) {
   s.ws.extent_pre = nullptr;  // (the direct sum does not consume it)
   s.checked = true;
   if (lean) {
-    PB_PASS(s.ext.ensure(16));
+    PB_PASS(s.ext.ensure(32));  // two alternating slots + the extent the last build used (statistics)
     if (s.ext_dirty) {
       PB_CUDA(cudaMemsetAsync(s.ext.p, 0, 16, st));
       s.ext_dirty = false;
@@ -682,7 +685,8 @@ cudaError_t sim_step(SimObj& s, bool force_check) {
     const int out = s.ext_slot ^ 1;
     PB_PASS(verlet_update_lean(s.cur.as<double4>(), s.prev.as<double4>(), s.ws.acc.as<float4>(), s.n, s.dt,
                                s.ext.as<unsigned long long>() + out, s.ext.as<unsigned long long>() + s.ext_slot,
-                               st, s.ls));
+                               s.ext.as<unsigned long long>() + 2, st, s.ls));
+    s.ext_last_valid = s.ws.extent_cur == s.ext.as<unsigned long long>() + s.ext_slot;
     std::swap(s.cur, s.prev);  // x_{n+1} was written over x_{n-1}
     s.ws.pos64 = s.cur.as<double4>();
     s.ext_slot = out;
@@ -697,6 +701,7 @@ cudaError_t sim_step(SimObj& s, bool force_check) {
   s.first = false;
   s.ext_ready = false;
   s.ext_dirty = true;
+  s.ext_last_valid = false;
   return cudaSuccess;
 }
 
@@ -1354,8 +1359,10 @@ int pb200_sim_stats(void* sim, Pb200Stats* out) {
     const bool direct = s.prm.kind == PB200_SIMPLE_ASTRO || !(s.prm.theta > 0.0);
     if (!direct) {
       gravity_cell_total(s.ws, s.gpu.stream, &total);
+      // the extent the last build consumed: its own reduction, or the slot the lean verlet step left
       unsigned long long bits = 0;
-      cudaMemcpy(&bits, s.ws.extent_bits.p, 8, cudaMemcpyDeviceToHost);
+      const void* src = s.ext_last_valid ? static_cast<const void*>(s.ext.as<unsigned long long>() + 2) : s.ws.extent_bits.p;
+      cudaMemcpy(&bits, src, 8, cudaMemcpyDeviceToHost);
       std::memcpy(&s.stats.extent, &bits, 8);
     }
     s.stats.n_cells = total;

@@ -1581,10 +1581,11 @@ __global__ void __launch_bounds__(128) climb_kernel(const uint32_t* __restrict__
     }
     cells.com[c] = out;
     if (me.parent == NO_PARENT) break;
-    // release: com[c] must be visible (at L2) before the arrival is.  The children are read with ld.cg
-    // straight from L2, so no acquire fence (which would invalidate this SM's whole L1) is needed.
+    // acq_rel: com[c] must be visible before the arrival is (release), and the thread that completes the
+    // parent must see the sums its siblings published before their arrivals (acquire) - ordered by the PTX
+    // memory model itself, not by the control dependency and ld.cg's bypass of the L1.
     cuda::atomic_ref<uint32_t, cuda::thread_scope_device> arrived(cells.arrived[me.parent]);
-    const uint32_t old = arrived.fetch_add(me.count, cuda::std::memory_order_release);
+    const uint32_t old = arrived.fetch_add(me.count, cuda::std::memory_order_acq_rel);
     if (old + me.count != up.count) break;
     c = me.parent;
     me = up;

@@ -20,7 +20,8 @@ const char kPlugin[] = "physim_b200";
 const char kVersion[] = "0.1.0";
 const char kLicense[] = "MIT";
 const char kAuthor[] = "physim_b200 authors";
-const char kRepo[] = "https://github.com/jhb123/physim";
+// this plugin has no public repository of its own; physim shows the string verbatim (meta.rs:95-135)
+const char kRepo[] = "physim_b200 (drop-in CUDA plugin for physim; not the physim repository)";
 
 // transformers.rs:91-104 / :182-196 / :258-263 (property docs shown by `physcan <element>`)
 const char kBhProps[] =

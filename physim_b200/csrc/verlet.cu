@@ -80,10 +80,14 @@ __global__ void __launch_bounds__(256) verlet_lean_kernel(const double4* __restr
                                                           double4* __restrict__ prev_inout,
                                                           const float4* __restrict__ acc32, size_t n, double dt2,
                                                           unsigned long long* __restrict__ extent_out,
-                                                          unsigned long long* __restrict__ extent_zero) {
+                                                          unsigned long long* __restrict__ extent_zero,
+                                                          unsigned long long* __restrict__ extent_last) {
   pb_pdl_sync();
   const size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
-  if (i == 0) *extent_zero = 0ull;
+  if (i == 0) {  // the slot the build of this step consumed: kept for the statistics, then cleared for re-use
+    *extent_last = *extent_zero;
+    *extent_zero = 0ull;
+  }
   double m = 0.0;
   if (i < n) {
     const double4 x = cur[i];
@@ -227,13 +231,13 @@ cudaError_t rk4_stage(int stage, const double4* e_pos, const double4* e_vel, con
 }
 
 cudaError_t verlet_update_lean(const double4* cur, double4* prev_inout, const float4* acc32, size_t n, double dt,
-                               unsigned long long* extent_out, unsigned long long* extent_zero, cudaStream_t st,
-                               LaunchStats& ls) {
+                               unsigned long long* extent_out, unsigned long long* extent_zero,
+                               unsigned long long* extent_last, cudaStream_t st, LaunchStats& ls) {
   if (n == 0) return cudaSuccess;
   const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
   const double dt2 = dt * dt;  // dt.powi(2)
   PB_LAUNCH(ls, st, "verlet_lean_kernel",
-            pb_launch_pdl(verlet_lean_kernel, dim3(blocks), dim3(256), 0, st, cur, prev_inout, acc32, n, dt2, extent_out, extent_zero));
+            pb_launch_pdl(verlet_lean_kernel, dim3(blocks), dim3(256), 0, st, cur, prev_inout, acc32, n, dt2, extent_out, extent_zero, extent_last));
   return cudaGetLastError();
 }
 

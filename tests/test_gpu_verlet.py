@@ -162,6 +162,20 @@ def test_lean_resident_steps_equal_general_kernel(name, theta, monkeypatch):
             assert np.array_equal(x[k], y[k]), (i, k)
 
 
+def test_stats_extent_after_lean_steps():
+    """Pb200Stats.extent must be the root half-width the LAST build used, also in the lean resident loop
+    where the build takes its extent from the slot the previous verlet step reduced into."""
+    s = gen.readme_pipeline(20_000, seed=3, spin=1000.0)
+    dt = 1e-5
+    sim = api.Sim("astro2", theta=1.5, e=0.5, dt=dt)
+    sim.upload(s)
+    sim.run(5)
+    before = sim.download(s.copy())        # state the 6th build will see
+    sim.run(1)
+    want = max(np.abs(before[k]).max() for k in ("x", "y", "z"))
+    assert sim.stats()["extent"] == want
+
+
 def potential(s, e):
     """Conserved potential of the reference's force law: U = -mi mj (pi/2 - atan(r/sqrt(e)))/sqrt(e)."""
     p = np.stack([s["x"], s["y"], s["z"]], 1)
