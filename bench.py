@@ -45,16 +45,21 @@ WORKLOADS = {
                 desc="cube n=1000000 seed=1 spin=500 + 4 stars ! astro2 theta=1.5 e=0.5 ! verlet"),
 }
 
-# Algorithmic HBM bytes per body per launch for each kernel (DESIGN.md "kernels" table).
+# Algorithmic HBM bytes per body per launch, SURVEY.md §8(d)'s rows (DESIGN.md §4 maps kernels to rows):
+#   extent 24 R | encode 24 R + 8 + 4 W | sort pass 12 R + 12 W | gather 4 + 32 R + 16 W |
+#   cell build (units, scan, cell table, centres of mass) 76 | accelerations out 16 R + 12 W | verlet 120-132
+# The cell-build row is charged IN FULL to cells_kernel (the kernel `roofline` names at c3) although
+# unit / scan / kids / climb share it: the fraction reported for cells_kernel is therefore an upper bound
+# on its own share, and `roofline_step` below carries the whole 0.55 kB/body against the whole step.
 ALG_BYTES_PER_BODY = {
-    "extent_kernel": 32, "encode_kernel": 32 + 12, "sort_hist_all": 8, "sort_onesweep_pass": 12 + 12,
-    "gather_kernel": 4 + 32 + 32, "unit_kernel": 8 + 32 + 2 + 4 + 1.1, "scan_lookback_kernel": 8,
-    "cells_kernel": 8 + 32 + 2 + 4 + 1.1 + 1.5 * (1 + 4 + 4 + 32 + 4 + 4 + 32) + 32, "parent_kernel": 1.5 * 8, "com_kernel": 1.5 * (32 + 32 + 12),
-    "kids_kernel": 1.5 * (4 + 4 + 1) + 0.09 * (4 * 8 + 16 + 4), "climb_kernel": 1.5 * 1 + 0.09 * (16 + 4 * 32 + 32 + 12),
-    "walk_kernel": 32 + 4 + 1 + 16, "verlet_kernel": 32 + 32 + 16 + 32 + 32 + 32,
-    "verlet_lean_kernel": 32 + 32 + 16 + 32, "verlet_velocity_kernel": 32 + 32 + 32,
-    "to_soa_kernel": 32 + 16, "sort_local_kernel": 12 + 12 + 32 + 32, "encode_bucket_kernel": 32 + 12,
+    "extent_kernel": 24, "encode_kernel": 36, "encode_bucket_kernel": 36, "sort_onesweep_pass": 24,
+    "sort_local_kernel": 24 + 52, "gather_kernel": 52, "cells_kernel": 76, "walk_kernel": 28,
+    "verlet_kernel": 132, "verlet_lean_kernel": 32 + 32 + 16 + 32, "verlet_velocity_kernel": 32 + 32 + 32,
+    "to_soa_kernel": 32 + 24, "bbox_kernel": 24,
+    # inside the cell-build row (no separate figure in §8(d)); compulsory bytes of each, for the per-kernel list only
+    "unit_kernel": 8 + 32 + 2 + 4 + 1.1, "scan_lookback_kernel": 8, "kids_kernel": 1.5 * 9, "climb_kernel": 0.09 * 188,
 }
+STEP_BYTES_PER_BODY = 550  # "Sum ~ 0.55 kB/body-step"
 FLOP_PER_INTERACTION = 19
 NCU_KERNELS = "r01d_ncu_c3_kernels.json"  # per-kernel DRAM traffic of the committed ncu --set full capture
 
@@ -291,6 +296,7 @@ def run_ours(args, w):
                 "peak_source": peak_kind, "avg_launch_ms": per_launch_ms,
                 "share_of_step": top["ms"] / tot_ms,
                 "alg_bytes_per_launch": alg_bytes,
+                "alg_bytes_source": "SURVEY.md §8(d) row for this kernel x bodies (cells_kernel: the whole 76 B/body cell-build row)",
                 "kernels": [{"kernel": k["kernel"], "launches_per_step": k["launches"] / prof_steps,
                              "ms_per_step": k["ms"] / prof_steps,
                              "gbs": (ALG_BYTES_PER_BODY.get(k["kernel"], 0) * n / (k["ms"] / k["launches"] * 1e-3) / 1e9)
@@ -311,6 +317,11 @@ def run_ours(args, w):
                          "back to back as in the simulation loop",
                    "precision": "keys/tree/acceptance/integrator fp64, force law fp32"},
         "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks,
+        # the whole step against HBM: SURVEY §8(d)'s 0.55 kB/body over the measured step time
+        "roofline_step": {"bound": "hbm", "achieved": STEP_BYTES_PER_BODY * n / (ms / args.steps * 1e-3) / 1e9,
+                          "peak": hbm_peak, "unit": "GB/s",
+                          "frac": STEP_BYTES_PER_BODY * n / (ms / args.steps * 1e-3) / 1e9 / hbm_peak,
+                          "alg_bytes_per_body": STEP_BYTES_PER_BODY, "n_gpus": world},
     }
 
     if rank == 0 and world == 1 and not args.skip_extras:

@@ -29,6 +29,15 @@ constexpr uint32_t NO_PARENT = 0xffffffffu;
 constexpr int MERGE_RUN_CAP = 1024;  // longer chains of <1e-9 neighbours are left unmerged
 constexpr unsigned char NSV_NONE = 255;  // entry of a body that heads no cell (merged into the unit before it)
 
+// Number of bodies a tree kernel works on: a host value (single GPU: every body), or a value left on the
+// device by the sort of the same build (sharded build: the bodies whose keys fall in this rank's key range
+// are only counted on the device; grids are then sized for the capacity and surplus CTAs leave at once).
+struct NRef {
+  const uint32_t* dev;
+  uint32_t host;
+  __device__ __forceinline__ size_t get() const { return dev ? size_t(*dev) : size_t(host); }
+};
+
 template <int DIM>
 struct TreeDim {
   static constexpr int LM = (DIM == 3) ? 21 : 31;  // key levels: 63 / 62 bits
@@ -392,7 +401,9 @@ __global__ void __launch_bounds__(256) encode_bucket_kernel(const double4* __res
                                                             const uint64_t* __restrict__ splitters /*[256]*/,
                                                             int lo, uint64_t* __restrict__ bkey,
                                                             uint32_t* __restrict__ bidx, unsigned cap,
-                                                            unsigned* __restrict__ cursor /*[256]*/) {
+                                                            unsigned* __restrict__ cursor /*[256]*/,
+                                                            const uint64_t* __restrict__ cuts /* sharded build: keep
+                                                            cuts[0] <= key < cuts[1]; nullptr: every body */) {
   pb_pdl_sync();
   constexpr int LM = TreeDim<DIM>::LM;
   __shared__ unsigned cnt[256];
@@ -433,6 +444,8 @@ __global__ void __launch_bounds__(256) encode_bucket_kernel(const double4* __res
     }
   }
   unsigned r[ENC_ITEMS], d[ENC_ITEMS];
+  const uint64_t cut_lo = cuts ? cuts[0] : 0ull, cut_hi = cuts ? cuts[1] : ~0ull;
+  bool keep[ENC_ITEMS];
 #pragma unroll
   for (int e = 0; e < ENC_ITEMS; ++e) {
     // bucket = number of splitters <= key >> lo, minus one (spl[0] = 0): 8-step search, no divergence
@@ -443,7 +456,8 @@ __global__ void __launch_bounds__(256) encode_bucket_kernel(const double4* __res
       if (spl[b + step] <= kk) b += step;
     d[e] = b;
     const size_t i = tile + size_t(e) * 256 + tid;
-    r[e] = i < n ? atomicAdd(&cnt[b], 1u) : 0u;
+    keep[e] = i < n && k[e] >= cut_lo && k[e] < cut_hi;
+    r[e] = keep[e] ? atomicAdd(&cnt[b], 1u) : 0u;
   }
   __syncthreads();
   {
@@ -454,7 +468,7 @@ __global__ void __launch_bounds__(256) encode_bucket_kernel(const double4* __res
 #pragma unroll
   for (int e = 0; e < ENC_ITEMS; ++e) {
     const size_t i = tile + size_t(e) * 256 + tid;
-    if (i < n) {
+    if (keep[e]) {
       const unsigned slot = gbase[d[e]] + r[e];
       if (slot < cap) {  // else: bucket over capacity, sort_local_kernel flags the build
         bkey[size_t(d[e]) * cap + slot] = k[e];
@@ -476,7 +490,8 @@ __global__ void __launch_bounds__(NT, 1024 / NT) sort_local_kernel(
     const uint64_t* __restrict__ splitters, unsigned cap, int lo, int key_bits, uint64_t* __restrict__ keys,
     uint32_t* __restrict__ vals,
     const double4* __restrict__ pos, double4* __restrict__ spos, unsigned* __restrict__ bad,
-    unsigned* __restrict__ stat_max) {
+    unsigned* __restrict__ stat_max, uint32_t* __restrict__ n_out /* sharded build: bodies sorted in all, capacity */,
+    uint32_t n_cap) {
   pb_pdl_sync();
   static_assert(NT >= 256 && NT % 32 == 0 && (1 << LOCAL_BIN_BITS) % NT == 0, "scan layout");
   constexpr int NBINS = 1 << LOCAL_BIN_BITS, BPT = NBINS / NT;  // bins per thread in the scan
@@ -485,14 +500,22 @@ __global__ void __launch_bounds__(NT, 1024 / NT) sort_local_kernel(
   uint32_t* vs = reinterpret_cast<uint32_t*>(ks + cap);
   unsigned* bins = vs + cap;     // [NBINS]: counts -> running ends
   unsigned* wsum = bins + NBINS; // [32]
-  unsigned* seg = wsum + 32;     // start, count of this bucket, largest bin
+  unsigned* seg = wsum + 32;     // start, count of this bucket, largest bin, (sharded build) total of all buckets
   const int tid = threadIdx.x;
   {
     const unsigned c = tid < 256 ? cursor[tid] : 0u;
     const unsigned ex = block_exclusive_scan_nt<NT>(c, wsum);
     if (tid == int(blockIdx.x)) { seg[0] = ex; seg[1] = c; }
     if (tid == 0) seg[2] = 0u;
+    if (n_out && tid == 255) {
+      seg[3] = ex + c;
+      if (blockIdx.x == 0) {
+        *n_out = min(ex + c, n_cap);  // (the later kernels never index past the capacity)
+        if (ex + c > n_cap) *bad = 1u;   // this rank's key range holds more bodies than its arrays: re-planned by the host
+      }
+    }
     __syncthreads();
+    if (n_out && seg[3] > n_cap) return;
   }
   const unsigned start = seg[0], cnt = seg[1];
   if (cnt == 0u) return;
@@ -641,12 +664,10 @@ __device__ __forceinline__ void nsv_level2_block(unsigned sb, uint8_t* __restric
 // small jobs that ride along with the scan of the cell counts (each would otherwise be a launch of a
 // few CTAs between two kernels of the build): the CTAs whose ticket is past the last scan tile do them
 struct ScanSide {
-  unsigned nsuper;            // CTAs [0, nsuper): nsv_level2_block
-  uint8_t* t2;
-  size_t b_pad, nblocks;
+  uint8_t* t2;                // CTAs [0, nsuper): nsv_level2_block (nsuper = super-blocks of the n bodies)
+  size_t b_pad;               // stride of a level of t2 (allocation)
   uint8_t* t3;
   const uint64_t* sorted;     // CTA nsuper: splitter_block
-  size_t n;
   uint64_t* spl_out;
 };
 
@@ -659,19 +680,24 @@ constexpr int SCAN_TILE = 256 * SCAN_ITEMS;
 constexpr unsigned long long SCAN_PART = 1ull << 32, SCAN_INCL = 2ull << 32;
 
 template <bool SIDE>
-__global__ void __launch_bounds__(256) scan_lookback_kernel(const uint32_t* __restrict__ in, size_t n,
+__global__ void __launch_bounds__(256) scan_lookback_kernel(const uint32_t* __restrict__ in, NRef nref,
                                                             uint32_t* __restrict__ out,
                                                             unsigned long long* status,
-                                                            unsigned* tile_counter, unsigned tiles, ScanSide side) {
+                                                            unsigned* tile_counter, ScanSide side) {
   pb_pdl_sync();
   __shared__ unsigned tile_s, tile_prefix_s;
   if (threadIdx.x == 0) tile_s = atomicAdd(tile_counter, 1u);
   __syncthreads();
   const unsigned tile = tile_s;
-  if (SIDE && tile >= tiles) {  // (the last tickets: nothing of the scan waits for these CTAs)
-    const unsigned job = tile - tiles;
-    if (job < side.nsuper) nsv_level2_block(job, side.t2, side.b_pad, side.nblocks, side.t3);
-    else if (job == side.nsuper) splitter_block(side.sorted, side.n, side.spl_out);
+  const size_t n = nref.get();
+  const unsigned tiles = max(1u, unsigned((n + SCAN_TILE - 1) / SCAN_TILE));  // (n = 0: one tile writes out[0] = 0)
+  if (tile >= tiles) {  // (the last tickets: nothing of the scan waits for these CTAs)
+    if (SIDE) {
+      const unsigned job = tile - tiles;
+      const size_t nblocks = (n + 255) / 256, nsuper = (nblocks + 255) / 256;
+      if (job < nsuper) nsv_level2_block(job, side.t2, side.b_pad, nblocks, side.t3);
+      else if (job == nsuper) splitter_block(side.sorted, n, side.spl_out);
+    }
     return;
   }
   const size_t base = size_t(tile) * SCAN_TILE + size_t(threadIdx.x) * SCAN_ITEMS;
@@ -735,6 +761,7 @@ __global__ void __launch_bounds__(256) scan_lookback_kernel(const uint32_t* __re
     }
     if (base + SCAN_ITEMS == n) out[n] = run;
   } else {
+    if (n == 0 && threadIdx.x == 0) out[0] = 0u;
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS; ++i) {
       if (base + i < n) out[base + i] = run;
@@ -803,14 +830,17 @@ constexpr int UNIT_CTAS_PER_SM = 5;
 
 template <int DIM>
 __global__ void __launch_bounds__(256) unit_kernel(const uint64_t* __restrict__ key,
-                                                   const double4* __restrict__ sp, size_t n,
+                                                   const double4* __restrict__ sp, NRef nref,
                                                    uchar2* __restrict__ ab,
                                                    uint32_t* __restrict__ cnt,
                                                    unsigned* __restrict__ max_shared_plus1,
                                                    int levels_sorted, uint8_t* __restrict__ nsv1,
-                                                   size_t n_pad, uint8_t* __restrict__ nsv2, unsigned n_tiles) {
+                                                   size_t n_pad /* offset of the window minima: allocation */,
+                                                   uint8_t* __restrict__ nsv2) {
   pb_pdl_sync();
   constexpr int LM = TreeDim<DIM>::LM;
+  const size_t n = nref.get();
+  const unsigned n_tiles = unsigned((n + UNIT_TILE - 1) / UNIT_TILE);
   // t_sp[b][i] = sp[s0 - 1 + i] (i = 0 .. 257), t_key[b][i] = key[s0 - 2 + i] (i = 0 .. 259): the windows
   // start at 16-byte aligned addresses and are a multiple of 16 bytes long, as bulk copies must be
   __shared__ __align__(128) double4 t_sp[2][UNIT_TILE + 2];
@@ -985,7 +1015,39 @@ struct NsvTables {
   size_t b_pad;   // stride of a level of t2
   const uint8_t* t3;
   size_t n, nblocks, nsuper;
+  // the sizes that follow from the body count (n_pad here is the LOGICAL one: whole blocks of the n bodies;
+  // t16 and b_pad carry the allocation's strides)
+  __device__ __forceinline__ void set_n(size_t nn) {
+    n = nn;
+    nblocks = (nn + 255) / 256;
+    n_pad = nblocks * 256;
+    nsuper = (nblocks + 255) / 256;
+  }
 };
+
+// Sharded build only (slot_cell == nullptr otherwise): where the cells that carry a level-K key prefix
+// ended up in this rank's table.  slot_cell[q] = 1 + index of the deepest cell holding exactly the bodies
+// whose keys start with the level-K prefix q: the level-K cell itself, or the leaf above level K that holds
+// them (one unit).  Zeroed per build; 0 = no body of this rank has the prefix.
+struct TopSlots {
+  uint32_t* slot_cell;
+  int level;  // K
+};
+
+// What a sharded build adds to the build of one rank (nullptr: single GPU, every body).
+struct ShardBuild {
+  const uint64_t* cuts;  // device: this rank keeps the bodies with cuts[0] <= key < cuts[1]
+  uint32_t* n_local;     // device: how many those were (written by the sort, read by every later kernel)
+  size_t n_cap;          // capacity of the per-rank arrays, in bodies
+  TopSlots slots;
+};
+
+struct BuildOut {
+  CellArrays cells;
+  NRef nref;
+  size_t n_cap;
+};
+
 
 // first index in [j, end) (end - j <= 256, same 256-aligned block) whose entry is <= l, else end
 __device__ __forceinline__ size_t nsv_descend(const uint8_t* __restrict__ tab, size_t stride, size_t j, size_t end,
@@ -1097,14 +1159,18 @@ __global__ void __launch_bounds__(256, MIN_BLOCKS) cells_kernel(const uint64_t* 
                                                     const double4* __restrict__ sp,
                                                     const uint32_t* __restrict__ perm,
                                                     const uchar2* __restrict__ ab,
-                                                    const uint32_t* __restrict__ cell_start, size_t n,
+                                                    const uint32_t* __restrict__ cell_start, NRef nref,
                                                     const unsigned long long* __restrict__ extent_bits,
                                                     const unsigned* __restrict__ tree_meta,
-                                                    unsigned* __restrict__ sticky, NsvTables tv, CellArrays cells) {
+                                                    unsigned* __restrict__ sticky, NsvTables tv, CellArrays cells,
+                                                    TopSlots slots) {
   pb_pdl_sync();
   constexpr int LM = TreeDim<DIM>::LM;
+  const size_t n = nref.get();
+  tv.set_n(n);
   const size_t s = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
   const unsigned lane = threadIdx.x & 31u;
+  if (size_t(blockIdx.x) * blockDim.x >= n && blockIdx.x != 0) return;  // (surplus CTAs of a grid sized for the capacity)
   const uint32_t total = cell_start[n];
   if (s == 0) {
     // worst case over every build since the last host check (builds run unverified in between):
@@ -1168,6 +1234,10 @@ __global__ void __launch_bounds__(256, MIN_BLOCKS) cells_kernel(const uint64_t* 
       cells.count[c] = static_cast<uint32_t>(e - s);
       cells.skip[c] = cell_start[e];
       cells.com[c] = unit_leaf(sp, perm, s, e);
+    }
+    if (slots.slot_cell && top <= slots.level) {  // s is the first body of its level-K prefix
+      const uint32_t q = uint32_t(kme >> (DIM * (LM - slots.level)));
+      slots.slot_cell[q] = c0 + uint32_t(min(leaf_level, slots.level) - top) + 1u;
     }
   }
 
@@ -1458,14 +1528,14 @@ constexpr uint32_t READY_LISTS = 16;
 constexpr uint32_t READY_STRIDE = 32;  // words between the lists' counters: one 128-byte line (one L2 atomic unit) each  // more children than 2^DIM (sibling leaves of a pseudo level)
 
 template <int DIM>
-__global__ void __launch_bounds__(256) kids_kernel(const uint32_t* __restrict__ cell_start, size_t n,
+__global__ void __launch_bounds__(256) kids_kernel(const uint32_t* __restrict__ cell_start, NRef nref,
                                                    CellArrays cells, uint32_t* __restrict__ kid_tab,
                                                    uint32_t* __restrict__ ready_list, unsigned* __restrict__ n_ready,
                                                    uint32_t sub_cap) {
   pb_pdl_sync();
   constexpr uint32_t K = 1u << DIM;
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t total = cell_start[n];
+  const uint32_t total = cell_start[nref.get()];
   const bool live = !(total > cells.capacity || *cells.bad) && p < total;
   uint32_t cnt = 0, end = 0;
   if (live) {
@@ -1505,13 +1575,13 @@ __global__ void __launch_bounds__(256) kids_kernel(const uint32_t* __restrict__ 
 }
 
 template <int DIM>
-__global__ void __launch_bounds__(128) climb_kernel(const uint32_t* __restrict__ cell_start, size_t n,
+__global__ void __launch_bounds__(128) climb_kernel(const uint32_t* __restrict__ cell_start, NRef nref,
                                                     CellArrays cells, const uint32_t* __restrict__ kid_tab,
                                                     const uint32_t* __restrict__ ready_list,
                                                     const unsigned* __restrict__ n_ready, uint32_t sub_cap) {
   pb_pdl_sync();
   constexpr int K = 1 << DIM;
-  const uint32_t total = cell_start[n];
+  const uint32_t total = cell_start[nref.get()];
   if (total > cells.capacity || *cells.bad) return;
   const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t l = gt % READY_LISTS, starts = n_ready[l * READY_STRIDE];
@@ -1731,18 +1801,68 @@ __global__ void __launch_bounds__(256) walk_kernel(const double4* __restrict__ s
 // copies below.  Massless bodies and the padding get 1/m = 0, e/m = +inf: (r² + e)/m = inf, so
 // their weight rsqrt(inf) is exactly 0.  Also publishes the ranges that decide whether the
 // folded-mass form of the kernel is safe (see direct_kernel_x2):
-//   meta[0] max |coordinate| (float bits), meta[1] 0x7fffffff - bits(min positive mass),
+//   meta[0] max |coordinate - box centre| (float bits), meta[1] 0x7fffffff - bits(min positive mass),
 //   meta[2] bits(max mass), meta[3] != 0: a negative or non-finite mass exists
+// Bounding box of the finite coordinates, for the fp32 copy below: the direct kernel differences fp32
+// positions, so they are taken relative to the centre of the box (in fp64, BEFORE rounding to fp32) - a
+// system far from the origin (`cube centre=[1000,0,0]`) would otherwise lose ~|x| * 2^-24 of every
+// difference.  box[0..2] = min x,y,z, box[3..5] = max, as order-preserving u64 images of the doubles.
+__device__ __forceinline__ unsigned long long ordered_bits(double v) {
+  const unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(v));
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double from_ordered_bits(unsigned long long o) {
+  const unsigned long long b = (o >> 63) ? (o & 0x7fffffffffffffffull) : ~o;
+  return __longlong_as_double(static_cast<long long>(b));
+}
+constexpr unsigned long long BOX_EMPTY_MIN = ~0ull, BOX_EMPTY_MAX = 0ull;
+
+__global__ void __launch_bounds__(256) bbox_kernel(const double4* __restrict__ pos, size_t n,
+                                                   unsigned long long* __restrict__ box) {
+  unsigned long long lo[3] = {BOX_EMPTY_MIN, BOX_EMPTY_MIN, BOX_EMPTY_MIN}, hi[3] = {BOX_EMPTY_MAX, BOX_EMPTY_MAX, BOX_EMPTY_MAX};
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+    const double4 p = pos[i];
+    const double c[3] = {p.x, p.y, p.z};
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+      if (fabs(c[a]) <= 1.7976931348623157e308) {  // finite
+        const unsigned long long o = ordered_bits(c[a]);
+        lo[a] = min(lo[a], o);
+        hi[a] = max(hi[a], o);
+      }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[a] = min(lo[a], __shfl_xor_sync(FULL, lo[a], o));
+      hi[a] = max(hi[a], __shfl_xor_sync(FULL, hi[a], o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+      if (lo[a] != BOX_EMPTY_MIN) atomicMin(&box[a], lo[a]);
+      if (hi[a] != BOX_EMPTY_MAX) atomicMax(&box[3 + a], hi[a]);
+    }
+  }
+}
+
+// centre of the box (0 for an axis without a finite coordinate)
+__device__ __forceinline__ double box_centre(const unsigned long long* __restrict__ box, int a) {
+  const unsigned long long lo = box[a], hi = box[3 + a];
+  if (lo == BOX_EMPTY_MIN || hi == BOX_EMPTY_MAX) return 0.0;
+  return 0.5 * from_ordered_bits(lo) + 0.5 * from_ordered_bits(hi);
+}
+
 __global__ void __launch_bounds__(256) to_soa_kernel(const double4* __restrict__ pos, size_t n, size_t n_pad,
-                                                     float easing, float* __restrict__ soa,
-                                                     unsigned* __restrict__ meta) {
+                                                     float easing, const unsigned long long* __restrict__ box,
+                                                     float* __restrict__ soa, unsigned* __restrict__ meta) {
   const size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
   float xm = 0.f, mlo = __int_as_float(0x7f800000), mhi = 0.f;
   bool odd = false;
+  const double ox = box_centre(box, 0), oy = box_centre(box, 1), oz = box_centre(box, 2);
   if (i < n_pad) {
-    double4 p = make_double4(0.0, 0.0, 0.0, 0.0);
+    double4 p = make_double4(ox, oy, oz, 0.0);
     if (i < n) p = pos[i];
-    const float x = float(p.x), y = float(p.y), z = float(p.z), m = float(p.w);
+    const float x = float(p.x - ox), y = float(p.y - oy), z = float(p.z - oz), m = float(p.w);
     soa[i] = x;
     soa[n_pad + i] = y;
     soa[2 * n_pad + i] = z;
@@ -1947,6 +2067,60 @@ __global__ void __launch_bounds__(DIRECT_THREADS) direct_kernel_x2(
   }
 }
 
+// Direct sum for small systems (n <= DIRECT_SMALL_N: the few-body configurations - solar.toml has 67
+// bodies, moons 0.01 from their planets): p_b - p_a is taken in fp64 like the reference and like the tree
+// walk, so close pairs keep their direction however small the separation is relative to the coordinates;
+// the force law stays fp32 (one MUFU.RSQ per pair), the terms are summed in fp64.  One thread per target, sources staged through shared
+// memory as the fp64 {x,y,z,m} records themselves (no fp32 copy).  At these sizes the FP64 subtractions
+// cost microseconds; the packed-FP32 kernel above is the one that matters from ~10^5 bodies up.
+constexpr size_t DIRECT_SMALL_N = 32768;
+constexpr int DIRECT_SMALL_THREADS = 128;
+
+__global__ void __launch_bounds__(DIRECT_SMALL_THREADS) direct_small_kernel(
+    const double4* __restrict__ pos, const uint8_t* __restrict__ fixed, size_t n, size_t t0, size_t n_targets,
+    float easing, float tiny, float4* __restrict__ acc) {
+  __shared__ double4 tile[DIRECT_SMALL_THREADS];
+  const size_t lt = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  const bool live = lt < n_targets;
+  const size_t i = live ? t0 + lt : 0;
+  const double4 me = pos[i < n ? i : 0];
+  // the per-pair terms are fp32; they are ADDED in fp64 (2000 fp32 additions next to one dominant partner
+  // term lose ~1e-5 of it; negligible cost at these sizes)
+  double ax = 0.0, ay = 0.0, az = 0.0;
+  for (size_t j0 = 0; j0 < n; j0 += DIRECT_SMALL_THREADS) {
+    const size_t j = j0 + threadIdx.x;
+    tile[threadIdx.x] = j < n ? pos[j] : make_double4(me.x, me.y, me.z, 0.0);
+    __syncthreads();
+    const int cnt = int(min(size_t(DIRECT_SMALL_THREADS), n - j0));
+#pragma unroll 4
+    for (int q = 0; q < cnt; ++q) {
+      const double4 sb = tile[q];
+      const float dx = static_cast<float>(sb.x - me.x);
+      const float dy = static_cast<float>(sb.y - me.y);
+      const float dz = static_cast<float>(sb.z - me.z);
+      float r2 = fmaf(dx, dx, tiny);  // tiny keeps r = 0 pairs (self / coincident: skipped by the reference) at w * 0 = 0
+      r2 = fmaf(dy, dy, r2);
+      r2 = fmaf(dz, dz, r2);
+      const float sft = r2 + easing;
+      const float mw = static_cast<float>(sb.w) * rsqrt_approx(r2 * sft * sft);
+      ax += double(mw * dx);
+      ay += double(mw * dy);
+      az += double(mw * dz);
+    }
+    __syncthreads();
+  }
+  if (!live) return;
+  float fx = float(ax), fy = float(ay), fz = float(az);
+  uint32_t inter = static_cast<uint32_t>(n);
+  if (fixed[i]) {
+    fx = fy = fz = 0.f;
+    inter = 0;
+  } else if (me.w == 0.0) {
+    fx = fy = fz = __int_as_float(0x7fc00000);
+  }
+  acc[i] = make_float4(fx, fy, fz, __uint_as_float(inter));
+}
+
 // sums the source splits in a fixed order and applies the per-target rules
 __global__ void __launch_bounds__(256) direct_finish_kernel(const float4* __restrict__ part, int splits,
                                                             size_t t0, size_t n_targets,
@@ -2010,21 +2184,24 @@ cudaError_t exclusive_scan(const uint32_t* in, uint32_t* out, size_t n, DevBuf& 
   PB_PASS(tmp.ensure(size_t(tiles) * 8 + 16));  // [tile status words][tile counter]
   PB_CUDA(cudaMemsetAsync(tmp.p, 0, size_t(tiles) * 8 + 16, st));
   PB_LAUNCH(ls, st, "scan_lookback_kernel",
-            scan_lookback_kernel<false><<<tiles, 256, 0, st>>>(in, n, out, tmp.as<unsigned long long>(),
+            scan_lookback_kernel<false><<<tiles, 256, 0, st>>>(in, NRef{nullptr, uint32_t(n)}, out, tmp.as<unsigned long long>(),
                                                                reinterpret_cast<unsigned*>(tmp.as<unsigned long long>() + tiles),
-                                                               tiles, ScanSide{}));
+                                                               ScanSide{}));
   return cudaGetLastError();
 }
 
 // the scan of the build's cell counts, with the side jobs; `scratch` ([tiles status words][counter]) is
 // part of the build's zeroed scratch block
 inline size_t scan_scratch_bytes(size_t n) { return size_t(blocks_for(n, SCAN_TILE)) * 8 + 16; }
-cudaError_t exclusive_scan_with_side(const uint32_t* in, uint32_t* out, size_t n, unsigned long long* scratch,
+// n_cap: the host's bound on the body count (== the count itself unless nref.dev is set); sizes the grid and
+// places the ticket counter behind n_cap's status words
+cudaError_t exclusive_scan_with_side(const uint32_t* in, uint32_t* out, NRef nref, size_t n_cap, unsigned long long* scratch,
                                      const ScanSide& side, cudaStream_t st, LaunchStats& ls) {
-  const unsigned tiles = blocks_for(n, SCAN_TILE);
+  const unsigned tiles = blocks_for(n_cap, SCAN_TILE);
+  const unsigned nsuper = blocks_for(blocks_for(n_cap, 256), 256);
   PB_LAUNCH(ls, st, "scan_lookback_kernel",
-            pb_launch_pdl(scan_lookback_kernel<true>, dim3(tiles + side.nsuper + 1), dim3(256), 0, st, 
-                in, n, out, scratch, reinterpret_cast<unsigned*>(scratch + tiles), tiles, side));
+            pb_launch_pdl(scan_lookback_kernel<true>, dim3(tiles + nsuper + 1), dim3(256), 0, st,
+                in, nref, out, scratch, reinterpret_cast<unsigned*>(scratch + tiles), side));
   return cudaGetLastError();
 }
 
@@ -2093,9 +2270,17 @@ cudaError_t sort_prepare(GravityWorkspace& ws, size_t n, int key_bits, int lo, i
 
 // keys -> sorted keys + permutation (ws.sorted_key / ws.perm) + sorted {x,y,z,m} (ws.spos64).
 // `bad` is the build's "keys not ordered" flag.
+inline int shard_sort_mode(size_t n_cap) {
+  const size_t want = n_cap / 256 + n_cap / 2048 + 64;
+  for (int m = 1; m <= 3; ++m)
+    if (want <= LOCAL_CAP[m]) return m;
+  return 0;
+}
+
+// n: every body of ws.pos64.  sh != nullptr: only the bodies in this rank's key range are kept (bucket forms only)
 template <int DIM>
 cudaError_t encode_and_sort(GravityWorkspace& ws, size_t n, const SortBuffers& sb, unsigned* bad, cudaStream_t st,
-                            LaunchStats& ls, uint64_t** splitters_out) {
+                            LaunchStats& ls, uint64_t** splitters_out, const ShardBuild* sh) {
   uint64_t* k[2] = {ws.key0.as<uint64_t>(), ws.key1.as<uint64_t>()};
   uint32_t* v[2] = {ws.idx0.as<uint32_t>(), ws.idx1.as<uint32_t>()};
   unsigned* stat_max = ws.sticky.as<unsigned>() + 3;
@@ -2109,20 +2294,22 @@ cudaError_t encode_and_sort(GravityWorkspace& ws, size_t n, const SortBuffers& s
     PB_LAUNCH(ls, st, "encode_bucket_kernel",
               pb_launch_pdl(encode_bucket_kernel<DIM>, dim3(blocks_for(n, 256 * ENC_ITEMS)), dim3(256), 0, st, 
                   ws.pos64, n, ws.extent_cur, spl_in, sb.lo, ws.bucket_key.as<uint64_t>(),
-                  ws.bucket_idx.as<uint32_t>(), sb.cap, sb.ghist));
+                  ws.bucket_idx.as<uint32_t>(), sb.cap, sb.ghist, sh ? sh->cuts : nullptr));
+    uint32_t* n_out = sh ? sh->n_local : nullptr;
+    const uint32_t n_cap = sh ? uint32_t(sh->n_cap) : 0u;
     const size_t smem = sort_local_smem(sb.cap);
     if (sb.mode == 1) {
       PB_CUDA(cudaFuncSetAttribute(sort_local_kernel<512, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
       PB_LAUNCH(ls, st, "sort_local_kernel",
                 pb_launch_pdl(sort_local_kernel<512, 9>, dim3(256), dim3(512), smem, st, 
                     ws.bucket_key.as<uint64_t>(), ws.bucket_idx.as<uint32_t>(), sb.ghist, spl_in, sb.cap, sb.lo,
-                    sb.key_bits, k[0], v[0], ws.pos64, ws.spos64.as<double4>(), bad, stat_max));
+                    sb.key_bits, k[0], v[0], ws.pos64, ws.spos64.as<double4>(), bad, stat_max, n_out, n_cap));
     } else {
       PB_CUDA(cudaFuncSetAttribute(sort_local_kernel<1024, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
       PB_LAUNCH(ls, st, "sort_local_kernel",
                 pb_launch_pdl(sort_local_kernel<1024, 8>, dim3(256), dim3(1024), smem, st, 
                     ws.bucket_key.as<uint64_t>(), ws.bucket_idx.as<uint32_t>(), sb.ghist, spl_in, sb.cap, sb.lo,
-                    sb.key_bits, k[0], v[0], ws.pos64, ws.spos64.as<double4>(), bad, stat_max));
+                    sb.key_bits, k[0], v[0], ws.pos64, ws.spos64.as<double4>(), bad, stat_max, n_out, n_cap));
     }
     ws.sorted_key = k[0];
     ws.perm = v[0];
@@ -2157,10 +2344,13 @@ cudaError_t encode_and_sort(GravityWorkspace& ws, size_t n, const SortBuffers& s
   return cudaGetLastError();
 }
 
+// keys -> sort -> units -> scan -> cell table -> centres of mass, for all ws.n bodies or (sh != nullptr)
+// for those in this rank's key range
 template <int DIM>
-cudaError_t tree_evaluate(GravityWorkspace& ws, const GravityParams& prm, size_t t0, size_t t1,
-                          float easing, float tiny, cudaStream_t st, LaunchStats& ls) {
-  const size_t n = ws.n;
+cudaError_t tree_build(GravityWorkspace& ws, const ShardBuild* sh, cudaStream_t st, LaunchStats& ls, BuildOut* out) {
+  const size_t n_all = ws.n;
+  const size_t n = sh ? sh->n_cap : n_all;  // capacity of everything indexed by sorted body
+  const NRef nref{sh ? sh->n_local : nullptr, uint32_t(n)};
   // one zeroed scratch block per build: [extent / flags: 32 B][scan status + counter][sort head][climb-start counters]
   const size_t scan_bytes = (scan_scratch_bytes(n) + 15) / 16 * 16;
   const size_t ready_off = (32 + scan_bytes + SORT_HEAD_WORDS * 4 + 127) / 128 * 128;
@@ -2170,7 +2360,7 @@ cudaError_t tree_evaluate(GravityWorkspace& ws, const GravityParams& prm, size_t
     PB_PASS(ws.sticky.ensure(16));
     PB_CUDA(cudaMemsetAsync(ws.sticky.p, 0, 16, st));
   }
-  PB_PASS(ws.key0.ensure(n * 8));
+  PB_PASS(ws.key0.ensure(n * 8 + 16));
   PB_PASS(ws.key1.ensure(n * 8));
   PB_PASS(ws.idx0.ensure(n * 4));
   PB_PASS(ws.idx1.ensure(n * 4));
@@ -2193,7 +2383,7 @@ cudaError_t tree_evaluate(GravityWorkspace& ws, const GravityParams& prm, size_t
   // members of a bin by comparing whole keys, so it sorts ALL bits at no extra cost - and a depth guess
   // that can no longer be wrong cannot make a chunk of the resident loop replay (one replay per ~150
   // steps of c3 while only the guessed bits were sorted: tools/steps_diag.py).
-  const int lo = (ws.sort_mode == 0 && ws.sort_lo > 0 && ws.sort_lo < key_bits) ? ws.sort_lo : 0;
+  const int lo = (!sh && ws.sort_mode == 0 && ws.sort_lo > 0 && ws.sort_lo < key_bits) ? ws.sort_lo : 0;
   ws.last_lo = lo;
   ws.unchecked_builds += 1;
   const unsigned nb = blocks_for(n, 256);
@@ -2201,26 +2391,31 @@ cudaError_t tree_evaluate(GravityWorkspace& ws, const GravityParams& prm, size_t
   const unsigned long long* extent = ws.extent_pre;
   ws.extent_pre = nullptr;  // (good for one build)
   if (!extent) {
-    PB_LAUNCH(ls, st, "extent_kernel", pb_launch_pdl(extent_kernel, dim3(min(nb, 148u * 8u)), dim3(256), 0, st, ws.pos64, n, ws.extent_bits.as<unsigned long long>()));
+    const unsigned nb_all = blocks_for(n_all, 256);
+    PB_LAUNCH(ls, st, "extent_kernel", pb_launch_pdl(extent_kernel, dim3(min(nb_all, 148u * 8u)), dim3(256), 0, st, ws.pos64, n_all, ws.extent_bits.as<unsigned long long>()));
     extent = ws.extent_bits.as<unsigned long long>();
   }
   ws.extent_cur = extent;
   SortBuffers sb;
-  PB_PASS(sort_prepare(ws, n, key_bits, lo, ws.sort_mode, st, sort_head, &sb));
+  PB_PASS(sort_prepare(ws, n, key_bits, lo, sh ? shard_sort_mode(n) : ws.sort_mode, st, sort_head, &sb));
+  if (sh && sb.mode == 0) {
+    set_error("sharded build: %zu bodies per rank exceed the bucket sort's capacity", n);
+    return cudaErrorInvalidValue;
+  }
   ws.last_mode = sb.mode;
   uint64_t* spl_out = nullptr;
-  PB_PASS(encode_and_sort<DIM>(ws, n, sb, max_shared_plus1 + 2, st, ls, &spl_out));
+  PB_PASS(encode_and_sort<DIM>(ws, n_all, sb, max_shared_plus1 + 2, st, ls, &spl_out, sh));
   // range-minimum tables over the sorted bodies' shared-level bytes (see NsvTables)
   const size_t n_pad = size_t(nb) * 256, nblocks = nb, b_pad = (nblocks + 255) / 256 * 256, nsuper = b_pad / 256;
   PB_PASS(ws.nsv1.ensure(n_pad + n_pad / 16));  // [a1 bytes][window minima]
   PB_PASS(ws.nsv2.ensure(9 * b_pad + nsuper));
   uint8_t* nsv3 = ws.nsv2.as<uint8_t>() + 9 * b_pad;
-  PB_LAUNCH(ls, st, "unit_kernel", pb_launch_pdl(unit_kernel<DIM>, dim3(min(nb, 148u * unsigned(UNIT_CTAS_PER_SM))), dim3(256), 0, st, ws.sorted_key, ws.spos64.as<double4>(), n, ws.ab.as<uchar2>(),
+  PB_LAUNCH(ls, st, "unit_kernel", pb_launch_pdl(unit_kernel<DIM>, dim3(min(nb, 148u * unsigned(UNIT_CTAS_PER_SM))), dim3(256), 0, st, ws.sorted_key, ws.spos64.as<double4>(), nref, ws.ab.as<uchar2>(),
                                        ws.tgt_flags.as<uint32_t>(), max_shared_plus1,
                                        lo > 0 ? (key_bits - lo) / DIM : TreeDim<DIM>::LM + 2,
-                                       ws.nsv1.as<uint8_t>(), n_pad, ws.nsv2.as<uint8_t>(), nb));
-  const ScanSide side{unsigned(nsuper), ws.nsv2.as<uint8_t>(), b_pad, nblocks, nsv3, ws.sorted_key, n, spl_out};
-  PB_PASS(exclusive_scan_with_side(ws.tgt_flags.as<uint32_t>(), ws.cell_start.as<uint32_t>(), n, scan_scratch, side, st, ls));
+                                       ws.nsv1.as<uint8_t>(), n_pad, ws.nsv2.as<uint8_t>()));
+  const ScanSide side{ws.nsv2.as<uint8_t>(), b_pad, nsv3, ws.sorted_key, spl_out};
+  PB_PASS(exclusive_scan_with_side(ws.tgt_flags.as<uint32_t>(), ws.cell_start.as<uint32_t>(), nref, n, scan_scratch, side, st, ls));
 
   // cell table capacity: grows when a previous evaluation reported more cells
   size_t cap = ws.n_cells ? ws.n_cells + ws.n_cells / 4 + 1024 : n * 5 / 2 + 1024;
@@ -2244,7 +2439,8 @@ cudaError_t tree_evaluate(GravityWorkspace& ws, const GravityParams& prm, size_t
   const unsigned nb128 = blocks_for(n, 128);
   const NsvTables tv{ws.nsv1.as<uint8_t>(), ws.nsv1.as<uint8_t>() + n_pad, n_pad, ws.nsv2.as<uint8_t>(), b_pad, nsv3, n, nblocks, nsuper};
   static const bool cells_chain = std::getenv("PB200_CELLS") && std::string(std::getenv("PB200_CELLS")) == "chain";
-  if (cells_chain) {
+  const TopSlots slots = sh ? sh->slots : TopSlots{nullptr, 0};
+  if (cells_chain && !sh) {
     PB_LAUNCH(ls, st, "cells_kernel_chain",
               cells_kernel_chain<DIM><<<nb, 256, 0, st>>>(ws.sorted_key, ws.spos64.as<double4>(), ws.perm,
                                                           ws.ab.as<uchar2>(), ws.cell_start.as<uint32_t>(), n,
@@ -2253,13 +2449,13 @@ cudaError_t tree_evaluate(GravityWorkspace& ws, const GravityParams& prm, size_t
   } else {
       PB_LAUNCH(ls, st, "cells_kernel",
                 (pb_launch_pdl(cells_kernel<DIM, 4>, dim3(nb), dim3(256), 0, st, ws.sorted_key, ws.spos64.as<double4>(), ws.perm,
-                                                          ws.ab.as<uchar2>(), ws.cell_start.as<uint32_t>(), n,
+                                                          ws.ab.as<uchar2>(), ws.cell_start.as<uint32_t>(), nref,
                                                           ws.extent_cur, max_shared_plus1,
-                                                          ws.sticky.as<unsigned>(), tv, cells)));
+                                                          ws.sticky.as<unsigned>(), tv, cells, slots)));
   }
   static const bool com_old = std::getenv("PB200_COM") && std::string(std::getenv("PB200_COM")) == "old";
   ws.parents_filled = false;
-  if (com_old) {
+  if (com_old && !sh) {
     PB_LAUNCH(ls, st, "parent_kernel",
               parent_kernel<<<blocks_for(cap, 256), 256, 0, st>>>(ws.cell_start.as<uint32_t>(), n, cells));
     ws.parents_filled = true;
@@ -2271,13 +2467,26 @@ cudaError_t tree_evaluate(GravityWorkspace& ws, const GravityParams& prm, size_t
     const uint32_t sub_cap = ((kid_blocks + READY_LISTS - 1) / READY_LISTS) * 256u;
     PB_PASS(ws.c_ready.ensure(size_t(READY_LISTS) * sub_cap * 4));
     PB_LAUNCH(ls, st, "kids_kernel",
-              pb_launch_pdl(kids_kernel<DIM>, dim3(kid_blocks), dim3(256), 0, st, ws.cell_start.as<uint32_t>(), n, cells,
+              pb_launch_pdl(kids_kernel<DIM>, dim3(kid_blocks), dim3(256), 0, st, ws.cell_start.as<uint32_t>(), nref, cells,
                                                            ws.c_kids.as<uint32_t>(), ws.c_ready.as<uint32_t>(), n_ready, sub_cap));
     PB_LAUNCH(ls, st, "climb_kernel",
-              pb_launch_pdl(climb_kernel<DIM>, dim3(148 * 4), dim3(128), 0, st, ws.cell_start.as<uint32_t>(), n, cells,
+              pb_launch_pdl(climb_kernel<DIM>, dim3(148 * 4), dim3(128), 0, st, ws.cell_start.as<uint32_t>(), nref, cells,
                                                          ws.c_kids.as<uint32_t>(), ws.c_ready.as<uint32_t>(), n_ready, sub_cap));
   }
+  out->cells = cells;
+  out->nref = nref;
+  out->n_cap = n;
+  return cudaGetLastError();
+}
 
+template <int DIM>
+cudaError_t tree_evaluate(GravityWorkspace& ws, const GravityParams& prm, size_t t0, size_t t1,
+                          float easing, float tiny, cudaStream_t st, LaunchStats& ls) {
+  const size_t n = ws.n;
+  BuildOut bo;
+  PB_PASS(tree_build<DIM>(ws, nullptr, st, ls, &bo));
+  const CellArrays& cells = bo.cells;
+  const unsigned nb = blocks_for(n, 256);
   const uint32_t* list = nullptr;
   const size_t n_targets = t1 - t0;
   if (n_targets != n) {
@@ -2300,13 +2509,25 @@ cudaError_t tree_evaluate(GravityWorkspace& ws, const GravityParams& prm, size_t
 cudaError_t direct_evaluate(GravityWorkspace& ws, size_t t0, size_t t1, float easing, float tiny,
                             cudaStream_t st, LaunchStats& ls) {
   const size_t n = ws.n, n_targets = t1 - t0;
+  const char* small_env = std::getenv("PB200_DIRECT_SMALL");  // =0: the packed kernel at every size (read per call: tests flip it)
+  const bool small_off = small_env && std::atoi(small_env) == 0;
+  if (n <= DIRECT_SMALL_N && !small_off) {
+    if (n_targets)
+      PB_LAUNCH(ls, st, "direct_small_kernel",
+                direct_small_kernel<<<blocks_for(n_targets, DIRECT_SMALL_THREADS), DIRECT_SMALL_THREADS, 0, st>>>(
+                    ws.pos64, ws.fixed, n, t0, n_targets, easing, tiny, ws.acc.as<float4>()));
+    return cudaGetLastError();
+  }
   const size_t n_pad = (n + DIRECT_TILE - 1) / DIRECT_TILE * DIRECT_TILE;
   PB_PASS(ws.src4.ensure(6 * n_pad * sizeof(float)));
-  PB_PASS(ws.counters.ensure(16));
+  PB_PASS(ws.counters.ensure(16 + 48));
   unsigned* meta = ws.counters.as<unsigned>();
-  PB_CUDA(cudaMemsetAsync(meta, 0, 16, st));
+  unsigned long long* box = reinterpret_cast<unsigned long long*>(meta + 4);  // [min x,y,z][max x,y,z]
+  PB_CUDA(cudaMemsetAsync(meta, 0, 16 + 48, st));
+  PB_CUDA(cudaMemsetAsync(box, 0xff, 24, st));
+  PB_LAUNCH(ls, st, "bbox_kernel", bbox_kernel<<<min(blocks_for(n, 256), 148u * 8u), 256, 0, st>>>(ws.pos64, n, box));
   PB_LAUNCH(ls, st, "to_soa_kernel",
-            to_soa_kernel<<<blocks_for(n_pad, 256), 256, 0, st>>>(ws.pos64, n, n_pad, easing, ws.src4.as<float>(), meta));
+            to_soa_kernel<<<blocks_for(n_pad, 256), 256, 0, st>>>(ws.pos64, n, n_pad, easing, box, ws.src4.as<float>(), meta));
   if (!n_targets) return cudaGetLastError();
   // 4 targets per thread when that still fills the chip, else 1; split the sources across
   // blockIdx.y until there are >= 2 CTAs per SM (partials summed in a fixed order afterwards)

@@ -123,6 +123,52 @@ def test_direct_sum_matches_reference(case):
     assert el.stats()["interactions"] == int(free.sum()) * len(s)
 
 
+@pytest.mark.parametrize("packed", [False, True])
+def test_direct_sum_far_from_the_origin(packed, monkeypatch):
+    """A system offset from the origin (`cube centre=[1000,-2000,500]`): positions are differenced in fp64
+    (small systems) or taken relative to the bounding-box centre in fp64 before the fp32 copy (packed kernel),
+    so the offset costs no accuracy.  (Rounding the raw coordinates to fp32 first loses ~|x| 2^-24 = 1e-4 of
+    every difference here: p99 error ~ 1e-2.)"""
+    monkeypatch.setenv("PB200_DIRECT_SMALL", "0" if packed else "1")
+    s = gen.cube(3000, seed=5, centre=(1000.0, -2000.0, 500.0))
+    acc = api.TransformElement("simple_astro", e=0.5).transform(s)
+    ref = ob.transform("simple_astro", s, e=0.5)
+    r = assert_acc_parity(acc, ref)
+    assert r.max() < 1e-4
+    far = gen.cube(3000, seed=5)                      # the same system at the origin: same accuracy
+    r0 = rel_err(api.TransformElement("simple_astro", e=0.5).transform(far), ob.transform("simple_astro", far, e=0.5))
+    assert np.median(r) < 4 * np.median(r0) + 1e-7
+
+
+def test_direct_sum_far_from_the_origin_packed_kernel_at_size():
+    """The packed FP32 kernel at a size it is selected for by itself (n > 32768), offset system, sampled."""
+    s = gen.cube(40_000, seed=6, centre=(-3000.0, 100.0, 7000.0))
+    acc = api.TransformElement("astro2", theta=0.0, e=0.5).transform(s)
+    pick = np.arange(0, len(s), 157)
+    ref = accelerations(len(s))
+    for i in pick:
+        ob.direct_range(s, 0.5, int(i), int(i) + 1, acc=ref)
+    r = assert_acc_parity(acc[pick], ref[pick])
+    assert r.max() < 1e-4
+
+
+def test_direct_sum_close_pairs_keep_their_direction():
+    """Pairs separated by 1e-7 of the system size (below fp32 resolution of the coordinates): the small-system
+    kernel differences in fp64, so each twin's acceleration - dominated by its partner - stays accurate."""
+    s = gen.cube(2000, seed=9)
+    rng = np.random.default_rng(1)
+    d = rng.normal(size=(40, 3))
+    d *= 1e-7 / np.linalg.norm(d, axis=1)[:, None]
+    for k, axis in enumerate("xyz"):
+        s[axis][40:80] = s[axis][:40] + d[:, k]
+    s["mass"][:80] = 50.0                               # partner's pull ~ m / e dominates the rest (~ 1)
+    acc = api.TransformElement("simple_astro", e=1e-3).transform(s)
+    ref = ob.transform("simple_astro", s, e=1e-3)
+    r = rel_err(acc, ref)
+    assert r[:80].max() < 5e-6, r[:80].max()      # (a lost direction would be an error of order 1)
+    assert_acc_parity(acc, ref)
+
+
 @pytest.mark.parametrize("name", ["astro2", "astro"])
 def test_nonpositive_theta_is_direct_sum(name):
     s = gen.readme_pipeline(3000, seed=12)
