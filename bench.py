@@ -223,24 +223,19 @@ def run_ours(args, w):
     hbm_peak, peak_kind, peaks = measured_peaks()
 
     # ---------------- device-resident steps (value) ----------------
-    sim = api.Sim(w["element"], theta=w["theta"], e=w["e"], dt=w["dt"], rank=rank, world=world)
+    # one GPU: pb200_sim_*; several: pb200_msim_* (csrc/multi.cu) - one rank per process here, the NCCL id made
+    # by rank 0 and handed round with a torch.distributed broadcast (plumbing); every collective of the step is
+    # issued by the library itself on its own stream
     stream = torch.cuda.Stream(device=local_rank)
-    sim.set_stream(stream.cuda_stream)
+    if world == 1:
+        sim = api.Sim(w["element"], theta=w["theta"], e=w["e"], dt=w["dt"])
+        sim.set_stream(stream.cuda_stream)
+    else:
+        sim = make_msim(api, torch, dist, w, rank, world, local_rank)
     sim.upload(state)
-    gathered = None
-    if world > 1:
-        from physim_b200.sharding import exchange
-        ptr, total, off, sl = sim.gather_buffer()
-        gathered = cuda_tensor_view(ptr, total)
 
     def steps(k):
-        if world == 1:
-            sim.run(k)  # k steps enqueued back to back; one host sync at the end
-        else:
-            def xchg():
-                with torch.cuda.stream(stream):
-                    exchange(gathered, n, rank, world)
-            sim.run_sharded(k, xchg)
+        sim.run(k)  # k steps enqueued back to back; one host sync at the end
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -251,24 +246,28 @@ def run_ours(args, w):
     if dist:
         dist.barrier()
         torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_region0 = time.perf_counter()
-    e0.record(stream)
-    steps(args.steps)
-    e1.record(stream)
-    torch.cuda.synchronize()
+    if world == 1:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        steps(args.steps)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+    else:
+        ms = sim.run_timed(args.steps)  # CUDA events on the library's stream of this rank; max over ranks below
+        torch.cuda.synchronize()
     sampler.window = (t_region0, time.perf_counter())
     if dist:
         dist.barrier()
         torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
     if dist:
         t = torch.tensor([ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     st = sim.stats()
-    launches = st["kernel_launches"] - launches0 - 1  # the stats call itself counts interactions
+    launches = st["kernel_launches"] - launches0 - (1 if world == 1 else 0)  # the stats call itself counts interactions
     value = n * args.steps / (ms * 1e-3)
 
     # ---------------- per-kernel device times (roofline) ----------------
@@ -311,8 +310,10 @@ def run_ours(args, w):
         "config": {"workload": args.workload, "description": w["desc"], "n_bodies": n,
                    "element": w["element"], "theta": w["theta"], "e": w["e"], "dt": w["dt"],
                    "n_cells": st["n_cells"], "interactions_per_step": st["interactions"],
-                   "parallelism": "replicated tree build, targets + verlet sharded by body index, "
-                                  "NCCL all-gather of fp64 {x,y,z,m}" if world > 1 else "single GPU",
+                   "parallelism": ("tree build + walk sharded by Morton key range (cuts at level-K cells, rebalanced "
+                                   "every step), level-K cell records and accelerations all-gathered in-library "
+                                   "(NCCL), remote cells read over NVLink peer memory, integrator state replicated")
+                   if world > 1 else "single GPU",
                    "l2": "no flush: per-step working set (~0.4 GB) exceeds the 126 MB L2; steps run "
                          "back to back as in the simulation loop",
                    "precision": "keys/tree/acceptance/integrator fp64, force law fp32"},
@@ -329,17 +330,20 @@ def run_ours(args, w):
         line["direct_sum"] = measure_direct(api, args, hbm_peak)
         line["cpu_baseline"] = measure_cpu(state, w)
         line["integrators"] = measure_integrators(api, state, w)
+    if world > 1:
+        bodies, cells = sim.rank_counts()
+        line["sharding"] = {"sharded_steps": st.get("sharded_steps"), "replicated_steps": st.get("replicated_steps"),
+                            "replays": st["replays"],
+                            "bodies_per_rank": None if bodies is None else [int(b) for b in bodies],
+                            "cells_per_rank": None if cells is None else [int(c) for c in cells]}
     if world > 1 and not args.skip_extras:
-        ds = measure_direct_multi(api, rank, world, local_rank, dist, torch, stream)
+        ds = measure_direct_multi(api, rank, world, local_rank, dist, torch)
         if rank == 0:
             line["direct_sum"] = ds
     if rank == 0 and world > 1:
         line["e2e"] = {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0,
                        "d2h_bytes_per_step": 0,
                        "note": "multi-rank run: state stays in HBM; the host-boundary number is the N=1 line's"}
-        line["scaling_note"] = ("the 1M-body Barnes-Hut step is latency-bound on one GPU (~0.5 ms) and its tree "
-                                "build is replicated, so it does not speed up with more GPUs; the path that shards "
-                                "is the all-pairs evaluation reported under direct_sum")
     if rank == 0:
         print(json.dumps(line))
     if dist:
@@ -414,54 +418,58 @@ def measure_direct(api, args, hbm_peak):
                          "frac_of_probe": tf / fp32_probe if fp32_probe > 0 else None}}
 
 
-def measure_direct_multi(api, rank, world, local_rank, dist, torch, stream):
-    """BASELINE configs[3] sharded by target: rank r owns targets [r N/G, (r+1) N/G) of 2^24 bodies and
-    evaluates them against all sources.  Timed on a 2-wave sample of each rank's slice (max over
-    ranks), plus the one collective a full step needs: the in-place all-gather of the fp64 {x,y,z,m}
-    slices (512 MB in total)."""
+def make_msim(api, torch, dist, w, rank, world, local_rank):
+    """pb200_msim_* handle of this process's rank; the communicator id travels by a torch.distributed broadcast."""
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt = torch.from_numpy(api.comm_unique_id().copy()).cuda()
+    dist.broadcast(idt, 0)
+    return api.MultiSim(w["element"], theta=w["theta"], e=w["e"], dt=w["dt"], world=world, rank=rank,
+                        device=local_rank, comm_id=idt.cpu().numpy())
+
+
+def measure_direct_multi(api, rank, world, local_rank, dist, torch):
+    """BASELINE configs[3]: 2^24 bodies, astro2 theta=0 (all pairs), targets sharded by body index over the
+    ranks, the accelerations all-gathered inside the step (csrc/multi.cu step_direct).  With 8 ranks ONE FULL
+    STEP is run and timed (every target x every source, gather and verlet included, ~15 s); with fewer ranks a
+    1/8 problem slice would take minutes, so 2^21 targets per rank are timed instead and the step extrapolated."""
     from physim_b200 import generators as gen
-    from physim_b200.sharding import exchange, owned_range
     n = 1 << 24
+    full = world >= 8
     state = gen.cube(n, seed=1)
-    sim = api.Sim("astro2", theta=0.0, e=0.5, dt=1e-6, rank=rank, world=world)
-    sim.set_stream(stream.cuda_stream)
-    sim.upload(state)
-    t0, t1 = owned_range(n, rank, world)
-    n_t = min(2 * 296 * 1024, t1 - t0)
-    sim.set_targets(t0, t0 + n_t)
-    sim.run_timed(1)
-    torch.cuda.synchronize()
-    dist.barrier()
-    steps = 2
-    ms = sim.run_timed(steps)
-    sim.set_targets(t0, t1)
-    ptr, total, off, sl = sim.gather_buffer()
-    gathered = cuda_tensor_view(ptr, total)
-    with torch.cuda.stream(stream):
-        exchange(gathered, n, rank, world)          # warm-up
+    w = dict(element="astro2", theta=0.0, e=0.5, dt=1e-6)
+    if full:
+        ms_ = make_msim(api, torch, dist, w, rank, world, local_rank)
+        ms_.upload(state)
+        t_ms = ms_.run_timed(1)        # first step (first-step verlet formula)
+        t_ms = ms_.run_timed(1)
+        t = torch.tensor([t_ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_ms = float(t.item())
+        rate = n * n / (t_ms * 1e-3)
+        sample = f"one full step: {n} targets x {n} sources over {world} ranks, all-gather of accelerations and verlet inside"
+        ms_.close()
+    else:
+        sim = api.Sim("astro2", theta=0.0, e=0.5, dt=1e-6, device=local_rank)
+        sim.upload(state)
+        per = n // world
+        n_t = min(2 * 296 * 1024, per)
+        sim.set_targets(rank * per, rank * per + n_t)
+        sim.run_timed(1)
         torch.cuda.synchronize()
         dist.barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(5):
-            exchange(gathered, n, rank, world)
-        e1.record(stream)
-    torch.cuda.synchronize()
-    ag_ms = e0.elapsed_time(e1) / 5
-    t = torch.tensor([ms, ag_ms], device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ag_ms = float(t[0].item()), float(t[1].item())
-    rate = world * n_t * n * steps / (ms * 1e-3)
+        t_ms = sim.run_timed(2) / 2
+        t = torch.tensor([t_ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_ms = float(t.item())
+        rate = world * n_t * n / (t_ms * 1e-3)
+        sample = f"per rank: {n_t} of its {per} targets x all {n} sources, 2 evaluations; max over ranks (extrapolated)"
     props = torch.cuda.get_device_properties(local_rank)
     nominal = world * props.multi_processor_count * 128 * 2 * 1.965e9 / 1e12
     tf = rate * FLOP_PER_INTERACTION / 1e12
-    compute_s = (n / world) * n / (rate / world)
-    return {"workload": "cube n=16777216 ! astro2 theta=0 e=0.5 (all pairs), targets sharded over %d GPUs" % world,
-            "sample": f"per rank: {n_t} of its {t1 - t0} targets x all {n} sources, {steps} evaluations; max over ranks",
-            "interactions_per_s": rate, "ms_per_evaluation": ms / steps,
-            "allgather_ms": ag_ms, "allgather_bytes": n * 32,
-            "allgather_gbs_per_gpu": n * 32 * (world - 1) / world / (ag_ms * 1e-3) / 1e9,
-            "full_step_s_extrapolated": compute_s + ag_ms * 1e-3,
+    return {"workload": "cube n=16777216 ! astro2 theta=0 e=0.5 ! verlet (all pairs), targets sharded over %d GPUs" % world,
+            "sample": sample, "full_step_measured": full, "interactions_per_s": rate,
+            "step_s": n * n / rate,
             "roofline": {"bound": "fp32", "achieved": tf, "unit": "TFLOP/s", "flop_per_interaction": 19,
                          "peak": nominal, "peak_source": f"{world} x {props.multi_processor_count} SMs x 128 x 2 x 1.965 GHz",
                          "frac": tf / nominal}}

@@ -276,6 +276,36 @@ int pb200_sim_set_stream(void *sim, void *stream);
 /* CUDA stream (cudaStream_t) the handle launches on, for event timing by the caller. */
 void *pb200_sim_stream(void *sim);
 
+/* --- the same simulation on several GPUs of one box (multi.cu) --------------
+ * One rank per GPU; the ranks of a run live in ONE process (n_local == world: the plugin's case, physim is
+ * one process driving G GPUs) or in one process each (n_local == 1: bench.py under torchrun).  Barnes-Hut:
+ * tree build and walk sharded by Morton key range, level-K cell records and accelerations exchanged with
+ * ncclAllGather (NCCL is dlopen'ed at the first multi-rank use), remote cells read through NVLink peer
+ * memory; direct sum: targets sharded by body index.  The integrator state is replicated, so any rank
+ * can hand the whole state back.  Replaces the single simulation thread of pipeline.rs:134-192 on the
+ * transformers.rs:123-160 / verlet.rs:52-82 path; results are bit-identical to the single-GPU handle's. */
+/* 128 bytes identifying one communicator; call on one process and hand the bytes to every other one
+ * (processes: any channel, e.g. a torch.distributed broadcast).  Not needed when n_local == world. */
+int pb200_comm_unique_id(uint8_t *out128);
+/* local_ranks[i] runs on CUDA device devices[i] (i < n_local).  Collective over all `world` ranks when world > 1. */
+void *pb200_msim_create(int kind, double theta, double e, double dt, int world, int n_local,
+                        const int *local_ranks, const int *devices, const uint8_t *nccl_id128);
+void pb200_msim_destroy(void *msim);
+/* every process passes the whole state (all n bodies) */
+int pb200_msim_upload(void *msim, const Entity *state, size_t n);
+int pb200_msim_run(void *msim, size_t steps);
+/* *ms = device time of the steps: CUDA events on every local rank's stream, the maximum over them */
+int pb200_msim_run_timed(void *msim, size_t steps, float *ms);
+int pb200_msim_download(void *msim, Entity *state, size_t n);
+int pb200_msim_last_accelerations(void *msim, Acceleration *acc, size_t n);
+int pb200_msim_stats(void *msim, Pb200Stats *out, uint64_t *sharded_steps, uint64_t *replicated_steps);
+/* bodies / cells per rank at the last sharded step; returns world, or -1 when no sharded step has run */
+int pb200_msim_rank_counts(void *msim, uint32_t *bodies, uint32_t *cells);
+/* 0: the local ranks' copies of the replicated state are bit-identical, 1: they differ, -1: error */
+int pb200_msim_replicas_identical(void *msim);
+int pb200_msim_profile(void *msim, int enable);
+int pb200_msim_profile_report(void *msim, char *buf, size_t cap);
+
 /* --- csvsink (utilities/src/csvsink.rs:44-80) ---------------------------
  * The headless renderer of a CPU run: one line per printed state, "x,y,z," per entity, numbers in
  * Rust's `{}` format for f64 (shortest round-trip digits, positional notation).  The first state

@@ -145,6 +145,20 @@ def lib():
     L.pb200_csv_format_f64.restype = sz
     L.pb200_csv_format_f64.argtypes = [dbl, C.c_char_p, sz]
     L.pb200_sim_run_csvsink.argtypes = [vp, sz, vp]
+    L.pb200_comm_unique_id.argtypes = [vp]
+    L.pb200_msim_create.restype = vp
+    L.pb200_msim_create.argtypes = [i32, dbl, dbl, dbl, i32, i32, vp, vp, vp]
+    L.pb200_msim_destroy.argtypes = [vp]
+    L.pb200_msim_upload.argtypes = [vp, vp, sz]
+    L.pb200_msim_run.argtypes = [vp, sz]
+    L.pb200_msim_run_timed.argtypes = [vp, sz, C.POINTER(C.c_float)]
+    L.pb200_msim_download.argtypes = [vp, vp, sz]
+    L.pb200_msim_last_accelerations.argtypes = [vp, vp, sz]
+    L.pb200_msim_stats.argtypes = [vp, C.POINTER(Pb200Stats), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.pb200_msim_rank_counts.argtypes = [vp, vp, vp]
+    L.pb200_msim_replicas_identical.argtypes = [vp]
+    L.pb200_msim_profile.argtypes = [vp, i32]
+    L.pb200_msim_profile_report.argtypes = [vp, C.c_char_p, sz]
     _lib = L
     return L
 
@@ -436,6 +450,104 @@ class Sim:
             if getattr(self, "_s", None):
                 lib().pb200_sim_destroy(self._s)
                 self._s = None
+        except Exception:
+            pass
+
+
+def comm_unique_id():
+    """128 bytes naming a communicator (NCCL unique id); make it on one process, give it to all."""
+    buf = np.zeros(128, dtype=np.uint8)
+    if lib().pb200_comm_unique_id(_ptr(buf)) != 0:
+        raise Pb200Error(last_error())
+    return buf
+
+
+class MultiSim:
+    """The device-resident loop on several GPUs of one box (csrc/multi.cu): one rank per GPU.
+
+    MultiSim(name, ..., devices=[0, 1])                    every rank in this process (the plugin's shape)
+    MultiSim(name, ..., world=W, rank=r, device=d, comm_id=id)   one rank per process (torchrun)"""
+
+    def __init__(self, name, theta=float("nan"), e=float("nan"), dt=1e-6, devices=None, world=None, rank=None,
+                 device=None, comm_id=None):
+        if devices is not None:
+            ranks = np.arange(len(devices), dtype=np.int32)
+            devs = np.asarray(devices, dtype=np.int32)
+            world = len(devices)
+            idp = None
+        else:
+            ranks = np.asarray([rank], dtype=np.int32)
+            devs = np.asarray([device], dtype=np.int32)
+            self._id = None if comm_id is None else np.ascontiguousarray(comm_id, dtype=np.uint8)
+            idp = _ptr(self._id)
+        self.world = int(world)
+        self._m = lib().pb200_msim_create(KINDS[name], float(theta), float(e), float(dt), self.world, len(ranks),
+                                          _ptr(ranks), _ptr(devs), idp)
+        if not self._m:
+            raise Pb200Error(last_error())
+        self.n = 0
+
+    def upload(self, state):
+        state = _state(state)
+        self.n = len(state)
+        if lib().pb200_msim_upload(self._m, _ptr(state), self.n) != 0:
+            raise Pb200Error(last_error())
+
+    def run(self, steps):
+        if lib().pb200_msim_run(self._m, int(steps)) != 0:
+            raise Pb200Error(last_error())
+
+    def run_timed(self, steps):
+        ms = C.c_float()
+        if lib().pb200_msim_run_timed(self._m, int(steps), C.byref(ms)) != 0:
+            raise Pb200Error(last_error())
+        return ms.value
+
+    def download(self, state):
+        state = _state(state)
+        if lib().pb200_msim_download(self._m, _ptr(state), len(state)) != 0:
+            raise Pb200Error(last_error())
+        return state
+
+    def last_accelerations(self):
+        acc = np.zeros(self.n, dtype=ACCELERATION)
+        if lib().pb200_msim_last_accelerations(self._m, _ptr(acc), self.n) != 0:
+            raise Pb200Error(last_error())
+        return acc
+
+    def stats(self):
+        st, a, b = Pb200Stats(), C.c_uint64(), C.c_uint64()
+        if lib().pb200_msim_stats(self._m, C.byref(st), C.byref(a), C.byref(b)) != 0:
+            raise Pb200Error(last_error())
+        d = st.as_dict()
+        d["sharded_steps"], d["replicated_steps"] = a.value, b.value
+        return d
+
+    def rank_counts(self):
+        bodies, cells = np.zeros(8, np.uint32), np.zeros(8, np.uint32)
+        w = lib().pb200_msim_rank_counts(self._m, _ptr(bodies), _ptr(cells))
+        return (bodies[:w].copy(), cells[:w].copy()) if w > 0 else (None, None)
+
+    def replicas_identical(self):
+        return lib().pb200_msim_replicas_identical(self._m) == 0
+
+    def profile(self, enable=True):
+        lib().pb200_msim_profile(self._m, 1 if enable else 0)
+
+    def profile_report(self):
+        buf = C.create_string_buffer(1 << 16)
+        if lib().pb200_msim_profile_report(self._m, buf, len(buf)) != 0:
+            raise Pb200Error("profile report failed")
+        return json.loads(buf.value.decode())
+
+    def close(self):
+        if getattr(self, "_m", None):
+            lib().pb200_msim_destroy(self._m)
+            self._m = None
+
+    def __del__(self):
+        try:
+            self.close()
         except Exception:
             pass
 

@@ -96,6 +96,29 @@ struct PinnedBuf {
   }
 };
 
+// ---- sharded Barnes-Hut: what one rank keeps besides its GravityWorkspace (see gravity.cu, "Sharded Barnes-Hut") ----
+struct ShardPeers {  // every rank's cell table as this device sees it (own rank: local pointers)
+  const void* centre_ext[8];
+  const void* com[8];
+  const void* skip[8];
+  uint32_t capacity;
+};
+struct ShardState {
+  int rank = 0, world = 1;
+  bool planned = false;   // cuts and splitters for a sharded build exist (left by gravity_shard_plan / the last sharded step)
+  size_t n_cap = 0;       // capacity of the per-rank arrays in bodies (the same on every rank)
+  DevBuf cuts;            // u64[world + 1]: key cuts of the NEXT build
+  DevBuf n_local;         // u32: bodies in this rank's range (left by the sort of the current build)
+  DevBuf slot_cell;       // u32[level-K prefixes]
+  DevBuf top_all;         // [world] x (prefixes + 1) 48-byte records: the all-gather buffer of step 2
+  DevBuf top_ce, top_com, top_info, top_meta;  // dense top tree (levels 0..K) + per-rank counts
+  DevBuf xacc;            // [world] x { float4 acc[n_cap], u32 perm[n_cap] }: the all-gather buffer of step 5
+  ShardPeers peers;
+  size_t top_block_bytes() const;   // bytes one rank contributes to top_all
+  size_t xacc_block_bytes() const { return n_cap * 20; }
+  void release();
+};
+
 // ---- device workspace of one gravity evaluation ------------------------------------------------
 // Layout in HBM (N bodies, C cells ≈ 1.5 N):
 //   pos64   double4[N]  {x,y,z,m}, original order            32 B/body   (input of every kernel)
@@ -145,6 +168,7 @@ struct GravityWorkspace {
   // where the sorted keys / permutation ended up after the last sort
   const uint64_t* sorted_key = nullptr;
   const uint32_t* perm = nullptr;
+  ShardState shard;
   void release_all();
 };
 
@@ -273,6 +297,18 @@ inline cudaError_t pb_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block
 // small; without it the caller must poll gravity_cell_total() before trusting the result.
 cudaError_t gravity_evaluate(GravityWorkspace& ws, const GravityParams& prm, size_t t0, size_t t1,
                              cudaStream_t stream, LaunchStats& ls, bool host_check = true);
+// Sharded Barnes-Hut, one call per phase; the caller runs the two collectives in between on the same stream:
+//   gravity_shard_plan    after a full build on every rank (gravity_evaluate over all bodies): first cuts + splitters
+//   gravity_shard_build   tree of this rank's key range + its level-K records into block `rank` of shard.top_all
+//                         -> all-gather shard.top_all (top_block_bytes() per rank, in place)
+//   gravity_shard_walk    top tree, walk of this rank's bodies -> accelerations (sorted order) + permutation in
+//                         block `rank` of shard.xacc           -> all-gather shard.xacc (xacc_block_bytes() per rank)
+// shard.peers must hold every rank's c_centre_ext / c_com / c_skip (peer-mapped) before gravity_shard_walk.
+cudaError_t gravity_shard_setup(GravityWorkspace& ws, int kind, int rank, int world, size_t n);
+bool gravity_shard_fits(const GravityWorkspace& ws);  // the per-rank capacity is within what the sharded build's sort takes
+cudaError_t gravity_shard_plan(GravityWorkspace& ws, cudaStream_t stream, LaunchStats& ls);
+cudaError_t gravity_shard_build(GravityWorkspace& ws, const GravityParams& prm, cudaStream_t stream, LaunchStats& ls);
+cudaError_t gravity_shard_walk(GravityWorkspace& ws, const GravityParams& prm, cudaStream_t stream, LaunchStats& ls);
 // Host-side verdict on the last tree build (one small D2H + stream sync).  Also feeds the next
 // evaluation: cell-table capacity follows the observed total, the sort drops the key bits below
 // the observed tree depth (+2 levels) and is re-validated every time.
@@ -285,7 +321,8 @@ struct TreeCheck {
   bool sort_error = false;  // look-back spin limit hit (never expected)
   uint32_t max_bucket = 0;  // bodies in the fullest bin of the keys' top 8 bits
   bool bucket_overflow = false;  // a bucket-local sort met a bucket larger than its shared-memory tile
-  bool ok() const { return !overflow && !sort_short && !sort_error && !bucket_overflow; }
+  bool shard_overflow = false;   // sharded build: a rank's key range held more bodies than its arrays
+  bool ok() const { return !overflow && !sort_short && !sort_error && !bucket_overflow && !shard_overflow; }
 };
 cudaError_t gravity_check(GravityWorkspace& ws, cudaStream_t stream, TreeCheck* out);
 cudaError_t gravity_cell_total(GravityWorkspace& ws, cudaStream_t stream, uint32_t* total);
@@ -311,6 +348,12 @@ cudaError_t gravity_count_interactions(GravityWorkspace& ws, cudaStream_t stream
 cudaError_t verlet_update_lean(const double4* cur, double4* prev_inout, const float4* acc32, size_t n, double dt,
                                unsigned long long* extent_out, unsigned long long* extent_zero,
                                unsigned long long* extent_last, cudaStream_t st, LaunchStats& ls);
+// the same step on every rank of a sharded run: body perm[r][j] takes acc[r][j] for j < n_locals[r] (the gathered
+// blocks of ShardState::xacc, n_cap records each)
+cudaError_t verlet_update_lean_sharded(const double4* cur, double4* prev_inout, const void* xacc, size_t n_cap,
+                                       int world, const uint32_t* n_locals, double dt, unsigned long long* extent_out,
+                                       unsigned long long* extent_zero, unsigned long long* extent_last,
+                                       cudaStream_t st, LaunchStats& ls);
 cudaError_t verlet_velocity(const double4* cur, const double4* prev, double4* vel, size_t n, double dt,
                             cudaStream_t st, LaunchStats& ls);
 cudaError_t verlet_update(double4* cur, double4* prev, double4* vel, const float4* acc32,

@@ -511,7 +511,10 @@ __global__ void __launch_bounds__(NT, 1024 / NT) sort_local_kernel(
       seg[3] = ex + c;
       if (blockIdx.x == 0) {
         *n_out = min(ex + c, n_cap);  // (the later kernels never index past the capacity)
-        if (ex + c > n_cap) *bad = 1u;   // this rank's key range holds more bodies than its arrays: re-planned by the host
+        if (ex + c > n_cap) {  // this rank's key range holds more bodies than its arrays: re-planned by the host
+          *bad = 1u;
+          stat_max[1] = 1u;    // sticky word 4
+        }
       }
     }
     __syncthreads();
@@ -576,6 +579,12 @@ __global__ void __launch_bounds__(NT, 1024 / NT) sort_local_kernel(
   }
   if (seg[2] > LOCAL_BIN_LIMIT) {  // too many bodies agree on the bin bits: leave it to the global sort
     if (tid == 0) {
+#ifdef PB200_DEBUG_SKEW
+      unsigned bmaxcnt = 0, bwhere = 0;
+      printf("[skew] bucket %u cnt %u maxbin %u kbase %llx ktop %llx span_bits %d bshift %d first %llx last %llx\n", blockIdx.x, cnt, seg[2],
+             (unsigned long long)kbase, (unsigned long long)ktop, span_bits, bshift, (unsigned long long)gk[0], (unsigned long long)gk[cnt - 1]);
+      (void)bmaxcnt; (void)bwhere;
+#endif
       *bad = 1u;
       atomicMax(stat_max, LOCAL_SKEWED);
     }
@@ -965,8 +974,43 @@ struct CellArrays {
   double4* centre_ext;  // {cx, cy, cz, half-width}
   double4* com;         // {X, Y, Z, M}
   uint32_t capacity;
-  uint32_t small;        // cells with <= this many bodies are summed directly in cells_kernel
+  uint32_t small;        // cells with <= this many bodies are summed directly in cells_kernel ...
   const unsigned* bad;   // != 0: the keys are not fully ordered (truncated sort too short): skip the build
+  uint32_t top_level;    // ... unless they lie above this level: those are always summed from their children
+};
+
+// Key levels [0, TOP_LEVEL) form the "top tree": 4^6 = 8^4 = 4096 level-K prefixes.  A sharded build cuts the
+// key space between ranks at level-K prefixes, every rank builds the cells at levels >= K of its own range,
+// and the cells above are recomputed on every rank from the level-K cells' sums (top_build_kernel).  For that
+// to give the bits of the single-GPU build, a cell above level K must be summed the same way in both: always
+// from its children in ascending digit order (never from its bodies, however few it has), with ComSum below.
+template <int DIM>
+struct TopTree {
+  static constexpr int K = (DIM == 3) ? 4 : 6;
+  static constexpr int R = 1 << DIM;
+  static constexpr uint32_t SLOTS = 1u << (DIM * K);                       // level-K prefixes
+  static constexpr uint32_t CELLS = ((1u << (DIM * (K + 1))) - 1u) / (R - 1);  // levels 0..K, dense
+  __host__ __device__ static constexpr uint32_t offset(int level) { return ((1u << (DIM * level)) - 1u) / (R - 1); }
+};
+
+// Mass-weighted sum of child cells / units: the ONE definition every kernel uses (explicit fma: the bits
+// must not depend on what the compiler contracts in which kernel).
+struct ComSum {
+  double m = 0.0, sx = 0.0, sy = 0.0, sz = 0.0;
+  __device__ __forceinline__ void add(const double4& q) {
+    m += q.w;
+    sx = fma(q.w, q.x, sx);
+    sy = fma(q.w, q.y, sy);
+    sz = fma(q.w, q.z, sz);
+  }
+  // a massless cell (the reference panics there): geometric centre g instead of 0/0
+  __device__ __forceinline__ double4 finish(const double4& g) const {
+    if (m != 0.0) {
+      const double inv = 1.0 / m;  // one division: the reference's own (...) * inv_total_mass form (lib.rs:43-49)
+      return make_double4(sx * inv, sy * inv, sz * inv, m);
+    }
+    return make_double4(g.x, g.y, g.z, 0.0);
+  }
 };
 
 constexpr uint32_t SMALL_CELL = 16;
@@ -1040,6 +1084,7 @@ struct ShardBuild {
   uint32_t* n_local;     // device: how many those were (written by the sort, read by every later kernel)
   size_t n_cap;          // capacity of the per-rank arrays, in bodies
   TopSlots slots;
+  uint32_t* perm_out;    // where the sort leaves the permutation (the rank's block of the exchange buffer)
 };
 
 struct BuildOut {
@@ -1152,8 +1197,6 @@ __device__ __forceinline__ size_t nsv_next_le(const NsvTables& tv, size_t j0, un
 //     bodies: first later body that starts a cell at a level <= its own), hence body count and skip link,
 //     and - for cells of <= SMALL_CELL bodies - the mass / centre of mass as a sum over its units in
 //     body order.  Larger cells are left to the bottom-up pass (K7).
-//     (cells_kernel_chain below is the earlier per-lane form: each lane loops over its own chain, the
-//     ends found leaf -> top and one running sum per chain; same results, ~10 of 32 lanes busy.)
 template <int DIM, int MIN_BLOCKS>
 __global__ void __launch_bounds__(256, MIN_BLOCKS) cells_kernel(const uint64_t* __restrict__ key,
                                                     const double4* __restrict__ sp,
@@ -1268,35 +1311,26 @@ __global__ void __launch_bounds__(256, MIN_BLOCKS) cells_kernel(const uint64_t* 
     const uint32_t cnt = static_cast<uint32_t>(e - so);
     cells.count[c] = cnt;
     cells.skip[c] = cell_start[e];
-    if (cnt > cells.small) continue;
-    // the per-cell sums start from zero: 0 + m x == m x exactly, so starting from the first unit's products is the same
-    double sm, sx, sy, sz;
+    if (cnt > cells.small || uint32_t(lev) < cells.top_level) continue;
+    ComSum sum;
     if (!merged_units) {  // no merged unit anywhere: plain sums over the run
-      const double4 q0 = sp[so];
-      sm = q0.w; sx = q0.w * q0.x; sy = q0.w * q0.y; sz = q0.w * q0.z;
-      double4 q = sp[min(so + 1, e - 1)];
-      for (size_t j = so + 1; j < e; ++j) {  // (the next body is fetched before this one is added)
+      double4 q = sp[so];
+      for (size_t j = so; j < e; ++j) {  // (the next body is fetched before this one is added)
         const double4 nq = sp[min(j + 1, e - 1)];
-        sm += q.w; sx += q.w * q.x; sy += q.w * q.y; sz += q.w * q.z;
+        sum.add(q);
         q = nq;
       }
     } else {
-      size_t j = so + 1;
-      while (j < e && ab[j].x == NOT_HEAD) ++j;
-      const double4 q0 = unit_leaf(sp, perm, so, j);
-      sm = q0.w; sx = q0.w * q0.x; sy = q0.w * q0.y; sz = q0.w * q0.z;
+      size_t j = so;
       while (j < e) {  // units in order
         size_t je = j + 1;
         while (je < e && ab[je].x == NOT_HEAD) ++je;
-        const double4 q = unit_leaf(sp, perm, j, je);
-        sm += q.w; sx += q.w * q.x; sy += q.w * q.y; sz += q.w * q.z;
+        sum.add(unit_leaf(sp, perm, j, je));
         j = je;
       }
     }
-    // a massless cell (the reference panics there): geometric centre instead of 0/0
-    const double inv = 1.0 / sm;  // one division: the reference's own (…) * inv_total_mass form (lib.rs:43-49)
-    if (sm != 0.0) {
-      cells.com[c] = make_double4(sx * inv, sy * inv, sz * inv, sm);
+    if (sum.m != 0.0) {
+      cells.com[c] = sum.finish(make_double4(0.0, 0.0, 0.0, 0.0));
     } else {
       // (written by another lane in phase 1: recompute instead of reading it back)
       double half = ext0;
@@ -1317,111 +1351,6 @@ __global__ void __launch_bounds__(256, MIN_BLOCKS) cells_kernel(const uint64_t* 
         if (DIM == 3) gz += with_sign(half, !(digit & 4u));
       }
       cells.com[c] = make_double4(gx, gy, gz, 0.0);
-    }
-  }
-}
-
-// K6 (earlier form, kept for A/B runs: PB200_CELLS=chain)
-template <int DIM>
-__global__ void __launch_bounds__(256) cells_kernel_chain(const uint64_t* __restrict__ key,
-                                                    const double4* __restrict__ sp,
-                                                    const uint32_t* __restrict__ perm,
-                                                    const uchar2* __restrict__ ab,
-                                                    const uint32_t* __restrict__ cell_start, size_t n,
-                                                    const unsigned long long* __restrict__ extent_bits,
-                                                    const unsigned* __restrict__ tree_meta,
-                                                    unsigned* __restrict__ sticky, NsvTables tv, CellArrays cells) {
-  constexpr int LM = TreeDim<DIM>::LM;
-  const size_t s = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
-  const uint32_t total = cell_start[n];
-  if (s == 0) {
-    // worst case over every build since the last host check (builds run unverified in between):
-    // [0] cells needed, [1] 1 + deepest level shared by distinct neighbouring keys
-    atomicMax(&sticky[0], total);
-    atomicMax(&sticky[1], tree_meta[0]);
-  }
-  if (s >= n) return;
-  if (total > cells.capacity || *cells.bad) return;  // host grows the table / sorts all bits and re-runs
-  const uchar2 abv = ab[s];
-  if (abv.x == NOT_HEAD) return;
-  const uint32_t c0 = cell_start[s];
-  if (s == 0) cells.parent[0] = NO_PARENT;
-  const int a = int(abv.x) - 1, b = int(abv.y) - 1;
-  const int top = a + 1, leaf_level = max(a, b) + 1;
-  const uint64_t kme = key[s];
-  const double4 me = sp[s];
-
-  double half = __longlong_as_double(static_cast<long long>(*extent_bits));
-  double cx = 0.0, cy = 0.0, cz = 0.0;
-  auto descend = [&](int l) {  // from level l to level l+1 along the head body's path
-    unsigned digit;
-    if (l < LM) {
-      digit = unsigned((kme >> (DIM * (LM - 1 - l))) & ((1u << DIM) - 1u));
-    } else {  // pseudo level below the key: compare the head body itself
-      digit = unsigned(me.x > cx) | (unsigned(me.y > cy) << 1);
-      if (DIM == 3) digit |= unsigned(me.z > cz) << 2;
-    }
-    half *= 0.5;
-    cx += with_sign(half, !(digit & 1u));
-    cy += with_sign(half, !(digit & 2u));
-    if (DIM == 3) cz += with_sign(half, !(digit & 4u));
-  };
-  for (int l = 0; l < top; ++l) descend(l);
-  for (int lev = top; lev <= leaf_level; ++lev) {
-    const uint32_t c = c0 + uint32_t(lev - top);
-    cells.level[c] = static_cast<uint8_t>(lev);
-    cells.head[c] = static_cast<uint32_t>(s);
-    cells.arrived[c] = 0u;
-    cells.centre_ext[c] = make_double4(cx, cy, cz, half);
-    if (lev < leaf_level) descend(lev);
-  }
-
-  // leaf: the unit itself
-  size_t e = s + 1;
-  while (e < n && ab[e].x == NOT_HEAD) ++e;
-  const double4 leaf = unit_leaf(sp, perm, s, e);
-  {
-    const uint32_t c = c0 + uint32_t(leaf_level - top);
-    cells.count[c] = static_cast<uint32_t>(e - s);
-    cells.skip[c] = cell_start[e];
-    cells.com[c] = leaf;
-  }
-  double sm = leaf.w, sx = leaf.w * leaf.x, sy = leaf.w * leaf.y, sz = leaf.w * leaf.z;
-  // the per-cell sums start from zero: 0 + m x == m x exactly, so carrying the leaf's products is the same
-  const bool merged_units = tree_meta[1] != 0u;
-  bool summing = true;
-  for (int lev = leaf_level - 1; lev >= top; --lev) {
-    const uint32_t c = c0 + uint32_t(lev - top);
-    const size_t e_prev = e;
-    e = nsv_next_le(tv, e_prev, unsigned(lev));
-    const uint32_t cnt = static_cast<uint32_t>(e - s);
-    cells.count[c] = cnt;
-    cells.skip[c] = cell_start[e];
-    if (summing && cnt <= cells.small) {
-      if (!merged_units) {  // no merged unit anywhere: plain sums over the run
-        for (size_t j = e_prev; j < e; ++j) {
-          const double4 q = sp[j];
-          sm += q.w; sx += q.w * q.x; sy += q.w * q.y; sz += q.w * q.z;
-        }
-      } else {
-        for (size_t j = e_prev; j < e;) {  // units in order
-          size_t je = j + 1;
-          while (je < e && ab[je].x == NOT_HEAD) ++je;
-          const double4 q = unit_leaf(sp, perm, j, je);
-          sm += q.w; sx += q.w * q.x; sy += q.w * q.y; sz += q.w * q.z;
-          j = je;
-        }
-      }
-      // a massless cell (the reference panics there): geometric centre instead of 0/0
-      const double inv = 1.0 / sm;  // one division: the reference's own (…) * inv_total_mass form (lib.rs:43-49)
-      if (sm != 0.0) {
-        cells.com[c] = make_double4(sx * inv, sy * inv, sz * inv, sm);
-      } else {
-        const double4 g = cells.centre_ext[c];
-        cells.com[c] = make_double4(g.x, g.y, g.z, 0.0);
-      }
-    } else {
-      summing = false;
     }
   }
 }
@@ -1456,63 +1385,6 @@ __device__ __forceinline__ double4 ld_cg_double4(const double4* p) {
   return make_double4(lo.x, lo.y, hi.x, hi.y);
 }
 
-__device__ __forceinline__ bool done_in_fill(const CellArrays& cells, uint32_t c) {
-  return cells.count[c] <= cells.small || cells.skip[c] == c + 1u;
-}
-
-__global__ void __launch_bounds__(128) com_kernel(const uchar2* __restrict__ ab,
-                                                  const uint32_t* __restrict__ cell_start, size_t n,
-                                                  CellArrays cells) {
-  const size_t s = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
-  if (s >= n) return;
-  if (cell_start[n] > cells.capacity || *cells.bad) return;
-  if (ab[s].x == NOT_HEAD) return;
-  // chain of cells headed by s: c0 (shallowest) .. c_last (leaf); body counts shrink with depth
-  const uint32_t c0 = cell_start[s], c_last = cell_start[s + 1] - 1;
-  uint32_t c = c0;
-  while (c < c_last && !done_in_fill(cells, c)) ++c;  // shallowest finished cell of the chain
-  if (c == c0) {
-    const uint32_t p = cells.parent[c0];
-    if (p == NO_PARENT || done_in_fill(cells, p)) return;  // an ancestor's sum already covers it
-  }
-  bool wrote = false;  // com[c] was written by this thread in this kernel (else by cells_kernel, already visible)
-  while (true) {
-    const uint32_t p = cells.parent[c];
-    if (p == NO_PARENT) break;
-    const uint32_t mine = cells.count[c];
-    // release only when there is something of ours to publish: com[c] must be visible (at L2) before
-    // the arrival is.  The children are then read with ld.cg straight from L2, so no acquire fence
-    // (which would invalidate this SM's whole L1, as __threadfence() does) is needed.
-    cuda::atomic_ref<uint32_t, cuda::thread_scope_device> arrived(cells.arrived[p]);
-    const uint32_t old = wrote ? arrived.fetch_add(mine, cuda::std::memory_order_release)
-                               : arrived.fetch_add(mine, cuda::std::memory_order_relaxed);
-    if (old + mine != cells.count[p]) break;
-    double m = 0.0, sx = 0.0, sy = 0.0, sz = 0.0;
-    const uint32_t end = cells.skip[p];
-    for (uint32_t ch = p + 1; ch < end;) {
-      const double4 q = ld_cg_double4(&cells.com[ch]);
-      m += q.w;
-      sx += q.w * q.x;
-      sy += q.w * q.y;
-      sz += q.w * q.z;
-      const uint32_t next = cells.skip[ch];
-      if (next <= ch) break;  // (never in a well-formed table)
-      ch = next;
-    }
-    double4 out;
-    if (m != 0.0) {
-      const double inv = 1.0 / m;  // (…) * inv_total_mass, lib.rs:43-49
-      out = make_double4(sx * inv, sy * inv, sz * inv, m);
-    } else {
-      const double4 g = cells.centre_ext[p];
-      out = make_double4(g.x, g.y, g.z, 0.0);
-    }
-    cells.com[p] = out;
-    wrote = true;
-    c = p;
-  }
-}
-
 // K7 (current form)  the same sums in two kernels without the per-unit scan and with one round of
 //     loads per level instead of a chain through the skip links:
 //     kids_kernel, one thread per cell, acts on the cells K6 left open (more than SMALL_CELL bodies, not
@@ -1537,19 +1409,22 @@ __global__ void __launch_bounds__(256) kids_kernel(const uint32_t* __restrict__ 
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t total = cell_start[nref.get()];
   const bool live = !(total > cells.capacity || *cells.bad) && p < total;
-  uint32_t cnt = 0, end = 0;
+  uint32_t cnt = 0, end = 0, lev = 0;
   if (live) {
     cnt = cells.count[p];
     end = cells.skip[p];
+    lev = cells.level[p];
   }
-  const bool open = live && cnt > cells.small && end != p + 1u;
+  // open = left to the bottom-up pass by K6: more than `small` bodies, or above the top level (any size)
+  const bool open = live && (cnt > cells.small || lev < cells.top_level) && end != p + 1u;
   if (!__any_sync(FULL, open)) return;  // (most warps: nothing but finished cells)
   bool start = false;
   if (open) {
     uint32_t nk = 0, pre = 0;
+    const bool kids_above_top = lev + 1u < cells.top_level;
     for (uint32_t ch = p + 1u; ch < end;) {
       const uint32_t c_cnt = cells.count[ch], next = cells.skip[ch];
-      if (c_cnt <= cells.small || next == ch + 1u) pre += c_cnt;  // finished by K6
+      if ((c_cnt <= cells.small && !kids_above_top) || next == ch + 1u) pre += c_cnt;  // finished by K6
       else cells.parent[ch] = p;                                  // climbs later
       if (nk >= 1u && nk < K) kid_tab[size_t(p) * K + nk] = ch;
       ++nk;
@@ -1610,7 +1485,7 @@ __global__ void __launch_bounds__(128) climb_kernel(const uint32_t* __restrict__
   while (true) {
     const uint32_t nk = me.kid[0];
     me.kid[0] = c + 1u;
-    double m = 0.0, sx = 0.0, sy = 0.0, sz = 0.0;
+    ComSum sum;
     double4 q[K];
     if (nk != KIDS_OVERFLOW) {
 #pragma unroll
@@ -1623,33 +1498,17 @@ __global__ void __launch_bounds__(128) climb_kernel(const uint32_t* __restrict__
     if (nk != KIDS_OVERFLOW) {
 #pragma unroll
       for (int i = 0; i < K; ++i)
-        if (uint32_t(i) < nk) {
-          m += q[i].w;
-          sx += q[i].w * q[i].x;
-          sy += q[i].w * q[i].y;
-          sz += q[i].w * q[i].z;
-        }
+        if (uint32_t(i) < nk) sum.add(q[i]);
     } else {
       const uint32_t end = cells.skip[c];
       for (uint32_t ch = c + 1u; ch < end;) {
-        const double4 qq = ld_cg_double4(&cells.com[ch]);
-        m += qq.w;
-        sx += qq.w * qq.x;
-        sy += qq.w * qq.y;
-        sz += qq.w * qq.z;
+        sum.add(ld_cg_double4(&cells.com[ch]));
         const uint32_t next = cells.skip[ch];
         if (next <= ch) break;
         ch = next;
       }
     }
-    double4 out;
-    if (m != 0.0) {
-      const double inv = 1.0 / m;  // (…) * inv_total_mass, lib.rs:43-49
-      out = make_double4(sx * inv, sy * inv, sz * inv, m);
-    } else {  // a massless cell (the reference panics there): geometric centre instead of 0/0
-      out = make_double4(g.x, g.y, g.z, 0.0);
-    }
-    cells.com[c] = out;
+    cells.com[c] = sum.finish(g);
     if (me.parent == NO_PARENT) break;
     // acq_rel: com[c] must be visible before the arrival is (release), and the thread that completes the
     // parent must see the sums its siblings published before their arrivals (acquire) - ordered by the PTX
@@ -1788,6 +1647,361 @@ __global__ void __launch_bounds__(256) walk_kernel(const double4* __restrict__ s
     if (active && sp[s].w == 0.0) fx = fy = fz = __int_as_float(0x7fc00000);
     acc[orig] = make_float4(fx, fy, fz, __uint_as_float(inter));
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sharded Barnes-Hut (one rank per GPU; SURVEY §8e, north_star "exchanges top-level tree nodes").
+//
+// The key space is cut between the ranks at level-K prefixes (TopTree<DIM>::K); every rank holds every
+// body's position (the integrator state is replicated) and
+//   1. keeps, sorts and builds the tree of the bodies whose keys fall in its own range (tree_build with a
+//      ShardBuild): its cell table is exact for every cell at level >= K of its range;
+//   2. publishes one TopSlotRec per level-K prefix it owns (top_export_kernel) - all ranks' records are
+//      all-gathered (a few hundred KB);
+//   3. rebuilds the cells ABOVE level K, redundantly and identically on every rank, from those records
+//      (top_build_kernel): counts, leaves, centres of mass in ascending digit order with ComSum - the
+//      operations the single-GPU build applies to the same cells, hence the same bits;
+//   4. walks its own bodies (a Morton-contiguous slice of the targets) over the dense top tree and,
+//      below an opened level-K cell, over the OWNER's cell table - through a peer pointer (NVLink P2P
+//      loads) when the owner is another rank.  The visiting order is the global pre-order, so the fp32
+//      sums are those of the single-GPU walk;
+//   5. all ranks' accelerations (in sorted order, with the permutation) are all-gathered and every rank
+//      advances the replicated state (verlet_lean_sharded_kernel).
+// The cuts for the next step come for free: step 3 sees the level-K histogram of ALL bodies.
+// ---------------------------------------------------------------------------------------------
+struct TopSlotRec {   // 48 bytes; what a rank tells the others about one level-K prefix
+  double4 com;        // {X, Y, Z, M} of the deepest cell that holds exactly the prefix's bodies
+  uint32_t count;     // bodies with the prefix (0: none on this rank)
+  uint32_t units;     // 1: a single unit (a leaf, possibly above level K), 2: an internal level-K cell
+  uint32_t cell;      // index of that cell in the owner's table
+  uint32_t end;       // the owner's skip[cell]: one past the cell's subtree
+};
+static_assert(sizeof(TopSlotRec) == 48, "TopSlotRec layout");
+
+// record SLOTS = the rank's header: count = bodies sorted, units = cells built, cell = build abandoned
+template <int DIM>
+__global__ void __launch_bounds__(256) top_export_kernel(const uint32_t* __restrict__ slot_cell, NRef nref,
+                                                         const uint32_t* __restrict__ cell_start, CellArrays cells,
+                                                         TopSlotRec* __restrict__ out) {
+  pb_pdl_sync();
+  constexpr uint32_t S = TopTree<DIM>::SLOTS;
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t n = nref.get();
+  const uint32_t total = cell_start[n];
+  const bool bad = total > cells.capacity || *cells.bad;
+  if (q == S) {
+    TopSlotRec h;
+    h.com = make_double4(0.0, 0.0, 0.0, 0.0);
+    h.count = uint32_t(n);
+    h.units = total;
+    h.cell = bad ? 1u : 0u;
+    h.end = 0u;
+    out[S] = h;
+  }
+  if (q >= S) return;
+  TopSlotRec r;
+  r.com = make_double4(0.0, 0.0, 0.0, 0.0);
+  r.count = r.units = r.cell = r.end = 0u;
+  const uint32_t c1 = bad ? 0u : slot_cell[q];
+  if (c1 != 0u && c1 <= total) {
+    const uint32_t c = c1 - 1u;
+    r.com = cells.com[c];
+    r.count = cells.count[c];
+    r.end = cells.skip[c];
+    r.cell = c;
+    r.units = (r.end == c + 1u) ? 1u : 2u;
+  }
+  out[q] = r;
+}
+
+// Dense top tree, levels 0..K (index TopTree::offset(level) + prefix), identical on every rank.
+struct TopView {
+  double4* centre_ext;  // {cx, cy, cz, half-width}
+  double4* com;         // {X, Y, Z, M}
+  uint4* info;          // x: units (0 none, 1 leaf, 2 internal) | owner rank << 8, y: cell, z: end (owner's table), w: bodies
+  uint32_t* meta;       // [0] some rank abandoned its build, [1 .. world] bodies per rank, [1 + world ..] cells per rank
+  uint64_t* cuts;       // [world + 1] key cuts for the NEXT build (balanced on this step's level-K histogram)
+};
+
+template <int DIM>
+__global__ void __launch_bounds__(1024) top_build_kernel(const TopSlotRec* __restrict__ all /* [world][SLOTS + 1] */,
+                                                         int world, size_t n_total,
+                                                         const unsigned long long* __restrict__ extent_bits,
+                                                         TopView top) {
+  pb_pdl_sync();
+  using TT = TopTree<DIM>;
+  constexpr int K = TT::K, R = TT::R, LM = TreeDim<DIM>::LM;
+  constexpr uint32_t S = TT::SLOTS;
+  __shared__ unsigned s_cum[1024];  // running body counts (cuts)
+  __shared__ unsigned s_wsum[32];
+  const int tid = threadIdx.x;
+  const double ext0 = __longlong_as_double(static_cast<long long>(*extent_bits));
+  if (tid == 0) {
+    unsigned bad = 0;
+    for (int r = 0; r < world; ++r) {
+      const TopSlotRec h = all[size_t(r) * (S + 1) + S];
+      bad |= h.cell;
+      top.meta[1 + r] = h.count;
+      top.meta[1 + world + r] = h.units;
+    }
+    top.meta[0] = bad;
+  }
+  // level K: the rank that holds the prefix (at most one does)
+  for (uint32_t q = tid; q < S; q += 1024) {
+    uint4 inf = make_uint4(0u, 0u, 0u, 0u);
+    double4 com = make_double4(0.0, 0.0, 0.0, 0.0);
+    for (int r = 0; r < world; ++r) {
+      const TopSlotRec rec = all[size_t(r) * (S + 1) + q];
+      if (rec.count != 0u && inf.w == 0u) {
+        inf = make_uint4(rec.units | (uint32_t(r) << 8), rec.cell, rec.end, rec.count);
+        com = rec.com;
+      }
+    }
+    top.info[TT::offset(K) + q] = inf;
+    top.com[TT::offset(K) + q] = com;
+  }
+  __syncthreads();
+  // levels K-1 .. 0 from their children, ascending digit order (= pre-order), ComSum
+  for (int l = K - 1; l >= 0; --l) {
+    const uint32_t cells_l = 1u << (DIM * l);
+    for (uint32_t p = tid; p < cells_l; p += 1024) {
+      uint32_t units = 0, bodies = 0;
+      uint4 only = make_uint4(0u, 0u, 0u, 0u);
+      double4 only_com = make_double4(0.0, 0.0, 0.0, 0.0);
+      ComSum sum;
+#pragma unroll
+      for (int d = 0; d < R; ++d) {
+        const uint32_t t = TT::offset(l + 1) + p * R + d;
+        const uint4 ci = top.info[t];
+        const uint32_t u = ci.x & 0xffu;
+        if (u == 0u) continue;
+        const double4 cc = top.com[t];
+        sum.add(cc);
+        units += u;  // (1 + anything >= 1 is already "internal")
+        bodies += ci.w;
+        only = ci;
+        only_com = cc;
+      }
+      uint4 inf = make_uint4(0u, 0u, 0u, 0u);
+      double4 com = make_double4(0.0, 0.0, 0.0, 0.0);
+      if (units == 1u) {  // one unit below: this cell is (or lies above) its leaf - the unit's own record
+        inf = only;
+        com = only_com;
+      } else if (units > 1u) {
+        // geometric centre for the massless case: replay the prefix digits (the arithmetic of cells_kernel)
+        double half = ext0, cx = 0.0, cy = 0.0, cz = 0.0;
+        for (int j = 0; j < l; ++j) {
+          const unsigned digit = (p >> (DIM * (l - 1 - j))) & unsigned(R - 1);
+          half *= 0.5;
+          cx += with_sign(half, !(digit & 1u));
+          cy += with_sign(half, !(digit & 2u));
+          if (DIM == 3) cz += with_sign(half, !(digit & 4u));
+        }
+        com = sum.finish(make_double4(cx, cy, cz, half));
+        inf = make_uint4(2u, 0u, 0u, bodies);
+      }
+      top.info[TT::offset(l) + p] = inf;
+      top.com[TT::offset(l) + p] = com;
+    }
+    __syncthreads();
+  }
+  // geometric centres / half-widths of every top cell
+  for (uint32_t t = tid; t < TT::CELLS; t += 1024) {
+    int l = 0;
+    while (l < K && TT::offset(l + 1) <= t) ++l;
+    const uint32_t p = t - TT::offset(l);
+    double half = ext0, cx = 0.0, cy = 0.0, cz = 0.0;
+    for (int j = 0; j < l; ++j) {
+      const unsigned digit = (p >> (DIM * (l - 1 - j))) & unsigned(R - 1);
+      half *= 0.5;
+      cx += with_sign(half, !(digit & 1u));
+      cy += with_sign(half, !(digit & 2u));
+      if (DIM == 3) cz += with_sign(half, !(digit & 4u));
+    }
+    top.centre_ext[t] = make_double4(cx, cy, cz, half);
+  }
+  // cuts for the next build: rank r starts at the first level-K prefix whose running count reaches r n / world
+  {
+    constexpr uint32_t PER = S / 1024;  // prefixes per thread (4)
+    unsigned mine = 0;
+#pragma unroll
+    for (uint32_t j = 0; j < PER; ++j) mine += top.info[TT::offset(K) + tid * PER + j].w;
+    const unsigned excl = block_exclusive_scan_nt<1024>(mine, s_wsum);
+    s_cum[tid] = excl;
+    __syncthreads();
+    if (tid <= world) {
+      uint64_t cut = 0ull;
+      if (tid == world) {
+        cut = ~0ull;
+      } else if (tid > 0) {
+        const unsigned want = unsigned((n_total * size_t(tid)) / size_t(world));
+        // first prefix q with (bodies in prefixes < q) >= want
+        int lo = 0, hi = 1024;  // thread groups
+        while (lo < hi) {
+          const int mid = (lo + hi) / 2;
+          if (s_cum[mid] >= want) hi = mid; else lo = mid + 1;
+        }
+        // lo = first group whose exclusive count >= want; the prefix lies in group lo-1 or is lo*PER
+        uint32_t q = uint32_t(lo) * PER;
+        if (lo > 0) {
+          unsigned run = s_cum[lo - 1];
+          q = uint32_t(lo - 1) * PER;
+          while (q < uint32_t(lo) * PER && run < want) {
+            run += top.info[TT::offset(K) + q].w;
+            ++q;
+          }
+        }
+        cut = uint64_t(q) << (DIM * (LM - K));
+      }
+      top.cuts[tid] = cut;
+    }
+  }
+}
+
+struct PeerTables {   // every rank's cell table, as seen from this device (own table: local pointers)
+  const double4* centre_ext[8];
+  const double4* com[8];
+  const uint32_t* skip[8];
+  uint32_t capacity;  // the same on every rank (symmetric allocation)
+};
+
+template <int DIM>
+__global__ void __launch_bounds__(256) walk_sharded_kernel(const double4* __restrict__ sp,
+                                                           const uint32_t* __restrict__ perm,
+                                                           const uint8_t* __restrict__ fixed, NRef nref, TopView top,
+                                                           PeerTables peers, double theta, float easing, float tiny,
+                                                           float4* __restrict__ acc_sorted) {
+  pb_pdl_sync();
+  using TT = TopTree<DIM>;
+  constexpr int K = TT::K, R = TT::R;
+  if (top.meta[0] != 0u) return;  // some rank's build was abandoned: the host replays the chunk
+  const size_t n = nref.get();
+  const size_t s = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  if (size_t(blockIdx.x) * blockDim.x >= n) return;
+  bool active = s < n;
+  double px = 0.0, py = 0.0, pz = 0.0, pm = 0.0;
+  if (active) {
+    const double4 p = sp[s];
+    px = p.x; py = p.y; pz = p.z; pm = p.w;
+    if (fixed[perm[s]]) active = false;  // transformers.rs:139-141
+  }
+  const double theta2 = theta * theta;
+  float fx = 0.f, fy = 0.f, fz = 0.f;
+  uint32_t inter = 0;
+  auto interact = [&](const double4& cm) {
+    const float dx = static_cast<float>(cm.x - px);
+    const float dy = static_cast<float>(cm.y - py);
+    const float dz = static_cast<float>(cm.z - pz);
+    float r2 = fmaf(dx, dx, tiny);
+    r2 = fmaf(dy, dy, r2);
+    r2 = fmaf(dz, dz, r2);
+    const float sft = r2 + easing;
+    const float w = rsqrt_approx(r2 * sft * sft);
+    const float mw = static_cast<float>(cm.w) * w;
+    fx = fmaf(mw, dx, fx);
+    fy = fmaf(mw, dy, fy);
+    fz = fmaf(mw, dz, fz);
+    ++inter;
+  };
+  int l = 0;
+  uint32_t p = 0;
+  bool done = !active;
+  while (!done) {
+    const uint32_t t = TT::offset(l) + p;
+    const uint4 inf = top.info[t];
+    const uint32_t units = inf.x & 0xffu;
+    bool descend = false;
+    if (units == 1u) {
+      interact(top.com[t]);  // a leaf: always taken (octree.rs:151-152)
+    } else if (units != 0u) {
+      const double4 ce = top.centre_ext[t];
+      if (accept_cell(px, py, pz, ce, theta, theta2)) {
+        interact(top.com[t]);
+      } else if (l < K) {
+        descend = true;
+      } else {
+        // an opened level-K cell: its subtree in the owner's table, pre-order (c -> c+1 / skip[c])
+        const uint32_t owner = inf.x >> 8;
+        const double4* __restrict__ t_ce = peers.centre_ext[owner];
+        const double4* __restrict__ t_cm = peers.com[owner];
+        const uint32_t* __restrict__ t_sk = peers.skip[owner];
+        const uint32_t end = min(inf.z, peers.capacity);
+        uint32_t c = inf.y + 1u;
+        while (c < end) {
+          const double4 ce2 = ld_now_double4(t_ce + c);
+          const double4 cm2 = ld_now_double4(t_cm + c);
+          const uint32_t sk = ld_now_u32(t_sk + c);
+          if (sk == c + 1u || accept_cell(px, py, pz, ce2, theta, theta2)) {
+            interact(cm2);
+            c = max(sk, c + 1u);
+          } else {
+            c = c + 1u;
+          }
+        }
+      }
+    }
+    if (descend) {
+      ++l;
+      p *= R;
+    } else {
+      while (l > 0 && (p & uint32_t(R - 1)) == uint32_t(R - 1)) {
+        --l;
+        p >>= DIM;
+      }
+      if (l == 0) done = true;
+      else ++p;
+    }
+  }
+  if (s < n) {
+    // a_i = f/m_a: a massless target is 0/0 = NaN in the reference (transformers.rs:154-158)
+    if (active && pm == 0.0) fx = fy = fz = __int_as_float(0x7fc00000);
+    acc_sorted[s] = make_float4(fx, fy, fz, __uint_as_float(inter));
+  }
+}
+
+// After a full (replicated) build: the first cuts, balanced on the sorted keys, and the splitters of this
+// rank's 256 buckets (quantiles of the keys in its range) for its first sharded build.
+template <int DIM>
+__global__ void __launch_bounds__(256) shard_plan_kernel(const uint64_t* __restrict__ sorted, size_t n, int rank,
+                                                         int world, uint64_t* __restrict__ cuts /* [world + 1] */,
+                                                         uint64_t* __restrict__ spl_out /* [257] */) {
+  constexpr int shift = DIM * (TreeDim<DIM>::LM - TopTree<DIM>::K);
+  __shared__ uint64_t s_cut[16];
+  __shared__ size_t s_range[2];
+  __shared__ uint64_t v[257];
+  const int t = threadIdx.x;
+  if (t <= world) {
+    uint64_t cut = 0ull;
+    if (t == world) cut = ~0ull;
+    else if (t > 0) cut = (sorted[(n * size_t(t)) / size_t(world)] >> shift) << shift;
+    s_cut[t] = cut;
+    cuts[t] = cut;
+  }
+  __syncthreads();
+  if (t < 2) {  // first sorted body with key >= cut
+    const uint64_t cut = s_cut[rank + t];
+    size_t lo = 0, hi = n;
+    while (lo < hi) {
+      const size_t mid = (lo + hi) / 2;
+      if (sorted[mid] >= cut) hi = mid; else lo = mid + 1;
+    }
+    s_range[t] = lo;
+  }
+  __syncthreads();
+  const size_t b = s_range[0], m = s_range[1] - s_range[0];
+  v[t] = m ? sorted[b + ((size_t(t) * m) >> 8)] : 0ull;
+  if (t == 0) v[256] = m ? sorted[b + m - 1] + 1ull : 0ull;
+  __syncthreads();
+  if (t == 0) {
+    uint64_t run = 0;
+    for (int j = 0; j <= 256; ++j) {
+      run = v[j] > run ? v[j] : run;
+      v[j] = run;
+    }
+  }
+  __syncthreads();
+  spl_out[t] = v[t];
+  if (t == 0) spl_out[256] = v[256];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -2282,7 +2496,7 @@ template <int DIM>
 cudaError_t encode_and_sort(GravityWorkspace& ws, size_t n, const SortBuffers& sb, unsigned* bad, cudaStream_t st,
                             LaunchStats& ls, uint64_t** splitters_out, const ShardBuild* sh) {
   uint64_t* k[2] = {ws.key0.as<uint64_t>(), ws.key1.as<uint64_t>()};
-  uint32_t* v[2] = {ws.idx0.as<uint32_t>(), ws.idx1.as<uint32_t>()};
+  uint32_t* v[2] = {(sh && sh->perm_out) ? sh->perm_out : ws.idx0.as<uint32_t>(), ws.idx1.as<uint32_t>()};
   unsigned* stat_max = ws.sticky.as<unsigned>() + 3;
   const unsigned nb = blocks_for(n, 256);
   // splitters: read the set the previous evaluation left, write the other one
@@ -2357,8 +2571,8 @@ cudaError_t tree_build(GravityWorkspace& ws, const ShardBuild* sh, cudaStream_t 
   const size_t scratch_bytes = ready_off + size_t(READY_LISTS) * READY_STRIDE * 4;
   PB_PASS(ws.extent_bits.ensure(scratch_bytes));
   if (!ws.sticky.p) {
-    PB_PASS(ws.sticky.ensure(16));
-    PB_CUDA(cudaMemsetAsync(ws.sticky.p, 0, 16, st));
+    PB_PASS(ws.sticky.ensure(32));
+    PB_CUDA(cudaMemsetAsync(ws.sticky.p, 0, 32, st));
   }
   PB_PASS(ws.key0.ensure(n * 8 + 16));
   PB_PASS(ws.key1.ensure(n * 8));
@@ -2435,32 +2649,16 @@ cudaError_t tree_build(GravityWorkspace& ws, const ShardBuild* sh, cudaStream_t 
   CellArrays cells{ws.c_level.as<uint8_t>(),   ws.c_head.as<uint32_t>(),  ws.c_count.as<uint32_t>(),
                    ws.c_skip.as<uint32_t>(),   ws.c_parent.as<uint32_t>(), ws.c_arrived.as<uint32_t>(),
                    ws.c_centre_ext.as<double4>(), ws.c_com.as<double4>(), static_cast<uint32_t>(cap), small_cell,
-                   max_shared_plus1 + 2};
-  const unsigned nb128 = blocks_for(n, 128);
+                   max_shared_plus1 + 2, uint32_t(TopTree<DIM>::K)};
   const NsvTables tv{ws.nsv1.as<uint8_t>(), ws.nsv1.as<uint8_t>() + n_pad, n_pad, ws.nsv2.as<uint8_t>(), b_pad, nsv3, n, nblocks, nsuper};
-  static const bool cells_chain = std::getenv("PB200_CELLS") && std::string(std::getenv("PB200_CELLS")) == "chain";
   const TopSlots slots = sh ? sh->slots : TopSlots{nullptr, 0};
-  if (cells_chain && !sh) {
-    PB_LAUNCH(ls, st, "cells_kernel_chain",
-              cells_kernel_chain<DIM><<<nb, 256, 0, st>>>(ws.sorted_key, ws.spos64.as<double4>(), ws.perm,
-                                                          ws.ab.as<uchar2>(), ws.cell_start.as<uint32_t>(), n,
-                                                          ws.extent_cur, max_shared_plus1,
-                                                          ws.sticky.as<unsigned>(), tv, cells));
-  } else {
-      PB_LAUNCH(ls, st, "cells_kernel",
-                (pb_launch_pdl(cells_kernel<DIM, 4>, dim3(nb), dim3(256), 0, st, ws.sorted_key, ws.spos64.as<double4>(), ws.perm,
-                                                          ws.ab.as<uchar2>(), ws.cell_start.as<uint32_t>(), nref,
-                                                          ws.extent_cur, max_shared_plus1,
-                                                          ws.sticky.as<unsigned>(), tv, cells, slots)));
-  }
-  static const bool com_old = std::getenv("PB200_COM") && std::string(std::getenv("PB200_COM")) == "old";
+  PB_LAUNCH(ls, st, "cells_kernel",
+            (pb_launch_pdl(cells_kernel<DIM, 4>, dim3(nb), dim3(256), 0, st, ws.sorted_key, ws.spos64.as<double4>(), ws.perm,
+                                                      ws.ab.as<uchar2>(), ws.cell_start.as<uint32_t>(), nref,
+                                                      ws.extent_cur, max_shared_plus1,
+                                                      ws.sticky.as<unsigned>(), tv, cells, slots)));
   ws.parents_filled = false;
-  if (com_old && !sh) {
-    PB_LAUNCH(ls, st, "parent_kernel",
-              parent_kernel<<<blocks_for(cap, 256), 256, 0, st>>>(ws.cell_start.as<uint32_t>(), n, cells));
-    ws.parents_filled = true;
-    PB_LAUNCH(ls, st, "com_kernel", com_kernel<<<nb128, 128, 0, st>>>(ws.ab.as<uchar2>(), ws.cell_start.as<uint32_t>(), n, cells));
-  } else {
+  {
     PB_PASS(ws.c_kids.ensure(cap * (size_t(4) << DIM)));
     // (a warp of 32 cells holds at most 32 starts; list l takes the warps = l mod READY_LISTS)
     const unsigned kid_blocks = blocks_for(cap, 256);
@@ -2572,7 +2770,131 @@ cudaError_t direct_evaluate(GravityWorkspace& ws, size_t t0, size_t t1, float ea
 
 }  // namespace
 
+// ---- sharded Barnes-Hut: host side ---------------------------------------------------------------
+namespace {
+inline uint32_t top_slots(int dim) { return dim == 3 ? TopTree<3>::SLOTS : TopTree<2>::SLOTS; }
+inline uint32_t top_cells(int dim) { return dim == 3 ? TopTree<3>::CELLS : TopTree<2>::CELLS; }
+}  // namespace
+
+size_t ShardState::top_block_bytes() const { return size_t(4096 + 1) * sizeof(TopSlotRec); }  // 4^6 = 8^4 prefixes + header
+
+void ShardState::release() {
+  DevBuf* all[] = {&cuts, &n_local, &slot_cell, &top_all, &top_ce, &top_com, &top_info, &top_meta, &xacc};
+  for (DevBuf* b : all) b->release();
+  planned = false;
+}
+
+cudaError_t gravity_shard_setup(GravityWorkspace& ws, int kind, int rank, int world, size_t n) {
+  ShardState& sh = ws.shard;
+  if (world < 1 || world > 8 || rank < 0 || rank >= world) {
+    set_error("sharded run: world must be 1..8 (got rank %d of %d)", rank, world);
+    return cudaErrorInvalidValue;
+  }
+  const int dim = kind == PB200_ASTRO ? 2 : 3;
+  static_assert(TopTree<2>::SLOTS == 4096 && TopTree<3>::SLOTS == 4096, "top_block_bytes");
+  sh.rank = rank;
+  sh.world = world;
+  sh.planned = false;
+  // 1/world of the bodies + 12.5 % (the cuts follow the level-K histogram, one step late) + one level-K cell's worth
+  size_t cap = n / size_t(world) + n / size_t(8 * world) + n / 2048 + 4096;
+  cap = (cap + 1023) / 1024 * 1024;
+  if (cap > n + 1024) cap = (n + 1023) / 1024 * 1024;
+  sh.n_cap = cap;
+  PB_PASS(sh.cuts.ensure(16 * 8));
+  PB_PASS(sh.n_local.ensure(16));
+  PB_PASS(sh.slot_cell.ensure(size_t(top_slots(dim)) * 4));
+  PB_PASS(sh.top_all.ensure(size_t(world) * sh.top_block_bytes()));
+  PB_PASS(sh.top_ce.ensure(size_t(top_cells(dim)) * sizeof(double4)));
+  PB_PASS(sh.top_com.ensure(size_t(top_cells(dim)) * sizeof(double4)));
+  PB_PASS(sh.top_info.ensure(size_t(top_cells(dim)) * sizeof(uint4)));
+  PB_PASS(sh.top_meta.ensure(64 * 4));
+  PB_PASS(sh.xacc.ensure(size_t(world) * sh.xacc_block_bytes()));
+  return cudaSuccess;
+}
+
+bool gravity_shard_fits(const GravityWorkspace& ws) { return shard_sort_mode(ws.shard.n_cap) != 0; }
+
+cudaError_t gravity_shard_plan(GravityWorkspace& ws, cudaStream_t st, LaunchStats& ls) {
+  ShardState& sh = ws.shard;
+  if (ws.tree_dim == 0 || !ws.sorted_key || ws.n == 0) {
+    set_error("gravity_shard_plan: no full tree build to plan from");
+    return cudaErrorInvalidValue;
+  }
+  // the splitter set the NEXT build reads (encode_and_sort toggles splitter_cur before it writes)
+  uint64_t* spl = ws.splitters.as<uint64_t>() + SPLITTER_STRIDE * ws.splitter_cur;
+  if (ws.tree_dim == 2)
+    PB_LAUNCH(ls, st, "shard_plan_kernel",
+              shard_plan_kernel<2><<<1, 256, 0, st>>>(ws.sorted_key, ws.n, sh.rank, sh.world, sh.cuts.as<uint64_t>(), spl));
+  else
+    PB_LAUNCH(ls, st, "shard_plan_kernel",
+              shard_plan_kernel<3><<<1, 256, 0, st>>>(ws.sorted_key, ws.n, sh.rank, sh.world, sh.cuts.as<uint64_t>(), spl));
+  sh.planned = true;
+  return cudaGetLastError();
+}
+
+namespace {
+template <int DIM>
+cudaError_t shard_build(GravityWorkspace& ws, cudaStream_t st, LaunchStats& ls) {
+  ShardState& sh = ws.shard;
+  using TT = TopTree<DIM>;
+  PB_CUDA(cudaMemsetAsync(sh.slot_cell.p, 0, size_t(TT::SLOTS) * 4, st));
+  ShardBuild sb;
+  sb.cuts = sh.cuts.as<uint64_t>() + sh.rank;
+  sb.n_local = sh.n_local.as<uint32_t>();
+  sb.n_cap = sh.n_cap;
+  sb.slots = TopSlots{sh.slot_cell.as<uint32_t>(), TT::K};
+  // the permutation goes straight into this rank's block of the exchange buffer (behind the accelerations)
+  sb.perm_out = reinterpret_cast<uint32_t*>(static_cast<char*>(sh.xacc.p) + size_t(sh.rank) * sh.xacc_block_bytes() +
+                                            sh.n_cap * sizeof(float4));
+  BuildOut bo;
+  PB_PASS(tree_build<DIM>(ws, &sb, st, ls, &bo));
+  TopSlotRec* mine = reinterpret_cast<TopSlotRec*>(static_cast<char*>(sh.top_all.p) + size_t(sh.rank) * sh.top_block_bytes());
+  PB_LAUNCH(ls, st, "top_export_kernel",
+            pb_launch_pdl(top_export_kernel<DIM>, dim3(blocks_for(TT::SLOTS + 1, 256)), dim3(256), 0, st,
+                          sh.slot_cell.as<uint32_t>(), bo.nref, ws.cell_start.as<uint32_t>(), bo.cells, mine));
+  return cudaGetLastError();
+}
+
+template <int DIM>
+cudaError_t shard_walk(GravityWorkspace& ws, const GravityParams& prm, float easing, float tiny, cudaStream_t st,
+                       LaunchStats& ls) {
+  ShardState& sh = ws.shard;
+  TopView top{sh.top_ce.as<double4>(), sh.top_com.as<double4>(), sh.top_info.as<uint4>(), sh.top_meta.as<uint32_t>(),
+              sh.cuts.as<uint64_t>()};
+  PB_LAUNCH(ls, st, "top_build_kernel",
+            top_build_kernel<DIM><<<1, 1024, 0, st>>>(sh.top_all.as<TopSlotRec>(), sh.world, ws.n, ws.extent_cur, top));
+  PeerTables pt;
+  for (int r = 0; r < 8; ++r) {
+    pt.centre_ext[r] = static_cast<const double4*>(sh.peers.centre_ext[r < sh.world ? r : sh.rank]);
+    pt.com[r] = static_cast<const double4*>(sh.peers.com[r < sh.world ? r : sh.rank]);
+    pt.skip[r] = static_cast<const uint32_t*>(sh.peers.skip[r < sh.world ? r : sh.rank]);
+  }
+  pt.capacity = sh.peers.capacity;
+  float4* acc_sorted = reinterpret_cast<float4*>(static_cast<char*>(sh.xacc.p) + size_t(sh.rank) * sh.xacc_block_bytes());
+  const NRef nref{sh.n_local.as<uint32_t>(), uint32_t(sh.n_cap)};
+  PB_LAUNCH(ls, st, "walk_sharded_kernel",
+            walk_sharded_kernel<DIM><<<blocks_for(sh.n_cap, 256), 256, 0, st>>>(
+                ws.spos64.as<double4>(), ws.perm, ws.fixed, nref, top, pt, prm.theta, easing, tiny, acc_sorted));
+  return cudaGetLastError();
+}
+}  // namespace
+
+cudaError_t gravity_shard_build(GravityWorkspace& ws, const GravityParams& prm, cudaStream_t st, LaunchStats& ls) {
+  if (!ws.shard.planned) {
+    set_error("gravity_shard_build: not planned");
+    return cudaErrorInvalidValue;
+  }
+  return prm.kind == PB200_ASTRO ? shard_build<2>(ws, st, ls) : shard_build<3>(ws, st, ls);
+}
+
+cudaError_t gravity_shard_walk(GravityWorkspace& ws, const GravityParams& prm, cudaStream_t st, LaunchStats& ls) {
+  const float easing = static_cast<float>(prm.easing);
+  const float tiny = (prm.easing >= 3e-5) ? 1e-24f : 1e-11f;
+  return prm.kind == PB200_ASTRO ? shard_walk<2>(ws, prm, easing, tiny, st, ls) : shard_walk<3>(ws, prm, easing, tiny, st, ls);
+}
+
 void GravityWorkspace::release_all() {
+  shard.release();
   DevBuf* all[] = {&src4, &key0, &key1, &idx0, &idx1, &bucket_key, &bucket_idx, &splitters, &nsv1, &nsv2, &spos64, &ab, &cell_start, &scan_tmp,
                    &tile_counts, &digit_base, &extent_bits, &tgt_list, &tgt_flags, &c_level, &c_head,
                    &c_count, &c_skip, &c_parent, &c_arrived, &c_kids, &c_ready, &c_centre_ext, &c_com, &acc, &acc_part, &sticky,
@@ -2627,10 +2949,12 @@ cudaError_t gravity_check(GravityWorkspace& ws, cudaStream_t st, TreeCheck* out)
     return cudaSuccess;
   }
   ws.unchecked_builds = 0;
-  uint32_t h[4] = {0, 0, 0, 0};  // {max cells, 1 + max deepest shared level, sort error, largest top-8-bit bucket} since the last check
-  PB_CUDA(cudaMemcpyAsync(h, ws.sticky.p, 16, cudaMemcpyDeviceToHost, st));
-  PB_CUDA(cudaMemsetAsync(ws.sticky.p, 0, 16, st));
+  // {max cells, 1 + max deepest shared level, sort error, largest bucket, sharded build over capacity} since the last check
+  uint32_t h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  PB_CUDA(cudaMemcpyAsync(h, ws.sticky.p, 32, cudaMemcpyDeviceToHost, st));
+  PB_CUDA(cudaMemsetAsync(ws.sticky.p, 0, 32, st));
   PB_CUDA(cudaStreamSynchronize(st));
+  out->shard_overflow = h[4] != 0;
   const int dim = ws.tree_dim;
   const int key_bits = dim * (dim == 3 ? 21 : 31);
   out->total = h[0];
@@ -2685,7 +3009,7 @@ cudaError_t gravity_fill_parents(GravityWorkspace& ws, cudaStream_t st, LaunchSt
   CellArrays cells{ws.c_level.as<uint8_t>(),   ws.c_head.as<uint32_t>(),  ws.c_count.as<uint32_t>(),
                    ws.c_skip.as<uint32_t>(),   ws.c_parent.as<uint32_t>(), ws.c_arrived.as<uint32_t>(),
                    ws.c_centre_ext.as<double4>(), ws.c_com.as<double4>(), static_cast<uint32_t>(ws.cell_cap), SMALL_CELL,
-                   flags + 2};
+                   flags + 2, 0u};
   PB_LAUNCH(ls, st, "parent_kernel",
             parent_kernel<<<blocks_for(ws.cell_cap, 256), 256, 0, st>>>(ws.cell_start.as<uint32_t>(), ws.n, cells));
   ws.parents_filled = true;
