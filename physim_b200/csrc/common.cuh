@@ -159,6 +159,7 @@ struct GravityWorkspace {
   int sort_mode = 0;    // next sort: 0 global LSD passes, 1..3 bucket sort (chosen by gravity_check)
   int last_mode = 0;    // ... that the last sort used
   int splitter_cur = 0; // which of the two splitter sets the next evaluation reads
+  unsigned spl_nb[2] = {0, 0};  // how many buckets each splitter set was written for (0: never written)
   int bucket_ban = 0;   // checks left during which the bucket sort stays off (a bucket's bodies were too alike)
   uint32_t last_max_bucket = 0;  // fullest top-8-bit bin seen at the last check
   int unchecked_builds = 0;   // tree builds since the last gravity_check()

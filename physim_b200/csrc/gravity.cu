@@ -391,27 +391,35 @@ __device__ __forceinline__ unsigned block_exclusive_scan_nt(unsigned v, unsigned
 }
 
 constexpr int ENC_ITEMS = 4;           // bodies per thread in encode_bucket_kernel
+constexpr unsigned MAX_BUCKETS = 1024;  // 256 buckets up to ~3.7 M bodies, 512 / 1024 above (x 16384 keys of shared memory each)
 constexpr int LOCAL_BIN_BITS = 12;     // counting-sort bins inside a bucket
-constexpr unsigned LOCAL_BIN_LIMIT = 64;  // larger bins would make the in-bin ranking quadratic
+// Members of a bin rank themselves against each other (quadratic in the bin): ~1 body per bin on smooth data.
+// A bucket whose bodies sit in a few clumps of its key range (a rotating cube leaves the corners of its bounding
+// cell empty: key ranges with nothing in them) puts 50-400 in a bin, which still costs microseconds; only a
+// bin of more than this many (a thousand bodies on one spot) hands the build to the global passes.
+constexpr unsigned LOCAL_BIN_LIMIT = 1024;
 constexpr unsigned LOCAL_SKEWED = 0x7fffffffu;  // published as "largest bucket" when a bin is too full
 
 template <int DIM>
 __global__ void __launch_bounds__(256) encode_bucket_kernel(const double4* __restrict__ pos, size_t n,
                                                             const unsigned long long* __restrict__ extent_bits,
-                                                            const uint64_t* __restrict__ splitters /*[256]*/,
+                                                            const uint64_t* __restrict__ splitters /*[nb]*/,
+                                                            unsigned nb /* buckets: 256, 512 or 1024 */,
                                                             int lo, uint64_t* __restrict__ bkey,
                                                             uint32_t* __restrict__ bidx, unsigned cap,
-                                                            unsigned* __restrict__ cursor /*[256]*/,
+                                                            unsigned* __restrict__ cursor /*[nb]*/,
                                                             const uint64_t* __restrict__ cuts /* sharded build: keep
                                                             cuts[0] <= key < cuts[1]; nullptr: every body */) {
   pb_pdl_sync();
   constexpr int LM = TreeDim<DIM>::LM;
-  __shared__ unsigned cnt[256];
-  __shared__ unsigned gbase[256];
-  __shared__ uint64_t spl[256];
+  __shared__ unsigned cnt[MAX_BUCKETS];
+  __shared__ unsigned gbase[MAX_BUCKETS];
+  __shared__ uint64_t spl[MAX_BUCKETS];
   const int tid = threadIdx.x;
-  cnt[tid] = 0u;
-  spl[tid] = tid ? (splitters[tid] >> lo) : 0ull;
+  for (unsigned j = tid; j < nb; j += 256) {
+    cnt[j] = 0u;
+    spl[j] = j ? (splitters[j] >> lo) : 0ull;
+  }
   __syncthreads();
   const double ext0 = __longlong_as_double(static_cast<long long>(*extent_bits));
   const size_t tile = size_t(blockIdx.x) * (256 * ENC_ITEMS);
@@ -448,11 +456,10 @@ __global__ void __launch_bounds__(256) encode_bucket_kernel(const double4* __res
   bool keep[ENC_ITEMS];
 #pragma unroll
   for (int e = 0; e < ENC_ITEMS; ++e) {
-    // bucket = number of splitters <= key >> lo, minus one (spl[0] = 0): 8-step search, no divergence
+    // bucket = number of splitters <= key >> lo, minus one (spl[0] = 0): log2(nb)-step search, no divergence
     const uint64_t kk = k[e] >> lo;
     unsigned b = 0;
-#pragma unroll
-    for (int step = 128; step > 0; step >>= 1)
+    for (unsigned step = nb >> 1; step > 0; step >>= 1)
       if (spl[b + step] <= kk) b += step;
     d[e] = b;
     const size_t i = tile + size_t(e) * 256 + tid;
@@ -460,9 +467,9 @@ __global__ void __launch_bounds__(256) encode_bucket_kernel(const double4* __res
     r[e] = keep[e] ? atomicAdd(&cnt[b], 1u) : 0u;
   }
   __syncthreads();
-  {
-    const unsigned c = cnt[tid];
-    if (c) gbase[tid] = atomicAdd(&cursor[tid], c);
+  for (unsigned j = tid; j < nb; j += 256) {
+    const unsigned c = cnt[j];
+    if (c) gbase[j] = atomicAdd(&cursor[j], c);
   }
   __syncthreads();
 #pragma unroll
@@ -479,7 +486,7 @@ __global__ void __launch_bounds__(256) encode_bucket_kernel(const double4* __res
 }
 
 inline size_t sort_local_smem(unsigned cap) {
-  return size_t(cap) * 12 + (size_t(1) << LOCAL_BIN_BITS) * 4 + 32 * 4 + 16;
+  return size_t(cap) * 12 + (size_t(1) << LOCAL_BIN_BITS) * 4 + 32 * 4 + 32;  // ... + seg[4] + key range (2 x u64)
 }
 
 // The first RITEMS * NT elements of the bucket stay in registers between the counting and the
@@ -491,7 +498,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) sort_local_kernel(
     uint32_t* __restrict__ vals,
     const double4* __restrict__ pos, double4* __restrict__ spos, unsigned* __restrict__ bad,
     unsigned* __restrict__ stat_max, uint32_t* __restrict__ n_out /* sharded build: bodies sorted in all, capacity */,
-    uint32_t n_cap) {
+    uint32_t n_cap, unsigned nb /* buckets = gridDim.x <= NT */) {
   pb_pdl_sync();
   static_assert(NT >= 256 && NT % 32 == 0 && (1 << LOCAL_BIN_BITS) % NT == 0, "scan layout");
   constexpr int NBINS = 1 << LOCAL_BIN_BITS, BPT = NBINS / NT;  // bins per thread in the scan
@@ -503,11 +510,11 @@ __global__ void __launch_bounds__(NT, 1024 / NT) sort_local_kernel(
   unsigned* seg = wsum + 32;     // start, count of this bucket, largest bin, (sharded build) total of all buckets
   const int tid = threadIdx.x;
   {
-    const unsigned c = tid < 256 ? cursor[tid] : 0u;
+    const unsigned c = unsigned(tid) < nb ? cursor[tid] : 0u;
     const unsigned ex = block_exclusive_scan_nt<NT>(c, wsum);
     if (tid == int(blockIdx.x)) { seg[0] = ex; seg[1] = c; }
     if (tid == 0) seg[2] = 0u;
-    if (n_out && tid == 255) {
+    if (n_out && unsigned(tid) == nb - 1u) {
       seg[3] = ex + c;
       if (blockIdx.x == 0) {
         *n_out = min(ex + c, n_cap);  // (the later kernels never index past the capacity)
@@ -527,33 +534,54 @@ __global__ void __launch_bounds__(NT, 1024 / NT) sort_local_kernel(
     if (tid == 0) *bad = 1u;
     return;
   }
-  // bins: (key >> lo) - bucket base, scaled so that the bucket's key range at the previous evaluation
-  // covers the bins, clamped at both ends (the first and the last bucket are open-ended, and keys
-  // drift): any non-decreasing map keeps the result exact
-  const uint64_t kbase = splitters[blockIdx.x] >> lo;
-  const uint64_t ktop = ((splitters[blockIdx.x + 1u] - 1ull) >> lo) + 1ull;  // splitters[256] = largest key + 1
-  const uint64_t span = ktop > kbase ? ktop - kbase : 1ull;
-  const int span_bits = 64 - __clzll(static_cast<long long>(span - 1ull) | 1ll);
-  const int bshift = span_bits > LOCAL_BIN_BITS ? span_bits - LOCAL_BIN_BITS : 0;
-  constexpr uint64_t bmax = (1u << LOCAL_BIN_BITS) - 1u;
-  auto bin_of = [&](uint64_t key) {
-    const uint64_t kk = key >> lo;
-    const uint64_t rel = kk > kbase ? (kk - kbase) >> bshift : 0ull;
-    return unsigned(rel < bmax ? rel : bmax);
-  };
   for (int j = tid; j < NBINS; j += NT) bins[j] = 0u;
   const uint64_t* gk = bkey + size_t(blockIdx.x) * cap;
   const uint32_t* gv = bidx + size_t(blockIdx.x) * cap;
   uint64_t k[RITEMS];
   uint32_t v[RITEMS];
+  uint64_t kmin = ~0ull, kmax = 0ull;
 #pragma unroll
   for (int i = 0; i < RITEMS; ++i) {
     const unsigned p = unsigned(i) * NT + tid;
     const bool ok = p < cnt;
     k[i] = ok ? gk[p] : 0ull;
     v[i] = ok ? gv[p] : 0u;
+    if (ok) { kmin = min(kmin, k[i]); kmax = max(kmax, k[i]); }
   }
-  __syncthreads();
+  for (unsigned p = unsigned(RITEMS) * NT + tid; p < cnt; p += NT) {
+    const uint64_t key = gk[p];
+    kmin = min(kmin, key);
+    kmax = max(kmax, key);
+  }
+  // bins: (key >> lo) - base, scaled so that the key range the bucket's bodies ACTUALLY span covers the bins
+  // (not the range between its splitters: that may reach across key space nothing lives in, and the bodies
+  // would crowd a few bins): any non-decreasing map keeps the result exact
+  {
+    unsigned long long* krange = reinterpret_cast<unsigned long long*>(seg + 4);  // [min, max], 8-byte aligned
+    if (tid == 0) { krange[0] = ~0ull; krange[1] = 0ull; }
+    __syncthreads();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      kmin = min(kmin, __shfl_xor_sync(FULL, kmin, o));
+      kmax = max(kmax, __shfl_xor_sync(FULL, kmax, o));
+    }
+    if ((tid & 31) == 0) {
+      atomicMin(&krange[0], static_cast<unsigned long long>(kmin));
+      atomicMax(&krange[1], static_cast<unsigned long long>(kmax));
+    }
+    __syncthreads();
+    kmin = krange[0];
+    kmax = krange[1];
+  }
+  const uint64_t kbase = kmin >> lo;
+  const uint64_t span = (kmax >> lo) - kbase + 1ull;
+  const int span_bits = 64 - __clzll(static_cast<long long>(span - 1ull) | 1ll);
+  const int bshift = span_bits > LOCAL_BIN_BITS ? span_bits - LOCAL_BIN_BITS : 0;
+  constexpr uint64_t bmax = (1u << LOCAL_BIN_BITS) - 1u;
+  auto bin_of = [&](uint64_t key) {
+    const uint64_t rel = ((key >> lo) - kbase) >> bshift;
+    return unsigned(rel < bmax ? rel : bmax);
+  };
 #pragma unroll
   for (int i = 0; i < RITEMS; ++i)
     if (unsigned(i) * NT + tid < cnt) atomicAdd(&bins[bin_of(k[i])], 1u);
@@ -579,12 +607,6 @@ __global__ void __launch_bounds__(NT, 1024 / NT) sort_local_kernel(
   }
   if (seg[2] > LOCAL_BIN_LIMIT) {  // too many bodies agree on the bin bits: leave it to the global sort
     if (tid == 0) {
-#ifdef PB200_DEBUG_SKEW
-      unsigned bmaxcnt = 0, bwhere = 0;
-      printf("[skew] bucket %u cnt %u maxbin %u kbase %llx ktop %llx span_bits %d bshift %d first %llx last %llx\n", blockIdx.x, cnt, seg[2],
-             (unsigned long long)kbase, (unsigned long long)ktop, span_bits, bshift, (unsigned long long)gk[0], (unsigned long long)gk[cnt - 1]);
-      (void)bmaxcnt; (void)bwhere;
-#endif
       *bad = 1u;
       atomicMax(stat_max, LOCAL_SKEWED);
     }
@@ -627,25 +649,24 @@ __global__ void __launch_bounds__(NT, 1024 / NT) sort_local_kernel(
 // splitters for the NEXT evaluation's bucket sort: out[0] = smallest key, out[1..255] = the 1/256
 // quantiles of the sorted keys, out[256] = largest key + 1; forced non-decreasing (whatever the
 // state of `sorted`, e.g. after a build that was abandoned)
-constexpr int SPLITTER_STRIDE = 264;  // u64 words per splitter set (257 used)
+constexpr int SPLITTER_STRIDE = MAX_BUCKETS + 8;  // u64 words per splitter set (nb + 1 used)
 
 __device__ __forceinline__ void splitter_block(const uint64_t* __restrict__ sorted, size_t n,
-                                               uint64_t* __restrict__ out /*[257]*/) {
-  __shared__ uint64_t v[257];
-  const int t = threadIdx.x;
-  v[t] = n ? sorted[(size_t(t) * n) >> 8] : 0ull;
-  if (t == 0) v[256] = n ? sorted[n - 1] + 1ull : 0ull;
+                                               uint64_t* __restrict__ out /*[nb + 1]*/, unsigned nb) {
+  __shared__ uint64_t v[MAX_BUCKETS + 1];
+  const unsigned t = threadIdx.x;
+  for (unsigned j = t; j < nb; j += 256) v[j] = n ? sorted[(size_t(j) * n) / nb] : 0ull;
+  if (t == 0) v[nb] = n ? sorted[n - 1] + 1ull : 0ull;
   __syncthreads();
   if (t == 0) {
     uint64_t run = 0;
-    for (int j = 0; j <= 256; ++j) {
+    for (unsigned j = 0; j <= nb; ++j) {
       run = v[j] > run ? v[j] : run;
       v[j] = run;
     }
   }
   __syncthreads();
-  out[t] = v[t];
-  if (t == 0) out[256] = v[256];
+  for (unsigned j = t; j <= nb; j += 256) out[j] = v[j];
 }
 
 // second level of the range-minimum tables (see NsvTables below): block minima -> tables inside
@@ -678,6 +699,7 @@ struct ScanSide {
   uint8_t* t3;
   const uint64_t* sorted;     // CTA nsuper: splitter_block
   uint64_t* spl_out;
+  unsigned nb;                // buckets the next evaluation's bucket sort will use
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -705,7 +727,7 @@ __global__ void __launch_bounds__(256) scan_lookback_kernel(const uint32_t* __re
       const unsigned job = tile - tiles;
       const size_t nblocks = (n + 255) / 256, nsuper = (nblocks + 255) / 256;
       if (job < nsuper) nsv_level2_block(job, side.t2, side.b_pad, nblocks, side.t3);
-      else if (job == nsuper) splitter_block(side.sorted, n, side.spl_out);
+      else if (job == nsuper) splitter_block(side.sorted, n, side.spl_out, side.nb);
     }
     return;
   }
@@ -1964,11 +1986,10 @@ __global__ void __launch_bounds__(256) walk_sharded_kernel(const double4* __rest
 template <int DIM>
 __global__ void __launch_bounds__(256) shard_plan_kernel(const uint64_t* __restrict__ sorted, size_t n, int rank,
                                                          int world, uint64_t* __restrict__ cuts /* [world + 1] */,
-                                                         uint64_t* __restrict__ spl_out /* [257] */) {
+                                                         uint64_t* __restrict__ spl_out /* [nb + 1] */, unsigned nb) {
   constexpr int shift = DIM * (TreeDim<DIM>::LM - TopTree<DIM>::K);
   __shared__ uint64_t s_cut[16];
   __shared__ size_t s_range[2];
-  __shared__ uint64_t v[257];
   const int t = threadIdx.x;
   if (t <= world) {
     uint64_t cut = 0ull;
@@ -1988,20 +2009,7 @@ __global__ void __launch_bounds__(256) shard_plan_kernel(const uint64_t* __restr
     s_range[t] = lo;
   }
   __syncthreads();
-  const size_t b = s_range[0], m = s_range[1] - s_range[0];
-  v[t] = m ? sorted[b + ((size_t(t) * m) >> 8)] : 0ull;
-  if (t == 0) v[256] = m ? sorted[b + m - 1] + 1ull : 0ull;
-  __syncthreads();
-  if (t == 0) {
-    uint64_t run = 0;
-    for (int j = 0; j <= 256; ++j) {
-      run = v[j] > run ? v[j] : run;
-      v[j] = run;
-    }
-  }
-  __syncthreads();
-  spl_out[t] = v[t];
-  if (t == 0) spl_out[256] = v[256];
+  splitter_block(sorted + s_range[0], s_range[1] - s_range[0], spl_out, nb);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -2423,6 +2431,7 @@ struct SortBuffers {
   SortPlan plan;   // global LSD passes (none in the bucket modes)
   int mode;        // 0: global LSD passes, 1 / 2 / 3: bucket sort with 4608 / 8192 / 16384-key buckets
   int lo, key_bits;
+  unsigned nb;     // buckets in the bucket modes (256 / 512 / 1024)
   unsigned cap;    // bucket capacity in the bucket modes
   unsigned tiles;
   int items;
@@ -2443,7 +2452,22 @@ inline SortPlan even_plan(int lo, int total) {
 
 // plans the sort of key bits [lo, key_bits) and clears histograms / look-back state
 constexpr size_t SORT_HEAD_WORDS = SORT_HIST_SLOTS * 256 + SORT_MAX_PASSES + 8;
-cudaError_t sort_prepare(GravityWorkspace& ws, size_t n, int key_bits, int lo, int mode, cudaStream_t st,
+// Buckets and capacity for n bodies: the fewest buckets whose share (n / nb + 12 % headroom: bodies drift between
+// evaluations) fits a shared-memory tile, the smallest tile that takes it.  mode 0: too many bodies for 1024 tiles.
+struct BucketPlan {
+  unsigned nb;
+  int mode;
+};
+inline BucketPlan bucket_plan(size_t n) {
+  for (unsigned nb = 256; nb <= MAX_BUCKETS; nb *= 2) {
+    const size_t want = n / nb + n / (8 * size_t(nb)) + 64;
+    for (int m = 1; m <= 3; ++m)
+      if (want <= LOCAL_CAP[m] && (m >= 2 || nb <= 512)) return BucketPlan{nb, m};  // (mode 1: 512-thread CTAs scan <= 512 cursors)
+  }
+  return BucketPlan{256, 0};
+}
+
+cudaError_t sort_prepare(GravityWorkspace& ws, size_t n, int key_bits, int lo, int mode, unsigned nb, cudaStream_t st,
                          unsigned* head /* SORT_HEAD_WORDS zeroed words */, SortBuffers* sb) {
   // keys per thread, measured on B200: 8 wins at 1e5 bodies and from 4e6 up (more CTAs in flight),
   // 16 at 1e6 (one wave of 245 CTAs)
@@ -2452,6 +2476,7 @@ cudaError_t sort_prepare(GravityWorkspace& ws, size_t n, int key_bits, int lo, i
   sb->tiles = blocks_for(n, SORT_THREADS * sb->items);
   if (key_bits - lo < 8) mode = 0;
   sb->mode = mode;
+  sb->nb = nb;
   sb->lo = lo;
   sb->key_bits = key_bits;
   sb->cap = LOCAL_CAP[mode];
@@ -2472,8 +2497,8 @@ cudaError_t sort_prepare(GravityWorkspace& ws, size_t n, int key_bits, int lo, i
   if (ws.sticky.p) sb->err_flag = ws.sticky.as<unsigned>() + 2;  // survives until the next host check
   ws.sort_err_flag = sb->err_flag;
   if (mode != 0) {
-    PB_PASS(ws.bucket_key.ensure(size_t(256) * sb->cap * 8));
-    PB_PASS(ws.bucket_idx.ensure(size_t(256) * sb->cap * 4));
+    PB_PASS(ws.bucket_key.ensure(size_t(nb) * sb->cap * 8));
+    PB_PASS(ws.bucket_idx.ensure(size_t(nb) * sb->cap * 4));
   }
   if (!ws.splitters.p) {
     PB_PASS(ws.splitters.ensure(2 * SPLITTER_STRIDE * 8));
@@ -2484,12 +2509,7 @@ cudaError_t sort_prepare(GravityWorkspace& ws, size_t n, int key_bits, int lo, i
 
 // keys -> sorted keys + permutation (ws.sorted_key / ws.perm) + sorted {x,y,z,m} (ws.spos64).
 // `bad` is the build's "keys not ordered" flag.
-inline int shard_sort_mode(size_t n_cap) {
-  const size_t want = n_cap / 256 + n_cap / 2048 + 64;
-  for (int m = 1; m <= 3; ++m)
-    if (want <= LOCAL_CAP[m]) return m;
-  return 0;
-}
+inline int shard_sort_mode(size_t n_cap) { return bucket_plan(n_cap).mode; }
 
 // n: every body of ws.pos64.  sh != nullptr: only the bodies in this rank's key range are kept (bucket forms only)
 template <int DIM>
@@ -2507,7 +2527,7 @@ cudaError_t encode_and_sort(GravityWorkspace& ws, size_t n, const SortBuffers& s
   if (sb.mode != 0) {
     PB_LAUNCH(ls, st, "encode_bucket_kernel",
               pb_launch_pdl(encode_bucket_kernel<DIM>, dim3(blocks_for(n, 256 * ENC_ITEMS)), dim3(256), 0, st, 
-                  ws.pos64, n, ws.extent_cur, spl_in, sb.lo, ws.bucket_key.as<uint64_t>(),
+                  ws.pos64, n, ws.extent_cur, spl_in, sb.nb, sb.lo, ws.bucket_key.as<uint64_t>(),
                   ws.bucket_idx.as<uint32_t>(), sb.cap, sb.ghist, sh ? sh->cuts : nullptr));
     uint32_t* n_out = sh ? sh->n_local : nullptr;
     const uint32_t n_cap = sh ? uint32_t(sh->n_cap) : 0u;
@@ -2515,15 +2535,15 @@ cudaError_t encode_and_sort(GravityWorkspace& ws, size_t n, const SortBuffers& s
     if (sb.mode == 1) {
       PB_CUDA(cudaFuncSetAttribute(sort_local_kernel<512, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
       PB_LAUNCH(ls, st, "sort_local_kernel",
-                pb_launch_pdl(sort_local_kernel<512, 9>, dim3(256), dim3(512), smem, st, 
+                pb_launch_pdl(sort_local_kernel<512, 9>, dim3(sb.nb), dim3(512), smem, st, 
                     ws.bucket_key.as<uint64_t>(), ws.bucket_idx.as<uint32_t>(), sb.ghist, spl_in, sb.cap, sb.lo,
-                    sb.key_bits, k[0], v[0], ws.pos64, ws.spos64.as<double4>(), bad, stat_max, n_out, n_cap));
+                    sb.key_bits, k[0], v[0], ws.pos64, ws.spos64.as<double4>(), bad, stat_max, n_out, n_cap, sb.nb));
     } else {
       PB_CUDA(cudaFuncSetAttribute(sort_local_kernel<1024, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
       PB_LAUNCH(ls, st, "sort_local_kernel",
-                pb_launch_pdl(sort_local_kernel<1024, 8>, dim3(256), dim3(1024), smem, st, 
+                pb_launch_pdl(sort_local_kernel<1024, 8>, dim3(sb.nb), dim3(1024), smem, st, 
                     ws.bucket_key.as<uint64_t>(), ws.bucket_idx.as<uint32_t>(), sb.ghist, spl_in, sb.cap, sb.lo,
-                    sb.key_bits, k[0], v[0], ws.pos64, ws.spos64.as<double4>(), bad, stat_max, n_out, n_cap));
+                    sb.key_bits, k[0], v[0], ws.pos64, ws.spos64.as<double4>(), bad, stat_max, n_out, n_cap, sb.nb));
     }
     ws.sorted_key = k[0];
     ws.perm = v[0];
@@ -2611,7 +2631,17 @@ cudaError_t tree_build(GravityWorkspace& ws, const ShardBuild* sh, cudaStream_t 
   }
   ws.extent_cur = extent;
   SortBuffers sb;
-  PB_PASS(sort_prepare(ws, n, key_bits, lo, sh ? shard_sort_mode(n) : ws.sort_mode, st, sort_head, &sb));
+  const BucketPlan bp = bucket_plan(n);
+  int mode = sh ? bp.mode : (bp.mode == 0 ? 0 : ws.sort_mode);
+  // the splitter set this build reads must have been written for the same number of buckets
+  if (mode != 0 && ws.spl_nb[ws.splitter_cur] != bp.nb) {
+    if (sh) {
+      set_error("sharded build: no splitters for %u buckets (gravity_shard_plan first)", bp.nb);
+      return cudaErrorInvalidValue;
+    }
+    mode = 0;
+  }
+  PB_PASS(sort_prepare(ws, n, key_bits, lo, mode, bp.nb, st, sort_head, &sb));
   if (sh && sb.mode == 0) {
     set_error("sharded build: %zu bodies per rank exceed the bucket sort's capacity", n);
     return cudaErrorInvalidValue;
@@ -2628,7 +2658,8 @@ cudaError_t tree_build(GravityWorkspace& ws, const ShardBuild* sh, cudaStream_t 
                                        ws.tgt_flags.as<uint32_t>(), max_shared_plus1,
                                        lo > 0 ? (key_bits - lo) / DIM : TreeDim<DIM>::LM + 2,
                                        ws.nsv1.as<uint8_t>(), n_pad, ws.nsv2.as<uint8_t>()));
-  const ScanSide side{ws.nsv2.as<uint8_t>(), b_pad, nsv3, ws.sorted_key, spl_out};
+  const ScanSide side{ws.nsv2.as<uint8_t>(), b_pad, nsv3, ws.sorted_key, spl_out, bp.nb};
+  ws.spl_nb[ws.splitter_cur] = bp.nb;  // (encode_and_sort toggled splitter_cur: this is the set the scan's side job writes)
   PB_PASS(exclusive_scan_with_side(ws.tgt_flags.as<uint32_t>(), ws.cell_start.as<uint32_t>(), nref, n, scan_scratch, side, st, ls));
 
   // cell table capacity: grows when a previous evaluation reported more cells
@@ -2745,9 +2776,13 @@ cudaError_t direct_evaluate(GravityWorkspace& ws, size_t t0, size_t t1, float ea
     }
   }
   const unsigned tb = blocks_for(n_targets, DIRECT_THREADS * T);
+  // The source splits decide the order in which a target's partial sums are added, so they follow from the
+  // number of SOURCES alone (as if every body were a target, 4 per thread): a run whose targets are sharded
+  // over several GPUs then adds in the same order - and gives the same bits - as one GPU evaluating them all.
   unsigned splits = 1;
   const unsigned max_splits = blocks_for(n, DIRECT_TILE);
-  while (tb * splits < 148u * 2u && splits * 2 <= max_splits && splits < 64) splits *= 2;
+  const unsigned tb_all = blocks_for(n, DIRECT_THREADS * 4);
+  while (tb_all * splits < 148u * 2u && splits * 2 <= max_splits && splits < 64) splits *= 2;
   size_t per = (n + splits - 1) / splits;
   per = (per + DIRECT_TILE - 1) / DIRECT_TILE * DIRECT_TILE;
   splits = blocks_for(n, int(per));
@@ -2822,12 +2857,14 @@ cudaError_t gravity_shard_plan(GravityWorkspace& ws, cudaStream_t st, LaunchStat
   }
   // the splitter set the NEXT build reads (encode_and_sort toggles splitter_cur before it writes)
   uint64_t* spl = ws.splitters.as<uint64_t>() + SPLITTER_STRIDE * ws.splitter_cur;
+  const unsigned nb = bucket_plan(sh.n_cap).nb;
+  ws.spl_nb[ws.splitter_cur] = nb;
   if (ws.tree_dim == 2)
     PB_LAUNCH(ls, st, "shard_plan_kernel",
-              shard_plan_kernel<2><<<1, 256, 0, st>>>(ws.sorted_key, ws.n, sh.rank, sh.world, sh.cuts.as<uint64_t>(), spl));
+              shard_plan_kernel<2><<<1, 256, 0, st>>>(ws.sorted_key, ws.n, sh.rank, sh.world, sh.cuts.as<uint64_t>(), spl, nb));
   else
     PB_LAUNCH(ls, st, "shard_plan_kernel",
-              shard_plan_kernel<3><<<1, 256, 0, st>>>(ws.sorted_key, ws.n, sh.rank, sh.world, sh.cuts.as<uint64_t>(), spl));
+              shard_plan_kernel<3><<<1, 256, 0, st>>>(ws.sorted_key, ws.n, sh.rank, sh.world, sh.cuts.as<uint64_t>(), spl, nb));
   sh.planned = true;
   return cudaGetLastError();
 }
@@ -2974,13 +3011,10 @@ cudaError_t gravity_check(GravityWorkspace& ws, cudaStream_t st, TreeCheck* out)
   else if (ws.bucket_ban > 0) --ws.bucket_ban;
   // the splitters left by a verified build balance the buckets at ~n/256 bodies: pick the smallest
   // capacity with ~12 % headroom (bodies drift between evaluations)
-  const size_t want = ws.n / 256 + ws.n / 2048 + 64;
   if ((mode_env && !std::strcmp(mode_env, "lsd")) || ws.bucket_ban > 0 || out->overflow || out->sort_short || out->sort_error)
     ws.sort_mode = 0;
-  else if (want <= LOCAL_CAP[1]) ws.sort_mode = 1;
-  else if (want <= LOCAL_CAP[2]) ws.sort_mode = 2;
-  else if (want <= LOCAL_CAP[3]) ws.sort_mode = 3;
-  else ws.sort_mode = 0;
+  else
+    ws.sort_mode = bucket_plan(ws.n).mode;
   static const bool debug_check = std::getenv("PB200_DEBUG_CHECK") != nullptr;
   if (debug_check)
     std::fprintf(stderr, "[physim_b200] check: cells %u (cap %zu) deepest %d lo %d mode %d max_bucket %u overflow %d short %d "

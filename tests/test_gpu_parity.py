@@ -295,18 +295,21 @@ def test_bucket_sort_overflow_and_skew_fall_back(name):
         if forced == 1:
             assert st["sort_mode"] == 0, st                                 # it did fall back
         el.transform(gen.cube(30_000, seed=2))
-    # 100 bodies on one spot (one key): a bin of the counting sort would hold them all
-    twins = gen.cube(20_000, seed=8)
-    twins["x"][:100], twins["y"][:100], twins["z"][:100] = 0.3, -0.2, 0.6
-    o = ob.CellTable(DIM[name], twins)
-    el = api.TransformElement(name, theta=1.0, e=0.5)
-    el.transform(twins)
-    acc = el.transform(twins)                                # bucket sort attempted, abandoned
-    t = el.debug_tree()
-    for k in TREE_KEYS:
-        assert np.array_equal(t[k], getattr(o, k)), k
-    assert el.stats()["sort_mode"] == 0
-    assert_acc_parity(acc, ob.transform(name, twins, 1.0, 0.5))
+    # bodies on (100) or within 1e-5 of (1500) one spot share a bin of the counting sort: 100 are ranked inside
+    # the bin, 1500 are more than a bin may hold and the build goes to the global passes
+    for crowd, want_mode in ((100, 1), (1500, 0)):
+        twins = gen.cube(20_000, seed=8)
+        jit = np.random.default_rng(crowd).random((crowd, 3)) * (0.0 if crowd == 100 else 1e-5)
+        twins["x"][:crowd], twins["y"][:crowd], twins["z"][:crowd] = 0.3 + jit[:, 0], -0.2 + jit[:, 1], 0.6 + jit[:, 2]
+        o = ob.CellTable(DIM[name], twins)
+        el = api.TransformElement(name, theta=1.0, e=0.5)
+        el.transform(twins)
+        acc = el.transform(twins)                            # bucket sort attempted (abandoned for the 1500)
+        t = el.debug_tree()
+        for k in TREE_KEYS:
+            assert np.array_equal(t[k], getattr(o, k)), (k, crowd)
+        assert el.stats()["sort_mode"] == want_mode, crowd
+        assert_acc_parity(acc, ob.transform(name, twins, 1.0, 0.5))
 
 
 def plummer_like(n, seed):
