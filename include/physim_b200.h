@@ -238,6 +238,11 @@ int pb200_integrator_step_fused(void *g, void *transform, const Entity *entities
 void *pb200_sim_create(int kind, double theta, double e, double dt, int rank, int world);
 void pb200_sim_destroy(void *sim);
 int pb200_sim_upload(void *sim, const Entity *state, size_t n);
+/* Instead of pb200_sim_upload: `cube n seed spin mass size centre` (astro/src/initialisers.rs:82-106 over
+ * Entity::random, physim-core/src/lib.rs:115-128) generated in place on the device from the reference's
+ * ChaCha8 stream; radius 0.02, id 0, fixed false.  centre3 NULL = origin. */
+int pb200_sim_generate_cube(void *sim, size_t n, uint64_t seed, double spin, double mass, double size,
+                            const double *centre3);
 /* Run `steps` steps of the owned slice back to back.  With world > 1 no positions are exchanged:
  * use pb200_sim_step_local + an all-gather for a real multi-rank run (this form serves sampled
  * timing of a target slice). */
@@ -293,6 +298,8 @@ void *pb200_msim_create(int kind, double theta, double e, double dt, int world, 
 void pb200_msim_destroy(void *msim);
 /* every process passes the whole state (all n bodies) */
 int pb200_msim_upload(void *msim, const Entity *state, size_t n);
+int pb200_msim_generate_cube(void *msim, size_t n, uint64_t seed, double spin, double mass, double size,
+                             const double *centre3);
 int pb200_msim_run(void *msim, size_t steps);
 /* *ms = device time of the steps: CUDA events on every local rank's stream, the maximum over them */
 int pb200_msim_run_timed(void *msim, size_t steps, float *ms);

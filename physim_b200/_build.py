@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libphysim_b200.so")
-SOURCES = ["gravity.cu", "verlet.cu", "engine.cu", "multi.cu", "plugin_abi.cpp", "csvsink.cpp"]
+SOURCES = ["gravity.cu", "verlet.cu", "engine.cu", "multi.cu", "generate.cu", "plugin_abi.cpp", "csvsink.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -145,6 +145,8 @@ def lib():
     L.pb200_csv_format_f64.restype = sz
     L.pb200_csv_format_f64.argtypes = [dbl, C.c_char_p, sz]
     L.pb200_sim_run_csvsink.argtypes = [vp, sz, vp]
+    L.pb200_sim_generate_cube.argtypes = [vp, sz, C.c_uint64, dbl, dbl, dbl, vp]
+    L.pb200_msim_generate_cube.argtypes = [vp, sz, C.c_uint64, dbl, dbl, dbl, vp]
     L.pb200_comm_unique_id.argtypes = [vp]
     L.pb200_msim_create.restype = vp
     L.pb200_msim_create.argtypes = [i32, dbl, dbl, dbl, i32, i32, vp, vp, vp]
@@ -368,6 +370,13 @@ class Sim:
         if lib().pb200_sim_upload(self._s, _ptr(state), self.n) != 0:
             raise Pb200Error(last_error())
 
+    def generate_cube(self, n, seed=0, spin=0.0, mass=1.0, size=1.0, centre=(0.0, 0.0, 0.0)):
+        """`cube` initial conditions made on the device from the reference's ChaCha8 stream (no host array)."""
+        c = np.asarray(centre, dtype=np.float64)
+        self.n = int(n)
+        if lib().pb200_sim_generate_cube(self._s, self.n, int(seed), float(spin), float(mass), float(size), _ptr(c)) != 0:
+            raise Pb200Error(last_error())
+
     def run(self, steps):
         if lib().pb200_sim_run(self._s, int(steps)) != 0:
             raise Pb200Error(last_error())
@@ -491,6 +500,12 @@ class MultiSim:
         state = _state(state)
         self.n = len(state)
         if lib().pb200_msim_upload(self._m, _ptr(state), self.n) != 0:
+            raise Pb200Error(last_error())
+
+    def generate_cube(self, n, seed=0, spin=0.0, mass=1.0, size=1.0, centre=(0.0, 0.0, 0.0)):
+        c = np.asarray(centre, dtype=np.float64)
+        self.n = int(n)
+        if lib().pb200_msim_generate_cube(self._m, self.n, int(seed), float(spin), float(mass), float(size), _ptr(c)) != 0:
             raise Pb200Error(last_error())
 
     def run(self, steps):

@@ -368,6 +368,10 @@ cudaError_t rk4_stage(int stage, const double4* e_pos, const double4* e_vel, con
                       const double* acc64, size_t n, double dt, double4* out_pos, double4* out_vel,
                       double* out6, cudaStream_t stream, LaunchStats& ls);
 
+// `cube` initial conditions generated in place on the device (generate.cu)
+cudaError_t generate_cube(double4* pos, double4* vel, uint8_t* fixed, size_t n, uint64_t seed, double spin, double mass,
+                          double size, const double centre[3], cudaStream_t st, LaunchStats& ls);
+
 // fp32 FFMA probe
 cudaError_t probe_fp32(double* tflops);
 

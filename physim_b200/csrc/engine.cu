@@ -624,6 +624,38 @@ cudaError_t sim_upload(SimObj& s, const Entity* state, size_t n) {
   return cudaSuccess;
 }
 
+// the same handle state as sim_upload, with the bodies made on the device (generate.cu)
+cudaError_t sim_generate_cube(SimObj& s, size_t n, uint64_t seed, double spin, double mass, double size,
+                              const double centre[3]) {
+  PB_PASS(s.gpu.init(s.device));
+  cudaStream_t st = s.gpu.stream;
+  s.n = n;
+  s.slice = (n + size_t(s.world) - 1) / size_t(s.world);
+  s.t0 = std::min(n, s.slice * size_t(s.rank));
+  s.t1 = std::min(n, s.slice * size_t(s.rank + 1));
+  s.first = true;
+  s.checked = false;
+  s.vel_stale = false;
+  s.ext_ready = false;
+  s.ext_dirty = true;
+  s.ext_last_valid = false;
+  if (n == 0) return cudaSuccess;
+  PB_PASS(s.cur.ensure(s.slice * size_t(s.world) * sizeof(double4)));
+  PB_PASS(s.prev.ensure(n * sizeof(double4)));
+  PB_PASS(s.vel.ensure(n * sizeof(double4)));
+  PB_PASS(s.fixed.ensure(n));
+  PB_PASS(s.h_pos.ensure(n * sizeof(double4)));  // (read-out staging)
+  PB_PASS(s.h_vel.ensure(n * sizeof(double4)));
+  PB_PASS(generate_cube(s.cur.as<double4>(), s.vel.as<double4>(), s.fixed.as<uint8_t>(), n, seed, spin, mass, size,
+                        centre, st, s.ls));
+  PB_CUDA(cudaStreamSynchronize(st));
+  s.ws.pos64 = s.cur.as<double4>();
+  s.ws.fixed = s.fixed.as<uint8_t>();
+  s.ws.n = n;
+  s.ws.n_cells = 0;
+  return cudaSuccess;
+}
+
 // velocities of the current state, if the lean steps left them implicit
 cudaError_t sim_materialise_velocities(SimObj& s) {
   if (!s.vel_stale) return cudaSuccess;
@@ -1126,6 +1158,19 @@ int pb200_sim_upload(void* sim, const Entity* state, size_t n) {
   std::lock_guard<std::mutex> lk(s.mu);
   if (sim_upload(s, state, n) != cudaSuccess) {
     std::fprintf(stderr, "[physim_b200] sim upload failed: %s\n", g_error);
+    return -1;
+  }
+  return 0;
+}
+
+int pb200_sim_generate_cube(void* sim, size_t n, uint64_t seed, double spin, double mass, double size,
+                            const double* centre3) {
+  if (!sim) return -1;
+  auto& s = *static_cast<SimObj*>(sim);
+  std::lock_guard<std::mutex> lk(s.mu);
+  const double zero[3] = {0.0, 0.0, 0.0};
+  if (sim_generate_cube(s, n, seed, spin, mass, size, centre3 ? centre3 : zero) != cudaSuccess) {
+    std::fprintf(stderr, "[physim_b200] sim generate failed: %s\n", g_error);
     return -1;
   }
   return 0;

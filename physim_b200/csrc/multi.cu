@@ -635,6 +635,46 @@ int pb200_msim_upload(void* h, const Entity* state, size_t n) {
   return 0;
 }
 
+/* `cube n seed spin mass size centre` (astro/src/initialisers.rs:82-106) generated on every rank's device */
+int pb200_msim_generate_cube(void* h, size_t n, uint64_t seed, double spin, double mass, double size,
+                             const double* centre3) {
+  if (!h) return -1;
+  auto& m = *static_cast<MultiSim*>(h);
+  std::lock_guard<std::mutex> lk(m.mu);
+  const double zero[3] = {0.0, 0.0, 0.0};
+  const double* centre = centre3 ? centre3 : zero;
+  m.n = n;
+  m.slice = (n + size_t(m.world) - 1) / size_t(m.world);
+  m.first = true;
+  m.checked = false;
+  m.shard_ok = true;
+  if (n == 0) return 0;
+  auto run = [&]() -> cudaError_t {
+    FOR_LOCAL(m, c) {
+      PB_PASS(c->cur.ensure(n * sizeof(double4)));
+      PB_PASS(c->prev.ensure(n * sizeof(double4)));
+      PB_PASS(c->vel.ensure(n * sizeof(double4)));
+      PB_PASS(c->fixed.ensure(n));
+      PB_PASS(generate_cube(c->cur.as<double4>(), c->vel.as<double4>(), c->fixed.as<uint8_t>(), n, seed, spin, mass,
+                            size, centre, c->stream, c->ls));
+      c->ws.pos64 = c->cur.as<double4>();
+      c->ws.fixed = c->fixed.as<uint8_t>();
+      c->ws.n = n;
+      c->ws.n_cells = 0;
+      c->ws.shard.planned = false;
+      c->vel_stale = false;
+      c->ext_ready = false;
+      c->ext_dirty = true;
+    }
+    return sync_all(m);
+  };
+  if (run() != cudaSuccess) {
+    std::fprintf(stderr, "[physim_b200] msim generate failed: %s\n", g_error);
+    return -1;
+  }
+  return 0;
+}
+
 int pb200_msim_run(void* h, size_t steps) {
   if (!h) return -1;
   auto& m = *static_cast<MultiSim*>(h);
@@ -682,6 +722,8 @@ int pb200_msim_download(void* h, Entity* state, size_t n) {
   auto run = [&]() -> cudaError_t {
     PB_PASS(materialise_velocities(m));
     PB_CUDA(cudaSetDevice(c->device));
+    PB_PASS(c->h_pos.ensure(n * sizeof(double4)));
+    PB_PASS(c->h_vel.ensure(n * sizeof(double4)));
     PB_CUDA(cudaMemcpyAsync(c->h_pos.p, c->cur.p, n * sizeof(double4), cudaMemcpyDeviceToHost, c->stream));
     PB_CUDA(cudaMemcpyAsync(c->h_vel.p, c->vel.p, n * sizeof(double4), cudaMemcpyDeviceToHost, c->stream));
     return sync_all(m);

@@ -295,11 +295,13 @@ def test_bucket_sort_overflow_and_skew_fall_back(name):
         if forced == 1:
             assert st["sort_mode"] == 0, st                                 # it did fall back
         el.transform(gen.cube(30_000, seed=2))
-    # bodies on (100) or within 1e-5 of (1500) one spot share a bin of the counting sort: 100 are ranked inside
-    # the bin, 1500 are more than a bin may hold and the build goes to the global passes
-    for crowd, want_mode in ((100, 1), (1500, 0)):
+    # Crowds around one spot.  100 coincident bodies (one merged unit) and 1500 within 1e-5 are sorted by the
+    # bucket sort: the bins follow the key range a bucket's bodies actually span, so a crowd spreads over them.
+    # 1500 bodies within 1e-7 share ONE 63-bit octree key (the key resolves extent * 2^-21 = 5e-7): more than a
+    # bin may hold, the build goes to the global passes.  (The 62-bit quadtree key resolves 5e-10: no crowding.)
+    for crowd, spread, want_mode in ((100, 0.0, 1), (1500, 1e-5, 1), (1500, 1e-7, 0 if name == "astro2" else 1)):
         twins = gen.cube(20_000, seed=8)
-        jit = np.random.default_rng(crowd).random((crowd, 3)) * (0.0 if crowd == 100 else 1e-5)
+        jit = np.random.default_rng(crowd).random((crowd, 3)) * spread
         twins["x"][:crowd], twins["y"][:crowd], twins["z"][:crowd] = 0.3 + jit[:, 0], -0.2 + jit[:, 1], 0.6 + jit[:, 2]
         o = ob.CellTable(DIM[name], twins)
         el = api.TransformElement(name, theta=1.0, e=0.5)
@@ -307,8 +309,8 @@ def test_bucket_sort_overflow_and_skew_fall_back(name):
         acc = el.transform(twins)                            # bucket sort attempted (abandoned for the 1500)
         t = el.debug_tree()
         for k in TREE_KEYS:
-            assert np.array_equal(t[k], getattr(o, k)), (k, crowd)
-        assert el.stats()["sort_mode"] == want_mode, crowd
+            assert np.array_equal(t[k], getattr(o, k)), (k, crowd, spread)
+        assert el.stats()["sort_mode"] == want_mode, (crowd, spread)
         assert_acc_parity(acc, ob.transform(name, twins, 1.0, 0.5))
 
 
