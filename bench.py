@@ -33,6 +33,16 @@ if ROOT not in sys.path:
 
 import numpy as np  # noqa: E402
 
+# stdout carries exactly ONE JSON line: everything else written to fd 1 by this process or by native libraries
+# (NCCL prints its version banner there) is sent to stderr
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 WORKLOADS = {
     # name: (generator args, element, theta, e, dt)
     "c3": dict(n=1_000_000, element="astro", theta=1.3, e=1.0, dt=1e-6,
@@ -184,17 +194,7 @@ def run_reference(args, w):
         "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
-
-
-def cuda_tensor_view(ptr, nbytes):
-    """torch view (float64) of raw device memory, for torch.distributed collectives."""
-    import torch
-
-    class Raw:
-        __cuda_array_interface__ = {"shape": (nbytes // 8,), "typestr": "<f8", "data": (ptr, False),
-                                    "version": 2}
-    return torch.as_tensor(Raw(), device="cuda")
+    emit(line)
 
 
 def run_ours(args, w):
@@ -345,7 +345,7 @@ def run_ours(args, w):
                        "d2h_bytes_per_step": 0,
                        "note": "multi-rank run: state stays in HBM; the host-boundary number is the N=1 line's"}
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if dist:
         dist.barrier()
         dist.destroy_process_group()

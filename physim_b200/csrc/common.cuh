@@ -97,24 +97,30 @@ struct PinnedBuf {
 };
 
 // ---- sharded Barnes-Hut: what one rank keeps besides its GravityWorkspace (see gravity.cu, "Sharded Barnes-Hut") ----
-struct ShardPeers {  // every rank's cell table as this device sees it (own rank: local pointers)
-  const void* centre_ext[8];
+struct ShardPeers {  // every rank's buffers as this device sees them (own rank: local pointers; others: NVLink peer mappings)
+  const void* centre_ext[8];  // cell tables, read by the walk
   const void* com[8];
   const void* skip[8];
-  uint32_t capacity;
+  void* top_info[8];          // dense top tree + per-rank counts, exchange buffer, flags: WRITTEN by the peers
+  void* top_com[8];
+  void* top_meta[8];
+  void* xacc[8];
+  void* flags[8];
+  uint32_t capacity;          // cells (the smallest table of any rank)
 };
 struct ShardState {
   int rank = 0, world = 1;
   bool planned = false;   // cuts and splitters for a sharded build exist (left by gravity_shard_plan / the last sharded step)
   size_t n_cap = 0;       // capacity of the per-rank arrays in bodies (the same on every rank)
+  uint32_t epoch = 0;     // sharded steps taken: the value the ranks signal each other with (same sequence on every rank)
   DevBuf cuts;            // u64[world + 1]: key cuts of the NEXT build
   DevBuf n_local;         // u32: bodies in this rank's range (left by the sort of the current build)
   DevBuf slot_cell;       // u32[level-K prefixes]
-  DevBuf top_all;         // [world] x (prefixes + 1) 48-byte records: the all-gather buffer of step 2
-  DevBuf top_ce, top_com, top_info, top_meta;  // dense top tree (levels 0..K) + per-rank counts
-  DevBuf xacc;            // [world] x { float4 acc[n_cap], u32 perm[n_cap] }: the all-gather buffer of step 5
+  DevBuf top_ce, top_com, top_info;  // dense top tree (levels 0..K); its level-K entries are written by their owners
+  DevBuf top_meta;        // u32: per-rank bodies / cells / abandoned-build flags, double-buffered by epoch parity
+  DevBuf xacc;            // [world] x { float4 acc[n_cap], u32 perm[n_cap] }: block r written by rank r's walk
+  DevBuf flags;           // u32: [0..7] "export of epoch e done" per rank, [8..15] "walk done", [16..18] local counters / timeout
   ShardPeers peers;
-  size_t top_block_bytes() const;   // bytes one rank contributes to top_all
   size_t xacc_block_bytes() const { return n_cap * 20; }
   void release();
 };
@@ -263,6 +269,25 @@ __device__ __forceinline__ void pb_pdl_sync() {
 }
 #endif
 
+#ifdef __CUDACC__
+// Cross-GPU signalling of the sharded step: flags are u32 epochs in the CONSUMER's memory, stored by the producers
+// through peer mappings.  Bounded spin: a rank that never signals (a crashed peer) leaves flags[18] set and the
+// wait returns - the results are then garbage and the host's next check reports the error instead of a hung GPU.
+constexpr int SHARD_FLAG_EXPORT = 0, SHARD_FLAG_WALK = 8, SHARD_CNT_EXPORT = 16, SHARD_CNT_WALK = 17, SHARD_TIMEOUT = 18;
+__device__ __forceinline__ void shard_wait_flag(uint32_t* flags, int slot, uint32_t epoch) {
+  volatile uint32_t* f = flags + slot;
+  unsigned spins = 0;
+  while (int32_t(*f - epoch) < 0) {
+    __nanosleep(64);
+    if (++spins > (1u << 25)) {  // ~ seconds
+      flags[SHARD_TIMEOUT] = 1u;
+      break;
+    }
+  }
+  __threadfence_system();
+}
+#endif
+
 inline bool pb_pdl_enabled() {
   static const bool v = !(std::getenv("PB200_PDL") && std::atoi(std::getenv("PB200_PDL")) == 0);
   return v;
@@ -298,13 +323,15 @@ inline cudaError_t pb_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block
 // small; without it the caller must poll gravity_cell_total() before trusting the result.
 cudaError_t gravity_evaluate(GravityWorkspace& ws, const GravityParams& prm, size_t t0, size_t t1,
                              cudaStream_t stream, LaunchStats& ls, bool host_check = true);
-// Sharded Barnes-Hut, one call per phase; the caller runs the two collectives in between on the same stream:
+// Sharded Barnes-Hut, one call per phase.  The exchanges are peer-memory stores issued by the kernels
+// themselves (no collective call per step): every phase ends by signalling the step's epoch to all ranks, the
+// consumer kernels wait for every rank's signal.
 //   gravity_shard_plan    after a full build on every rank (gravity_evaluate over all bodies): first cuts + splitters
-//   gravity_shard_build   tree of this rank's key range + its level-K records into block `rank` of shard.top_all
-//                         -> all-gather shard.top_all (top_block_bytes() per rank, in place)
-//   gravity_shard_walk    top tree, walk of this rank's bodies -> accelerations (sorted order) + permutation in
-//                         block `rank` of shard.xacc           -> all-gather shard.xacc (xacc_block_bytes() per rank)
-// shard.peers must hold every rank's c_centre_ext / c_com / c_skip (peer-mapped) before gravity_shard_walk.
+//   gravity_shard_build   tree of this rank's key range; its level-K records stored into EVERY rank's dense top tree
+//   gravity_shard_walk    cells above level K, walk of this rank's bodies; accelerations (sorted order) and the
+//                         permutation stored into block `rank` of EVERY rank's shard.xacc
+// shard.peers must hold every rank's buffers (peer-mapped) before gravity_shard_build; shard.epoch is advanced
+// by gravity_shard_build.
 cudaError_t gravity_shard_setup(GravityWorkspace& ws, int kind, int rank, int world, size_t n);
 bool gravity_shard_fits(const GravityWorkspace& ws);  // the per-rank capacity is within what the sharded build's sort takes
 cudaError_t gravity_shard_plan(GravityWorkspace& ws, cudaStream_t stream, LaunchStats& ls);
@@ -351,10 +378,11 @@ cudaError_t verlet_update_lean(const double4* cur, double4* prev_inout, const fl
                                unsigned long long* extent_last, cudaStream_t st, LaunchStats& ls);
 // the same step on every rank of a sharded run: body perm[r][j] takes acc[r][j] for j < n_locals[r] (the gathered
 // blocks of ShardState::xacc, n_cap records each)
+// Waits until every rank's walk of `epoch` has signalled (flags[8 + r] >= epoch).
 cudaError_t verlet_update_lean_sharded(const double4* cur, double4* prev_inout, const void* xacc, size_t n_cap,
-                                       int world, const uint32_t* n_locals, double dt, unsigned long long* extent_out,
-                                       unsigned long long* extent_zero, unsigned long long* extent_last,
-                                       cudaStream_t st, LaunchStats& ls);
+                                       int world, const uint32_t* n_locals, uint32_t* flags, uint32_t epoch, double dt,
+                                       unsigned long long* extent_out, unsigned long long* extent_zero,
+                                       unsigned long long* extent_last, cudaStream_t st, LaunchStats& ls);
 cudaError_t verlet_velocity(const double4* cur, const double4* prev, double4* vel, size_t n, double dt,
                             cudaStream_t st, LaunchStats& ls);
 cudaError_t verlet_update(double4* cur, double4* prev, double4* vel, const float4* acc32,

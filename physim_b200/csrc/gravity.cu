@@ -1428,9 +1428,11 @@ __global__ void __launch_bounds__(256) kids_kernel(const uint32_t* __restrict__ 
                                                    uint32_t sub_cap) {
   pb_pdl_sync();
   constexpr uint32_t K = 1u << DIM;
-  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t total = cell_start[nref.get()];
-  const bool live = !(total > cells.capacity || *cells.bad) && p < total;
+  if (total > cells.capacity || *cells.bad) return;
+  // (grid-stride over the cells, whole warps together: the grid may be sized for fewer cells than exist)
+  for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; (p & ~31u) < total; p += gridDim.x * blockDim.x) {
+  const bool live = p < total;
   uint32_t cnt = 0, end = 0, lev = 0;
   if (live) {
     cnt = cells.count[p];
@@ -1439,7 +1441,7 @@ __global__ void __launch_bounds__(256) kids_kernel(const uint32_t* __restrict__ 
   }
   // open = left to the bottom-up pass by K6: more than `small` bodies, or above the top level (any size)
   const bool open = live && (cnt > cells.small || lev < cells.top_level) && end != p + 1u;
-  if (!__any_sync(FULL, open)) return;  // (most warps: nothing but finished cells)
+  if (!__any_sync(FULL, open)) continue;  // (most warps: nothing but finished cells)
   bool start = false;
   if (open) {
     uint32_t nk = 0, pre = 0;
@@ -1462,13 +1464,14 @@ __global__ void __launch_bounds__(256) kids_kernel(const uint32_t* __restrict__ 
   // the slowest walk; the order inside a list does not matter: every sum is taken by one thread, over
   // the children in pre-order)
   const unsigned who = __ballot_sync(FULL, start);
-  if (!who) return;
+  if (!who) continue;
   const unsigned lane = threadIdx.x & 31u, leader = unsigned(__ffs(who) - 1);
   const uint32_t l = (p >> 5) % READY_LISTS;
   uint32_t base = 0;
   if (lane == leader) base = atomicAdd(n_ready + l * READY_STRIDE, unsigned(__popc(who)));
   base = __shfl_sync(FULL, base, leader);
   if (start) ready_list[size_t(l) * sub_cap + base + __popc(who & ((1u << lane) - 1u))] = p;
+  }
 }
 
 template <int DIM>
@@ -1678,8 +1681,9 @@ __global__ void __launch_bounds__(256) walk_kernel(const double4* __restrict__ s
 // body's position (the integrator state is replicated) and
 //   1. keeps, sorts and builds the tree of the bodies whose keys fall in its own range (tree_build with a
 //      ShardBuild): its cell table is exact for every cell at level >= K of its range;
-//   2. publishes one TopSlotRec per level-K prefix it owns (top_export_kernel) - all ranks' records are
-//      all-gathered (a few hundred KB);
+//   2. stores one record per level-K prefix of its range into EVERY rank's dense top tree, through peer
+//      mappings over NVLink (top_export_kernel; the prefixes partition between the ranks, so the stores of all
+//      ranks together ARE the all-gather), and signals the step's epoch to every rank;
 //   3. rebuilds the cells ABOVE level K, redundantly and identically on every rank, from those records
 //      (top_build_kernel): counts, leaves, centres of mass in ascending digit order with ComSum - the
 //      operations the single-GPU build applies to the same cells, hence the same bits;
@@ -1687,151 +1691,122 @@ __global__ void __launch_bounds__(256) walk_kernel(const double4* __restrict__ s
 //      below an opened level-K cell, over the OWNER's cell table - through a peer pointer (NVLink P2P
 //      loads) when the owner is another rank.  The visiting order is the global pre-order, so the fp32
 //      sums are those of the single-GPU walk;
-//   5. all ranks' accelerations (in sorted order, with the permutation) are all-gathered and every rank
-//      advances the replicated state (verlet_lean_sharded_kernel).
+//   5. stores its accelerations (sorted order) and the permutation into its block of EVERY rank's exchange
+//      buffer from inside the walk kernel and signals; every rank then advances the replicated state
+//      (verlet_lean_sharded_kernel, which waits for all ranks' signals).  No collective call per step.
 // The cuts for the next step come for free: step 3 sees the level-K histogram of ALL bodies.
 // ---------------------------------------------------------------------------------------------
-struct TopSlotRec {   // 48 bytes; what a rank tells the others about one level-K prefix
-  double4 com;        // {X, Y, Z, M} of the deepest cell that holds exactly the prefix's bodies
-  uint32_t count;     // bodies with the prefix (0: none on this rank)
-  uint32_t units;     // 1: a single unit (a leaf, possibly above level K), 2: an internal level-K cell
-  uint32_t cell;      // index of that cell in the owner's table
-  uint32_t end;       // the owner's skip[cell]: one past the cell's subtree
+// Where a rank's kernels store what the other ranks need (own rank included: local pointers).
+struct PeerTargets {
+  uint4* top_info[8];
+  double4* top_com[8];
+  uint32_t* meta[8];
+  char* xacc[8];
+  uint32_t* flags[8];
+  int world, rank;
 };
-static_assert(sizeof(TopSlotRec) == 48, "TopSlotRec layout");
 
-// record SLOTS = the rank's header: count = bodies sorted, units = cells built, cell = build abandoned
+// meta layout (u32), double-buffered by the parity of the epoch (a rank one phase ahead already writes the next
+// step's counts while a slower rank's verlet still reads this step's):
+constexpr int META_STRIDE = 32, META_BODIES = 1, META_CELLS = 9, META_BAD = 17, META_ANY_BAD = 64;
+
+// End of a producer kernel: when the last CTA has passed (all peer stores of the grid performed), tell every
+// rank that this rank's phase of `epoch` is complete.  (threadFenceReduction pattern, system scope.)
+__device__ __forceinline__ void shard_signal(const PeerTargets& pt, int slot, int counter, uint32_t epoch) {
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t* mine = pt.flags[pt.rank];
+    const unsigned done = atomicAdd(mine + counter, 1u) + 1u;
+    if (done == gridDim.x * gridDim.y) {
+      mine[counter] = 0u;  // (the next launch of this phase is stream-ordered behind this one)
+      __threadfence_system();
+      for (int r = 0; r < pt.world; ++r) *reinterpret_cast<volatile uint32_t*>(pt.flags[r] + slot + pt.rank) = epoch;
+    }
+  }
+}
+
+// Step 2: one thread per level-K prefix.  The prefixes of this rank's key range - cuts[rank] .. cuts[rank+1],
+// every prefix belongs to exactly one rank - get their record (or "no body") in EVERY rank's dense top tree:
+//   info.x  units (0 none, 1 a single unit: a leaf, possibly above level K, 2 an internal level-K cell) | rank << 8
+//   info.y  index of that cell in this rank's table, info.z its skip link (end of its subtree), info.w bodies
+//   com     {X, Y, Z, M} of that cell
 template <int DIM>
 __global__ void __launch_bounds__(256) top_export_kernel(const uint32_t* __restrict__ slot_cell, NRef nref,
                                                          const uint32_t* __restrict__ cell_start, CellArrays cells,
-                                                         TopSlotRec* __restrict__ out) {
+                                                         const uint64_t* __restrict__ cuts, PeerTargets pt,
+                                                         uint32_t epoch) {
   pb_pdl_sync();
-  constexpr uint32_t S = TopTree<DIM>::SLOTS;
+  using TT = TopTree<DIM>;
+  constexpr uint32_t S = TT::SLOTS;
+  constexpr int shift = DIM * (TreeDim<DIM>::LM - TT::K);
   const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
   const size_t n = nref.get();
   const uint32_t total = cell_start[n];
   const bool bad = total > cells.capacity || *cells.bad;
-  if (q == S) {
-    TopSlotRec h;
-    h.com = make_double4(0.0, 0.0, 0.0, 0.0);
-    h.count = uint32_t(n);
-    h.units = total;
-    h.cell = bad ? 1u : 0u;
-    h.end = 0u;
-    out[S] = h;
+  const uint32_t q_lo = uint32_t(min(cuts[pt.rank] >> shift, uint64_t(S)));
+  const uint32_t q_hi = pt.rank + 1 == pt.world ? S : uint32_t(min(cuts[pt.rank + 1] >> shift, uint64_t(S)));
+  if (q == 0) {
+    const int base = int(epoch & 1u) * META_STRIDE;
+    for (int r = 0; r < pt.world; ++r) {
+      pt.meta[r][base + META_BODIES + pt.rank] = uint32_t(n);
+      pt.meta[r][base + META_CELLS + pt.rank] = total;
+      pt.meta[r][base + META_BAD + pt.rank] = bad ? 1u : 0u;
+    }
   }
-  if (q >= S) return;
-  TopSlotRec r;
-  r.com = make_double4(0.0, 0.0, 0.0, 0.0);
-  r.count = r.units = r.cell = r.end = 0u;
-  const uint32_t c1 = bad ? 0u : slot_cell[q];
-  if (c1 != 0u && c1 <= total) {
-    const uint32_t c = c1 - 1u;
-    r.com = cells.com[c];
-    r.count = cells.count[c];
-    r.end = cells.skip[c];
-    r.cell = c;
-    r.units = (r.end == c + 1u) ? 1u : 2u;
+  if (q >= q_lo && q < q_hi) {
+    uint4 inf = make_uint4(0u, 0u, 0u, 0u);
+    double4 com = make_double4(0.0, 0.0, 0.0, 0.0);
+    const uint32_t c1 = bad ? 0u : slot_cell[q];
+    if (c1 != 0u && c1 <= total) {
+      const uint32_t c = c1 - 1u;
+      com = cells.com[c];
+      const uint32_t end = cells.skip[c];
+      inf = make_uint4(((end == c + 1u) ? 1u : 2u) | (uint32_t(pt.rank) << 8), c, end, cells.count[c]);
+    }
+    for (int r = 0; r < pt.world; ++r) {
+      pt.top_info[r][TT::offset(TT::K) + q] = inf;
+      pt.top_com[r][TT::offset(TT::K) + q] = com;
+    }
   }
-  out[q] = r;
+  shard_signal(pt, SHARD_FLAG_EXPORT, SHARD_CNT_EXPORT, epoch);
 }
 
 // Dense top tree, levels 0..K (index TopTree::offset(level) + prefix), identical on every rank.
 struct TopView {
   double4* centre_ext;  // {cx, cy, cz, half-width}
   double4* com;         // {X, Y, Z, M}
-  uint4* info;          // x: units (0 none, 1 leaf, 2 internal) | owner rank << 8, y: cell, z: end (owner's table), w: bodies
-  uint32_t* meta;       // [0] some rank abandoned its build, [1 .. world] bodies per rank, [1 + world ..] cells per rank
+  uint4* info;          // see top_export_kernel
+  uint32_t* meta;       // see META_*
   uint64_t* cuts;       // [world + 1] key cuts for the NEXT build (balanced on this step's level-K histogram)
 };
 
+// Step 3 (one CTA): waits for every rank's records, then rebuilds the cells above level K from their children in
+// ascending digit order with ComSum - the single-GPU build's operations on the same cells.  Level K-1 reads the
+// level-K entries from global memory (one round of loads), the levels above live in shared memory.
 template <int DIM>
-__global__ void __launch_bounds__(1024) top_build_kernel(const TopSlotRec* __restrict__ all /* [world][SLOTS + 1] */,
-                                                         int world, size_t n_total,
+__global__ void __launch_bounds__(1024) top_build_kernel(int world, size_t n_total,
                                                          const unsigned long long* __restrict__ extent_bits,
-                                                         TopView top) {
+                                                         TopView top, uint32_t* flags, uint32_t epoch) {
   pb_pdl_sync();
   using TT = TopTree<DIM>;
   constexpr int K = TT::K, R = TT::R, LM = TreeDim<DIM>::LM;
-  constexpr uint32_t S = TT::SLOTS;
-  __shared__ unsigned s_cum[1024];  // running body counts (cuts)
+  constexpr uint32_t S = TT::SLOTS, ABOVE = TT::offset(K);  // cells above level K
+  extern __shared__ __align__(16) unsigned char top_smem[];
+  double4* s_com = reinterpret_cast<double4*>(top_smem);     // [ABOVE]
+  uint4* s_info = reinterpret_cast<uint4*>(s_com + ABOVE);   // [ABOVE]
+  __shared__ unsigned s_cum[1024];
   __shared__ unsigned s_wsum[32];
   const int tid = threadIdx.x;
+  if (tid < world) shard_wait_flag(flags, SHARD_FLAG_EXPORT + tid, epoch);
+  __syncthreads();
   const double ext0 = __longlong_as_double(static_cast<long long>(*extent_bits));
   if (tid == 0) {
-    unsigned bad = 0;
-    for (int r = 0; r < world; ++r) {
-      const TopSlotRec h = all[size_t(r) * (S + 1) + S];
-      bad |= h.cell;
-      top.meta[1 + r] = h.count;
-      top.meta[1 + world + r] = h.units;
-    }
-    top.meta[0] = bad;
+    unsigned bad = flags[SHARD_TIMEOUT];
+    for (int r = 0; r < world; ++r) bad |= top.meta[int(epoch & 1u) * META_STRIDE + META_BAD + r];
+    top.meta[META_ANY_BAD] = bad;
   }
-  // level K: the rank that holds the prefix (at most one does)
-  for (uint32_t q = tid; q < S; q += 1024) {
-    uint4 inf = make_uint4(0u, 0u, 0u, 0u);
-    double4 com = make_double4(0.0, 0.0, 0.0, 0.0);
-    for (int r = 0; r < world; ++r) {
-      const TopSlotRec rec = all[size_t(r) * (S + 1) + q];
-      if (rec.count != 0u && inf.w == 0u) {
-        inf = make_uint4(rec.units | (uint32_t(r) << 8), rec.cell, rec.end, rec.count);
-        com = rec.com;
-      }
-    }
-    top.info[TT::offset(K) + q] = inf;
-    top.com[TT::offset(K) + q] = com;
-  }
-  __syncthreads();
-  // levels K-1 .. 0 from their children, ascending digit order (= pre-order), ComSum
-  for (int l = K - 1; l >= 0; --l) {
-    const uint32_t cells_l = 1u << (DIM * l);
-    for (uint32_t p = tid; p < cells_l; p += 1024) {
-      uint32_t units = 0, bodies = 0;
-      uint4 only = make_uint4(0u, 0u, 0u, 0u);
-      double4 only_com = make_double4(0.0, 0.0, 0.0, 0.0);
-      ComSum sum;
-#pragma unroll
-      for (int d = 0; d < R; ++d) {
-        const uint32_t t = TT::offset(l + 1) + p * R + d;
-        const uint4 ci = top.info[t];
-        const uint32_t u = ci.x & 0xffu;
-        if (u == 0u) continue;
-        const double4 cc = top.com[t];
-        sum.add(cc);
-        units += u;  // (1 + anything >= 1 is already "internal")
-        bodies += ci.w;
-        only = ci;
-        only_com = cc;
-      }
-      uint4 inf = make_uint4(0u, 0u, 0u, 0u);
-      double4 com = make_double4(0.0, 0.0, 0.0, 0.0);
-      if (units == 1u) {  // one unit below: this cell is (or lies above) its leaf - the unit's own record
-        inf = only;
-        com = only_com;
-      } else if (units > 1u) {
-        // geometric centre for the massless case: replay the prefix digits (the arithmetic of cells_kernel)
-        double half = ext0, cx = 0.0, cy = 0.0, cz = 0.0;
-        for (int j = 0; j < l; ++j) {
-          const unsigned digit = (p >> (DIM * (l - 1 - j))) & unsigned(R - 1);
-          half *= 0.5;
-          cx += with_sign(half, !(digit & 1u));
-          cy += with_sign(half, !(digit & 2u));
-          if (DIM == 3) cz += with_sign(half, !(digit & 4u));
-        }
-        com = sum.finish(make_double4(cx, cy, cz, half));
-        inf = make_uint4(2u, 0u, 0u, bodies);
-      }
-      top.info[TT::offset(l) + p] = inf;
-      top.com[TT::offset(l) + p] = com;
-    }
-    __syncthreads();
-  }
-  // geometric centres / half-widths of every top cell
-  for (uint32_t t = tid; t < TT::CELLS; t += 1024) {
-    int l = 0;
-    while (l < K && TT::offset(l + 1) <= t) ++l;
-    const uint32_t p = t - TT::offset(l);
+  auto centre_of = [&](int l, uint32_t p) {  // the arithmetic of cells_kernel: digits of the prefix, root first
     double half = ext0, cx = 0.0, cy = 0.0, cz = 0.0;
     for (int j = 0; j < l; ++j) {
       const unsigned digit = (p >> (DIM * (l - 1 - j))) & unsigned(R - 1);
@@ -1840,14 +1815,68 @@ __global__ void __launch_bounds__(1024) top_build_kernel(const TopSlotRec* __res
       cy += with_sign(half, !(digit & 2u));
       if (DIM == 3) cz += with_sign(half, !(digit & 4u));
     }
-    top.centre_ext[t] = make_double4(cx, cy, cz, half);
+    return make_double4(cx, cy, cz, half);
+  };
+  for (int l = K - 1; l >= 0; --l) {
+    const uint32_t cells_l = 1u << (DIM * l);
+    for (uint32_t p = tid; p < cells_l; p += 1024) {
+      uint4 ci[R];
+      double4 cc[R];
+#pragma unroll
+      for (int d = 0; d < R; ++d) {  // all children at once (unconditional loads)
+        const uint32_t child = p * R + d;
+        if (l == K - 1) {
+          ci[d] = top.info[ABOVE + child];
+          cc[d] = top.com[ABOVE + child];
+        } else {
+          ci[d] = s_info[TT::offset(l + 1) + child];
+          cc[d] = s_com[TT::offset(l + 1) + child];
+        }
+      }
+      uint32_t units = 0, bodies = 0;
+      uint4 only = make_uint4(0u, 0u, 0u, 0u);
+      double4 only_com = make_double4(0.0, 0.0, 0.0, 0.0);
+      ComSum sum;
+#pragma unroll
+      for (int d = 0; d < R; ++d) {
+        const uint32_t u = ci[d].x & 0xffu;
+        if (u == 0u) continue;
+        sum.add(cc[d]);
+        units += u;  // (1 + anything >= 1 is already "internal")
+        bodies += ci[d].w;
+        only = ci[d];
+        only_com = cc[d];
+      }
+      uint4 inf = make_uint4(0u, 0u, 0u, 0u);
+      double4 com = make_double4(0.0, 0.0, 0.0, 0.0);
+      if (units == 1u) {  // one unit below: this cell is (or lies above) its leaf - the unit's own record
+        inf = only;
+        com = only_com;
+      } else if (units > 1u) {
+        com = sum.finish(centre_of(l, p));
+        inf = make_uint4(2u, 0u, 0u, bodies);
+      }
+      s_info[TT::offset(l) + p] = inf;
+      s_com[TT::offset(l) + p] = com;
+    }
+    __syncthreads();
+  }
+  for (uint32_t t = tid; t < ABOVE; t += 1024) {
+    top.info[t] = s_info[t];
+    top.com[t] = s_com[t];
+  }
+  // geometric centres / half-widths of every top cell
+  for (uint32_t t = tid; t < TT::CELLS; t += 1024) {
+    int l = 0;
+    while (l < K && TT::offset(l + 1) <= t) ++l;
+    top.centre_ext[t] = centre_of(l, t - TT::offset(l));
   }
   // cuts for the next build: rank r starts at the first level-K prefix whose running count reaches r n / world
   {
     constexpr uint32_t PER = S / 1024;  // prefixes per thread (4)
     unsigned mine = 0;
 #pragma unroll
-    for (uint32_t j = 0; j < PER; ++j) mine += top.info[TT::offset(K) + tid * PER + j].w;
+    for (uint32_t j = 0; j < PER; ++j) mine += top.info[ABOVE + tid * PER + j].w;
     const unsigned excl = block_exclusive_scan_nt<1024>(mine, s_wsum);
     s_cum[tid] = excl;
     __syncthreads();
@@ -1857,19 +1886,17 @@ __global__ void __launch_bounds__(1024) top_build_kernel(const TopSlotRec* __res
         cut = ~0ull;
       } else if (tid > 0) {
         const unsigned want = unsigned((n_total * size_t(tid)) / size_t(world));
-        // first prefix q with (bodies in prefixes < q) >= want
-        int lo = 0, hi = 1024;  // thread groups
+        int lo = 0, hi = 1024;  // first group of PER prefixes whose exclusive count >= want
         while (lo < hi) {
           const int mid = (lo + hi) / 2;
           if (s_cum[mid] >= want) hi = mid; else lo = mid + 1;
         }
-        // lo = first group whose exclusive count >= want; the prefix lies in group lo-1 or is lo*PER
         uint32_t q = uint32_t(lo) * PER;
-        if (lo > 0) {
+        if (lo > 0) {  // the prefix lies inside group lo - 1, or is the first of group lo
           unsigned run = s_cum[lo - 1];
           q = uint32_t(lo - 1) * PER;
           while (q < uint32_t(lo) * PER && run < want) {
-            run += top.info[TT::offset(K) + q].w;
+            run += top.info[ABOVE + q].w;
             ++q;
           }
         }
@@ -1887,25 +1914,30 @@ struct PeerTables {   // every rank's cell table, as seen from this device (own 
   uint32_t capacity;  // the same on every rank (symmetric allocation)
 };
 
+// Step 4.  The result of target s - acceleration and original index - is stored into block `rank` of EVERY
+// rank's exchange buffer (coalesced 16 + 4 byte stores over NVLink, issued while the rest of the grid still
+// walks), then the phase is signalled.
 template <int DIM>
 __global__ void __launch_bounds__(256) walk_sharded_kernel(const double4* __restrict__ sp,
                                                            const uint32_t* __restrict__ perm,
                                                            const uint8_t* __restrict__ fixed, NRef nref, TopView top,
-                                                           PeerTables peers, double theta, float easing, float tiny,
-                                                           float4* __restrict__ acc_sorted) {
+                                                           PeerTables peers, PeerTargets pt, size_t n_cap, uint32_t epoch,
+                                                           double theta, float easing, float tiny) {
   pb_pdl_sync();
   using TT = TopTree<DIM>;
   constexpr int K = TT::K, R = TT::R;
-  if (top.meta[0] != 0u) return;  // some rank's build was abandoned: the host replays the chunk
   const size_t n = nref.get();
   const size_t s = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
-  if (size_t(blockIdx.x) * blockDim.x >= n) return;
-  bool active = s < n;
+  // (some rank's build abandoned: nothing is walked, the host replays the chunk; the phase is still signalled)
+  const bool run = top.meta[META_ANY_BAD] == 0u && size_t(blockIdx.x) * blockDim.x < n;
+  bool active = run && s < n;
   double px = 0.0, py = 0.0, pz = 0.0, pm = 0.0;
+  uint32_t orig = 0;
   if (active) {
     const double4 p = sp[s];
     px = p.x; py = p.y; pz = p.z; pm = p.w;
-    if (fixed[perm[s]]) active = false;  // transformers.rs:139-141
+    orig = perm[s];
+    if (fixed[orig]) active = false;  // transformers.rs:139-141
   }
   const double theta2 = theta * theta;
   float fx = 0.f, fy = 0.f, fz = 0.f;
@@ -1930,15 +1962,17 @@ __global__ void __launch_bounds__(256) walk_sharded_kernel(const double4* __rest
   bool done = !active;
   while (!done) {
     const uint32_t t = TT::offset(l) + p;
-    const uint4 inf = top.info[t];
+    // the three records of the cell at once (the top tree is a few hundred KB: L1 / L2 hits)
+    const uint4 inf = __ldg(top.info + t);
+    const double4 ce = ld_now_double4(top.centre_ext + t);
+    const double4 cm = ld_now_double4(top.com + t);
     const uint32_t units = inf.x & 0xffu;
     bool descend = false;
     if (units == 1u) {
-      interact(top.com[t]);  // a leaf: always taken (octree.rs:151-152)
+      interact(cm);  // a leaf: always taken (octree.rs:151-152)
     } else if (units != 0u) {
-      const double4 ce = top.centre_ext[t];
       if (accept_cell(px, py, pz, ce, theta, theta2)) {
-        interact(top.com[t]);
+        interact(cm);
       } else if (l < K) {
         descend = true;
       } else {
@@ -1974,11 +2008,17 @@ __global__ void __launch_bounds__(256) walk_sharded_kernel(const double4* __rest
       else ++p;
     }
   }
-  if (s < n) {
+  if (run && s < n) {
     // a_i = f/m_a: a massless target is 0/0 = NaN in the reference (transformers.rs:154-158)
     if (active && pm == 0.0) fx = fy = fz = __int_as_float(0x7fc00000);
-    acc_sorted[s] = make_float4(fx, fy, fz, __uint_as_float(inter));
+    const float4 out = make_float4(fx, fy, fz, __uint_as_float(inter));
+    const size_t block = size_t(pt.rank) * (n_cap * 20);
+    for (int r = 0; r < pt.world; ++r) {
+      reinterpret_cast<float4*>(pt.xacc[r] + block)[s] = out;
+      if (r != pt.rank) reinterpret_cast<uint32_t*>(pt.xacc[r] + block + n_cap * sizeof(float4))[s] = orig;
+    }
   }
+  shard_signal(pt, SHARD_FLAG_WALK, SHARD_CNT_WALK, epoch);
 }
 
 // After a full (replicated) build: the first cuts, balanced on the sorted keys, and the splitters of this
@@ -2695,8 +2735,10 @@ cudaError_t tree_build(GravityWorkspace& ws, const ShardBuild* sh, cudaStream_t 
     const unsigned kid_blocks = blocks_for(cap, 256);
     const uint32_t sub_cap = ((kid_blocks + READY_LISTS - 1) / READY_LISTS) * 256u;
     PB_PASS(ws.c_ready.ensure(size_t(READY_LISTS) * sub_cap * 4));
+    // the grid follows the cells expected for THIS build's bodies (the table may be sized for a full build)
+    const unsigned kid_grid = std::min(kid_blocks, blocks_for(n * 5 / 2 + 1024, 256));
     PB_LAUNCH(ls, st, "kids_kernel",
-              pb_launch_pdl(kids_kernel<DIM>, dim3(kid_blocks), dim3(256), 0, st, ws.cell_start.as<uint32_t>(), nref, cells,
+              pb_launch_pdl(kids_kernel<DIM>, dim3(kid_grid), dim3(256), 0, st, ws.cell_start.as<uint32_t>(), nref, cells,
                                                            ws.c_kids.as<uint32_t>(), ws.c_ready.as<uint32_t>(), n_ready, sub_cap));
     PB_LAUNCH(ls, st, "climb_kernel",
               pb_launch_pdl(climb_kernel<DIM>, dim3(148 * 4), dim3(128), 0, st, ws.cell_start.as<uint32_t>(), nref, cells,
@@ -2811,10 +2853,8 @@ inline uint32_t top_slots(int dim) { return dim == 3 ? TopTree<3>::SLOTS : TopTr
 inline uint32_t top_cells(int dim) { return dim == 3 ? TopTree<3>::CELLS : TopTree<2>::CELLS; }
 }  // namespace
 
-size_t ShardState::top_block_bytes() const { return size_t(4096 + 1) * sizeof(TopSlotRec); }  // 4^6 = 8^4 prefixes + header
-
 void ShardState::release() {
-  DevBuf* all[] = {&cuts, &n_local, &slot_cell, &top_all, &top_ce, &top_com, &top_info, &top_meta, &xacc};
+  DevBuf* all[] = {&cuts, &n_local, &slot_cell, &top_ce, &top_com, &top_info, &top_meta, &xacc, &flags};
   for (DevBuf* b : all) b->release();
   planned = false;
 }
@@ -2826,7 +2866,6 @@ cudaError_t gravity_shard_setup(GravityWorkspace& ws, int kind, int rank, int wo
     return cudaErrorInvalidValue;
   }
   const int dim = kind == PB200_ASTRO ? 2 : 3;
-  static_assert(TopTree<2>::SLOTS == 4096 && TopTree<3>::SLOTS == 4096, "top_block_bytes");
   sh.rank = rank;
   sh.world = world;
   sh.planned = false;
@@ -2834,16 +2873,22 @@ cudaError_t gravity_shard_setup(GravityWorkspace& ws, int kind, int rank, int wo
   size_t cap = n / size_t(world) + n / size_t(8 * world) + n / 2048 + 4096;
   cap = (cap + 1023) / 1024 * 1024;
   if (cap > n + 1024) cap = (n + 1023) / 1024 * 1024;
+  const bool fresh = !sh.flags.p;
   sh.n_cap = cap;
   PB_PASS(sh.cuts.ensure(16 * 8));
   PB_PASS(sh.n_local.ensure(16));
   PB_PASS(sh.slot_cell.ensure(size_t(top_slots(dim)) * 4));
-  PB_PASS(sh.top_all.ensure(size_t(world) * sh.top_block_bytes()));
   PB_PASS(sh.top_ce.ensure(size_t(top_cells(dim)) * sizeof(double4)));
   PB_PASS(sh.top_com.ensure(size_t(top_cells(dim)) * sizeof(double4)));
   PB_PASS(sh.top_info.ensure(size_t(top_cells(dim)) * sizeof(uint4)));
-  PB_PASS(sh.top_meta.ensure(64 * 4));
+  PB_PASS(sh.top_meta.ensure(128 * 4));
   PB_PASS(sh.xacc.ensure(size_t(world) * sh.xacc_block_bytes()));
+  PB_PASS(sh.flags.ensure(32 * 4));
+  if (fresh) {  // epochs only ever grow: the flags are cleared once, when the buffer is made
+    PB_CUDA(cudaMemset(sh.flags.p, 0, 32 * 4));
+    PB_CUDA(cudaMemset(sh.top_meta.p, 0, 128 * 4));
+    sh.epoch = 0;
+  }
   return cudaSuccess;
 }
 
@@ -2870,10 +2915,26 @@ cudaError_t gravity_shard_plan(GravityWorkspace& ws, cudaStream_t st, LaunchStat
 }
 
 namespace {
+PeerTargets peer_targets(const ShardState& sh) {
+  PeerTargets pt;
+  for (int r = 0; r < 8; ++r) {
+    const int q = r < sh.world ? r : sh.rank;
+    pt.top_info[r] = static_cast<uint4*>(sh.peers.top_info[q]);
+    pt.top_com[r] = static_cast<double4*>(sh.peers.top_com[q]);
+    pt.meta[r] = static_cast<uint32_t*>(sh.peers.top_meta[q]);
+    pt.xacc[r] = static_cast<char*>(sh.peers.xacc[q]);
+    pt.flags[r] = static_cast<uint32_t*>(sh.peers.flags[q]);
+  }
+  pt.world = sh.world;
+  pt.rank = sh.rank;
+  return pt;
+}
+
 template <int DIM>
 cudaError_t shard_build(GravityWorkspace& ws, cudaStream_t st, LaunchStats& ls) {
   ShardState& sh = ws.shard;
   using TT = TopTree<DIM>;
+  sh.epoch += 1;
   PB_CUDA(cudaMemsetAsync(sh.slot_cell.p, 0, size_t(TT::SLOTS) * 4, st));
   ShardBuild sb;
   sb.cuts = sh.cuts.as<uint64_t>() + sh.rank;
@@ -2885,10 +2946,10 @@ cudaError_t shard_build(GravityWorkspace& ws, cudaStream_t st, LaunchStats& ls) 
                                             sh.n_cap * sizeof(float4));
   BuildOut bo;
   PB_PASS(tree_build<DIM>(ws, &sb, st, ls, &bo));
-  TopSlotRec* mine = reinterpret_cast<TopSlotRec*>(static_cast<char*>(sh.top_all.p) + size_t(sh.rank) * sh.top_block_bytes());
   PB_LAUNCH(ls, st, "top_export_kernel",
-            pb_launch_pdl(top_export_kernel<DIM>, dim3(blocks_for(TT::SLOTS + 1, 256)), dim3(256), 0, st,
-                          sh.slot_cell.as<uint32_t>(), bo.nref, ws.cell_start.as<uint32_t>(), bo.cells, mine));
+            pb_launch_pdl(top_export_kernel<DIM>, dim3(TT::SLOTS / 256), dim3(256), 0, st, sh.slot_cell.as<uint32_t>(),
+                          bo.nref, ws.cell_start.as<uint32_t>(), bo.cells, sh.cuts.as<uint64_t>(), peer_targets(sh),
+                          sh.epoch));
   return cudaGetLastError();
 }
 
@@ -2896,10 +2957,14 @@ template <int DIM>
 cudaError_t shard_walk(GravityWorkspace& ws, const GravityParams& prm, float easing, float tiny, cudaStream_t st,
                        LaunchStats& ls) {
   ShardState& sh = ws.shard;
+  using TT = TopTree<DIM>;
   TopView top{sh.top_ce.as<double4>(), sh.top_com.as<double4>(), sh.top_info.as<uint4>(), sh.top_meta.as<uint32_t>(),
               sh.cuts.as<uint64_t>()};
+  const size_t smem = size_t(TT::offset(TT::K)) * (sizeof(double4) + sizeof(uint4));
+  PB_CUDA(cudaFuncSetAttribute(top_build_kernel<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   PB_LAUNCH(ls, st, "top_build_kernel",
-            top_build_kernel<DIM><<<1, 1024, 0, st>>>(sh.top_all.as<TopSlotRec>(), sh.world, ws.n, ws.extent_cur, top));
+            pb_launch_pdl(top_build_kernel<DIM>, dim3(1), dim3(1024), smem, st, sh.world, ws.n, ws.extent_cur, top,
+                          sh.flags.as<uint32_t>(), sh.epoch));
   PeerTables pt;
   for (int r = 0; r < 8; ++r) {
     pt.centre_ext[r] = static_cast<const double4*>(sh.peers.centre_ext[r < sh.world ? r : sh.rank]);
@@ -2907,11 +2972,11 @@ cudaError_t shard_walk(GravityWorkspace& ws, const GravityParams& prm, float eas
     pt.skip[r] = static_cast<const uint32_t*>(sh.peers.skip[r < sh.world ? r : sh.rank]);
   }
   pt.capacity = sh.peers.capacity;
-  float4* acc_sorted = reinterpret_cast<float4*>(static_cast<char*>(sh.xacc.p) + size_t(sh.rank) * sh.xacc_block_bytes());
   const NRef nref{sh.n_local.as<uint32_t>(), uint32_t(sh.n_cap)};
   PB_LAUNCH(ls, st, "walk_sharded_kernel",
-            walk_sharded_kernel<DIM><<<blocks_for(sh.n_cap, 256), 256, 0, st>>>(
-                ws.spos64.as<double4>(), ws.perm, ws.fixed, nref, top, pt, prm.theta, easing, tiny, acc_sorted));
+            pb_launch_pdl(walk_sharded_kernel<DIM>, dim3(blocks_for(sh.n_cap, 256)), dim3(256), 0, st,
+                          ws.spos64.as<double4>(), ws.perm, ws.fixed, nref, top, pt, peer_targets(sh), sh.n_cap, sh.epoch,
+                          prm.theta, easing, tiny));
   return cudaGetLastError();
 }
 }  // namespace

@@ -105,17 +105,19 @@ float elapsed_ms(cudaEvent_t a, cudaEvent_t b) {
   return ms;
 }
 
-// what a rank tells the others about its cell table (exchanged once per plan)
+// what a rank tells the others about the buffers they read or write (exchanged once per plan):
+// cell table (centre_ext, com, skip), dense top tree (info, com), per-rank counts, exchange buffer, flags
+constexpr int kPeerBufs = 8;
 struct PeerRecord {
   uint64_t pid;
-  uint64_t ptr[3];       // centre_ext, com, skip (valid inside process `pid`)
   uint64_t capacity;     // cells
   uint64_t device;
-  cudaIpcMemHandle_t handle[3];
-  char pad[16];
+  uint64_t pad;
+  uint64_t ptr[kPeerBufs];              // valid inside process `pid`
+  cudaIpcMemHandle_t handle[kPeerBufs];
 };
 static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
-static_assert(sizeof(PeerRecord) == 256, "PeerRecord is exchanged as 256 bytes");
+static_assert(sizeof(PeerRecord) == 32 + 8 * kPeerBufs + 64 * kPeerBufs, "PeerRecord layout");
 
 struct RankCtx {
   int rank = 0, device = 0;
@@ -128,8 +130,8 @@ struct RankCtx {
   LaunchStats ls;
   bool vel_stale = false, ext_ready = false, ext_dirty = true;
   int ext_slot = 0;
-  PeerRecord opened[8];          // what the currently mapped peer pointers were opened from
-  void* mapped[8][3] = {};       // cudaIpcOpenMemHandle results to close
+  PeerRecord opened[8];                  // what the currently mapped peer pointers were opened from
+  void* mapped[8][kPeerBufs] = {};       // cudaIpcOpenMemHandle results to close
   bool have_peers = false;
 };
 
@@ -149,7 +151,7 @@ struct MultiSim {
       cudaSetDevice(c->device);
       if (c->stream) cudaStreamSynchronize(c->stream);
       for (int r = 0; r < 8; ++r)
-        for (int k = 0; k < 3; ++k)
+        for (int k = 0; k < kPeerBufs; ++k)
           if (c->mapped[r][k]) cudaIpcCloseMemHandle(c->mapped[r][k]);
       if (c->comm && g_nccl.so) g_nccl.CommDestroy(c->comm);
       c->ws.release_all();
@@ -195,8 +197,6 @@ cudaError_t all_gather_blocks(MultiSim& m, DevBuf RankCtx::*unused, size_t block
   return cudaSuccess;
 }
 
-void* buf_top(RankCtx* c) { return c->ws.shard.top_all.p; }
-void* buf_xacc(RankCtx* c) { return c->ws.shard.xacc.p; }
 void* buf_acc(RankCtx* c) { return c->ws.acc.p; }
 void* buf_peer(RankCtx* c) { return c->peer_stage.p; }
 
@@ -205,8 +205,8 @@ cudaError_t sync_all(MultiSim& m) {
   return cudaSuccess;
 }
 
-// (re)map every rank's cell table into every local rank: direct pointers inside a process (peer access
-// enabled), CUDA IPC handles across processes.  Collective; synchronises.
+// (re)map every rank's buffers into every local rank: direct pointers inside a process (peer access enabled),
+// CUDA IPC handles across processes.  Collective (one small ncclAllGather of the records); synchronises.
 cudaError_t exchange_peers(MultiSim& m) {
   const uint64_t pid = uint64_t(getpid());
   std::vector<std::vector<PeerRecord>> all(m.local.size(), std::vector<PeerRecord>(m.world));
@@ -216,8 +216,10 @@ cudaError_t exchange_peers(MultiSim& m) {
     rec.pid = pid;
     rec.device = uint64_t(c->device);
     rec.capacity = c->ws.cell_cap;
-    const void* p[3] = {c->ws.c_centre_ext.p, c->ws.c_com.p, c->ws.c_skip.p};
-    for (int k = 0; k < 3; ++k) {
+    const ShardState& sh = c->ws.shard;
+    const void* p[kPeerBufs] = {c->ws.c_centre_ext.p, c->ws.c_com.p, c->ws.c_skip.p, sh.top_info.p,
+                                sh.top_com.p,         sh.top_meta.p, sh.xacc.p,      sh.flags.p};
+    for (int k = 0; k < kPeerBufs; ++k) {
       rec.ptr[k] = reinterpret_cast<uint64_t>(p[k]);
       if (m.local.size() < size_t(m.world)) PB_CUDA(cudaIpcGetMemHandle(&rec.handle[k], const_cast<void*>(p[k])));
     }
@@ -241,7 +243,7 @@ cudaError_t exchange_peers(MultiSim& m) {
     for (int r = 0; r < m.world; ++r) {
       const PeerRecord& rec = all[li][r];
       cap = std::min(cap, rec.capacity);
-      const void* q[3];
+      void* q[kPeerBufs];
       if (rec.pid == pid) {
         if (int(rec.device) != c->device) {
           cudaError_t e = cudaDeviceEnablePeerAccess(int(rec.device), 0);
@@ -251,11 +253,11 @@ cudaError_t exchange_peers(MultiSim& m) {
             return e;
           }
         }
-        for (int k = 0; k < 3; ++k) q[k] = reinterpret_cast<const void*>(rec.ptr[k]);
+        for (int k = 0; k < kPeerBufs; ++k) q[k] = reinterpret_cast<void*>(rec.ptr[k]);
       } else {
-        const bool same = c->have_peers && !std::memcmp(&c->opened[r].handle, &rec.handle, sizeof rec.handle) &&
-                          c->opened[r].pid == rec.pid;
-        for (int k = 0; k < 3; ++k) {
+        for (int k = 0; k < kPeerBufs; ++k) {
+          const bool same = c->have_peers && c->mapped[r][k] && c->opened[r].pid == rec.pid &&
+                            !std::memcmp(&c->opened[r].handle[k], &rec.handle[k], sizeof rec.handle[k]);
           if (!same) {
             if (c->mapped[r][k]) {
               cudaIpcCloseMemHandle(c->mapped[r][k]);
@@ -263,7 +265,7 @@ cudaError_t exchange_peers(MultiSim& m) {
             }
             cudaError_t e = cudaIpcOpenMemHandle(&c->mapped[r][k], rec.handle[k], cudaIpcMemLazyEnablePeerAccess);
             if (e != cudaSuccess) {
-              set_error("cudaIpcOpenMemHandle (rank %d's table on rank %d): %s", r, c->rank, cudaGetErrorString(e));
+              set_error("cudaIpcOpenMemHandle (buffer %d of rank %d on rank %d): %s", k, r, c->rank, cudaGetErrorString(e));
               return e;
             }
           }
@@ -274,11 +276,19 @@ cudaError_t exchange_peers(MultiSim& m) {
       sp.centre_ext[r] = q[0];
       sp.com[r] = q[1];
       sp.skip[r] = q[2];
+      sp.top_info[r] = q[3];
+      sp.top_com[r] = q[4];
+      sp.top_meta[r] = q[5];
+      sp.xacc[r] = q[6];
+      sp.flags[r] = q[7];
     }
     sp.capacity = uint32_t(std::min<uint64_t>(cap, 0xfffffff0ull));
     c->have_peers = true;
     ++li;
   }
+  // nobody may start storing into a peer before that peer has finished this exchange (its buffers may be new)
+  PB_PASS(all_gather_blocks(m, nullptr, sizeof(PeerRecord), buf_peer));
+  PB_PASS(sync_all(m));
   return cudaSuccess;
 }
 
@@ -359,21 +369,24 @@ cudaError_t plan_shards(MultiSim& m) {
 }
 
 cudaError_t step_sharded(MultiSim& m) {
+  // three phases per rank, no collective call: the kernels store into the peers' buffers and signal / wait on
+  // epoch flags (gravity.cu).  With several ranks in this process the phases are enqueued rank by rank so that
+  // no device waits for work this thread has not enqueued yet.
   FOR_LOCAL(m, c) {
     c->ws.pos64 = c->cur.as<double4>();
     c->ws.extent_pre = c->ext_ready ? c->ext.as<unsigned long long>() + c->ext_slot : nullptr;
     PB_PASS(gravity_shard_build(c->ws, m.prm, c->stream, c->ls));
     c->ws.extent_pre = nullptr;
   }
-  PB_PASS(all_gather_blocks(m, nullptr, m.local[0]->ws.shard.top_block_bytes(), buf_top));
   FOR_LOCAL(m, c) PB_PASS(gravity_shard_walk(c->ws, m.prm, c->stream, c->ls));
-  PB_PASS(all_gather_blocks(m, nullptr, m.local[0]->ws.shard.xacc_block_bytes(), buf_xacc));
   FOR_LOCAL(m, c) {
     LeanSlots s;
     PB_PASS(lean_prepare(c, &s));
-    const ShardState& sh = c->ws.shard;
+    ShardState& sh = c->ws.shard;
+    const uint32_t* n_locals = sh.top_meta.as<uint32_t>() + (sh.epoch & 1u) * 32u + 1u;  // META_STRIDE, META_BODIES
     PB_PASS(verlet_update_lean_sharded(c->cur.as<double4>(), c->prev.as<double4>(), sh.xacc.p, sh.n_cap, m.world,
-                                       sh.top_meta.as<uint32_t>() + 1, m.dt, s.out, s.zero, s.last, c->stream, c->ls));
+                                       n_locals, sh.flags.as<uint32_t>(), sh.epoch, m.dt, s.out, s.zero, s.last,
+                                       c->stream, c->ls));
     lean_done(c);
   }
   m.sharded_steps += 1;
@@ -423,6 +436,14 @@ cudaError_t collective_check(MultiSim& m, TreeCheck* out) {
     TreeCheck chk;
     PB_PASS(gravity_check(c->ws, c->stream, &chk));
     if (c == m.local[0]) *out = chk;
+    if (c->ws.shard.flags.p) {
+      uint32_t timed_out = 0;
+      PB_CUDA(cudaMemcpy(&timed_out, c->ws.shard.flags.as<uint32_t>() + 18, 4, cudaMemcpyDeviceToHost));  // SHARD_TIMEOUT
+      if (timed_out) {
+        set_error("sharded step: rank %d waited in vain for a peer's signal (a rank stopped or lost its mapping)", c->rank);
+        return cudaErrorUnknown;
+      }
+    }
   }
   return cudaSuccess;
 }
@@ -780,15 +801,16 @@ int pb200_msim_stats(void* h, Pb200Stats* out, uint64_t* sharded_steps, uint64_t
   out->max_bucket = c->ws.last_max_bucket;
   const ShardState& sh = c->ws.shard;
   if (!m.direct() && m.world > 1 && sh.planned && m.sharded_steps > 0 && sh.top_meta.p) {
-    uint32_t meta[64];
-    if (cudaMemcpy(meta, sh.top_meta.p, sizeof meta, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    uint32_t meta[32];
+    if (cudaMemcpy(meta, sh.top_meta.as<uint32_t>() + (sh.epoch & 1u) * 32u, sizeof meta, cudaMemcpyDeviceToHost) != cudaSuccess)
+      return -1;
     uint64_t cells = 0;
-    for (int r = 0; r < m.world; ++r) cells += meta[1 + m.world + r];
+    for (int r = 0; r < m.world; ++r) cells += meta[9 + r];
     out->n_cells = cells;  // (the ranks' tables; the cells above level K exist once more in each)
     if (c->cnt.ensure(8) != cudaSuccess) return -1;
     cudaMemset(c->cnt.p, 0, 8);
     count_sharded_kernel<<<dim3(148 * 2, m.world), 256, 0, c->stream>>>(static_cast<const char*>(sh.xacc.p), sh.n_cap,
-                                                                        sh.top_meta.as<uint32_t>() + 1,
+                                                                        sh.top_meta.as<uint32_t>() + (sh.epoch & 1u) * 32u + 1u,
                                                                         c->cnt.as<unsigned long long>());
     unsigned long long inter = 0;
     if (cudaMemcpyAsync(&inter, c->cnt.p, 8, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
@@ -812,13 +834,13 @@ int pb200_msim_rank_counts(void* h, uint32_t* bodies, uint32_t* cells) {
   RankCtx* c = m.local[0];
   const ShardState& sh = c->ws.shard;
   if (!sh.top_meta.p || m.sharded_steps == 0) return -1;
-  uint32_t meta[64];
+  uint32_t meta[32];
   if (cudaSetDevice(c->device) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess ||
-      cudaMemcpy(meta, sh.top_meta.p, sizeof meta, cudaMemcpyDeviceToHost) != cudaSuccess)
+      cudaMemcpy(meta, sh.top_meta.as<uint32_t>() + (sh.epoch & 1u) * 32u, sizeof meta, cudaMemcpyDeviceToHost) != cudaSuccess)
     return -1;
   for (int r = 0; r < m.world; ++r) {
     if (bodies) bodies[r] = meta[1 + r];
-    if (cells) cells[r] = meta[1 + m.world + r];
+    if (cells) cells[r] = meta[9 + r];
   }
   return m.world;
 }
@@ -833,8 +855,9 @@ int pb200_msim_last_accelerations(void* h, Acceleration* acc, size_t n) {
   if (cudaSetDevice(c->device) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) return -1;
   const ShardState& sh = c->ws.shard;
   if (!m.direct() && m.world > 1 && sh.planned && m.sharded_steps > 0) {
-    uint32_t meta[64];
-    if (cudaMemcpy(meta, sh.top_meta.p, sizeof meta, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    uint32_t meta[32];
+    if (cudaMemcpy(meta, sh.top_meta.as<uint32_t>() + (sh.epoch & 1u) * 32u, sizeof meta, cudaMemcpyDeviceToHost) != cudaSuccess)
+      return -1;
     std::vector<float4> a(sh.n_cap);
     std::vector<uint32_t> p(sh.n_cap);
     for (int r = 0; r < m.world; ++r) {

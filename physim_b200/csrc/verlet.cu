@@ -122,11 +122,15 @@ __global__ void __launch_bounds__(256) verlet_lean_kernel(const double4* __restr
 __global__ void __launch_bounds__(256) verlet_lean_sharded_kernel(const double4* __restrict__ cur,
                                                                   double4* __restrict__ prev_inout,
                                                                   const char* __restrict__ xacc, size_t n_cap,
-                                                                  const uint32_t* __restrict__ n_locals, double dt2,
+                                                                  const uint32_t* __restrict__ n_locals,
+                                                                  uint32_t* flags, uint32_t epoch, int world, double dt2,
                                                                   unsigned long long* __restrict__ extent_out,
                                                                   unsigned long long* __restrict__ extent_zero,
                                                                   unsigned long long* __restrict__ extent_last) {
   pb_pdl_sync();
+  // every rank's walk of this epoch must have stored its block here (the flags live in this device's memory)
+  if (int(threadIdx.x) < world) shard_wait_flag(flags, SHARD_FLAG_WALK + int(threadIdx.x), epoch);
+  __syncthreads();
   const size_t j = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
   const unsigned r = blockIdx.y;
   if (j == 0 && r == 0) {
@@ -290,15 +294,16 @@ cudaError_t verlet_update_lean(const double4* cur, double4* prev_inout, const fl
 }
 
 cudaError_t verlet_update_lean_sharded(const double4* cur, double4* prev_inout, const void* xacc, size_t n_cap,
-                                       int world, const uint32_t* n_locals, double dt, unsigned long long* extent_out,
-                                       unsigned long long* extent_zero, unsigned long long* extent_last,
-                                       cudaStream_t st, LaunchStats& ls) {
+                                       int world, const uint32_t* n_locals, uint32_t* flags, uint32_t epoch, double dt,
+                                       unsigned long long* extent_out, unsigned long long* extent_zero,
+                                       unsigned long long* extent_last, cudaStream_t st, LaunchStats& ls) {
   if (n_cap == 0) return cudaSuccess;
   const dim3 grid(static_cast<unsigned>((n_cap + 255) / 256), static_cast<unsigned>(world));
   const double dt2 = dt * dt;  // dt.powi(2)
   PB_LAUNCH(ls, st, "verlet_lean_sharded_kernel",
             pb_launch_pdl(verlet_lean_sharded_kernel, grid, dim3(256), 0, st, cur, prev_inout,
-                          static_cast<const char*>(xacc), n_cap, n_locals, dt2, extent_out, extent_zero, extent_last));
+                          static_cast<const char*>(xacc), n_cap, n_locals, flags, epoch, world, dt2, extent_out,
+                          extent_zero, extent_last));
   return cudaGetLastError();
 }
 
