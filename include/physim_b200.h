@@ -212,7 +212,26 @@ int pb200_verlet_step(void *v, const Entity *entities, Entity *new_state, size_t
  * leave the device: H2D packed state -> tree/force kernels -> verlet kernel -> D2H x,v. */
 int pb200_verlet_step_fused(void *v, void *transform, const Entity *entities, Entity *new_state,
                             size_t n, double dt);
+/* Opt-in for the fused step: keep the state in HBM between calls and return whole Entity records by one DMA
+ * into the caller's (persistent, page-locked on first use) new_state.  CONTRACT: between two calls nothing edits
+ * the state - physim's loop then passes a clone of what the previous call returned (pipeline.rs:166-173); a
+ * pipeline with transmute elements (pipeline.rs:169-171) must not set it.  Each call compares 2048 sampled
+ * entities with the previous output and falls back to a full upload on any difference (another run, a reset,
+ * a wholesale edit); an edit of a few bodies can escape the sample, hence the contract.  The Rust shim's
+ * `resident` property. */
+int pb200_verlet_set_resident(void *v, int on);
+int pb200_verlet_resident_counts(void *v, uint64_t *steps_without_upload, uint64_t *steps_with_upload);
 int pb200_verlet_stats(void *v, Pb200Stats *out);
+
+/* The composition stock physim runs, in C: an acc_fn that calls a transform element through its plugin vtable
+ * (pipeline.rs:137-141 builds that closure; plugin/transform.rs:85-104 is the call).  ctx = &Pb200TransformRef. */
+#ifndef PHYSIM_B200_NO_HOST_TYPES
+typedef struct Pb200TransformRef {
+  const TransformElementAPI *api;
+  void *obj;
+} Pb200TransformRef;
+#endif
+void pb200_acc_from_transform(void *ctx, const Entity *state, size_t n, Acceleration *acc);
 
 /* --- euler and rk4 (integrators/src/euler.rs:17-50, rk4.rs:23-183) ------
  * Same handle type and calling convention as verlet; a Rust shim's `euler` / `rk4` elements forward

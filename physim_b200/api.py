@@ -51,6 +51,11 @@ class ElementMetaFFI(C.Structure):
                                       ("name", "plugin", "version", "license", "author", "blurb", "repo")]
 
 
+class Pb200TransformRef(C.Structure):
+    """ctx of pb200_acc_from_transform: a transform element as physim holds it (vtable + object)."""
+    _fields_ = [("api", C.POINTER(TransformElementAPI)), ("obj", C.c_void_p)]
+
+
 class Pb200Stats(C.Structure):
     _fields_ = [("n_bodies", C.c_uint64), ("n_cells", C.c_uint64), ("interactions", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("extent", C.c_double), ("ms_h2d", C.c_float),
@@ -109,6 +114,8 @@ def lib():
     L.pb200_verlet_step.argtypes = [vp, vp, vp, sz, ACC_FN, vp, dbl]
     L.pb200_verlet_step_fused.argtypes = [vp, vp, vp, vp, sz, dbl]
     L.pb200_verlet_stats.argtypes = [vp, C.POINTER(Pb200Stats)]
+    L.pb200_verlet_set_resident.argtypes = [vp, i32]
+    L.pb200_verlet_resident_counts.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.pb200_integrator_create.restype = vp
     L.pb200_integrator_create.argtypes = [i32]
     L.pb200_integrator_destroy.argtypes = [vp]
@@ -337,6 +344,28 @@ class Verlet:
         if rc != 0:
             raise Pb200Error(last_error())
         return new_state
+
+    def integrate_dropin(self, entities, transform, dt, out=None):
+        """The composition stock physim runs, natively: IntegratorElement::integrate with an acc_fn that calls
+        `transform` (a TransformElement) through its plugin vtable (pipeline.rs:137-141) - what the Rust shim's
+        `verlet` does when the gravity element is a separate plugin element."""
+        entities = _state(entities)
+        n = len(entities)
+        new_state = np.zeros(n, dtype=ENTITY) if out is None else out
+        ref = Pb200TransformRef(C.pointer(transform._api), transform._obj)
+        fn = C.cast(lib().pb200_acc_from_transform, ACC_FN)
+        if lib().pb200_integrator_step(self._v, _ptr(entities), _ptr(new_state), n, fn, C.byref(ref), float(dt)) != 0:
+            raise Pb200Error(last_error())
+        return new_state
+
+    def set_resident(self, on=True):
+        """Opt-in of the fused step: state kept in HBM between calls, whole Entity records returned by one DMA."""
+        lib().pb200_verlet_set_resident(self._v, 1 if on else 0)
+
+    def resident_counts(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        lib().pb200_verlet_resident_counts(self._v, C.byref(a), C.byref(b))
+        return a.value, b.value
 
     def stats(self):
         st = Pb200Stats()

@@ -389,6 +389,11 @@ cudaError_t verlet_update(double4* cur, double4* prev, double4* vel, const float
                           const double* acc64, size_t n, double dt, int first, cudaStream_t stream,
                           LaunchStats& ls, double* out6 = nullptr);
 
+// Entity AoS (80-byte records) on the device <-> the kernels' state arrays (resident host boundary)
+cudaError_t entity_split(const void* ent80, size_t n, double4* pos, double4* vel, uint8_t* fixed, cudaStream_t st,
+                         LaunchStats& ls);
+cudaError_t entity_merge(void* ent80, size_t n, const double4* pos, const double4* vel, cudaStream_t st, LaunchStats& ls);
+
 // One rk4 stage (1..4): folds k_stage into the running sums, writes the next evaluation point
 // (stages 1-3; also packed into out6 when given) or the new state (stage 4: out_pos/out_vel/out6).
 cudaError_t rk4_stage(int stage, const double4* e_pos, const double4* e_vel, const uint8_t* fixed,

@@ -400,11 +400,10 @@ constexpr int LOCAL_BIN_BITS = 12;     // counting-sort bins inside a bucket
 constexpr unsigned LOCAL_BIN_LIMIT = 1024;
 constexpr unsigned LOCAL_SKEWED = 0x7fffffffu;  // published as "largest bucket" when a bin is too full
 
-template <int DIM>
+template <int DIM, unsigned NB /* buckets: 256, 512 or 1024 */>
 __global__ void __launch_bounds__(256) encode_bucket_kernel(const double4* __restrict__ pos, size_t n,
                                                             const unsigned long long* __restrict__ extent_bits,
-                                                            const uint64_t* __restrict__ splitters /*[nb]*/,
-                                                            unsigned nb /* buckets: 256, 512 or 1024 */,
+                                                            const uint64_t* __restrict__ splitters /*[NB]*/,
                                                             int lo, uint64_t* __restrict__ bkey,
                                                             uint32_t* __restrict__ bidx, unsigned cap,
                                                             unsigned* __restrict__ cursor /*[nb]*/,
@@ -412,10 +411,12 @@ __global__ void __launch_bounds__(256) encode_bucket_kernel(const double4* __res
                                                             cuts[0] <= key < cuts[1]; nullptr: every body */) {
   pb_pdl_sync();
   constexpr int LM = TreeDim<DIM>::LM;
-  __shared__ unsigned cnt[MAX_BUCKETS];
-  __shared__ unsigned gbase[MAX_BUCKETS];
-  __shared__ uint64_t spl[MAX_BUCKETS];
+  constexpr unsigned nb = NB;
+  __shared__ unsigned cnt[NB];
+  __shared__ unsigned gbase[NB];
+  __shared__ uint64_t spl[NB];
   const int tid = threadIdx.x;
+#pragma unroll
   for (unsigned j = tid; j < nb; j += 256) {
     cnt[j] = 0u;
     spl[j] = j ? (splitters[j] >> lo) : 0ull;
@@ -459,6 +460,7 @@ __global__ void __launch_bounds__(256) encode_bucket_kernel(const double4* __res
     // bucket = number of splitters <= key >> lo, minus one (spl[0] = 0): log2(nb)-step search, no divergence
     const uint64_t kk = k[e] >> lo;
     unsigned b = 0;
+#pragma unroll
     for (unsigned step = nb >> 1; step > 0; step >>= 1)
       if (spl[b + step] <= kk) b += step;
     d[e] = b;
@@ -1713,9 +1715,11 @@ constexpr int META_STRIDE = 32, META_BODIES = 1, META_CELLS = 9, META_BAD = 17, 
 // End of a producer kernel: when the last CTA has passed (all peer stores of the grid performed), tell every
 // rank that this rank's phase of `epoch` is complete.  (threadFenceReduction pattern, system scope.)
 __device__ __forceinline__ void shard_signal(const PeerTargets& pt, int slot, int counter, uint32_t epoch) {
-  __threadfence_system();
+  // one system-scope fence per CTA, by the thread that counts the CTA in: the barrier orders the other threads'
+  // stores before it and the fence is cumulative (a fence per thread waits out an NVLink round trip per warp)
   __syncthreads();
   if (threadIdx.x == 0) {
+    __threadfence_system();
     uint32_t* mine = pt.flags[pt.rank];
     const unsigned done = atomicAdd(mine + counter, 1u) + 1u;
     if (done == gridDim.x * gridDim.y) {
@@ -2565,10 +2569,15 @@ cudaError_t encode_and_sort(GravityWorkspace& ws, size_t n, const SortBuffers& s
   ws.splitter_cur ^= 1;
   *splitters_out = spl_out;  // written by the side job of the scan that follows the sort
   if (sb.mode != 0) {
-    PB_LAUNCH(ls, st, "encode_bucket_kernel",
-              pb_launch_pdl(encode_bucket_kernel<DIM>, dim3(blocks_for(n, 256 * ENC_ITEMS)), dim3(256), 0, st, 
-                  ws.pos64, n, ws.extent_cur, spl_in, sb.nb, sb.lo, ws.bucket_key.as<uint64_t>(),
-                  ws.bucket_idx.as<uint32_t>(), sb.cap, sb.ghist, sh ? sh->cuts : nullptr));
+#define PB_ENCODE(NBV)                                                                                            \
+  PB_LAUNCH(ls, st, "encode_bucket_kernel",                                                                      \
+            pb_launch_pdl(encode_bucket_kernel<DIM, NBV>, dim3(blocks_for(n, 256 * ENC_ITEMS)), dim3(256), 0, st, \
+                          ws.pos64, n, ws.extent_cur, spl_in, sb.lo, ws.bucket_key.as<uint64_t>(),              \
+                          ws.bucket_idx.as<uint32_t>(), sb.cap, sb.ghist, sh ? sh->cuts : nullptr))
+    if (sb.nb == 256) PB_ENCODE(256u);
+    else if (sb.nb == 512) PB_ENCODE(512u);
+    else PB_ENCODE(1024u);
+#undef PB_ENCODE
     uint32_t* n_out = sh ? sh->n_local : nullptr;
     const uint32_t n_cap = sh ? uint32_t(sh->n_cap) : 0u;
     const size_t smem = sort_local_smem(sb.cap);

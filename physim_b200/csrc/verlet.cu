@@ -177,6 +177,35 @@ __global__ void __launch_bounds__(256) verlet_velocity_kernel(const double4* __r
                         __ddiv_rn(__dsub_rn(x.z, p.z), dt), 0.0);  // (x' - x)/dt     (verlet.rs:68-70)
 }
 
+// ---- resident host boundary: whole Entity records on the device --------------------------------------
+// ent80 holds the caller's Entity array (80-byte records, physim-core/src/lib.rs:16-30).  split: the state the
+// kernels work on ({x,y,z,m}, {vx,vy,vz,0}, fixed flags) out of it; merge: new positions / velocities back into
+// it, the other fields (radius, mass, id, fixed) untouched - so that one DMA of ent80 IS new_state
+// (verlet.rs:41-48 / :72-79 copy the entity and overwrite six fields).
+__global__ void __launch_bounds__(256) entity_split_kernel(const double2* __restrict__ ent80, size_t n,
+                                                           double4* __restrict__ pos, double4* __restrict__ vel,
+                                                           uint8_t* __restrict__ fixed) {
+  const size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const double2* e = ent80 + 5 * i;  // {x,y} {z,vx} {vy,vz} {radius,mass} {id,fixed}
+  const double2 a = e[0], b = e[1], c = e[2], d = e[3], t = e[4];
+  pos[i] = make_double4(a.x, a.y, b.x, d.y);
+  vel[i] = make_double4(b.y, c.x, c.y, 0.0);
+  fixed[i] = (__double_as_longlong(t.y) & 0xff) ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(256) entity_merge_kernel(double2* __restrict__ ent80, size_t n,
+                                                           const double4* __restrict__ pos,
+                                                           const double4* __restrict__ vel) {
+  const size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const double4 p = pos[i], v = vel[i];
+  double2* e = ent80 + 5 * i;
+  e[0] = make_double2(p.x, p.y);
+  e[1] = make_double2(p.z, v.x);
+  e[2] = make_double2(v.y, v.z);
+}
+
 // ---- rk4 (integrators/src/rk4.rs:23-183) -----------------------------------------------------
 // One kernel per stage.  k = (dt * v_at, dt * a) is folded into the running sums
 // S = ((k1 + 2 k2) + 2 k3) + k4 in the reference's left-to-right order, and the next evaluation
@@ -290,6 +319,23 @@ cudaError_t verlet_update_lean(const double4* cur, double4* prev_inout, const fl
   const double dt2 = dt * dt;  // dt.powi(2)
   PB_LAUNCH(ls, st, "verlet_lean_kernel",
             pb_launch_pdl(verlet_lean_kernel, dim3(blocks), dim3(256), 0, st, cur, prev_inout, acc32, n, dt2, extent_out, extent_zero, extent_last));
+  return cudaGetLastError();
+}
+
+cudaError_t entity_split(const void* ent80, size_t n, double4* pos, double4* vel, uint8_t* fixed, cudaStream_t st,
+                         LaunchStats& ls) {
+  if (n == 0) return cudaSuccess;
+  PB_LAUNCH(ls, st, "entity_split_kernel",
+            entity_split_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(
+                static_cast<const double2*>(ent80), n, pos, vel, fixed));
+  return cudaGetLastError();
+}
+
+cudaError_t entity_merge(void* ent80, size_t n, const double4* pos, const double4* vel, cudaStream_t st, LaunchStats& ls) {
+  if (n == 0) return cudaSuccess;
+  PB_LAUNCH(ls, st, "entity_merge_kernel",
+            entity_merge_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(static_cast<double2*>(ent80), n,
+                                                                                      pos, vel));
   return cudaGetLastError();
 }
 

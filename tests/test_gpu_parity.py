@@ -297,9 +297,9 @@ def test_bucket_sort_overflow_and_skew_fall_back(name):
         el.transform(gen.cube(30_000, seed=2))
     # Crowds around one spot.  100 coincident bodies (one merged unit) and 1500 within 1e-5 are sorted by the
     # bucket sort: the bins follow the key range a bucket's bodies actually span, so a crowd spreads over them.
-    # 1500 bodies within 1e-7 share ONE 63-bit octree key (the key resolves extent * 2^-21 = 5e-7): more than a
-    # bin may hold, the build goes to the global passes.  (The 62-bit quadtree key resolves 5e-10: no crowding.)
-    for crowd, spread, want_mode in ((100, 0.0, 1), (1500, 1e-5, 1), (1500, 1e-7, 0 if name == "astro2" else 1)):
+    # 3000 bodies within 1e-7 share one or two 63-bit octree keys (the key resolves extent * 2^-21 = 5e-7): more than
+    # a bin may hold, the build goes to the global passes.  (The 62-bit quadtree key resolves 5e-10: no crowding.)
+    for crowd, spread, want_mode in ((100, 0.0, 1), (1500, 1e-5, 1), (3000, 1e-7, 0 if name == "astro2" else 1)):
         twins = gen.cube(20_000, seed=8)
         jit = np.random.default_rng(crowd).random((crowd, 3)) * spread
         twins["x"][:crowd], twins["y"][:crowd], twins["z"][:crowd] = 0.3 + jit[:, 0], -0.2 + jit[:, 1], 0.6 + jit[:, 2]

@@ -238,3 +238,62 @@ def test_device_resident_run_feeds_csvsink(tmp_path):
         else:
             disp = np.abs(ref - np.stack([s["x"], s["y"], s["z"]], 1)).max()
             assert np.abs(row - ref).max() <= 1e-5 * disp
+
+
+def test_resident_fused_steps_equal_copy_every_step():
+    """pb200_verlet_set_resident: same bits as the fused step that copies the state in and out every call; the
+    upload is skipped once the input is the previous output, and a replaced state is noticed."""
+    s = gen.readme_pipeline(30_000, seed=6, spin=1000.0)
+    s["radius"] = np.linspace(0.01, 0.02, len(s))          # pass-through fields must come back untouched
+    s["id"] = np.arange(len(s)) % 7
+    s["fixed"][11] = True
+    dt = 1e-5
+    el_a, el_b = api.TransformElement("astro2", theta=1.0, e=0.5), api.TransformElement("astro2", theta=1.0, e=0.5)
+    va, vb = api.Verlet(), api.Verlet()
+    vb.set_resident(True)
+    bufs_a, bufs_b = [s.copy(), s.copy()], [s.copy(), s.copy()]
+    k = 0
+    for step in range(6):
+        va.integrate_fused(bufs_a[k], el_a, dt, out=bufs_a[k ^ 1])
+        vb.integrate_fused(bufs_b[k], el_b, dt, out=bufs_b[k ^ 1])
+        k ^= 1
+        for f in ("x", "y", "z", "vx", "vy", "vz", "radius", "mass", "id", "fixed"):
+            assert np.array_equal(bufs_a[k][f], bufs_b[k][f]), (step, f)
+    hits, misses = vb.resident_counts()
+    # call 1 uploads; call 2 writes into the other buffer (newly page-locked: uploads); from then on the buffers
+    # alternate and the input of a call is NOT the buffer the previous call wrote... unless the caller clones, as
+    # physim does: emulate that from here on
+    state, new_state = bufs_b[k].copy(), bufs_b[k].copy()
+    ref_state = bufs_a[k].copy()
+    vb.integrate_fused(state, el_b, dt, out=new_state)     # new output buffer: full upload
+    h0, m0 = vb.resident_counts()
+    for step in range(5):
+        state = new_state.copy()                           # pipeline.rs:173
+        vb.integrate_fused(state, el_b, dt, out=new_state)
+    h1, m1 = vb.resident_counts()
+    assert (h1 - h0, m1 - m0) == (5, 0)
+    ref_new = ref_state.copy()
+    for step in range(6):
+        va.integrate_fused(ref_state, el_a, dt, out=ref_new)
+        ref_state = ref_new.copy()
+    for f in ("x", "y", "z", "vx", "vy", "vz", "radius", "id", "fixed"):
+        assert np.array_equal(new_state[f], ref_new[f]), f
+    # a different state in the same buffers: noticed by the sample, uploaded in full
+    other = gen.readme_pipeline(30_000, seed=99, spin=10.0)
+    vb.integrate_fused(other, el_b, dt, out=new_state)
+    h2, m2 = vb.resident_counts()
+    assert m2 == m1 + 1
+    want = api.Verlet().integrate_fused(other, api.TransformElement("astro2", theta=1.0, e=0.5), dt)
+    for f in ("x", "y", "z", "vx", "vy", "vz"):
+        assert np.array_equal(new_state[f], want[f]), f
+
+
+def test_dropin_composition_equals_fused_within_acc_rounding():
+    """IntegratorElement::integrate with an acc_fn that calls the plugin transform through its vtable (what stock
+    physim runs): same accelerations (fp32 -> fp64 on the host), same verlet arithmetic as the fused step."""
+    s = gen.readme_pipeline(20_000, seed=2, spin=1000.0)
+    el = api.TransformElement("astro2", theta=1.0, e=0.5)
+    a = api.Verlet().integrate_dropin(s, el, 1e-5)
+    b = api.Verlet().integrate_fused(s, el, 1e-5)
+    for f in ("x", "y", "z", "vx", "vy", "vz"):
+        assert np.array_equal(a[f], b[f]), f

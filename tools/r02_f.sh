@@ -1,0 +1,16 @@
+set -x
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_r02f.log 2>&1; echo pytest rc=$?; tail -12 gpurun_out/pytest_gpu_r02f.log
+for w in c3 c3o; do
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 2 --steps 100 --warmup 5 --skip-extras --workload $w > gpurun_out/bench_r02f_${w}_g2.json 2> gpurun_out/bench_r02f_${w}_g2.err; echo bench2 $w rc=$?
+done
+timeout 400 python bench.py --steps 100 > gpurun_out/bench_r02f_c3.json 2> gpurun_out/bench_r02f_c3.err; echo bench rc=$?; tail -3 gpurun_out/bench_r02f_c3.err
+python - <<'PY'
+import json
+for f in ("c3_g2","c3o_g2","c3"):
+    try:
+        d=json.load(open(f"gpurun_out/bench_r02f_{f}.json"))
+        print(f, round(d["ms_per_step"],4), d.get("sharding"), [(k["kernel"],k["launches_per_step"],round(k["ms_per_step"]*1e3,1)) for k in d["roofline"]["kernels"]])
+        if "e2e" in d and "resident" in d["e2e"]:
+            e=d["e2e"]; print("e2e", e["ms_per_step"], "resident", e["resident"], "dropin", e["dropin"]["ms_per_step"], "roofline", d["roofline"]["frac"], d["roofline_step"], d["direct_sum"]["interactions_per_s"], d["cpu_baseline"]["value"])
+    except Exception as e: print(f, "ERR", e)
+PY
