@@ -45,13 +45,13 @@ def emit(line):
 
 WORKLOADS = {
     # name: (generator args, element, theta, e, dt)
-    "c3": dict(n=1_000_000, element="astro", theta=1.3, e=1.0, dt=1e-6,
+    "c3": dict(n=1_000_000, stars=4, element="astro", theta=1.3, e=1.0, dt=1e-6,
                desc="cube n=1000000 seed=1 spin=500 + 4 stars ! astro theta=1.3 ! verlet"),
-    "c1": dict(n=100_000, element="astro2", theta=1.5, e=0.5, dt=1e-5,
+    "c1": dict(n=100_000, stars=2, element="astro2", theta=1.5, e=0.5, dt=1e-5,
                desc="cube n=100000 seed=1 spin=1000 + 2 stars ! astro2 theta=1.5 e=0.5 ! verlet"),
     "c5s": dict(n=4_194_304, element="astro2", theta=0.7, e=0.5, dt=1e-6,
                 desc="cube n=4194304 seed=1 ! astro2 theta=0.7 e=0.5 ! verlet (configs[4] at 1/16 size)"),
-    "c3o": dict(n=1_000_000, element="astro2", theta=1.5, e=0.5, dt=1e-5,
+    "c3o": dict(n=1_000_000, stars=4, element="astro2", theta=1.5, e=0.5, dt=1e-5,
                 desc="cube n=1000000 seed=1 spin=500 + 4 stars ! astro2 theta=1.5 e=0.5 ! verlet"),
 }
 
@@ -76,11 +76,22 @@ NCU_KERNELS = "r01d_ncu_c3_kernels.json"  # per-kernel DRAM traffic of the commi
 
 def make_state(w):
     from physim_b200 import generators as gen
-    if w["n"] > 1_000_000:
-        return gen.cube(w["n"], seed=1)
-    if w["n"] == 1_000_000:
+    if w.get("stars") == 4:
         return gen.headline_pipeline(w["n"], seed=1, spin=500.0)
-    return gen.readme_pipeline(w["n"], seed=1, spin=1000.0)
+    if w.get("stars") == 2:
+        return gen.readme_pipeline(w["n"], seed=1, spin=1000.0)
+    return gen.cube(w["n"], seed=1)
+
+
+def workload(name, world=1, scaling="weak"):
+    """The named workload; under weak scaling (N > 1) the SAME simulation grows to N x the body count, one
+    sharded simulation over the N GPUs (BASELINE's own multi-GPU configs are larger problems on more GPUs)."""
+    w = dict(WORKLOADS[name])
+    if world > 1 and scaling == "weak":
+        w["n"] = w["n"] * world
+        w["desc"] = w["desc"].replace("n=%d" % WORKLOADS[name]["n"], "n=%d" % w["n"]) + \
+            f" [weak scaling: {WORKLOADS[name]['n']} bodies per GPU x {world} GPUs, one simulation]"
+    return w
 
 
 def measured_peaks():
@@ -172,24 +183,28 @@ def run_reference(args, w):
     state = make_state(w)
     n = len(state)
     cur = state
-    for _ in range(args.warmup):
+    # bounded sample: about 90 s of CPU work (a 1 M-body step takes 0.6-0.9 s on one core), never more than asked
+    steps_run = max(2, min(args.steps, int(100e6 // max(n, 1)) + 1))
+    warm_run = min(args.warmup, 2)
+    for _ in range(warm_run):
         cur, _ = ob.run_pipeline(w["element"], cur, w["theta"], w["e"], w["dt"], 1)
     t0 = time.perf_counter()
-    cur, secs = ob.run_pipeline(w["element"], cur, w["theta"], w["e"], w["dt"], args.steps)
+    cur, secs = ob.run_pipeline(w["element"], cur, w["theta"], w["e"], w["dt"], steps_run)
     dt = time.perf_counter() - t0
-    value = n * args.steps / dt
+    value = n * steps_run / dt
     model, cores = cpu_info()
     line = {
         "impl": "reference", "metric": "particle-steps/s", "value": value, "unit": "particle-steps/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+        "n_gpus": args.gpus, "steps": steps_run, "steps_requested": args.steps, "warmup": warm_run,
+        "ms_per_step": dt / steps_run * 1e3, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload, "description": w["desc"], "n_bodies": n,
                    "element": w["element"], "theta": w["theta"], "e": w["e"], "dt": w["dt"]},
         "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": 1, "kind": "port",
-                         "sample": f"{args.steps} full steps of the {n}-body workload after {args.warmup} warm-up",
-                         "phases_s_per_step": {"build": secs[0] / args.steps, "walk_force": secs[1] / args.steps,
-                                               "integrate_copies": secs[2] / args.steps},
+                         "sample": f"{steps_run} full steps of the {n}-body workload after {warm_run} warm-up "
+                                   f"(bounded: ~90 s of CPU work; value is per step)",
+                         "phases_s_per_step": {"build": secs[0] / steps_run, "walk_force": secs[1] / steps_run,
+                                               "integrate_copies": secs[2] / steps_run},
                          "cpu": model, "host_cores": cores},
         "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -305,15 +320,18 @@ def run_ours(args, w):
     line = {
         "metric": "particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": args.workload, "description": w["desc"], "n_bodies": n,
                    "element": w["element"], "theta": w["theta"], "e": w["e"], "dt": w["dt"],
                    "n_cells": st["n_cells"], "interactions_per_step": st["interactions"],
-                   "parallelism": ("tree build + walk sharded by Morton key range (cuts at level-K cells, rebalanced "
-                                   "every step), level-K cell records and accelerations all-gathered in-library "
-                                   "(NCCL), remote cells read over NVLink peer memory, integrator state replicated")
+                   "parallelism": ("one simulation over %d GPUs: key encoding sharded by body index, tree build + walk "
+                                   "sharded by Morton key range (cuts at level-K cells, rebalanced every step); keys, "
+                                   "level-K cell records and accelerations stored into the peers' HBM from inside the "
+                                   "kernels over NVLink (epoch flags, no collective call per step), remote cells read "
+                                   "through peer pointers in the walk, integrator state replicated" % world)
                    if world > 1 else "single GPU",
+                   "bodies_per_gpu": n // world,
                    "l2": "no flush: per-step working set (~0.4 GB) exceeds the 126 MB L2; steps run "
                          "back to back as in the simulation loop",
                    "precision": "keys/tree/acceptance/integrator fp64, force law fp32"},
@@ -330,6 +348,7 @@ def run_ours(args, w):
         line["direct_sum"] = measure_direct(api, args, hbm_peak)
         line["cpu_baseline"] = measure_cpu(state, w)
         line["integrators"] = measure_integrators(api, state, w)
+        line["other_workloads"] = measure_other_workloads(api, args)
     if world > 1:
         bodies, cells = sim.rank_counts()
         line["sharding"] = {"sharded_steps": st.get("sharded_steps"), "replicated_steps": st.get("replicated_steps"),
@@ -340,6 +359,13 @@ def run_ours(args, w):
         ds = measure_direct_multi(api, rank, world, local_rank, dist, torch)
         if rank == 0:
             line["direct_sum"] = ds
+    if (world == 1 or world >= 8) and not args.skip_extras:
+        if world > 1:
+            sim.close()
+        sim = state = None  # (frees the 1-GPU handle: its buffers go with the last reference)
+        bl = measure_bh_large(api, torch, dist, rank, world, local_rank)
+        if rank == 0:
+            line["bh_large"] = bl
     if rank == 0 and world > 1:
         line["e2e"] = {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0,
                        "d2h_bytes_per_step": 0,
@@ -509,6 +535,86 @@ def measure_direct_multi(api, rank, world, local_rank, dist, torch):
                          "frac": tf / nominal}}
 
 
+def measure_bh_large(api, torch, dist, rank, world, local_rank):
+    """BASELINE configs[4]: cube n=2^26 ! astro2 theta=0.7 e=0.5 ! verlet, the bodies made on the device from the
+    reference's ChaCha8 `cube seed=1` stream.  One GPU: the single-GPU step (global radix sort).  8 GPUs: one
+    simulation sharded by Morton key range (2 and 4 GPUs would hold more bodies per rank than the shared-memory
+    bucket sort of the sharded build takes, so they are not run)."""
+    n = 1 << 26
+    w = dict(element="astro2", theta=0.7, e=0.5, dt=1e-6)
+    out = {"workload": "cube n=67108864 seed=1 ! astro2 theta=0.7 e=0.5 ! verlet", "n_gpus": world}
+    try:
+        if world == 1:
+            sim = api.Sim(w["element"], theta=w["theta"], e=w["e"], dt=w["dt"])
+        else:
+            sim = make_msim(api, torch, dist, w, rank, world, local_rank)
+        sim.generate_cube(n, seed=1)
+        sim.run(3)  # first step (replicated, plans the shards) + two regular steps
+        steps = 5
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        ms = sim.run_timed(steps)
+        if dist:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        st = sim.stats()
+        out.update({"ms_per_step": ms / steps, "value": n * steps / (ms * 1e-3), "unit": "particle-steps/s",
+                    "steps": steps, "n_cells": st["n_cells"], "interactions_per_step": st["interactions"],
+                    "interactions_per_s": st["interactions"] * steps / (ms * 1e-3)})
+        if world > 1:
+            bodies, _ = sim.rank_counts()
+            out["sharding"] = {"sharded_steps": st.get("sharded_steps"), "replicated_steps": st.get("replicated_steps"),
+                               "replays": st["replays"],
+                               "bodies_per_rank": None if bodies is None else [int(b) for b in bodies]}
+            sim.close()
+        del sim
+    except Exception as e:  # noqa: BLE001  (the headline line must still be printed)
+        out["error"] = repr(e)
+    return out
+
+
+def measure_other_workloads(api, args):
+    """The other BASELINE configurations that fit one GPU, device-resident (state in HBM), so that they appear in
+    the driver's record: c1 (configs[0]), c3o (north_star's target config: 1 M bodies, astro2 theta=1.5, with its
+    own end-to-end and CPU legs), c5s (configs[4] at 1/16 size)."""
+    out = {}
+    for name, steps in (("c1", 400), ("c3o", 100), ("c5s", 20)):
+        w = workload(name)
+        state = make_state(w)
+        n = len(state)
+        sim = api.Sim(w["element"], theta=w["theta"], e=w["e"], dt=w["dt"])
+        sim.upload(state)
+        sim.run_timed(5)
+        ms = sim.run_timed(steps)
+        st = sim.stats()
+        row = {"description": w["desc"], "n_bodies": n, "ms_per_step": ms / steps, "value": n * steps / (ms * 1e-3),
+               "unit": "particle-steps/s", "steps": steps, "n_cells": st["n_cells"],
+               "interactions_per_step": st["interactions"], "sort_mode": st["sort_mode"]}
+        del sim
+        if name == "c3o":
+            el = api.TransformElement(w["element"], theta=w["theta"], e=w["e"])
+            v = api.Verlet()
+            bufs = [state.copy(), state.copy()]
+            cur = 0
+            for _ in range(3):
+                v.integrate_fused(bufs[cur], el, w["dt"], out=bufs[cur ^ 1])
+                cur ^= 1
+            k = 30
+            t0 = time.perf_counter()
+            for _ in range(k):
+                v.integrate_fused(bufs[cur], el, w["dt"], out=bufs[cur ^ 1])
+                cur ^= 1
+            dt = (time.perf_counter() - t0) / k
+            row["e2e"] = {"value": n / dt, "unit": "particle-steps/s", "ms_per_step": dt * 1e3,
+                          "h2d_bytes_per_step": n * 33, "d2h_bytes_per_step": n * 48,
+                          "api": "pb200_verlet_step_fused(host Entity[n] -> host Entity[n])"}
+            row["cpu_baseline"] = measure_cpu(state, w, budget=4e6)
+        out[name] = row
+    return out
+
+
 def measure_integrators(api, state, w):
     """the same workload under `euler` and `rk4` (four force evaluations per step),
     device-resident, next to the CPU oracle's loop (1 thread, bounded number of steps)."""
@@ -530,11 +636,11 @@ def measure_integrators(api, state, w):
     return out
 
 
-def measure_cpu(state, w):
+def measure_cpu(state, w, budget=12e6):
     from oracle import binding as ob
     ob.build()
     n = len(state)
-    steps = max(2, min(10, int(12e6 // max(n, 1))))  # about 10-20 s of CPU work
+    steps = max(2, min(10, int(budget // max(n, 1))))  # about 10-20 s of CPU work
     t0 = time.perf_counter()
     _, secs = ob.run_pipeline(w["element"], state, w["theta"], w["e"], w["dt"], steps)
     dt = time.perf_counter() - t0
@@ -555,8 +661,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--skip-extras", action="store_true", help="skip e2e / direct-sum / cpu legs")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = N x the workload's bodies in one sharded simulation (default), strong = the same bodies")
     args = ap.parse_args()
-    w = WORKLOADS[args.workload]
+    world = int(os.environ.get("WORLD_SIZE", "1")) if args.impl == "ours" else args.gpus
+    w = workload(args.workload, max(world, 1), args.scaling)
     if args.impl == "reference":
         run_reference(args, w)
     else:

@@ -106,6 +106,7 @@ struct ShardPeers {  // every rank's buffers as this device sees them (own rank:
   void* top_meta[8];
   void* xacc[8];
   void* flags[8];
+  void* keys[8];
   uint32_t capacity;          // cells (the smallest table of any rank)
 };
 struct ShardState {
@@ -119,7 +120,8 @@ struct ShardState {
   DevBuf top_ce, top_com, top_info;  // dense top tree (levels 0..K); its level-K entries are written by their owners
   DevBuf top_meta;        // u32: per-rank bodies / cells / abandoned-build flags, double-buffered by epoch parity
   DevBuf xacc;            // [world] x { float4 acc[n_cap], u32 perm[n_cap] }: block r written by rank r's walk
-  DevBuf flags;           // u32: [0..7] "export of epoch e done" per rank, [8..15] "walk done", [16..18] local counters / timeout
+  DevBuf flags;           // u32 epochs per phase and rank (SHARD_FLAG_*), stored by the peers
+  DevBuf keys_all;        // u64[n]: every body's key of the current build; slice r computed and stored by rank r
   ShardPeers peers;
   size_t xacc_block_bytes() const { return n_cap * 20; }
   void release();
@@ -273,7 +275,9 @@ __device__ __forceinline__ void pb_pdl_sync() {
 // Cross-GPU signalling of the sharded step: flags are u32 epochs in the CONSUMER's memory, stored by the producers
 // through peer mappings.  Bounded spin: a rank that never signals (a crashed peer) leaves flags[18] set and the
 // wait returns - the results are then garbage and the host's next check reports the error instead of a hung GPU.
-constexpr int SHARD_FLAG_EXPORT = 0, SHARD_FLAG_WALK = 8, SHARD_CNT_EXPORT = 16, SHARD_CNT_WALK = 17, SHARD_TIMEOUT = 18;
+// [0..7] "rank r's level-K records of epoch e are in place", [8..15] "... accelerations ...", [16..23] "... keys ...",
+// [24] a wait gave up
+constexpr int SHARD_FLAG_EXPORT = 0, SHARD_FLAG_WALK = 8, SHARD_FLAG_KEYS = 16, SHARD_TIMEOUT = 24;
 __device__ __forceinline__ void shard_wait_flag(uint32_t* flags, int slot, uint32_t epoch) {
   volatile uint32_t* f = flags + slot;
   unsigned spins = 0;
@@ -330,6 +334,8 @@ cudaError_t gravity_evaluate(GravityWorkspace& ws, const GravityParams& prm, siz
 //   gravity_shard_build   tree of this rank's key range; its level-K records stored into EVERY rank's dense top tree
 //   gravity_shard_walk    cells above level K, walk of this rank's bodies; accelerations (sorted order) and the
 //                         permutation stored into block `rank` of EVERY rank's shard.xacc
+//   gravity_shard_scatter waits for every rank's block, then ws.acc[i] (original order, all bodies) for the
+//                         integrator - every rank advances the whole replicated state
 // shard.peers must hold every rank's buffers (peer-mapped) before gravity_shard_build; shard.epoch is advanced
 // by gravity_shard_build.
 cudaError_t gravity_shard_setup(GravityWorkspace& ws, int kind, int rank, int world, size_t n);
@@ -337,6 +343,7 @@ bool gravity_shard_fits(const GravityWorkspace& ws);  // the per-rank capacity i
 cudaError_t gravity_shard_plan(GravityWorkspace& ws, cudaStream_t stream, LaunchStats& ls);
 cudaError_t gravity_shard_build(GravityWorkspace& ws, const GravityParams& prm, cudaStream_t stream, LaunchStats& ls);
 cudaError_t gravity_shard_walk(GravityWorkspace& ws, const GravityParams& prm, cudaStream_t stream, LaunchStats& ls);
+cudaError_t gravity_shard_scatter(GravityWorkspace& ws, cudaStream_t stream, LaunchStats& ls);
 // Host-side verdict on the last tree build (one small D2H + stream sync).  Also feeds the next
 // evaluation: cell-table capacity follows the observed total, the sort drops the key bits below
 // the observed tree depth (+2 levels) and is re-validated every time.
@@ -378,11 +385,6 @@ cudaError_t verlet_update_lean(const double4* cur, double4* prev_inout, const fl
                                unsigned long long* extent_last, cudaStream_t st, LaunchStats& ls);
 // the same step on every rank of a sharded run: body perm[r][j] takes acc[r][j] for j < n_locals[r] (the gathered
 // blocks of ShardState::xacc, n_cap records each)
-// Waits until every rank's walk of `epoch` has signalled (flags[8 + r] >= epoch).
-cudaError_t verlet_update_lean_sharded(const double4* cur, double4* prev_inout, const void* xacc, size_t n_cap,
-                                       int world, const uint32_t* n_locals, uint32_t* flags, uint32_t epoch, double dt,
-                                       unsigned long long* extent_out, unsigned long long* extent_zero,
-                                       unsigned long long* extent_last, cudaStream_t st, LaunchStats& ls);
 cudaError_t verlet_velocity(const double4* cur, const double4* prev, double4* vel, size_t n, double dt,
                             cudaStream_t st, LaunchStats& ls);
 cudaError_t verlet_update(double4* cur, double4* prev, double4* vel, const float4* acc32,

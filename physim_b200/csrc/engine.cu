@@ -564,8 +564,8 @@ cudaError_t verlet_step_fused_resident(VerletObj& v, TransformObj& t, const Enti
     v.resident_misses += 1;
     PB_CUDA(cudaMemcpyAsync(v.ent80.p, entities, bytes, cudaMemcpyHostToDevice, st));
     PB_PASS(entity_split(v.ent80.p, n, v.cur.as<double4>(), v.vel.as<double4>(), v.fixed.as<uint8_t>(), st, v.ls));
-    // a state that is not the one this handle produced: the stored previous positions do not belong to it
-    first = true;
+    // (same n: the regular step still uses the previous call's input as x_{n-1}, whatever this input is - exactly
+    // what verlet.rs:52-82 does with its stored previous_state)
   } else {
     v.resident_hits += 1;
   }

@@ -38,6 +38,31 @@ struct NRef {
   __device__ __forceinline__ size_t get() const { return dev ? size_t(*dev) : size_t(host); }
 };
 
+// Where a rank's kernels store what the other ranks need (own rank included: local pointers).
+struct PeerTargets {
+  uint4* top_info[8];
+  double4* top_com[8];
+  uint32_t* meta[8];
+  char* xacc[8];
+  uint32_t* flags[8];
+  uint64_t* keys[8];
+  int world, rank;
+};
+
+// Producer -> consumer hand-over between ranks.  A producer kernel (keys, level-K records, accelerations) only
+// stores into the peers' buffers.  The kernel that FOLLOWS it on the same stream - launched in plain stream order,
+// so the producer grid has completed and its stores are performed - begins with shard_signal_then_wait: one thread
+// tells every rank "this rank's part of `epoch` is in place" (system fence, then the epoch into the peers' flag
+// words), then the kernel waits until every rank has said so.  No fence or atomic in the producers.
+__device__ __forceinline__ void shard_signal_then_wait(const PeerTargets& pt, int slot, uint32_t epoch, bool signaller) {
+  if (signaller && threadIdx.x == 0) {
+    __threadfence_system();
+    for (int r = 0; r < pt.world; ++r) *reinterpret_cast<volatile uint32_t*>(pt.flags[r] + slot + pt.rank) = epoch;
+  }
+  if (int(threadIdx.x) < pt.world) shard_wait_flag(pt.flags[pt.rank], slot + int(threadIdx.x), epoch);
+  __syncthreads();
+}
+
 template <int DIM>
 struct TreeDim {
   static constexpr int LM = (DIM == 3) ? 21 : 31;  // key levels: 63 / 62 bits
@@ -478,6 +503,116 @@ __global__ void __launch_bounds__(256) encode_bucket_kernel(const double4* __res
   for (int e = 0; e < ENC_ITEMS; ++e) {
     const size_t i = tile + size_t(e) * 256 + tid;
     if (keep[e]) {
+      const unsigned slot = gbase[d[e]] + r[e];
+      if (slot < cap) {  // else: bucket over capacity, sort_local_kernel flags the build
+        bkey[size_t(d[e]) * cap + slot] = k[e];
+        bidx[size_t(d[e]) * cap + slot] = static_cast<uint32_t>(i);
+      }
+    }
+  }
+}
+
+// Sharded build, keys: the FP64 compare-and-halve chain (the expensive half of encode_bucket_kernel) is done once per
+// body in the whole job - rank r encodes the bodies of index slice r and stores the keys into EVERY rank's keys_all
+// (coalesced 8-byte stores over NVLink) - and bucket_append_kernel then runs over all bodies on every rank, reading
+// keys instead of computing them.
+template <int DIM>
+__global__ void __launch_bounds__(256) encode_keys_kernel(const double4* __restrict__ pos, size_t i0, size_t i1,
+                                                          const unsigned long long* __restrict__ extent_bits,
+                                                          PeerTargets pt) {
+  pb_pdl_sync();
+  constexpr int LM = TreeDim<DIM>::LM;
+  const double ext0 = __longlong_as_double(static_cast<long long>(*extent_bits));
+  const size_t tile = i0 + size_t(blockIdx.x) * (256 * ENC_ITEMS);
+  double px[ENC_ITEMS], py[ENC_ITEMS], pz[ENC_ITEMS], cx[ENC_ITEMS], cy[ENC_ITEMS], cz[ENC_ITEMS];
+  uint64_t k[ENC_ITEMS];
+#pragma unroll
+  for (int e = 0; e < ENC_ITEMS; ++e) {
+    const size_t i = tile + size_t(e) * 256 + threadIdx.x;
+    const double4 p = i < i1 ? pos[i] : make_double4(0.0, 0.0, 0.0, 0.0);
+    px[e] = p.x; py[e] = p.y; pz[e] = p.z;
+    cx[e] = cy[e] = cz[e] = 0.0;
+    k[e] = 0;
+  }
+  double half = ext0;
+#pragma unroll 1
+  for (int l = 0; l < LM; ++l) {
+    half *= 0.5;  // == extent / 2.0 in IEEE arithmetic
+#pragma unroll
+    for (int e = 0; e < ENC_ITEMS; ++e) {  // independent chains: the compare/add latency overlaps
+      const bool bx = px[e] > cx[e], by = py[e] > cy[e];
+      unsigned digit = unsigned(bx) | (unsigned(by) << 1);
+      cx[e] += with_sign(half, !bx);
+      cy[e] += with_sign(half, !by);
+      if (DIM == 3) {
+        const bool bz = pz[e] > cz[e];
+        digit |= unsigned(bz) << 2;
+        cz[e] += with_sign(half, !bz);
+      }
+      k[e] = (k[e] << DIM) | digit;
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < ENC_ITEMS; ++e) {
+    const size_t i = tile + size_t(e) * 256 + threadIdx.x;
+    if (i < i1)
+      for (int r = 0; r < pt.world; ++r) pt.keys[r][i] = k[e];
+  }
+}
+
+template <unsigned NB>
+__global__ void __launch_bounds__(256) bucket_append_kernel(const uint64_t* __restrict__ keys_all, size_t n,
+                                                            const uint64_t* __restrict__ splitters, int lo,
+                                                            uint64_t* __restrict__ bkey, uint32_t* __restrict__ bidx,
+                                                            unsigned cap, unsigned* __restrict__ cursor,
+                                                            const uint64_t* __restrict__ cuts, PeerTargets pt,
+                                                            uint32_t epoch) {
+  pb_pdl_sync();
+  __shared__ unsigned cnt[NB];
+  __shared__ unsigned gbase[NB];
+  __shared__ uint64_t spl[NB];
+  const int tid = threadIdx.x;
+  // this rank's slice of the keys (encode_keys_kernel, just completed on this stream) is in place everywhere
+  shard_signal_then_wait(pt, SHARD_FLAG_KEYS, epoch, blockIdx.x == 0);
+#pragma unroll
+  for (unsigned j = tid; j < NB; j += 256) {
+    cnt[j] = 0u;
+    spl[j] = j ? (splitters[j] >> lo) : 0ull;
+  }
+  __syncthreads();
+  const uint64_t cut_lo = cuts[0], cut_hi = cuts[1];
+  const size_t tile = size_t(blockIdx.x) * (256 * ENC_ITEMS);
+  uint64_t k[ENC_ITEMS];
+  unsigned r[ENC_ITEMS], d[ENC_ITEMS];
+  bool keep[ENC_ITEMS];
+#pragma unroll
+  for (int e = 0; e < ENC_ITEMS; ++e) {
+    const size_t i = tile + size_t(e) * 256 + tid;
+    k[e] = i < n ? keys_all[i] : 0ull;
+  }
+#pragma unroll
+  for (int e = 0; e < ENC_ITEMS; ++e) {
+    const size_t i = tile + size_t(e) * 256 + tid;
+    keep[e] = i < n && k[e] >= cut_lo && k[e] < cut_hi;
+    const uint64_t kk = k[e] >> lo;
+    unsigned b = 0;
+#pragma unroll
+    for (unsigned step = NB >> 1; step > 0; step >>= 1)
+      if (spl[b + step] <= kk) b += step;
+    d[e] = b;
+    r[e] = keep[e] ? atomicAdd(&cnt[b], 1u) : 0u;
+  }
+  __syncthreads();
+#pragma unroll
+  for (unsigned j = tid; j < NB; j += 256) {
+    const unsigned c = cnt[j];
+    if (c) gbase[j] = atomicAdd(&cursor[j], c);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int e = 0; e < ENC_ITEMS; ++e) {
+    if (keep[e]) {
+      const size_t i = tile + size_t(e) * 256 + tid;
       const unsigned slot = gbase[d[e]] + r[e];
       if (slot < cap) {  // else: bucket over capacity, sort_local_kernel flags the build
         bkey[size_t(d[e]) * cap + slot] = k[e];
@@ -1109,6 +1244,10 @@ struct ShardBuild {
   size_t n_cap;          // capacity of the per-rank arrays, in bodies
   TopSlots slots;
   uint32_t* perm_out;    // where the sort leaves the permutation (the rank's block of the exchange buffer)
+  uint64_t* keys_all;    // every body's key: slice [i0, i1) encoded here and stored into every rank's copy
+  size_t i0, i1;
+  PeerTargets pt;
+  uint32_t epoch;
 };
 
 struct BuildOut {
@@ -1698,37 +1837,9 @@ __global__ void __launch_bounds__(256) walk_kernel(const double4* __restrict__ s
 //      (verlet_lean_sharded_kernel, which waits for all ranks' signals).  No collective call per step.
 // The cuts for the next step come for free: step 3 sees the level-K histogram of ALL bodies.
 // ---------------------------------------------------------------------------------------------
-// Where a rank's kernels store what the other ranks need (own rank included: local pointers).
-struct PeerTargets {
-  uint4* top_info[8];
-  double4* top_com[8];
-  uint32_t* meta[8];
-  char* xacc[8];
-  uint32_t* flags[8];
-  int world, rank;
-};
-
 // meta layout (u32), double-buffered by the parity of the epoch (a rank one phase ahead already writes the next
 // step's counts while a slower rank's verlet still reads this step's):
 constexpr int META_STRIDE = 32, META_BODIES = 1, META_CELLS = 9, META_BAD = 17, META_ANY_BAD = 64;
-
-// End of a producer kernel: when the last CTA has passed (all peer stores of the grid performed), tell every
-// rank that this rank's phase of `epoch` is complete.  (threadFenceReduction pattern, system scope.)
-__device__ __forceinline__ void shard_signal(const PeerTargets& pt, int slot, int counter, uint32_t epoch) {
-  // one system-scope fence per CTA, by the thread that counts the CTA in: the barrier orders the other threads'
-  // stores before it and the fence is cumulative (a fence per thread waits out an NVLink round trip per warp)
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence_system();
-    uint32_t* mine = pt.flags[pt.rank];
-    const unsigned done = atomicAdd(mine + counter, 1u) + 1u;
-    if (done == gridDim.x * gridDim.y) {
-      mine[counter] = 0u;  // (the next launch of this phase is stream-ordered behind this one)
-      __threadfence_system();
-      for (int r = 0; r < pt.world; ++r) *reinterpret_cast<volatile uint32_t*>(pt.flags[r] + slot + pt.rank) = epoch;
-    }
-  }
-}
 
 // Step 2: one thread per level-K prefix.  The prefixes of this rank's key range - cuts[rank] .. cuts[rank+1],
 // every prefix belongs to exactly one rank - get their record (or "no body") in EVERY rank's dense top tree:
@@ -1773,7 +1884,6 @@ __global__ void __launch_bounds__(256) top_export_kernel(const uint32_t* __restr
       pt.top_com[r][TT::offset(TT::K) + q] = com;
     }
   }
-  shard_signal(pt, SHARD_FLAG_EXPORT, SHARD_CNT_EXPORT, epoch);
 }
 
 // Dense top tree, levels 0..K (index TopTree::offset(level) + prefix), identical on every rank.
@@ -1785,13 +1895,13 @@ struct TopView {
   uint64_t* cuts;       // [world + 1] key cuts for the NEXT build (balanced on this step's level-K histogram)
 };
 
-// Step 3 (one CTA): waits for every rank's records, then rebuilds the cells above level K from their children in
+// Step 3 (one CTA): signals this rank's records, waits for every rank's, then rebuilds the cells above level K from their children in
 // ascending digit order with ComSum - the single-GPU build's operations on the same cells.  Level K-1 reads the
 // level-K entries from global memory (one round of loads), the levels above live in shared memory.
 template <int DIM>
 __global__ void __launch_bounds__(1024) top_build_kernel(int world, size_t n_total,
                                                          const unsigned long long* __restrict__ extent_bits,
-                                                         TopView top, uint32_t* flags, uint32_t epoch) {
+                                                         TopView top, PeerTargets pt, uint32_t epoch) {
   pb_pdl_sync();
   using TT = TopTree<DIM>;
   constexpr int K = TT::K, R = TT::R, LM = TreeDim<DIM>::LM;
@@ -1802,11 +1912,10 @@ __global__ void __launch_bounds__(1024) top_build_kernel(int world, size_t n_tot
   __shared__ unsigned s_cum[1024];
   __shared__ unsigned s_wsum[32];
   const int tid = threadIdx.x;
-  if (tid < world) shard_wait_flag(flags, SHARD_FLAG_EXPORT + tid, epoch);
-  __syncthreads();
+  shard_signal_then_wait(pt, SHARD_FLAG_EXPORT, epoch, true);  // this rank's records (top_export_kernel) are in place
   const double ext0 = __longlong_as_double(static_cast<long long>(*extent_bits));
   if (tid == 0) {
-    unsigned bad = flags[SHARD_TIMEOUT];
+    unsigned bad = pt.flags[pt.rank][SHARD_TIMEOUT];
     for (int r = 0; r < world; ++r) bad |= top.meta[int(epoch & 1u) * META_STRIDE + META_BAD + r];
     top.meta[META_ANY_BAD] = bad;
   }
@@ -2022,7 +2131,23 @@ __global__ void __launch_bounds__(256) walk_sharded_kernel(const double4* __rest
       if (r != pt.rank) reinterpret_cast<uint32_t*>(pt.xacc[r] + block + n_cap * sizeof(float4))[s] = orig;
     }
   }
-  shard_signal(pt, SHARD_FLAG_WALK, SHARD_CNT_WALK, epoch);
+}
+
+// Step 5: signals this rank's accelerations (walk_sharded_kernel, just completed on this stream), waits for every
+// rank's, then puts block r's record j where the integrator reads it: acc[perm_r[j]] (original order, all bodies).
+// Coalesced 20-byte reads, 16-byte scattered stores; the lean verlet step that follows is the single-GPU one.
+__global__ void __launch_bounds__(256) shard_scatter_kernel(const char* __restrict__ xacc, size_t n_cap,
+                                                            const uint32_t* __restrict__ n_locals, PeerTargets pt,
+                                                            uint32_t epoch, float4* __restrict__ acc, size_t n) {
+  shard_signal_then_wait(pt, SHARD_FLAG_WALK, epoch, blockIdx.x == 0 && blockIdx.y == 0);
+  const unsigned r = blockIdx.y;
+  const size_t n_r = min(size_t(n_locals[r]), n_cap);
+  const size_t j = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  if (j >= n_r) return;
+  const char* block = xacc + size_t(r) * (n_cap * 20);
+  const float4 a = reinterpret_cast<const float4*>(block)[j];
+  const uint32_t i = reinterpret_cast<const uint32_t*>(block + n_cap * sizeof(float4))[j];
+  if (i < n) acc[i] = a;
 }
 
 // After a full (replicated) build: the first cuts, balanced on the sorted keys, and the splitters of this
@@ -2203,7 +2328,7 @@ __device__ __forceinline__ void direct_tiles(const float* __restrict__ soa, size
                                              unsigned n_tiles, float (*tile)[5][DIRECT_TILE], uint64_t* full,
                                              const f32x2 (&px)[T], const f32x2 (&py)[T], const f32x2 (&pz)[T],
                                              f32x2 (&ax)[T], f32x2 (&ay)[T], f32x2 (&az)[T], f32x2 e2,
-                                             f32x2 tiny2) {
+                                             f32x2 tiny2, double (*wide)[DIRECT_THREADS]) {
   constexpr int NARR = FOLDED ? 5 : 4;  // x y z 1/m e/m  |  x y z m
   constexpr unsigned kTileBytes = unsigned(NARR) * DIRECT_TILE * sizeof(float);
   auto issue = [&](unsigned t) {  // tile t of this split -> buffer t & 1
@@ -2267,6 +2392,20 @@ __device__ __forceinline__ void direct_tiles(const float* __restrict__ soa, size
         }
       }
     }
+    // The fp32 accumulators only ever hold ONE tile's terms (512 per packed lane); the tiles are added in fp64.
+    // At 2^24 sources a single fp32 running sum per lane drifts to ~1e-3 of the (heavily cancelling) net force;
+    // per-tile flushing keeps the sum at fp32-term accuracy for 24 DADD per 13 k packed FP32 instructions.
+#pragma unroll
+    for (int k = 0; k < T; ++k) {
+      float a0, a1, b0, b1, c0, c1;
+      unpack2(ax[k], a0, a1);
+      unpack2(ay[k], b0, b1);
+      unpack2(az[k], c0, c1);
+      wide[3 * k + 0][threadIdx.x] += double(a0) + double(a1);
+      wide[3 * k + 1][threadIdx.x] += double(b0) + double(b1);
+      wide[3 * k + 2][threadIdx.x] += double(c0) + double(c1);
+      ax[k] = ay[k] = az[k] = pack2(0.f, 0.f);
+    }
     __syncthreads();  // everyone is done with buffer t&1 before it is refilled
   }
 }
@@ -2280,6 +2419,9 @@ __global__ void __launch_bounds__(DIRECT_THREADS) direct_kernel_x2(
   // adjacent, so an aligned 16-byte shared read yields two source pairs.
   __shared__ __align__(128) float tile[2][5][DIRECT_TILE];
   __shared__ __align__(8) uint64_t full[2];
+  // fp64 sums over the tiles, private to each thread (no register cost); dynamic: static shared memory ends at 48 KB
+  extern __shared__ __align__(16) unsigned char direct_dyn[];
+  double (*wide)[DIRECT_THREADS] = reinterpret_cast<double (*)[DIRECT_THREADS]>(direct_dyn);
   const float* gx = soa;
   const float* gy = soa + n_pad;
   const float* gz = soa + 2 * n_pad;
@@ -2316,20 +2458,18 @@ __global__ void __launch_bounds__(DIRECT_THREADS) direct_kernel_x2(
     py[k] = pack2(y, y);
     pz[k] = pack2(z, z);
     ax[k] = ay[k] = az[k] = pack2(0.f, 0.f);
+    wide[3 * k + 0][threadIdx.x] = wide[3 * k + 1][threadIdx.x] = wide[3 * k + 2][threadIdx.x] = 0.0;
   }
   const f32x2 e2 = pack2(easing, easing), tiny2 = pack2(tiny, tiny);
-  if (folded) direct_tiles<T, true>(soa, n_pad, sb, n_tiles, tile, full, px, py, pz, ax, ay, az, e2, tiny2);
-  else direct_tiles<T, false>(soa, n_pad, sb, n_tiles, tile, full, px, py, pz, ax, ay, az, e2, tiny2);
+  if (folded) direct_tiles<T, true>(soa, n_pad, sb, n_tiles, tile, full, px, py, pz, ax, ay, az, e2, tiny2, wide);
+  else direct_tiles<T, false>(soa, n_pad, sb, n_tiles, tile, full, px, py, pz, ax, ay, az, e2, tiny2, wide);
 #pragma unroll
   for (int k = 0; k < T; ++k) {
     const size_t lt = tbase + size_t(k) * DIRECT_THREADS + threadIdx.x;
-    if (lt < n_targets) {
-      float a0, a1, b0, b1, c0, c1;
-      unpack2(ax[k], a0, a1);
-      unpack2(ay[k], b0, b1);
-      unpack2(az[k], c0, c1);
-      part[size_t(blockIdx.y) * n_targets + lt] = make_float4(a0 + a1, b0 + b1, c0 + c1, 0.f);
-    }
+    if (lt < n_targets)
+      part[size_t(blockIdx.y) * n_targets + lt] =
+          make_float4(float(wide[3 * k + 0][threadIdx.x]), float(wide[3 * k + 1][threadIdx.x]),
+                      float(wide[3 * k + 2][threadIdx.x]), 0.f);
   }
 }
 
@@ -2568,7 +2708,23 @@ cudaError_t encode_and_sort(GravityWorkspace& ws, size_t n, const SortBuffers& s
   uint64_t* spl_out = ws.splitters.as<uint64_t>() + SPLITTER_STRIDE * (ws.splitter_cur ^ 1);
   ws.splitter_cur ^= 1;
   *splitters_out = spl_out;  // written by the side job of the scan that follows the sort
-  if (sb.mode != 0) {
+ if (sb.mode != 0 && sh) {
+    const size_t slice = sh->i1 - sh->i0;
+    if (slice)
+      PB_LAUNCH(ls, st, "encode_keys_kernel",
+                pb_launch_pdl(encode_keys_kernel<DIM>, dim3(blocks_for(slice, 256 * ENC_ITEMS)), dim3(256), 0, st, ws.pos64,
+                              sh->i0, sh->i1, ws.extent_cur, sh->pt));
+    // (plain stream order: the kernel signals this rank's keys and waits for the other ranks')
+#define PB_APPEND(NBV)                                                                                          \
+  PB_LAUNCH(ls, st, "bucket_append_kernel",                                                                      \
+            bucket_append_kernel<NBV><<<blocks_for(n, 256 * ENC_ITEMS), 256, 0, st>>>(                          \
+                sh->keys_all, n, spl_in, sb.lo, ws.bucket_key.as<uint64_t>(), ws.bucket_idx.as<uint32_t>(), sb.cap, \
+                sb.ghist, sh->cuts, sh->pt, sh->epoch))
+    if (sb.nb == 256) PB_APPEND(256u);
+    else if (sb.nb == 512) PB_APPEND(512u);
+    else PB_APPEND(1024u);
+#undef PB_APPEND
+  } else if (sb.mode != 0) {
 #define PB_ENCODE(NBV)                                                                                            \
   PB_LAUNCH(ls, st, "encode_bucket_kernel",                                                                      \
             pb_launch_pdl(encode_bucket_kernel<DIM, NBV>, dim3(blocks_for(n, 256 * ENC_ITEMS)), dim3(256), 0, st, \
@@ -2578,6 +2734,8 @@ cudaError_t encode_and_sort(GravityWorkspace& ws, size_t n, const SortBuffers& s
     else if (sb.nb == 512) PB_ENCODE(512u);
     else PB_ENCODE(1024u);
 #undef PB_ENCODE
+  }
+  if (sb.mode != 0) {
     uint32_t* n_out = sh ? sh->n_local : nullptr;
     const uint32_t n_cap = sh ? uint32_t(sh->n_cap) : 0u;
     const size_t smem = sort_local_smem(sb.cap);
@@ -2839,14 +2997,15 @@ cudaError_t direct_evaluate(GravityWorkspace& ws, size_t t0, size_t t1, float ea
   splits = blocks_for(n, int(per));
   PB_PASS(ws.acc_part.ensure(size_t(splits) * n_targets * sizeof(float4)));
   const dim3 grid(tb, splits);
-#define PB_DIRECT(TT)                                                                                  \
-  PB_LAUNCH(ls, st, "direct_kernel_x2",                                                                \
-            direct_kernel_x2<TT><<<grid, DIRECT_THREADS, 0, st>>>(ws.src4.as<float>(), n_pad, per, t0, \
-                                                                  n_targets, easing, tiny, meta,       \
-                                                                  ws.acc_part.as<float4>()))
-  if (T == 4) PB_DIRECT(4);
-  else if (T == 2) PB_DIRECT(2);
-  else PB_DIRECT(1);
+#define PB_DIRECT(TT)                                                                                         \
+  PB_CUDA(cudaFuncSetAttribute(direct_kernel_x2<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize,             \
+                               3 * TT * DIRECT_THREADS * int(sizeof(double))));                               \
+  PB_LAUNCH(ls, st, "direct_kernel_x2",                                                                       \
+            direct_kernel_x2<TT><<<grid, DIRECT_THREADS, 3 * TT * DIRECT_THREADS * sizeof(double), st>>>(     \
+                ws.src4.as<float>(), n_pad, per, t0, n_targets, easing, tiny, meta, ws.acc_part.as<float4>()))
+  if (T == 4) { PB_DIRECT(4); }
+  else if (T == 2) { PB_DIRECT(2); }
+  else { PB_DIRECT(1); }
 #undef PB_DIRECT
   PB_LAUNCH(ls, st, "direct_finish_kernel", direct_finish_kernel<<<blocks_for(n_targets, 256), 256, 0, st>>>(
       ws.acc_part.as<float4>(), int(splits), t0, n_targets, ws.pos64, ws.fixed, uint32_t(n),
@@ -2863,7 +3022,7 @@ inline uint32_t top_cells(int dim) { return dim == 3 ? TopTree<3>::CELLS : TopTr
 }  // namespace
 
 void ShardState::release() {
-  DevBuf* all[] = {&cuts, &n_local, &slot_cell, &top_ce, &top_com, &top_info, &top_meta, &xacc, &flags};
+  DevBuf* all[] = {&cuts, &n_local, &slot_cell, &top_ce, &top_com, &top_info, &top_meta, &xacc, &flags, &keys_all};
   for (DevBuf* b : all) b->release();
   planned = false;
 }
@@ -2893,6 +3052,7 @@ cudaError_t gravity_shard_setup(GravityWorkspace& ws, int kind, int rank, int wo
   PB_PASS(sh.top_meta.ensure(128 * 4));
   PB_PASS(sh.xacc.ensure(size_t(world) * sh.xacc_block_bytes()));
   PB_PASS(sh.flags.ensure(32 * 4));
+  PB_PASS(sh.keys_all.ensure(n * 8 + 64));
   if (fresh) {  // epochs only ever grow: the flags are cleared once, when the buffer is made
     PB_CUDA(cudaMemset(sh.flags.p, 0, 32 * 4));
     PB_CUDA(cudaMemset(sh.top_meta.p, 0, 128 * 4));
@@ -2933,6 +3093,7 @@ PeerTargets peer_targets(const ShardState& sh) {
     pt.meta[r] = static_cast<uint32_t*>(sh.peers.top_meta[q]);
     pt.xacc[r] = static_cast<char*>(sh.peers.xacc[q]);
     pt.flags[r] = static_cast<uint32_t*>(sh.peers.flags[q]);
+    pt.keys[r] = static_cast<uint64_t*>(sh.peers.keys[q]);
   }
   pt.world = sh.world;
   pt.rank = sh.rank;
@@ -2953,6 +3114,13 @@ cudaError_t shard_build(GravityWorkspace& ws, cudaStream_t st, LaunchStats& ls) 
   // the permutation goes straight into this rank's block of the exchange buffer (behind the accelerations)
   sb.perm_out = reinterpret_cast<uint32_t*>(static_cast<char*>(sh.xacc.p) + size_t(sh.rank) * sh.xacc_block_bytes() +
                                             sh.n_cap * sizeof(float4));
+  // keys: this rank encodes index slice `rank` of the (replicated) bodies for everybody
+  const size_t per = (ws.n + size_t(sh.world) - 1) / size_t(sh.world);
+  sb.keys_all = sh.keys_all.as<uint64_t>();
+  sb.i0 = std::min(ws.n, per * size_t(sh.rank));
+  sb.i1 = std::min(ws.n, per * size_t(sh.rank + 1));
+  sb.pt = peer_targets(sh);
+  sb.epoch = sh.epoch;
   BuildOut bo;
   PB_PASS(tree_build<DIM>(ws, &sb, st, ls, &bo));
   PB_LAUNCH(ls, st, "top_export_kernel",
@@ -2971,9 +3139,9 @@ cudaError_t shard_walk(GravityWorkspace& ws, const GravityParams& prm, float eas
               sh.cuts.as<uint64_t>()};
   const size_t smem = size_t(TT::offset(TT::K)) * (sizeof(double4) + sizeof(uint4));
   PB_CUDA(cudaFuncSetAttribute(top_build_kernel<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  // (plain stream order, not a programmatic dependent: see shard_signal_then_wait)
   PB_LAUNCH(ls, st, "top_build_kernel",
-            pb_launch_pdl(top_build_kernel<DIM>, dim3(1), dim3(1024), smem, st, sh.world, ws.n, ws.extent_cur, top,
-                          sh.flags.as<uint32_t>(), sh.epoch));
+            top_build_kernel<DIM><<<1, 1024, smem, st>>>(sh.world, ws.n, ws.extent_cur, top, peer_targets(sh), sh.epoch));
   PeerTables pt;
   for (int r = 0; r < 8; ++r) {
     pt.centre_ext[r] = static_cast<const double4*>(sh.peers.centre_ext[r < sh.world ? r : sh.rank]);
@@ -3002,6 +3170,17 @@ cudaError_t gravity_shard_walk(GravityWorkspace& ws, const GravityParams& prm, c
   const float easing = static_cast<float>(prm.easing);
   const float tiny = (prm.easing >= 3e-5) ? 1e-24f : 1e-11f;
   return prm.kind == PB200_ASTRO ? shard_walk<2>(ws, prm, easing, tiny, st, ls) : shard_walk<3>(ws, prm, easing, tiny, st, ls);
+}
+
+cudaError_t gravity_shard_scatter(GravityWorkspace& ws, cudaStream_t st, LaunchStats& ls) {
+  ShardState& sh = ws.shard;
+  PB_PASS(ws.acc.ensure(ws.n * sizeof(float4)));
+  const uint32_t* n_locals = sh.top_meta.as<uint32_t>() + (sh.epoch & 1u) * uint32_t(META_STRIDE) + uint32_t(META_BODIES);
+  // (plain stream order, not a programmatic dependent: see shard_signal_then_wait)
+  PB_LAUNCH(ls, st, "shard_scatter_kernel",
+            shard_scatter_kernel<<<dim3(blocks_for(sh.n_cap, 256), unsigned(sh.world)), 256, 0, st>>>(
+                static_cast<const char*>(sh.xacc.p), sh.n_cap, n_locals, peer_targets(sh), sh.epoch, ws.acc.as<float4>(), ws.n));
+  return cudaGetLastError();
 }
 
 void GravityWorkspace::release_all() {

@@ -107,7 +107,7 @@ float elapsed_ms(cudaEvent_t a, cudaEvent_t b) {
 
 // what a rank tells the others about the buffers they read or write (exchanged once per plan):
 // cell table (centre_ext, com, skip), dense top tree (info, com), per-rank counts, exchange buffer, flags
-constexpr int kPeerBufs = 8;
+constexpr int kPeerBufs = 9;
 struct PeerRecord {
   uint64_t pid;
   uint64_t capacity;     // cells
@@ -218,7 +218,8 @@ cudaError_t exchange_peers(MultiSim& m) {
     rec.capacity = c->ws.cell_cap;
     const ShardState& sh = c->ws.shard;
     const void* p[kPeerBufs] = {c->ws.c_centre_ext.p, c->ws.c_com.p, c->ws.c_skip.p, sh.top_info.p,
-                                sh.top_com.p,         sh.top_meta.p, sh.xacc.p,      sh.flags.p};
+                                sh.top_com.p,         sh.top_meta.p, sh.xacc.p,      sh.flags.p,
+                                sh.keys_all.p};
     for (int k = 0; k < kPeerBufs; ++k) {
       rec.ptr[k] = reinterpret_cast<uint64_t>(p[k]);
       if (m.local.size() < size_t(m.world)) PB_CUDA(cudaIpcGetMemHandle(&rec.handle[k], const_cast<void*>(p[k])));
@@ -281,6 +282,7 @@ cudaError_t exchange_peers(MultiSim& m) {
       sp.top_meta[r] = q[5];
       sp.xacc[r] = q[6];
       sp.flags[r] = q[7];
+      sp.keys[r] = q[8];
     }
     sp.capacity = uint32_t(std::min<uint64_t>(cap, 0xfffffff0ull));
     c->have_peers = true;
@@ -380,13 +382,11 @@ cudaError_t step_sharded(MultiSim& m) {
   }
   FOR_LOCAL(m, c) PB_PASS(gravity_shard_walk(c->ws, m.prm, c->stream, c->ls));
   FOR_LOCAL(m, c) {
+    PB_PASS(gravity_shard_scatter(c->ws, c->stream, c->ls));
     LeanSlots s;
     PB_PASS(lean_prepare(c, &s));
-    ShardState& sh = c->ws.shard;
-    const uint32_t* n_locals = sh.top_meta.as<uint32_t>() + (sh.epoch & 1u) * 32u + 1u;  // META_STRIDE, META_BODIES
-    PB_PASS(verlet_update_lean_sharded(c->cur.as<double4>(), c->prev.as<double4>(), sh.xacc.p, sh.n_cap, m.world,
-                                       n_locals, sh.flags.as<uint32_t>(), sh.epoch, m.dt, s.out, s.zero, s.last,
-                                       c->stream, c->ls));
+    PB_PASS(verlet_update_lean(c->cur.as<double4>(), c->prev.as<double4>(), c->ws.acc.as<float4>(), m.n, m.dt, s.out,
+                               s.zero, s.last, c->stream, c->ls));
     lean_done(c);
   }
   m.sharded_steps += 1;
@@ -438,7 +438,7 @@ cudaError_t collective_check(MultiSim& m, TreeCheck* out) {
     if (c == m.local[0]) *out = chk;
     if (c->ws.shard.flags.p) {
       uint32_t timed_out = 0;
-      PB_CUDA(cudaMemcpy(&timed_out, c->ws.shard.flags.as<uint32_t>() + 18, 4, cudaMemcpyDeviceToHost));  // SHARD_TIMEOUT
+      PB_CUDA(cudaMemcpy(&timed_out, c->ws.shard.flags.as<uint32_t>() + SHARD_TIMEOUT, 4, cudaMemcpyDeviceToHost));
       if (timed_out) {
         set_error("sharded step: rank %d waited in vain for a peer's signal (a rank stopped or lost its mapping)", c->rank);
         return cudaErrorUnknown;

@@ -115,58 +115,6 @@ __global__ void __launch_bounds__(256) verlet_lean_kernel(const double4* __restr
   }
 }
 
-// The lean step of a sharded run, executed identically on every rank (the integrator state is replicated):
-// rank r's walk left the accelerations of ITS bodies in sorted order, next to the permutation, in block r of
-// the gathered exchange buffer; thread (r, j) advances body perm[r][j].  Coalesced reads of the blocks,
-// 32-byte gathers / scatters of the state.
-__global__ void __launch_bounds__(256) verlet_lean_sharded_kernel(const double4* __restrict__ cur,
-                                                                  double4* __restrict__ prev_inout,
-                                                                  const char* __restrict__ xacc, size_t n_cap,
-                                                                  const uint32_t* __restrict__ n_locals,
-                                                                  uint32_t* flags, uint32_t epoch, int world, double dt2,
-                                                                  unsigned long long* __restrict__ extent_out,
-                                                                  unsigned long long* __restrict__ extent_zero,
-                                                                  unsigned long long* __restrict__ extent_last) {
-  pb_pdl_sync();
-  // every rank's walk of this epoch must have stored its block here (the flags live in this device's memory)
-  if (int(threadIdx.x) < world) shard_wait_flag(flags, SHARD_FLAG_WALK + int(threadIdx.x), epoch);
-  __syncthreads();
-  const size_t j = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
-  const unsigned r = blockIdx.y;
-  if (j == 0 && r == 0) {
-    *extent_last = *extent_zero;
-    *extent_zero = 0ull;
-  }
-  const size_t n_r = n_locals[r];
-  if (size_t(blockIdx.x) * blockDim.x >= n_r) return;
-  double m = 0.0;
-  if (j < n_r) {
-    const char* block = xacc + size_t(r) * (n_cap * 20);
-    const float4 a = reinterpret_cast<const float4*>(block)[j];
-    const uint32_t i = reinterpret_cast<const uint32_t*>(block + n_cap * sizeof(float4))[j];
-    const double4 x = cur[i];
-    const double4 p = prev_inout[i];
-    double4 nx;
-    nx.x = next_pos(x.x, p.x, double(a.x), dt2);
-    nx.y = next_pos(x.y, p.y, double(a.y), dt2);
-    nx.z = next_pos(x.z, p.z, double(a.z), dt2);
-    nx.w = x.w;
-    prev_inout[i] = nx;
-    m = fmax(fmax(fabs(nx.x), fabs(nx.y)), fabs(nx.z));
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-  __shared__ double s[8];
-  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = m;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double v = s[0];
-#pragma unroll
-    for (int w = 1; w < 8; ++w) v = fmax(v, s[w]);
-    if (v > 0.0) atomicMax(extent_out, static_cast<unsigned long long>(__double_as_longlong(v)));
-  }
-}
-
 __global__ void __launch_bounds__(256) verlet_velocity_kernel(const double4* __restrict__ cur,
                                                               const double4* __restrict__ prev,
                                                               double4* __restrict__ vel, size_t n, double dt) {
@@ -336,20 +284,6 @@ cudaError_t entity_merge(void* ent80, size_t n, const double4* pos, const double
   PB_LAUNCH(ls, st, "entity_merge_kernel",
             entity_merge_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(static_cast<double2*>(ent80), n,
                                                                                       pos, vel));
-  return cudaGetLastError();
-}
-
-cudaError_t verlet_update_lean_sharded(const double4* cur, double4* prev_inout, const void* xacc, size_t n_cap,
-                                       int world, const uint32_t* n_locals, uint32_t* flags, uint32_t epoch, double dt,
-                                       unsigned long long* extent_out, unsigned long long* extent_zero,
-                                       unsigned long long* extent_last, cudaStream_t st, LaunchStats& ls) {
-  if (n_cap == 0) return cudaSuccess;
-  const dim3 grid(static_cast<unsigned>((n_cap + 255) / 256), static_cast<unsigned>(world));
-  const double dt2 = dt * dt;  // dt.powi(2)
-  PB_LAUNCH(ls, st, "verlet_lean_sharded_kernel",
-            pb_launch_pdl(verlet_lean_sharded_kernel, grid, dim3(256), 0, st, cur, prev_inout,
-                          static_cast<const char*>(xacc), n_cap, n_locals, flags, epoch, world, dt2, extent_out,
-                          extent_zero, extent_last));
   return cudaGetLastError();
 }
 
