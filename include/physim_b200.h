@@ -329,6 +329,9 @@ int pb200_msim_stats(void *msim, Pb200Stats *out, uint64_t *sharded_steps, uint6
 int pb200_msim_rank_counts(void *msim, uint32_t *bodies, uint32_t *cells);
 /* 0: the local ranks' copies of the replicated state are bit-identical, 1: they differ, -1: error */
 int pb200_msim_replicas_identical(void *msim);
+/* diagnostics: out[0..8] key cuts of local rank 0's next sharded build, [9] bodies its last one kept, [10] epoch,
+   [11] per-rank capacity in bodies, [12] "a wait for a peer gave up" */
+int pb200_msim_debug_shard(void *msim, uint64_t *out13);
 int pb200_msim_profile(void *msim, int enable);
 int pb200_msim_profile_report(void *msim, char *buf, size_t cap);
 

@@ -166,6 +166,7 @@ def lib():
     L.pb200_msim_stats.argtypes = [vp, C.POINTER(Pb200Stats), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.pb200_msim_rank_counts.argtypes = [vp, vp, vp]
     L.pb200_msim_replicas_identical.argtypes = [vp]
+    L.pb200_msim_debug_shard.argtypes = [vp, vp]
     L.pb200_msim_profile.argtypes = [vp, i32]
     L.pb200_msim_profile_report.argtypes = [vp, C.c_char_p, sz]
     _lib = L
@@ -571,6 +572,13 @@ class MultiSim:
         bodies, cells = np.zeros(8, np.uint32), np.zeros(8, np.uint32)
         w = lib().pb200_msim_rank_counts(self._m, _ptr(bodies), _ptr(cells))
         return (bodies[:w].copy(), cells[:w].copy()) if w > 0 else (None, None)
+
+    def debug_shard(self):
+        out = np.zeros(13, dtype=np.uint64)
+        if lib().pb200_msim_debug_shard(self._m, _ptr(out)) != 0:
+            return None
+        return {"cuts": [hex(int(v)) for v in out[:self.world + 1]], "kept": int(out[9]), "epoch": int(out[10]),
+                "capacity": int(out[11]), "wait_gave_up": int(out[12])}
 
     def replicas_identical(self):
         return lib().pb200_msim_replicas_identical(self._m) == 0

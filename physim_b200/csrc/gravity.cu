@@ -175,6 +175,81 @@ __device__ __forceinline__ double with_sign(double half, bool negative) {
   return __hiloint2double(hi, __double2loint(half));
 }
 
+// ---- keys without the chain ------------------------------------------------------------------------
+// The digit of level l says whether p > c_l, c_l being the centre the reference reaches by l rounded additions
+// of +-extent/2^j.  c_l differs from the exact dyadic point c_l* = extent (k / 2^l) by at most l half-ulps of
+// the extent (< 3.4e-15 extent over 31 levels), so for a body that is further than KEY_GUARD x extent from
+// EVERY cell boundary of every level (they all lie on the finest grid) each decision equals the exact one, and
+// the digits are the bits of floor((p + extent) 2^(LM-1) / extent) - three fp64 operations and a bit
+// interleave per axis instead of LM dependent compare/add steps.  The quantised coordinate itself carries
+// < 5e-16 x 2^LM grid units of rounding, far inside the guard.  Bodies inside the guard band of some boundary
+// (2 x KEY_GUARD x 2^(LM-1) of them: 2e-4 of a quadtree's axes, 2e-7 of an octree's), NaNs, infinities and a zero or
+// denormal extent take the chain (key_chain): the reference's operations, always right.
+constexpr double KEY_GUARD = 1e-13;
+
+template <int DIM>
+__device__ __noinline__ uint64_t key_chain(double px, double py, double pz, double ext0) {
+  double half = ext0, cx = 0.0, cy = 0.0, cz = 0.0;
+  uint64_t k = 0;
+#pragma unroll 1
+  for (int l = 0; l < TreeDim<DIM>::LM; ++l) {
+    half *= 0.5;  // == extent / 2.0 in IEEE arithmetic
+    const bool bx = px > cx, by = py > cy;
+    unsigned digit = unsigned(bx) | (unsigned(by) << 1);
+    cx += with_sign(half, !bx);  // x + (-h) == x - h exactly
+    cy += with_sign(half, !by);
+    if (DIM == 3) {
+      const bool bz = pz > cz;
+      digit |= unsigned(bz) << 2;
+      cz += with_sign(half, !bz);
+    }
+    k = (k << DIM) | digit;
+  }
+  return k;
+}
+
+template <int DIM>
+__device__ __forceinline__ uint64_t spread_bits(uint64_t x) {
+  if (DIM == 2) {  // 31 bits -> every second bit
+    x = (x | (x << 16)) & 0x0000ffff0000ffffull;
+    x = (x | (x << 8)) & 0x00ff00ff00ff00ffull;
+    x = (x | (x << 4)) & 0x0f0f0f0f0f0f0f0full;
+    x = (x | (x << 2)) & 0x3333333333333333ull;
+    x = (x | (x << 1)) & 0x5555555555555555ull;
+  } else {  // 21 bits -> every third bit
+    x = (x | (x << 32)) & 0x001f00000000ffffull;
+    x = (x | (x << 16)) & 0x001f0000ff0000ffull;
+    x = (x | (x << 8)) & 0x100f00f00f00f00full;
+    x = (x | (x << 4)) & 0x10c30c30c30c30c3ull;
+    x = (x | (x << 2)) & 0x1249249249249249ull;
+  }
+  return x;
+}
+
+// scale = 2^(LM-1) / extent (one division per thread, key_scale)
+template <int DIM>
+__device__ __forceinline__ double key_scale(double ext0) {
+  return __ddiv_rn(double(1ull << (TreeDim<DIM>::LM - 1)), ext0);
+}
+
+template <int DIM>
+__device__ __forceinline__ uint64_t key_of(double px, double py, double pz, double ext0, double scale) {
+  constexpr int LM = TreeDim<DIM>::LM;
+  constexpr double top = double(1ull << LM), guard = KEY_GUARD * double(1ull << (LM - 1));
+  const double vx = (px + ext0) * scale, vy = (py + ext0) * scale, vz = DIM == 3 ? (pz + ext0) * scale : 0.5;
+  const double fx = floor(vx), fy = floor(vy), fz = floor(vz);
+  const double ex = vx - fx, ey = vy - fy, ez = vz - fz;  // exact (Sterbenz-like: same binade or smaller)
+  // every comparison is written so that a NaN fails it
+  const bool fast = vx > 0.0 && vx < top && vy > 0.0 && vy < top && vz > 0.0 && vz < top &&
+                    ex >= guard && ex <= 1.0 - guard && ey >= guard && ey <= 1.0 - guard &&
+                    (DIM != 3 || (ez >= guard && ez <= 1.0 - guard));
+  if (!fast) return key_chain<DIM>(px, py, pz, ext0);
+  uint64_t k = spread_bits<DIM>(static_cast<uint64_t>(static_cast<long long>(fx))) |
+               (spread_bits<DIM>(static_cast<uint64_t>(static_cast<long long>(fy))) << 1);
+  if (DIM == 3) k |= spread_bits<DIM>(static_cast<uint64_t>(static_cast<long long>(fz))) << 2;
+  return k;
+}
+
 constexpr int SORT_HIST_SLOTS = 8;  // 8 sort passes at most (bucket sort: slot 0 holds the bucket cursors)
 
 // Also accumulates the digit histograms of every sort pass (the keys are in registers anyway),
@@ -190,6 +265,7 @@ __global__ void __launch_bounds__(256) encode_kernel(const double4* __restrict__
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const double ext0 = __longlong_as_double(static_cast<long long>(*extent_bits));
+  const double scale = key_scale<DIM>(ext0);
   const size_t stride = size_t(gridDim.x) * 256;
   // whole warps iterate together (the histogram step is warp-collective)
   for (size_t base = size_t(blockIdx.x) * 256 + (threadIdx.x & ~31); base < n; base += stride) {
@@ -198,22 +274,7 @@ __global__ void __launch_bounds__(256) encode_kernel(const double4* __restrict__
     uint64_t k = 0;
     if (ok) {
       const double4 p = pos[i];
-      double half = ext0;
-      double cx = 0.0, cy = 0.0, cz = 0.0;
-#pragma unroll
-      for (int l = 0; l < TreeDim<DIM>::LM; ++l) {
-        half *= 0.5;  // == extent / 2.0 in IEEE arithmetic
-        const bool bx = p.x > cx, by = p.y > cy;
-        unsigned digit = unsigned(bx) | (unsigned(by) << 1);
-        cx += with_sign(half, !bx);  // x + (-h) == x - h exactly
-        cy += with_sign(half, !by);
-        if (DIM == 3) {
-          const bool bz = p.z > cz;
-          digit |= unsigned(bz) << 2;
-          cz += with_sign(half, !bz);
-        }
-        k = (k << DIM) | digit;
-      }
+      k = key_of<DIM>(p.x, p.y, p.z, ext0, scale);
       key[i] = k;
       idx[i] = static_cast<uint32_t>(i);
     }
@@ -435,7 +496,6 @@ __global__ void __launch_bounds__(256) encode_bucket_kernel(const double4* __res
                                                             const uint64_t* __restrict__ cuts /* sharded build: keep
                                                             cuts[0] <= key < cuts[1]; nullptr: every body */) {
   pb_pdl_sync();
-  constexpr int LM = TreeDim<DIM>::LM;
   constexpr unsigned nb = NB;
   __shared__ unsigned cnt[NB];
   __shared__ unsigned gbase[NB];
@@ -449,34 +509,16 @@ __global__ void __launch_bounds__(256) encode_bucket_kernel(const double4* __res
   __syncthreads();
   const double ext0 = __longlong_as_double(static_cast<long long>(*extent_bits));
   const size_t tile = size_t(blockIdx.x) * (256 * ENC_ITEMS);
-  double px[ENC_ITEMS], py[ENC_ITEMS], pz[ENC_ITEMS], cx[ENC_ITEMS], cy[ENC_ITEMS], cz[ENC_ITEMS];
+  const double scale = key_scale<DIM>(ext0);
+  double4 p[ENC_ITEMS];
   uint64_t k[ENC_ITEMS];
 #pragma unroll
-  for (int e = 0; e < ENC_ITEMS; ++e) {
+  for (int e = 0; e < ENC_ITEMS; ++e) {  // all loads first
     const size_t i = tile + size_t(e) * 256 + tid;
-    const double4 p = i < n ? pos[i] : make_double4(0.0, 0.0, 0.0, 0.0);
-    px[e] = p.x; py[e] = p.y; pz[e] = p.z;
-    cx[e] = cy[e] = cz[e] = 0.0;
-    k[e] = 0;
+    p[e] = i < n ? pos[i] : make_double4(0.0, 0.0, 0.0, 0.0);
   }
-  double half = ext0;
-#pragma unroll 1
-  for (int l = 0; l < LM; ++l) {
-    half *= 0.5;  // == extent / 2.0 in IEEE arithmetic
 #pragma unroll
-    for (int e = 0; e < ENC_ITEMS; ++e) {  // independent chains: the compare/add latency overlaps
-      const bool bx = px[e] > cx[e], by = py[e] > cy[e];
-      unsigned digit = unsigned(bx) | (unsigned(by) << 1);
-      cx[e] += with_sign(half, !bx);
-      cy[e] += with_sign(half, !by);
-      if (DIM == 3) {
-        const bool bz = pz[e] > cz[e];
-        digit |= unsigned(bz) << 2;
-        cz[e] += with_sign(half, !bz);
-      }
-      k[e] = (k[e] << DIM) | digit;
-    }
-  }
+  for (int e = 0; e < ENC_ITEMS; ++e) k[e] = key_of<DIM>(p[e].x, p[e].y, p[e].z, ext0, scale);
   unsigned r[ENC_ITEMS], d[ENC_ITEMS];
   const uint64_t cut_lo = cuts ? cuts[0] : 0ull, cut_hi = cuts ? cuts[1] : ~0ull;
   bool keep[ENC_ITEMS];
@@ -521,37 +563,18 @@ __global__ void __launch_bounds__(256) encode_keys_kernel(const double4* __restr
                                                           const unsigned long long* __restrict__ extent_bits,
                                                           PeerTargets pt) {
   pb_pdl_sync();
-  constexpr int LM = TreeDim<DIM>::LM;
   const double ext0 = __longlong_as_double(static_cast<long long>(*extent_bits));
   const size_t tile = i0 + size_t(blockIdx.x) * (256 * ENC_ITEMS);
-  double px[ENC_ITEMS], py[ENC_ITEMS], pz[ENC_ITEMS], cx[ENC_ITEMS], cy[ENC_ITEMS], cz[ENC_ITEMS];
+  const double scale = key_scale<DIM>(ext0);
+  double4 p[ENC_ITEMS];
   uint64_t k[ENC_ITEMS];
 #pragma unroll
   for (int e = 0; e < ENC_ITEMS; ++e) {
     const size_t i = tile + size_t(e) * 256 + threadIdx.x;
-    const double4 p = i < i1 ? pos[i] : make_double4(0.0, 0.0, 0.0, 0.0);
-    px[e] = p.x; py[e] = p.y; pz[e] = p.z;
-    cx[e] = cy[e] = cz[e] = 0.0;
-    k[e] = 0;
+    p[e] = i < i1 ? pos[i] : make_double4(0.0, 0.0, 0.0, 0.0);
   }
-  double half = ext0;
-#pragma unroll 1
-  for (int l = 0; l < LM; ++l) {
-    half *= 0.5;  // == extent / 2.0 in IEEE arithmetic
 #pragma unroll
-    for (int e = 0; e < ENC_ITEMS; ++e) {  // independent chains: the compare/add latency overlaps
-      const bool bx = px[e] > cx[e], by = py[e] > cy[e];
-      unsigned digit = unsigned(bx) | (unsigned(by) << 1);
-      cx[e] += with_sign(half, !bx);
-      cy[e] += with_sign(half, !by);
-      if (DIM == 3) {
-        const bool bz = pz[e] > cz[e];
-        digit |= unsigned(bz) << 2;
-        cz[e] += with_sign(half, !bz);
-      }
-      k[e] = (k[e] << DIM) | digit;
-    }
-  }
+  for (int e = 0; e < ENC_ITEMS; ++e) k[e] = key_of<DIM>(p[e].x, p[e].y, p[e].z, ext0, scale);
 #pragma unroll
   for (int e = 0; e < ENC_ITEMS; ++e) {
     const size_t i = tile + size_t(e) * 256 + threadIdx.x;
@@ -1396,6 +1419,28 @@ __global__ void __launch_bounds__(256, MIN_BLOCKS) cells_kernel(const uint64_t* 
   const double ext0 = __longlong_as_double(static_cast<long long>(*extent_bits));
   const bool merged_units = tree_meta[1] != 0u;
   const bool is_head = abv.x != NOT_HEAD;  // (lanes past n and merged bodies stay for the shuffles)
+  // Reference path: the centres along the path of the CTA's FIRST body, level by level, computed once by thread 0
+  // while the loads above are in flight.  A body shares its leading `lcp` digits with that body, and the centre at
+  // a level depends on the digits above it only, so every lane starts its own replay at level min(lcp, top)
+  // with the reference's doubles - the same operations on the same operands as a replay from the root, hence
+  // the same bits - and runs ~5 instead of ~11 iterations (256 neighbours of 10^6 sorted bodies share ~6 levels).
+  __shared__ double s_ref[LM + 1][4];
+  __shared__ uint64_t s_refkey;
+  if (threadIdx.x == 0) {
+    s_refkey = kme;  // (s < n for thread 0 of every CTA that gets here, or n == 0 and nobody is a head)
+    double half = ext0, cx = 0.0, cy = 0.0, cz = 0.0;
+    uint64_t digits = kme << (64 - DIM * LM);
+    for (int l = 0; l <= LM; ++l) {
+      s_ref[l][0] = cx; s_ref[l][1] = cy; s_ref[l][2] = cz; s_ref[l][3] = half;
+      const unsigned digit = unsigned(digits >> (64 - DIM));
+      digits <<= DIM;
+      half *= 0.5;
+      cx += with_sign(half, !(digit & 1u));
+      cy += with_sign(half, !(digit & 2u));
+      if (DIM == 3) cz += with_sign(half, !(digit & 4u));
+    }
+  }
+  __syncthreads();
   int top = 0, leaf_level = 0;
   uint32_t c0 = 0;
   if (is_head) {
@@ -1404,15 +1449,16 @@ __global__ void __launch_bounds__(256, MIN_BLOCKS) cells_kernel(const uint64_t* 
     const int a = int(abv.x) - 1, b = int(abv.y) - 1;
     top = a + 1;
     leaf_level = max(a, b) + 1;
-    double half = ext0;
-    double cx = 0.0, cy = 0.0, cz = 0.0;
-    uint64_t digits = kme << (64 - DIM * LM);  // next digit in the top DIM bits
-    for (int l = 0; l <= leaf_level; ++l) {
+    const uint64_t diff = (kme ^ s_refkey) << (64 - DIM * LM);
+    const int lcp = diff ? __clzll(static_cast<long long>(diff)) / DIM : LM;
+    const int l0 = min(min(lcp, top), leaf_level);
+    double half = s_ref[l0][3];
+    double cx = s_ref[l0][0], cy = s_ref[l0][1], cz = s_ref[l0][2];
+    uint64_t digits = l0 < LM ? kme << (64 - DIM * LM + DIM * l0) : 0ull;  // next digit in the top DIM bits (pseudo levels compare the body)
+    for (int l = l0; l <= leaf_level; ++l) {
       if (l >= top) {
         const uint32_t c = c0 + uint32_t(l - top);
         cells.level[c] = static_cast<uint8_t>(l);
-        cells.head[c] = static_cast<uint32_t>(s);
-        cells.arrived[c] = 0u;
         cells.centre_ext[c] = make_double4(cx, cy, cz, half);
       }
       if (l < leaf_level) {  // from level l to level l+1 along the head body's path
@@ -1532,6 +1578,14 @@ __global__ void __launch_bounds__(256) parent_kernel(const uint32_t* __restrict_
     if (next <= ch) break;  // (never in a well-formed table; keeps a broken one from hanging the GPU)
     ch = next;
   }
+}
+
+// cells.head (the first sorted body of every cell) is part of the inspected table only - no kernel of the step
+// reads it - so it is filled when the table is read back: body s heads cells cell_start[s] .. cell_start[s+1]-1.
+__global__ void __launch_bounds__(256) head_kernel(const uint32_t* __restrict__ cell_start, size_t n, CellArrays cells) {
+  const size_t s = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  if (s >= n || cell_start[n] > cells.capacity || *cells.bad) return;
+  for (uint32_t c = cell_start[s]; c < cell_start[s + 1]; ++c) cells.head[c] = static_cast<uint32_t>(s);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1753,6 +1807,9 @@ __device__ __forceinline__ bool accept_cell(double px, double py, double pz, con
   return __ddiv_rn(ce.w, r) < theta;
 }
 
+// (Measured and rejected, r02: prefetch.global.L1 of the three records the skip link points to, issued as soon as
+// the link is known - 46 -> 49 us at c3, 1.71 -> 3.03 ms at 4.2 M bodies / theta 0.7: the prefetches evict the
+// lines the neighbouring lanes are about to reuse.)
 template <int DIM>
 __global__ void __launch_bounds__(256) walk_kernel(const double4* __restrict__ sp,
                                                    const uint32_t* __restrict__ perm,
@@ -1835,7 +1892,7 @@ __global__ void __launch_bounds__(256) walk_kernel(const double4* __restrict__ s
 //   5. stores its accelerations (sorted order) and the permutation into its block of EVERY rank's exchange
 //      buffer from inside the walk kernel and signals; every rank then advances the replicated state
 //      (verlet_lean_sharded_kernel, which waits for all ranks' signals).  No collective call per step.
-// The cuts for the next step come for free: step 3 sees the level-K histogram of ALL bodies.
+// The cuts are planned from a replicated (whole-set) build and stay until the host re-plans (multi.cu).
 // ---------------------------------------------------------------------------------------------
 // meta layout (u32), double-buffered by the parity of the epoch (a rank one phase ahead already writes the next
 // step's counts while a slower rank's verlet still reads this step's):
@@ -1892,7 +1949,7 @@ struct TopView {
   double4* com;         // {X, Y, Z, M}
   uint4* info;          // see top_export_kernel
   uint32_t* meta;       // see META_*
-  uint64_t* cuts;       // [world + 1] key cuts for the NEXT build (balanced on this step's level-K histogram)
+  uint64_t* cuts;       // [world + 1] key cuts of the plan (read only)
 };
 
 // Step 3 (one CTA): signals this rank's records, waits for every rank's, then rebuilds the cells above level K from their children in
@@ -1904,13 +1961,11 @@ __global__ void __launch_bounds__(1024) top_build_kernel(int world, size_t n_tot
                                                          TopView top, PeerTargets pt, uint32_t epoch) {
   pb_pdl_sync();
   using TT = TopTree<DIM>;
-  constexpr int K = TT::K, R = TT::R, LM = TreeDim<DIM>::LM;
-  constexpr uint32_t S = TT::SLOTS, ABOVE = TT::offset(K);  // cells above level K
+  constexpr int K = TT::K, R = TT::R;
+  constexpr uint32_t ABOVE = TT::offset(K);  // cells above level K
   extern __shared__ __align__(16) unsigned char top_smem[];
   double4* s_com = reinterpret_cast<double4*>(top_smem);     // [ABOVE]
   uint4* s_info = reinterpret_cast<uint4*>(s_com + ABOVE);   // [ABOVE]
-  __shared__ unsigned s_cum[1024];
-  __shared__ unsigned s_wsum[32];
   const int tid = threadIdx.x;
   shard_signal_then_wait(pt, SHARD_FLAG_EXPORT, epoch, true);  // this rank's records (top_export_kernel) are in place
   const double ext0 = __longlong_as_double(static_cast<long long>(*extent_bits));
@@ -1984,40 +2039,10 @@ __global__ void __launch_bounds__(1024) top_build_kernel(int world, size_t n_tot
     while (l < K && TT::offset(l + 1) <= t) ++l;
     top.centre_ext[t] = centre_of(l, t - TT::offset(l));
   }
-  // cuts for the next build: rank r starts at the first level-K prefix whose running count reaches r n / world
-  {
-    constexpr uint32_t PER = S / 1024;  // prefixes per thread (4)
-    unsigned mine = 0;
-#pragma unroll
-    for (uint32_t j = 0; j < PER; ++j) mine += top.info[ABOVE + tid * PER + j].w;
-    const unsigned excl = block_exclusive_scan_nt<1024>(mine, s_wsum);
-    s_cum[tid] = excl;
-    __syncthreads();
-    if (tid <= world) {
-      uint64_t cut = 0ull;
-      if (tid == world) {
-        cut = ~0ull;
-      } else if (tid > 0) {
-        const unsigned want = unsigned((n_total * size_t(tid)) / size_t(world));
-        int lo = 0, hi = 1024;  // first group of PER prefixes whose exclusive count >= want
-        while (lo < hi) {
-          const int mid = (lo + hi) / 2;
-          if (s_cum[mid] >= want) hi = mid; else lo = mid + 1;
-        }
-        uint32_t q = uint32_t(lo) * PER;
-        if (lo > 0) {  // the prefix lies inside group lo - 1, or is the first of group lo
-          unsigned run = s_cum[lo - 1];
-          q = uint32_t(lo - 1) * PER;
-          while (q < uint32_t(lo) * PER && run < want) {
-            run += top.info[ABOVE + q].w;
-            ++q;
-          }
-        }
-        cut = uint64_t(q) << (DIM * (LM - K));
-      }
-      top.cuts[tid] = cut;
-    }
-  }
+  // The cuts stay as planned (gravity_shard_plan, from a fully sorted replicated build) until the host re-plans:
+  // the splitters of a rank's buckets are quantiles of ITS range, so a cut that moved by one level-K cell would
+  // pour that cell's bodies (n / 4096 and more) into one edge bucket.  The host watches the per-rank counts
+  // (meta) and re-plans from a replicated step when the balance has drifted.
 }
 
 struct PeerTables {   // every rank's cell table, as seen from this device (own table: local pointers)
@@ -2937,7 +2962,7 @@ cudaError_t tree_evaluate(GravityWorkspace& ws, const GravityParams& prm, size_t
     list = lst;
   }
   if (n_targets) {
-    PB_LAUNCH(ls, st, "walk_kernel", pb_launch_pdl(walk_kernel<DIM>, dim3(blocks_for(n_targets, 256)), dim3(256), 0, st, 
+    PB_LAUNCH(ls, st, "walk_kernel", pb_launch_pdl(walk_kernel<DIM>, dim3(blocks_for(n_targets, 256)), dim3(256), 0, st,
         ws.spos64.as<double4>(), ws.perm, ws.fixed, list, n_targets, ws.cell_start.as<uint32_t>(), n,
         cells, prm.theta, easing, tiny, ws.acc.as<float4>()));
   }
@@ -3299,6 +3324,7 @@ cudaError_t gravity_fill_parents(GravityWorkspace& ws, cudaStream_t st, LaunchSt
                    flags + 2, 0u};
   PB_LAUNCH(ls, st, "parent_kernel",
             parent_kernel<<<blocks_for(ws.cell_cap, 256), 256, 0, st>>>(ws.cell_start.as<uint32_t>(), ws.n, cells));
+  PB_LAUNCH(ls, st, "head_kernel", head_kernel<<<blocks_for(ws.n, 256), 256, 0, st>>>(ws.cell_start.as<uint32_t>(), ws.n, cells));
   ws.parents_filled = true;
   return cudaGetLastError();
 }

@@ -144,7 +144,7 @@ struct MultiSim {
   size_t n = 0, slice = 0;
   bool first = true, checked = false;
   bool shard_ok = true;       // false: sharding given up for this state (a rank's range cannot fit); every step replicated
-  uint64_t replays = 0, sharded_steps = 0, replicated_steps = 0;
+  uint64_t replays = 0, sharded_steps = 0, replicated_steps = 0, replans = 0;
   bool direct() const { return prm.kind == PB200_SIMPLE_ASTRO || !(prm.theta > 0.0); }
   ~MultiSim() {
     for (RankCtx* c : local) {
@@ -448,6 +448,28 @@ cudaError_t collective_check(MultiSim& m, TreeCheck* out) {
   return cudaSuccess;
 }
 
+// The cuts between the ranks' key ranges are fixed by the plan; bodies drift across them.  Every rank holds every
+// rank's body count of the last sharded step (meta): when the fullest rank has used up half of its headroom over
+// n / world, the next step runs replicated and the shards are planned afresh (same verdict on every rank).
+cudaError_t rebalance_if_drifted(MultiSim& m) {
+  if (m.world < 2 || !m.shard_ok || m.sharded_steps == 0) return cudaSuccess;
+  bool replan = false;
+  FOR_LOCAL(m, c) {
+    const ShardState& sh = c->ws.shard;
+    if (!sh.planned || !sh.top_meta.p) continue;
+    uint32_t meta[32];
+    PB_CUDA(cudaMemcpy(meta, sh.top_meta.as<uint32_t>() + (sh.epoch & 1u) * 32u, sizeof meta, cudaMemcpyDeviceToHost));
+    const size_t fair = m.n / size_t(m.world);
+    for (int r = 0; r < m.world; ++r)
+      if (size_t(meta[1 + r]) > fair + (sh.n_cap - fair) / 2) replan = true;
+  }
+  if (replan) {
+    for (RankCtx* c : m.local) c->ws.shard.planned = false;
+    m.replans += 1;
+  }
+  return cudaSuccess;
+}
+
 cudaError_t run_steps(MultiSim& m, size_t steps) {
   if (m.n == 0) return cudaSuccess;
   if (m.direct()) {
@@ -479,6 +501,7 @@ cudaError_t run_steps(MultiSim& m, size_t steps) {
     }
     TreeCheck chk;
     PB_PASS(collective_check(m, &chk));
+    if (chk.ok()) PB_PASS(rebalance_if_drifted(m));
     if (!chk.ok()) {
       if (chk.sort_error) {
         set_error("radix sort look-back did not complete");
@@ -843,6 +866,29 @@ int pb200_msim_rank_counts(void* h, uint32_t* bodies, uint32_t* cells) {
     if (cells) cells[r] = meta[9 + r];
   }
   return m.world;
+}
+
+/* diagnostics of local rank 0's shard plan: out[0..8] the key cuts the next build will use, out[9] bodies kept by the
+   last sharded build, out[10] epoch, out[11] capacity in bodies, out[12] "a wait gave up" flag */
+int pb200_msim_debug_shard(void* h, uint64_t* out13) {
+  if (!h || !out13) return -1;
+  auto& m = *static_cast<MultiSim*>(h);
+  std::lock_guard<std::mutex> lk(m.mu);
+  RankCtx* c = m.local[0];
+  const ShardState& sh = c->ws.shard;
+  std::memset(out13, 0, 13 * 8);
+  if (!sh.cuts.p || !sh.flags.p) return -1;
+  uint32_t nl = 0, to = 0;
+  if (cudaSetDevice(c->device) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess ||
+      cudaMemcpy(out13, sh.cuts.p, 9 * 8, cudaMemcpyDeviceToHost) != cudaSuccess ||
+      cudaMemcpy(&nl, sh.n_local.p, 4, cudaMemcpyDeviceToHost) != cudaSuccess ||
+      cudaMemcpy(&to, sh.flags.as<uint32_t>() + SHARD_TIMEOUT, 4, cudaMemcpyDeviceToHost) != cudaSuccess)
+    return -1;
+  out13[9] = nl;
+  out13[10] = sh.epoch;
+  out13[11] = sh.n_cap;
+  out13[12] = to;
+  return 0;
 }
 
 /* accelerations of the last step's force evaluation, original order (tests; gathers on the host) */

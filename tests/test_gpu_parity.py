@@ -42,7 +42,36 @@ def bucket_twins(seed):
     return np.concatenate([s, twin])
 
 
+def boundary_lattice(ext, seed):
+    """Bodies ON cell boundaries of every level and a few ulps either side of them (the keys' guard band: these
+    take the reference's compare-and-halve chain on the device, everything else the quantised form), distinct in x
+    by >= ext / 4096 so that nothing merges; one body pins the extent to `ext`."""
+    rng = np.random.default_rng(seed)
+    n = 1500
+
+    def near_lattice(k, m):
+        v = ext * (k / 2.0 ** m)
+        d = rng.integers(-2, 3, len(v))
+        for step in (1, 2):
+            v = np.where(d >= step, np.nextafter(v, np.inf), v)
+            v = np.where(d <= -step, np.nextafter(v, -np.inf), v)
+        return v
+
+    s = entities(n + 1)
+    kx = rng.choice(np.arange(-4095, 4096), n, replace=False)
+    s["x"][:n] = near_lattice(kx, np.full(n, 12))
+    for f in ("y", "z"):
+        m = rng.integers(1, 22, n)
+        k = np.array([rng.integers(-(2 ** int(mm)) + 1, 2 ** int(mm)) for mm in m])
+        s[f][:n] = near_lattice(k, m)
+    s["mass"] = rng.uniform(0.5, 2.0, n + 1)
+    s["x"][n], s["y"][n], s["z"][n] = -ext, ext, ext / 3
+    return s
+
+
 TREE_CASES = {
+    "lattice_pow2": lambda: boundary_lattice(1.0, 5),
+    "lattice_ugly": lambda: boundary_lattice(0.7368421052631579, 6),
     "cube20k": lambda: gen.readme_pipeline(20_000, seed=3),
     "merges": lambda: with_merges(7),
     "bucket": lambda: bucket_twins(9),

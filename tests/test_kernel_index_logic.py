@@ -129,3 +129,49 @@ def test_every_climb_start_is_taken_once():
                 it += threads // LISTS
         for l in range(LISTS):
             assert (taken[l] == 1).all()
+
+
+# ---- keys without the compare-and-halve chain (gravity.cu key_of) -----------------------------------------
+def _spread(q, dim):
+    out = np.zeros(len(q), dtype=np.uint64)
+    lm = 31 if dim == 2 else 21
+    for b in range(lm):
+        out |= ((q >> np.uint64(b)) & np.uint64(1)) << np.uint64(dim * b)
+    return out
+
+
+def _key_quantised(s, ext, dim):
+    """Host restatement of key_of's fast path: (keys, which bodies may take it)."""
+    lm = 31 if dim == 2 else 21
+    scale = np.float64(2.0 ** (lm - 1)) / np.float64(ext)
+    guard = 1e-13 * 2.0 ** (lm - 1)
+    fast = np.ones(len(s), dtype=bool)
+    key = np.zeros(len(s), dtype=np.uint64)
+    for a, f in enumerate(("x", "y", "z")[:dim]):
+        v = (s[f] + ext) * scale
+        fl = np.floor(v)
+        e = v - fl
+        fast &= (v > 0.0) & (v < 2.0 ** lm) & (e >= guard) & (e <= 1.0 - guard)
+        key |= _spread(np.where(fast, fl, 0.0).astype(np.int64).astype(np.uint64), dim) << np.uint64(a)
+    return key, fast
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_quantised_keys_equal_the_chain_outside_the_guard_band(dim):
+    """The oracle's keys come from the reference's chain (octree.rs:160-215 centre +- extent/2 per level); the
+    quantised form must give the same 62 / 63 bits for every body it accepts, and must REFUSE the bodies that sit
+    on or within a few ulps of a cell boundary."""
+    from oracle import binding as ob
+    from physim_b200 import generators as gen
+    from tests.test_gpu_parity import boundary_lattice
+    for s, must_refuse in ((gen.cube(200_000, seed=4), False), (gen.readme_pipeline(50_000, seed=2), False),
+                           (boundary_lattice(1.0, 5), True), (boundary_lattice(0.7368421052631579, 6), True)):
+        o = ob.CellTable(dim, s)
+        want = np.zeros(len(s), dtype=np.uint64)
+        want[o.perm] = o.key
+        got, fast = _key_quantised(s, o.extent, dim)
+        assert np.array_equal(got[fast], want[fast])
+        if must_refuse:
+            assert (~fast).sum() > 0.9 * len(s)      # x is always near a level-12 boundary
+        else:
+            assert fast.mean() > 0.99

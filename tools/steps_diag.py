@@ -11,4 +11,4 @@ sim.run_timed(3)
 for chunk in (32, 32, 32, 32, 64, 64, 64, 64):
     ms = sim.run_timed(chunk)
     st = sim.stats()
-    print(chunk, "steps: %.4f ms/step" % (ms / chunk), {k: st[k] for k in ("replays", "sort_bits", "n_cells") if k in st}, flush=True)
+    print(chunk, "steps: %.4f ms/step" % (ms / chunk), {k: st[k] for k in ("replays", "sort_bits", "sort_mode", "max_bucket", "n_cells", "extent") if k in st}, flush=True)
