@@ -71,7 +71,7 @@ ALG_BYTES_PER_BODY = {
 }
 STEP_BYTES_PER_BODY = 550  # "Sum ~ 0.55 kB/body-step"
 FLOP_PER_INTERACTION = 19
-NCU_KERNELS = "r01d_ncu_c3_kernels.json"  # per-kernel DRAM traffic of the committed ncu --set full capture
+NCU_KERNELS = "r02_ncu_c3_kernels.json"  # per-kernel DRAM traffic of the committed ncu --set full capture
 
 
 def make_state(w):
@@ -425,8 +425,10 @@ def measure_e2e(api, state, w, args):
         acc = el.transform(cur, acc)
     dt_tr = (time.perf_counter() - t1) / 5
     return {"value": n / dt, "unit": "particle-steps/s", "ms_per_step": dt * 1e3,
-            "h2d_bytes_per_step": n * 33, "d2h_bytes_per_step": n * 48,
-            "api": "pb200_verlet_step_fused(host Entity[n] -> host Entity[n]), state copied in and out every step",
+            "h2d_bytes_per_step": n * 33, "d2h_bytes_per_step": n * 24,
+            "api": "pb200_verlet_step_fused(host Entity[n] -> host Entity[n]), state copied in and out every step "
+                   "(H2D {x,y,z,m,fixed}; D2H {x,y,z}: the regular step's velocity (x' - x)/dt is taken on the host from "
+                   "the caller's own input, verlet.rs:68-70, same bits)",
             "device_ms": {"h2d": vs["ms_h2d"], "force": vs["ms_force"], "integrate": vs["ms_integrate"],
                           "d2h": vs["ms_d2h"]},
             "host_ms": {"pack": vs["ms_host_pack"], "unpack": vs["ms_host_unpack"], "call": vs["ms_wall"]},
@@ -438,7 +440,7 @@ def measure_e2e(api, state, w, args):
                          "device_ms": {"h2d": rs["ms_h2d"], "force": rs["ms_force"], "integrate": rs["ms_integrate"],
                                        "d2h": rs["ms_d2h"]}},
             "dropin": {"value": n / dt_drop, "ms_per_step": dt_drop * 1e3,
-                       "h2d_bytes_per_step": n * (33 + 56 + 24), "d2h_bytes_per_step": n * (16 + 48),
+                       "h2d_bytes_per_step": n * (33 + 56 + 24), "d2h_bytes_per_step": n * (16 + 24),
                        "api": f"pb200_integrator_step(acc_fn = {w['element']}_get_api()->transform): what the Rust "
                               "shim's verlet runs when gravity is a separate plugin element"},
             "transform_only": {"api": f"{w['element']}_get_api()->transform", "ms_per_call": dt_tr * 1e3,
@@ -550,7 +552,7 @@ def measure_bh_large(api, torch, dist, rank, world, local_rank):
             sim = make_msim(api, torch, dist, w, rank, world, local_rank)
         sim.generate_cube(n, seed=1)
         sim.run(3)  # first step (replicated, plans the shards) + two regular steps
-        steps = 5
+        steps = 16  # (half a checkpoint interval of the resident loop: its 3 x 2 GB state copies weigh as in a long run)
         torch.cuda.synchronize()
         if dist:
             dist.barrier()
@@ -608,7 +610,7 @@ def measure_other_workloads(api, args):
                 cur ^= 1
             dt = (time.perf_counter() - t0) / k
             row["e2e"] = {"value": n / dt, "unit": "particle-steps/s", "ms_per_step": dt * 1e3,
-                          "h2d_bytes_per_step": n * 33, "d2h_bytes_per_step": n * 48,
+                          "h2d_bytes_per_step": n * 33, "d2h_bytes_per_step": n * 24,
                           "api": "pb200_verlet_step_fused(host Entity[n] -> host Entity[n])"}
             row["cpu_baseline"] = measure_cpu(state, w, budget=4e6)
         out[name] = row

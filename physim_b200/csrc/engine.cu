@@ -346,6 +346,7 @@ struct VerletObj {
   void* reg_ptr = nullptr;
   size_t reg_bytes = 0;
   uint64_t resident_hits = 0, resident_misses = 0;
+  int d2h_bytes_per_body = 48;  // of the last step through the host boundary (24: regular verlet step, positions only)
   LaunchStats ls;
   Pb200Stats stats;
   ~VerletObj() {
@@ -389,6 +390,33 @@ void unpack_state_range(const Entity* entities, Entity* out, size_t b, size_t e,
   }
 }
 
+// the regular verlet step's form: the device returned {x,y,z} only, v = (x' - x_in) / dt (verlet.rs:68-70) is taken
+// here from the input the caller handed in.  Everything of record i is read before anything of it is written, so
+// `out` may be the input array itself.
+void unpack_positions_range(const Entity* entities, Entity* out, size_t b, size_t e, const double* out3, double dt) {
+  const bool aligned = (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
+  for (size_t i = b; i < e; ++i) {
+    const double* o = out3 + 3 * i;
+    const double* src = reinterpret_cast<const double*>(entities + i);
+    const double x = o[0], y = o[1], z = o[2];
+    const double vx = (x - src[0]) / dt, vy = (y - src[1]) / dt, vz = (z - src[2]) / dt;
+    const __m128d tail0 = _mm_loadu_pd(src + 6), tail1 = _mm_loadu_pd(src + 8);  // radius, mass | id, fixed (+ padding)
+    double* dst = reinterpret_cast<double*>(out + i);
+    if (aligned) {
+      _mm_stream_pd(dst, _mm_set_pd(y, x));
+      _mm_stream_pd(dst + 2, _mm_set_pd(vx, z));
+      _mm_stream_pd(dst + 4, _mm_set_pd(vz, vy));
+      _mm_stream_pd(dst + 6, tail0);
+      _mm_stream_pd(dst + 8, tail1);
+    } else {
+      dst[0] = x; dst[1] = y; dst[2] = z; dst[3] = vx; dst[4] = vy; dst[5] = vz;
+      _mm_storeu_pd(dst + 6, tail0);
+      _mm_storeu_pd(dst + 8, tail1);
+    }
+  }
+  if (aligned) _mm_sfence();
+}
+
 cudaError_t verlet_buffers(VerletObj& v, size_t n) {
   PB_PASS(v.gpu.init(v.device));
   PB_PASS(v.cur.ensure(n * sizeof(double4)));
@@ -404,11 +432,20 @@ cudaError_t verlet_buffers(VerletObj& v, size_t n) {
 }
 
 // shared tail of both verlet entry points: chunked D2H of the packed result, unpack behind the copies
-cudaError_t verlet_finish(VerletObj& v, cudaStream_t st, const Entity* entities, Entity* new_state, size_t n) {
+// (first-step formula: {x,y,z,vx,vy,vz} come back, 48 B/body; regular step: {x,y,z}, 24 B/body)
+cudaError_t verlet_finish(VerletObj& v, cudaStream_t st, const Entity* entities, Entity* new_state, size_t n,
+                          bool first = true, double dt = 0.0) {
   const double* h = v.h_out.as<double>();
-  PB_PASS(download_chunked(v.gpu, st, v.h_out.p, v.out6.p, n, 48, v.gpu.ev[4], [&](size_t b, size_t e) {
-    unpack_state_range(entities, new_state, b, e, h);
-  }));
+  v.d2h_bytes_per_body = first ? 48 : 24;
+  if (first) {
+    PB_PASS(download_chunked(v.gpu, st, v.h_out.p, v.out6.p, n, 48, v.gpu.ev[4], [&](size_t b, size_t e) {
+      unpack_state_range(entities, new_state, b, e, h);
+    }));
+  } else {
+    PB_PASS(download_chunked(v.gpu, st, v.h_out.p, v.out6.p, n, 24, v.gpu.ev[4], [&](size_t b, size_t e) {
+      unpack_positions_range(entities, new_state, b, e, h, dt);
+    }));
+  }
   PB_CUDA(cudaStreamSynchronize(st));
   v.n_prev = n;
   v.stats.n_bodies = n;
@@ -458,30 +495,34 @@ cudaError_t rk4_step_generic(VerletObj& v, const Entity* entities, Entity* new_s
 cudaError_t verlet_step_generic(VerletObj& v, const Entity* entities, Entity* new_state, size_t n,
                                 Pb200AccFn acc_fn, void* ctx, double dt) {
   if (v.kind == PB200_RK4) return rk4_step_generic(v, entities, new_state, n, acc_fn, ctx, dt);
-  std::vector<Acceleration> acc(n, Acceleration{0.0, 0.0, 0.0});  // verlet.rs:93
-  acc_fn(ctx, entities, n, acc.data());                           // verlet.rs:94
   if (n == 0) {
+    acc_fn(ctx, entities, 0, nullptr);  // verlet.rs:93-94 (an empty vector)
     v.n_prev = 0;
     return cudaSuccess;
   }
   PB_PASS(verlet_buffers(v, n));
   PB_PASS(v.acc64.ensure(n * sizeof(Acceleration)));
   PB_PASS(v.h_acc.ensure(n * sizeof(Acceleration)));
+  // verlet.rs:93-94 `vec![Acceleration::zero(); n]` + acc_fn: the vector is this handle's page-locked upload
+  // buffer, zeroed by the pool (a fresh 24 MB std::vector per step costs milliseconds of page faults, and the
+  // accelerations would have to be copied once more before they can be uploaded)
+  Acceleration* acc = v.h_acc.as<Acceleration>();
+  HostPool::instance().parallel_for(n, kParallelGrain, [&](size_t b, size_t e) {
+    std::memset(static_cast<void*>(acc + b), 0, (e - b) * sizeof(Acceleration));
+  });
+  acc_fn(ctx, entities, n, acc);
   cudaStream_t st = v.gpu.stream;
   // euler (euler.rs:30-37) is verlet's first-step formula on every step
   const bool first = v.kind == PB200_EULER || v.n_prev != n;
   PB_CUDA(cudaEventRecord(v.gpu.ev[0], st));
   PB_PASS(upload_packed(entities, n, v.h_pos.as<double4>(), nullptr, v.h_vel.as<double4>(),
                         v.cur.as<double4>(), nullptr, first ? v.vel.as<double4>() : nullptr, st));
-  HostPool::instance().parallel_for(n, kParallelGrain, [&](size_t b, size_t e) {
-    std::memcpy(v.h_acc.as<Acceleration>() + b, acc.data() + b, (e - b) * sizeof(Acceleration));
-  });
   PB_CUDA(cudaMemcpyAsync(v.acc64.p, v.h_acc.p, n * sizeof(Acceleration), cudaMemcpyHostToDevice, st));
   PB_CUDA(cudaEventRecord(v.gpu.ev[1], st));
   PB_PASS(verlet_update(v.cur.as<double4>(), v.prev.as<double4>(), v.vel.as<double4>(), nullptr,
                         v.acc64.as<double>(), n, dt, first ? 1 : 0, st, v.ls, v.out6.as<double>()));
   PB_CUDA(cudaEventRecord(v.gpu.ev[3], st));
-  PB_PASS(verlet_finish(v, st, entities, new_state, n));
+  PB_PASS(verlet_finish(v, st, entities, new_state, n, first, dt));
   v.stats.ms_h2d = elapsed(v.gpu.ev[0], v.gpu.ev[1]);
   v.stats.ms_force = 0.f;
   v.stats.ms_integrate = elapsed(v.gpu.ev[1], v.gpu.ev[3]);
@@ -630,7 +671,7 @@ cudaError_t verlet_step_fused(VerletObj& v, TransformObj& t, const Entity* entit
   PB_PASS(verlet_update(v.cur.as<double4>(), v.prev.as<double4>(), v.vel.as<double4>(),
                         t.ws.acc.as<float4>(), nullptr, n, dt, first ? 1 : 0, st, v.ls, v.out6.as<double>()));
   PB_CUDA(cudaEventRecord(v.gpu.ev[3], st));
-  PB_PASS(verlet_finish(v, st, entities, new_state, n));
+  PB_PASS(verlet_finish(v, st, entities, new_state, n, first, dt));
   t.last_n = n;
   t.stats.n_bodies = n;
   t.stats.n_cells = t.ws.n_cells;
@@ -1131,6 +1172,15 @@ int pb200_transform_debug_tree(void* obj, uint64_t* key, uint32_t* perm, uint32_
       PB_PASS(copy_out(com_mass, t.ws.c_com.p, c * 4, st));
     }
     PB_CUDA(cudaStreamSynchronize(st));
+    if (t.have_tree && centre_ext && level) {
+      // the device keeps the walk's link (skip | level) in the fourth word of a centre record; the inspected table
+      // carries the half-width there: extent / 2^level, the same double the build's halving reaches
+      unsigned long long bits = 0;
+      PB_CUDA(cudaMemcpy(&bits, t.ws.extent_bits.p, 8, cudaMemcpyDeviceToHost));
+      double ext = 0.0;
+      std::memcpy(&ext, &bits, 8);
+      for (size_t i = 0; i < c; ++i) centre_ext[4 * i + 3] = std::ldexp(ext, -int(level[i]));
+    }
     if (counts) {
       std::vector<float4> a(n);
       PB_CUDA(cudaMemcpy(a.data(), t.ws.acc.p, n * sizeof(float4), cudaMemcpyDeviceToHost));

@@ -1161,6 +1161,25 @@ struct CellArrays {
   uint32_t top_level;    // ... unless they lie above this level: those are always summed from their children
 };
 
+// The fourth word of a cell's centre record is not the half-width (extent / 2^level: derived, exactly, from
+// the level) but the walk's link: skip link in the low 32 bits, level in the next 8.  One record load then tells
+// the walk everything it needs to decide about a cell and to move on; the centre of mass is fetched only for
+// the cells it takes (the walk is bound by L1 wavefronts: ncu l1tex__data_pipe_lsu_wavefronts 88 % of peak at
+// theta = 0.7 with three unconditional loads per visit).
+__device__ __forceinline__ double pack_link(uint32_t skip, int level) {
+  return __longlong_as_double(static_cast<long long>((static_cast<unsigned long long>(level & 0xff) << 32) | skip));
+}
+__device__ __forceinline__ uint32_t link_skip(double w) { return static_cast<uint32_t>(__double_as_longlong(w)); }
+__device__ __forceinline__ int link_level(double w) { return int((__double_as_longlong(w) >> 32) & 0xff); }
+// extent / 2^level, the value `half *= 0.5` reaches after `level` steps (exact; the exponent trick needs a normal
+// result, else ldexp)
+__device__ __forceinline__ double half_width_at(double ext0, int level) {
+  const int hi = __double2hiint(ext0);
+  if (((hi >> 20) & 0x7ff) > level + 1 && ((hi >> 20) & 0x7ff) != 0x7ff)
+    return __hiloint2double(hi - (level << 20), __double2loint(ext0));
+  return ldexp(ext0, -level);
+}
+
 // Key levels [0, TOP_LEVEL) form the "top tree": 4^6 = 8^4 = 4096 level-K prefixes.  A sharded build cuts the
 // key space between ranks at level-K prefixes, every rank builds the cells at levels >= K of its own range,
 // and the cells above are recomputed on every rank from the level-K cells' sums (top_build_kernel).  For that
@@ -1459,7 +1478,11 @@ __global__ void __launch_bounds__(256, MIN_BLOCKS) cells_kernel(const uint64_t* 
       if (l >= top) {
         const uint32_t c = c0 + uint32_t(l - top);
         cells.level[c] = static_cast<uint8_t>(l);
-        cells.centre_ext[c] = make_double4(cx, cy, cz, half);
+        // {cx, cy, cz}; the fourth word (link) is written once, by whoever learns the skip link: below for the
+        // leaf, in phase 2 for the internal cells
+        double* rec = reinterpret_cast<double*>(cells.centre_ext + c);
+        *reinterpret_cast<double2*>(rec) = make_double2(cx, cy);
+        rec[2] = cz;
       }
       if (l < leaf_level) {  // from level l to level l+1 along the head body's path
         unsigned digit = unsigned(digits >> (64 - DIM));
@@ -1476,15 +1499,19 @@ __global__ void __launch_bounds__(256, MIN_BLOCKS) cells_kernel(const uint64_t* 
     }
     // leaf: the unit itself
     const uint32_t c = c0 + uint32_t(leaf_level - top);
+    double* link = reinterpret_cast<double*>(cells.centre_ext + c) + 3;
     if (abn.x != NOT_HEAD) {  // (always, unless bodies were merged)
       cells.count[c] = 1u;
       cells.skip[c] = cs1;
+      *link = pack_link(cs1, leaf_level);
       cells.com[c] = me;
     } else {
       size_t e = s + 2;
       while (e < n && ab[e].x == NOT_HEAD) ++e;
       cells.count[c] = static_cast<uint32_t>(e - s);
-      cells.skip[c] = cell_start[e];
+      const uint32_t sk = cell_start[e];
+      cells.skip[c] = sk;
+      *link = pack_link(sk, leaf_level);
       cells.com[c] = unit_leaf(sp, perm, s, e);
     }
     if (slots.slot_cell && top <= slots.level) {  // s is the first body of its level-K prefix
@@ -1519,7 +1546,9 @@ __global__ void __launch_bounds__(256, MIN_BLOCKS) cells_kernel(const uint64_t* 
     const size_t e = nsv_next_le(tv, so + 1, unsigned(lev));
     const uint32_t cnt = static_cast<uint32_t>(e - so);
     cells.count[c] = cnt;
-    cells.skip[c] = cell_start[e];
+    const uint32_t sk_c = cell_start[e];
+    cells.skip[c] = sk_c;
+    reinterpret_cast<double*>(cells.centre_ext + c)[3] = pack_link(sk_c, lev);
     if (cnt > cells.small || uint32_t(lev) < cells.top_level) continue;
     ComSum sum;
     if (!merged_units) {  // no merged unit anywhere: plain sums over the run
@@ -1788,12 +1817,6 @@ __device__ __forceinline__ double4 ld_now_double4(const double4* p) {
   asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2+16];" : "=d"(v.z), "=d"(v.w) : "l"(p));
   return v;
 }
-__device__ __forceinline__ uint32_t ld_now_u32(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
-  return v;
-}
-
 __device__ __forceinline__ bool accept_cell(double px, double py, double pz, const double4& ce,
                                             double theta, double theta2) {
   if (!(theta > 0.0)) return false;  // half_width / r >= 0 is never < theta <= 0
@@ -1810,17 +1833,25 @@ __device__ __forceinline__ bool accept_cell(double px, double py, double pz, con
 // (Measured and rejected, r02: prefetch.global.L1 of the three records the skip link points to, issued as soon as
 // the link is known - 46 -> 49 us at c3, 1.71 -> 3.03 ms at 4.2 M bodies / theta 0.7: the prefetches evict the
 // lines the neighbouring lanes are about to reuse.)
+__device__ __forceinline__ double4 ld_now_double4_256(const double4* p) {  // one 256-bit load (LDG.E.256, sm_100)
+  double4 v;
+  asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+  return v;
+}
+
 template <int DIM>
-__global__ void __launch_bounds__(256) walk_kernel(const double4* __restrict__ sp,
+__global__ void __launch_bounds__(256, 5) walk_kernel(const double4* __restrict__ sp,
                                                    const uint32_t* __restrict__ perm,
                                                    const uint8_t* __restrict__ fixed,
                                                    const uint32_t* __restrict__ tgt_list,
                                                    size_t n_targets, const uint32_t* __restrict__ cell_start,
-                                                   size_t n, CellArrays cells, double theta, float easing,
-                                                   float tiny, float4* __restrict__ acc) {
+                                                   size_t n, CellArrays cells,
+                                                   const unsigned long long* __restrict__ extent_bits, double theta,
+                                                   float easing, float tiny, float4* __restrict__ acc) {
   pb_pdl_sync();
   const uint32_t total = cell_start[n];
   if (total > cells.capacity || *cells.bad) return;
+  const double ext0 = __longlong_as_double(static_cast<long long>(*extent_bits));
   const size_t t = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
   bool active = t < n_targets;
   uint32_t s = 0, orig = 0;
@@ -1838,31 +1869,39 @@ __global__ void __launch_bounds__(256) walk_kernel(const double4* __restrict__ s
   // every lane follows its own pre-order path (c -> c+1 or skip[c]); lanes of a warp are spatial
   // neighbours, so they mostly touch the same cache lines, and no lane waits for cells that only
   // other lanes need
+  // Two records per visit - {centre, link} and the centre of mass - requested together at the top of the
+  // iteration (measured, r02: fetching the centre of mass only for the cells that are taken saves 30 % of the L1
+  // wavefronts but puts a second memory latency into every accepted visit: 1.60 vs 1.53 ms at 4.2 M bodies,
+  // theta 0.7); the skip link travels in the centre record, so there is no third load; each record is ONE
+  // 256-bit load (1.39 vs 1.47 ms with two 128-bit loads each; 1.71 ms with the three-array form of round 1).
   uint32_t c = active ? 0u : total;
   while (c < total) {
-    const double4 ce = ld_now_double4(cells.centre_ext + c);
-    const double4 cm = ld_now_double4(cells.com + c);
-    const uint32_t sk = ld_now_u32(cells.skip + c);
-    {
-      const bool leaf = (sk == c + 1u);
-      if (leaf || accept_cell(px, py, pz, ce, theta, theta2)) {
-        const float dx = static_cast<float>(cm.x - px);
-        const float dy = static_cast<float>(cm.y - py);
-        const float dz = static_cast<float>(cm.z - pz);
-        float r2 = fmaf(dx, dx, tiny);  // tiny keeps r = 0 (self / coincident: skipped by the
-        r2 = fmaf(dy, dy, r2);          // reference, transformers.rs:145-147) finite: w·0 = 0
-        r2 = fmaf(dz, dz, r2);
-        const float sft = r2 + easing;
-        const float w = rsqrt_approx(r2 * sft * sft);  // 1 / (|r| (r² + e))
-        const float mw = static_cast<float>(cm.w) * w;
-        fx = fmaf(mw, dx, fx);
-        fy = fmaf(mw, dy, fy);
-        fz = fmaf(mw, dz, fz);
-        ++inter;
-        c = max(sk, c + 1u);  // (sk > c in a well-formed table; a broken one must not hang the walk)
-      } else {
-        c = c + 1u;
-      }
+    const double4 ce = ld_now_double4_256(cells.centre_ext + c);
+    const double4 cm = ld_now_double4_256(cells.com + c);
+    const uint32_t sk = link_skip(ce.w);
+    const bool leaf = (sk == c + 1u);
+    bool take = leaf;
+    if (!leaf) {
+      const double4 cw = make_double4(ce.x, ce.y, ce.z, half_width_at(ext0, link_level(ce.w)));
+      take = accept_cell(px, py, pz, cw, theta, theta2);
+    }
+    if (take) {
+      const float dx = static_cast<float>(cm.x - px);
+      const float dy = static_cast<float>(cm.y - py);
+      const float dz = static_cast<float>(cm.z - pz);
+      float r2 = fmaf(dx, dx, tiny);  // tiny keeps r = 0 (self / coincident: skipped by the
+      r2 = fmaf(dy, dy, r2);          // reference, transformers.rs:145-147) finite: w·0 = 0
+      r2 = fmaf(dz, dz, r2);
+      const float sft = r2 + easing;
+      const float w = rsqrt_approx(r2 * sft * sft);  // 1 / (|r| (r² + e))
+      const float mw = static_cast<float>(cm.w) * w;
+      fx = fmaf(mw, dx, fx);
+      fy = fmaf(mw, dy, fy);
+      fz = fmaf(mw, dz, fz);
+      ++inter;
+      c = max(sk, c + 1u);  // (sk > c in a well-formed table; a broken one must not hang the walk)
+    } else {
+      c = c + 1u;
     }
   }
   if (t < n_targets) {
@@ -2078,6 +2117,7 @@ __global__ void __launch_bounds__(256) walk_sharded_kernel(const double4* __rest
     if (fixed[orig]) active = false;  // transformers.rs:139-141
   }
   const double theta2 = theta * theta;
+  const double ext0 = top.centre_ext[0].w;  // the root's half-width (top_build_kernel)
   float fx = 0.f, fy = 0.f, fz = 0.f;
   uint32_t inter = 0;
   auto interact = [&](const double4& cm) {
@@ -2118,14 +2158,18 @@ __global__ void __launch_bounds__(256) walk_sharded_kernel(const double4* __rest
         const uint32_t owner = inf.x >> 8;
         const double4* __restrict__ t_ce = peers.centre_ext[owner];
         const double4* __restrict__ t_cm = peers.com[owner];
-        const uint32_t* __restrict__ t_sk = peers.skip[owner];
         const uint32_t end = min(inf.z, peers.capacity);
         uint32_t c = inf.y + 1u;
-        while (c < end) {
+        while (c < end) {  // (same loop as walk_kernel, on the owner's table)
           const double4 ce2 = ld_now_double4(t_ce + c);
           const double4 cm2 = ld_now_double4(t_cm + c);
-          const uint32_t sk = ld_now_u32(t_sk + c);
-          if (sk == c + 1u || accept_cell(px, py, pz, ce2, theta, theta2)) {
+          const uint32_t sk = link_skip(ce2.w);
+          bool take = (sk == c + 1u);
+          if (!take) {
+            const double4 cw = make_double4(ce2.x, ce2.y, ce2.z, half_width_at(ext0, link_level(ce2.w)));
+            take = accept_cell(px, py, pz, cw, theta, theta2);
+          }
+          if (take) {
             interact(cm2);
             c = max(sk, c + 1u);
           } else {
@@ -2964,7 +3008,7 @@ cudaError_t tree_evaluate(GravityWorkspace& ws, const GravityParams& prm, size_t
   if (n_targets) {
     PB_LAUNCH(ls, st, "walk_kernel", pb_launch_pdl(walk_kernel<DIM>, dim3(blocks_for(n_targets, 256)), dim3(256), 0, st,
         ws.spos64.as<double4>(), ws.perm, ws.fixed, list, n_targets, ws.cell_start.as<uint32_t>(), n,
-        cells, prm.theta, easing, tiny, ws.acc.as<float4>()));
+        cells, ws.extent_cur, prm.theta, easing, tiny, ws.acc.as<float4>()));
   }
   return cudaGetLastError();
 }

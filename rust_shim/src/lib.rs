@@ -34,6 +34,14 @@ unsafe extern "C" {
         ctx: *mut c_void,
         dt: f64,
     ) -> i32;
+    // the fused step (include/physim_b200.h "Fused step"): accelerations never leave the device
+    fn pb200_verlet_create() -> *mut c_void;
+    fn pb200_verlet_destroy(v: *mut c_void);
+    fn pb200_verlet_set_resident(v: *mut c_void, on: i32) -> i32;
+    fn pb200_verlet_step_fused(v: *mut c_void, transform: *mut c_void, entities: *const Entity, new_state: *mut Entity, n: usize, dt: f64) -> i32;
+    // Pb200Kind { PB200_ASTRO = 0, PB200_ASTRO2 = 1, PB200_SIMPLE_ASTRO = 2 }; NaN = the element's default (1.0)
+    fn pb200_transform_create(kind: i32, theta: f64, e: f64) -> *mut c_void;
+    fn pb200_transform_destroy(t: *mut c_void);
 }
 
 #[integrator_element(
@@ -42,6 +50,10 @@ unsafe extern "C" {
 )]
 struct Verlet {
     handle: *mut c_void,
+    /// `verlet gravity=astro2 theta=1.5 e=0.5 [resident=true]`: the gravity element lives inside the integrator
+    /// (pb200_verlet_step_fused) and is left out of the pipeline; null = the stock composition through acc_fn.
+    fused: *mut c_void,
+    gravity: *mut c_void,
 }
 
 unsafe impl Send for Verlet {}
@@ -64,7 +76,11 @@ impl IntegratorElement for Verlet {
     ) {
         let ctx = &acc_fn as *const &dyn Fn(&[Entity], &mut [Acceleration]) as *mut c_void;
         let rc = unsafe {
-            pb200_integrator_step(self.handle, entities.as_ptr(), new_state.as_mut_ptr(), entities.len(), trampoline, ctx, dt)
+            if !self.fused.is_null() {
+                pb200_verlet_step_fused(self.fused, self.gravity, entities.as_ptr(), new_state.as_mut_ptr(), entities.len(), dt)
+            } else {
+                pb200_integrator_step(self.handle, entities.as_ptr(), new_state.as_mut_ptr(), entities.len(), trampoline, ctx, dt)
+            }
         };
         if rc != 0 {
             eprintln!("physim_b200 verlet step failed");
@@ -75,21 +91,49 @@ impl IntegratorElement for Verlet {
 
 impl Drop for Verlet {
     fn drop(&mut self) {
-        unsafe { pb200_integrator_destroy(self.handle) }
+        unsafe {
+            pb200_integrator_destroy(self.handle);
+            if !self.fused.is_null() {
+                pb200_verlet_destroy(self.fused);
+                pb200_transform_destroy(self.gravity);
+            }
+        }
     }
 }
 
 impl MessageClient for Verlet {}
 
 impl ElementCreator for Verlet {
-    fn create_element(_: HashMap<String, Value>) -> Box<Self> {
-        Box::new(Self { handle: unsafe { pb200_integrator_create(0) } })
+    fn create_element(properties: HashMap<String, Value>) -> Box<Self> {
+        let num = |k: &str| properties.get(k).and_then(|v| v.as_f64()).unwrap_or(f64::NAN);
+        let kind = match properties.get("gravity").and_then(|v| v.as_str()) {
+            Some("astro") => Some(0),
+            Some("astro2") => Some(1),
+            Some("simple_astro") => Some(2),
+            _ => None,
+        };
+        let (mut fused, mut gravity) = (std::ptr::null_mut(), std::ptr::null_mut());
+        if let Some(kind) = kind {
+            unsafe {
+                fused = pb200_verlet_create();
+                gravity = pb200_transform_create(kind, num("theta"), num("e"));
+                if properties.get("resident").and_then(|v| v.as_bool()).unwrap_or(false) {
+                    pb200_verlet_set_resident(fused, 1);
+                }
+            }
+        }
+        Box::new(Self { handle: unsafe { pb200_integrator_create(0) }, fused, gravity })
     }
 }
 
 impl Element for Verlet {
     fn get_property_descriptions(&self) -> Result<HashMap<String, String>, Box<dyn std::error::Error>> {
-        Ok(HashMap::from([]))
+        Ok(HashMap::from([
+            (String::from("gravity"), String::from("astro | astro2 | simple_astro: evaluate this gravity element inside the integrator (accelerations stay on the GPU); leave that element out of the pipeline")),
+            (String::from("theta"), String::from("Barnes-Hut parameter of the fused gravity element. Default=1.0")),
+            (String::from("e"), String::from("Easing factor of the fused gravity element. Default=1.0")),
+            (String::from("resident"), String::from("true: keep the state in GPU memory between steps; the input is checked on a sample against the previous output and uploaded only when it differs. Default=false")),
+        ]))
     }
 }
 

@@ -15,3 +15,4 @@ w = bench.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "c3"]
 args = argparse.Namespace(steps=int(sys.argv[2]) if len(sys.argv) > 2 else 50, warmup=3)
 r = bench.measure_e2e(api, bench.make_state(w), w, args)
 print(json.dumps({k: r[k] for k in ("ms_per_step", "device_ms", "host_ms")}))
+print("resident", r["resident"]["ms_per_step"], "dropin", r["dropin"]["ms_per_step"], "transform_only", r["transform_only"]["ms_per_call"])
