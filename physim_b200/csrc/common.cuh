@@ -106,7 +106,6 @@ struct ShardPeers {  // every rank's buffers as this device sees them (own rank:
   void* top_meta[8];
   void* xacc[8];
   void* flags[8];
-  void* keys[8];
   uint32_t capacity;          // cells (the smallest table of any rank)
 };
 struct ShardState {
@@ -121,7 +120,6 @@ struct ShardState {
   DevBuf top_meta;        // u32: per-rank bodies / cells / abandoned-build flags, double-buffered by epoch parity
   DevBuf xacc;            // [world] x { float4 acc[n_cap], u32 perm[n_cap] }: block r written by rank r's walk
   DevBuf flags;           // u32 epochs per phase and rank (SHARD_FLAG_*), stored by the peers
-  DevBuf keys_all;        // u64[n]: every body's key of the current build; slice r computed and stored by rank r
   ShardPeers peers;
   size_t xacc_block_bytes() const { return n_cap * 20; }
   void release();
@@ -169,6 +167,7 @@ struct GravityWorkspace {
   int splitter_cur = 0; // which of the two splitter sets the next evaluation reads
   unsigned spl_nb[2] = {0, 0};  // how many buckets each splitter set was written for (0: never written)
   int bucket_ban = 0;   // checks left during which the bucket sort stays off (a bucket's bodies were too alike)
+  int bucket_min_mode = 1;  // smallest bucket capacity class still trusted (raised when a bucket overflowed its tile)
   uint32_t last_max_bucket = 0;  // fullest top-8-bit bin seen at the last check
   int unchecked_builds = 0;   // tree builds since the last gravity_check()
   uint32_t last_total = 0;    // verdict of the last gravity_check(), returned again when nothing was built since
@@ -275,9 +274,8 @@ __device__ __forceinline__ void pb_pdl_sync() {
 // Cross-GPU signalling of the sharded step: flags are u32 epochs in the CONSUMER's memory, stored by the producers
 // through peer mappings.  Bounded spin: a rank that never signals (a crashed peer) leaves flags[18] set and the
 // wait returns - the results are then garbage and the host's next check reports the error instead of a hung GPU.
-// [0..7] "rank r's level-K records of epoch e are in place", [8..15] "... accelerations ...", [16..23] "... keys ...",
-// [24] a wait gave up
-constexpr int SHARD_FLAG_EXPORT = 0, SHARD_FLAG_WALK = 8, SHARD_FLAG_KEYS = 16, SHARD_TIMEOUT = 24;
+// [0..7] "rank r's level-K records of epoch e are in place", [8..15] "... accelerations ...", [24] a wait gave up
+constexpr int SHARD_FLAG_EXPORT = 0, SHARD_FLAG_WALK = 8, SHARD_TIMEOUT = 24;
 __device__ __forceinline__ void shard_wait_flag(uint32_t* flags, int slot, uint32_t epoch) {
   volatile uint32_t* f = flags + slot;
   unsigned spins = 0;

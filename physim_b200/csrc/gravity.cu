@@ -45,7 +45,6 @@ struct PeerTargets {
   uint32_t* meta[8];
   char* xacc[8];
   uint32_t* flags[8];
-  uint64_t* keys[8];
   int world, rank;
 };
 
@@ -545,97 +544,6 @@ __global__ void __launch_bounds__(256) encode_bucket_kernel(const double4* __res
   for (int e = 0; e < ENC_ITEMS; ++e) {
     const size_t i = tile + size_t(e) * 256 + tid;
     if (keep[e]) {
-      const unsigned slot = gbase[d[e]] + r[e];
-      if (slot < cap) {  // else: bucket over capacity, sort_local_kernel flags the build
-        bkey[size_t(d[e]) * cap + slot] = k[e];
-        bidx[size_t(d[e]) * cap + slot] = static_cast<uint32_t>(i);
-      }
-    }
-  }
-}
-
-// Sharded build, keys: the FP64 compare-and-halve chain (the expensive half of encode_bucket_kernel) is done once per
-// body in the whole job - rank r encodes the bodies of index slice r and stores the keys into EVERY rank's keys_all
-// (coalesced 8-byte stores over NVLink) - and bucket_append_kernel then runs over all bodies on every rank, reading
-// keys instead of computing them.
-template <int DIM>
-__global__ void __launch_bounds__(256) encode_keys_kernel(const double4* __restrict__ pos, size_t i0, size_t i1,
-                                                          const unsigned long long* __restrict__ extent_bits,
-                                                          PeerTargets pt) {
-  pb_pdl_sync();
-  const double ext0 = __longlong_as_double(static_cast<long long>(*extent_bits));
-  const size_t tile = i0 + size_t(blockIdx.x) * (256 * ENC_ITEMS);
-  const double scale = key_scale<DIM>(ext0);
-  double4 p[ENC_ITEMS];
-  uint64_t k[ENC_ITEMS];
-#pragma unroll
-  for (int e = 0; e < ENC_ITEMS; ++e) {
-    const size_t i = tile + size_t(e) * 256 + threadIdx.x;
-    p[e] = i < i1 ? pos[i] : make_double4(0.0, 0.0, 0.0, 0.0);
-  }
-#pragma unroll
-  for (int e = 0; e < ENC_ITEMS; ++e) k[e] = key_of<DIM>(p[e].x, p[e].y, p[e].z, ext0, scale);
-#pragma unroll
-  for (int e = 0; e < ENC_ITEMS; ++e) {
-    const size_t i = tile + size_t(e) * 256 + threadIdx.x;
-    if (i < i1)
-      for (int r = 0; r < pt.world; ++r) pt.keys[r][i] = k[e];
-  }
-}
-
-template <unsigned NB>
-__global__ void __launch_bounds__(256) bucket_append_kernel(const uint64_t* __restrict__ keys_all, size_t n,
-                                                            const uint64_t* __restrict__ splitters, int lo,
-                                                            uint64_t* __restrict__ bkey, uint32_t* __restrict__ bidx,
-                                                            unsigned cap, unsigned* __restrict__ cursor,
-                                                            const uint64_t* __restrict__ cuts, PeerTargets pt,
-                                                            uint32_t epoch) {
-  pb_pdl_sync();
-  __shared__ unsigned cnt[NB];
-  __shared__ unsigned gbase[NB];
-  __shared__ uint64_t spl[NB];
-  const int tid = threadIdx.x;
-  // this rank's slice of the keys (encode_keys_kernel, just completed on this stream) is in place everywhere
-  shard_signal_then_wait(pt, SHARD_FLAG_KEYS, epoch, blockIdx.x == 0);
-#pragma unroll
-  for (unsigned j = tid; j < NB; j += 256) {
-    cnt[j] = 0u;
-    spl[j] = j ? (splitters[j] >> lo) : 0ull;
-  }
-  __syncthreads();
-  const uint64_t cut_lo = cuts[0], cut_hi = cuts[1];
-  const size_t tile = size_t(blockIdx.x) * (256 * ENC_ITEMS);
-  uint64_t k[ENC_ITEMS];
-  unsigned r[ENC_ITEMS], d[ENC_ITEMS];
-  bool keep[ENC_ITEMS];
-#pragma unroll
-  for (int e = 0; e < ENC_ITEMS; ++e) {
-    const size_t i = tile + size_t(e) * 256 + tid;
-    k[e] = i < n ? keys_all[i] : 0ull;
-  }
-#pragma unroll
-  for (int e = 0; e < ENC_ITEMS; ++e) {
-    const size_t i = tile + size_t(e) * 256 + tid;
-    keep[e] = i < n && k[e] >= cut_lo && k[e] < cut_hi;
-    const uint64_t kk = k[e] >> lo;
-    unsigned b = 0;
-#pragma unroll
-    for (unsigned step = NB >> 1; step > 0; step >>= 1)
-      if (spl[b + step] <= kk) b += step;
-    d[e] = b;
-    r[e] = keep[e] ? atomicAdd(&cnt[b], 1u) : 0u;
-  }
-  __syncthreads();
-#pragma unroll
-  for (unsigned j = tid; j < NB; j += 256) {
-    const unsigned c = cnt[j];
-    if (c) gbase[j] = atomicAdd(&cursor[j], c);
-  }
-  __syncthreads();
-#pragma unroll
-  for (int e = 0; e < ENC_ITEMS; ++e) {
-    if (keep[e]) {
-      const size_t i = tile + size_t(e) * 256 + tid;
       const unsigned slot = gbase[d[e]] + r[e];
       if (slot < cap) {  // else: bucket over capacity, sort_local_kernel flags the build
         bkey[size_t(d[e]) * cap + slot] = k[e];
@@ -1286,10 +1194,6 @@ struct ShardBuild {
   size_t n_cap;          // capacity of the per-rank arrays, in bodies
   TopSlots slots;
   uint32_t* perm_out;    // where the sort leaves the permutation (the rank's block of the exchange buffer)
-  uint64_t* keys_all;    // every body's key: slice [i0, i1) encoded here and stored into every rank's copy
-  size_t i0, i1;
-  PeerTargets pt;
-  uint32_t epoch;
 };
 
 struct BuildOut {
@@ -1920,7 +1824,7 @@ __global__ void __launch_bounds__(256, 5) walk_kernel(const double4* __restrict_
 //      ShardBuild): its cell table is exact for every cell at level >= K of its range;
 //   2. stores one record per level-K prefix of its range into EVERY rank's dense top tree, through peer
 //      mappings over NVLink (top_export_kernel; the prefixes partition between the ranks, so the stores of all
-//      ranks together ARE the all-gather), and signals the step's epoch to every rank;
+//      ranks together ARE the all-gather); the kernel that follows signals the step's epoch to every rank;
 //   3. rebuilds the cells ABOVE level K, redundantly and identically on every rank, from those records
 //      (top_build_kernel): counts, leaves, centres of mass in ascending digit order with ComSum - the
 //      operations the single-GPU build applies to the same cells, hence the same bits;
@@ -1929,8 +1833,9 @@ __global__ void __launch_bounds__(256, 5) walk_kernel(const double4* __restrict_
 //      loads) when the owner is another rank.  The visiting order is the global pre-order, so the fp32
 //      sums are those of the single-GPU walk;
 //   5. stores its accelerations (sorted order) and the permutation into its block of EVERY rank's exchange
-//      buffer from inside the walk kernel and signals; every rank then advances the replicated state
-//      (verlet_lean_sharded_kernel, which waits for all ranks' signals).  No collective call per step.
+//      buffer from inside the walk kernel; shard_scatter_kernel signals, waits for all ranks' blocks and puts
+//      the accelerations into original order, and every rank advances the replicated state with the
+//      single-GPU lean verlet step.  No collective call per step.
 // The cuts are planned from a replicated (whole-set) build and stay until the host re-plans (multi.cu).
 // ---------------------------------------------------------------------------------------------
 // meta layout (u32), double-buffered by the parity of the epoch (a rank one phase ahead already writes the next
@@ -2777,23 +2682,11 @@ cudaError_t encode_and_sort(GravityWorkspace& ws, size_t n, const SortBuffers& s
   uint64_t* spl_out = ws.splitters.as<uint64_t>() + SPLITTER_STRIDE * (ws.splitter_cur ^ 1);
   ws.splitter_cur ^= 1;
   *splitters_out = spl_out;  // written by the side job of the scan that follows the sort
- if (sb.mode != 0 && sh) {
-    const size_t slice = sh->i1 - sh->i0;
-    if (slice)
-      PB_LAUNCH(ls, st, "encode_keys_kernel",
-                pb_launch_pdl(encode_keys_kernel<DIM>, dim3(blocks_for(slice, 256 * ENC_ITEMS)), dim3(256), 0, st, ws.pos64,
-                              sh->i0, sh->i1, ws.extent_cur, sh->pt));
-    // (plain stream order: the kernel signals this rank's keys and waits for the other ranks')
-#define PB_APPEND(NBV)                                                                                          \
-  PB_LAUNCH(ls, st, "bucket_append_kernel",                                                                      \
-            bucket_append_kernel<NBV><<<blocks_for(n, 256 * ENC_ITEMS), 256, 0, st>>>(                          \
-                sh->keys_all, n, spl_in, sb.lo, ws.bucket_key.as<uint64_t>(), ws.bucket_idx.as<uint32_t>(), sb.cap, \
-                sb.ghist, sh->cuts, sh->pt, sh->epoch))
-    if (sb.nb == 256) PB_APPEND(256u);
-    else if (sb.nb == 512) PB_APPEND(512u);
-    else PB_APPEND(1024u);
-#undef PB_APPEND
-  } else if (sb.mode != 0) {
+  // (Sharded build: every rank computes the keys of ALL bodies itself and keeps those in its range.  Measured,
+  // r02: computing the keys of index slice r on rank r and storing them into every rank's key array - worth it
+  // while a key cost a 21 / 31-step fp64 chain - loses to recomputing the quantised keys: 0.430 vs 0.397 ms per
+  // step at 2 x 1 M bodies, and 8 B x n x (G-1)/G of NVLink stores per rank less.)
+  if (sb.mode != 0) {
 #define PB_ENCODE(NBV)                                                                                            \
   PB_LAUNCH(ls, st, "encode_bucket_kernel",                                                                      \
             pb_launch_pdl(encode_bucket_kernel<DIM, NBV>, dim3(blocks_for(n, 256 * ENC_ITEMS)), dim3(256), 0, st, \
@@ -2803,8 +2696,6 @@ cudaError_t encode_and_sort(GravityWorkspace& ws, size_t n, const SortBuffers& s
     else if (sb.nb == 512) PB_ENCODE(512u);
     else PB_ENCODE(1024u);
 #undef PB_ENCODE
-  }
-  if (sb.mode != 0) {
     uint32_t* n_out = sh ? sh->n_local : nullptr;
     const uint32_t n_cap = sh ? uint32_t(sh->n_cap) : 0u;
     const size_t smem = sort_local_smem(sb.cap);
@@ -2887,7 +2778,7 @@ cudaError_t tree_build(GravityWorkspace& ws, const ShardBuild* sh, cudaStream_t 
   unsigned* n_ready = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(ws.extent_bits.p) + ready_off);
   unsigned* max_shared_plus1 = reinterpret_cast<unsigned*>(ws.extent_bits.as<unsigned long long>() + 1);
   const int key_bits = DIM * TreeDim<DIM>::LM;
-  if (ws.tree_dim != DIM) ws.sort_lo = 0, ws.sort_mode = 0;  // depth / bucket estimates belong to the other tree kind
+  if (ws.tree_dim != DIM) ws.sort_lo = 0, ws.sort_mode = 0, ws.bucket_min_mode = 1;  // depth / bucket estimates belong to the other tree kind
   ws.tree_dim = DIM;
   // Only the global LSD passes get cheaper with fewer key bits (fewer passes).  The bucket sort ranks the
   // members of a bin by comparing whole keys, so it sorts ALL bits at no extra cost - and a depth guess
@@ -2908,7 +2799,7 @@ cudaError_t tree_build(GravityWorkspace& ws, const ShardBuild* sh, cudaStream_t 
   ws.extent_cur = extent;
   SortBuffers sb;
   const BucketPlan bp = bucket_plan(n);
-  int mode = sh ? bp.mode : (bp.mode == 0 ? 0 : ws.sort_mode);
+  int mode = sh ? (bp.mode ? std::max(bp.mode, ws.bucket_min_mode) : 0) : (bp.mode == 0 ? 0 : ws.sort_mode);
   // the splitter set this build reads must have been written for the same number of buckets
   if (mode != 0 && ws.spl_nb[ws.splitter_cur] != bp.nb) {
     if (sh) {
@@ -3091,7 +2982,7 @@ inline uint32_t top_cells(int dim) { return dim == 3 ? TopTree<3>::CELLS : TopTr
 }  // namespace
 
 void ShardState::release() {
-  DevBuf* all[] = {&cuts, &n_local, &slot_cell, &top_ce, &top_com, &top_info, &top_meta, &xacc, &flags, &keys_all};
+  DevBuf* all[] = {&cuts, &n_local, &slot_cell, &top_ce, &top_com, &top_info, &top_meta, &xacc, &flags};
   for (DevBuf* b : all) b->release();
   planned = false;
 }
@@ -3121,7 +3012,6 @@ cudaError_t gravity_shard_setup(GravityWorkspace& ws, int kind, int rank, int wo
   PB_PASS(sh.top_meta.ensure(128 * 4));
   PB_PASS(sh.xacc.ensure(size_t(world) * sh.xacc_block_bytes()));
   PB_PASS(sh.flags.ensure(32 * 4));
-  PB_PASS(sh.keys_all.ensure(n * 8 + 64));
   if (fresh) {  // epochs only ever grow: the flags are cleared once, when the buffer is made
     PB_CUDA(cudaMemset(sh.flags.p, 0, 32 * 4));
     PB_CUDA(cudaMemset(sh.top_meta.p, 0, 128 * 4));
@@ -3162,7 +3052,6 @@ PeerTargets peer_targets(const ShardState& sh) {
     pt.meta[r] = static_cast<uint32_t*>(sh.peers.top_meta[q]);
     pt.xacc[r] = static_cast<char*>(sh.peers.xacc[q]);
     pt.flags[r] = static_cast<uint32_t*>(sh.peers.flags[q]);
-    pt.keys[r] = static_cast<uint64_t*>(sh.peers.keys[q]);
   }
   pt.world = sh.world;
   pt.rank = sh.rank;
@@ -3183,13 +3072,6 @@ cudaError_t shard_build(GravityWorkspace& ws, cudaStream_t st, LaunchStats& ls) 
   // the permutation goes straight into this rank's block of the exchange buffer (behind the accelerations)
   sb.perm_out = reinterpret_cast<uint32_t*>(static_cast<char*>(sh.xacc.p) + size_t(sh.rank) * sh.xacc_block_bytes() +
                                             sh.n_cap * sizeof(float4));
-  // keys: this rank encodes index slice `rank` of the (replicated) bodies for everybody
-  const size_t per = (ws.n + size_t(sh.world) - 1) / size_t(sh.world);
-  sb.keys_all = sh.keys_all.as<uint64_t>();
-  sb.i0 = std::min(ws.n, per * size_t(sh.rank));
-  sb.i1 = std::min(ws.n, per * size_t(sh.rank + 1));
-  sb.pt = peer_targets(sh);
-  sb.epoch = sh.epoch;
   BuildOut bo;
   PB_PASS(tree_build<DIM>(ws, &sb, st, ls, &bo));
   PB_LAUNCH(ls, st, "top_export_kernel",
@@ -3329,14 +3211,27 @@ cudaError_t gravity_check(GravityWorkspace& ws, cudaStream_t st, TreeCheck* out)
   ws.last_max_bucket = h[3];
   out->bucket_overflow = ws.last_mode != 0 && h[3] > LOCAL_CAP[ws.last_mode];
   static const char* mode_env = std::getenv("PB200_SORT_MODE");  // "lsd": global passes only (A/B runs)
-  if (h[3] >= LOCAL_SKEWED || out->bucket_overflow) ws.bucket_ban = 16;  // global passes for a while
-  else if (ws.bucket_ban > 0) --ws.bucket_ban;
+  if (h[3] >= LOCAL_SKEWED) {
+    ws.bucket_ban = 16;  // a thousand bodies on one spot: global passes for a while
+  } else if (out->bucket_overflow) {
+    // fast movers (bodies close to a heavy star cross many keys per step) make the quantile buckets of the
+    // previous step fluctuate: go on with the next capacity class that takes the bucket just seen with 12 % to
+    // spare (4608 -> 8192 -> 16384 keys of shared memory); only when none does, global passes for a while
+    int m = ws.last_mode + 1;
+    while (m <= 3 && LOCAL_CAP[m] < h[3] + h[3] / 8) ++m;
+    if (m <= 3) ws.bucket_min_mode = m;
+    else ws.bucket_ban = 16;
+  } else if (ws.bucket_ban > 0) {
+    --ws.bucket_ban;
+  }
   // the splitters left by a verified build balance the buckets at ~n/256 bodies: pick the smallest
   // capacity with ~12 % headroom (bodies drift between evaluations)
   if ((mode_env && !std::strcmp(mode_env, "lsd")) || ws.bucket_ban > 0 || out->overflow || out->sort_short || out->sort_error)
     ws.sort_mode = 0;
-  else
-    ws.sort_mode = bucket_plan(ws.n).mode;
+  else {
+    const int m = bucket_plan(ws.n).mode;
+    ws.sort_mode = m ? std::max(m, ws.bucket_min_mode) : 0;
+  }
   static const bool debug_check = std::getenv("PB200_DEBUG_CHECK") != nullptr;
   if (debug_check)
     std::fprintf(stderr, "[physim_b200] check: cells %u (cap %zu) deepest %d lo %d mode %d max_bucket %u overflow %d short %d "

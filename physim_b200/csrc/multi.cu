@@ -107,7 +107,7 @@ float elapsed_ms(cudaEvent_t a, cudaEvent_t b) {
 
 // what a rank tells the others about the buffers they read or write (exchanged once per plan):
 // cell table (centre_ext, com, skip), dense top tree (info, com), per-rank counts, exchange buffer, flags
-constexpr int kPeerBufs = 9;
+constexpr int kPeerBufs = 8;
 struct PeerRecord {
   uint64_t pid;
   uint64_t capacity;     // cells
@@ -218,8 +218,7 @@ cudaError_t exchange_peers(MultiSim& m) {
     rec.capacity = c->ws.cell_cap;
     const ShardState& sh = c->ws.shard;
     const void* p[kPeerBufs] = {c->ws.c_centre_ext.p, c->ws.c_com.p, c->ws.c_skip.p, sh.top_info.p,
-                                sh.top_com.p,         sh.top_meta.p, sh.xacc.p,      sh.flags.p,
-                                sh.keys_all.p};
+                                sh.top_com.p,         sh.top_meta.p, sh.xacc.p,      sh.flags.p};
     for (int k = 0; k < kPeerBufs; ++k) {
       rec.ptr[k] = reinterpret_cast<uint64_t>(p[k]);
       if (m.local.size() < size_t(m.world)) PB_CUDA(cudaIpcGetMemHandle(&rec.handle[k], const_cast<void*>(p[k])));
@@ -282,7 +281,6 @@ cudaError_t exchange_peers(MultiSim& m) {
       sp.top_meta[r] = q[5];
       sp.xacc[r] = q[6];
       sp.flags[r] = q[7];
-      sp.keys[r] = q[8];
     }
     sp.capacity = uint32_t(std::min<uint64_t>(cap, 0xfffffff0ull));
     c->have_peers = true;
