@@ -1375,6 +1375,7 @@ __global__ void __launch_bounds__(256, MIN_BLOCKS) cells_kernel(const uint64_t* 
     const uint64_t diff = (kme ^ s_refkey) << (64 - DIM * LM);
     const int lcp = diff ? __clzll(static_cast<long long>(diff)) / DIM : LM;
     const int l0 = min(min(lcp, top), leaf_level);
+    const uint32_t leaf_skip = abn.x != NOT_HEAD ? cs1 : 0u;  // (merged unit: written once its end is known)
     double half = s_ref[l0][3];
     double cx = s_ref[l0][0], cy = s_ref[l0][1], cz = s_ref[l0][2];
     uint64_t digits = l0 < LM ? kme << (64 - DIM * LM + DIM * l0) : 0ull;  // next digit in the top DIM bits (pseudo levels compare the body)
@@ -1382,11 +1383,12 @@ __global__ void __launch_bounds__(256, MIN_BLOCKS) cells_kernel(const uint64_t* 
       if (l >= top) {
         const uint32_t c = c0 + uint32_t(l - top);
         cells.level[c] = static_cast<uint8_t>(l);
-        // {cx, cy, cz}; the fourth word (link) is written once, by whoever learns the skip link: below for the
-        // leaf, in phase 2 for the internal cells
-        double* rec = reinterpret_cast<double*>(cells.centre_ext + c);
-        *reinterpret_cast<double2*>(rec) = make_double2(cx, cy);
-        rec[2] = cz;
+        // {cx, cy, cz, link}: the leaf's link is complete here (its skip link is the next body's first cell);
+        // an internal cell's carries the level, its skip half is filled in by phase 2 (a 4-byte store by the
+        // lane that runs the cell's query; __syncwarp below orders the two stores)
+        double2* rec = reinterpret_cast<double2*>(cells.centre_ext + c);
+        rec[0] = make_double2(cx, cy);
+        rec[1] = make_double2(cz, pack_link(l == leaf_level ? leaf_skip : 0u, l));
       }
       if (l < leaf_level) {  // from level l to level l+1 along the head body's path
         unsigned digit = unsigned(digits >> (64 - DIM));
@@ -1403,11 +1405,9 @@ __global__ void __launch_bounds__(256, MIN_BLOCKS) cells_kernel(const uint64_t* 
     }
     // leaf: the unit itself
     const uint32_t c = c0 + uint32_t(leaf_level - top);
-    double* link = reinterpret_cast<double*>(cells.centre_ext + c) + 3;
     if (abn.x != NOT_HEAD) {  // (always, unless bodies were merged)
       cells.count[c] = 1u;
       cells.skip[c] = cs1;
-      *link = pack_link(cs1, leaf_level);
       cells.com[c] = me;
     } else {
       size_t e = s + 2;
@@ -1415,7 +1415,7 @@ __global__ void __launch_bounds__(256, MIN_BLOCKS) cells_kernel(const uint64_t* 
       cells.count[c] = static_cast<uint32_t>(e - s);
       const uint32_t sk = cell_start[e];
       cells.skip[c] = sk;
-      *link = pack_link(sk, leaf_level);
+      reinterpret_cast<uint32_t*>(cells.centre_ext + c)[6] = sk;  // (the low half of the link word)
       cells.com[c] = unit_leaf(sp, perm, s, e);
     }
     if (slots.slot_cell && top <= slots.level) {  // s is the first body of its level-K prefix
@@ -1425,6 +1425,7 @@ __global__ void __launch_bounds__(256, MIN_BLOCKS) cells_kernel(const uint64_t* 
   }
 
   // phase 2: task t of the warp = internal cell number (t - excl[o]) of the chain of lane o
+  __syncwarp();  // phase 1's record stores before phase 2's stores into the same link words (other lanes)
   const int mine = is_head ? leaf_level - top : 0;
   int incl = mine;
 #pragma unroll
@@ -1452,7 +1453,7 @@ __global__ void __launch_bounds__(256, MIN_BLOCKS) cells_kernel(const uint64_t* 
     cells.count[c] = cnt;
     const uint32_t sk_c = cell_start[e];
     cells.skip[c] = sk_c;
-    reinterpret_cast<double*>(cells.centre_ext + c)[3] = pack_link(sk_c, lev);
+    reinterpret_cast<uint32_t*>(cells.centre_ext + c)[6] = sk_c;  // (low half of the link word; phase 1 wrote the level)
     if (cnt > cells.small || uint32_t(lev) < cells.top_level) continue;
     ComSum sum;
     if (!merged_units) {  // no merged unit anywhere: plain sums over the run
