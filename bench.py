@@ -565,6 +565,12 @@ def measure_bh_large(api, torch, dist, rank, world, local_rank):
         out.update({"ms_per_step": ms / steps, "value": n * steps / (ms * 1e-3), "unit": "particle-steps/s",
                     "steps": steps, "n_cells": st["n_cells"], "interactions_per_step": st["interactions"],
                     "interactions_per_s": st["interactions"] * steps / (ms * 1e-3)})
+        sim.profile(True)   # per-kernel device times (event pairs around every launch), 3 more steps
+        sim.run(3)
+        torch.cuda.synchronize()
+        rep = sim.profile_report()
+        sim.profile(False)
+        out["kernels_ms_per_step"] = {k["kernel"]: round(k["ms"] / 3, 4) for k in sorted(rep, key=lambda k: -k["ms"])}
         if world > 1:
             bodies, _ = sim.rank_counts()
             out["sharding"] = {"sharded_steps": st.get("sharded_steps"), "replicated_steps": st.get("replicated_steps"),
