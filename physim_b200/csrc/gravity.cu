@@ -442,10 +442,12 @@ __global__ void __launch_bounds__(SORT_THREADS, SORT_ITEMS >= 16 ? 2 : 4) sort_o
 //                            (per-CTA counts in shared memory, one global atomic per CTA and bucket)
 //      sort_local_kernel     CTA b sorts bucket b in shared memory: counting sort on <= 12 bits of
 //                            (key >> lo) - bucket base, then every element ranks itself inside its
-//                            (tiny) bin by (key >> lo, index); keys, permutation and the gathered
-//                            {x,y,z,m} records go straight to their final places.
-//      A bucket above capacity or a bin above LOCAL_BIN_LIMIT leaves the build flagged `bad`; the
-//      host re-runs it with the global passes.
+//                            (tiny) bin by (key >> lo, index) - a bin of more than LOCAL_BIN_LIMIT
+//                            bodies (a clump inside the bucket) is sorted by the whole CTA instead;
+//                            keys, permutation and the gathered {x,y,z,m} records go straight to their
+//                            final places.
+//      A bucket above capacity leaves the build flagged `bad`; the host re-runs it with the next capacity
+//      class (or, beyond the largest, with the global passes).
 // HBM per body: 32 R + 12 W, then 12 R + 12 W + 32 R + 32 W.
 // ---------------------------------------------------------------------------------------------
 template <int NT>
@@ -482,8 +484,9 @@ constexpr int LOCAL_BIN_BITS = 12;     // counting-sort bins inside a bucket
 // A bucket whose bodies sit in a few clumps of its key range (a rotating cube leaves the corners of its bounding
 // cell empty: key ranges with nothing in them) puts 50-400 in a bin, which still costs microseconds; only a
 // bin of more than this many (a thousand bodies on one spot) hands the build to the global passes.
-constexpr unsigned LOCAL_BIN_LIMIT = 1024;
-constexpr unsigned LOCAL_SKEWED = 0x7fffffffu;  // published as "largest bucket" when a bin is too full
+constexpr unsigned LOCAL_BIN_LIMIT = 512;     // bins up to this size: every member ranks itself by scanning the bin
+constexpr unsigned LOCAL_BIG_BINS = 62;       // larger bins a bucket may have (each is sorted by the whole CTA)
+constexpr unsigned LOCAL_SKEWED = 0x7fffffffu;  // published as "largest bucket" when a bucket has more big bins than that
 
 template <int DIM, unsigned NB /* buckets: 256, 512 or 1024 */>
 __global__ void __launch_bounds__(256) encode_bucket_kernel(const double4* __restrict__ pos, size_t n,
@@ -554,7 +557,8 @@ __global__ void __launch_bounds__(256) encode_bucket_kernel(const double4* __res
 }
 
 inline size_t sort_local_smem(unsigned cap) {
-  return size_t(cap) * 12 + (size_t(1) << LOCAL_BIN_BITS) * 4 + 32 * 4 + 32;  // ... + seg[4] + key range (2 x u64)
+  // ... + seg[4] + key range (2 x u64) + the list of big bins
+  return size_t(cap) * 12 + (size_t(1) << LOCAL_BIN_BITS) * 4 + 32 * 4 + 32 + (LOCAL_BIG_BINS + 2) * 4;
 }
 
 // The first RITEMS * NT elements of the bucket stay in registers between the counting and the
@@ -655,16 +659,13 @@ __global__ void __launch_bounds__(NT, 1024 / NT) sort_local_kernel(
     if (unsigned(i) * NT + tid < cnt) atomicAdd(&bins[bin_of(k[i])], 1u);
   for (unsigned p = unsigned(RITEMS) * NT + tid; p < cnt; p += NT) atomicAdd(&bins[bin_of(gk[p])], 1u);
   __syncthreads();
-  {  // exclusive scan of the bin counts (BPT consecutive bins per thread) + the largest bin
-    unsigned c[BPT], sum = 0, mx = 0;
+  {  // exclusive scan of the bin counts (BPT consecutive bins per thread)
+    unsigned c[BPT], sum = 0;
 #pragma unroll
     for (int q = 0; q < BPT; ++q) {
       c[q] = bins[tid * BPT + q];
       sum += c[q];
-      mx = max(mx, c[q]);
     }
-    mx = __reduce_max_sync(FULL, mx);
-    if ((tid & 31) == 0 && mx > LOCAL_BIN_LIMIT) atomicMax(&seg[2], mx);
     unsigned run = block_exclusive_scan_nt<NT>(sum, wsum);  // syncs
 #pragma unroll
     for (int q = 0; q < BPT; ++q) {
@@ -672,13 +673,6 @@ __global__ void __launch_bounds__(NT, 1024 / NT) sort_local_kernel(
       run += c[q];
     }
     __syncthreads();
-  }
-  if (seg[2] > LOCAL_BIN_LIMIT) {  // too many bodies agree on the bin bits: leave it to the global sort
-    if (tid == 0) {
-      *bad = 1u;
-      atomicMax(stat_max, LOCAL_SKEWED);
-    }
-    return;
   }
 #pragma unroll
   for (int i = 0; i < RITEMS; ++i) {
@@ -695,6 +689,62 @@ __global__ void __launch_bounds__(NT, 1024 / NT) sort_local_kernel(
     vs[slot] = gv[p];
   }
   __syncthreads();
+  // Big bins.  A bucket that holds a clump AND a few far bodies maps the clump onto one or two of its bins (bodies
+  // falling towards a heavy star do that to the cube within ~100 steps of the 1 M-body astro2 run): ranking by
+  // scanning is quadratic in the bin, so a bin of more than LOCAL_BIN_LIMIT bodies is sorted here by the whole CTA
+  // - a bitonic network in its all-ascending form (first step of a merge against the mirrored partner), which
+  // needs no padding: a partner index past the end stands for +infinity and never moves anything - by (key bits,
+  // index), the order the scan establishes.  Its members then rank by position.
+  unsigned* big = seg + 8;  // [0] count, [1..] bin ids
+  if (tid == 0) big[0] = 0u;
+  __syncthreads();
+  for (unsigned b = tid; b < unsigned(NBINS); b += NT) {
+    const unsigned sz = bins[b] - (b ? bins[b - 1u] : 0u);
+    if (sz > LOCAL_BIN_LIMIT) {
+      const unsigned at = atomicAdd(&big[0], 1u);
+      if (at < LOCAL_BIG_BINS) big[1u + at] = b;
+    }
+  }
+  __syncthreads();
+  const unsigned n_big = big[0];
+  if (n_big > LOCAL_BIG_BINS) {  // (32 k bodies in one bucket would be needed: leave it to the global sort)
+    if (tid == 0) {
+      *bad = 1u;
+      atomicMax(stat_max, LOCAL_SKEWED);
+    }
+    return;
+  }
+  for (unsigned bi = 0; bi < n_big; ++bi) {
+    const unsigned b = big[1u + bi];
+    const unsigned s0 = b ? bins[b - 1u] : 0u, m = bins[b] - s0;
+    unsigned P = 1u;
+    while (P < m) P <<= 1;
+    auto exchange = [&](unsigned i, unsigned j) {  // ascending: the smaller (key bits, index) to the lower place
+      if (j >= m) return;
+      const uint64_t ki = ks[s0 + i], kj = ks[s0 + j];
+      const uint32_t vi = vs[s0 + i], vj = vs[s0 + j];
+      const uint64_t bi_ = ki >> lo, bj_ = kj >> lo;
+      if (bi_ > bj_ || (bi_ == bj_ && vi > vj)) {
+        ks[s0 + i] = kj; ks[s0 + j] = ki;
+        vs[s0 + i] = vj; vs[s0 + j] = vi;
+      }
+    };
+    for (unsigned kk = 2u; kk <= P; kk <<= 1) {
+      const unsigned hk = kk >> 1;
+      for (unsigned t = tid; t < (P >> 1); t += NT) {
+        const unsigned blk = t / hk, off = t % hk;
+        exchange(blk * kk + off, blk * kk + kk - 1u - off);
+      }
+      __syncthreads();
+      for (unsigned j2 = kk >> 2; j2 > 0u; j2 >>= 1) {
+        for (unsigned t = tid; t < (P >> 1); t += NT) {
+          const unsigned i = (t / j2) * 2u * j2 + (t % j2);
+          exchange(i, i + j2);
+        }
+        __syncthreads();
+      }
+    }
+  }
   // bins[b] is now the end of bin b (and the start of bin b+1)
   for (unsigned p = tid; p < cnt; p += NT) {
     const uint64_t key = ks[p];
@@ -702,10 +752,13 @@ __global__ void __launch_bounds__(NT, 1024 / NT) sort_local_kernel(
     const unsigned bin = bin_of(key);
     const unsigned s = bin ? bins[bin - 1u] : 0u, e = bins[bin];
     const uint64_t kme = key >> lo;
-    unsigned rank = 0;
-    for (unsigned q = s; q < e; ++q) {
-      const uint64_t kq = ks[q] >> lo;
-      rank += (kq < kme || (kq == kme && vs[q] < id)) ? 1u : 0u;
+    unsigned rank = p - s;  // (a big bin: sorted above)
+    if (e - s <= LOCAL_BIN_LIMIT) {
+      rank = 0;
+      for (unsigned q = s; q < e; ++q) {
+        const uint64_t kq = ks[q] >> lo;
+        rank += (kq < kme || (kq == kme && vs[q] < id)) ? 1u : 0u;
+      }
     }
     const size_t dst = size_t(start) + s + rank;
     keys[dst] = key;
@@ -768,6 +821,8 @@ struct ScanSide {
   const uint64_t* sorted;     // CTA nsuper: splitter_block
   uint64_t* spl_out;
   unsigned nb;                // buckets the next evaluation's bucket sort will use
+  const uint64_t* spl_keep;   // the set THIS build read (same nb), or nullptr; handed on unchanged when the build
+  const unsigned* bad;        // ... was abandoned (a bucket over capacity: `sorted` is incomplete)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -795,7 +850,13 @@ __global__ void __launch_bounds__(256) scan_lookback_kernel(const uint32_t* __re
       const unsigned job = tile - tiles;
       const size_t nblocks = (n + 255) / 256, nsuper = (nblocks + 255) / 256;
       if (job < nsuper) nsv_level2_block(job, side.t2, side.b_pad, nblocks, side.t3);
-      else if (job == nsuper) splitter_block(side.sorted, n, side.spl_out, side.nb);
+      else if (job == nsuper) {
+        if (side.spl_keep && *side.bad) {
+          for (unsigned j = threadIdx.x; j <= side.nb; j += 256) side.spl_out[j] = side.spl_keep[j];
+        } else {
+          splitter_block(side.sorted, n, side.spl_out, side.nb);
+        }
+      }
     }
     return;
   }
@@ -2826,7 +2887,10 @@ cudaError_t tree_build(GravityWorkspace& ws, const ShardBuild* sh, cudaStream_t 
                                        ws.tgt_flags.as<uint32_t>(), max_shared_plus1,
                                        lo > 0 ? (key_bits - lo) / DIM : TreeDim<DIM>::LM + 2,
                                        ws.nsv1.as<uint8_t>(), n_pad, ws.nsv2.as<uint8_t>()));
-  const ScanSide side{ws.nsv2.as<uint8_t>(), b_pad, nsv3, ws.sorted_key, spl_out, bp.nb};
+  // (encode_and_sort toggled splitter_cur: [cur] is the set the scan's side job writes, [cur ^ 1] the one this build read)
+  const uint64_t* spl_read = ws.splitters.as<uint64_t>() + SPLITTER_STRIDE * (ws.splitter_cur ^ 1);
+  const ScanSide side{ws.nsv2.as<uint8_t>(), b_pad, nsv3, ws.sorted_key, spl_out, bp.nb,
+                      (sb.mode != 0 && ws.spl_nb[ws.splitter_cur ^ 1] == bp.nb) ? spl_read : nullptr, max_shared_plus1 + 2};
   ws.spl_nb[ws.splitter_cur] = bp.nb;  // (encode_and_sort toggled splitter_cur: this is the set the scan's side job writes)
   PB_PASS(exclusive_scan_with_side(ws.tgt_flags.as<uint32_t>(), ws.cell_start.as<uint32_t>(), nref, n, scan_scratch, side, st, ls));
 

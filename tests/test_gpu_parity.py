@@ -326,9 +326,12 @@ def test_bucket_sort_overflow_and_skew_fall_back(name):
         el.transform(gen.cube(30_000, seed=2))
     # Crowds around one spot.  100 coincident bodies (one merged unit) and 1500 within 1e-5 are sorted by the
     # bucket sort: the bins follow the key range a bucket's bodies actually span, so a crowd spreads over them.
-    # 3000 bodies within 1e-7 share one or two 63-bit octree keys (the key resolves extent * 2^-21 = 5e-7): more than
-    # a bin may hold, the build goes to the global passes.  (The 62-bit quadtree key resolves 5e-10: no crowding.)
-    for crowd, spread, want_mode in ((100, 0.0, 1), (1500, 1e-5, 1), (3000, 1e-7, 0 if name == "astro2" else 1)):
+    # 3000 bodies within 1e-7 share one or two 63-bit octree keys (the key resolves extent * 2^-21 = 5e-7): one bin
+    # of thousands, which the bucket's CTA sorts as a whole (bitonic network) instead of letting every member scan
+    # it - the build stays on the bucket sort.  (The 62-bit quadtree key resolves 5e-10: no crowding.)
+    for crowd, spread, want_mode in ((100, 0.0, 1), (1500, 1e-5, 1), (3000, 1e-7, 1), (6000, 1e-7, 1),
+                                    # 6000 bodies on ONE octree key: a bucket of > 4608, the next capacity class
+                                    (6000, 2e-8, 2 if name == "astro2" else 1)):
         twins = gen.cube(20_000, seed=8)
         jit = np.random.default_rng(crowd).random((crowd, 3)) * spread
         twins["x"][:crowd], twins["y"][:crowd], twins["z"][:crowd] = 0.3 + jit[:, 0], -0.2 + jit[:, 1], 0.6 + jit[:, 2]
