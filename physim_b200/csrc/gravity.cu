@@ -442,8 +442,8 @@ __global__ void __launch_bounds__(SORT_THREADS, SORT_ITEMS >= 16 ? 2 : 4) sort_o
 //                            (per-CTA counts in shared memory, one global atomic per CTA and bucket)
 //      sort_local_kernel     CTA b sorts bucket b in shared memory: counting sort on <= 12 bits of
 //                            (key >> lo) - bucket base, then every element ranks itself inside its
-//                            (tiny) bin by (key >> lo, index) - a bin of more than LOCAL_BIN_LIMIT
-//                            bodies (a clump inside the bucket) is sorted by the whole CTA instead;
+//                            (tiny) bin by (key >> lo, index) - a bin of more than LOCAL_SCAN_LIMIT
+//                            bodies (a clump inside the bucket) is sorted by a warp or the whole CTA instead;
 //                            keys, permutation and the gathered {x,y,z,m} records go straight to their
 //                            final places.
 //      A bucket above capacity leaves the build flagged `bad`; the host re-runs it with the next capacity
@@ -484,8 +484,10 @@ constexpr int LOCAL_BIN_BITS = 12;     // counting-sort bins inside a bucket
 // A bucket whose bodies sit in a few clumps of its key range (a rotating cube leaves the corners of its bounding
 // cell empty: key ranges with nothing in them) puts 50-400 in a bin, which still costs microseconds; only a
 // bin of more than this many (a thousand bodies on one spot) hands the build to the global passes.
-constexpr unsigned LOCAL_BIN_LIMIT = 512;     // bins up to this size: every member ranks itself by scanning the bin
-constexpr unsigned LOCAL_BIG_BINS = 62;       // larger bins a bucket may have (each is sorted by the whole CTA)
+constexpr unsigned LOCAL_SCAN_LIMIT = 48;     // bins up to this size: every member ranks itself by scanning the bin
+constexpr unsigned LOCAL_BIN_LIMIT = 1024;    // bins up to this size are sorted by one warp, larger ones by the whole CTA
+constexpr unsigned LOCAL_BIG_BINS = 30;       // CTA-sorted bins a bucket may have (16 k keys / 1024 = 16 at most)
+constexpr unsigned LOCAL_MID_BINS = 352;      // warp-sorted bins a bucket may have (16 k keys / 48 = 341 at most)
 constexpr unsigned LOCAL_SKEWED = 0x7fffffffu;  // published as "largest bucket" when a bucket has more big bins than that
 
 template <int DIM, unsigned NB /* buckets: 256, 512 or 1024 */>
@@ -558,7 +560,7 @@ __global__ void __launch_bounds__(256) encode_bucket_kernel(const double4* __res
 
 inline size_t sort_local_smem(unsigned cap) {
   // ... + seg[4] + key range (2 x u64) + the list of big bins
-  return size_t(cap) * 12 + (size_t(1) << LOCAL_BIN_BITS) * 4 + 32 * 4 + 32 + (LOCAL_BIG_BINS + 2) * 4;
+  return size_t(cap) * 12 + (size_t(1) << LOCAL_BIN_BITS) * 4 + 32 * 4 + 32 + (LOCAL_BIG_BINS + 2 + LOCAL_MID_BINS) * 4;
 }
 
 // The first RITEMS * NT elements of the bucket stay in registers between the counting and the
@@ -689,62 +691,92 @@ __global__ void __launch_bounds__(NT, 1024 / NT) sort_local_kernel(
     vs[slot] = gv[p];
   }
   __syncthreads();
-  // Big bins.  A bucket that holds a clump AND a few far bodies maps the clump onto one or two of its bins (bodies
-  // falling towards a heavy star do that to the cube within ~100 steps of the 1 M-body astro2 run): ranking by
-  // scanning is quadratic in the bin, so a bin of more than LOCAL_BIN_LIMIT bodies is sorted here by the whole CTA
-  // - a bitonic network in its all-ascending form (first step of a merge against the mirrored partner), which
-  // needs no padding: a partner index past the end stands for +infinity and never moves anything - by (key bits,
-  // index), the order the scan establishes.  Its members then rank by position.
-  unsigned* big = seg + 8;  // [0] count, [1..] bin ids
-  if (tid == 0) big[0] = 0u;
+  // Crowded bins.  A bucket that holds a clump AND a few far bodies maps the clump onto a few of its bins (bodies
+  // falling towards a heavy star do that to the cube within ~100 steps of the 1 M-body astro2 run).  Ranking by
+  // scanning is quadratic in the bin, so only bins of <= LOCAL_SCAN_LIMIT bodies are ranked that way; a larger bin
+  // is SORTED in place - by one warp up to LOCAL_BIN_LIMIT bodies (the warps share the bins out), by the whole CTA
+  // above - with a bitonic network in its all-ascending form (first step of a merge against the mirrored partner),
+  // which needs no padding: a partner index past the end stands for +infinity and never moves anything.  The order
+  // is (key bits, index), the one the scan establishes; the members of a sorted bin then rank by position.
+  unsigned* big = seg + 8;                      // [0] count, [1 ..] bin ids: CTA-sorted
+  unsigned* mid = big + LOCAL_BIG_BINS + 2;     // [0] count, [1 ..] bin ids: warp-sorted
+  if (tid == 0) big[0] = mid[0] = 0u;
   __syncthreads();
   for (unsigned b = tid; b < unsigned(NBINS); b += NT) {
     const unsigned sz = bins[b] - (b ? bins[b - 1u] : 0u);
     if (sz > LOCAL_BIN_LIMIT) {
       const unsigned at = atomicAdd(&big[0], 1u);
       if (at < LOCAL_BIG_BINS) big[1u + at] = b;
+    } else if (sz > LOCAL_SCAN_LIMIT) {
+      const unsigned at = atomicAdd(&mid[0], 1u);
+      if (at < LOCAL_MID_BINS - 1u) mid[1u + at] = b;
     }
   }
   __syncthreads();
-  const unsigned n_big = big[0];
-  if (n_big > LOCAL_BIG_BINS) {  // (32 k bodies in one bucket would be needed: leave it to the global sort)
+  const unsigned n_big = big[0], n_mid = mid[0];
+  if (n_big > LOCAL_BIG_BINS || n_mid > LOCAL_MID_BINS - 1u) {  // (cannot happen within the capacity; kept as a guard)
     if (tid == 0) {
       *bad = 1u;
       atomicMax(stat_max, LOCAL_SKEWED);
     }
     return;
   }
-  for (unsigned bi = 0; bi < n_big; ++bi) {
+  auto exchange = [&](unsigned s0, unsigned m, unsigned i, unsigned j) {  // ascending: the smaller (key bits, index) first
+    if (j >= m) return;
+    const uint64_t ki = ks[s0 + i], kj = ks[s0 + j];
+    const uint32_t vi = vs[s0 + i], vj = vs[s0 + j];
+    const uint64_t bi_ = ki >> lo, bj_ = kj >> lo;
+    if (bi_ > bj_ || (bi_ == bj_ && vi > vj)) {
+      ks[s0 + i] = kj; ks[s0 + j] = ki;
+      vs[s0 + i] = vj; vs[s0 + j] = vi;
+    }
+  };
+  for (unsigned bi = 0; bi < n_big; ++bi) {  // the whole CTA, one bin after the other
     const unsigned b = big[1u + bi];
     const unsigned s0 = b ? bins[b - 1u] : 0u, m = bins[b] - s0;
     unsigned P = 1u;
     while (P < m) P <<= 1;
-    auto exchange = [&](unsigned i, unsigned j) {  // ascending: the smaller (key bits, index) to the lower place
-      if (j >= m) return;
-      const uint64_t ki = ks[s0 + i], kj = ks[s0 + j];
-      const uint32_t vi = vs[s0 + i], vj = vs[s0 + j];
-      const uint64_t bi_ = ki >> lo, bj_ = kj >> lo;
-      if (bi_ > bj_ || (bi_ == bj_ && vi > vj)) {
-        ks[s0 + i] = kj; ks[s0 + j] = ki;
-        vs[s0 + i] = vj; vs[s0 + j] = vi;
-      }
-    };
-    for (unsigned kk = 2u; kk <= P; kk <<= 1) {
+    for (unsigned kk = 2u; kk <= P; kk <<= 1) {  // (powers of two: masks and shifts, no divisions)
       const unsigned hk = kk >> 1;
       for (unsigned t = tid; t < (P >> 1); t += NT) {
-        const unsigned blk = t / hk, off = t % hk;
-        exchange(blk * kk + off, blk * kk + kk - 1u - off);
+        const unsigned base = (t & ~(hk - 1u)) << 1, off = t & (hk - 1u);
+        exchange(s0, m, base + off, base + kk - 1u - off);
       }
       __syncthreads();
       for (unsigned j2 = kk >> 2; j2 > 0u; j2 >>= 1) {
         for (unsigned t = tid; t < (P >> 1); t += NT) {
-          const unsigned i = (t / j2) * 2u * j2 + (t % j2);
-          exchange(i, i + j2);
+          const unsigned i = ((t & ~(j2 - 1u)) << 1) | (t & (j2 - 1u));
+          exchange(s0, m, i, i + j2);
         }
         __syncthreads();
       }
     }
   }
+  {  // one warp per bin
+    const unsigned warp = unsigned(tid) >> 5, lane = unsigned(tid) & 31u;
+    for (unsigned mi = warp; mi < n_mid; mi += NT / 32) {
+      const unsigned b = mid[1u + mi];
+      const unsigned s0 = b ? bins[b - 1u] : 0u, m = bins[b] - s0;
+      unsigned P = 1u;
+      while (P < m) P <<= 1;
+      for (unsigned kk = 2u; kk <= P; kk <<= 1) {
+        const unsigned hk = kk >> 1;
+        for (unsigned t = lane; t < (P >> 1); t += 32u) {
+          const unsigned base = (t & ~(hk - 1u)) << 1, off = t & (hk - 1u);
+          exchange(s0, m, base + off, base + kk - 1u - off);
+        }
+        __syncwarp();
+        for (unsigned j2 = kk >> 2; j2 > 0u; j2 >>= 1) {
+          for (unsigned t = lane; t < (P >> 1); t += 32u) {
+            const unsigned i = ((t & ~(j2 - 1u)) << 1) | (t & (j2 - 1u));
+            exchange(s0, m, i, i + j2);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  }
+  __syncthreads();
   // bins[b] is now the end of bin b (and the start of bin b+1)
   for (unsigned p = tid; p < cnt; p += NT) {
     const uint64_t key = ks[p];
@@ -752,8 +784,8 @@ __global__ void __launch_bounds__(NT, 1024 / NT) sort_local_kernel(
     const unsigned bin = bin_of(key);
     const unsigned s = bin ? bins[bin - 1u] : 0u, e = bins[bin];
     const uint64_t kme = key >> lo;
-    unsigned rank = p - s;  // (a big bin: sorted above)
-    if (e - s <= LOCAL_BIN_LIMIT) {
+    unsigned rank = p - s;  // (a crowded bin: sorted above)
+    if (e - s <= LOCAL_SCAN_LIMIT) {
       rank = 0;
       for (unsigned q = s; q < e; ++q) {
         const uint64_t kq = ks[q] >> lo;
