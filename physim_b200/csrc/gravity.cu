@@ -2201,21 +2201,54 @@ __global__ void __launch_bounds__(256) walk_sharded_kernel(const double4* __rest
   }
 }
 
-// Step 5: signals this rank's accelerations (walk_sharded_kernel, just completed on this stream), waits for every
-// rank's, then puts block r's record j where the integrator reads it: acc[perm_r[j]] (original order, all bodies).
+// Step 5: signals this rank's accelerations (walk_sharded_kernel, just completed on this stream), then puts block
+// r's record j - once rank r has signalled - where the integrator reads it: acc[perm_r[j]] (original order, all bodies).
 // Coalesced 20-byte reads, 16-byte scattered stores; the lean verlet step that follows is the single-GPU one.
 __global__ void __launch_bounds__(256) shard_scatter_kernel(const char* __restrict__ xacc, size_t n_cap,
                                                             const uint32_t* __restrict__ n_locals, PeerTargets pt,
                                                             uint32_t epoch, float4* __restrict__ acc, size_t n) {
-  shard_signal_then_wait(pt, SHARD_FLAG_WALK, epoch, blockIdx.x == 0 && blockIdx.y == 0);
-  const unsigned r = blockIdx.y;
-  const size_t n_r = min(size_t(n_locals[r]), n_cap);
-  const size_t j = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
-  if (j >= n_r) return;
-  const char* block = xacc + size_t(r) * (n_cap * 20);
-  const float4 a = reinterpret_cast<const float4*>(block)[j];
-  const uint32_t i = reinterpret_cast<const uint32_t*>(block + n_cap * sizeof(float4))[j];
-  if (i < n) acc[i] = a;
+  // Persistent CTAs (one wave): each takes its grid-stride share of EVERY rank's block, in the order in which the
+  // ranks signal (own block first): what has arrived is put in place while slower ranks are still walking.
+  __shared__ unsigned s_next;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {  // this rank's accelerations are in place everywhere
+    __threadfence_system();
+    for (int q = 0; q < pt.world; ++q)
+      *reinterpret_cast<volatile uint32_t*>(pt.flags[q] + SHARD_FLAG_WALK + pt.rank) = epoch;
+  }
+  const size_t j0 = blockIdx.x * size_t(blockDim.x) + threadIdx.x, stride = size_t(gridDim.x) * blockDim.x;
+  const unsigned world = unsigned(pt.world), all = (1u << world) - 1u;
+  unsigned done = 0u, spins = 0u;
+  while (done != all) {
+    if (threadIdx.x == 0) {
+      unsigned found = world;
+      volatile uint32_t* f = pt.flags[pt.rank] + SHARD_FLAG_WALK;
+      for (unsigned k = 0; k < world; ++k) {
+        const unsigned r = (unsigned(pt.rank) + k) % world;
+        if (!((done >> r) & 1u) && int32_t(f[r] - epoch) >= 0) { found = r; break; }
+      }
+      if (found != world) __threadfence_system();
+      s_next = found;
+    }
+    __syncthreads();
+    const unsigned r = s_next;
+    __syncthreads();
+    if (r == world) {  // nobody new yet
+      __nanosleep(128);
+      if (++spins > (1u << 24)) {  // ~ seconds: a peer never signalled (the host's next check reports it)
+        if (threadIdx.x == 0) pt.flags[pt.rank][SHARD_TIMEOUT] = 1u;
+        break;
+      }
+      continue;
+    }
+    done |= 1u << r;
+    const size_t n_r = min(size_t(n_locals[r]), n_cap);
+    const char* block = xacc + size_t(r) * (n_cap * 20);
+    for (size_t j = j0; j < n_r; j += stride) {
+      const float4 a = reinterpret_cast<const float4*>(block)[j];
+      const uint32_t i = reinterpret_cast<const uint32_t*>(block + n_cap * sizeof(float4))[j];
+      if (i < n) acc[i] = a;
+    }
+  }
 }
 
 // After a full (replicated) build: the first cuts, balanced on the sorted keys, and the splitters of this
@@ -3226,7 +3259,7 @@ cudaError_t gravity_shard_scatter(GravityWorkspace& ws, cudaStream_t st, LaunchS
   const uint32_t* n_locals = sh.top_meta.as<uint32_t>() + (sh.epoch & 1u) * uint32_t(META_STRIDE) + uint32_t(META_BODIES);
   // (plain stream order, not a programmatic dependent: see shard_signal_then_wait)
   PB_LAUNCH(ls, st, "shard_scatter_kernel",
-            shard_scatter_kernel<<<dim3(blocks_for(sh.n_cap, 256), unsigned(sh.world)), 256, 0, st>>>(
+            shard_scatter_kernel<<<std::min(blocks_for(sh.n_cap, 256), 148u * 8u), 256, 0, st>>>(
                 static_cast<const char*>(sh.xacc.p), sh.n_cap, n_locals, peer_targets(sh), sh.epoch, ws.acc.as<float4>(), ws.n));
   return cudaGetLastError();
 }
