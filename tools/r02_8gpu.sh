@@ -1,4 +1,5 @@
 set -x
+timeout 300 python -m pytest tests/test_gpu_multi.py -m gpu -q > gpurun_out/pytest_gpu_multi_r02_8gpu.log 2>&1; echo pytest rc=$?; tail -2 gpurun_out/pytest_gpu_multi_r02_8gpu.log
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus 8 --steps 50 --warmup 5 > gpurun_out/bench_r02_8gpu_c3_g8.json 2> gpurun_out/bench_r02_8gpu_c3_g8.err; echo bench8 rc=$?; tail -3 gpurun_out/bench_r02_8gpu_c3_g8.err | cut -c1-400
 python - <<'PY'
 import json
