@@ -276,6 +276,7 @@ __device__ __forceinline__ void pb_pdl_sync() {
 // wait returns - the results are then garbage and the host's next check reports the error instead of a hung GPU.
 // [0..7] "rank r's level-K records of epoch e are in place", [8..15] "... accelerations ...", [24] a wait gave up
 constexpr int SHARD_FLAG_EXPORT = 0, SHARD_FLAG_WALK = 8, SHARD_TIMEOUT = 24;
+constexpr size_t SHARD_ACC_STRIDE = 2;  // gravity_shard_scatter leaves the accelerations as 32-byte records (float4 + padding)
 __device__ __forceinline__ void shard_wait_flag(uint32_t* flags, int slot, uint32_t epoch) {
   volatile uint32_t* f = flags + slot;
   unsigned spins = 0;
@@ -380,7 +381,8 @@ cudaError_t gravity_count_interactions(GravityWorkspace& ws, cudaStream_t stream
 // this step used - in *extent_last.
 cudaError_t verlet_update_lean(const double4* cur, double4* prev_inout, const float4* acc32, size_t n, double dt,
                                unsigned long long* extent_out, unsigned long long* extent_zero,
-                               unsigned long long* extent_last, cudaStream_t st, LaunchStats& ls);
+                               unsigned long long* extent_last, cudaStream_t st, LaunchStats& ls,
+                               size_t acc_stride = 1 /* float4 records between consecutive bodies' accelerations */);
 // the same step on every rank of a sharded run: body perm[r][j] takes acc[r][j] for j < n_locals[r] (the gathered
 // blocks of ShardState::xacc, n_cap records each)
 cudaError_t verlet_velocity(const double4* cur, const double4* prev, double4* vel, size_t n, double dt,

@@ -384,7 +384,7 @@ cudaError_t step_sharded(MultiSim& m) {
     LeanSlots s;
     PB_PASS(lean_prepare(c, &s));
     PB_PASS(verlet_update_lean(c->cur.as<double4>(), c->prev.as<double4>(), c->ws.acc.as<float4>(), m.n, m.dt, s.out,
-                               s.zero, s.last, c->stream, c->ls));
+                               s.zero, s.last, c->stream, c->ls, SHARD_ACC_STRIDE));
     lean_done(c);
   }
   m.sharded_steps += 1;

@@ -86,7 +86,8 @@ __global__ void __launch_bounds__(256) verlet_kernel(double4* __restrict__ cur, 
 // kernel also leaves max(|x|,|y|,|z|) of the new positions for the next tree build (transformers.rs:35-40).
 __global__ void __launch_bounds__(256) verlet_lean_kernel(const double4* __restrict__ cur,
                                                           double4* __restrict__ prev_inout,
-                                                          const float4* __restrict__ acc32, size_t n, double dt2,
+                                                          const float4* __restrict__ acc32, size_t acc_stride,
+                                                          size_t n, double dt2,
                                                           unsigned long long* __restrict__ extent_out,
                                                           unsigned long long* __restrict__ extent_zero,
                                                           unsigned long long* __restrict__ extent_last) {
@@ -100,7 +101,7 @@ __global__ void __launch_bounds__(256) verlet_lean_kernel(const double4* __restr
   if (i < n) {
     const double4 x = cur[i];
     const double4 p = prev_inout[i];
-    const float4 a = acc32[i];
+    const float4 a = acc32[i * acc_stride];
     double4 nx;
     nx.x = next_pos(x.x, p.x, double(a.x), dt2);
     nx.y = next_pos(x.y, p.y, double(a.y), dt2);
@@ -269,12 +270,12 @@ cudaError_t rk4_stage(int stage, const double4* e_pos, const double4* e_vel, con
 
 cudaError_t verlet_update_lean(const double4* cur, double4* prev_inout, const float4* acc32, size_t n, double dt,
                                unsigned long long* extent_out, unsigned long long* extent_zero,
-                               unsigned long long* extent_last, cudaStream_t st, LaunchStats& ls) {
+                               unsigned long long* extent_last, cudaStream_t st, LaunchStats& ls, size_t acc_stride) {
   if (n == 0) return cudaSuccess;
   const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
   const double dt2 = dt * dt;  // dt.powi(2)
   PB_LAUNCH(ls, st, "verlet_lean_kernel",
-            pb_launch_pdl(verlet_lean_kernel, dim3(blocks), dim3(256), 0, st, cur, prev_inout, acc32, n, dt2, extent_out, extent_zero, extent_last));
+            pb_launch_pdl(verlet_lean_kernel, dim3(blocks), dim3(256), 0, st, cur, prev_inout, acc32, acc_stride, n, dt2, extent_out, extent_zero, extent_last));
   return cudaGetLastError();
 }
 

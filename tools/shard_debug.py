@@ -27,5 +27,15 @@ for c in range(chunks):
     if rank == 0:
         print(f"chunk {c}: {t / 3:.3f} ms/step sharded {st['sharded_steps']} replicated {st['replicated_steps']} replays {st['replays']} "
               f"cells {st['n_cells']} inter/target {st['interactions'] / n:.1f} bodies/rank {bodies} dbg {dbg}", flush=True)
+# per-kernel device times of EVERY rank (event pairs around each launch), 3 profiled steps
+ms.profile(True)
+ms.run(3)
+rep = {k["kernel"]: round(k["ms"] / 3, 3) for k in ms.profile_report()}
+ms.profile(False)
+allrep = [None] * world
+dist.all_gather_object(allrep, rep)
+if rank == 0:
+    for name in sorted(allrep[0], key=lambda k: -allrep[0][k]):
+        print("%-24s" % name, [r.get(name) for r in allrep], flush=True)
 ms.close()
 dist.destroy_process_group()
