@@ -68,7 +68,11 @@ ALG_BYTES_PER_BODY = {
     "to_soa_kernel": 32 + 24, "bbox_kernel": 24,
     # inside the cell-build row (no separate figure in §8(d)); compulsory bytes of each, for the per-kernel list only
     "unit_kernel": 8 + 32 + 2 + 4 + 1.1, "scan_lookback_kernel": 8, "kids_kernel": 1.5 * 9, "climb_kernel": 0.09 * 188,
+    # sharded step (N > 1): HBM bytes on the rank that runs the kernel; the peer stores travel over NVLink
+    "walk_sharded_kernel": 32 + 20, "shard_scatter_kernel": 20 + 32, "top_export_kernel": 0.2, "top_build_kernel": 0.4,
 }
+# kernels of the sharded step that run over ALL bodies on every rank (the others see one rank's share)
+REPLICATED_KERNELS = {"encode_bucket_kernel", "shard_scatter_kernel", "verlet_lean_kernel", "verlet_kernel", "extent_kernel"}
 STEP_BYTES_PER_BODY = 550  # "Sum ~ 0.55 kB/body-step"
 FLOP_PER_INTERACTION = 19
 NCU_KERNELS = "r02_ncu_c3_kernels.json"  # per-kernel DRAM traffic of the committed ncu --set full capture
@@ -295,7 +299,10 @@ def run_ours(args, w):
     tot_ms = sum(k["ms"] for k in report) or 1.0
     top = max(report, key=lambda k: k["ms"])
     per_launch_ms = top["ms"] / top["launches"]
-    alg_bytes = ALG_BYTES_PER_BODY.get(top["kernel"], 0) * n
+    def bodies_of(kernel):  # bodies one launch of `kernel` on one rank handles
+        return n if (world == 1 or kernel in REPLICATED_KERNELS) else n // world
+
+    alg_bytes = ALG_BYTES_PER_BODY.get(top["kernel"], 0) * bodies_of(top["kernel"])
     achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9 if alg_bytes else None
     traffic = None  # dram read + write bytes per launch, from the committed ncu --set full capture
     try:
@@ -310,10 +317,11 @@ def run_ours(args, w):
                 "peak_source": peak_kind, "avg_launch_ms": per_launch_ms,
                 "share_of_step": top["ms"] / tot_ms,
                 "alg_bytes_per_launch": alg_bytes,
-                "alg_bytes_source": "SURVEY.md §8(d) row for this kernel x bodies (cells_kernel: the whole 76 B/body cell-build row)",
+                "alg_bytes_source": "SURVEY.md §8(d) row for this kernel x the bodies one launch handles on one rank "
+                                    "(cells_kernel: the whole 76 B/body cell-build row)",
                 "kernels": [{"kernel": k["kernel"], "launches_per_step": k["launches"] / prof_steps,
                              "ms_per_step": k["ms"] / prof_steps,
-                             "gbs": (ALG_BYTES_PER_BODY.get(k["kernel"], 0) * n / (k["ms"] / k["launches"] * 1e-3) / 1e9)
+                             "gbs": (ALG_BYTES_PER_BODY.get(k["kernel"], 0) * bodies_of(k["kernel"]) / (k["ms"] / k["launches"] * 1e-3) / 1e9)
                              if k["ms"] > 0 else None}
                             for k in sorted(report, key=lambda k: -k["ms"])]}
 
@@ -338,9 +346,10 @@ def run_ours(args, w):
         "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks,
         # the whole step against HBM: SURVEY §8(d)'s 0.55 kB/body over the measured step time
         "roofline_step": {"bound": "hbm", "achieved": STEP_BYTES_PER_BODY * n / (ms / args.steps * 1e-3) / 1e9,
-                          "peak": hbm_peak, "unit": "GB/s",
-                          "frac": STEP_BYTES_PER_BODY * n / (ms / args.steps * 1e-3) / 1e9 / hbm_peak,
-                          "alg_bytes_per_body": STEP_BYTES_PER_BODY, "n_gpus": world},
+                          "peak": hbm_peak * world, "unit": "GB/s",
+                          "frac": STEP_BYTES_PER_BODY * n / (ms / args.steps * 1e-3) / 1e9 / (hbm_peak * world),
+                          "alg_bytes_per_body": STEP_BYTES_PER_BODY, "n_gpus": world,
+                          "peak_note": "aggregate over the GPUs of the run"},
     }
 
     if rank == 0 and world == 1 and not args.skip_extras:

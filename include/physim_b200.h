@@ -251,9 +251,10 @@ int pb200_integrator_step_fused(void *g, void *transform, const Entity *entities
 
 /* --- device-resident simulation (bench `value`, multi-GPU sharding) ----------------------
  * State lives in HBM across steps: fp64 {x,y,z,m}, previous positions, velocities.
- * rank/world: this process owns bodies [rank*S, min(n, (rank+1)*S)), S = ceil(n/world), as force targets and
- * integrator state; every step needs all positions, exchanged by the caller (torch.distributed
- * all_gather on the pointers below) between pb200_sim_step_local calls. */
+ * rank/world: this handle owns bodies [rank*S, min(n, (rank+1)*S)), S = ceil(n/world), as force targets and
+ * integrator state (sampled timing of a target slice; pb200_sim_step_local + the caller's all-gather on the
+ * pointers below for a step-by-step multi-rank run).  The multi-GPU simulation loop proper is pb200_msim_* below:
+ * it takes its replay decisions collectively, which a per-handle loop with a caller-side exchange cannot. */
 void *pb200_sim_create(int kind, double theta, double e, double dt, int rank, int world);
 void pb200_sim_destroy(void *sim);
 int pb200_sim_upload(void *sim, const Entity *state, size_t n);
@@ -266,12 +267,7 @@ int pb200_sim_generate_cube(void *sim, size_t n, uint64_t seed, double spin, dou
  * use pb200_sim_step_local + an all-gather for a real multi-rank run (this form serves sampled
  * timing of a target slice). */
 int pb200_sim_run(void *sim, size_t steps);
-/* Multi-rank form: `steps` steps of the owned slice with `exchange(ctx)` called after every step on
- * the caller's side (an in-place all-gather of the gather buffer enqueued on the handle's stream).
- * Tree builds run unverified between checkpoints exactly as in pb200_sim_run; a chunk that fails
- * verification is restored and replayed (exchanges included). */
-int pb200_sim_run_sharded(void *sim, size_t steps, void (*exchange)(void *), void *ctx);
-/* Same, bracketed by CUDA events on the handle's stream: *ms = device time of the `steps` steps. */
+/* pb200_sim_run bracketed by CUDA events on the handle's stream: *ms = device time of the `steps` steps. */
 int pb200_sim_run_timed(void *sim, size_t steps, float *ms);
 /* Per-kernel device times: enable (resets the table), run steps, then read a JSON array
  * [{"kernel": name, "launches": k, "ms": total}, ...] into buf. */

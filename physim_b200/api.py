@@ -25,7 +25,6 @@ KINDS = {"astro": 0, "astro2": 1, "simple_astro": 2}
 
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_char_p)  # RustStringAllocFn: char* (*)(const char*)
 ACC_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
-EXCHANGE_FN = C.CFUNCTYPE(None, C.c_void_p)
 
 
 class CMessage(C.Structure):
@@ -128,7 +127,6 @@ def lib():
     L.pb200_sim_upload.argtypes = [vp, vp, sz]
     L.pb200_sim_run.argtypes = [vp, sz]
     L.pb200_sim_step_local.argtypes = [vp]
-    L.pb200_sim_run_sharded.argtypes = [vp, sz, EXCHANGE_FN, vp]
     L.pb200_sim_run_timed.argtypes = [vp, sz, C.POINTER(C.c_float)]
     L.pb200_sim_profile.argtypes = [vp, i32]
     L.pb200_sim_profile_report.argtypes = [vp, C.c_char_p, sz]
@@ -426,13 +424,6 @@ class Sim:
         if lib().pb200_sim_profile_report(self._s, buf, len(buf)) != 0:
             raise Pb200Error("profile report failed")
         return json.loads(buf.value.decode())
-
-    def run_sharded(self, steps, exchange):
-        """`steps` steps of the owned slice; `exchange()` (the caller's in-place all-gather on the
-        sim's stream) runs after every step."""
-        cb = EXCHANGE_FN(lambda _ctx: exchange())
-        if lib().pb200_sim_run_sharded(self._s, int(steps), cb, None) != 0:
-            raise Pb200Error(last_error())
 
     def step_local(self):
         if lib().pb200_sim_step_local(self._s) != 0:

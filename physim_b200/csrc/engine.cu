@@ -1403,22 +1403,6 @@ int pb200_sim_run_csvsink(void* sim, size_t steps, void* sink) {
   return cudaStreamSynchronize(st) == cudaSuccess ? 0 : -1;
 }
 
-int pb200_sim_run_sharded(void* sim, size_t steps, void (*exchange)(void*), void* ctx) {
-  if (!sim || !exchange) return -1;
-  auto& s = *static_cast<SimObj*>(sim);
-  std::lock_guard<std::mutex> lk(s.mu);
-  if (!s.gpu.ready) {
-    set_error("pb200_sim_upload first");
-    return -1;
-  }
-  cudaSetDevice(s.gpu.device);
-  if (sim_run_steps(s, steps, exchange, ctx) != cudaSuccess) {
-    std::fprintf(stderr, "[physim_b200] sharded sim run failed: %s\n", g_error);
-    return -1;
-  }
-  return 0;
-}
-
 int pb200_sim_run_timed(void* sim, size_t steps, float* ms) {
   if (!sim || !ms) return -1;
   auto& s = *static_cast<SimObj*>(sim);
