@@ -175,3 +175,68 @@ def test_quantised_keys_equal_the_chain_outside_the_guard_band(dim):
             assert (~fast).sum() > 0.9 * len(s)      # x is always near a level-12 boundary
         else:
             assert fast.mean() > 0.99
+
+
+# ---- sort_local_kernel: the padding-free bitonic network that sorts a crowded bin ---------------------------
+def _bitonic_all_ascending(items):
+    """Host restatement of the network in sort_local_kernel: every exchange puts the smaller element at the lower
+    index; the first step of each merge pairs i with its mirror in the block; a partner index >= m (the virtual
+    +infinity padding up to the next power of two) never moves anything."""
+    a = list(items)
+    m = len(a)
+    P = 1
+    while P < m:
+        P <<= 1
+
+    def exchange(i, j):
+        if j >= m:
+            return
+        if a[i] > a[j]:
+            a[i], a[j] = a[j], a[i]
+
+    kk = 2
+    while kk <= P:
+        hk = kk >> 1
+        for t in range(P >> 1):
+            base, off = (t & ~(hk - 1)) << 1, t & (hk - 1)
+            exchange(base + off, base + kk - 1 - off)
+        j2 = kk >> 2
+        while j2 > 0:
+            for t in range(P >> 1):
+                i = ((t & ~(j2 - 1)) << 1) | (t & (j2 - 1))
+                exchange(i, i + j2)
+            j2 >>= 1
+        kk <<= 1
+    return a
+
+
+def test_padding_free_bitonic_network_sorts_every_length():
+    rng = np.random.default_rng(11)
+    for m in list(range(1, 70)) + [100, 127, 128, 129, 513, 1000, 1025]:
+        keys = rng.integers(0, max(2, m // 3), m)          # many equal keys: ties go by the index
+        items = [(int(keys[i]), int(i)) for i in rng.permutation(m)]
+        assert _bitonic_all_ascending(items) == sorted(items), m
+
+
+# ---- the walk's link word: skip | level << 32 in the fourth double of a centre record --------------------------
+def test_link_word_and_half_width_from_level():
+    """pack_link / link_skip / link_level, and half_width_at: extent / 2^level taken from the exponent field equals
+    the value `half *= 0.5` reaches after `level` steps (what cells_kernel's replay holds), for every level a tree
+    can have, as long as the result is a normal double."""
+    rng = np.random.default_rng(3)
+    for _ in range(2000):
+        skip = int(rng.integers(0, 2**32))
+        level = int(rng.integers(0, 256))
+        word = np.array([(level << 32) | skip], dtype=np.uint64).view(np.float64)[0]   # pack_link
+        bits = int(np.array([word]).view(np.uint64)[0])
+        assert bits & 0xFFFFFFFF == skip and (bits >> 32) & 0xFF == level
+    for ext in list(rng.uniform(1e-3, 1e3, 200)) + [1.0, 0.7368421052631579, 5e-300, 1e300]:
+        ext = np.float64(ext)
+        half = ext
+        for level in range(0, 80):
+            hi = int(np.array([ext]).view(np.uint64)[0] >> np.uint64(32))
+            if ((hi >> 20) & 0x7FF) > level + 1:               # the exponent trick's own condition
+                tricked = (np.array([ext]).view(np.uint64) - np.uint64(level << 52)).view(np.float64)[0]
+                assert tricked == half, (ext, level)
+            assert np.ldexp(ext, -level) == half or half < 2.3e-308   # the fall-back (exact while normal)
+            half = half * np.float64(0.5)
