@@ -195,6 +195,7 @@ struct KernelTime {
   double ms;
 };
 struct LaunchStats {
+  static inline thread_local const char* current = "";  // the kernel being launched (read by pb_launch_pdl)
   uint64_t launches = 0;
   bool profiling = false;
   struct Pending {
@@ -216,6 +217,7 @@ struct LaunchStats {
   }
   void begin(const char* name, cudaStream_t st) {
     ++launches;
+    current = name;
     if (!profiling) return;
     Pending p{name, get_event(), get_event()};
     cudaEventRecord(p.e0, st);
@@ -308,7 +310,9 @@ inline cudaError_t pb_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pb_pdl_enabled() ? 1 : 0;
+  // PB200_PDL_OFF=kids_kernel,climb_kernel: plain launches for the named kernels only (tuning runs)
+  static const char* off = std::getenv("PB200_PDL_OFF");
+  cfg.numAttrs = (pb_pdl_enabled() && !(off && *LaunchStats::current && std::strstr(off, LaunchStats::current))) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
 }
 

@@ -2985,11 +2985,18 @@ cudaError_t tree_build(GravityWorkspace& ws, const ShardBuild* sh, cudaStream_t 
                    max_shared_plus1 + 2, uint32_t(TopTree<DIM>::K)};
   const NsvTables tv{ws.nsv1.as<uint8_t>(), ws.nsv1.as<uint8_t>() + n_pad, n_pad, ws.nsv2.as<uint8_t>(), b_pad, nsv3, n, nblocks, nsuper};
   const TopSlots slots = sh ? sh->slots : TopSlots{nullptr, 0};
-  PB_LAUNCH(ls, st, "cells_kernel",
-            (pb_launch_pdl(cells_kernel<DIM, 4>, dim3(nb), dim3(256), 0, st, ws.sorted_key, ws.spos64.as<double4>(), ws.perm,
-                                                      ws.ab.as<uchar2>(), ws.cell_start.as<uint32_t>(), nref,
-                                                      ws.extent_cur, max_shared_plus1,
-                                                      ws.sticky.as<unsigned>(), tv, cells, slots)));
+  // Resident CTAs per SM the compiler makes room for: 5 (48 registers, no spills; 62 % of the warp slots) beats 4
+  // (64 registers) by 2.5 us at c3 and 15 us at 4.2 M bodies - the kernel waits on dependent loads and on divergent
+  // paths, more warps hide them; 6 (40 registers) spills and loses 6 us.  PB200_CELLS_BLOCKS=4: the earlier build.
+  static const int cells_blocks = std::getenv("PB200_CELLS_BLOCKS") ? std::atoi(std::getenv("PB200_CELLS_BLOCKS")) : 5;  // (tuning runs)
+#define PB_CELLS_LAUNCH(MB)                                                                                          \
+  PB_LAUNCH(ls, st, "cells_kernel",                                                                                  \
+            (pb_launch_pdl(cells_kernel<DIM, MB>, dim3(nb), dim3(256), 0, st, ws.sorted_key, ws.spos64.as<double4>(), \
+                           ws.perm, ws.ab.as<uchar2>(), ws.cell_start.as<uint32_t>(), nref, ws.extent_cur,           \
+                           max_shared_plus1, ws.sticky.as<unsigned>(), tv, cells, slots)))
+  if (cells_blocks == 4) PB_CELLS_LAUNCH(4);
+  else PB_CELLS_LAUNCH(5);
+#undef PB_CELLS_LAUNCH
   ws.parents_filled = false;
   {
     PB_PASS(ws.c_kids.ensure(cap * (size_t(4) << DIM)));
