@@ -1215,7 +1215,10 @@ struct ComSum {
   }
 };
 
-constexpr uint32_t SMALL_CELL = 16;
+// 24 instead of 16 (r02, 1 x B200): cells_kernel + 5 us (longer divergent sums), kids_kernel - 2 us, climb_kernel - 5 us
+// (one level less of its store / atomic / load chain): c3 244.1 -> 241.5 us per step, octree 247.8 -> 244.9.
+// The sums differ from the 16-body build's within fp64 rounding (another order of additions), not bit for bit.
+constexpr uint32_t SMALL_CELL = 24;
 constexpr unsigned char NOT_HEAD = 255;  // ab[j].x of a body merged into the unit before it
 
 // {x, y, z, m} of the leaf made of sorted bodies [s, e): masses add, the member inserted last
